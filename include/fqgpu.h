@@ -1,0 +1,183 @@
+/*
+ * fqgpu.h -- C ABI of libfqgpu: the B200 (sm_100a) FASTQ scanning hot path behind
+ * `sc fq-count` and the quality-range scan of `sc fq-meta` (danielecook/seq-collection).
+ *
+ * The reference has no FFI for this path: the "interface" is two Nim procs,
+ *   fq_count*(fastq, basename, absolute)            src/fq_count.nim:14  (called at sc.nim:116)
+ *   qual_min_max*(quality_scores, prev_min, prev_max) src/fq_meta.nim:97 (called at src/fq_meta.nim:246)
+ * whose bodies iterate text lines on one CPU core.  This header is what a Nim `importc` shim binds
+ * (see INTEGRATION.md and seq-collection_b200/nim/fqgpu.nim): the loop body of
+ * src/fq_count.nim:38-45 and the fold of src/fq_meta.nim:245-246 become
+ *   "fill pinned chunk -> fqgpu_submit -> ... -> fqgpu_finish -> read integers",
+ * and the unchanged output code (src/fq_count.nim:47-52, src/fq_meta.nim:255-278) runs on the
+ * integers returned in fqgpu_stats.  Only integers cross the boundary; the single float
+ * (gc_content, src/fq_count.nim:48) is derived by the caller exactly as the reference does.
+ *
+ * Plain C99: pointers and sizes only, no exceptions, no torch types.  All functions returning int
+ * return FQGPU_OK (0) or a negative FQGPU_E* code; the message is available from fqgpu_last_error().
+ * The library never writes to stdout and never calls exit().  There is NO CPU fallback: if no CUDA
+ * device is usable every entry point that computes fails with FQGPU_ECUDA.
+ */
+#ifndef FQGPU_H
+#define FQGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FQGPU_ABI_VERSION 1
+
+/* Per-position tables hold positions 0..FQGPU_POS_BINS-1; index FQGPU_POS_BINS is the overflow bin
+ * (all positions >= FQGPU_POS_BINS).  Exact length histograms use the same binning. */
+#define FQGPU_POS_BINS 512
+#define FQGPU_LEN_LOG2_BINS 64
+
+enum {
+  FQGPU_OK = 0,
+  FQGPU_ECUDA = -1, /* CUDA runtime / no device / kernel failure              */
+  FQGPU_ENCCL = -2, /* collective failure (multi-GPU)                         */
+  FQGPU_EIO = -3,   /* file could not be opened / read  (maps to exit code 2, src/fq_count.nim:36) */
+  FQGPU_EARG = -4,  /* bad argument / call sequence                           */
+  FQGPU_ENOMEM = -5
+};
+
+/* fqgpu_config.flags */
+enum {
+  FQGPU_F_CORE_ONLY = 1u << 0 /* compute only what `sc fq-count` prints (reads, bases, G/C/N):
+                                 base_counts/len tables for sequence lines stay exact, all
+                                 quality-line outputs are left zero.  Default: full statistics. */
+};
+
+typedef struct fqgpu_ctx fqgpu_ctx;
+
+typedef struct {
+  int device;            /* CUDA ordinal; -1 = current device                                   */
+  size_t chunk_bytes;    /* pinned staging chunk size; 0 = default (64 MiB)                     */
+  int n_buffers;         /* staging ring depth; 0 = default (3)                                 */
+  uint64_t meta_records; /* fq-meta sample_n: quality range is folded over the first
+                            meta_records records (sc.nim:70 default 100); 0 = skip the scan     */
+  uint32_t flags;        /* FQGPU_F_*                                                            */
+  uint32_t reserved;
+} fqgpu_config;
+
+/* meta_status values */
+enum {
+  FQGPU_META_OK = 0,
+  FQGPU_META_EMPTY_QUAL = 1 /* the reference would raise here: an empty quality line reached
+                               qual_min_max with no valid history (min() of an empty seq,
+                               src/fq_meta.nim:102) */
+};
+
+/* Everything is an integer.  Line classes follow src/fq_count.nim:39-42: with the 1-based line
+ * counter i, i mod 4 == 1 is a header line (reads++), i mod 4 == 2 a sequence line; we call
+ * i mod 4 == 0 the quality line (src/fq_meta.nim:245 uses the 0-based i %% 4 == 3).  No '@'/'+'
+ * validation is performed, exactly like the reference.  "Line" = Nim streams.lines semantics:
+ * split at '\n', one '\r' directly before the '\n' is dropped, a trailing unterminated non-empty
+ * line counts, blank lines count. */
+typedef struct {
+  uint64_t bytes;     /* bytes scanned                                                          */
+  uint64_t lines;     /* lines yielded (== final value of i, src/fq_count.nim:39)               */
+  uint64_t reads;     /* n_reads   src/fq_count.nim:40-41                                       */
+  uint64_t bases;     /* total_len src/fq_count.nim:45                                          */
+  uint64_t gc_bases;  /* gc_cnt    src/fq_count.nim:43  (uppercase 'G' + 'C' only)              */
+  uint64_t n_bases;   /* n_cnt     src/fq_count.nim:44  (uppercase 'N' only)                    */
+  uint64_t seq_lines; /* number of sequence lines (including empty ones)                        */
+  uint64_t qual_lines;
+  /* --- superset named by the north star; no reference oracle, defined by oracle/fq_oracle.c --- */
+  uint64_t base_counts[256]; /* byte histogram over sequence lines (A/C/G/T/N/... fall out)     */
+  uint64_t qual_counts[256]; /* byte histogram over quality lines                               */
+  uint64_t seq_len_min, seq_len_max;   /* over sequence lines; min = UINT64_MAX, max = 0 if none */
+  uint64_t qual_len_min, qual_len_max; /* over quality lines                                     */
+  uint64_t seq_len_hist[FQGPU_POS_BINS + 1];  /* exact length histogram, last bin = len >= POS_BINS */
+  uint64_t qual_len_hist[FQGPU_POS_BINS + 1];
+  uint64_t seq_len_log2[FQGPU_LEN_LOG2_BINS]; /* bin 0: len 0; bin k: 2^(k-1) <= len < 2^k      */
+  uint64_t qual_pos_sum[FQGPU_POS_BINS + 1];  /* sum of raw quality bytes at 0-based position p  */
+  uint64_t qual_pos_cnt[FQGPU_POS_BINS + 1];  /* quality lines that have a byte at position p;
+                                                 last bin = number of bytes at p >= POS_BINS     */
+  /* --- fq-meta quality-range scan, src/fq_meta.nim:207-208,226-248,277 --- */
+  int64_t meta_qual_min;  /* qual_min after the loop (ord-33 units, -1 = none/invalid)          */
+  int64_t meta_qual_max;  /* qual_max                                                            */
+  uint64_t meta_lines;    /* i after the loop: min(4*meta_records, lines); n_lines = meta_lines/4 */
+  uint32_t meta_status;   /* FQGPU_META_*                                                        */
+  uint32_t reserved;
+} fqgpu_stats;
+
+/* Version / capability probes (no GPU needed). */
+int fqgpu_abi_version(void);
+size_t fqgpu_stats_size(void);
+const char* fqgpu_build_info(void);
+int fqgpu_device_count(void); /* CUDA devices visible, <= 0 if none */
+
+/* Context = one GPU + its staging ring + its device-resident counters and carry state. */
+int fqgpu_create(fqgpu_ctx** out, const fqgpu_config* cfg); /* cfg NULL or zeroed = defaults */
+void fqgpu_destroy(fqgpu_ctx* ctx);
+const char* fqgpu_last_error(const fqgpu_ctx* ctx); /* ctx may be NULL: last create() failure */
+
+/* Streaming interface (replaces the `for line in lines(stream)` loop, src/fq_count.nim:38).
+ * acquire: next free PINNED host chunk (blocks while every chunk is in flight); the host reads
+ *          file bytes or gzread()s (gzip_stream.nim:16-17) straight into it.
+ * submit:  async H2D + scan kernel on the context's stream; a chunk may end anywhere (mid-line,
+ *          between '\r' and '\n'); the carry is resolved on the device.
+ * finish:  flush the carry (trailing unterminated line), reduce the per-CTA partial counters,
+ *          copy the result (~20 KB) back.  reset: ready for the next file. */
+void* fqgpu_acquire(fqgpu_ctx* ctx, size_t* capacity);
+int fqgpu_submit(fqgpu_ctx* ctx, void* chunk, size_t nbytes);
+int fqgpu_finish(fqgpu_ctx* ctx, fqgpu_stats* out);
+int fqgpu_reset(fqgpu_ctx* ctx);
+
+/* Whole-buffer conveniences on top of the streaming interface. */
+int fqgpu_count_host(fqgpu_ctx* ctx, const void* buf, size_t nbytes, fqgpu_stats* out); /* pageable host memory */
+int fqgpu_count_file(fqgpu_ctx* ctx, const char* path, fqgpu_stats* out); /* plain or .gz (zlib inflate on host) */
+
+/* HBM-resident interface (kernel-only measurements; data already on the context's device).
+ * scan_device may be called repeatedly: each call continues the same stream of bytes (carry
+ * state is kept on the device), exactly as if the buffers were concatenated. */
+int fqgpu_scan_device(fqgpu_ctx* ctx, const void* dptr, size_t nbytes);
+int fqgpu_count_device(fqgpu_ctx* ctx, const void* dptr, size_t nbytes, fqgpu_stats* out); /* reset+scan+finish */
+
+/* Multi-GPU byte-range sharding: rank g of `world` scans bytes [g*N/world,(g+1)*N/world)
+ * of ONE logical stream.  A rank > 0 does not know the line phase of its first byte, so it
+ * resynchronises on the first true record start ('@' line whose line+2 starts with '+'), scans with
+ * that guessed phase, keeps the statistics of its head fragment (bytes before its first newline)
+ * and of its open tail detached, and exports everything as one block of uint64 words:
+ *   fqgpu_shard_begin():   reset the context as shard `rank` of `world`
+ *   [fqgpu_scan_device / fqgpu_submit ... as usual]
+ *   fqgpu_shard_export():  write this rank's block into slot `rank` of a device buffer of
+ *                          world*fqgpu_shard_block_words() uint64 that the caller zeroed
+ *   [caller SUM-all-reduces the buffer: ncclAllReduce / torch.distributed -- the ONE collective]
+ *   fqgpu_shard_combine(): every rank folds the world blocks into the final stats: stitches
+ *                          tail(g-1)+head(g) lines, shifts head per-position sums, verifies every
+ *                          guessed phase against the exact line counts.  Returns FQGPU_OK, or
+ *                          FQGPU_ERETRY when some rank guessed wrong (malformed input): then each
+ *                          rank calls fqgpu_shard_rescan(), scans its range again (now with the
+ *                          exact carry taken from the blocks), and export/all-reduce/combine repeat. */
+#define FQGPU_ERETRY 1
+size_t fqgpu_shard_block_words(void);
+int fqgpu_shard_begin(fqgpu_ctx* ctx, int rank, int world);
+int fqgpu_shard_export(fqgpu_ctx* ctx, uint64_t* d_blocks);
+int fqgpu_shard_combine(fqgpu_ctx* ctx, const uint64_t* d_blocks, fqgpu_stats* out);
+int fqgpu_shard_rescan(fqgpu_ctx* ctx, const uint64_t* d_blocks);
+
+/* Timing of the most recent scan launches on this context (CUDA events on the context's stream):
+ * kernel_ms = sum of scan-kernel durations since the last reset, launches = how many kernels. */
+int fqgpu_last_timing(fqgpu_ctx* ctx, double* kernel_ms, uint64_t* launches);
+
+/* Raw CUDA stream of the context (cudaStream_t as void*), for callers that want to order their
+ * own work (e.g. a collective) after the scan without a host sync. */
+void* fqgpu_stream(fqgpu_ctx* ctx);
+
+/* Synthetic FASTQ generators, counter-based so any byte range can be
+ * produced independently on any GPU; used by bench.py and the parity tests.  `first_record` lets a
+ * rank generate its own shard.  Both write whole records only and return the bytes written. */
+int fqgpu_synth_illumina(fqgpu_ctx* ctx, void* dptr, size_t capacity, uint64_t first_record,
+                         uint64_t n_records, uint64_t seed, size_t* bytes_written);
+int fqgpu_synth_ont(fqgpu_ctx* ctx, void* dptr, size_t capacity, uint64_t first_record,
+                    uint64_t n_records, uint64_t seed, size_t* bytes_written);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FQGPU_H */
