@@ -176,6 +176,9 @@ int fqgpu_synth_illumina(fqgpu_ctx* ctx, void* dptr, size_t capacity, uint64_t f
                          uint64_t n_records, uint64_t seed, size_t* bytes_written);
 int fqgpu_synth_ont(fqgpu_ctx* ctx, void* dptr, size_t capacity, uint64_t first_record,
                     uint64_t n_records, uint64_t seed, size_t* bytes_written);
+/* Arbitrary byte range [first_byte, first_byte+nbytes) of the Illumina stream (a shard may start
+ * mid-record). */
+int fqgpu_synth_illumina_bytes(fqgpu_ctx* ctx, void* dptr, uint64_t first_byte, uint64_t nbytes, uint64_t seed);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,366 @@
+"""seq-collection_b200 -- B200-native FASTQ scanning behind `sc fq-count` / `sc fq-meta`.
+
+Python binding (ctypes) over the C ABI of libfqgpu.so (include/fqgpu.h).  The shared library is the
+product; this module only mirrors the reference's two procs for this path:
+
+    fq_count(fastq, basename, absolute)             /root/reference/src/fq_count.nim:14
+    fq_meta_quality(fastq, sample_n, ...)           /root/reference/src/fq_meta.nim:197 (quality part)
+
+There is no CPU fallback: if libfqgpu.so is missing or no CUDA device is usable, every compute call
+raises FqGpuError.  (The package directory name has a hyphen, so import it with
+`importlib.import_module("seq-collection_b200")` or via the `seq_collection_b200` alias module at
+the repo root.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libfqgpu.so")
+POS_BINS = 512
+LEN_LOG2_BINS = 64
+
+OK, ECUDA, ENCCL, EIO, EARG, ENOMEM = 0, -1, -2, -3, -4, -5
+ERETRY = 1
+
+
+class FqGpuError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libfqgpu error {code}: {msg}")
+        self.code = code
+        self.msg = msg
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("device", C.c_int),
+        ("chunk_bytes", C.c_size_t),
+        ("n_buffers", C.c_int),
+        ("meta_records", C.c_uint64),
+        ("flags", C.c_uint32),
+        ("reserved", C.c_uint32),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("bytes", C.c_uint64),
+        ("lines", C.c_uint64),
+        ("reads", C.c_uint64),
+        ("bases", C.c_uint64),
+        ("gc_bases", C.c_uint64),
+        ("n_bases", C.c_uint64),
+        ("seq_lines", C.c_uint64),
+        ("qual_lines", C.c_uint64),
+        ("base_counts", C.c_uint64 * 256),
+        ("qual_counts", C.c_uint64 * 256),
+        ("seq_len_min", C.c_uint64),
+        ("seq_len_max", C.c_uint64),
+        ("qual_len_min", C.c_uint64),
+        ("qual_len_max", C.c_uint64),
+        ("seq_len_hist", C.c_uint64 * (POS_BINS + 1)),
+        ("qual_len_hist", C.c_uint64 * (POS_BINS + 1)),
+        ("seq_len_log2", C.c_uint64 * LEN_LOG2_BINS),
+        ("qual_pos_sum", C.c_uint64 * (POS_BINS + 1)),
+        ("qual_pos_cnt", C.c_uint64 * (POS_BINS + 1)),
+        ("meta_qual_min", C.c_int64),
+        ("meta_qual_max", C.c_int64),
+        ("meta_lines", C.c_uint64),
+        ("meta_status", C.c_uint32),
+        ("reserved", C.c_uint32),
+    ]
+
+    SCALARS = ("bytes", "lines", "reads", "bases", "gc_bases", "n_bases", "seq_lines", "qual_lines",
+               "seq_len_min", "seq_len_max", "qual_len_min", "qual_len_max",
+               "meta_qual_min", "meta_qual_max", "meta_lines", "meta_status")
+    ARRAYS = ("base_counts", "qual_counts", "seq_len_hist", "qual_len_hist", "seq_len_log2",
+              "qual_pos_sum", "qual_pos_cnt")
+
+    def to_dict(self) -> dict:
+        d = {k: int(getattr(self, k)) for k in self.SCALARS}
+        for k in self.ARRAYS:
+            d[k] = [int(v) for v in getattr(self, k)]
+        return d
+
+
+_lib = None
+
+
+def load_library(path: str | None = None):
+    """dlopen libfqgpu.so and declare the C ABI.  Raises if the library has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise FqGpuError(ECUDA, f"{p} not found: build it with `python seq-collection_b200/build.py` "
+                                "(there is no CPU fallback)")
+    L = C.CDLL(p, mode=C.RTLD_GLOBAL)
+    vp, sz, u64, i32 = C.c_void_p, C.c_size_t, C.c_uint64, C.c_int
+    sig = {
+        "fqgpu_abi_version": (i32, []),
+        "fqgpu_stats_size": (sz, []),
+        "fqgpu_build_info": (C.c_char_p, []),
+        "fqgpu_device_count": (i32, []),
+        "fqgpu_create": (i32, [C.POINTER(vp), C.POINTER(Config)]),
+        "fqgpu_destroy": (None, [vp]),
+        "fqgpu_last_error": (C.c_char_p, [vp]),
+        "fqgpu_acquire": (vp, [vp, C.POINTER(sz)]),
+        "fqgpu_submit": (i32, [vp, vp, sz]),
+        "fqgpu_finish": (i32, [vp, C.POINTER(Stats)]),
+        "fqgpu_reset": (i32, [vp]),
+        "fqgpu_count_host": (i32, [vp, vp, sz, C.POINTER(Stats)]),
+        "fqgpu_count_file": (i32, [vp, C.c_char_p, C.POINTER(Stats)]),
+        "fqgpu_scan_device": (i32, [vp, vp, sz]),
+        "fqgpu_count_device": (i32, [vp, vp, sz, C.POINTER(Stats)]),
+        "fqgpu_shard_block_words": (sz, []),
+        "fqgpu_shard_begin": (i32, [vp, i32, i32]),
+        "fqgpu_shard_export": (i32, [vp, vp]),
+        "fqgpu_shard_combine": (i32, [vp, vp, C.POINTER(Stats)]),
+        "fqgpu_shard_rescan": (i32, [vp, vp]),
+        "fqgpu_last_timing": (i32, [vp, C.POINTER(C.c_double), C.POINTER(u64)]),
+        "fqgpu_stream": (vp, [vp]),
+        "fqgpu_synth_illumina": (i32, [vp, vp, sz, u64, u64, u64, C.POINTER(sz)]),
+        "fqgpu_synth_illumina_bytes": (i32, [vp, vp, u64, u64, u64]),
+        "fqgpu_synth_ont": (i32, [vp, vp, sz, u64, u64, u64, C.POINTER(sz)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    if L.fqgpu_stats_size() != C.sizeof(Stats):
+        raise FqGpuError(EARG, "Stats mirror out of sync with include/fqgpu.h")
+    if path is None:
+        _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "fqgpu_abi_version", "fqgpu_stats_size", "fqgpu_build_info", "fqgpu_device_count", "fqgpu_create",
+    "fqgpu_destroy", "fqgpu_last_error", "fqgpu_acquire", "fqgpu_submit", "fqgpu_finish", "fqgpu_reset",
+    "fqgpu_count_host", "fqgpu_count_file", "fqgpu_scan_device", "fqgpu_count_device",
+    "fqgpu_shard_block_words", "fqgpu_shard_begin", "fqgpu_shard_export", "fqgpu_shard_combine",
+    "fqgpu_shard_rescan", "fqgpu_last_timing", "fqgpu_stream", "fqgpu_synth_illumina",
+    "fqgpu_synth_illumina_bytes", "fqgpu_synth_ont",
+]
+
+
+class FqGpu:
+    """One context = one GPU + its staging ring, device counters and stream carry (fqgpu_ctx)."""
+
+    def __init__(self, device: int = -1, chunk_bytes: int = 0, n_buffers: int = 0, meta_records: int = 0,
+                 flags: int = 0):
+        self.lib = load_library()
+        self._ctx = C.c_void_p()
+        cfg = Config(device, chunk_bytes, n_buffers, meta_records, flags, 0)
+        rc = self.lib.fqgpu_create(C.byref(self._ctx), C.byref(cfg))
+        if rc != OK:
+            msg = self.lib.fqgpu_last_error(None).decode()
+            self._ctx = C.c_void_p()
+            raise FqGpuError(rc, msg)
+
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self.lib.fqgpu_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc < 0:
+            raise FqGpuError(rc, self.lib.fqgpu_last_error(self._ctx).decode())
+        return rc
+
+    # -- streaming -------------------------------------------------------------------------
+    def reset(self):
+        self._check(self.lib.fqgpu_reset(self._ctx))
+
+    def acquire(self):
+        cap = C.c_size_t()
+        p = self.lib.fqgpu_acquire(self._ctx, C.byref(cap))
+        if not p:
+            raise FqGpuError(ECUDA, self.lib.fqgpu_last_error(self._ctx).decode())
+        return p, cap.value
+
+    def submit(self, chunk_ptr: int, nbytes: int):
+        self._check(self.lib.fqgpu_submit(self._ctx, chunk_ptr, nbytes))
+
+    def submit_bytes(self, data: bytes):
+        """Feed `data` through the pinned ring (splits at the chunk capacity)."""
+        off = 0
+        n = len(data)
+        while off < n:
+            p, cap = self.acquire()
+            k = min(cap, n - off)
+            C.memmove(p, data[off:off + k], k)
+            self.submit(p, k)
+            off += k
+
+    def finish(self) -> Stats:
+        st = Stats()
+        self._check(self.lib.fqgpu_finish(self._ctx, C.byref(st)))
+        return st
+
+    # -- whole buffers -----------------------------------------------------------------------
+    def count_bytes(self, data) -> Stats:
+        st = Stats()
+        if isinstance(data, (bytes, bytearray)):
+            buf = (C.c_char * max(1, len(data))).from_buffer_copy(bytes(data) or b"\0")
+            self._check(self.lib.fqgpu_count_host(self._ctx, C.addressof(buf), len(data), C.byref(st)))
+        else:  # numpy uint8 array
+            self._check(self.lib.fqgpu_count_host(self._ctx, data.ctypes.data, data.size, C.byref(st)))
+        return st
+
+    def count_host_ptr(self, ptr: int, nbytes: int) -> Stats:
+        st = Stats()
+        self._check(self.lib.fqgpu_count_host(self._ctx, ptr, nbytes, C.byref(st)))
+        return st
+
+    def count_file(self, path: str) -> Stats:
+        st = Stats()
+        self._check(self.lib.fqgpu_count_file(self._ctx, os.fsencode(path), C.byref(st)))
+        return st
+
+    # -- HBM resident --------------------------------------------------------------------------
+    def scan_device(self, dptr: int, nbytes: int):
+        self._check(self.lib.fqgpu_scan_device(self._ctx, dptr, nbytes))
+
+    def count_device(self, dptr: int, nbytes: int) -> Stats:
+        st = Stats()
+        self._check(self.lib.fqgpu_count_device(self._ctx, dptr, nbytes, C.byref(st)))
+        return st
+
+    def last_timing(self):
+        ms = C.c_double()
+        n = C.c_uint64()
+        self._check(self.lib.fqgpu_last_timing(self._ctx, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    @property
+    def stream(self) -> int:
+        return self.lib.fqgpu_stream(self._ctx) or 0
+
+    # -- multi-GPU shards ----------------------------------------------------------------------
+    def shard_block_words(self) -> int:
+        return self.lib.fqgpu_shard_block_words()
+
+    def shard_begin(self, rank: int, world: int):
+        self._check(self.lib.fqgpu_shard_begin(self._ctx, rank, world))
+
+    def shard_export(self, d_blocks: int):
+        self._check(self.lib.fqgpu_shard_export(self._ctx, d_blocks))
+
+    def shard_combine(self, d_blocks: int):
+        st = Stats()
+        rc = self._check(self.lib.fqgpu_shard_combine(self._ctx, d_blocks, C.byref(st)))
+        return rc, st
+
+    def shard_rescan(self, d_blocks: int):
+        self._check(self.lib.fqgpu_shard_rescan(self._ctx, d_blocks))
+
+    # -- synthetic data --------------------------------------------------------------------------
+    def synth_illumina(self, dptr: int, capacity: int, first_record: int, n_records: int, seed: int) -> int:
+        w = C.c_size_t()
+        self._check(self.lib.fqgpu_synth_illumina(self._ctx, dptr, capacity, first_record, n_records, seed, C.byref(w)))
+        return w.value
+
+    def synth_illumina_bytes(self, dptr: int, first_byte: int, nbytes: int, seed: int):
+        self._check(self.lib.fqgpu_synth_illumina_bytes(self._ctx, dptr, first_byte, nbytes, seed))
+
+    def synth_ont(self, dptr: int, capacity: int, first_record: int, n_records: int, seed: int) -> int:
+        w = C.c_size_t()
+        self._check(self.lib.fqgpu_synth_ont(self._ctx, dptr, capacity, first_record, n_records, seed, C.byref(w)))
+        return w.value
+
+
+# ------------------------------------------------------------------------------------------------
+# Host-side mirror of the reference's output code for this path (unchanged semantics).
+# ------------------------------------------------------------------------------------------------
+FQ_COUNT_HEADER = "\t".join(["reads", "gc_content", "gc_bases", "n_bases", "bases"])  # src/fq_count.nim:7-11
+
+
+def nim_float_str(v: float) -> str:
+    """Nim 1.0.6 `$`(float): "%.16g", ".0" appended when the text has no '.', ',' or letter."""
+    if math.isnan(v):
+        return "nan"
+    if math.isinf(v):
+        return "inf" if v > 0 else "-inf"
+    s = "%.16g" % v
+    if not any(ch == "." or ch.isalpha() for ch in s):
+        s += ".0"
+    return s
+
+
+def output_header(header: str, basename: bool, absolute: bool) -> str:
+    """src/utils/helpers.nim:200-208"""
+    cols = [header, "basename" if basename else "", "absolute" if absolute else ""]
+    return "\t".join(c for c in cols if c)
+
+
+def output_w_fnames(row: str, path: str, basename: bool, absolute: bool) -> str:
+    """src/utils/helpers.nim:210-224"""
+    b = os.path.basename(path.rstrip("/")) if basename else ""
+    a = ""
+    if absolute:
+        a = os.path.abspath(os.readlink(path)) if os.path.islink(path) else os.path.abspath(path)
+    return "\t".join(c for c in [row, b, a] if c)
+
+
+def fq_count_row(st) -> str:
+    """src/fq_count.nim:47-51 from the integers returned by the GPU."""
+    gc, n, total = int(st.gc_bases), int(st.n_bases), int(st.bases)
+    den = float(total - n)
+    if den == 0.0:
+        gc_content = float("nan") if gc == 0 else float("inf")
+    else:
+        gc_content = float(gc) / den
+    return "\t".join([str(int(st.reads)), nim_float_str(gc_content), str(gc), str(n), str(total)])
+
+
+def fq_count(fastq: str, basename: bool = False, absolute: bool = False, ctx: FqGpu | None = None) -> str:
+    """Mirror of fq_count* (src/fq_count.nim:14-53): returns the line the reference echoes.
+    Raises FqGpuError(EIO) where the reference does quit_error("Unable to open file", 2)."""
+    own = ctx is None
+    ctx = ctx or FqGpu()
+    try:
+        st = ctx.count_file(fastq)
+    finally:
+        if own:
+            ctx.close()
+    return output_w_fnames(fq_count_row(st), fastq, basename, absolute)
+
+
+# src/fq_meta.nim:35-39 (bounds reproduced as written)
+FASTQ_TYPES = [
+    ("Sanger", "Phred+33", 0, 40),
+    ("Solexa", "Solexa+64", 59, 104),
+    ("Illumina 1.3+", "Phred+64", 64, 104),
+    ("Illumina 1.5+", "Phred+64", 64, 104),
+    ("Illumina 1.8+", "Phred+33", 0, 42),
+]
+
+
+def fq_meta_quality_fields(st) -> list:
+    """qual_format, qual_phred, qual_multiple, min_qual, max_qual, n_lines (src/fq_meta.nim:255-277)."""
+    qmin, qmax = int(st.meta_qual_min), int(st.meta_qual_max)
+    hits = [t for t in FASTQ_TYPES if qmin >= t[2] and qmax <= t[3]]
+    phreds = []
+    for t in hits:
+        if t[1] not in phreds:
+            phreds.append(t[1])
+    return [";".join(t[0] for t in hits), ";".join(phreds), "true" if len(hits) > 1 else "false",
+            str(qmin) if qmin >= 0 else "", str(qmax) if qmax >= 0 else "", str(int(st.meta_lines) // 4)]
+
+
+def fq_meta_quality(fastq: str, sample_n: int = 20) -> list:
+    """Quality part of fq_meta* (src/fq_meta.nim:197, default sample_n = 20; the CLI passes 100)."""
+    with FqGpu(meta_records=sample_n) as ctx:
+        return fq_meta_quality_fields(ctx.count_file(fastq))

@@ -1,0 +1,471 @@
+// fqgpu_api.cu -- host side of libfqgpu: contexts, the pinned staging ring, launch orchestration
+// and the assembly of fqgpu_stats from the reduced counter block + stream carry.
+// The C ABI is declared in include/fqgpu.h (each entry point cites the reference code it replaces).
+#include <cuda_runtime.h>
+#include <fcntl.h>
+#include <stdio.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <string>
+#include <vector>
+
+#include "fq_layout.h"
+
+namespace fq {
+typedef unsigned long long u64;
+size_t scan_smem_bytes();
+int scan_tile_bytes();
+int scan_threads();
+cudaError_t scan_configure();
+cudaError_t launch_reset(u64* partials, int nblocks, Carry* carry, cudaStream_t st);
+cudaError_t launch_scan(const void* ptr, size_t nbytes, TileState* ts, LaunchInfo* info, Carry* carry,
+                        u64* partials, int grid, u64 meta_records, cudaStream_t st);
+cudaError_t launch_reduce(const u64* partials, int nblocks, u64* out, cudaStream_t st);
+cudaError_t launch_synth_illumina(void* dptr, u64 first_byte, u64 nbytes, u64 seed, cudaStream_t st);
+cudaError_t synth_ont(void* dptr, size_t capacity, u64 first_record, u64 n_records, u64 seed, size_t* bytes_written,
+                      cudaStream_t st);
+}  // namespace fq
+
+using fq::u64;
+
+static const size_t kMaxLaunchBytes = ((size_t)4 << 30) - ((size_t)1 << 20);  // keeps 32-bit smem counters exact
+static thread_local std::string g_create_error;
+
+struct StageBuf {
+  void* host = nullptr;
+  cudaEvent_t copied = nullptr;  // H2D of this buffer finished -> host side reusable
+  bool in_flight = false;
+};
+
+struct fqgpu_ctx {
+  int device = 0;
+  fqgpu_config cfg{};
+  cudaStream_t stream = nullptr;
+  int grid = 0;
+  u64* d_partials = nullptr;
+  fq::Carry* d_carry = nullptr;
+  fq::TileState* d_ts = nullptr;
+  size_t ts_cap = 0;  // tiles
+  fq::LaunchInfo* d_info = nullptr;
+  u64* d_out = nullptr;
+  u64* h_out = nullptr;  // pinned: reduced block followed by the carry
+  std::vector<StageBuf> ring;
+  void* d_stage = nullptr;  // device landing buffer of the staging path
+  size_t chunk_bytes = 0;
+  int next = 0;
+  std::string err;
+  // timing of scan launches since the last reset
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
+  std::vector<cudaEvent_t> event_pool;
+  double kernel_ms_done = 0.0;
+  u64 launches = 0;
+  // shard mode
+  int shard_rank = 0, shard_world = 1;
+};
+
+#define CU_TRY(ctx, call)                                                              \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess) {                                                           \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                 \
+      return FQGPU_ECUDA;                                                              \
+    }                                                                                  \
+  } while (0)
+
+static int fail(fqgpu_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg; else g_create_error = msg;
+  return code;
+}
+
+extern "C" {
+
+int fqgpu_abi_version(void) { return FQGPU_ABI_VERSION; }
+size_t fqgpu_stats_size(void) { return sizeof(fqgpu_stats); }
+const char* fqgpu_build_info(void) {
+  return "libfqgpu sm_100a; scan tile " "16 KiB" "; built " __DATE__;
+}
+int fqgpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+const char* fqgpu_last_error(const fqgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+void fqgpu_destroy(fqgpu_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (auto& b : ctx->ring) {
+    if (b.host) cudaFreeHost(b.host);
+    if (b.copied) cudaEventDestroy(b.copied);
+  }
+  for (auto& p : ctx->timed) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  for (auto e : ctx->event_pool) cudaEventDestroy(e);
+  cudaFree(ctx->d_stage);
+  cudaFree(ctx->d_partials);
+  cudaFree(ctx->d_carry);
+  cudaFree(ctx->d_ts);
+  cudaFree(ctx->d_info);
+  cudaFree(ctx->d_out);
+  if (ctx->h_out) cudaFreeHost(ctx->h_out);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int fqgpu_create(fqgpu_ctx** out, const fqgpu_config* cfg) {
+  if (!out) return fail(nullptr, FQGPU_EARG, "fqgpu_create: out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    return fail(nullptr, FQGPU_ECUDA,
+                std::string("no usable CUDA device (libfqgpu has no CPU fallback): ") + cudaGetErrorString(e));
+  }
+  fqgpu_ctx* ctx = new fqgpu_ctx();
+  if (cfg) ctx->cfg = *cfg;
+  else ctx->cfg.device = -1;
+  int dev = ctx->cfg.device;
+  if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+  if (dev >= ndev) { delete ctx; return fail(nullptr, FQGPU_EARG, "fqgpu_create: device ordinal out of range"); }
+  ctx->device = dev;
+  ctx->chunk_bytes = ctx->cfg.chunk_bytes ? ctx->cfg.chunk_bytes : ((size_t)64 << 20);
+  ctx->chunk_bytes = (ctx->chunk_bytes + 4095) & ~(size_t)4095;
+  int nbuf = ctx->cfg.n_buffers > 0 ? ctx->cfg.n_buffers : 3;
+  auto bail = [&](const std::string& m) { g_create_error = m; fqgpu_destroy(ctx); return FQGPU_ECUDA; };
+#define CU_NEW(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return bail(std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+  CU_NEW(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  CU_NEW(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major < 10) return bail("libfqgpu is built for sm_100a (B200); device is sm_" + std::to_string(prop.major * 10 + prop.minor));
+  CU_NEW(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CU_NEW(fq::scan_configure());
+  ctx->grid = prop.multiProcessorCount * 2;
+  CU_NEW(cudaMalloc(&ctx->d_partials, (size_t)ctx->grid * fq::BLOCK_WORDS * sizeof(u64)));
+  CU_NEW(cudaMalloc(&ctx->d_carry, sizeof(fq::Carry)));
+  CU_NEW(cudaMalloc(&ctx->d_info, sizeof(fq::LaunchInfo)));
+  CU_NEW(cudaMalloc(&ctx->d_out, fq::BLOCK_WORDS * sizeof(u64)));
+  CU_NEW(cudaMallocHost(&ctx->h_out, fq::BLOCK_WORDS * sizeof(u64) + sizeof(fq::Carry)));
+  ctx->ts_cap = kMaxLaunchBytes / fq::scan_tile_bytes() + 4;
+  CU_NEW(cudaMalloc(&ctx->d_ts, (ctx->ts_cap + 1) * sizeof(fq::TileState)));
+  ctx->ring.resize(nbuf);  // pinned chunks are allocated lazily by the first acquire()
+#undef CU_NEW
+  *out = ctx;
+  int rc = fqgpu_reset(ctx);
+  if (rc != FQGPU_OK) { g_create_error = ctx->err; fqgpu_destroy(ctx); *out = nullptr; return rc; }
+  return FQGPU_OK;
+}
+
+int fqgpu_reset(fqgpu_ctx* ctx) {
+  if (!ctx) return FQGPU_EARG;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  CU_TRY(ctx, fq::launch_reset(ctx->d_partials, ctx->grid, ctx->d_carry, ctx->stream));
+  for (auto& p : ctx->timed) { ctx->event_pool.push_back(p.first); ctx->event_pool.push_back(p.second); }
+  ctx->timed.clear();
+  ctx->kernel_ms_done = 0.0;
+  ctx->launches = 0;
+  ctx->shard_rank = 0;
+  ctx->shard_world = 1;
+  return FQGPU_OK;
+}
+
+static cudaEvent_t get_event(fqgpu_ctx* ctx) {
+  if (!ctx->event_pool.empty()) { cudaEvent_t e = ctx->event_pool.back(); ctx->event_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+int fqgpu_scan_device(fqgpu_ctx* ctx, const void* dptr, size_t nbytes) {
+  if (!ctx) return FQGPU_EARG;
+  if (nbytes == 0) return FQGPU_OK;
+  if (!dptr) return fail(ctx, FQGPU_EARG, "fqgpu_scan_device: NULL pointer");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
+  CU_TRY(ctx, cudaEventRecord(e0, ctx->stream));
+  const uint8_t* p = (const uint8_t*)dptr;
+  size_t left = nbytes;
+  while (left) {
+    size_t n = left < kMaxLaunchBytes ? left : kMaxLaunchBytes;
+    CU_TRY(ctx, fq::launch_scan(p, n, ctx->d_ts, ctx->d_info, ctx->d_carry, ctx->d_partials, ctx->grid,
+                                ctx->cfg.meta_records, ctx->stream));
+    ctx->launches++;
+    p += n;
+    left -= n;
+  }
+  CU_TRY(ctx, cudaEventRecord(e1, ctx->stream));
+  ctx->timed.emplace_back(e0, e1);
+  return FQGPU_OK;
+}
+
+void* fqgpu_stream(fqgpu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int fqgpu_last_timing(fqgpu_ctx* ctx, double* kernel_ms, uint64_t* launches) {
+  if (!ctx) return FQGPU_EARG;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  for (auto& p : ctx->timed) {
+    float ms = 0.f;
+    CU_TRY(ctx, cudaEventElapsedTime(&ms, p.first, p.second));
+    ctx->kernel_ms_done += ms;
+    ctx->event_pool.push_back(p.first);
+    ctx->event_pool.push_back(p.second);
+  }
+  ctx->timed.clear();
+  if (kernel_ms) *kernel_ms = ctx->kernel_ms_done;
+  if (launches) *launches = ctx->launches;
+  return FQGPU_OK;
+}
+
+// ---- stats assembly (host): the reduced block + the stream carry -> fqgpu_stats ----------------
+static inline unsigned log2_bin(u64 len) { unsigned b = 0; while (len) { b++; len >>= 1; } return b; }
+
+static void assemble_stats(const u64* blk, const fq::Carry& c, u64 meta_records, fqgpu_stats* st) {
+  memset(st, 0, sizeof(*st));
+  for (int i = 0; i < 256; i++) { st->base_counts[i] = blk[fq::OFF_HIST_SEQ + i]; st->qual_counts[i] = blk[fq::OFF_HIST_QUAL + i]; }
+  for (int i = 0; i <= fq::POS_BINS; i++) {
+    st->seq_len_hist[i] = blk[fq::OFF_SEQ_LEN + i];
+    st->qual_len_hist[i] = blk[fq::OFF_QUAL_LEN + i];
+    st->qual_pos_sum[i] = blk[fq::OFF_POS_SUM + i];
+  }
+  for (int i = 0; i < fq::LOG2_BINS; i++) st->seq_len_log2[i] = blk[fq::OFF_SEQ_LOG2 + i];
+  st->seq_len_min = blk[fq::OFF_SEQ_LEN_MIN]; st->seq_len_max = blk[fq::OFF_SEQ_LEN_MAX];
+  st->qual_len_min = blk[fq::OFF_QUAL_LEN_MIN]; st->qual_len_max = blk[fq::OFF_QUAL_LEN_MAX];
+  st->bytes = c.bytes;
+  st->lines = c.lines;
+  // trailing unterminated, non-empty line (Nim `lines` yields it as is; its '\r', if any, stays)
+  const bool tail_cr = c.bytes && c.open_len && c.last_byte == '\r';
+  if (c.open_len) {
+    const int cls = (int)(c.lines & 3);
+    const u64 len = c.open_len;
+    st->lines++;
+    if (cls == 1) {
+      if (tail_cr) st->base_counts['\r']++;
+      st->seq_len_hist[len < (u64)fq::POS_BINS ? len : (u64)fq::POS_BINS]++;
+      st->seq_len_log2[log2_bin(len)]++;
+      if (len < st->seq_len_min) st->seq_len_min = len;
+      if (len > st->seq_len_max) st->seq_len_max = len;
+    } else if (cls == 3) {
+      if (tail_cr) {
+        st->qual_counts['\r']++;
+        st->qual_pos_sum[(len - 1) < (u64)fq::POS_BINS ? (len - 1) : (u64)fq::POS_BINS] += '\r';
+      }
+      st->qual_len_hist[len < (u64)fq::POS_BINS ? len : (u64)fq::POS_BINS]++;
+      if (len < st->qual_len_min) st->qual_len_min = len;
+      if (len > st->qual_len_max) st->qual_len_max = len;
+    }
+  }
+  st->reads = (st->lines + 3) / 4;  // lines with i mod 4 == 1
+  u64 bases = 0, quals = 0;
+  for (int i = 0; i < 256; i++) { bases += st->base_counts[i]; quals += st->qual_counts[i]; }
+  st->bases = bases;
+  st->gc_bases = st->base_counts['G'] + st->base_counts['C'];
+  st->n_bases = st->base_counts['N'];
+  u64 sl = 0, ql = 0;
+  for (int i = 0; i <= fq::POS_BINS; i++) { sl += st->seq_len_hist[i]; ql += st->qual_len_hist[i]; }
+  st->seq_lines = sl;
+  st->qual_lines = ql;
+  // quality lines that have a byte at position p = lines longer than p
+  u64 longer = ql, inbins = 0;
+  for (int p = 0; p < fq::POS_BINS; p++) {
+    longer -= st->qual_len_hist[p];
+    st->qual_pos_cnt[p] = longer;
+    inbins += longer;
+  }
+  st->qual_pos_cnt[fq::POS_BINS] = quals - inbins;
+  // fq-meta fold: account the trailing line if the sampling loop would still read it
+  long long qmin = c.qual_min, qmax = c.qual_max;
+  u64 ml = c.meta_lines;
+  unsigned status = c.meta_status;
+  if (meta_records && c.open_len && ml < meta_records * 4) {
+    int has = c.cur_has, mn = c.cur_min, mx = c.cur_max;
+    if (c.meta_pending_cr) { if (!has) { has = 1; mn = mx = -1; } else mn = -1; }
+    if ((ml & 3) == 3 && status == FQGPU_META_OK) {
+      if (has) {
+        long long a = mn, b = mx;
+        if (qmin >= 0) { a = a < qmin ? a : qmin; b = b > qmax ? b : qmax; }
+        qmin = a; qmax = b;
+      } else if (qmin < 0) status = FQGPU_META_EMPTY_QUAL;
+    }
+    ml++;
+  }
+  st->meta_qual_min = qmin;
+  st->meta_qual_max = qmax;
+  st->meta_lines = ml;
+  st->meta_status = status;
+}
+
+int fqgpu_finish(fqgpu_ctx* ctx, fqgpu_stats* out) {
+  if (!ctx || !out) return FQGPU_EARG;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  CU_TRY(ctx, fq::launch_reduce(ctx->d_partials, ctx->grid, ctx->d_out, ctx->stream));
+  CU_TRY(ctx, cudaMemcpyAsync(ctx->h_out, ctx->d_out, fq::BLOCK_WORDS * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaMemcpyAsync(ctx->h_out + fq::BLOCK_WORDS, ctx->d_carry, sizeof(fq::Carry), cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  fq::Carry c;
+  memcpy(&c, ctx->h_out + fq::BLOCK_WORDS, sizeof(c));
+  assemble_stats(ctx->h_out, c, ctx->cfg.meta_records, out);
+  return FQGPU_OK;
+}
+
+int fqgpu_count_device(fqgpu_ctx* ctx, const void* dptr, size_t nbytes, fqgpu_stats* out) {
+  int rc = fqgpu_reset(ctx);
+  if (rc != FQGPU_OK) return rc;
+  rc = fqgpu_scan_device(ctx, dptr, nbytes);
+  if (rc != FQGPU_OK) return rc;
+  return fqgpu_finish(ctx, out);
+}
+
+// ---- staging ring -------------------------------------------------------------------------------
+void* fqgpu_acquire(fqgpu_ctx* ctx, size_t* capacity) {
+  if (!ctx) return nullptr;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return nullptr; }
+  StageBuf& b = ctx->ring[ctx->next];
+  if (!b.host) {
+    cudaError_t e = cudaMallocHost(&b.host, ctx->chunk_bytes);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b.copied, cudaEventDisableTiming);
+    if (e == cudaSuccess && !ctx->d_stage) e = cudaMalloc(&ctx->d_stage, ctx->chunk_bytes);
+    if (e != cudaSuccess) { ctx->err = std::string("staging allocation failed: ") + cudaGetErrorString(e); return nullptr; }
+  }
+  if (b.in_flight) {
+    cudaError_t e = cudaEventSynchronize(b.copied);
+    if (e != cudaSuccess) { ctx->err = std::string("cudaEventSynchronize: ") + cudaGetErrorString(e); return nullptr; }
+    b.in_flight = false;
+  }
+  if (capacity) *capacity = ctx->chunk_bytes;
+  return b.host;
+}
+
+int fqgpu_submit(fqgpu_ctx* ctx, void* chunk, size_t nbytes) {
+  if (!ctx) return FQGPU_EARG;
+  int slot = -1;
+  for (size_t i = 0; i < ctx->ring.size(); i++) if (ctx->ring[i].host == chunk && chunk) slot = (int)i;
+  if (slot < 0) return fail(ctx, FQGPU_EARG, "fqgpu_submit: chunk was not handed out by fqgpu_acquire");
+  if (nbytes > ctx->chunk_bytes) return fail(ctx, FQGPU_EARG, "fqgpu_submit: nbytes exceeds the chunk capacity");
+  if (nbytes == 0) return FQGPU_OK;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  StageBuf& b = ctx->ring[slot];
+  // one device landing buffer: the copy of chunk k+1 is ordered after the scan of chunk k on the
+  // context's stream (the scan is ~1% of the copy time, so nothing is lost by not overlapping them)
+  CU_TRY(ctx, cudaMemcpyAsync(ctx->d_stage, b.host, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(ctx, cudaEventRecord(b.copied, ctx->stream));
+  b.in_flight = true;
+  ctx->next = (slot + 1) % (int)ctx->ring.size();
+  return fqgpu_scan_device(ctx, ctx->d_stage, nbytes);
+}
+
+int fqgpu_count_host(fqgpu_ctx* ctx, const void* buf, size_t nbytes, fqgpu_stats* out) {
+  if (!ctx || !out || (!buf && nbytes)) return FQGPU_EARG;
+  int rc = fqgpu_reset(ctx);
+  if (rc != FQGPU_OK) return rc;
+  const uint8_t* p = (const uint8_t*)buf;
+  size_t left = nbytes;
+  while (left) {
+    size_t cap = 0;
+    void* chunk = fqgpu_acquire(ctx, &cap);
+    if (!chunk) return FQGPU_ECUDA;
+    size_t n = left < cap ? left : cap;
+    memcpy(chunk, p, n);
+    rc = fqgpu_submit(ctx, chunk, n);
+    if (rc != FQGPU_OK) return rc;
+    p += n;
+    left -= n;
+  }
+  return fqgpu_finish(ctx, out);
+}
+
+// src/fq_count.nim:30-36: ".gz" (case-sensitive) selects the gz stream; gzread() inflates straight
+// into the pinned chunk, the call shape of gzip_stream.nim:16-17.
+int fqgpu_count_file(fqgpu_ctx* ctx, const char* path, fqgpu_stats* out) {
+  if (!ctx || !path || !out) return FQGPU_EARG;
+  const size_t L = strlen(path);
+  const bool gz = L >= 3 && strcmp(path + L - 3, ".gz") == 0;
+  int rc = fqgpu_reset(ctx);
+  if (rc != FQGPU_OK) return rc;
+  if (gz) {
+    gzFile f = gzopen(path, "rb");
+    if (!f) return fail(ctx, FQGPU_EIO, std::string("Unable to open file: ") + path);
+    gzbuffer(f, 1 << 20);
+    for (;;) {
+      size_t cap = 0;
+      uint8_t* chunk = (uint8_t*)fqgpu_acquire(ctx, &cap);
+      if (!chunk) { gzclose(f); return FQGPU_ECUDA; }
+      size_t got = 0;
+      while (got < cap) {
+        size_t want = cap - got;
+        if (want > ((size_t)1 << 30)) want = (size_t)1 << 30;
+        int r = gzread(f, chunk + got, (unsigned)want);
+        if (r < 0) { gzclose(f); return fail(ctx, FQGPU_EIO, std::string("gzread failed: ") + path); }
+        if (r == 0) break;
+        got += (size_t)r;
+      }
+      if (got == 0) break;
+      rc = fqgpu_submit(ctx, chunk, got);
+      if (rc != FQGPU_OK) { gzclose(f); return rc; }
+      if (got < cap) break;
+    }
+    gzclose(f);
+  } else {
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail(ctx, FQGPU_EIO, std::string("Unable to open file: ") + path);
+    for (;;) {
+      size_t cap = 0;
+      uint8_t* chunk = (uint8_t*)fqgpu_acquire(ctx, &cap);
+      if (!chunk) { close(fd); return FQGPU_ECUDA; }
+      size_t got = 0;
+      while (got < cap) {
+        ssize_t r = read(fd, chunk + got, cap - got);
+        if (r < 0) { close(fd); return fail(ctx, FQGPU_EIO, std::string("read failed: ") + path); }
+        if (r == 0) break;
+        got += (size_t)r;
+      }
+      if (got == 0) break;
+      rc = fqgpu_submit(ctx, chunk, got);
+      if (rc != FQGPU_OK) { close(fd); return rc; }
+      if (got < cap) break;
+    }
+    close(fd);
+  }
+  return fqgpu_finish(ctx, out);
+}
+
+// ---- synthetic data -----------------------------------------------------------------------------
+int fqgpu_synth_illumina(fqgpu_ctx* ctx, void* dptr, size_t capacity, uint64_t first_record,
+                         uint64_t n_records, uint64_t seed, size_t* bytes_written) {
+  if (!ctx || !dptr) return FQGPU_EARG;
+  const u64 nbytes = n_records * 360ull;
+  if (nbytes > capacity) return fail(ctx, FQGPU_EARG, "fqgpu_synth_illumina: capacity too small");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  CU_TRY(ctx, fq::launch_synth_illumina(dptr, first_record * 360ull, nbytes, seed, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (bytes_written) *bytes_written = (size_t)nbytes;
+  return FQGPU_OK;
+}
+
+int fqgpu_synth_illumina_bytes(fqgpu_ctx* ctx, void* dptr, uint64_t first_byte, uint64_t nbytes, uint64_t seed) {
+  if (!ctx || !dptr) return FQGPU_EARG;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  CU_TRY(ctx, fq::launch_synth_illumina(dptr, first_byte, nbytes, seed, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return FQGPU_OK;
+}
+
+int fqgpu_synth_ont(fqgpu_ctx* ctx, void* dptr, size_t capacity, uint64_t first_record,
+                    uint64_t n_records, uint64_t seed, size_t* bytes_written) {
+  if (!ctx || !dptr) return FQGPU_EARG;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  size_t w = 0;
+  cudaError_t e = fq::synth_ont(dptr, capacity, first_record, n_records, seed, &w, ctx->stream);
+  if (e == cudaErrorInvalidValue) return fail(ctx, FQGPU_EARG, "fqgpu_synth_ont: capacity too small");
+  CU_TRY(ctx, e);
+  if (bytes_written) *bytes_written = w;
+  return FQGPU_OK;
+}
+
+// ---- multi-GPU shard protocol: implemented in fq_shard.cu ----------------------------------------
+
+}  // extern "C"

@@ -1,0 +1,215 @@
+"""GPU parity: libfqgpu (through its C ABI) against the CPU oracle, bit-exact on every integer.
+
+Covers the reference's golden fixtures, the edge corpus, every chunk/tile boundary offset, the
+pinned streaming ring, unaligned device pointers and the synthetic generators at moderate size.
+Nothing here reads /root/reference (it does not exist on the GPU box).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import seq_collection_b200 as fq
+from oracle import fq_oracle as O
+from tests import corpus
+
+pytestmark = pytest.mark.gpu
+
+TILE = 16384
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def assert_equal_stats(got: dict, want: dict, ctxmsg=""):
+    for k in O.SCALARS:
+        assert got[k] == want[k], f"{ctxmsg}: {k}: gpu={got[k]} oracle={want[k]}"
+    for k in O.ARRAYS:
+        if got[k] != want[k]:
+            bad = [(i, a, b) for i, (a, b) in enumerate(zip(got[k], want[k])) if a != b][:8]
+            raise AssertionError(f"{ctxmsg}: {k} differs at (idx, gpu, oracle) {bad}")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = fq.FqGpu(meta_records=100)
+    yield c
+    c.close()
+
+
+def test_golden_fixtures_rows(ctx, golden_dir):
+    """docs/fq-count.md rows + docs/fq-meta.md min/max through the product path (file API, incl. .gz)."""
+    lines = open(os.path.join(golden_dir, "fq_count_docs.tsv")).read().splitlines()[1:]
+    for ln in lines:
+        name, reads, gc_content, gc, n, bases = ln.split("\t")
+        path = os.path.join(golden_dir, "fastq", name)
+        st = ctx.count_file(path)
+        assert (st.reads, st.gc_bases, st.n_bases, st.bases) == (int(reads), int(gc), int(n), int(bases)), name
+        assert fq.fq_count_row(st) == O.fq_count_row(O.count_file(path)), name
+        assert_equal_stats(st.to_dict(), O.count_file(path, 100), name)
+    for ln in open(os.path.join(golden_dir, "fq_meta_docs.tsv")).read().splitlines()[1:]:
+        name, fmt, phred, multiple, qmin, qmax, n_lines = ln.split("\t")
+        st = ctx.count_file(os.path.join(golden_dir, "fastq", name))
+        f = fq.fq_meta_quality_fields(st)
+        assert f == [fmt, phred, multiple.lower(), qmin, qmax, n_lines], name
+
+
+def test_missing_file_is_eio(ctx):
+    with pytest.raises(fq.FqGpuError) as ei:
+        ctx.count_file("/nonexistent/file.fq")
+    assert ei.value.code == fq.EIO and "Unable to open file" in ei.value.msg
+
+
+@pytest.mark.parametrize("name", sorted(corpus.edge_cases()))
+def test_edge_corpus(ctx, name):
+    data = corpus.edge_cases()[name]
+    assert_equal_stats(ctx.count_bytes(data).to_dict(), O.count(data, 100), name)
+
+
+@pytest.mark.parametrize("meta_n", [1, 2, 3, 7, 1000])
+def test_meta_records_values(meta_n):
+    with fq.FqGpu(meta_records=meta_n) as c:
+        for name, data in corpus.edge_cases().items():
+            assert_equal_stats(c.count_bytes(data).to_dict(), O.count(data, meta_n), f"{name} n={meta_n}")
+
+
+def test_chunk_edges_every_offset():
+    """Feed one stream in two device scans split at every byte offset (carry resolved on device)."""
+    torch = _torch()
+    cases = corpus.edge_cases()
+    data = cases["crlf"] + cases["qual_starts_with_at"] + cases["blank_lines"] + cases["crlf_no_final"]
+    want = O.count(data, 100)
+    buf = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+    with fq.FqGpu(meta_records=100) as c:
+        for cut in range(0, len(data) + 1):
+            c.reset()
+            c.scan_device(buf.data_ptr(), cut)
+            c.scan_device(buf.data_ptr() + cut, len(data) - cut)
+            assert_equal_stats(c.finish().to_dict(), want, f"cut={cut}")
+
+
+def test_streaming_ring_tiny_chunks():
+    """fqgpu_acquire/submit with a ring of tiny pinned chunks: every record straddles chunk edges."""
+    rng = np.random.default_rng(5)
+    data = corpus.random_fastq(rng, 400, max_len=400, crlf=True, final_newline=False)
+    want = O.count(data, 100)
+    for chunk in (4096, 4096 * 3):
+        with fq.FqGpu(meta_records=100, chunk_bytes=chunk, n_buffers=2) as c:
+            c.reset()
+            c.submit_bytes(data)
+            assert_equal_stats(c.finish().to_dict(), want, f"chunk={chunk}")
+
+
+def test_tile_edges_and_unaligned_pointers():
+    """Lines, CRLF pairs and '\\n' bytes placed on and around tile boundaries; unaligned base pointers."""
+    torch = _torch()
+    rng = np.random.default_rng(9)
+    body = corpus.random_fastq(rng, 300, min_len=30, max_len=260, crlf=True)
+    with fq.FqGpu(meta_records=50) as c:
+        for shift in list(range(0, 20)) + [TILE - 2, TILE - 1, TILE, TILE + 1]:
+            data = b"@pad\n" + b"A" * shift + b"\n+\n" + b"I" * shift + b"\n" + body
+            want = O.count(data, 50)
+            for misalign in (0, 1, 7, 15):
+                buf = torch.zeros(len(data) + 64, dtype=torch.uint8, device="cuda")
+                buf[misalign:misalign + len(data)] = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+                st = c.count_device(buf.data_ptr() + misalign, len(data))
+                assert_equal_stats(st.to_dict(), want, f"shift={shift} misalign={misalign}")
+
+
+def test_dense_newlines_windowed_path(ctx):
+    """More newlines per tile than the newline-index window holds."""
+    data = (b"A\n" * 30000) + (b"\n" * 40000) + b"@x\nACGT\n+\nIIII\n"
+    assert_equal_stats(ctx.count_bytes(data).to_dict(), O.count(data, 100), "dense")
+
+
+def test_long_lines_across_many_tiles(ctx):
+    rng = np.random.default_rng(3)
+    recs = []
+    for L in (1, TILE - 7, TILE, 3 * TILE + 5, 70000, 2048, 2049, 100):
+        s = bytes(rng.choice(list(b"ACGTN"), size=L).astype(np.uint8))
+        q = bytes(rng.integers(33, 90, size=L, dtype=np.uint8))
+        recs.append(b"@r\n" + s + b"\n+\n" + q + b"\n")
+    data = b"".join(recs)
+    assert_equal_stats(ctx.count_bytes(data).to_dict(), O.count(data, 100), "long")
+
+
+@pytest.mark.parametrize("kind,n_records", [("illumina", 300000), ("ont", 1500)])
+def test_synthetic_generators_vs_oracle(kind, n_records):
+    """Generated on the device, scanned on the device, copied back and scanned by the oracle."""
+    torch = _torch()
+    cap = 360 * n_records if kind == "illumina" else 64 << 20
+    buf = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    with fq.FqGpu(meta_records=100) as c:
+        if kind == "illumina":
+            n = c.synth_illumina(buf.data_ptr(), cap, 0, n_records, 20240229)
+            assert n == 360 * n_records
+        else:
+            n = c.synth_ont(buf.data_ptr(), cap, 0, n_records, 20240301)
+        st = c.count_device(buf.data_ptr(), n)
+        host = buf[:n].cpu().numpy()
+        want = O.count(host, 100)
+        assert_equal_stats(st.to_dict(), want, kind)
+        assert st.reads == n_records
+        if kind == "illumina":
+            assert st.bases == 150 * n_records and st.seq_len_min == 150 == st.seq_len_max
+            assert host[:56].tobytes().startswith(b"@A00156:217:HKJWGDSXX:")
+            assert abs(st.gc_bases / (st.bases - st.n_bases) - 0.41) < 0.01
+        else:
+            assert st.seq_len_min >= 1000 and st.seq_len_max <= 100000
+        # odd split of the same bytes must not change anything (carry on the device)
+        c.reset()
+        cut = n // 3 + 13
+        c.scan_device(buf.data_ptr(), cut)
+        c.scan_device(buf.data_ptr() + cut, n - cut)
+        assert_equal_stats(c.finish().to_dict(), want, kind + " split")
+
+
+def test_illumina_byte_range_generation():
+    torch = _torch()
+    n = 360 * 1000
+    a = torch.empty(n, dtype=torch.uint8, device="cuda")
+    b = torch.empty(n, dtype=torch.uint8, device="cuda")
+    with fq.FqGpu() as c:
+        c.synth_illumina(a.data_ptr(), n, 0, 1000, 7)
+        cut = 123457
+        c.synth_illumina_bytes(b.data_ptr(), 0, cut, 7)
+        c.synth_illumina_bytes(b.data_ptr() + cut, cut, n - cut, 7)
+    assert torch.equal(a, b)
+
+
+def test_size_independent_properties_large():
+    """1.44 GB Illumina stream: invariants that need no oracle pass over the full size."""
+    torch = _torch()
+    n_records = 4_000_000
+    n = 360 * n_records
+    buf = torch.empty(n, dtype=torch.uint8, device="cuda")
+    with fq.FqGpu(meta_records=n_records) as c:
+        c.synth_illumina(buf.data_ptr(), n, 0, n_records, 20240229)
+        st = c.count_device(buf.data_ptr(), n)
+        d = st.to_dict()
+        assert d["bytes"] == n and d["lines"] == 4 * n_records and d["reads"] == n_records
+        assert d["bases"] == 150 * n_records == sum(d["base_counts"])
+        assert sum(d["qual_counts"]) == 150 * n_records
+        assert d["seq_len_hist"][150] == n_records and d["qual_len_hist"][150] == n_records
+        assert all(d["qual_pos_cnt"][p] == n_records for p in range(150)) and d["qual_pos_cnt"][150] == 0
+        assert sum(d["qual_pos_sum"]) == sum(v * cnt for v, cnt in enumerate(d["qual_counts"]))
+        assert set(i for i, v in enumerate(d["qual_counts"]) if v) == {ord("F"), ord(":"), ord(","), ord("#")}
+        assert (d["meta_qual_min"], d["meta_qual_max"], d["meta_lines"]) == (2, 37, 4 * n_records)
+        # linearity: the sum of two halves (independent streams cut at a record edge) equals the whole
+        half = 360 * (n_records // 2)
+        c2 = fq.FqGpu()
+        s1 = c2.count_device(buf.data_ptr(), half).to_dict()
+        s2 = c2.count_device(buf.data_ptr() + half, n - half).to_dict()
+        c2.close()
+        for k in ("reads", "bases", "gc_bases", "n_bases"):
+            assert s1[k] + s2[k] == d[k]
+        for k in ("base_counts", "qual_counts", "qual_pos_sum"):
+            assert [x + y for x, y in zip(s1[k], s2[k])] == d[k]
+        # a 64 MB prefix against the oracle
+        m = 360 * 180_000
+        assert_equal_stats(fq.FqGpu(meta_records=100).count_device(buf.data_ptr(), m).to_dict(),
+                           O.count(buf[:m].cpu().numpy(), 100), "prefix")
