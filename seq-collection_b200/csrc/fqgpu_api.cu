@@ -53,7 +53,13 @@ struct fqgpu_ctx {
   u64* d_out = nullptr;
   u64* h_out = nullptr;  // pinned: reduced block followed by the carry
   std::vector<StageBuf> ring;
-  void* d_stage = nullptr;  // device landing buffer of the staging path
+  // device landing buffers of the host paths: H2D of chunk k+1 (copy stream) overlaps the scan of
+  // chunk k (compute stream)
+  void* d_stage[2] = {nullptr, nullptr};
+  cudaStream_t cstream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr};   // H2D into d_stage[b] finished
+  cudaEvent_t ev_scanned[2] = {nullptr, nullptr};  // scan of d_stage[b] finished -> buffer free
+  u64 n_staged = 0;
   size_t chunk_bytes = 0;
   int next = 0;
   std::string err;
@@ -99,13 +105,19 @@ void fqgpu_destroy(fqgpu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->cstream) cudaStreamSynchronize(ctx->cstream);
   for (auto& b : ctx->ring) {
     if (b.host) cudaFreeHost(b.host);
     if (b.copied) cudaEventDestroy(b.copied);
   }
   for (auto& p : ctx->timed) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   for (auto e : ctx->event_pool) cudaEventDestroy(e);
-  cudaFree(ctx->d_stage);
+  for (int b = 0; b < 2; b++) {
+    cudaFree(ctx->d_stage[b]);
+    if (ctx->ev_copied[b]) cudaEventDestroy(ctx->ev_copied[b]);
+    if (ctx->ev_scanned[b]) cudaEventDestroy(ctx->ev_scanned[b]);
+  }
+  if (ctx->cstream) cudaStreamDestroy(ctx->cstream);
   cudaFree(ctx->d_partials);
   cudaFree(ctx->d_carry);
   cudaFree(ctx->d_ts);
@@ -302,7 +314,11 @@ static void assemble_stats(const u64* blk, const fq::Carry& c, u64 meta_records,
 int fqgpu_finish(fqgpu_ctx* ctx, fqgpu_stats* out) {
   if (!ctx || !out) return FQGPU_EARG;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
+  CU_TRY(ctx, cudaEventRecord(e0, ctx->stream));
   CU_TRY(ctx, fq::launch_reduce(ctx->d_partials, ctx->grid, ctx->d_out, ctx->stream));
+  CU_TRY(ctx, cudaEventRecord(e1, ctx->stream));
+  ctx->timed.emplace_back(e0, e1);
   CU_TRY(ctx, cudaMemcpyAsync(ctx->h_out, ctx->d_out, fq::BLOCK_WORDS * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
   CU_TRY(ctx, cudaMemcpyAsync(ctx->h_out + fq::BLOCK_WORDS, ctx->d_carry, sizeof(fq::Carry), cudaMemcpyDeviceToHost, ctx->stream));
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -320,6 +336,37 @@ int fqgpu_count_device(fqgpu_ctx* ctx, const void* dptr, size_t nbytes, fqgpu_st
   return fqgpu_finish(ctx, out);
 }
 
+// ---- host -> device staging ------------------------------------------------------------------
+static int ensure_stage(fqgpu_ctx* ctx) {
+  if (ctx->d_stage[0]) return FQGPU_OK;
+  CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->cstream, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; b++) {
+    CU_TRY(ctx, cudaMalloc(&ctx->d_stage[b], ctx->chunk_bytes));
+    CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_copied[b], cudaEventDisableTiming));
+    CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_scanned[b], cudaEventDisableTiming));
+  }
+  return FQGPU_OK;
+}
+
+// Copies `nbytes` (<= chunk_bytes) of host memory into the next landing buffer on the copy stream
+// and scans it on the compute stream.  `copied` (optional) is recorded when the host bytes are no
+// longer needed.
+static int stage_and_scan(fqgpu_ctx* ctx, const void* host, size_t nbytes, cudaEvent_t copied) {
+  int rc = ensure_stage(ctx);
+  if (rc != FQGPU_OK) return rc;
+  const int b = (int)(ctx->n_staged & 1);
+  if (ctx->n_staged >= 2) CU_TRY(ctx, cudaStreamWaitEvent(ctx->cstream, ctx->ev_scanned[b], 0));
+  CU_TRY(ctx, cudaMemcpyAsync(ctx->d_stage[b], host, nbytes, cudaMemcpyHostToDevice, ctx->cstream));
+  CU_TRY(ctx, cudaEventRecord(ctx->ev_copied[b], ctx->cstream));
+  if (copied) CU_TRY(ctx, cudaEventRecord(copied, ctx->cstream));
+  CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
+  rc = fqgpu_scan_device(ctx, ctx->d_stage[b], nbytes);
+  if (rc != FQGPU_OK) return rc;
+  CU_TRY(ctx, cudaEventRecord(ctx->ev_scanned[b], ctx->stream));
+  ctx->n_staged++;
+  return FQGPU_OK;
+}
+
 // ---- staging ring -------------------------------------------------------------------------------
 void* fqgpu_acquire(fqgpu_ctx* ctx, size_t* capacity) {
   if (!ctx) return nullptr;
@@ -328,7 +375,6 @@ void* fqgpu_acquire(fqgpu_ctx* ctx, size_t* capacity) {
   if (!b.host) {
     cudaError_t e = cudaMallocHost(&b.host, ctx->chunk_bytes);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b.copied, cudaEventDisableTiming);
-    if (e == cudaSuccess && !ctx->d_stage) e = cudaMalloc(&ctx->d_stage, ctx->chunk_bytes);
     if (e != cudaSuccess) { ctx->err = std::string("staging allocation failed: ") + cudaGetErrorString(e); return nullptr; }
   }
   if (b.in_flight) {
@@ -349,28 +395,22 @@ int fqgpu_submit(fqgpu_ctx* ctx, void* chunk, size_t nbytes) {
   if (nbytes == 0) return FQGPU_OK;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   StageBuf& b = ctx->ring[slot];
-  // one device landing buffer: the copy of chunk k+1 is ordered after the scan of chunk k on the
-  // context's stream (the scan is ~1% of the copy time, so nothing is lost by not overlapping them)
-  CU_TRY(ctx, cudaMemcpyAsync(ctx->d_stage, b.host, nbytes, cudaMemcpyHostToDevice, ctx->stream));
-  CU_TRY(ctx, cudaEventRecord(b.copied, ctx->stream));
   b.in_flight = true;
   ctx->next = (slot + 1) % (int)ctx->ring.size();
-  return fqgpu_scan_device(ctx, ctx->d_stage, nbytes);
+  return stage_and_scan(ctx, b.host, nbytes, b.copied);
 }
 
 int fqgpu_count_host(fqgpu_ctx* ctx, const void* buf, size_t nbytes, fqgpu_stats* out) {
   if (!ctx || !out || (!buf && nbytes)) return FQGPU_EARG;
   int rc = fqgpu_reset(ctx);
   if (rc != FQGPU_OK) return rc;
+  // H2D straight from the caller's buffer (asynchronous when it is pinned), double-buffered on
+  // the device so the copy of chunk k+1 overlaps the scan of chunk k
   const uint8_t* p = (const uint8_t*)buf;
   size_t left = nbytes;
   while (left) {
-    size_t cap = 0;
-    void* chunk = fqgpu_acquire(ctx, &cap);
-    if (!chunk) return FQGPU_ECUDA;
-    size_t n = left < cap ? left : cap;
-    memcpy(chunk, p, n);
-    rc = fqgpu_submit(ctx, chunk, n);
+    size_t n = left < ctx->chunk_bytes ? left : ctx->chunk_bytes;
+    rc = stage_and_scan(ctx, p, n, nullptr);
     if (rc != FQGPU_OK) return rc;
     p += n;
     left -= n;
