@@ -1,6 +1,6 @@
 // fq_layout.h -- constants shared by the device kernels and the host side of libfqgpu.
-// Counter blocks are arrays of uint64 words; every persistent CTA owns one partial block, the
-// reduction kernel (K3) folds them into one block of the same layout.
+// Counter blocks are arrays of uint64 words; every span (one persistent CTA per span and launch)
+// owns one block, the reduction kernel (K3) folds them into one block of the same layout.
 #pragma once
 #include <stdint.h>
 
@@ -25,6 +25,8 @@ constexpr int OFF_QUAL_LEN_MAX = OFF_QUAL_LEN_MIN + 1;
 constexpr int BLOCK_WORDS = ((OFF_QUAL_LEN_MAX + 1 + 31) / 32) * 32;
 constexpr int N_SUM_WORDS = OFF_SEQ_LEN_MIN;  // words [0, N_SUM_WORDS) are sum-reduced
 
+constexpr int MAX_SPANS = 296;  // 2 CTAs per SM on a 148-SM B200
+
 // ---- stream carry: device-resident state that makes consecutive scans one logical stream ----
 struct Carry {
   unsigned long long lines;     // '\n' seen so far == terminated lines
@@ -42,16 +44,29 @@ struct Carry {
   unsigned int pad;
 };
 
-// tile descriptors of the decoupled look-back (two self-describing 64-bit words)
-struct TileState {
-  unsigned long long a;  // status<<62 | newline count (aggregate) or inclusive line count (prefix)
-  unsigned long long b;  // status<<62 | has_nl<<61 | open-line bytes at tile end (see fq_scan.cu)
+// One span = the contiguous run of tiles one CTA scans in a launch.  The line phase at a span start
+// is GUESSED from the content (first '@' line whose line+2 starts with '+') so that no CTA ever
+// waits for another; the stitch kernel verifies every guess against the exact line counts.
+enum { SPAN_PENDING = 0, SPAN_COMMITTED = 1, SPAN_RESCAN = 2 };
+constexpr unsigned int PHASE_UNKNOWN = 4;
+struct SpanDesc {
+  unsigned long long T;         // newlines in the span
+  unsigned long long head_len;  // bytes before the first newline (span length when T == 0)
+  unsigned long long tail_len;  // bytes after the last newline (T > 0)
+  unsigned long long G, P0;     // exact lines / open-line bytes before the span (stitch kernel)
+  unsigned int guess;           // (lines before the span) mod 4 used by pass 0; PHASE_UNKNOWN = count only
+  unsigned int state;           // SPAN_*
+  unsigned int exact;           // exact phase (stitch kernel)
+  unsigned int pad;
+  unsigned long long pad2[2];
 };
 
-struct LaunchInfo {
-  unsigned int tile_counter;  // dynamic tile scheduler
-  unsigned int lookbehind;    // byte preceding the launch's first byte (0 when none)
-  unsigned int pad[2];
+// Snapshot of the carry taken at the start of a launch (read by every stitch CTA while the last
+// one writes the new carry).
+struct LaunchHdr {
+  unsigned long long lines0, open0, bytes0;
+  unsigned int last_byte0, phase_known;
+  unsigned int mismatches, pad;
 };
 
 }  // namespace fq

@@ -20,10 +20,10 @@ size_t scan_smem_bytes();
 int scan_tile_bytes();
 int scan_threads();
 cudaError_t scan_configure();
-cudaError_t launch_reset(u64* partials, int nblocks, Carry* carry, cudaStream_t st);
-cudaError_t launch_scan(const void* ptr, size_t nbytes, TileState* ts, LaunchInfo* info, Carry* carry,
-                        u64* partials, int grid, u64 meta_records, cudaStream_t st);
-cudaError_t launch_reduce(const u64* partials, int nblocks, u64* out, cudaStream_t st);
+cudaError_t launch_reset(u64* committed, int nblocks, Carry* carry, cudaStream_t st);
+cudaError_t launch_scan(const void* ptr, size_t nbytes, SpanDesc* desc, LaunchHdr* hdr, Carry* carry,
+                        u64* pending, u64* committed, int max_spans, u64 meta_records, cudaStream_t st);
+cudaError_t launch_reduce(const u64* blocks, int nblocks, u64* out, cudaStream_t st);
 cudaError_t launch_synth_illumina(void* dptr, u64 first_byte, u64 nbytes, u64 seed, cudaStream_t st);
 cudaError_t synth_ont(void* dptr, size_t capacity, u64 first_record, u64 n_records, u64 seed, size_t* bytes_written,
                       cudaStream_t st);
@@ -31,7 +31,8 @@ cudaError_t synth_ont(void* dptr, size_t capacity, u64 first_record, u64 n_recor
 
 using fq::u64;
 
-static const size_t kMaxLaunchBytes = ((size_t)4 << 30) - ((size_t)1 << 20);  // keeps 32-bit smem counters exact
+// one launch = up to MAX_SPANS spans; a span stays below 2 GiB so its 32-bit shared-memory counters are exact
+static const size_t kMaxLaunchBytes = (size_t)fq::MAX_SPANS * ((size_t)2 << 30) - ((size_t)64 << 20);
 static thread_local std::string g_create_error;
 
 struct StageBuf {
@@ -45,11 +46,11 @@ struct fqgpu_ctx {
   fqgpu_config cfg{};
   cudaStream_t stream = nullptr;
   int grid = 0;
-  u64* d_partials = nullptr;
+  u64* d_pending = nullptr;    // [MAX_SPANS] blocks of the launch in flight
+  u64* d_committed = nullptr;  // [MAX_SPANS] blocks accumulated since the last reset
   fq::Carry* d_carry = nullptr;
-  fq::TileState* d_ts = nullptr;
-  size_t ts_cap = 0;  // tiles
-  fq::LaunchInfo* d_info = nullptr;
+  fq::SpanDesc* d_desc = nullptr;
+  fq::LaunchHdr* d_hdr = nullptr;
   u64* d_out = nullptr;
   u64* h_out = nullptr;  // pinned: reduced block followed by the carry
   std::vector<StageBuf> ring;
@@ -118,10 +119,11 @@ void fqgpu_destroy(fqgpu_ctx* ctx) {
     if (ctx->ev_scanned[b]) cudaEventDestroy(ctx->ev_scanned[b]);
   }
   if (ctx->cstream) cudaStreamDestroy(ctx->cstream);
-  cudaFree(ctx->d_partials);
+  cudaFree(ctx->d_pending);
+  cudaFree(ctx->d_committed);
   cudaFree(ctx->d_carry);
-  cudaFree(ctx->d_ts);
-  cudaFree(ctx->d_info);
+  cudaFree(ctx->d_desc);
+  cudaFree(ctx->d_hdr);
   cudaFree(ctx->d_out);
   if (ctx->h_out) cudaFreeHost(ctx->h_out);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -157,13 +159,14 @@ int fqgpu_create(fqgpu_ctx** out, const fqgpu_config* cfg) {
   CU_NEW(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CU_NEW(fq::scan_configure());
   ctx->grid = prop.multiProcessorCount * 2;
-  CU_NEW(cudaMalloc(&ctx->d_partials, (size_t)ctx->grid * fq::BLOCK_WORDS * sizeof(u64)));
+  if (ctx->grid > fq::MAX_SPANS) ctx->grid = fq::MAX_SPANS;
+  CU_NEW(cudaMalloc(&ctx->d_pending, (size_t)fq::MAX_SPANS * fq::BLOCK_WORDS * sizeof(u64)));
+  CU_NEW(cudaMalloc(&ctx->d_committed, (size_t)fq::MAX_SPANS * fq::BLOCK_WORDS * sizeof(u64)));
   CU_NEW(cudaMalloc(&ctx->d_carry, sizeof(fq::Carry)));
-  CU_NEW(cudaMalloc(&ctx->d_info, sizeof(fq::LaunchInfo)));
+  CU_NEW(cudaMalloc(&ctx->d_desc, fq::MAX_SPANS * sizeof(fq::SpanDesc)));
+  CU_NEW(cudaMalloc(&ctx->d_hdr, sizeof(fq::LaunchHdr)));
   CU_NEW(cudaMalloc(&ctx->d_out, fq::BLOCK_WORDS * sizeof(u64)));
   CU_NEW(cudaMallocHost(&ctx->h_out, fq::BLOCK_WORDS * sizeof(u64) + sizeof(fq::Carry)));
-  ctx->ts_cap = kMaxLaunchBytes / fq::scan_tile_bytes() + 4;
-  CU_NEW(cudaMalloc(&ctx->d_ts, (ctx->ts_cap + 1) * sizeof(fq::TileState)));
   ctx->ring.resize(nbuf);  // pinned chunks are allocated lazily by the first acquire()
 #undef CU_NEW
   *out = ctx;
@@ -175,7 +178,7 @@ int fqgpu_create(fqgpu_ctx** out, const fqgpu_config* cfg) {
 int fqgpu_reset(fqgpu_ctx* ctx) {
   if (!ctx) return FQGPU_EARG;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
-  CU_TRY(ctx, fq::launch_reset(ctx->d_partials, ctx->grid, ctx->d_carry, ctx->stream));
+  CU_TRY(ctx, fq::launch_reset(ctx->d_committed, fq::MAX_SPANS, ctx->d_carry, ctx->stream));
   for (auto& p : ctx->timed) { ctx->event_pool.push_back(p.first); ctx->event_pool.push_back(p.second); }
   ctx->timed.clear();
   ctx->kernel_ms_done = 0.0;
@@ -203,8 +206,8 @@ int fqgpu_scan_device(fqgpu_ctx* ctx, const void* dptr, size_t nbytes) {
   size_t left = nbytes;
   while (left) {
     size_t n = left < kMaxLaunchBytes ? left : kMaxLaunchBytes;
-    CU_TRY(ctx, fq::launch_scan(p, n, ctx->d_ts, ctx->d_info, ctx->d_carry, ctx->d_partials, ctx->grid,
-                                ctx->cfg.meta_records, ctx->stream));
+    CU_TRY(ctx, fq::launch_scan(p, n, ctx->d_desc, ctx->d_hdr, ctx->d_carry, ctx->d_pending, ctx->d_committed,
+                                ctx->grid, ctx->cfg.meta_records, ctx->stream));
     ctx->launches++;
     p += n;
     left -= n;
@@ -316,7 +319,7 @@ int fqgpu_finish(fqgpu_ctx* ctx, fqgpu_stats* out) {
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
   CU_TRY(ctx, cudaEventRecord(e0, ctx->stream));
-  CU_TRY(ctx, fq::launch_reduce(ctx->d_partials, ctx->grid, ctx->d_out, ctx->stream));
+  CU_TRY(ctx, fq::launch_reduce(ctx->d_committed, fq::MAX_SPANS, ctx->d_out, ctx->stream));
   CU_TRY(ctx, cudaEventRecord(e1, ctx->stream));
   ctx->timed.emplace_back(e0, e1);
   CU_TRY(ctx, cudaMemcpyAsync(ctx->h_out, ctx->d_out, fq::BLOCK_WORDS * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
