@@ -213,3 +213,44 @@ def test_size_independent_properties_large():
         m = 360 * 180_000
         assert_equal_stats(fq.FqGpu(meta_records=100).count_device(buf.data_ptr(), m).to_dict(),
                            O.count(buf[:m].cpu().numpy(), 100), "prefix")
+
+
+def _adversarial_records(n):
+    """Every quality line starts with '@' and every sequence line with '+': the content resync of a
+    span start picks the wrong line as the header, so the stitch kernel's verification must catch the
+    wrong phase and the span must be rescanned exactly."""
+    out = []
+    for i in range(n):
+        L = 40 + (i * 7) % 90
+        out.append(b"@r%d\n" % i + b"+" + b"ACGT" * (L // 4) + b"\n+\n" + b"@" + b"I" * (L // 4 * 4) + b"\n")
+    return b"".join(out)
+
+
+def test_wrong_resync_guess_is_verified_and_rescanned(ctx):
+    data = _adversarial_records(6000)  # ~0.8 MB: dozens of spans
+    assert_equal_stats(ctx.count_bytes(data).to_dict(), O.count(data, 100), "adversarial")
+
+
+def test_blank_line_shifts_phase_large(ctx):
+    """A stray blank line makes every following record start at line phase 1: guesses made on the
+    '@'/'+' pattern are wrong for all later spans (reference semantics are line-number based)."""
+    rng = np.random.default_rng(21)
+    body = corpus.random_fastq(rng, 4000, min_len=50, max_len=150)
+    data = body[:100000] + b"\n" + body[100000:]
+    assert_equal_stats(ctx.count_bytes(data).to_dict(), O.count(data, 100), "blank-shift")
+
+
+def test_no_resync_possible(ctx):
+    """Spans that contain no '@'...'+' pattern at all (unknown phase -> counted only, then rescanned)."""
+    data = (b"ACGTNACGTN" * 9 + b"\n") * 40000  # 3.6 MB of anonymous lines
+    assert_equal_stats(ctx.count_bytes(data).to_dict(), O.count(data, 100), "no-pattern")
+    data = b"@x\n" + b"G" * 2_000_000 + b"\n+\n" + b"5" * 2_000_000 + b"\n" + corpus.random_fastq(np.random.default_rng(2), 500)
+    assert_equal_stats(ctx.count_bytes(data).to_dict(), O.count(data, 100), "two huge lines")
+
+
+def test_span_edges_with_crlf(ctx):
+    """CRLF records sized so that '\\r' / '\\n' pairs fall on span and tile boundaries."""
+    for pad in range(0, 6):
+        rec = b"@h\r\n" + b"ACGT" * 31 + b"\r\n+\r\n" + b"IIII" * 31 + b"\r\n"  # 260 bytes
+        data = b"A" * pad + b"\n" + rec * 3000
+        assert_equal_stats(ctx.count_bytes(data).to_dict(), O.count(data, 100), f"pad={pad}")
