@@ -89,7 +89,7 @@ struct TileMeta {
   int lo, hi;   // valid byte range of the tile
   int walker;   // 1: dense or high-byte tile -> generic bitmap walker
   int npieces;
-  int pad;
+  int nrec;     // relevant lines in rec[] (interior lines and, when it is one, the tail piece)
 };
 
 struct __align__(128) Smem {
@@ -99,6 +99,7 @@ struct __align__(128) Smem {
   uint32_t bitmap[2][BM_WORDS];      // bit b of word w: byte 32*w+b is '\n'
   uint16_t wordbase[2][BM_WORDS];    // newlines before bitmap word w
   uint16_t nl[2][NL_CAP];
+  uint32_t rec[2][NL_CAP / 2 + 2];   // relevant (sequence / quality) lines of a tile: start | length << 14
   uint32_t seq_len[POS_BINS + 1];
   uint32_t qual_len[POS_BINS + 1];
   uint32_t seq_log2[LOG2_BINS];
@@ -201,27 +202,46 @@ __device__ __forceinline__ void flush_pos_acc(Smem& sm, PosAcc& acc, int sub) {
 // funnel), `rem` = line bytes left from this lane's word on.  Bytes past the line end are forced to
 // 0 and counted in histogram bin 0 ("junk"); the caller keeps the junk total and subtracts it at the
 // end, so the step has no branches and no predicates.
+// IDP.4A byte selectors kept in registers (the compiler would otherwise re-materialise each
+// immediate with a UMOV in front of every IDP.4A)
+struct Sel {
+  uint32_t h0, h1, h2, h3;  // 128 << 8k : histogram address = byte_k * 128 + base
+  uint32_t p0, p1, p2, p3;  // 1 << 8k   : per-position sum += byte_k
+};
+__device__ __forceinline__ Sel make_sel() {
+  Sel s;
+  asm volatile("mov.u32 %0, 0x00000080;" : "=r"(s.h0));
+  asm volatile("mov.u32 %0, 0x00008000;" : "=r"(s.h1));
+  asm volatile("mov.u32 %0, 0x00800000;" : "=r"(s.h2));
+  asm volatile("mov.u32 %0, 0x80000000;" : "=r"(s.h3));
+  asm volatile("mov.u32 %0, 0x00000001;" : "=r"(s.p0));
+  asm volatile("mov.u32 %0, 0x00000100;" : "=r"(s.p1));
+  asm volatile("mov.u32 %0, 0x00010000;" : "=r"(s.p2));
+  asm volatile("mov.u32 %0, 0x01000000;" : "=r"(s.p3));
+  return s;
+}
+
 template <bool QUAL>
-__device__ __forceinline__ void line_step(uint32_t al, uint32_t sh, int rem, uint32_t hbase, uint32_t* acc4) {
+__device__ __forceinline__ void line_step(const Sel& k, uint32_t al, uint32_t sh, int rem, uint32_t hbase, uint32_t* acc4) {
   uint32_t w = __funnelshift_r(lds32(al), lds32(al + 4), sh);
   const int rc = min(max(rem, 0), 4);
   w &= __funnelshift_rc(0xFFFFFFFFu, 0u, 32 - 8 * rc);
-  red_inc(__dp4a(w, 0x00000080u, hbase));
-  red_inc(__dp4a(w, 0x00008000u, hbase));
-  red_inc(__dp4a(w, 0x00800000u, hbase));
-  red_inc(__dp4a(w, 0x80000000u, hbase));
+  red_inc(__dp4a(w, k.h0, hbase));
+  red_inc(__dp4a(w, k.h1, hbase));
+  red_inc(__dp4a(w, k.h2, hbase));
+  red_inc(__dp4a(w, k.h3, hbase));
   if (QUAL) {
-    acc4[0] = __dp4a(w, 0x00000001u, acc4[0]);
-    acc4[1] = __dp4a(w, 0x00000100u, acc4[1]);
-    acc4[2] = __dp4a(w, 0x00010000u, acc4[2]);
-    acc4[3] = __dp4a(w, 0x01000000u, acc4[3]);
+    acc4[0] = __dp4a(w, k.p0, acc4[0]);
+    acc4[1] = __dp4a(w, k.p1, acc4[1]);
+    acc4[2] = __dp4a(w, k.p2, acc4[2]);
+    acc4[3] = __dp4a(w, k.p3, acc4[3]);
   }
 }
 
 // Four lines of one class per warp (a quarter-warp each): n content bytes at shared address a0
 // (n == 0: this quarter-warp has no line).  Returns the histogram slots touched by this lane.
 template <bool QUAL>
-__device__ __forceinline__ uint32_t lines_fast(Smem& sm, uint32_t a0, int n, int sub, uint32_t hbase, PosAcc& acc) {
+__device__ __forceinline__ uint32_t lines_fast(Smem& sm, const Sel& k, uint32_t a0, int n, int sub, uint32_t hbase, PosAcc& acc) {
   const uint32_t sh = (a0 & 3u) * 8u;
   const uint32_t al = (a0 & ~3u) + 4u * sub;
   const int rem = n - 4 * sub;
@@ -229,11 +249,11 @@ __device__ __forceinline__ uint32_t lines_fast(Smem& sm, uint32_t a0, int n, int
   ms = max(ms, __shfl_xor_sync(0xffffffffu, ms, 8));
   ms = max(ms, __shfl_xor_sync(0xffffffffu, ms, 16));
   switch (ms) {  // warp-uniform
-    case 5: line_step<QUAL>(al + 128, sh, rem - 128, hbase, acc.a[4]);
-    case 4: line_step<QUAL>(al + 96, sh, rem - 96, hbase, acc.a[3]);
-    case 3: line_step<QUAL>(al + 64, sh, rem - 64, hbase, acc.a[2]);
-    case 2: line_step<QUAL>(al + 32, sh, rem - 32, hbase, acc.a[1]);
-    case 1: line_step<QUAL>(al, sh, rem, hbase, acc.a[0]);
+    case 5: line_step<QUAL>(k, al + 128, sh, rem - 128, hbase, acc.a[4]);
+    case 4: line_step<QUAL>(k, al + 96, sh, rem - 96, hbase, acc.a[3]);
+    case 3: line_step<QUAL>(k, al + 64, sh, rem - 64, hbase, acc.a[2]);
+    case 2: line_step<QUAL>(k, al + 32, sh, rem - 32, hbase, acc.a[1]);
+    case 1: line_step<QUAL>(k, al, sh, rem, hbase, acc.a[0]);
     default: break;
   }
   if (n > 32 * REG_STEPS) {  // positions beyond the register window (reads longer than 160)
@@ -408,6 +428,7 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
   for (int st = 0; st < REG_STEPS; st++)
 #pragma unroll
     for (int k = 0; k < 4; k++) acc.a[st][k] = 0;
+  const Sel ksel = make_sel();
   const uint32_t hb_seq = smem_u32(&sm.hist[0][0]) + 4u * lane;
   const uint32_t hb_qual = smem_u32(&sm.hist[1][0]) + 4u * lane;
   __syncthreads();
@@ -517,7 +538,7 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
         TileMeta& m = sm.meta[sb];
         if (tid == 0) {
           m.Lrel = Lrel; m.open = open; m.toff = toffB; m.T = (int)T; m.lo = loB; m.hi = hiB;
-          m.walker = walker ? 1 : 0; m.npieces = walker ? 0 : 2;
+          m.walker = walker ? 1 : 0; m.npieces = walker ? 0 : 2; m.nrec = 0;
           sm.hiflag[sb] = 0;
           sm.bytes_since_flush += (uint32_t)(hiB - loB);
         }
@@ -538,6 +559,9 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
         }
         if (walker) {
         } else if (!count_only) {
+          const uint32_t ph = (uint32_t)((phase + Lrel) & 3);  // class of the tile's line 0
+          const int jr0 = (ph & 1) ? 2 : 1;                    // first interior line with an odd class
+          const int R = (int)T > jr0 ? ((int)T - jr0 + 1) >> 1 : 0;
           if (tid == 0) {
             // head piece: the line open at the tile start continues up to the first newline;
             // tail piece: the line open at the tile end.  A '\r' directly before '\n' is dropped.
@@ -551,28 +575,40 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
             }
             sm.pieces[sb][0] = hp;
             Piece tp; tp.vs = 0; tp.ve = 0; tp.line = T; tp.pad = 0; tp.vpos = 0;
+            int nrec = R;
             if (T) {
               const int vs = last_nl + 1;
               int ve = hiB;
               if (ve > vs && buf[ve - 1] == '\r') { const int nx = byte_after_tile(a, m); if (nx == '\n' || nx < 0) ve--; }
-              tp.vs = vs; tp.ve = ve;
+              // the tail piece starts a line in this tile: when it has an odd class it is the next relevant
+              // line (line T), so it simply extends the record list; long ones stay cooperative pieces
+              const bool relevant = (int)T >= jr0 && (((int)T - jr0) & 1) == 0;
+              if (relevant && ve - vs <= LONG_SEG) { sm.rec[sb][R] = ve > vs ? ((uint32_t)vs | ((uint32_t)(ve - vs) << 14)) : 0u; nrec = R + 1; }
+              else { tp.vs = vs; tp.ve = ve; }
             }
             sm.pieces[sb][1] = tp;
+            m.nrec = nrec;
           }
-          // line-length tables of the lines that end in tile B; long interior lines join the pieces
+          // line-length tables of the lines that end in tile B, records of the relevant interior lines;
+          // long interior lines join the pieces
           for (int j = tid; j < (int)T; j += SCAN_THREADS) {
             const int e = (int)sm.nl[sb][j];
             const int s = j ? (int)sm.nl[sb][j - 1] + 1 : loB;
             const u64 lidx = Lrel + (u64)j;
-            const int cls = (int)((phase + lidx) & 3);
+            const int cls = (int)((ph + (uint32_t)j) & 3);
             if ((cls & 1) && lidx != 0) {
               const u64 raw = (j ? 0ull : open) + (u64)(e - s);
               const int cr = (raw > 0 && byte_before(a, buf, m, e) == '\r') ? 1 : 0;
               account_line_len(sm, cls, raw - (u64)cr, my_min, my_max);
-              if (j && e - s > LONG_SEG) {
-                const int q = atomicAdd(&m.npieces, 1);
-                Piece p; p.vs = s; p.ve = e - cr; p.line = (uint32_t)j; p.pad = 0; p.vpos = 0;
-                sm.pieces[sb][q] = p;
+              if (j) {
+                uint32_t n = (uint32_t)(e - cr - s);
+                if (e - s > LONG_SEG) {
+                  const int q = atomicAdd(&m.npieces, 1);
+                  Piece p; p.vs = s; p.ve = e - cr; p.line = (uint32_t)j; p.pad = 0; p.vpos = 0;
+                  sm.pieces[sb][q] = p;
+                  n = 0;
+                }
+                sm.rec[sb][(j - jr0) >> 1] = (uint32_t)s | (n << 14);
               }
             }
           }
@@ -591,36 +627,35 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
         if (m.walker) {
           tile_walker(sm, a, buf, m, phase, sm.bitmap[sc], sm.wordbase[sc], wr, WORK_THREADS, my_min, my_max);
         } else {
-          const int T = m.T;
           const uint32_t ph = (uint32_t)((phase + m.Lrel) & 3);  // class of the tile's line 0
-          // interior lines 1..T-1 with an odd class; relevant line r is j = jr0 + 2r.  A warp takes the
-          // four even (or the four odd) relevant lines of a group of eight: one class per warp.
+          // relevant line r (record r) is tile line jr0 + 2r; its class alternates with r.  A warp takes
+          // the four even (or the four odd) records of a group of eight: one class per warp.
           const int jr0 = (ph & 1) ? 2 : 1;
-          const int R = T > jr0 ? (T - jr0 + 1) >> 1 : 0;
+          const int R = m.nrec;
           const int ww = warp - SCAN_WARPS, qi = lane >> 3;
           for (int u = ww; 8 * (u >> 1) + (u & 1) < R; u += WORK_WARPS) {  // task u: group u>>1, parity u&1
             const int r = 8 * (u >> 1) + 2 * qi + (u & 1);
-            const int j = jr0 + 2 * r;
             const bool qual = ((ph + (uint32_t)(jr0 + 2 * (u & 1))) & 3) == 3;  // warp-uniform
-            int n = 0;
-            uint32_t a0 = buf_s;
-            if (r < R) {
-              const int s = (int)sm.nl[sc][j - 1] + 1;
-              const int e = (int)sm.nl[sc][j];
-              const int cr = (e > s && buf[e - 1] == '\r') ? 1 : 0;
-              if (e - s <= LONG_SEG) { n = e - cr - s; a0 = buf_s + (uint32_t)s; }
-            }
-            if (qual) { slots[1] += lines_fast<true>(sm, a0, n, sub, hb_qual, acc); if (sub == 0) valid[1] += (u64)min(n, 32 * REG_STEPS); }
-            else { slots[0] += lines_fast<false>(sm, a0, n, sub, hb_seq, acc); if (sub == 0) valid[0] += (u64)min(n, 32 * REG_STEPS); }
+            const uint32_t rc = r < R ? sm.rec[sc][r] : 0u;
+            const int n = (int)(rc >> 14);
+            const uint32_t a0 = buf_s + (rc & 0x3FFFu);
+            if (qual) { slots[1] += lines_fast<true>(sm, ksel, a0, n, sub, hb_qual, acc); if (sub == 0) valid[1] += (u64)min(n, 32 * REG_STEPS); }
+            else { slots[0] += lines_fast<false>(sm, ksel, a0, n, sub, hb_seq, acc); if (sub == 0) valid[0] += (u64)min(n, 32 * REG_STEPS); }
           }
-          // pieces: head / tail of the tile and long lines, all worker threads together
+          // pieces: a short one is taken by a single warp, a long one by all worker threads together
           const int np = m.npieces;
           for (int k = 0; k < np; k++) {
             const Piece p = sm.pieces[sc][k];
             const u64 lidx = m.Lrel + p.line;
             const int cls = (int)((phase + lidx) & 3);
-            if (!(cls & 1) || lidx == 0 || p.ve <= p.vs) continue;
-            piece_coop(sm, buf, p.vs, p.ve, p.vpos, cls, cls == 3 ? hb_qual : hb_seq, wr, WORK_THREADS);
+            const int len = p.ve - p.vs;
+            if (!(cls & 1) || lidx == 0 || len <= 0) continue;
+            if (len <= 512) {
+              if (ww == (k + (int)(m.toff >> 14)) % WORK_WARPS)
+                for (int o = p.vs + lane; o < p.ve; o += 32) account_byte(sm.ghist, sm.pos_sum, cls, buf[o], p.vpos + (u64)(o - p.vs));
+            } else {
+              piece_coop(sm, buf, p.vs, p.ve, p.vpos, cls, cls == 3 ? hb_qual : hb_seq, wr, WORK_THREADS);
+            }
           }
         }
       }
@@ -876,47 +911,77 @@ __device__ __forceinline__ void meta_fold(long long& qmin, long long& qmax, unsi
   }
 }
 
-__global__ void fq_meta_kernel(const uint8_t* __restrict__ p, u64 n, Carry* __restrict__ carry, u64 meta_records) {
+// One warp, 512 bytes per iteration (16 per lane): newline masks by SWAR, the segments between
+// newlines are reduced with warp min/max; only quality lines (0-based index % 4 == 3) are examined.
+__global__ void fq_meta_kernel(const uint8_t* __restrict__ base, uint32_t lo0, u64 end, Carry* __restrict__ carry, u64 meta_records) {
   const int lane = threadIdx.x;
   const u64 limit = meta_records * 4;
   u64 ml = carry->meta_lines;
-  if (ml >= limit || n == 0) return;
+  if (ml >= limit || end <= (u64)lo0) return;
   long long qmin = carry->qual_min, qmax = carry->qual_max;
   unsigned status = carry->meta_status;
   int cur_has = carry->cur_has, cur_min = carry->cur_min, cur_max = carry->cur_max;
-  if (carry->meta_pending_cr && p[0] != '\n') {  // the '\r' that ended the previous chunk was content
+  if (carry->meta_pending_cr && base[lo0] != '\n') {  // the '\r' that ended the previous chunk was content
     if (!cur_has) { cur_has = 1; cur_min = -1; cur_max = -1; } else { cur_min = -1; }
   }
   unsigned pending = 0;
   bool done = false;
-  for (u64 o = 0; o < n && !done; o += 32) {
-    const u64 idx = o + lane;
-    const bool valid = idx < n;
-    const uint32_t b = valid ? p[idx] : 0u;
-    const uint32_t nxt = (idx + 1 < n) ? p[idx + 1] : 0x100u;
-    const bool is_nl = valid && b == '\n';
-    const bool pend = valid && b == '\r' && idx + 1 == n;
-    const bool contributes = valid && !is_nl && !(b == '\r' && nxt == '\n') && !pend;
-    const int q = (b >= 33 && b <= 126) ? (int)b - 33 : -1;
-    uint32_t nlmask = __ballot_sync(0xffffffffu, is_nl);
-    if (__ballot_sync(0xffffffffu, pend)) pending = 1;
-    int start = 0;
+  for (u64 o = 0; o < end && !done; o += 512) {
+    const u64 g = o + (u64)lane * 16;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (g < end) v = *reinterpret_cast<const uint4*>(base + g);
+    // valid byte range of this lane: [va, vb) within its 16 bytes
+    int va = g >= (u64)lo0 ? 0 : (int)min((u64)16, (u64)lo0 - g);
+    int vb = g + 16 <= end ? 16 : (g < end ? (int)(end - g) : 0);
+    uint32_t nlm = nl_mask16(v) & ((1u << vb) - 1u) & ~((1u << va) - 1u);
+    // byte following this lane's 16 (for the '\r' rule): next lane's first byte, or memory, or none
+    uint32_t nxt = __shfl_down_sync(0xffffffffu, v.x & 0xFFu, 1);
+    if (lane == 31) nxt = (g + 16 < end) ? (uint32_t)base[g + 16] : 0u;
+    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+    uint32_t lanes_nl = __ballot_sync(0xffffffffu, nlm != 0);
+    int seg_lane = 0, seg_k = 0;  // current segment starts at (lane, byte) = (seg_lane, seg_k)
     for (;;) {
-      const int endl = nlmask ? (__ffs(nlmask) - 1) : 32;
-      const bool inseg = contributes && lane >= start && lane < endl;
-      if (__ballot_sync(0xffffffffu, inseg)) {
-        const int mn = __reduce_min_sync(0xffffffffu, inseg ? q : 0x7fffffff);
-        const int mx = __reduce_max_sync(0xffffffffu, inseg ? q : -0x7fffffff);
-        if (!cur_has) { cur_has = 1; cur_min = mn; cur_max = mx; }
-        else { cur_min = mn < cur_min ? mn : cur_min; cur_max = mx > cur_max ? mx : cur_max; }
+      // next newline at or after the segment start
+      int nl_lane = 32, nl_k = 0;
+      if (lanes_nl) {
+        nl_lane = __ffs(lanes_nl) - 1;
+        const uint32_t m = __shfl_sync(0xffffffffu, nlm, nl_lane);
+        nl_k = __ffs(m) - 1;
       }
-      if (endl == 32) break;
+      if ((ml & 3) == 3) {  // quality line: min/max of qual_to_int over [segment start, newline or window end)
+        int a = lane < seg_lane ? 16 : (lane == seg_lane ? seg_k : 0);
+        int b = lane > nl_lane ? 0 : (lane == nl_lane ? nl_k : 16);
+        a = max(a, va); b = min(b, vb);
+        int mn = 0x7fffffff, mx = -0x7fffffff;
+        for (int k = a; k < b; k++) {
+          const uint32_t c = (w4[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+          if (c == '\r') {
+            if (g + (u64)k + 1 >= end) { pending = 1; continue; }  // last byte of the chunk: decided later
+            const uint32_t nx = k < 15 ? ((w4[(k + 1) >> 2] >> (8 * ((k + 1) & 3))) & 0xFFu) : nxt;
+            if (nx == '\n') continue;                              // dropped: directly before the newline
+          }
+          const int q = (c >= 33 && c <= 126) ? (int)c - 33 : -1;
+          mn = min(mn, q); mx = max(mx, q);
+        }
+        mn = __reduce_min_sync(0xffffffffu, mn);
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        pending = __reduce_max_sync(0xffffffffu, pending);
+        if (mn != 0x7fffffff) {
+          if (!cur_has) { cur_has = 1; cur_min = mn; cur_max = mx; }
+          else { cur_min = min(cur_min, mn); cur_max = max(cur_max, mx); }
+        }
+      }
+      if (nl_lane == 32) break;
       if ((ml & 3) == 3 && status == FQGPU_META_OK) meta_fold(qmin, qmax, status, cur_has, cur_min, cur_max);
       ml++;
       cur_has = 0;
+      pending = 0;
       if (ml >= limit) { done = true; break; }
-      nlmask &= nlmask - 1;
-      start = endl + 1;
+      // consume this newline
+      if (lane == nl_lane) nlm &= nlm - 1;
+      lanes_nl = __ballot_sync(0xffffffffu, nlm != 0);
+      seg_lane = nl_lane; seg_k = nl_k + 1;
+      if (seg_k == 16) { seg_lane++; seg_k = 0; }
     }
   }
   if (lane == 0) {
@@ -961,7 +1026,7 @@ cudaError_t launch_scan(const void* ptr, size_t nbytes, SpanDesc* desc, LaunchHd
   a.tps = (a.ntiles + nspans - 1) / nspans;
   a.nspans = (a.ntiles + a.tps - 1) / a.tps;
   a.desc = desc; a.hdr = hdr; a.carry = carry; a.pending = pending; a.committed = committed; a.dbg = dbg;
-  if (meta_records) fq_meta_kernel<<<1, 32, 0, st>>>((const uint8_t*)ptr, nbytes, carry, meta_records);
+  if (meta_records) fq_meta_kernel<<<1, 32, 0, st>>>(a.base, a.lo0, a.end, carry, meta_records);
   fq_resync_kernel<<<a.nspans, 32, 0, st>>>(a);
   fq_scan_kernel<<<a.nspans, THREADS, sizeof(Smem), st>>>(a, 0);
   fq_stitch_kernel<<<a.nspans, STITCH_THREADS, 0, st>>>(a);
