@@ -74,6 +74,13 @@ struct ScanArgs {
   uint32_t dbg;
 };
 
+// IDP.4A byte selectors.  Loaded once from shared memory into registers: as immediates or kernel
+// parameters the compiler re-materialises each of them (UMOV / LDCU) in front of every IDP.4A.
+struct Sel {
+  uint32_t h0, h1, h2, h3;  // 128 << 8k : histogram address = byte_k * 128 + base
+  uint32_t p0, p1, p2, p3;  // 1 << 8k   : per-position sum += byte_k
+};
+
 struct Piece {  // a run of content bytes handled cooperatively: [vs, ve) of the tile
   int vs, ve;
   uint32_t line;  // tile-relative line index
@@ -113,6 +120,7 @@ struct __align__(128) Smem {
   u64 run_L, run_open;               // span-running newline count / open-line bytes
   u64 head_len, junk[2];
   uint32_t bytes_since_flush, hiflag[2], head_done;
+  uint32_t ksel[8];
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -202,30 +210,14 @@ __device__ __forceinline__ void flush_pos_acc(Smem& sm, PosAcc& acc, int sub) {
 // funnel), `rem` = line bytes left from this lane's word on.  Bytes past the line end are forced to
 // 0 and counted in histogram bin 0 ("junk"); the caller keeps the junk total and subtracts it at the
 // end, so the step has no branches and no predicates.
-// IDP.4A byte selectors kept in registers (the compiler would otherwise re-materialise each
-// immediate with a UMOV in front of every IDP.4A)
-struct Sel {
-  uint32_t h0, h1, h2, h3;  // 128 << 8k : histogram address = byte_k * 128 + base
-  uint32_t p0, p1, p2, p3;  // 1 << 8k   : per-position sum += byte_k
-};
-__device__ __forceinline__ Sel make_sel() {
-  Sel s;
-  asm volatile("mov.u32 %0, 0x00000080;" : "=r"(s.h0));
-  asm volatile("mov.u32 %0, 0x00008000;" : "=r"(s.h1));
-  asm volatile("mov.u32 %0, 0x00800000;" : "=r"(s.h2));
-  asm volatile("mov.u32 %0, 0x80000000;" : "=r"(s.h3));
-  asm volatile("mov.u32 %0, 0x00000001;" : "=r"(s.p0));
-  asm volatile("mov.u32 %0, 0x00000100;" : "=r"(s.p1));
-  asm volatile("mov.u32 %0, 0x00010000;" : "=r"(s.p2));
-  asm volatile("mov.u32 %0, 0x01000000;" : "=r"(s.p3));
-  return s;
-}
-
-template <bool QUAL>
-__device__ __forceinline__ void line_step(const Sel& k, uint32_t al, uint32_t sh, int rem, uint32_t hbase, uint32_t* acc4) {
+// One 32-byte step of a line for one quarter-warp lane: 4 line bytes at shared address al (+4 for the
+// funnel).  MASKED steps force the bytes past the line end to 0; those are counted in histogram bin 0
+// ("junk"), the caller keeps the junk total and subtracts it at the end -- no predicates in the step.
+// msh = 32 - 8*(line bytes left from this lane's word on): <= 0 full word, >= 32 nothing left.
+template <bool QUAL, bool MASKED>
+__device__ __forceinline__ void line_step(const Sel& k, uint32_t al, uint32_t sh, int msh, uint32_t hbase, uint32_t* acc4) {
   uint32_t w = __funnelshift_r(lds32(al), lds32(al + 4), sh);
-  const int rc = min(max(rem, 0), 4);
-  w &= __funnelshift_rc(0xFFFFFFFFu, 0u, 32 - 8 * rc);
+  if (MASKED) w &= __funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t)min(max(msh, 0), 32));
   red_inc(__dp4a(w, k.h0, hbase));
   red_inc(__dp4a(w, k.h1, hbase));
   red_inc(__dp4a(w, k.h2, hbase));
@@ -239,22 +231,35 @@ __device__ __forceinline__ void line_step(const Sel& k, uint32_t al, uint32_t sh
 }
 
 // Four lines of one class per warp (a quarter-warp each): n content bytes at shared address a0
-// (n == 0: this quarter-warp has no line).  Returns the histogram slots touched by this lane.
+// (n == 0: this quarter-warp has no line).  Steps that are full for all four lines run unmasked.
+// Returns the histogram slots touched by this lane.
 template <bool QUAL>
 __device__ __forceinline__ uint32_t lines_fast(Smem& sm, const Sel& k, uint32_t a0, int n, int sub, uint32_t hbase, PosAcc& acc) {
   const uint32_t sh = (a0 & 3u) * 8u;
   const uint32_t al = (a0 & ~3u) + 4u * sub;
   const int rem = n - 4 * sub;
-  int ms = min((n + 31) >> 5, REG_STEPS);      // steps in the register window, maximum over the warp's four lines
-  ms = max(ms, __shfl_xor_sync(0xffffffffu, ms, 8));
-  ms = max(ms, __shfl_xor_sync(0xffffffffu, ms, 16));
-  switch (ms) {  // warp-uniform
-    case 5: line_step<QUAL>(k, al + 128, sh, rem - 128, hbase, acc.a[4]);
-    case 4: line_step<QUAL>(k, al + 96, sh, rem - 96, hbase, acc.a[3]);
-    case 3: line_step<QUAL>(k, al + 64, sh, rem - 64, hbase, acc.a[2]);
-    case 2: line_step<QUAL>(k, al + 32, sh, rem - 32, hbase, acc.a[1]);
-    case 1: line_step<QUAL>(k, al, sh, rem, hbase, acc.a[0]);
+  const int msh = 32 - 8 * rem;  // mask shift of step 0; each step adds 256
+  // packed warp reduction: steps in the register window (max over the four lines) and full steps (min)
+  int ms = min((n + 31) >> 5, REG_STEPS), nf = min(n >> 5, REG_STEPS);
+  int pk = (ms << 8) | (REG_STEPS - nf);  // max of both fields at once
+  pk = max(pk & 0xFF00, __shfl_xor_sync(0xffffffffu, pk, 8) & 0xFF00) | max(pk & 0xFF, __shfl_xor_sync(0xffffffffu, pk, 8) & 0xFF);
+  pk = max(pk & 0xFF00, __shfl_xor_sync(0xffffffffu, pk, 16) & 0xFF00) | max(pk & 0xFF, __shfl_xor_sync(0xffffffffu, pk, 16) & 0xFF);
+  ms = pk >> 8;
+  nf = REG_STEPS - (pk & 0xFF);
+  switch (nf) {  // warp-uniform: steps [0, nf) are full words for every lane
+    case 5: line_step<QUAL, false>(k, al + 128, sh, 0, hbase, acc.a[4]);
+    case 4: line_step<QUAL, false>(k, al + 96, sh, 0, hbase, acc.a[3]);
+    case 3: line_step<QUAL, false>(k, al + 64, sh, 0, hbase, acc.a[2]);
+    case 2: line_step<QUAL, false>(k, al + 32, sh, 0, hbase, acc.a[1]);
+    case 1: line_step<QUAL, false>(k, al, sh, 0, hbase, acc.a[0]);
     default: break;
+  }
+  if (ms > nf) {  // steps [nf, ms): some lane is partial or past its line end
+    if (nf <= 0 && ms > 0) line_step<QUAL, true>(k, al, sh, msh, hbase, acc.a[0]);
+    if (nf <= 1 && ms > 1) line_step<QUAL, true>(k, al + 32, sh, msh + 256, hbase, acc.a[1]);
+    if (nf <= 2 && ms > 2) line_step<QUAL, true>(k, al + 64, sh, msh + 512, hbase, acc.a[2]);
+    if (nf <= 3 && ms > 3) line_step<QUAL, true>(k, al + 96, sh, msh + 768, hbase, acc.a[3]);
+    if (nf <= 4 && ms > 4) line_step<QUAL, true>(k, al + 128, sh, msh + 1024, hbase, acc.a[4]);
   }
   if (n > 32 * REG_STEPS) {  // positions beyond the register window (reads longer than 160)
     uint32_t a2 = al + 32 * REG_STEPS;
@@ -262,12 +267,12 @@ __device__ __forceinline__ uint32_t lines_fast(Smem& sm, const Sel& k, uint32_t 
     for (int base = 32 * REG_STEPS; base < n; base += 32) {
       const uint32_t w = __funnelshift_r(lds32(a2), lds32(a2 + 4), sh);
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        if (r2 > k) {
-          const uint32_t b = (w >> (8 * k)) & 0xFFu;
+      for (int kk = 0; kk < 4; kk++) {
+        if (r2 > kk) {
+          const uint32_t b = (w >> (8 * kk)) & 0xFFu;
           red_inc(hbase + (b << 7));
           if (QUAL) {
-            const int p = base + 4 * sub + k;
+            const int p = base + 4 * sub + kk;
             atomicAdd(&sm.pos_sum[p < POS_BINS ? p : POS_BINS], b);
           }
         }
@@ -412,6 +417,7 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
     sm.hiflag[0] = sm.hiflag[1] = 0;
     sm.run_L = 0; sm.run_open = 0; sm.head_len = 0; sm.head_done = 0;
     sm.junk[0] = sm.junk[1] = 0;
+    for (int k = 0; k < 4; k++) { sm.ksel[k] = 0x80u << (8 * k); sm.ksel[4 + k] = 1u << (8 * k); }
     for (int s = 0; s < NSTAGE; s++) mbar_init(&sm.full_bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (t0 < t1) {  // prologue: the first tile into stage 0
@@ -428,10 +434,15 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
   for (int st = 0; st < REG_STEPS; st++)
 #pragma unroll
     for (int k = 0; k < 4; k++) acc.a[st][k] = 0;
-  const Sel ksel = make_sel();
   const uint32_t hb_seq = smem_u32(&sm.hist[0][0]) + 4u * lane;
   const uint32_t hb_qual = smem_u32(&sm.hist[1][0]) + 4u * lane;
   __syncthreads();
+  Sel ksel;
+  {
+    const uint32_t ks = smem_u32(&sm.ksel[0]);
+    ksel.h0 = lds32(ks); ksel.h1 = lds32(ks + 4); ksel.h2 = lds32(ks + 8); ksel.h3 = lds32(ks + 12);
+    ksel.p0 = lds32(ks + 16); ksel.p1 = lds32(ks + 20); ksel.p2 = lds32(ks + 24); ksel.p3 = lds32(ks + 28);
+  }
 
   // pipeline: iteration `it` classifies tile B = t0+it (stage it%3, slot it&1) while the workers
   // take tile C = B-1; the TMA of tile A = B+1 is started at the top.
@@ -633,14 +644,24 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
           const int jr0 = (ph & 1) ? 2 : 1;
           const int R = m.nrec;
           const int ww = warp - SCAN_WARPS, qi = lane >> 3;
-          for (int u = ww; 8 * (u >> 1) + (u & 1) < R; u += WORK_WARPS) {  // task u: group u>>1, parity u&1
-            const int r = 8 * (u >> 1) + 2 * qi + (u & 1);
-            const bool qual = ((ph + (uint32_t)(jr0 + 2 * (u & 1))) & 3) == 3;  // warp-uniform
-            const uint32_t rc = r < R ? sm.rec[sc][r] : 0u;
-            const int n = (int)(rc >> 14);
-            const uint32_t a0 = buf_s + (rc & 0x3FFFu);
-            if (qual) { slots[1] += lines_fast<true>(sm, ksel, a0, n, sub, hb_qual, acc); if (sub == 0) valid[1] += (u64)min(n, 32 * REG_STEPS); }
-            else { slots[0] += lines_fast<false>(sm, ksel, a0, n, sub, hb_seq, acc); if (sub == 0) valid[0] += (u64)min(n, 32 * REG_STEPS); }
+          static_assert((WORK_WARPS & 1) == 0, "a warp keeps its record parity (= class) for the whole tile");
+          const bool qual = ((ph + (uint32_t)(jr0 + 2 * (ww & 1))) & 3) == 3;  // warp-uniform, same for all its tasks
+          const uint32_t rec_s = smem_u32(&sm.rec[sc][0]);
+          // task: records 8g + 2*qi + (ww & 1), g = ww>>1, ww>>1 + WORK_WARPS/2, ...
+          if (qual) {
+            for (int r = 8 * (ww >> 1) + (ww & 1) + 2 * qi; r - 2 * qi < R; r += 4 * WORK_WARPS) {
+              const uint32_t rc = r < R ? lds32(rec_s + 4u * (uint32_t)r) : 0u;
+              const int n = (int)(rc >> 14);
+              slots[1] += lines_fast<true>(sm, ksel, buf_s + (rc & 0x3FFFu), n, sub, hb_qual, acc);
+              if (sub == 0) valid[1] += (u64)min(n, 32 * REG_STEPS);
+            }
+          } else {
+            for (int r = 8 * (ww >> 1) + (ww & 1) + 2 * qi; r - 2 * qi < R; r += 4 * WORK_WARPS) {
+              const uint32_t rc = r < R ? lds32(rec_s + 4u * (uint32_t)r) : 0u;
+              const int n = (int)(rc >> 14);
+              slots[0] += lines_fast<false>(sm, ksel, buf_s + (rc & 0x3FFFu), n, sub, hb_seq, acc);
+              if (sub == 0) valid[0] += (u64)min(n, 32 * REG_STEPS);
+            }
           }
           // pieces: a short one is taken by a single warp, a long one by all worker threads together
           const int np = m.npieces;
@@ -1026,6 +1047,7 @@ cudaError_t launch_scan(const void* ptr, size_t nbytes, SpanDesc* desc, LaunchHd
   a.tps = (a.ntiles + nspans - 1) / nspans;
   a.nspans = (a.ntiles + a.tps - 1) / a.tps;
   a.desc = desc; a.hdr = hdr; a.carry = carry; a.pending = pending; a.committed = committed; a.dbg = dbg;
+
   if (meta_records) fq_meta_kernel<<<1, 32, 0, st>>>(a.base, a.lo0, a.end, carry, meta_records);
   fq_resync_kernel<<<a.nspans, 32, 0, st>>>(a);
   fq_scan_kernel<<<a.nspans, THREADS, sizeof(Smem), st>>>(a, 0);
