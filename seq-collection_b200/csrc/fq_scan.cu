@@ -32,6 +32,7 @@
 // streams.lines: split at '\n', drop one '\r' directly before it; the trailing unterminated line is
 // accounted by the host from fq::Carry at finish().
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -239,14 +240,10 @@ __device__ __forceinline__ uint32_t lines_fast(Smem& sm, const Sel& k, uint32_t 
   const uint32_t al = (a0 & ~3u) + 4u * sub;
   const int rem = n - 4 * sub;
   const int msh = 32 - 8 * rem;  // mask shift of step 0; each step adds 256
-  // packed warp reduction: steps in the register window (max over the four lines) and full steps (min)
-  int ms = min((n + 31) >> 5, REG_STEPS), nf = min(n >> 5, REG_STEPS);
-  int pk = (ms << 8) | (REG_STEPS - nf);  // max of both fields at once
-  pk = max(pk & 0xFF00, __shfl_xor_sync(0xffffffffu, pk, 8) & 0xFF00) | max(pk & 0xFF, __shfl_xor_sync(0xffffffffu, pk, 8) & 0xFF);
-  pk = max(pk & 0xFF00, __shfl_xor_sync(0xffffffffu, pk, 16) & 0xFF00) | max(pk & 0xFF, __shfl_xor_sync(0xffffffffu, pk, 16) & 0xFF);
-  ms = pk >> 8;
-  nf = REG_STEPS - (pk & 0xFF);
-  switch (nf) {  // warp-uniform: steps [0, nf) are full words for every lane
+  // steps in the register window: nf full ones, then at most one partial one (ms - nf <= 1).  The
+  // four lines of a warp usually have the same length, so this per-quarter-warp control flow rarely diverges.
+  const int ms = min((n + 31) >> 5, REG_STEPS), nf = min(n >> 5, REG_STEPS);
+  switch (nf) {
     case 5: line_step<QUAL, false>(k, al + 128, sh, 0, hbase, acc.a[4]);
     case 4: line_step<QUAL, false>(k, al + 96, sh, 0, hbase, acc.a[3]);
     case 3: line_step<QUAL, false>(k, al + 64, sh, 0, hbase, acc.a[2]);
@@ -254,12 +251,14 @@ __device__ __forceinline__ uint32_t lines_fast(Smem& sm, const Sel& k, uint32_t 
     case 1: line_step<QUAL, false>(k, al, sh, 0, hbase, acc.a[0]);
     default: break;
   }
-  if (ms > nf) {  // steps [nf, ms): some lane is partial or past its line end
-    if (nf <= 0 && ms > 0) line_step<QUAL, true>(k, al, sh, msh, hbase, acc.a[0]);
-    if (nf <= 1 && ms > 1) line_step<QUAL, true>(k, al + 32, sh, msh + 256, hbase, acc.a[1]);
-    if (nf <= 2 && ms > 2) line_step<QUAL, true>(k, al + 64, sh, msh + 512, hbase, acc.a[2]);
-    if (nf <= 3 && ms > 3) line_step<QUAL, true>(k, al + 96, sh, msh + 768, hbase, acc.a[3]);
-    if (nf <= 4 && ms > 4) line_step<QUAL, true>(k, al + 128, sh, msh + 1024, hbase, acc.a[4]);
+  if (ms > nf) {
+    switch (nf) {
+      case 0: line_step<QUAL, true>(k, al, sh, msh, hbase, acc.a[0]); break;
+      case 1: line_step<QUAL, true>(k, al + 32, sh, msh + 256, hbase, acc.a[1]); break;
+      case 2: line_step<QUAL, true>(k, al + 64, sh, msh + 512, hbase, acc.a[2]); break;
+      case 3: line_step<QUAL, true>(k, al + 96, sh, msh + 768, hbase, acc.a[3]); break;
+      default: line_step<QUAL, true>(k, al + 128, sh, msh + 1024, hbase, acc.a[4]); break;
+    }
   }
   if (n > 32 * REG_STEPS) {  // positions beyond the register window (reads longer than 160)
     uint32_t a2 = al + 32 * REG_STEPS;
@@ -434,12 +433,13 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
   for (int st = 0; st < REG_STEPS; st++)
 #pragma unroll
     for (int k = 0; k < 4; k++) acc.a[st][k] = 0;
-  const uint32_t hb_seq = smem_u32(&sm.hist[0][0]) + 4u * lane;
-  const uint32_t hb_qual = smem_u32(&sm.hist[1][0]) + 4u * lane;
+  const uint32_t sm0 = smem_u32(smem_raw);
+  const uint32_t hb_seq = sm0 + (uint32_t)offsetof(Smem, hist) + 4u * lane;
+  const uint32_t hb_qual = hb_seq + HB * 32 * 4;
   __syncthreads();
   Sel ksel;
   {
-    const uint32_t ks = smem_u32(&sm.ksel[0]);
+    const uint32_t ks = sm0 + (uint32_t)offsetof(Smem, ksel);
     ksel.h0 = lds32(ks); ksel.h1 = lds32(ks + 4); ksel.h2 = lds32(ks + 8); ksel.h3 = lds32(ks + 12);
     ksel.p0 = lds32(ks + 16); ksel.p1 = lds32(ks + 20); ksel.p2 = lds32(ks + 24); ksel.p3 = lds32(ks + 28);
   }
@@ -448,15 +448,15 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
   // take tile C = B-1; the TMA of tile A = B+1 is started at the top.
   const int nt = (int)(t1 - t0);
   uint32_t par_bits = 0;  // mbarrier parity per stage (bit s)
+  int stB = 0, stC = 2, stA = 1;  // stages of tiles B, C, A; rotated at the end of every iteration
   for (int it = 0; it <= nt; it++) {
     const int sb = it & 1, sc = sb ^ 1;
-    const int stB = it % NSTAGE, stC = (it + NSTAGE - 1) % NSTAGE, stA = (it + 1) % NSTAGE;
     const bool haveB = it < nt, haveC = it > 0;
     const uint32_t tileB = t0 + (uint32_t)it;
 
     if (tid == 0 && it + 1 < nt) {  // stage stA held tile B-2, whose K2 finished last iteration
       const u64 noff = (u64)(tileB + 1) * TILE;
-      const uint32_t bytes = (uint32_t)((((a.end - noff) < (u64)TILE ? (a.end - noff) : (u64)TILE) + 15) & ~15ull);
+      const uint32_t bytes = (tileB + 2 < a.ntiles) ? (uint32_t)TILE : (uint32_t)(((a.end - noff) + 15) & ~15ull);
       mbar_expect_tx(&sm.full_bar[stA], bytes);
       tma_load_1d(&sm.buf[stA][PAD], a.base + noff, bytes, &sm.full_bar[stA]);
     }
@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
     const u64 toffB = (u64)tileB * TILE;
     if (haveB) {
       loB = (tileB == 0) ? (int)a.lo0 : 0;
-      hiB = (int)((a.end - toffB) < (u64)TILE ? (a.end - toffB) : (u64)TILE);
+      hiB = (tileB + 1 < a.ntiles) ? TILE : (int)(a.end - toffB);
       mbar_wait(&sm.full_bar[stB], (par_bits >> stB) & 1u);
       par_bits ^= 1u << stB;
       const uint8_t* buf = &sm.buf[stB][PAD];
@@ -633,7 +633,7 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
       if (haveC && !count_only) {
         const TileMeta& m = sm.meta[sc];
         const uint8_t* buf = &sm.buf[stC][PAD];
-        const uint32_t buf_s = smem_u32(buf);
+        const uint32_t buf_s = sm0 + (uint32_t)offsetof(Smem, buf) + (uint32_t)stC * STAGE_BYTES + PAD;
         const int wr = tid - SCAN_THREADS;  // worker rank
         if (m.walker) {
           tile_walker(sm, a, buf, m, phase, sm.bitmap[sc], sm.wordbase[sc], wr, WORK_THREADS, my_min, my_max);
@@ -646,7 +646,7 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
           const int ww = warp - SCAN_WARPS, qi = lane >> 3;
           static_assert((WORK_WARPS & 1) == 0, "a warp keeps its record parity (= class) for the whole tile");
           const bool qual = ((ph + (uint32_t)(jr0 + 2 * (ww & 1))) & 3) == 3;  // warp-uniform, same for all its tasks
-          const uint32_t rec_s = smem_u32(&sm.rec[sc][0]);
+          const uint32_t rec_s = sm0 + (uint32_t)offsetof(Smem, rec) + (uint32_t)sc * (uint32_t)sizeof(sm.rec[0]);
           // task: records 8g + 2*qi + (ww & 1), g = ww>>1, ww>>1 + WORK_WARPS/2, ...
           if (qual) {
             for (int r = 8 * (ww >> 1) + (ww & 1) + 2 * qi; r - 2 * qi < R; r += 4 * WORK_WARPS) {
@@ -683,6 +683,7 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
     }
 
     // ---- end of iteration: tile C is consumed, B becomes C ----
+    { const int t = stC; stC = stB; stB = stA; stA = t; }
     __syncthreads();
     if (sm.bytes_since_flush > (1u << 24)) {  // keep the 32-bit per-position sums from overflowing
       flush_pos_acc(sm, acc, sub);
