@@ -810,13 +810,30 @@ __global__ void __launch_bounds__(STITCH_THREADS) fq_stitch_kernel(const ScanArg
   const LaunchHdr& h = *a.hdr;
   auto span_begin = [&](int c) -> u64 { return c == 0 ? (u64)a.lo0 : (u64)c * a.tps * TILE; };
   auto span_end = [&](int c) -> u64 { const u64 e = (u64)(c + 1) * a.tps * TILE; return e < a.end ? e : a.end; };
+  // exact prefix over the earlier spans: G = lines before this span, P0 = open-line bytes before it
+  // (tail of the last earlier span that has a newline, plus the lengths of the newline-free spans after it)
+  __shared__ u64 s_sumT[STITCH_THREADS / 32], s_sumL[STITCH_THREADS / 32];
+  __shared__ int s_last[STITCH_THREADS / 32];
+  {
+    u64 myT = 0;
+    int mylast = -1;
+    for (int c = tid; c < span; c += STITCH_THREADS) { const u64 T = a.desc[c].T; myT += T; if (T) mylast = c; }
+    for (int d = 16; d > 0; d >>= 1) { myT += __shfl_xor_sync(0xffffffffu, myT, d); mylast = max(mylast, __shfl_xor_sync(0xffffffffu, mylast, d)); }
+    if ((tid & 31) == 0) { s_sumT[tid >> 5] = myT; s_last[tid >> 5] = mylast; }
+    __syncthreads();
+    int last = -1;
+    for (int w = 0; w < STITCH_THREADS / 32; w++) last = max(last, s_last[w]);
+    u64 myL = 0;
+    for (int c = last + 1 + tid; c < span; c += STITCH_THREADS) myL += span_end(c) - span_begin(c);
+    for (int d = 16; d > 0; d >>= 1) myL += __shfl_xor_sync(0xffffffffu, myL, d);
+    if ((tid & 31) == 0) s_sumL[tid >> 5] = myL;
+    __syncthreads();
+  }
   if (tid == 0) {
-    u64 G = h.lines0, P0 = h.open0;
-    for (int c = 0; c < span; c++) {
-      const SpanDesc& p = a.desc[c];
-      if (p.T) { G += p.T; P0 = p.tail_len; }
-      else P0 += span_end(c) - span_begin(c);
-    }
+    u64 G = h.lines0, P0 = 0;
+    int last = -1;
+    for (int w = 0; w < STITCH_THREADS / 32; w++) { G += s_sumT[w]; P0 += s_sumL[w]; last = max(last, s_last[w]); }
+    P0 += last >= 0 ? a.desc[last].tail_len : h.open0;
     sG = G; sP0 = P0;
     d.G = G; d.P0 = P0; d.exact = (uint32_t)(G & 3);
     const int ok = d.guess == (uint32_t)(G & 3);
@@ -905,19 +922,32 @@ __global__ void fq_reset_kernel(u64* committed, int nblocks, Carry* carry) {
 }
 
 // K3: fold the per-span counter blocks into one block (sum words, then the four min/max words).
-__global__ void fq_reduce_kernel(const u64* __restrict__ blocks, int nblocks, u64* __restrict__ out) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= BLOCK_WORDS) return;
+__global__ void __launch_bounds__(256) fq_reduce_kernel(const u64* __restrict__ blocks, int nblocks, u64* __restrict__ out) {
+  __shared__ u64 part[8][32];
+  const int wl = threadIdx.x & 31, p = threadIdx.x >> 5;  // word within the CTA's 32 words, part 0..7
+  const int w = blockIdx.x * 32 + wl;
   const bool is_min = (w == OFF_SEQ_LEN_MIN || w == OFF_QUAL_LEN_MIN);
   const bool is_max = (w == OFF_SEQ_LEN_MAX || w == OFF_QUAL_LEN_MAX);
   u64 acc = is_min ? ~0ull : 0ull;
-  for (int b = 0; b < nblocks; b++) {
-    const u64 x = blocks[(size_t)b * BLOCK_WORDS + w];
-    if (is_min) acc = x < acc ? x : acc;
-    else if (is_max) acc = x > acc ? x : acc;
-    else acc += x;
+  if (w < BLOCK_WORDS) {
+    for (int b = p; b < nblocks; b += 8) {
+      const u64 x = blocks[(size_t)b * BLOCK_WORDS + w];
+      if (is_min) acc = x < acc ? x : acc;
+      else if (is_max) acc = x > acc ? x : acc;
+      else acc += x;
+    }
   }
-  out[w] = acc;
+  part[p][wl] = acc;
+  __syncthreads();
+  if (p == 0 && w < BLOCK_WORDS) {
+    for (int q = 1; q < 8; q++) {
+      const u64 x = part[q][wl];
+      if (is_min) acc = x < acc ? x : acc;
+      else if (is_max) acc = x > acc ? x : acc;
+      else acc += x;
+    }
+    out[w] = acc;
+  }
 }
 
 // fq-meta quality-range fold over the first 4*meta_records lines (src/fq_meta.nim:226-248): one
@@ -948,18 +978,19 @@ __global__ void fq_meta_kernel(const uint8_t* __restrict__ base, uint32_t lo0, u
   }
   unsigned pending = 0;
   bool done = false;
+  uint4 vnext = make_uint4(0, 0, 0, 0);
+  if ((u64)lane * 16 < end) vnext = *reinterpret_cast<const uint4*>(base + (u64)lane * 16);
   for (u64 o = 0; o < end && !done; o += 512) {
     const u64 g = o + (u64)lane * 16;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (g < end) v = *reinterpret_cast<const uint4*>(base + g);
+    const uint4 v = vnext;
+    if (g + 512 < end) vnext = *reinterpret_cast<const uint4*>(base + g + 512);  // prefetch the next window
     // valid byte range of this lane: [va, vb) within its 16 bytes
     int va = g >= (u64)lo0 ? 0 : (int)min((u64)16, (u64)lo0 - g);
     int vb = g + 16 <= end ? 16 : (g < end ? (int)(end - g) : 0);
     uint32_t nlm = nl_mask16(v) & ((1u << vb) - 1u) & ~((1u << va) - 1u);
-    // byte following this lane's 16 (for the '\r' rule): next lane's first byte, or memory, or none
+    // byte following this lane's 16 (for the '\r' rule): next lane's first byte, or memory
     uint32_t nxt = __shfl_down_sync(0xffffffffu, v.x & 0xFFu, 1);
     if (lane == 31) nxt = (g + 16 < end) ? (uint32_t)base[g + 16] : 0u;
-    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
     uint32_t lanes_nl = __ballot_sync(0xffffffffu, nlm != 0);
     int seg_lane = 0, seg_k = 0;  // current segment starts at (lane, byte) = (seg_lane, seg_k)
     for (;;) {
@@ -975,15 +1006,23 @@ __global__ void fq_meta_kernel(const uint8_t* __restrict__ base, uint32_t lo0, u
         int b = lane > nl_lane ? 0 : (lane == nl_lane ? nl_k : 16);
         a = max(a, va); b = min(b, vb);
         int mn = 0x7fffffff, mx = -0x7fffffff;
-        for (int k = a; k < b; k++) {
-          const uint32_t c = (w4[k >> 2] >> (8 * (k & 3))) & 0xFFu;
-          if (c == '\r') {
-            if (g + (u64)k + 1 >= end) { pending = 1; continue; }  // last byte of the chunk: decided later
-            const uint32_t nx = k < 15 ? ((w4[(k + 1) >> 2] >> (8 * ((k + 1) & 3))) & 0xFFu) : nxt;
-            if (nx == '\n') continue;                              // dropped: directly before the newline
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+          const uint32_t wk = k < 4 ? v.x : (k < 8 ? v.y : (k < 12 ? v.z : v.w));
+          const uint32_t c = (wk >> (8 * (k & 3))) & 0xFFu;
+          bool use = k >= a && k < b;
+          if (c == '\r' && use) {
+            if (g + (u64)k + 1 >= end) { pending = 1; use = false; }  // last byte of the chunk: decided later
+            else {
+              const uint32_t wn = (k + 1) < 4 ? v.x : ((k + 1) < 8 ? v.y : ((k + 1) < 12 ? v.z : v.w));
+              const uint32_t nx = k < 15 ? ((wn >> (8 * ((k + 1) & 3))) & 0xFFu) : nxt;
+              if (nx == '\n') use = false;                            // dropped: directly before the newline
+            }
           }
-          const int q = (c >= 33 && c <= 126) ? (int)c - 33 : -1;
-          mn = min(mn, q); mx = max(mx, q);
+          if (use) {
+            const int q = (c >= 33 && c <= 126) ? (int)c - 33 : -1;
+            mn = min(mn, q); mx = max(mx, q);
+          }
         }
         mn = __reduce_min_sync(0xffffffffu, mn);
         mx = __reduce_max_sync(0xffffffffu, mx);
@@ -1058,7 +1097,7 @@ cudaError_t launch_scan(const void* ptr, size_t nbytes, SpanDesc* desc, LaunchHd
 }
 
 cudaError_t launch_reduce(const u64* blocks, int nblocks, u64* out, cudaStream_t st) {
-  fq_reduce_kernel<<<(BLOCK_WORDS + 255) / 256, 256, 0, st>>>(blocks, nblocks, out);
+  fq_reduce_kernel<<<(BLOCK_WORDS + 31) / 32, 256, 0, st>>>(blocks, nblocks, out);
   return cudaGetLastError();
 }
 
