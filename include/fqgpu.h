@@ -131,6 +131,9 @@ int fqgpu_reset(fqgpu_ctx* ctx);
 /* Whole-buffer conveniences on top of the streaming interface. */
 int fqgpu_count_host(fqgpu_ctx* ctx, const void* buf, size_t nbytes, fqgpu_stats* out); /* pageable host memory */
 int fqgpu_count_file(fqgpu_ctx* ctx, const char* path, fqgpu_stats* out); /* plain or .gz (zlib inflate on host) */
+/* Same with the stream kind chosen by the caller: fq_count picks gz by a case-SENSITIVE ".gz" suffix
+ * (src/fq_count.nim:31), fq_meta by a case-INsensitive one (src/fq_meta.nim:219). */
+int fqgpu_count_file_as(fqgpu_ctx* ctx, const char* path, int as_gz, fqgpu_stats* out);
 
 /* HBM-resident interface (kernel-only measurements; data already on the context's device).
  * scan_device may be called repeatedly: each call continues the same stream of bytes (carry

@@ -113,6 +113,7 @@ def load_library(path: str | None = None):
         "fqgpu_reset": (i32, [vp]),
         "fqgpu_count_host": (i32, [vp, vp, sz, C.POINTER(Stats)]),
         "fqgpu_count_file": (i32, [vp, C.c_char_p, C.POINTER(Stats)]),
+        "fqgpu_count_file_as": (i32, [vp, C.c_char_p, i32, C.POINTER(Stats)]),
         "fqgpu_scan_device": (i32, [vp, vp, sz]),
         "fqgpu_count_device": (i32, [vp, vp, sz, C.POINTER(Stats)]),
         "fqgpu_shard_block_words": (sz, []),
@@ -140,7 +141,7 @@ def load_library(path: str | None = None):
 EXPORTED_SYMBOLS = [
     "fqgpu_abi_version", "fqgpu_stats_size", "fqgpu_build_info", "fqgpu_device_count", "fqgpu_create",
     "fqgpu_destroy", "fqgpu_last_error", "fqgpu_acquire", "fqgpu_submit", "fqgpu_finish", "fqgpu_reset",
-    "fqgpu_count_host", "fqgpu_count_file", "fqgpu_scan_device", "fqgpu_count_device",
+    "fqgpu_count_host", "fqgpu_count_file", "fqgpu_count_file_as", "fqgpu_scan_device", "fqgpu_count_device",
     "fqgpu_shard_block_words", "fqgpu_shard_begin", "fqgpu_shard_export", "fqgpu_shard_combine",
     "fqgpu_shard_rescan", "fqgpu_last_timing", "fqgpu_stream", "fqgpu_synth_illumina",
     "fqgpu_synth_illumina_bytes", "fqgpu_synth_ont",
@@ -224,9 +225,12 @@ class FqGpu:
         self._check(self.lib.fqgpu_count_host(self._ctx, ptr, nbytes, C.byref(st)))
         return st
 
-    def count_file(self, path: str) -> Stats:
+    def count_file(self, path: str, as_gz: bool | None = None) -> Stats:
         st = Stats()
-        self._check(self.lib.fqgpu_count_file(self._ctx, os.fsencode(path), C.byref(st)))
+        if as_gz is None:
+            self._check(self.lib.fqgpu_count_file(self._ctx, os.fsencode(path), C.byref(st)))
+        else:
+            self._check(self.lib.fqgpu_count_file_as(self._ctx, os.fsencode(path), int(as_gz), C.byref(st)))
         return st
 
     # -- HBM resident --------------------------------------------------------------------------
@@ -363,4 +367,4 @@ def fq_meta_quality_fields(st) -> list:
 def fq_meta_quality(fastq: str, sample_n: int = 20) -> list:
     """Quality part of fq_meta* (src/fq_meta.nim:197, default sample_n = 20; the CLI passes 100)."""
     with FqGpu(meta_records=sample_n) as ctx:
-        return fq_meta_quality_fields(ctx.count_file(fastq))
+        return fq_meta_quality_fields(ctx.count_file(fastq, as_gz=fastq.lower().endswith(".gz")))

@@ -52,7 +52,7 @@ def build_cli(force: bool = False) -> str:
     src = os.path.join(CSRC, "sc_main.cpp")
     if os.path.exists(src) and (force or _stale(SC, [src, LIB])):
         subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-o", SC, src, "-I", os.path.join(HERE, "..", "include"),
-                        "-L", HERE, "-lfqgpu", "-Wl,-rpath,$ORIGIN"], check=True)
+                        "-L", HERE, "-lfqgpu", "-lz", "-Wl,-rpath,$ORIGIN"], check=True)
     return SC
 
 

@@ -426,7 +426,12 @@ int fqgpu_count_host(fqgpu_ctx* ctx, const void* buf, size_t nbytes, fqgpu_stats
 int fqgpu_count_file(fqgpu_ctx* ctx, const char* path, fqgpu_stats* out) {
   if (!ctx || !path || !out) return FQGPU_EARG;
   const size_t L = strlen(path);
-  const bool gz = L >= 3 && strcmp(path + L - 3, ".gz") == 0;
+  return fqgpu_count_file_as(ctx, path, L >= 3 && strcmp(path + L - 3, ".gz") == 0, out);
+}
+
+int fqgpu_count_file_as(fqgpu_ctx* ctx, const char* path, int as_gz, fqgpu_stats* out) {
+  if (!ctx || !path || !out) return FQGPU_EARG;
+  const bool gz = as_gz != 0;
   int rc = fqgpu_reset(ctx);
   if (rc != FQGPU_OK) return rc;
   if (gz) {
