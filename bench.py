@@ -226,22 +226,27 @@ def main():
         bw = ctx.shard_block_words()
         blocks = torch.zeros(world * bw, dtype=torch.int64, device="cuda")
 
+    lib_stream = torch.cuda.ExternalStream(ctx.stream)
+
     def step():
         """One pass of the hot path over this rank's bytes; returns Stats."""
         if world == 1:
             return ctx.count_device(buf.data_ptr(), nbytes)
+        ctx.shard_begin(rank, world)
+        ctx.scan_device(buf.data_ptr(), nbytes)
         while True:
-            ctx.shard_begin(rank, world)
-            ctx.scan_device(buf.data_ptr(), nbytes)
             blocks.zero_()
+            lib_stream.wait_stream(torch.cuda.current_stream())  # the library runs on its own non-blocking stream
             ctx.shard_export(blocks.data_ptr())
-            torch.cuda.current_stream().wait_stream(torch.cuda.ExternalStream(ctx.stream))
+            torch.cuda.current_stream().wait_stream(lib_stream)
             dist.all_reduce(blocks)  # the ONE collective: SUM of disjoint slots == gather
             torch.cuda.current_stream().synchronize()
             rc, st = ctx.shard_combine(blocks.data_ptr())
             if rc == 0:
                 return st
-            ctx.shard_rescan(blocks.data_ptr())  # malformed input only: rescan with the exact carry
+            # malformed input only: a rank resynced to a wrong phase; it scans again with the exact carry
+            if ctx.shard_rescan(blocks.data_ptr()) == fq.ERETRY:
+                ctx.scan_device(buf.data_ptr(), nbytes)
 
     def barrier():
         torch.cuda.synchronize()
@@ -259,7 +264,6 @@ def main():
     launches = 0
     t0 = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    lib_stream = torch.cuda.ExternalStream(ctx.stream)
     ev0.record(lib_stream)
     for _ in range(args.steps):
         st = step()
@@ -344,7 +348,8 @@ def main():
                          "note": "algorithmic bytes = input bytes (1 B read per byte); device time = CUDA events around "
                                  "memset+meta+scan+reduce on the library stream (scan kernel > 99 %)"},
             "clocks": clocks,
-            "gpu_launches": int(args.steps * (scan_launches_per_step * (3 if args.meta_records else 2) + 1)),
+            # per scan call: meta + resync + scan + stitch + scan(pass 1); per step also reset + reduce
+            "gpu_launches": int(args.steps * (scan_launches_per_step * (5 if args.meta_records else 4) + 2)),
             "e2e": e2e,
             "cpu_baseline": cpu,
         }

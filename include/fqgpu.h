@@ -66,9 +66,11 @@ typedef struct {
 /* meta_status values */
 enum {
   FQGPU_META_OK = 0,
-  FQGPU_META_EMPTY_QUAL = 1 /* the reference would raise here: an empty quality line reached
-                               qual_min_max with no valid history (min() of an empty seq,
-                               src/fq_meta.nim:102) */
+  FQGPU_META_EMPTY_QUAL = 1, /* the reference would raise here: an empty quality line reached
+                                qual_min_max with no valid history (min() of an empty seq,
+                                src/fq_meta.nim:102) */
+  FQGPU_META_INCOMPLETE = 0x100 /* multi-GPU shards only (flag, OR-ed in): the sampled first meta_records
+                                   records extend beyond shard 0, whose range is all that is reported */
 };
 
 /* Everything is an integer.  Line classes follow src/fq_count.nim:39-42: with the 1-based line
@@ -155,14 +157,19 @@ int fqgpu_count_device(fqgpu_ctx* ctx, const void* dptr, size_t nbytes, fqgpu_st
  *                          tail(g-1)+head(g) lines, shifts head per-position sums, verifies every
  *                          guessed phase against the exact line counts.  Returns FQGPU_OK, or
  *                          FQGPU_ERETRY when some rank guessed wrong (malformed input): then each
- *                          rank calls fqgpu_shard_rescan(), scans its range again (now with the
- *                          exact carry taken from the blocks), and export/all-reduce/combine repeat. */
+ *                          rank calls fqgpu_shard_rescan() (the first wrong rank scans its range again
+ *                          with the exact carry taken from the blocks), every rank exports again, and
+ *                          all-reduce/combine repeat -- at most world-1 rounds. */
 #define FQGPU_ERETRY 1
 size_t fqgpu_shard_block_words(void);
 int fqgpu_shard_begin(fqgpu_ctx* ctx, int rank, int world);
 int fqgpu_shard_export(fqgpu_ctx* ctx, uint64_t* d_blocks);
 int fqgpu_shard_combine(fqgpu_ctx* ctx, const uint64_t* d_blocks, fqgpu_stats* out);
+/* After FQGPU_ERETRY: FQGPU_OK = this rank's block stands, just export it again; FQGPU_ERETRY = the exact
+ * carry in front of this rank has been installed, scan the rank's byte range again, then export. */
 int fqgpu_shard_rescan(fqgpu_ctx* ctx, const uint64_t* d_blocks);
+/* The combine step alone, over gathered blocks in HOST memory (pure host arithmetic, needs no GPU). */
+int fqgpu_shard_combine_host(int world, const uint64_t* h_blocks, uint64_t meta_records, fqgpu_stats* out);
 
 /* Timing of the most recent scan launches on this context (CUDA events on the context's stream):
  * kernel_ms = sum of scan-kernel durations since the last reset, launches = how many kernels. */

@@ -121,6 +121,7 @@ def load_library(path: str | None = None):
         "fqgpu_shard_export": (i32, [vp, vp]),
         "fqgpu_shard_combine": (i32, [vp, vp, C.POINTER(Stats)]),
         "fqgpu_shard_rescan": (i32, [vp, vp]),
+        "fqgpu_shard_combine_host": (i32, [i32, vp, u64, C.POINTER(Stats)]),
         "fqgpu_last_timing": (i32, [vp, C.POINTER(C.c_double), C.POINTER(u64)]),
         "fqgpu_stream": (vp, [vp]),
         "fqgpu_synth_illumina": (i32, [vp, vp, sz, u64, u64, u64, C.POINTER(sz)]),
@@ -143,7 +144,7 @@ EXPORTED_SYMBOLS = [
     "fqgpu_destroy", "fqgpu_last_error", "fqgpu_acquire", "fqgpu_submit", "fqgpu_finish", "fqgpu_reset",
     "fqgpu_count_host", "fqgpu_count_file", "fqgpu_count_file_as", "fqgpu_scan_device", "fqgpu_count_device",
     "fqgpu_shard_block_words", "fqgpu_shard_begin", "fqgpu_shard_export", "fqgpu_shard_combine",
-    "fqgpu_shard_rescan", "fqgpu_last_timing", "fqgpu_stream", "fqgpu_synth_illumina",
+    "fqgpu_shard_rescan", "fqgpu_shard_combine_host", "fqgpu_last_timing", "fqgpu_stream", "fqgpu_synth_illumina",
     "fqgpu_synth_illumina_bytes", "fqgpu_synth_ont",
 ]
 
@@ -163,9 +164,13 @@ class FqGpu:
             raise FqGpuError(rc, msg)
 
     def close(self):
-        if getattr(self, "_ctx", None) and self._ctx.value:
-            self.lib.fqgpu_destroy(self._ctx)
-            self._ctx = C.c_void_p()
+        ctx = getattr(self, "_ctx", None)
+        if ctx is not None and ctx.value:
+            self._ctx = None
+            try:
+                self.lib.fqgpu_destroy(ctx)
+            except Exception:  # interpreter shutdown
+                pass
 
     __del__ = close
 
@@ -267,8 +272,9 @@ class FqGpu:
         rc = self._check(self.lib.fqgpu_shard_combine(self._ctx, d_blocks, C.byref(st)))
         return rc, st
 
-    def shard_rescan(self, d_blocks: int):
-        self._check(self.lib.fqgpu_shard_rescan(self._ctx, d_blocks))
+    def shard_rescan(self, d_blocks: int) -> int:
+        """ERETRY (1): the exact carry was installed, scan this rank's range again; OK (0): just export again."""
+        return self._check(self.lib.fqgpu_shard_rescan(self._ctx, d_blocks))
 
     # -- synthetic data --------------------------------------------------------------------------
     def synth_illumina(self, dptr: int, capacity: int, first_record: int, n_records: int, seed: int) -> int:
@@ -283,6 +289,15 @@ class FqGpu:
         w = C.c_size_t()
         self._check(self.lib.fqgpu_synth_ont(self._ctx, dptr, capacity, first_record, n_records, seed, C.byref(w)))
         return w.value
+
+
+def shard_combine_host(world: int, blocks_ptr: int, meta_records: int = 0):
+    """Combine step over gathered shard blocks in host memory (no GPU needed)."""
+    st = Stats()
+    rc = load_library().fqgpu_shard_combine_host(world, blocks_ptr, meta_records, C.byref(st))
+    if rc < 0:
+        raise FqGpuError(rc, "fqgpu_shard_combine_host failed")
+    return rc, st
 
 
 # ------------------------------------------------------------------------------------------------

@@ -33,7 +33,7 @@ struct Carry {
   unsigned long long open_len;  // raw bytes since the last '\n' (the open line)
   unsigned long long bytes;     // bytes scanned so far
   unsigned int last_byte;       // last byte of the stream so far (0 when bytes == 0)
-  unsigned int flags;
+  unsigned int flags;           // CARRY_* (multi-GPU shards)
   // fq-meta fold (src/fq_meta.nim:207-208,226-248)
   unsigned long long meta_lines;  // lines consumed by the sampling loop (<= 4*meta_records)
   long long qual_min, qual_max;   // running qual_min/qual_max, -1 initially
@@ -42,6 +42,31 @@ struct Carry {
   int cur_has;                    // open line: any attributed byte so far
   int cur_min, cur_max;           // open line: min/max of qual_to_int so far
   unsigned int pad;
+};
+
+// Multi-GPU shards: a rank > 0 does not know the line phase of its first byte.
+//   CARRY_UNKNOWN_START  the shard started with an unknown phase; `lines` counts from the shard start
+//   CARRY_HYP_VALID      flags >> 8 & 3 is the phase hypothesis (resynced from the content) the shard
+//                        was scanned with; verified by fqgpu_shard_combine against the exact counts
+enum { CARRY_UNKNOWN_START = 1u, CARRY_HYP_VALID = 2u, CARRY_HYP_SHIFT = 8 };
+
+// What a shard exports besides its counter block (one slot of the all-reduced buffer).
+constexpr int SH_OFF_HEAD_POS = 0;                         // [POS_BINS+1] per-position sums of the detached head fragment
+constexpr int SH_OFF_SCALARS = SH_OFF_HEAD_POS + POS_BINS + 1;
+enum {
+  SH_LINES = 0, SH_BYTES, SH_OPEN_LEN, SH_LAST_BYTE, SH_FIRST_BYTE, SH_HEAD_LEN, SH_HEAD_CR, SH_HYP, SH_HYP_VALID,
+  SH_EXACT, SH_META_LINES, SH_META_QMIN, SH_META_QMAX, SH_META_STATUS, SH_META_PENDING_CR, SH_META_CUR_HAS,
+  SH_META_CUR_MIN, SH_META_CUR_MAX, SH_PRESENT, SH_NSCALARS
+};
+constexpr int SHARD_EXTRA_WORDS = ((SH_OFF_SCALARS + SH_NSCALARS + 31) / 32) * 32;
+
+// Device-resident description of the shard's detached head (first line fragment of the shard).
+struct ShardInfo {
+  unsigned long long head_pos[POS_BINS + 1];  // per-position sums relative to the shard start
+  unsigned long long head_len;                // bytes before the shard's first newline
+  unsigned int head_cr;                       // the byte before that newline is '\r' (and inside the shard)
+  unsigned int first_byte;                    // first byte of the shard
+  unsigned int pad[2];
 };
 
 // One span = the contiguous run of tiles one CTA scans in a launch.  The line phase at a span start
@@ -65,7 +90,7 @@ struct SpanDesc {
 // one writes the new carry).
 struct LaunchHdr {
   unsigned long long lines0, open0, bytes0;
-  unsigned int last_byte0, phase_known;
+  unsigned int last_byte0, flags0;   // flags0 = Carry.flags at the start of the launch
   unsigned int mismatches, pad;
 };
 

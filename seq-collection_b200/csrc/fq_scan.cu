@@ -72,6 +72,7 @@ struct ScanArgs {
   Carry* carry;
   u64* pending;    // [nspans][BLOCK_WORDS] results of pass 0, committed by the stitch kernel
   u64* committed;  // [MAX_SPANS][BLOCK_WORDS] accumulated over launches
+  ShardInfo* shard;  // detached head of a multi-GPU shard (rank > 0)
   uint32_t dbg;
 };
 
@@ -747,16 +748,22 @@ constexpr u64 RESYNC_BYTES = 4ull << 20;
 
 __global__ void fq_resync_kernel(const ScanArgs a) {
   const int span = blockIdx.x, lane = threadIdx.x;
+  const unsigned cflags = a.carry->flags;
   if (span == 0 && lane == 0) {
     LaunchHdr h;
     h.lines0 = a.carry->lines; h.open0 = a.carry->open_len; h.bytes0 = a.carry->bytes;
-    h.last_byte0 = a.carry->last_byte; h.phase_known = 1; h.mismatches = 0; h.pad = 0;
+    h.last_byte0 = a.carry->last_byte; h.flags0 = cflags; h.mismatches = 0; h.pad = 0;
     *a.hdr = h;
+    if ((cflags & CARRY_UNKNOWN_START) && a.carry->bytes == 0) a.shard->first_byte = a.base[a.lo0];
   }
   SpanDesc& d = a.desc[span];
   if (lane == 0) { d.T = 0; d.head_len = 0; d.tail_len = 0; d.state = SPAN_PENDING; d.exact = PHASE_UNKNOWN; d.G = 0; d.P0 = 0; }
-  if (span == 0) {  // the phase of the launch's first byte is known exactly from the stream carry
-    if (lane == 0) d.guess = (uint32_t)(a.carry->lines & 3);
+  // The phase of the launch's first byte: exact from the stream carry, or (multi-GPU shard with an
+  // unknown start) the shard's hypothesis plus the lines counted so far, or resynced like any span.
+  const bool start_known = !(cflags & CARRY_UNKNOWN_START) || (cflags & CARRY_HYP_VALID);
+  if (span == 0 && start_known) {
+    const unsigned hyp = (cflags & CARRY_UNKNOWN_START) ? (cflags >> CARRY_HYP_SHIFT) & 3u : 0u;
+    if (lane == 0) d.guess = (uint32_t)((hyp + a.carry->lines) & 3);
     return;
   }
   const u64 begin = (u64)span * a.tps * TILE;  // 16-byte aligned
@@ -771,6 +778,7 @@ __global__ void fq_resync_kernel(const ScanArgs a) {
       const uint4 v = *reinterpret_cast<const uint4*>(a.base + g);
       m = nl_mask16(v);
       if (g + 16 > a.end) m &= (1u << (a.end - g)) - 1u;
+      if (g < (u64)a.lo0) m &= ~((1u << min((u64)16, (u64)a.lo0 - g)) - 1u);
     }
     uint32_t any = __ballot_sync(0xffffffffu, m != 0);
     while (any && nlines < RESYNC_LINES) {
@@ -803,8 +811,9 @@ constexpr int STITCH_THREADS = 256;
 __global__ void __launch_bounds__(STITCH_THREADS) fq_stitch_kernel(const ScanArgs a) {
   __shared__ uint32_t ghist[2][256];
   __shared__ uint32_t pos_sum[POS_BINS + 1];
-  __shared__ u64 sG, sP0;
-  __shared__ int s_commit;
+  __shared__ u64 sP0;
+  __shared__ int s_commit, s_detached;
+  __shared__ uint32_t s_phase;
   const int span = blockIdx.x, tid = threadIdx.x;
   SpanDesc& d = a.desc[span];
   const LaunchHdr& h = *a.hdr;
@@ -834,9 +843,28 @@ __global__ void __launch_bounds__(STITCH_THREADS) fq_stitch_kernel(const ScanArg
     int last = -1;
     for (int w = 0; w < STITCH_THREADS / 32; w++) { G += s_sumT[w]; P0 += s_sumL[w]; last = max(last, s_last[w]); }
     P0 += last >= 0 ? a.desc[last].tail_len : h.open0;
-    sG = G; sP0 = P0;
-    d.G = G; d.P0 = P0; d.exact = (uint32_t)(G & 3);
-    const int ok = d.guess == (uint32_t)(G & 3);
+    // Multi-GPU shard with an unknown start: G counts from the shard start and the phase is the shard's
+    // hypothesis -- carried over from an earlier launch, or fixed now by the first span whose resync
+    // found a header (fqgpu_shard_combine verifies it against the exact counts of the other ranks).
+    const bool unknown = (h.flags0 & CARRY_UNKNOWN_START) != 0;
+    unsigned hyp = 0;
+    bool hyp_ok = true;
+    if (unknown) {
+      if (h.flags0 & CARRY_HYP_VALID) hyp = (h.flags0 >> CARRY_HYP_SHIFT) & 3u;
+      else {
+        hyp_ok = false;
+        u64 Gc = h.lines0;
+        for (int c = 0; c < (int)a.nspans; c++) {
+          if (a.desc[c].guess < 4) { hyp = (unsigned)((a.desc[c].guess - Gc) & 3); hyp_ok = true; break; }
+          Gc += a.desc[c].T;
+        }
+      }
+    }
+    const uint32_t exact = hyp_ok ? (uint32_t)((hyp + G) & 3) : PHASE_UNKNOWN;
+    sP0 = P0; s_phase = exact;
+    s_detached = unknown && G == 0;  // still inside the shard's first line fragment
+    d.G = G; d.P0 = P0; d.exact = exact;
+    const int ok = hyp_ok && d.guess == exact;
     d.state = ok ? SPAN_COMMITTED : SPAN_RESCAN;
     if (!ok) atomicAdd(&a.hdr->mismatches, 1u);
     s_commit = ok;
@@ -846,6 +874,7 @@ __global__ void __launch_bounds__(STITCH_THREADS) fq_stitch_kernel(const ScanArg
       a.carry->open_len = d.T ? d.tail_len : P0 + len;
       a.carry->bytes = h.bytes0 + (a.end - a.lo0);
       a.carry->last_byte = a.base[a.end - 1];
+      if (unknown && hyp_ok) a.carry->flags = CARRY_UNKNOWN_START | CARRY_HYP_VALID | (hyp << CARRY_HYP_SHIFT);
     }
   }
   for (int i = tid; i < 512; i += STITCH_THREADS) (&ghist[0][0])[i] = 0;
@@ -862,10 +891,11 @@ __global__ void __launch_bounds__(STITCH_THREADS) fq_stitch_kernel(const ScanArg
     }
   }
   __syncthreads();  // the commit is complete before the head fragment is added to the same block
-  // ---- head fragment: bytes [b0, b0 + head_len) belong to absolute line G, at line position P0 ----
-  const u64 G = sG, P0 = sP0;
-  const int cls = (int)(G & 3);
-  if (!(cls & 1)) return;
+  // ---- head fragment: bytes [b0, b0 + head_len) belong to line G, at line position P0 ----
+  const u64 P0 = sP0;
+  const bool detached = s_detached != 0;  // the fragment belongs to the shard's first line: P0 is relative
+  if (s_phase > 3) return;
+  const int cls = (int)s_phase;
   const u64 b0 = span_begin(span);
   const u64 hl = d.head_len;
   u64 ve = b0 + hl;  // content end
@@ -880,12 +910,17 @@ __global__ void __launch_bounds__(STITCH_THREADS) fq_stitch_kernel(const ScanArg
     const int nx = ve < a.end ? (int)a.base[ve] : -1;
     if (nx == '\n' || nx < 0) ve--;
   }
+  if (detached && tid == 0 && d.T) {  // the shard's first line ends here; its length is stitched by the combine step
+    a.shard->head_len = P0 + hl;
+    a.shard->head_cr = (unsigned)cr;
+  }
+  if (!(cls & 1)) return;
   for (u64 o = b0 + tid; o < ve; o += STITCH_THREADS) account_byte(ghist, pos_sum, cls, a.base[o], P0 + (o - b0));
   if (tid == 0) {
     // the '\r' that ended the previous launch is content unless this launch starts with '\n'
     if (span == 0 && h.bytes0 && h.open0 && h.last_byte0 == '\r' && a.base[a.lo0] != '\n')
       account_byte(ghist, pos_sum, cls, '\r', P0 - 1);
-    if (d.T) {
+    if (d.T && !detached) {
       const u64 len = P0 + hl - (u64)cr;
       const uint32_t bin = len < (u64)POS_BINS ? (uint32_t)len : (uint32_t)POS_BINS;
       if (cls == 3) {
@@ -902,7 +937,9 @@ __global__ void __launch_bounds__(STITCH_THREADS) fq_stitch_kernel(const ScanArg
   }
   __syncthreads();
   for (int i = tid; i < 512; i += STITCH_THREADS) { const uint32_t v = (&ghist[0][0])[i]; if (v) cblock[OFF_HIST_SEQ + i] += v; }
-  for (int i = tid; i <= POS_BINS; i += STITCH_THREADS) { const uint32_t v = pos_sum[i]; if (v) cblock[OFF_POS_SUM + i] += v; }
+  // per-position sums of a detached head are relative to the shard start: kept apart, shifted by the combine step
+  u64* ptarget = detached ? a.shard->head_pos : cblock + OFF_POS_SUM;
+  for (int i = tid; i <= POS_BINS; i += STITCH_THREADS) { const uint32_t v = pos_sum[i]; if (v) atomicAdd(&ptarget[i], (u64)v); }
 }
 
 // Resets the committed span blocks and the stream carry (a new file).
@@ -1074,7 +1111,7 @@ cudaError_t launch_reset(u64* committed, int nblocks, Carry* carry, cudaStream_t
 // resync -> scan (guessed phases) -> stitch (verify, commit, head fragments, carry) -> scan pass 1
 // (only spans whose guess was wrong or unknown; exits immediately otherwise).
 cudaError_t launch_scan(const void* ptr, size_t nbytes, SpanDesc* desc, LaunchHdr* hdr, Carry* carry,
-                        u64* pending, u64* committed, int max_spans, u64 meta_records, cudaStream_t st) {
+                        u64* pending, u64* committed, ShardInfo* shard, int max_spans, u64 meta_records, cudaStream_t st) {
   if (nbytes == 0) return cudaSuccess;
   static const uint32_t dbg = getenv("FQGPU_DEBUG") ? (uint32_t)atoi(getenv("FQGPU_DEBUG")) : 0u;
   const uintptr_t addr = (uintptr_t)ptr;
@@ -1086,7 +1123,7 @@ cudaError_t launch_scan(const void* ptr, size_t nbytes, SpanDesc* desc, LaunchHd
   uint32_t nspans = a.ntiles < (uint32_t)max_spans ? a.ntiles : (uint32_t)max_spans;
   a.tps = (a.ntiles + nspans - 1) / nspans;
   a.nspans = (a.ntiles + a.tps - 1) / a.tps;
-  a.desc = desc; a.hdr = hdr; a.carry = carry; a.pending = pending; a.committed = committed; a.dbg = dbg;
+  a.desc = desc; a.hdr = hdr; a.carry = carry; a.pending = pending; a.committed = committed; a.shard = shard; a.dbg = dbg;
 
   if (meta_records) fq_meta_kernel<<<1, 32, 0, st>>>(a.base, a.lo0, a.end, carry, meta_records);
   fq_resync_kernel<<<a.nspans, 32, 0, st>>>(a);

@@ -14,78 +14,7 @@
 
 #include "fq_layout.h"
 
-namespace fq {
-typedef unsigned long long u64;
-size_t scan_smem_bytes();
-int scan_tile_bytes();
-int scan_threads();
-cudaError_t scan_configure();
-cudaError_t launch_reset(u64* committed, int nblocks, Carry* carry, cudaStream_t st);
-cudaError_t launch_scan(const void* ptr, size_t nbytes, SpanDesc* desc, LaunchHdr* hdr, Carry* carry,
-                        u64* pending, u64* committed, int max_spans, u64 meta_records, cudaStream_t st);
-cudaError_t launch_reduce(const u64* blocks, int nblocks, u64* out, cudaStream_t st);
-cudaError_t launch_synth_illumina(void* dptr, u64 first_byte, u64 nbytes, u64 seed, cudaStream_t st);
-cudaError_t synth_ont(void* dptr, size_t capacity, u64 first_record, u64 n_records, u64 seed, size_t* bytes_written,
-                      cudaStream_t st);
-}  // namespace fq
-
-using fq::u64;
-
-// one launch = up to MAX_SPANS spans; a span stays below 2 GiB so its 32-bit shared-memory counters are exact
-static const size_t kMaxLaunchBytes = (size_t)fq::MAX_SPANS * ((size_t)2 << 30) - ((size_t)64 << 20);
-static thread_local std::string g_create_error;
-
-struct StageBuf {
-  void* host = nullptr;
-  cudaEvent_t copied = nullptr;  // H2D of this buffer finished -> host side reusable
-  bool in_flight = false;
-};
-
-struct fqgpu_ctx {
-  int device = 0;
-  fqgpu_config cfg{};
-  cudaStream_t stream = nullptr;
-  int grid = 0;
-  u64* d_pending = nullptr;    // [MAX_SPANS] blocks of the launch in flight
-  u64* d_committed = nullptr;  // [MAX_SPANS] blocks accumulated since the last reset
-  fq::Carry* d_carry = nullptr;
-  fq::SpanDesc* d_desc = nullptr;
-  fq::LaunchHdr* d_hdr = nullptr;
-  u64* d_out = nullptr;
-  u64* h_out = nullptr;  // pinned: reduced block followed by the carry
-  std::vector<StageBuf> ring;
-  // device landing buffers of the host paths: H2D of chunk k+1 (copy stream) overlaps the scan of
-  // chunk k (compute stream)
-  void* d_stage[2] = {nullptr, nullptr};
-  cudaStream_t cstream = nullptr;
-  cudaEvent_t ev_copied[2] = {nullptr, nullptr};   // H2D into d_stage[b] finished
-  cudaEvent_t ev_scanned[2] = {nullptr, nullptr};  // scan of d_stage[b] finished -> buffer free
-  u64 n_staged = 0;
-  size_t chunk_bytes = 0;
-  int next = 0;
-  std::string err;
-  // timing of scan launches since the last reset
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
-  std::vector<cudaEvent_t> event_pool;
-  double kernel_ms_done = 0.0;
-  u64 launches = 0;
-  // shard mode
-  int shard_rank = 0, shard_world = 1;
-};
-
-#define CU_TRY(ctx, call)                                                              \
-  do {                                                                                 \
-    cudaError_t e_ = (call);                                                           \
-    if (e_ != cudaSuccess) {                                                           \
-      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                 \
-      return FQGPU_ECUDA;                                                              \
-    }                                                                                  \
-  } while (0)
-
-static int fail(fqgpu_ctx* ctx, int code, const std::string& msg) {
-  if (ctx) ctx->err = msg; else g_create_error = msg;
-  return code;
-}
+#include "fqgpu_ctx.h"
 
 extern "C" {
 
@@ -124,6 +53,8 @@ void fqgpu_destroy(fqgpu_ctx* ctx) {
   cudaFree(ctx->d_carry);
   cudaFree(ctx->d_desc);
   cudaFree(ctx->d_hdr);
+  cudaFree(ctx->d_shard);
+  if (ctx->h_shard) cudaFreeHost(ctx->h_shard);
   cudaFree(ctx->d_out);
   if (ctx->h_out) cudaFreeHost(ctx->h_out);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -165,6 +96,8 @@ int fqgpu_create(fqgpu_ctx** out, const fqgpu_config* cfg) {
   CU_NEW(cudaMalloc(&ctx->d_carry, sizeof(fq::Carry)));
   CU_NEW(cudaMalloc(&ctx->d_desc, fq::MAX_SPANS * sizeof(fq::SpanDesc)));
   CU_NEW(cudaMalloc(&ctx->d_hdr, sizeof(fq::LaunchHdr)));
+  CU_NEW(cudaMalloc(&ctx->d_shard, sizeof(fq::ShardInfo)));
+  CU_NEW(cudaMallocHost(&ctx->h_shard, (size_t)64 * fqgpu_shard_block_words() * sizeof(u64)));
   CU_NEW(cudaMalloc(&ctx->d_out, fq::BLOCK_WORDS * sizeof(u64)));
   CU_NEW(cudaMallocHost(&ctx->h_out, fq::BLOCK_WORDS * sizeof(u64) + sizeof(fq::Carry)));
   ctx->ring.resize(nbuf);  // pinned chunks are allocated lazily by the first acquire()
@@ -188,26 +121,30 @@ int fqgpu_reset(fqgpu_ctx* ctx) {
   return FQGPU_OK;
 }
 
-static cudaEvent_t get_event(fqgpu_ctx* ctx) {
+}  // extern "C"
+
+cudaEvent_t fqgpu_get_event(fqgpu_ctx* ctx) {
   if (!ctx->event_pool.empty()) { cudaEvent_t e = ctx->event_pool.back(); ctx->event_pool.pop_back(); return e; }
   cudaEvent_t e = nullptr;
   cudaEventCreate(&e);
   return e;
 }
 
+extern "C" {
+
 int fqgpu_scan_device(fqgpu_ctx* ctx, const void* dptr, size_t nbytes) {
   if (!ctx) return FQGPU_EARG;
   if (nbytes == 0) return FQGPU_OK;
   if (!dptr) return fail(ctx, FQGPU_EARG, "fqgpu_scan_device: NULL pointer");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
-  cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
+  cudaEvent_t e0 = fqgpu_get_event(ctx), e1 = fqgpu_get_event(ctx);
   CU_TRY(ctx, cudaEventRecord(e0, ctx->stream));
   const uint8_t* p = (const uint8_t*)dptr;
   size_t left = nbytes;
   while (left) {
     size_t n = left < kMaxLaunchBytes ? left : kMaxLaunchBytes;
     CU_TRY(ctx, fq::launch_scan(p, n, ctx->d_desc, ctx->d_hdr, ctx->d_carry, ctx->d_pending, ctx->d_committed,
-                                ctx->grid, ctx->cfg.meta_records, ctx->stream));
+                                ctx->d_shard, ctx->grid, ctx->shard_rank > 0 ? 0 : ctx->cfg.meta_records, ctx->stream));
     ctx->launches++;
     p += n;
     left -= n;
@@ -236,10 +173,12 @@ int fqgpu_last_timing(fqgpu_ctx* ctx, double* kernel_ms, uint64_t* launches) {
   return FQGPU_OK;
 }
 
-// ---- stats assembly (host): the reduced block + the stream carry -> fqgpu_stats ----------------
-static inline unsigned log2_bin(u64 len) { unsigned b = 0; while (len) { b++; len >>= 1; } return b; }
+}  // extern "C"
 
-static void assemble_stats(const u64* blk, const fq::Carry& c, u64 meta_records, fqgpu_stats* st) {
+// ---- stats assembly (host): the reduced block + the stream carry -> fqgpu_stats ----------------
+static inline unsigned log2_bin_host(u64 len) { unsigned b = 0; while (len) { b++; len >>= 1; } return b; }
+
+void fqgpu_assemble_stats(const u64* blk, const fq::Carry& c, u64 meta_records, fqgpu_stats* st) {
   memset(st, 0, sizeof(*st));
   for (int i = 0; i < 256; i++) { st->base_counts[i] = blk[fq::OFF_HIST_SEQ + i]; st->qual_counts[i] = blk[fq::OFF_HIST_QUAL + i]; }
   for (int i = 0; i <= fq::POS_BINS; i++) {
@@ -261,7 +200,7 @@ static void assemble_stats(const u64* blk, const fq::Carry& c, u64 meta_records,
     if (cls == 1) {
       if (tail_cr) st->base_counts['\r']++;
       st->seq_len_hist[len < (u64)fq::POS_BINS ? len : (u64)fq::POS_BINS]++;
-      st->seq_len_log2[log2_bin(len)]++;
+      st->seq_len_log2[log2_bin_host(len)]++;
       if (len < st->seq_len_min) st->seq_len_min = len;
       if (len > st->seq_len_max) st->seq_len_max = len;
     } else if (cls == 3) {
@@ -314,10 +253,12 @@ static void assemble_stats(const u64* blk, const fq::Carry& c, u64 meta_records,
   st->meta_status = status;
 }
 
+extern "C" {
+
 int fqgpu_finish(fqgpu_ctx* ctx, fqgpu_stats* out) {
   if (!ctx || !out) return FQGPU_EARG;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
-  cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
+  cudaEvent_t e0 = fqgpu_get_event(ctx), e1 = fqgpu_get_event(ctx);
   CU_TRY(ctx, cudaEventRecord(e0, ctx->stream));
   CU_TRY(ctx, fq::launch_reduce(ctx->d_committed, fq::MAX_SPANS, ctx->d_out, ctx->stream));
   CU_TRY(ctx, cudaEventRecord(e1, ctx->stream));
@@ -327,7 +268,7 @@ int fqgpu_finish(fqgpu_ctx* ctx, fqgpu_stats* out) {
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   fq::Carry c;
   memcpy(&c, ctx->h_out + fq::BLOCK_WORDS, sizeof(c));
-  assemble_stats(ctx->h_out, c, ctx->cfg.meta_records, out);
+  fqgpu_assemble_stats(ctx->h_out, c, ctx->cfg.meta_records, out);
   return FQGPU_OK;
 }
 
@@ -514,6 +455,5 @@ int fqgpu_synth_ont(fqgpu_ctx* ctx, void* dptr, size_t capacity, uint64_t first_
   return FQGPU_OK;
 }
 
-// ---- multi-GPU shard protocol: implemented in fq_shard.cu ----------------------------------------
 
 }  // extern "C"
