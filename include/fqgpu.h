@@ -130,6 +130,10 @@ int fqgpu_submit(fqgpu_ctx* ctx, void* chunk, size_t nbytes);
 int fqgpu_finish(fqgpu_ctx* ctx, fqgpu_stats* out);
 int fqgpu_reset(fqgpu_ctx* ctx);
 
+/* Continues the stream with `nbytes` of HOST memory (H2D straight from the caller's buffer, asynchronous
+ * when it is pinned; the copy of chunk k+1 overlaps the scan of chunk k).  No reset, no finish. */
+int fqgpu_scan_host(fqgpu_ctx* ctx, const void* buf, size_t nbytes);
+
 /* Whole-buffer conveniences on top of the streaming interface. */
 int fqgpu_count_host(fqgpu_ctx* ctx, const void* buf, size_t nbytes, fqgpu_stats* out); /* pageable host memory */
 int fqgpu_count_file(fqgpu_ctx* ctx, const char* path, fqgpu_stats* out); /* plain or .gz (zlib inflate on host) */

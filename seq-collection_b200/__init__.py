@@ -111,6 +111,7 @@ def load_library(path: str | None = None):
         "fqgpu_submit": (i32, [vp, vp, sz]),
         "fqgpu_finish": (i32, [vp, C.POINTER(Stats)]),
         "fqgpu_reset": (i32, [vp]),
+        "fqgpu_scan_host": (i32, [vp, vp, sz]),
         "fqgpu_count_host": (i32, [vp, vp, sz, C.POINTER(Stats)]),
         "fqgpu_count_file": (i32, [vp, C.c_char_p, C.POINTER(Stats)]),
         "fqgpu_count_file_as": (i32, [vp, C.c_char_p, i32, C.POINTER(Stats)]),
@@ -142,7 +143,7 @@ def load_library(path: str | None = None):
 EXPORTED_SYMBOLS = [
     "fqgpu_abi_version", "fqgpu_stats_size", "fqgpu_build_info", "fqgpu_device_count", "fqgpu_create",
     "fqgpu_destroy", "fqgpu_last_error", "fqgpu_acquire", "fqgpu_submit", "fqgpu_finish", "fqgpu_reset",
-    "fqgpu_count_host", "fqgpu_count_file", "fqgpu_count_file_as", "fqgpu_scan_device", "fqgpu_count_device",
+    "fqgpu_scan_host", "fqgpu_count_host", "fqgpu_count_file", "fqgpu_count_file_as", "fqgpu_scan_device", "fqgpu_count_device",
     "fqgpu_shard_block_words", "fqgpu_shard_begin", "fqgpu_shard_export", "fqgpu_shard_combine",
     "fqgpu_shard_rescan", "fqgpu_shard_combine_host", "fqgpu_last_timing", "fqgpu_stream", "fqgpu_synth_illumina",
     "fqgpu_synth_illumina_bytes", "fqgpu_synth_ont",
@@ -224,6 +225,9 @@ class FqGpu:
         else:  # numpy uint8 array
             self._check(self.lib.fqgpu_count_host(self._ctx, data.ctypes.data, data.size, C.byref(st)))
         return st
+
+    def scan_host_ptr(self, ptr: int, nbytes: int):
+        self._check(self.lib.fqgpu_scan_host(self._ctx, ptr, nbytes))
 
     def count_host_ptr(self, ptr: int, nbytes: int) -> Stats:
         st = Stats()

@@ -344,21 +344,28 @@ int fqgpu_submit(fqgpu_ctx* ctx, void* chunk, size_t nbytes) {
   return stage_and_scan(ctx, b.host, nbytes, b.copied);
 }
 
-int fqgpu_count_host(fqgpu_ctx* ctx, const void* buf, size_t nbytes, fqgpu_stats* out) {
-  if (!ctx || !out || (!buf && nbytes)) return FQGPU_EARG;
-  int rc = fqgpu_reset(ctx);
-  if (rc != FQGPU_OK) return rc;
+int fqgpu_scan_host(fqgpu_ctx* ctx, const void* buf, size_t nbytes) {
+  if (!ctx || (!buf && nbytes)) return FQGPU_EARG;
   // H2D straight from the caller's buffer (asynchronous when it is pinned), double-buffered on
   // the device so the copy of chunk k+1 overlaps the scan of chunk k
   const uint8_t* p = (const uint8_t*)buf;
   size_t left = nbytes;
   while (left) {
     size_t n = left < ctx->chunk_bytes ? left : ctx->chunk_bytes;
-    rc = stage_and_scan(ctx, p, n, nullptr);
+    int rc = stage_and_scan(ctx, p, n, nullptr);
     if (rc != FQGPU_OK) return rc;
     p += n;
     left -= n;
   }
+  return FQGPU_OK;
+}
+
+int fqgpu_count_host(fqgpu_ctx* ctx, const void* buf, size_t nbytes, fqgpu_stats* out) {
+  if (!ctx || !out || (!buf && nbytes)) return FQGPU_EARG;
+  int rc = fqgpu_reset(ctx);
+  if (rc != FQGPU_OK) return rc;
+  rc = fqgpu_scan_host(ctx, buf, nbytes);
+  if (rc != FQGPU_OK) return rc;
   return fqgpu_finish(ctx, out);
 }
 
