@@ -22,6 +22,7 @@ is needed between steps.
 from __future__ import annotations
 
 import argparse
+import glob
 import json
 import os
 import statistics
@@ -37,6 +38,17 @@ REC_BYTES = 360
 SEED_ILLUMINA = 20240229
 SEED_ONT = 20240301
 METRIC = "fastq_scan_throughput"
+
+
+def measured_traffic_ratio():
+    """DRAM bytes (read + write) per input byte of fq_scan_kernel, from the committed `ncu --set full` capture."""
+    best = None
+    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json"))):
+        try:
+            best = (float(json.load(open(p))["dram_bytes_per_input_byte"]), os.path.relpath(p, ROOT))
+        except Exception:
+            pass
+    return best
 
 
 def measured_hbm_peak():
@@ -364,6 +376,7 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
+        tr = measured_traffic_ratio()
         kern_ms_per_step = dev_ms / args.steps
         achieved = (nbytes / 1e9) / (kern_ms_per_step / 1e3)  # this rank's bytes / its device time
         scan_launches_per_step = launches / args.steps
@@ -379,7 +392,10 @@ def main():
                        "l2": "input >> 126 MB L2, no flush needed", "meta_records": args.meta_records,
                        "stats": "full (fq-count + A/C/G/T/N, length tables, quality histogram, per-position sums, fq-meta range)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": (tr[0] * nbytes / max(1.0, scan_launches_per_step)) if tr else None,
+                         "traffic_unit": "bytes per launch", "traffic_source": tr[1] if tr else None,
+                         "algorithmic_bytes_per_launch": nbytes / max(1.0, scan_launches_per_step),
+                         "peak_source": peak_src,
                          "note": "algorithmic bytes = input bytes (1 B read per byte); device time = CUDA events around "
                                  "memset+meta+scan+reduce on the library stream (scan kernel > 99 %)"},
             "clocks": clocks,
