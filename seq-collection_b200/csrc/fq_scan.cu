@@ -10,16 +10,18 @@
 //
 //   resync  fq_resync_kernel guesses the line phase (line number mod 4) at every span start from the
 //           content: the first line that starts with '@' and whose line+2 starts with '+' is a header.
-//   K1      boundary classification: every warp turns 16-byte groups into '\n' masks (SWAR compare,
-//           IDP.4A movemask) -> tile bitmap; four SCANNER warps popc / prefix-sum the bitmap into the
-//           tile's newline index, keep the span's running line count / open-line length (the
-//           tile-edge record carry) and the line-length tables;  concurrently
-//   K2      twelve WORKER warps walk the lines of the previous tile (a quarter-warp per line, 4 bytes
-//           per lane and step, aligned to the line start; the four lines of a warp have one class):
-//           histogram addresses and per-position sums are formed with IDP.4A (FMA pipe), histograms
-//           are lane-striped (conflict-free) shared-memory atomics, per-position sums live in
-//           registers.  Pieces that cross tile edges and long lines (ONT) are processed cooperatively
-//           in aligned 16-byte groups.
+//   K1a     boundary classification: every warp turns 16-byte groups into '\n' masks (SWAR compare,
+//           IDP.4A movemask) -> tile bitmap.
+//   K1b     four SCANNER warps popc / prefix-sum the bitmap into the tile's newline index and keep the
+//           span's running line count / open-line length (the tile-edge record carry).
+//   K1c     LINE tasks: one thread per sequence / quality line with bytes in the tile: line-length
+//           tables, the '\r' rule, and the line's bytes FLATTENED into entries of 16-byte groups --
+//           full groups (per class) and partial groups (first / last group of a line, byte range).
+//   K2      WORKER warps consume the entry lists of the previous tile, 32 entries per warp step, every
+//           lane one aligned 16-byte group (LDS.128): histogram addresses by IDP.4A (FMA pipe) into
+//           lane-striped (conflict-free) shared-memory atomics; per-position quality sums by shared
+//           atomics with immediate offsets into a bank-skewed table.  No per-line control flow, no
+//           alignment shifts; lines that cross tile edges are simply two runs of entries.
 //   stitch  fq_stitch_kernel prefix-sums the span descriptors, VERIFIES every guessed phase against
 //           the exact line counts (a wrong guess -- malformed input -- marks the span for an exact
 //           second pass, so results are exact on any input), commits the span blocks, accounts the
@@ -45,22 +47,26 @@ typedef unsigned long long u64;
 
 constexpr int TILE = 16384;
 constexpr int THREADS = 512;
+constexpr int NWARPS = THREADS / 32;
 constexpr int SCAN_WARPS = 4;
 constexpr int SCAN_THREADS = SCAN_WARPS * 32;
-constexpr int WORK_THREADS = THREADS - SCAN_THREADS;
-constexpr int WORK_WARPS = WORK_THREADS / 32;
-constexpr int GPT = TILE / 16 / THREADS;      // 16-byte groups per thread (2)
+constexpr int LINE_WARPS = 6;                 // warps 0..LINE_WARPS-1 run the line tasks (the scanner warps first)
+constexpr int LINE_THREADS = LINE_WARPS * 32;
+constexpr int WORK_WARPS = NWARPS - LINE_WARPS;
+constexpr int GPT = TILE / 16 / THREADS;      // 16-byte groups per thread in K1a (2)
+constexpr int NGROUPS = TILE / 16;
 constexpr int BM_WORDS = TILE / 32;           // bitmap words per tile
 constexpr int WPS = BM_WORDS / SCAN_THREADS;  // bitmap words per scanner thread (4)
-constexpr int NL_CAP = 2048;                  // newline index capacity; denser tiles take the walker path
+constexpr int NL_CAP = 1024;                  // newline index capacity; denser tiles take the walker path
+constexpr int PART_CAP = NL_CAP / 2 + 8;      // partial-entry slots per class (two per line)
 constexpr int PAD = 16;
 constexpr int STAGE_BYTES = PAD + TILE + 16;
 constexpr int NSTAGE = 3;
-constexpr int LONG_SEG = 1024;                // lines longer than this are processed cooperatively
-constexpr int PIECE_CAP = 24;
-constexpr int REG_STEPS = 5;                  // per-position sums of positions < 32*REG_STEPS live in registers
 constexpr int HB = 128;                       // striped histogram bins (tiles with bytes >= 128 take the walker path)
+constexpr int PT_STRIDE = 33;                 // per-position table: cell (r, c) = position 16*(c-1) + r, r < 31, c < 33
+constexpr int PT_WORDS = 1024;
 static_assert(WPS == 4, "scanner threads read their bitmap words with one LDS.128");
+static_assert(LINE_WARPS >= SCAN_WARPS && WORK_WARPS > 0, "warp roles");
 
 struct ScanArgs {
   const uint8_t* base;  // 16-byte aligned; the launch covers bytes [lo0, end) relative to base
@@ -80,14 +86,7 @@ struct ScanArgs {
 // parameters the compiler re-materialises each of them (UMOV / LDCU) in front of every IDP.4A.
 struct Sel {
   uint32_t h0, h1, h2, h3;  // 128 << 8k : histogram address = byte_k * 128 + base
-  uint32_t p0, p1, p2, p3;  // 1 << 8k   : per-position sum += byte_k
-};
-
-struct Piece {  // a run of content bytes handled cooperatively: [vs, ve) of the tile
-  int vs, ve;
-  uint32_t line;  // tile-relative line index
-  uint32_t pad;
-  u64 vpos;       // position of byte vs inside its line
+  uint32_t p1, p2;          // 1 << 8k   : byte_k (k = 1, 2) extracted on the FMA pipe
 };
 
 struct TileMeta {
@@ -97,33 +96,40 @@ struct TileMeta {
   int T;        // newlines in the tile
   int lo, hi;   // valid byte range of the tile
   int walker;   // 1: dense or high-byte tile -> generic bitmap walker
-  int npieces;
-  int nrec;     // relevant lines in rec[] (interior lines and, when it is one, the tail piece)
+  int R;        // sequence / quality lines with bytes in the tile (line tasks)
+  int first_q;  // line task 0 is a quality line (the classes of the tasks alternate)
+  uint32_t nfull;  // full-group entries: sequence | quality << 16
+  uint32_t pad;
 };
 
+// Entries: a full entry is  group | q << 10 ; a partial entry is  group | lo << 10 | hi << 14 | q << 19
+// (bytes [lo, hi) of the group; 0 = empty slot).  q = 16 + (line position of the group's byte 0),
+// saturated at 1023 (positions >= POS_BINS all fall into the overflow bin).
 struct __align__(128) Smem {
   uint8_t buf[NSTAGE][STAGE_BYTES];  // tile stages; data at buf[s] + PAD
   uint32_t hist[2][HB * 32];         // [0] sequence, [1] quality; word index = byte*32 + lane
   uint32_t ghist[2][256];            // un-striped tables of the generic paths
-  uint32_t bitmap[2][BM_WORDS];      // bit b of word w: byte 32*w+b is '\n'
-  uint16_t wordbase[2][BM_WORDS];    // newlines before bitmap word w
-  uint16_t nl[2][NL_CAP];
-  uint32_t rec[2][NL_CAP / 2 + 2];   // relevant (sequence / quality) lines of a tile: start | length << 14
-  uint32_t seq_len[POS_BINS + 1];
-  uint32_t qual_len[POS_BINS + 1];
+  uint32_t bitmap[BM_WORDS];         // bit b of word w: byte 32*w+b is '\n'
+  uint16_t nl[NL_CAP];
+  uint32_t full[2][NGROUPS];         // sequence entries from the front, quality entries from the back
+  uint32_t part[2][2][PART_CAP];     // [slot][class]
+  uint32_t seq_len[POS_BINS + 2];
+  uint32_t qual_len[POS_BINS + 2];
   uint32_t seq_log2[LOG2_BINS];
-  uint32_t pos_sum[POS_BINS + 1];
-  Piece pieces[2][PIECE_CAP];
+  uint32_t ptab[PT_WORDS];           // per-position quality sums, cell (r, c) at r*PT_STRIDE + c
+  uint4 masks[17];                   // masks[n]: the first n bytes of a group
   TileMeta meta[2];
   uint32_t scan_tot[SCAN_WARPS];
   int scan_last[SCAN_WARPS];
   u64 full_bar[NSTAGE];              // mbarriers of the stages
   u64 len_min[2], len_max[2];        // [0] seq, [1] qual
   u64 run_L, run_open;               // span-running newline count / open-line bytes
-  u64 head_len, junk[2];
-  uint32_t bytes_since_flush, hiflag[2], head_done;
+  u64 head_len, junk[2], pos_over;
+  uint32_t bytes_since_flush, hiflag, head_done;
   uint32_t ksel[8];
 };
+
+static_assert(sizeof(Smem) <= 115712, "two CTAs per SM");
 
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -151,8 +157,22 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ uint32_t lds8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void red_inc(uint32_t addr) {
   asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void red_add_at(uint32_t addr, uint32_t v) {
+  asm volatile("red.shared.add.u32 [%0+%2], %1;" ::"r"(addr), "r"(v), "n"(OFF) : "memory");
 }
 
 // 0x80 in every byte lane of w that equals '\n' (exact: no carries cross byte lanes)
@@ -160,11 +180,20 @@ __device__ __forceinline__ uint32_t nl_flags(uint32_t w) {
   uint32_t x = w ^ 0x0A0A0A0Au;
   return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
 }
+// the same for words whose bytes are all < 0x80 (one operation less)
+__device__ __forceinline__ uint32_t nl_flags_ascii(uint32_t w) {
+  return ~((w ^ 0x0A0A0A0Au) + 0x7F7F7F7Fu) & 0x80808080u;
+}
 // 16-bit mask of the '\n' bytes of a 16-byte group; the movemask is two IDP.4A chains (FMA pipe)
 __device__ __forceinline__ uint32_t nl_mask16(const uint4& v) {
   uint32_t lo = __dp4a(nl_flags(v.x), 0x08040201u, __dp4a(nl_flags(v.y), 0x80402010u, 0u));
   uint32_t hi = __dp4a(nl_flags(v.z), 0x08040201u, __dp4a(nl_flags(v.w), 0x80402010u, 0u));
   return (lo >> 7) | (hi << 1);  // the flags weigh 128
+}
+__device__ __forceinline__ uint32_t nl_mask16_ascii(const uint4& v) {
+  uint32_t lo = __dp4a(nl_flags_ascii(v.x), 0x08040201u, __dp4a(nl_flags_ascii(v.y), 0x80402010u, 0u));
+  uint32_t hi = __dp4a(nl_flags_ascii(v.z), 0x08040201u, __dp4a(nl_flags_ascii(v.w), 0x80402010u, 0u));
+  return (lo >> 7) | (hi << 1);
 }
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 #pragma unroll
@@ -176,12 +205,22 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 }
 __device__ __forceinline__ unsigned log2_bin(u64 len) { return len ? 64 - __clzll((long long)len) : 0; }
 
-// One byte of a sequence (cls 1) / quality (cls 3) line -- generic path, un-striped tables.
+// One byte of a sequence (cls 1) / quality (cls 3) line -- stitch kernel, linear tables.
 __device__ __forceinline__ void account_byte(uint32_t (*ghist)[256], uint32_t* pos_sum, int cls, uint32_t b, u64 pos) {
   atomicAdd(&ghist[cls == 3][b], 1u);
   if (cls == 3) {
     uint32_t p = pos < (u64)POS_BINS ? (uint32_t)pos : (uint32_t)POS_BINS;
     atomicAdd(&pos_sum[p], b);
+  }
+}
+// Cell of line position p (< POS_BINS) in the per-position table.
+__device__ __forceinline__ uint32_t pt_cell(uint32_t p) { return (p & 15u) * PT_STRIDE + (p >> 4) + 1u; }
+// The same byte through the scan kernel's tables (generic paths).
+__device__ __forceinline__ void account_byte_tab(Smem& sm, int cls, uint32_t b, u64 pos, u64& over) {
+  atomicAdd(&sm.ghist[cls == 3][b], 1u);
+  if (cls == 3) {
+    if (pos < (u64)POS_BINS) atomicAdd(&sm.ptab[pt_cell((uint32_t)pos)], b);
+    else over += b;
   }
 }
 __device__ __forceinline__ void account_line_len(Smem& sm, int cls, u64 len, u64* my_min, u64* my_max) {
@@ -193,131 +232,37 @@ __device__ __forceinline__ void account_line_len(Smem& sm, int cls, u64 len, u64
   if (len > my_max[q]) my_max[q] = len;
 }
 
-// Per-position sums held in registers: lane `sub` of a quarter-warp owns positions
-// 32*st + 4*sub + k (k < 4) for st < REG_STEPS.
-struct PosAcc {
-  uint32_t a[REG_STEPS][4];
-};
-__device__ __forceinline__ void flush_pos_acc(Smem& sm, PosAcc& acc, int sub) {
-#pragma unroll
-  for (int st = 0; st < REG_STEPS; st++)
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      if (acc.a[st][k]) atomicAdd(&sm.pos_sum[32 * st + 4 * sub + k], acc.a[st][k]);
-      acc.a[st][k] = 0;
-    }
+// 16 bytes into the lane-striped histogram at hbase (bytes < 128): one IDP.4A and one shared atomic per byte.
+__device__ __forceinline__ void hist16(const Sel& k, const uint4& v, uint32_t hbase) {
+  red_inc(__dp4a(v.x, k.h0, hbase)); red_inc(__dp4a(v.x, k.h1, hbase)); red_inc(__dp4a(v.x, k.h2, hbase)); red_inc(__dp4a(v.x, k.h3, hbase));
+  red_inc(__dp4a(v.y, k.h0, hbase)); red_inc(__dp4a(v.y, k.h1, hbase)); red_inc(__dp4a(v.y, k.h2, hbase)); red_inc(__dp4a(v.y, k.h3, hbase));
+  red_inc(__dp4a(v.z, k.h0, hbase)); red_inc(__dp4a(v.z, k.h1, hbase)); red_inc(__dp4a(v.z, k.h2, hbase)); red_inc(__dp4a(v.z, k.h3, hbase));
+  red_inc(__dp4a(v.w, k.h0, hbase)); red_inc(__dp4a(v.w, k.h1, hbase)); red_inc(__dp4a(v.w, k.h2, hbase)); red_inc(__dp4a(v.w, k.h3, hbase));
 }
-
-// One 32-byte step of a line for one quarter-warp lane: 4 line bytes at shared address al (+4 for the
-// funnel), `rem` = line bytes left from this lane's word on.  Bytes past the line end are forced to
-// 0 and counted in histogram bin 0 ("junk"); the caller keeps the junk total and subtracts it at the
-// end, so the step has no branches and no predicates.
-// One 32-byte step of a line for one quarter-warp lane: 4 line bytes at shared address al (+4 for the
-// funnel).  MASKED steps force the bytes past the line end to 0; those are counted in histogram bin 0
-// ("junk"), the caller keeps the junk total and subtracts it at the end -- no predicates in the step.
-// msh = 32 - 8*(line bytes left from this lane's word on): <= 0 full word, >= 32 nothing left.
-template <bool QUAL, bool MASKED>
-__device__ __forceinline__ void line_step(const Sel& k, uint32_t al, uint32_t sh, int msh, uint32_t hbase, uint32_t* acc4) {
-  uint32_t w = __funnelshift_r(lds32(al), lds32(al + 4), sh);
-  if (MASKED) w &= __funnelshift_rc(0xFFFFFFFFu, 0u, (uint32_t)min(max(msh, 0), 32));
-  red_inc(__dp4a(w, k.h0, hbase));
-  red_inc(__dp4a(w, k.h1, hbase));
-  red_inc(__dp4a(w, k.h2, hbase));
-  red_inc(__dp4a(w, k.h3, hbase));
-  if (QUAL) {
-    acc4[0] = __dp4a(w, k.p0, acc4[0]);
-    acc4[1] = __dp4a(w, k.p1, acc4[1]);
-    acc4[2] = __dp4a(w, k.p2, acc4[2]);
-    acc4[3] = __dp4a(w, k.p3, acc4[3]);
-  }
+// The four bytes of word w (bytes 4W..4W+3 of the group) added to the per-position cells r0 + PT_STRIDE*(4W + k).
+template <int W>
+__device__ __forceinline__ void pos4(const Sel& k, uint32_t w, uint32_t r0) {
+  red_add_at<4 * PT_STRIDE * (4 * W + 0)>(r0, w & 0xFFu);
+  red_add_at<4 * PT_STRIDE * (4 * W + 1)>(r0, __dp4a(w, k.p1, 0u));
+  red_add_at<4 * PT_STRIDE * (4 * W + 2)>(r0, __dp4a(w, k.p2, 0u));
+  red_add_at<4 * PT_STRIDE * (4 * W + 3)>(r0, w >> 24);
 }
-
-// Four lines of one class per warp (a quarter-warp each): n content bytes at shared address a0
-// (n == 0: this quarter-warp has no line).  Steps that are full for all four lines run unmasked.
-// Returns the histogram slots touched by this lane.
-template <bool QUAL>
-__device__ __forceinline__ uint32_t lines_fast(Smem& sm, const Sel& k, uint32_t a0, int n, int sub, uint32_t hbase, PosAcc& acc) {
-  const uint32_t sh = (a0 & 3u) * 8u;
-  const uint32_t al = (a0 & ~3u) + 4u * sub;
-  const int rem = n - 4 * sub;
-  const int msh = 32 - 8 * rem;  // mask shift of step 0; each step adds 256
-  // steps in the register window: nf full ones, then at most one partial one (ms - nf <= 1).  The
-  // four lines of a warp usually have the same length, so this per-quarter-warp control flow rarely diverges.
-  const int ms = min((n + 31) >> 5, REG_STEPS), nf = min(n >> 5, REG_STEPS);
-  switch (nf) {
-    case 5: line_step<QUAL, false>(k, al + 128, sh, 0, hbase, acc.a[4]);
-    case 4: line_step<QUAL, false>(k, al + 96, sh, 0, hbase, acc.a[3]);
-    case 3: line_step<QUAL, false>(k, al + 64, sh, 0, hbase, acc.a[2]);
-    case 2: line_step<QUAL, false>(k, al + 32, sh, 0, hbase, acc.a[1]);
-    case 1: line_step<QUAL, false>(k, al, sh, 0, hbase, acc.a[0]);
-    default: break;
-  }
-  if (ms > nf) {
-    switch (nf) {
-      case 0: line_step<QUAL, true>(k, al, sh, msh, hbase, acc.a[0]); break;
-      case 1: line_step<QUAL, true>(k, al + 32, sh, msh + 256, hbase, acc.a[1]); break;
-      case 2: line_step<QUAL, true>(k, al + 64, sh, msh + 512, hbase, acc.a[2]); break;
-      case 3: line_step<QUAL, true>(k, al + 96, sh, msh + 768, hbase, acc.a[3]); break;
-      default: line_step<QUAL, true>(k, al + 128, sh, msh + 1024, hbase, acc.a[4]); break;
-    }
-  }
-  if (n > 32 * REG_STEPS) {  // positions beyond the register window (reads longer than 160)
-    uint32_t a2 = al + 32 * REG_STEPS;
-    int r2 = rem - 32 * REG_STEPS;
-    for (int base = 32 * REG_STEPS; base < n; base += 32) {
-      const uint32_t w = __funnelshift_r(lds32(a2), lds32(a2 + 4), sh);
-#pragma unroll
-      for (int kk = 0; kk < 4; kk++) {
-        if (r2 > kk) {
-          const uint32_t b = (w >> (8 * kk)) & 0xFFu;
-          red_inc(hbase + (b << 7));
-          if (QUAL) {
-            const int p = base + 4 * sub + kk;
-            atomicAdd(&sm.pos_sum[p < POS_BINS ? p : POS_BINS], b);
-          }
-        }
-      }
-      a2 += 32;
-      r2 -= 32;
-    }
-  }
-  return 4u * (uint32_t)ms;
-}
-
-// A run of content bytes [vs, ve) processed by `nthr` threads (rank `r`): aligned 16-byte groups
-// through the striped histogram, the ragged ends byte-wise.  Bytes < 128 guaranteed by the caller.
-__device__ __forceinline__ void piece_coop(Smem& sm, const uint8_t* buf, int vs, int ve, u64 vpos, int cls,
-                                           uint32_t hbase, int r, int nthr) {
-  const int body0 = (vs + 15) & ~15, body1 = ve & ~15;
-  if (body1 > body0) {
-    for (int o = body0 + r * 16; o < body1; o += nthr * 16) {
-      const uint4 v = *reinterpret_cast<const uint4*>(buf + o);
-      const uint32_t ww[4] = {v.x, v.y, v.z, v.w};
-      const u64 p = vpos + (u64)(o - vs);
-      uint32_t over = 0;
-#pragma unroll
-      for (int x = 0; x < 4; x++) {
-        red_inc(__dp4a(ww[x], 0x00000080u, hbase));
-        red_inc(__dp4a(ww[x], 0x00008000u, hbase));
-        red_inc(__dp4a(ww[x], 0x00800000u, hbase));
-        red_inc(__dp4a(ww[x], 0x80000000u, hbase));
-        over = __dp4a(ww[x], 0x01010101u, over);
-      }
-      if (cls == 3) {
-        if (p >= (u64)POS_BINS) atomicAdd(&sm.pos_sum[POS_BINS], over);
-        else {
-#pragma unroll
-          for (int x = 0; x < 16; x++) {
-            const u64 pp = p + x;
-            atomicAdd(&sm.pos_sum[pp < (u64)POS_BINS ? (uint32_t)pp : (uint32_t)POS_BINS], (ww[x >> 2] >> (8 * (x & 3))) & 0xFFu);
-          }
-        }
-      }
-    }
-    for (int o = vs + r; o < body0; o += nthr) account_byte(sm.ghist, sm.pos_sum, cls, buf[o], vpos + (u64)(o - vs));
-    for (int o = body1 + r; o < ve; o += nthr) account_byte(sm.ghist, sm.pos_sum, cls, buf[o], vpos + (u64)(o - vs));
+// Per-position sums of the bytes [lo, hi) of a quality group (bytes outside are zero in v): q = 16 + position
+// of the group's byte 0.  Inside the table: 16 atomics with immediate offsets (consecutive groups of a line hit
+// consecutive banks); beyond POS_BINS: the overflow bin; the one group per long line that straddles: byte-wise.
+__device__ __forceinline__ void pos16(Smem& sm, const Sel& k, const uint4& v, uint32_t ga, uint32_t ptab_s,
+                                      uint32_t q, uint32_t lo, uint32_t hi, u64& over) {
+  if (q + hi <= (uint32_t)POS_BINS + 16u) {
+    const uint32_t r0 = ptab_s + 4u * ((q & 15u) * PT_STRIDE + (q >> 4));
+    pos4<0>(k, v.x, r0); pos4<1>(k, v.y, r0); pos4<2>(k, v.z, r0); pos4<3>(k, v.w, r0);
+  } else if (q + lo >= (uint32_t)POS_BINS + 16u) {
+    over += __dp4a(v.x, 0x01010101u, __dp4a(v.y, 0x01010101u, __dp4a(v.z, 0x01010101u, __dp4a(v.w, 0x01010101u, 0u))));
   } else {
-    for (int o = vs + r; o < ve; o += nthr) account_byte(sm.ghist, sm.pos_sum, cls, buf[o], vpos + (u64)(o - vs));
+    for (uint32_t x = lo; x < hi; x++) {
+      const uint32_t b = lds8(ga + x), p = q - 16u + x;
+      if (p < (uint32_t)POS_BINS) atomicAdd(&sm.ptab[pt_cell(p)], b);
+      else over += b;
+    }
   }
 }
 
@@ -339,7 +284,7 @@ __device__ __forceinline__ int byte_after_tile(const ScanArgs& a, const TileMeta
 // bytes taken one at a time.  Exact for any content; also keeps the line-length tables.
 __device__ __noinline__ void tile_walker(Smem& sm, const ScanArgs& a, const uint8_t* buf, const TileMeta& m, uint32_t phase,
                                          const uint32_t* bitmap, const uint16_t* wordbase, int r, int nthr,
-                                         u64* my_min, u64* my_max) {
+                                         u64* my_min, u64* my_max, u64& over) {
   const int nwords = (m.hi + 31) >> 5;
   for (int w = r; w < nwords; w += nthr) {
     const int o0 = w * 32 > m.lo ? w * 32 : m.lo;
@@ -373,25 +318,38 @@ __device__ __noinline__ void tile_walker(Smem& sm, const ScanArgs& a, const uint
           const int nx = (o + 1 < m.hi) ? (int)buf[o + 1] : byte_after_tile(a, m);
           content = nx != '\n' && nx >= 0;
         }
-        if (content) account_byte(sm.ghist, sm.pos_sum, cls, b, pos);
+        if (content) account_byte_tab(sm, cls, b, pos, over);
       }
       pos++;
     }
   }
 }
 
-__device__ __forceinline__ void flush_pos_sum_to(Smem& sm, u64* block, int tid) {
-  for (int i = tid; i <= POS_BINS; i += THREADS) {
-    uint32_t v = sm.pos_sum[i];
-    if (v) { block[OFF_POS_SUM + i] += v; sm.pos_sum[i] = 0; }
+// Adds the per-position table to the span block and clears it (position p: its cell and the alias cell).
+__device__ __forceinline__ void flush_pos_tab(Smem& sm, u64* block, int tid) {
+  for (int p = tid; p < POS_BINS; p += THREADS) {
+    const uint32_t c0 = pt_cell((uint32_t)p);
+    u64 v = sm.ptab[c0];
+    sm.ptab[c0] = 0;
+    if ((p & 15) != 15) {  // row r+16 of the previous column is the same position
+      const uint32_t c1 = c0 + 16u * PT_STRIDE - 1u;
+      v += sm.ptab[c1];
+      sm.ptab[c1] = 0;
+    }
+    if (v) block[OFF_POS_SUM + p] += v;
   }
+}
+
+__device__ __forceinline__ uint32_t part_entry(int g, int lo, int hi, uint32_t q) {
+  return (uint32_t)g | ((uint32_t)lo << 10) | ((uint32_t)hi << 14) | ((q < 1023u ? q : 1023u) << 19);
 }
 
 __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, const int pass) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, sub = tid & 7;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool scanner = warp < SCAN_WARPS;
+  const bool liner = warp < LINE_WARPS;
   const int span = blockIdx.x;
   SpanDesc& desc = a.desc[span];
   if (pass == 1 && desc.state != SPAN_RESCAN) return;
@@ -405,8 +363,13 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
 
   for (int i = tid; i < 2 * HB * 32; i += THREADS) (&sm.hist[0][0])[i] = 0;
   for (int i = tid; i < 512; i += THREADS) (&sm.ghist[0][0])[i] = 0;
-  for (int i = tid; i <= POS_BINS; i += THREADS) { sm.seq_len[i] = 0; sm.qual_len[i] = 0; sm.pos_sum[i] = 0; }
+  for (int i = tid; i < POS_BINS + 2; i += THREADS) { sm.seq_len[i] = 0; sm.qual_len[i] = 0; }
+  for (int i = tid; i < PT_WORDS; i += THREADS) sm.ptab[i] = 0;
   if (tid < LOG2_BINS) sm.seq_log2[tid] = 0;
+  if (tid < 17 * 4) {  // masks[n]: 0xFF in the first n bytes
+    const int n = tid >> 2, w = tid & 3, k = n - 4 * w;
+    (&sm.masks[0].x)[tid] = k >= 4 ? 0xFFFFFFFFu : (k <= 0 ? 0u : ((1u << (8 * k)) - 1u));
+  }
   if (pass == 0) {
     for (int i = tid; i < BLOCK_WORDS; i += THREADS) block[i] = (i == OFF_SEQ_LEN_MIN || i == OFF_QUAL_LEN_MIN) ? ~0ull : 0ull;
   }
@@ -414,9 +377,12 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
     sm.len_min[0] = sm.len_min[1] = ~0ull;
     sm.len_max[0] = sm.len_max[1] = 0;
     sm.bytes_since_flush = 0;
-    sm.hiflag[0] = sm.hiflag[1] = 0;
+    sm.hiflag = 0;
     sm.run_L = 0; sm.run_open = 0; sm.head_len = 0; sm.head_done = 0;
-    sm.junk[0] = sm.junk[1] = 0;
+    sm.junk[0] = sm.junk[1] = 0; sm.pos_over = 0;
+    sm.meta[0].walker = sm.meta[1].walker = 0;
+    sm.meta[0].R = sm.meta[1].R = 0;
+    sm.meta[0].nfull = sm.meta[1].nfull = 0;
     for (int k = 0; k < 4; k++) { sm.ksel[k] = 0x80u << (8 * k); sm.ksel[4 + k] = 1u << (8 * k); }
     for (int s = 0; s < NSTAGE; s++) mbar_init(&sm.full_bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -428,21 +394,19 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
     }
   }
   u64 my_min[2] = {~0ull, ~0ull}, my_max[2] = {0, 0};  // line-length extrema seen by this thread
-  u64 slots[2] = {0, 0}, valid[2] = {0, 0};             // histogram slots touched / line bytes (junk = slots - valid)
-  PosAcc acc;
-#pragma unroll
-  for (int st = 0; st < REG_STEPS; st++)
-#pragma unroll
-    for (int k = 0; k < 4; k++) acc.a[st][k] = 0;
+  uint32_t junk_s = 0, junk_q = 0;                      // histogram slots of masked bytes (counted in bin 0)
+  u64 over = 0;                                         // quality bytes at positions >= POS_BINS
   const uint32_t sm0 = smem_u32(smem_raw);
   const uint32_t hb_seq = sm0 + (uint32_t)offsetof(Smem, hist) + 4u * lane;
   const uint32_t hb_qual = hb_seq + HB * 32 * 4;
+  const uint32_t ptab_s = sm0 + (uint32_t)offsetof(Smem, ptab);
+  const uint32_t masks_s = sm0 + (uint32_t)offsetof(Smem, masks);
   __syncthreads();
   Sel ksel;
   {
     const uint32_t ks = sm0 + (uint32_t)offsetof(Smem, ksel);
     ksel.h0 = lds32(ks); ksel.h1 = lds32(ks + 4); ksel.h2 = lds32(ks + 8); ksel.h3 = lds32(ks + 12);
-    ksel.p0 = lds32(ks + 16); ksel.p1 = lds32(ks + 20); ksel.p2 = lds32(ks + 24); ksel.p3 = lds32(ks + 28);
+    ksel.p1 = lds32(ks + 20); ksel.p2 = lds32(ks + 24);
   }
 
   // pipeline: iteration `it` classifies tile B = t0+it (stage it%3, slot it&1) while the workers
@@ -470,16 +434,17 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
       hiB = (tileB + 1 < a.ntiles) ? TILE : (int)(a.end - toffB);
       mbar_wait(&sm.full_bar[stB], (par_bits >> stB) & 1u);
       par_bits ^= 1u << stB;
-      const uint8_t* buf = &sm.buf[stB][PAD];
-      uint16_t* bm16 = reinterpret_cast<uint16_t*>(sm.bitmap[sb]);
+      const uint32_t bufB_s = sm0 + (uint32_t)offsetof(Smem, buf) + (uint32_t)stB * STAGE_BYTES + PAD;
+      uint16_t* bm16 = reinterpret_cast<uint16_t*>(sm.bitmap);
       uint32_t hib = 0;
       if (loB == 0 && hiB == TILE) {  // interior tile: no edge handling
 #pragma unroll
         for (int j = 0; j < GPT; j++) {
           const int g = tid + j * THREADS;
-          const uint4 v = *reinterpret_cast<const uint4*>(buf + g * 16);
-          hib |= (v.x | v.y) | (v.z | v.w);
-          bm16[g] = (uint16_t)nl_mask16(v);
+          const uint4 v = lds128(bufB_s + 16u * (uint32_t)g);
+          const uint32_t o = (v.x | v.y) | (v.z | v.w);
+          hib |= o;
+          bm16[g] = (uint16_t)((o & 0x80808080u) ? nl_mask16(v) : nl_mask16_ascii(v));
         }
       } else {
 #pragma unroll
@@ -488,221 +453,261 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
           const int off = g * 16;
           uint32_t m = 0;
           if (off < hiB && off + 16 > loB) {
-            const uint4 v = *reinterpret_cast<const uint4*>(buf + off);
+            const uint4 v = lds128(bufB_s + 16u * (uint32_t)g);
             m = nl_mask16(v);
-            hib |= (v.x | v.y) | (v.z | v.w);
             int lo_k = loB - off; lo_k = lo_k < 0 ? 0 : lo_k;
             int hi_k = hiB - off; hi_k = hi_k > 16 ? 16 : hi_k;
-            m &= ((1u << hi_k) - 1u) & ~((1u << lo_k) - 1u);
+            const uint32_t valid = ((1u << hi_k) - 1u) & ~((1u << lo_k) - 1u);
+            m &= valid;
+            // high bytes only matter inside the valid range (stale shared memory beyond it)
+            const uint4 ml = sm.masks[lo_k], mh = sm.masks[hi_k];
+            hib |= ((v.x & mh.x & ~ml.x) | (v.y & mh.y & ~ml.y)) | ((v.z & mh.z & ~ml.z) | (v.w & mh.w & ~ml.w));
           }
           bm16[g] = (uint16_t)m;
         }
       }
-      if (hib & 0x80808080u) sm.hiflag[sb] = 1;
+      if (hib & 0x80808080u) sm.hiflag = 1;
     }
 
-    if (scanner) {
+    if (liner) {
       // =====================================================================================
-      // SCANNER warps: newline index of tile B, span-running carry, line-length tables, pieces
+      // SCANNER warps: newline index of tile B and the span-running carry
       // =====================================================================================
-      bar_sync(1, THREADS);  // bitmap of tile B complete (workers only arrive)
-      if (haveB) {
-        const uint8_t* buf = &sm.buf[stB][PAD];
-        const uint4 bw4 = *reinterpret_cast<const uint4*>(&sm.bitmap[sb][tid * WPS]);
-        const uint32_t bw[WPS] = {bw4.x, bw4.y, bw4.z, bw4.w};
-        const uint32_t c0 = __popc(bw[0]), c1 = __popc(bw[1]), c2 = __popc(bw[2]), c3 = __popc(bw[3]);
-        const uint32_t c = c0 + c1 + c2 + c3;
-        const uint32_t inc = warp_incl_scan(c, lane);
-        int my_last = -1;
+      if (scanner) {
+        bar_sync(1, THREADS);  // bitmap of tile B complete (the other warps only arrive)
+        if (haveB) {
+          const uint4 bw4 = *reinterpret_cast<const uint4*>(&sm.bitmap[tid * WPS]);
+          const uint32_t bw[WPS] = {bw4.x, bw4.y, bw4.z, bw4.w};
+          const uint32_t c0 = __popc(bw[0]), c1 = __popc(bw[1]), c2 = __popc(bw[2]), c3 = __popc(bw[3]);
+          const uint32_t c = c0 + c1 + c2 + c3;
+          const uint32_t inc = warp_incl_scan(c, lane);
+          int my_last = -1;
 #pragma unroll
-        for (int x = 0; x < WPS; x++) if (bw[x]) my_last = (tid * WPS + x) * 32 + 31 - __clz(bw[x]);
-        my_last = __reduce_max_sync(0xffffffffu, my_last);
-        if (lane == 31) { sm.scan_tot[warp] = inc; sm.scan_last[warp] = my_last; }
-        bar_sync(2, SCAN_THREADS);
-        uint32_t wbase = 0, T = 0;
-        int last_nl = -1;
+          for (int x = 0; x < WPS; x++) if (bw[x]) my_last = (tid * WPS + x) * 32 + 31 - __clz(bw[x]);
+          my_last = __reduce_max_sync(0xffffffffu, my_last);
+          if (lane == 31) { sm.scan_tot[warp] = inc; sm.scan_last[warp] = my_last; }
+          bar_sync(2, SCAN_THREADS);
+          uint32_t wbase = 0, T = 0;
+          int last_nl = -1;
 #pragma unroll
-        for (int w = 0; w < SCAN_WARPS; w++) {
-          const uint32_t x = sm.scan_tot[w];
-          if (w < warp) wbase += x;
-          T += x;
-          last_nl = max(last_nl, sm.scan_last[w]);
-        }
-        uint32_t first = wbase + inc - c;  // index of this thread's first newline
-        {
-          uint16_t* wb = &sm.wordbase[sb][tid * WPS];
-          wb[0] = (uint16_t)first; wb[1] = (uint16_t)(first + c0); wb[2] = (uint16_t)(first + c0 + c1); wb[3] = (uint16_t)(first + c0 + c1 + c2);
-        }
-        const bool walker = T > (uint32_t)NL_CAP || sm.hiflag[sb] != 0 || (a.dbg & 2);
-        if (!walker) {
+          for (int w = 0; w < SCAN_WARPS; w++) {
+            const uint32_t x = sm.scan_tot[w];
+            if (w < warp) wbase += x;
+            T += x;
+            last_nl = max(last_nl, sm.scan_last[w]);
+          }
+          uint32_t first = wbase + inc - c;  // index of this thread's first newline
+          const bool walker = T > (uint32_t)NL_CAP || sm.hiflag != 0 || (a.dbg & 2);
+          if (walker) {  // the walker wants the newline count before every bitmap word (scratch: the entry list)
+            uint16_t* wb = reinterpret_cast<uint16_t*>(sm.full[sb]) + tid * WPS;
+            wb[0] = (uint16_t)first; wb[1] = (uint16_t)(first + c0); wb[2] = (uint16_t)(first + c0 + c1); wb[3] = (uint16_t)(first + c0 + c1 + c2);
+          } else {
 #pragma unroll
-          for (int x = 0; x < WPS; x++) {
-            uint32_t m = bw[x];
-            while (m) {
-              const int k = __ffs(m) - 1;
-              m &= m - 1;
-              sm.nl[sb][first] = (uint16_t)((tid * WPS + x) * 32 + k);
-              first++;
-            }
-          }
-        }
-        const u64 Lrel = sm.run_L, open = sm.run_open;  // before this tile (written last iteration)
-        TileMeta& m = sm.meta[sb];
-        if (tid == 0) {
-          m.Lrel = Lrel; m.open = open; m.toff = toffB; m.T = (int)T; m.lo = loB; m.hi = hiB;
-          m.walker = walker ? 1 : 0; m.npieces = walker ? 0 : 2; m.nrec = 0;
-          sm.hiflag[sb] = 0;
-          sm.bytes_since_flush += (uint32_t)(hiB - loB);
-        }
-        bar_sync(2, SCAN_THREADS);  // nl index, meta and the old running carry are visible / consumed
-        if (tid == 0) {
-          sm.run_L = Lrel + T;
-          sm.run_open = T ? (u64)(hiB - (last_nl + 1)) : open + (u64)(hiB - loB);
-          if (!sm.head_done) {  // bytes of the span before its first newline (the stitch kernel's share)
-            if (T) {
-              int first_nl = 0;  // lowest set bit of the bitmap (the newline index is not built for walker tiles)
-              for (int w = 0; w < BM_WORDS; w++) { const uint32_t x = sm.bitmap[sb][w]; if (x) { first_nl = w * 32 + __ffs(x) - 1; break; } }
-              sm.head_len = open + (u64)(first_nl - loB);
-              sm.head_done = 1;
-            } else {
-              sm.head_len = open + (u64)(hiB - loB);
-            }
-          }
-        }
-        if (walker) {
-        } else if (!count_only) {
-          const uint32_t ph = (uint32_t)((phase + Lrel) & 3);  // class of the tile's line 0
-          const int jr0 = (ph & 1) ? 2 : 1;                    // first interior line with an odd class
-          const int R = (int)T > jr0 ? ((int)T - jr0 + 1) >> 1 : 0;
-          if (tid == 0) {
-            // head piece: the line open at the tile start continues up to the first newline;
-            // tail piece: the line open at the tile end.  A '\r' directly before '\n' is dropped.
-            Piece hp; hp.vs = 0; hp.ve = 0; hp.line = 0; hp.pad = 0; hp.vpos = open;
-            {
-              const int e0 = T ? (int)sm.nl[sb][0] : hiB;
-              int ve = e0;
-              if (T) { if (ve > loB && buf[ve - 1] == '\r') ve--; }
-              else if (ve > loB && buf[ve - 1] == '\r') { const int nx = byte_after_tile(a, m); if (nx == '\n' || nx < 0) ve--; }
-              hp.vs = loB; hp.ve = ve;
-            }
-            sm.pieces[sb][0] = hp;
-            Piece tp; tp.vs = 0; tp.ve = 0; tp.line = T; tp.pad = 0; tp.vpos = 0;
-            int nrec = R;
-            if (T) {
-              const int vs = last_nl + 1;
-              int ve = hiB;
-              if (ve > vs && buf[ve - 1] == '\r') { const int nx = byte_after_tile(a, m); if (nx == '\n' || nx < 0) ve--; }
-              // the tail piece starts a line in this tile: when it has an odd class it is the next relevant
-              // line (line T), so it simply extends the record list; long ones stay cooperative pieces
-              const bool relevant = (int)T >= jr0 && (((int)T - jr0) & 1) == 0;
-              if (relevant && ve - vs <= LONG_SEG) { sm.rec[sb][R] = ve > vs ? ((uint32_t)vs | ((uint32_t)(ve - vs) << 14)) : 0u; nrec = R + 1; }
-              else { tp.vs = vs; tp.ve = ve; }
-            }
-            sm.pieces[sb][1] = tp;
-            m.nrec = nrec;
-          }
-          // line-length tables of the lines that end in tile B, records of the relevant interior lines;
-          // long interior lines join the pieces
-          for (int j = tid; j < (int)T; j += SCAN_THREADS) {
-            const int e = (int)sm.nl[sb][j];
-            const int s = j ? (int)sm.nl[sb][j - 1] + 1 : loB;
-            const u64 lidx = Lrel + (u64)j;
-            const int cls = (int)((ph + (uint32_t)j) & 3);
-            if ((cls & 1) && lidx != 0) {
-              const u64 raw = (j ? 0ull : open) + (u64)(e - s);
-              const int cr = (raw > 0 && byte_before(a, buf, m, e) == '\r') ? 1 : 0;
-              account_line_len(sm, cls, raw - (u64)cr, my_min, my_max);
-              if (j) {
-                uint32_t n = (uint32_t)(e - cr - s);
-                if (e - s > LONG_SEG) {
-                  const int q = atomicAdd(&m.npieces, 1);
-                  Piece p; p.vs = s; p.ve = e - cr; p.line = (uint32_t)j; p.pad = 0; p.vpos = 0;
-                  sm.pieces[sb][q] = p;
-                  n = 0;
-                }
-                sm.rec[sb][(j - jr0) >> 1] = (uint32_t)s | (n << 14);
+            for (int x = 0; x < WPS; x++) {
+              uint32_t m = bw[x];
+              while (m) {
+                const int k = __ffs(m) - 1;
+                m &= m - 1;
+                sm.nl[first] = (uint16_t)((tid * WPS + x) * 32 + k);
+                first++;
               }
+            }
+          }
+          if (tid == 0) {
+            const u64 Lrel = sm.run_L, open = sm.run_open;  // before this tile
+            TileMeta& m = sm.meta[sb];
+            const uint32_t ph = (uint32_t)((phase + Lrel) & 3);  // class of the tile's line 0
+            const int jr0 = (ph & 1) ? 0 : 1;                    // first line of the tile with an odd class
+            m.Lrel = Lrel; m.open = open; m.toff = toffB; m.T = (int)T; m.lo = loB; m.hi = hiB;
+            m.walker = (walker && !count_only) ? 1 : 0;
+            m.R = (walker || count_only) ? 0 : ((int)T + 2 - jr0) >> 1;
+            m.first_q = ((ph + (uint32_t)jr0) & 3) == 3;
+            m.nfull = 0;
+            sm.bytes_since_flush += (uint32_t)(hiB - loB);
+            sm.run_L = Lrel + T;
+            sm.run_open = T ? (u64)(hiB - (last_nl + 1)) : open + (u64)(hiB - loB);
+            if (!sm.head_done) {  // bytes of the span before its first newline (the stitch kernel's share)
+              if (T) {
+                int first_nl = 0;  // lowest set bit of the bitmap (the newline index is not built for walker tiles)
+                for (int w = 0; w < BM_WORDS; w++) { const uint32_t x = sm.bitmap[w]; if (x) { first_nl = w * 32 + __ffs(x) - 1; break; } }
+                sm.head_len = open + (u64)(first_nl - loB);
+                sm.head_done = 1;
+              } else {
+                sm.head_len = open + (u64)(hiB - loB);
+              }
+            }
+          }
+        }
+      } else {
+        bar_arrive(1, THREADS);
+      }
+      bar_sync(3, LINE_THREADS);  // newline index and meta of tile B are visible to all line warps
+      if (tid == 0) sm.hiflag = 0;
+
+      // =====================================================================================
+      // LINE tasks of tile B: one thread per sequence / quality line with bytes in the tile
+      // =====================================================================================
+      const TileMeta& m = sm.meta[sb];
+      const int R = haveB ? m.R : 0;
+      if (R > 0) {
+        const uint8_t* buf = &sm.buf[stB][PAD];
+        const int T = m.T, lo = m.lo, hi = m.hi;
+        const u64 Lrel = m.Lrel, open = m.open;
+        const uint32_t ph = (uint32_t)((phase + Lrel) & 3);
+        const int jr0 = (ph & 1) ? 0 : 1;
+        uint32_t* fullv = sm.full[sb];
+        for (int base = warp * 32; base < R; base += LINE_THREADS) {
+          const int i = base + lane;
+          uint32_t nfull = 0, gf0 = 0, qf0 = 0, pe0 = 0, pe1 = 0;
+          bool qual = false;
+          if (i < R) {
+            const int j = jr0 + 2 * i;
+            qual = ((ph + (uint32_t)j) & 3) == 3;
+            const bool tail = j == T;  // the line still open at the tile end
+            const int e = tail ? hi : (int)sm.nl[j];
+            const int s = j ? (int)sm.nl[j - 1] + 1 : lo;
+            const u64 pre = j ? 0ull : open;
+            if (j != 0 || Lrel != 0) {  // line 0 of the span is the head fragment (stitch kernel)
+              int xe = e, cr = 0;
+              if (e > s) {
+                if (buf[e - 1] == '\r') {  // dropped when directly before '\n'; at the launch end: decided later
+                  if (!tail) { xe = e - 1; cr = 1; }
+                  else { const int nx = byte_after_tile(a, m); if (nx == '\n' || nx < 0) xe = e - 1; }
+                }
+              } else if (!tail && pre > 0) {
+                cr = byte_before(a, buf, m, e) == '\r';  // the '\r' ended the previous tile and was dropped there
+              }
+              if (!tail) account_line_len(sm, qual ? 3 : 1, pre + (u64)(e - s) - (u64)cr, my_min, my_max);
+              if (xe > s) {
+                const uint32_t poff = pre < 2048ull ? (uint32_t)pre : 2048u;
+                const int g0 = s >> 4, g1 = xe >> 4, a4 = s & 15, b4 = xe & 15;
+                const uint32_t q0 = 16u + poff - (uint32_t)a4;  // q of group g0
+                if (g0 == g1) {
+                  pe0 = part_entry(g0, a4, b4, q0);
+                } else {
+                  int gf = g0;
+                  if (a4) { pe0 = part_entry(g0, a4, 16, q0); gf = g0 + 1; }
+                  nfull = (uint32_t)(g1 - gf); gf0 = (uint32_t)gf; qf0 = q0 + 16u * (uint32_t)(gf - g0);
+                  if (b4) pe1 = part_entry(g1, 0, b4, q0 + 16u * (uint32_t)(g1 - g0));
+                }
+              }
+            }
+            uint32_t* ps = &sm.part[sb][qual ? 1 : 0][2 * (i >> 1)];
+            ps[0] = pe0; ps[1] = pe1;
+          }
+          // full entries: sequence entries grow from the front of the list, quality entries from its back
+          const uint32_t packed = qual ? (nfull << 16) : nfull;
+          const uint32_t inc = warp_incl_scan(packed, lane);
+          const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
+          uint32_t basep = 0;
+          if (lane == 0 && tot) basep = atomicAdd(&sm.meta[sb].nfull, tot);
+          basep = __shfl_sync(0xffffffffu, basep, 0);
+          const uint32_t excl = basep + inc - packed;
+          const uint32_t idx = qual ? (excl >> 16) : (excl & 0xFFFFu);
+          if (nfull <= 32u) {
+            for (uint32_t t = 0; t < nfull; t++) {
+              const uint32_t q = qf0 + 16u * t;
+              const uint32_t ent = (gf0 + t) | ((q < 1023u ? q : 1023u) << 10);
+              fullv[qual ? (uint32_t)(NGROUPS - 1) - (idx + t) : idx + t] = ent;
+            }
+          }
+          uint32_t longm = __ballot_sync(0xffffffffu, nfull > 32u);  // long lines: the warp writes their entries together
+          while (longm) {
+            const int src = __ffs(longm) - 1;
+            longm &= longm - 1;
+            const uint32_t n = __shfl_sync(0xffffffffu, nfull, src), g = __shfl_sync(0xffffffffu, gf0, src);
+            const uint32_t q1 = __shfl_sync(0xffffffffu, qf0, src), ix = __shfl_sync(0xffffffffu, idx, src);
+            const bool ql = __shfl_sync(0xffffffffu, (int)qual, src) != 0;
+            for (uint32_t t = lane; t < n; t += 32) {
+              const uint32_t q = q1 + 16u * t;
+              const uint32_t ent = (g + t) | ((q < 1023u ? q : 1023u) << 10);
+              fullv[ql ? (uint32_t)(NGROUPS - 1) - (ix + t) : ix + t] = ent;
             }
           }
         }
       }
     } else {
       // =====================================================================================
-      // WORKER warps: byte statistics of tile C
+      // WORKER warps: byte statistics of tile C from its entry lists
       // =====================================================================================
       bar_arrive(1, THREADS);
-      if (haveC && !count_only) {
-        const TileMeta& m = sm.meta[sc];
-        const uint8_t* buf = &sm.buf[stC][PAD];
+      const TileMeta& m = sm.meta[sc];
+      if (haveC && m.R > 0) {
         const uint32_t buf_s = sm0 + (uint32_t)offsetof(Smem, buf) + (uint32_t)stC * STAGE_BYTES + PAD;
-        const int wr = tid - SCAN_THREADS;  // worker rank
-        if (m.walker) {
-          tile_walker(sm, a, buf, m, phase, sm.bitmap[sc], sm.wordbase[sc], wr, WORK_THREADS, my_min, my_max);
-        } else {
-          const uint32_t ph = (uint32_t)((phase + m.Lrel) & 3);  // class of the tile's line 0
-          // relevant line r (record r) is tile line jr0 + 2r; its class alternates with r.  A warp takes
-          // the four even (or the four odd) records of a group of eight: one class per warp.
-          const int jr0 = (ph & 1) ? 2 : 1;
-          const int R = m.nrec;
-          const int ww = warp - SCAN_WARPS, qi = lane >> 3;
-          static_assert((WORK_WARPS & 1) == 0, "a warp keeps its record parity (= class) for the whole tile");
-          const bool qual = ((ph + (uint32_t)(jr0 + 2 * (ww & 1))) & 3) == 3;  // warp-uniform, same for all its tasks
-          const uint32_t rec_s = sm0 + (uint32_t)offsetof(Smem, rec) + (uint32_t)sc * (uint32_t)sizeof(sm.rec[0]);
-          // task: records 8g + 2*qi + (ww & 1), g = ww>>1, ww>>1 + WORK_WARPS/2, ...
-          if (qual) {
-            for (int r = 8 * (ww >> 1) + (ww & 1) + 2 * qi; r - 2 * qi < R; r += 4 * WORK_WARPS) {
-              const uint32_t rc = r < R ? lds32(rec_s + 4u * (uint32_t)r) : 0u;
-              const int n = (int)(rc >> 14);
-              slots[1] += lines_fast<true>(sm, ksel, buf_s + (rc & 0x3FFFu), n, sub, hb_qual, acc);
-              if (sub == 0) valid[1] += (u64)min(n, 32 * REG_STEPS);
+        const int ww = warp - LINE_WARPS;
+        const uint32_t nf = m.nfull;
+        const int nfs = (int)(nf & 0xFFFFu), nfq = (int)(nf >> 16);
+        const int R = m.R, n_a = (R + 1) >> 1, n_b = R >> 1;  // lines of the class of task 0 / of the other class
+        const int npq = 2 * (m.first_q ? n_a : n_b), nps = 2 * (m.first_q ? n_b : n_a);
+        const int cA = (nfq + 31) >> 5, cB = cA + ((nfs + 31) >> 5), cC = cB + ((npq + 31) >> 5), cD = cC + ((nps + 31) >> 5);
+        const uint32_t* fullv = sm.full[sc];
+        int c = ww - (it % WORK_WARPS);  // rotate the chunk -> warp map from tile to tile
+        if (c < 0) c += WORK_WARPS;
+        for (; c < cD; c += WORK_WARPS) {
+          if (c < cA) {            // full quality groups
+            const int x = c * 32 + lane;
+            if (x < nfq) {
+              const uint32_t ent = fullv[NGROUPS - 1 - x];
+              const uint32_t ga = buf_s + 16u * (ent & 1023u);
+              const uint4 v = lds128(ga);
+              hist16(ksel, v, hb_qual);
+              pos16(sm, ksel, v, ga, ptab_s, ent >> 10, 0u, 16u, over);
             }
-          } else {
-            for (int r = 8 * (ww >> 1) + (ww & 1) + 2 * qi; r - 2 * qi < R; r += 4 * WORK_WARPS) {
-              const uint32_t rc = r < R ? lds32(rec_s + 4u * (uint32_t)r) : 0u;
-              const int n = (int)(rc >> 14);
-              slots[0] += lines_fast<false>(sm, ksel, buf_s + (rc & 0x3FFFu), n, sub, hb_seq, acc);
-              if (sub == 0) valid[0] += (u64)min(n, 32 * REG_STEPS);
+          } else if (c < cB) {     // full sequence groups
+            const int x = (c - cA) * 32 + lane;
+            if (x < nfs) {
+              const uint32_t ent = fullv[x];
+              const uint4 v = lds128(buf_s + 16u * (ent & 1023u));
+              hist16(ksel, v, hb_seq);
             }
-          }
-          // pieces: a short one is taken by a single warp, a long one by all worker threads together
-          const int np = m.npieces;
-          for (int k = 0; k < np; k++) {
-            const Piece p = sm.pieces[sc][k];
-            const u64 lidx = m.Lrel + p.line;
-            const int cls = (int)((phase + lidx) & 3);
-            const int len = p.ve - p.vs;
-            if (!(cls & 1) || lidx == 0 || len <= 0) continue;
-            if (len <= 512) {
-              if (ww == (k + (int)(m.toff >> 14)) % WORK_WARPS)
-                for (int o = p.vs + lane; o < p.ve; o += 32) account_byte(sm.ghist, sm.pos_sum, cls, buf[o], p.vpos + (u64)(o - p.vs));
-            } else {
-              piece_coop(sm, buf, p.vs, p.ve, p.vpos, cls, cls == 3 ? hb_qual : hb_seq, wr, WORK_THREADS);
+          } else {                 // partial groups: bytes [lo, hi) of the group, the others masked to zero (bin 0 = junk)
+            const bool ql = c < cC;
+            const int x = (c - (ql ? cB : cC)) * 32 + lane;
+            const uint32_t ent = x < (ql ? npq : nps) ? sm.part[sc][ql ? 1 : 0][x] : 0u;
+            if (ent) {
+              const uint32_t ga = buf_s + 16u * (ent & 1023u);
+              const uint32_t lo = (ent >> 10) & 15u, hi = (ent >> 14) & 31u;
+              uint4 v = lds128(ga);
+              const uint4 ml = lds128(masks_s + 16u * lo), mh = lds128(masks_s + 16u * hi);
+              v.x &= mh.x & ~ml.x; v.y &= mh.y & ~ml.y; v.z &= mh.z & ~ml.z; v.w &= mh.w & ~ml.w;
+              if (ql) {
+                hist16(ksel, v, hb_qual);
+                pos16(sm, ksel, v, ga, ptab_s, ent >> 19, lo, hi, over);
+                junk_q += 16u - (hi - lo);
+              } else {
+                hist16(ksel, v, hb_seq);
+                junk_s += 16u - (hi - lo);
+              }
             }
           }
         }
       }
     }
 
+    __syncthreads();
+    // ---- dense or high-byte tile B: the whole CTA walks it now (its bitmap is still in place) ----
+    if (haveB && sm.meta[sb].walker) {
+      tile_walker(sm, a, &sm.buf[stB][PAD], sm.meta[sb], phase, sm.bitmap, reinterpret_cast<const uint16_t*>(sm.full[sb]),
+                  tid, THREADS, my_min, my_max, over);
+      __syncthreads();
+    }
     // ---- end of iteration: tile C is consumed, B becomes C ----
     { const int t = stC; stC = stB; stB = stA; stA = t; }
-    __syncthreads();
     if (sm.bytes_since_flush > (1u << 24)) {  // keep the 32-bit per-position sums from overflowing
-      flush_pos_acc(sm, acc, sub);
-      __syncthreads();
-      flush_pos_sum_to(sm, block, tid);
+      flush_pos_tab(sm, block, tid);
       if (tid == 0) sm.bytes_since_flush = 0;
       __syncthreads();
     }
   }
 
   // ---- flush this span's counters into its block; pass 0 also records the span descriptor ----
-  if (!scanner) flush_pos_acc(sm, acc, sub);
   for (int q = 0; q < 2; q++) {
     if (my_min[q] != ~0ull) atomicMin(&sm.len_min[q], my_min[q]);
     if (my_max[q] != 0) atomicMax(&sm.len_max[q], my_max[q]);
-    const u64 j = slots[q] - valid[q];  // may wrap per thread; the sum over the CTA is the junk total
-    if (slots[q] | valid[q]) atomicAdd(&sm.junk[q], j);
   }
+  if (junk_s) atomicAdd(&sm.junk[0], (u64)junk_s);
+  if (junk_q) atomicAdd(&sm.junk[1], (u64)junk_q);
+  if (over) atomicAdd(&sm.pos_over, over);
   __syncthreads();
   if (pass == 0 && tid == 0) {
     desc.T = sm.run_L;
@@ -719,7 +724,7 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
 #pragma unroll 8
       for (int l = 0; l < 32; l++) s += hp[(l + bin) & 31];
     }
-    if (b == 0) s -= sm.junk[h];  // histogram slots past line ends were counted as byte 0
+    if (b == 0) s -= sm.junk[h];  // masked bytes of partial groups were counted as byte 0
     if (s) block[OFF_HIST_SEQ + bin] += s;
   }
   for (int i = tid; i <= POS_BINS; i += THREADS) {
@@ -727,8 +732,9 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
     if (sm.qual_len[i]) block[OFF_QUAL_LEN + i] += sm.qual_len[i];
   }
   if (tid < LOG2_BINS && sm.seq_log2[tid]) block[OFF_SEQ_LOG2 + tid] += sm.seq_log2[tid];
-  flush_pos_sum_to(sm, block, tid);
+  flush_pos_tab(sm, block, tid);
   if (tid == 0) {
+    if (sm.pos_over) block[OFF_POS_SUM + POS_BINS] += sm.pos_over;
     if (sm.len_min[0] < block[OFF_SEQ_LEN_MIN]) block[OFF_SEQ_LEN_MIN] = sm.len_min[0];
     if (sm.len_max[0] > block[OFF_SEQ_LEN_MAX]) block[OFF_SEQ_LEN_MAX] = sm.len_max[0];
     if (sm.len_min[1] < block[OFF_QUAL_LEN_MIN]) block[OFF_QUAL_LEN_MIN] = sm.len_min[1];
