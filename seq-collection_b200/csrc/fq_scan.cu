@@ -54,11 +54,13 @@ constexpr int LINE_WARPS = 6;                 // warps 0..LINE_WARPS-1 run the l
 constexpr int LINE_THREADS = LINE_WARPS * 32;
 constexpr int WORK_WARPS = NWARPS - LINE_WARPS;
 constexpr int GPT = TILE / 16 / THREADS;      // 16-byte groups per thread in K1a (2)
-constexpr int NGROUPS = TILE / 16;
 constexpr int BM_WORDS = TILE / 32;           // bitmap words per tile
 constexpr int WPS = BM_WORDS / SCAN_THREADS;  // bitmap words per scanner thread (4)
 constexpr int NL_CAP = 1024;                  // newline index capacity; denser tiles take the walker path
-constexpr int PART_CAP = NL_CAP / 2 + 8;      // partial-entry slots per class (two per line)
+constexpr int PART_CAP = NL_CAP / 2 + 8;      // partial-group slots per class (two per line)
+constexpr int REC_CAP = NL_CAP / 4 + 8;       // line records per class
+constexpr int KMAX = 32;                      // lines with more full groups are "long": taken by all worker warps together
+constexpr int LONG_CAP = 32;                  // long lines per tile (each has > KMAX * 16 bytes in the tile)
 constexpr int PAD = 16;
 constexpr int STAGE_BYTES = PAD + TILE + 16;
 constexpr int NSTAGE = 3;
@@ -98,21 +100,26 @@ struct TileMeta {
   int walker;   // 1: dense or high-byte tile -> generic bitmap walker
   int R;        // sequence / quality lines with bytes in the tile (line tasks)
   int first_q;  // line task 0 is a quality line (the classes of the tasks alternate)
-  uint32_t nfull;  // full-group entries: sequence | quality << 16
-  uint32_t pad;
+  uint32_t K;      // most full groups of a (not long) line of the tile: the workers map slot x -> (line x / K, group x % K)
+  uint32_t nlong;  // long lines of the tile
 };
 
-// Entries: a full entry is  group | q << 10 ; a partial entry is  group | lo << 10 | hi << 14 | q << 19
-// (bytes [lo, hi) of the group; 0 = empty slot).  q = 16 + (line position of the group's byte 0),
-// saturated at 1023 (positions >= POS_BINS all fall into the overflow bin).
+// What a line task leaves for the workers (per class):
+//   rec   first full group | full groups (0 for long lines) << 10 | q << 16      -- the line's aligned 16-byte groups
+//   part  group | lo << 10 | hi << 14 | q << 19  (0 = empty)                      -- bytes [lo, hi) of its first / last group
+//   longl first full group | full groups << 10 | q << 21 | class << 31           -- lines with more than KMAX full groups
+// q = 16 + (line position of the group's byte 0), saturated at 1023 (positions >= POS_BINS all fall into
+// the overflow bin).
 struct __align__(128) Smem {
   uint8_t buf[NSTAGE][STAGE_BYTES];  // tile stages; data at buf[s] + PAD
   uint32_t hist[2][HB * 32];         // [0] sequence, [1] quality; word index = byte*32 + lane
   uint32_t ghist[2][256];            // un-striped tables of the generic paths
   uint32_t bitmap[BM_WORDS];         // bit b of word w: byte 32*w+b is '\n'
   uint16_t nl[NL_CAP];
-  uint32_t full[2][NGROUPS];         // sequence entries from the front, quality entries from the back
-  uint32_t part[2][2][PART_CAP];     // [slot][class]
+  uint32_t rec[2][2][REC_CAP];       // [slot][class]
+  uint32_t part[2][2][PART_CAP];     // [slot][class]; walker tiles: scratch for the per-word newline counts
+  uint32_t longl[2][LONG_CAP];
+  uint32_t inv[KMAX + 1];            // ceil(2^32 / K)
   uint32_t seq_len[POS_BINS + 2];
   uint32_t qual_len[POS_BINS + 2];
   uint32_t seq_log2[LOG2_BINS];
@@ -133,22 +140,22 @@ static_assert(sizeof(Smem) <= 115712, "two CTAs per SM");
 
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(u64* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+__device__ __forceinline__ void mbar_init(uint32_t bar_s, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s), "r"(count));
 }
-__device__ __forceinline__ void mbar_expect_tx(u64* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar_s, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(u64* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar_s, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tFQ_WAIT:\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra FQ_DONE;\n\tbra FQ_WAIT;\n\tFQ_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+      "@p bra FQ_DONE;\n\tbra FQ_WAIT;\n\tFQ_DONE:\n\t}" ::"r"(bar_s), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, u64* bar) {
+__device__ __forceinline__ void tma_load_1d(uint32_t dst_s, const void* src, uint32_t bytes, uint32_t bar_s) {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of dst before the async write
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+               ::"r"(dst_s), "l"(src), "r"(bytes), "r"(bar_s) : "memory");
 }
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -344,6 +351,18 @@ __device__ __forceinline__ uint32_t part_entry(int g, int lo, int hi, uint32_t q
   return (uint32_t)g | ((uint32_t)lo << 10) | ((uint32_t)hi << 14) | ((q < 1023u ? q : 1023u) << 19);
 }
 
+// One aligned 16-byte group of a quality / sequence line through the tables.
+__device__ __forceinline__ void group_full(Smem& sm, const Sel& k, uint32_t ga, bool ql, uint32_t hb_seq, uint32_t ptab_s,
+                                           uint32_t q, u64& over) {
+  const uint4 v = lds128(ga);
+  if (ql) {
+    hist16(k, v, hb_seq + HB * 32 * 4);
+    pos16(sm, k, v, ga, ptab_s, q < 1023u ? q : 1023u, 0u, 16u, over);
+  } else {
+    hist16(k, v, hb_seq);
+  }
+}
+
 __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, const int pass) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
@@ -360,6 +379,9 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
   u64* block = (pass == 0 ? a.pending : a.committed) + (size_t)span * BLOCK_WORDS;
   const uint32_t t0 = (uint32_t)span * a.tps;
   const uint32_t t1 = min(a.ntiles, t0 + a.tps);
+  const uint32_t sm0 = smem_u32(smem_raw);
+  const uint32_t buf0_s = sm0 + (uint32_t)offsetof(Smem, buf) + PAD;
+  const uint32_t bar0_s = sm0 + (uint32_t)offsetof(Smem, full_bar);
 
   for (int i = tid; i < 2 * HB * 32; i += THREADS) (&sm.hist[0][0])[i] = 0;
   for (int i = tid; i < 512; i += THREADS) (&sm.ghist[0][0])[i] = 0;
@@ -369,6 +391,10 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
   if (tid < 17 * 4) {  // masks[n]: 0xFF in the first n bytes
     const int n = tid >> 2, w = tid & 3, k = n - 4 * w;
     (&sm.masks[0].x)[tid] = k >= 4 ? 0xFFFFFFFFu : (k <= 0 ? 0u : ((1u << (8 * k)) - 1u));
+  }
+  if (tid >= 128 && tid <= 128 + KMAX) {
+    const uint32_t k = (uint32_t)(tid - 128);
+    sm.inv[k] = k >= 2 ? (uint32_t)(((1ull << 32) + k - 1) / k) : 0u;
   }
   if (pass == 0) {
     for (int i = tid; i < BLOCK_WORDS; i += THREADS) block[i] = (i == OFF_SEQ_LEN_MIN || i == OFF_QUAL_LEN_MIN) ? ~0ull : 0ull;
@@ -382,23 +408,20 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
     sm.junk[0] = sm.junk[1] = 0; sm.pos_over = 0;
     sm.meta[0].walker = sm.meta[1].walker = 0;
     sm.meta[0].R = sm.meta[1].R = 0;
-    sm.meta[0].nfull = sm.meta[1].nfull = 0;
     for (int k = 0; k < 4; k++) { sm.ksel[k] = 0x80u << (8 * k); sm.ksel[4 + k] = 1u << (8 * k); }
-    for (int s = 0; s < NSTAGE; s++) mbar_init(&sm.full_bar[s], 1);
+    for (int s = 0; s < NSTAGE; s++) mbar_init(bar0_s + 8u * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (t0 < t1) {  // prologue: the first tile into stage 0
       const u64 toff = (u64)t0 * TILE;
       const uint32_t bytes = (uint32_t)((((a.end - toff) < (u64)TILE ? (a.end - toff) : (u64)TILE) + 15) & ~15ull);
-      mbar_expect_tx(&sm.full_bar[0], bytes);
-      tma_load_1d(&sm.buf[0][PAD], a.base + toff, bytes, &sm.full_bar[0]);
+      mbar_expect_tx(bar0_s, bytes);
+      tma_load_1d(buf0_s, a.base + toff, bytes, bar0_s);
     }
   }
   u64 my_min[2] = {~0ull, ~0ull}, my_max[2] = {0, 0};  // line-length extrema seen by this thread
   uint32_t junk_s = 0, junk_q = 0;                      // histogram slots of masked bytes (counted in bin 0)
   u64 over = 0;                                         // quality bytes at positions >= POS_BINS
-  const uint32_t sm0 = smem_u32(smem_raw);
   const uint32_t hb_seq = sm0 + (uint32_t)offsetof(Smem, hist) + 4u * lane;
-  const uint32_t hb_qual = hb_seq + HB * 32 * 4;
   const uint32_t ptab_s = sm0 + (uint32_t)offsetof(Smem, ptab);
   const uint32_t masks_s = sm0 + (uint32_t)offsetof(Smem, masks);
   __syncthreads();
@@ -412,18 +435,19 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
   // pipeline: iteration `it` classifies tile B = t0+it (stage it%3, slot it&1) while the workers
   // take tile C = B-1; the TMA of tile A = B+1 is started at the top.
   const int nt = (int)(t1 - t0);
-  uint32_t par_bits = 0;  // mbarrier parity per stage (bit s)
+  uint32_t par_bits = 0;          // mbarrier parity per stage (bit s)
   int stB = 0, stC = 2, stA = 1;  // stages of tiles B, C, A; rotated at the end of every iteration
   for (int it = 0; it <= nt; it++) {
     const int sb = it & 1, sc = sb ^ 1;
     const bool haveB = it < nt, haveC = it > 0;
     const uint32_t tileB = t0 + (uint32_t)it;
+    const uint32_t bufB_s = buf0_s + (uint32_t)stB * STAGE_BYTES;
 
     if (tid == 0 && it + 1 < nt) {  // stage stA held tile B-2, whose K2 finished last iteration
       const u64 noff = (u64)(tileB + 1) * TILE;
       const uint32_t bytes = (tileB + 2 < a.ntiles) ? (uint32_t)TILE : (uint32_t)(((a.end - noff) + 15) & ~15ull);
-      mbar_expect_tx(&sm.full_bar[stA], bytes);
-      tma_load_1d(&sm.buf[stA][PAD], a.base + noff, bytes, &sm.full_bar[stA]);
+      mbar_expect_tx(bar0_s + 8u * stA, bytes);
+      tma_load_1d(buf0_s + (uint32_t)stA * STAGE_BYTES, a.base + noff, bytes, bar0_s + 8u * stA);
     }
 
     // ---- K1a (all warps): newline masks of tile B's 16-byte groups -> bitmap ----
@@ -432,9 +456,8 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
     if (haveB) {
       loB = (tileB == 0) ? (int)a.lo0 : 0;
       hiB = (tileB + 1 < a.ntiles) ? TILE : (int)(a.end - toffB);
-      mbar_wait(&sm.full_bar[stB], (par_bits >> stB) & 1u);
+      mbar_wait(bar0_s + 8u * stB, (par_bits >> stB) & 1u);
       par_bits ^= 1u << stB;
-      const uint32_t bufB_s = sm0 + (uint32_t)offsetof(Smem, buf) + (uint32_t)stB * STAGE_BYTES + PAD;
       uint16_t* bm16 = reinterpret_cast<uint16_t*>(sm.bitmap);
       uint32_t hib = 0;
       if (loB == 0 && hiB == TILE) {  // interior tile: no edge handling
@@ -457,8 +480,7 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
             m = nl_mask16(v);
             int lo_k = loB - off; lo_k = lo_k < 0 ? 0 : lo_k;
             int hi_k = hiB - off; hi_k = hi_k > 16 ? 16 : hi_k;
-            const uint32_t valid = ((1u << hi_k) - 1u) & ~((1u << lo_k) - 1u);
-            m &= valid;
+            m &= ((1u << hi_k) - 1u) & ~((1u << lo_k) - 1u);
             // high bytes only matter inside the valid range (stale shared memory beyond it)
             const uint4 ml = sm.masks[lo_k], mh = sm.masks[hi_k];
             hib |= ((v.x & mh.x & ~ml.x) | (v.y & mh.y & ~ml.y)) | ((v.z & mh.z & ~ml.z) | (v.w & mh.w & ~ml.w));
@@ -498,8 +520,8 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
           }
           uint32_t first = wbase + inc - c;  // index of this thread's first newline
           const bool walker = T > (uint32_t)NL_CAP || sm.hiflag != 0 || (a.dbg & 2);
-          if (walker) {  // the walker wants the newline count before every bitmap word (scratch: the entry list)
-            uint16_t* wb = reinterpret_cast<uint16_t*>(sm.full[sb]) + tid * WPS;
+          if (walker) {  // the walker wants the newline count before every bitmap word (scratch: the partial-group slots)
+            uint16_t* wb = reinterpret_cast<uint16_t*>(&sm.part[sb][0][0]) + tid * WPS;
             wb[0] = (uint16_t)first; wb[1] = (uint16_t)(first + c0); wb[2] = (uint16_t)(first + c0 + c1); wb[3] = (uint16_t)(first + c0 + c1 + c2);
           } else {
 #pragma unroll
@@ -522,7 +544,7 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
             m.walker = (walker && !count_only) ? 1 : 0;
             m.R = (walker || count_only) ? 0 : ((int)T + 2 - jr0) >> 1;
             m.first_q = ((ph + (uint32_t)jr0) & 3) == 3;
-            m.nfull = 0;
+            m.K = 0; m.nlong = 0;
             sm.bytes_since_flush += (uint32_t)(hiB - loB);
             sm.run_L = Lrel + T;
             sm.run_open = T ? (u64)(hiB - (last_nl + 1)) : open + (u64)(hiB - loB);
@@ -547,30 +569,29 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
       // =====================================================================================
       // LINE tasks of tile B: one thread per sequence / quality line with bytes in the tile
       // =====================================================================================
-      const TileMeta& m = sm.meta[sb];
+      TileMeta& m = sm.meta[sb];
       const int R = haveB ? m.R : 0;
-      if (R > 0) {
+      if (warp * 32 < R) {
         const uint8_t* buf = &sm.buf[stB][PAD];
         const int T = m.T, lo = m.lo, hi = m.hi;
         const u64 Lrel = m.Lrel, open = m.open;
         const uint32_t ph = (uint32_t)((phase + Lrel) & 3);
         const int jr0 = (ph & 1) ? 0 : 1;
-        uint32_t* fullv = sm.full[sb];
         for (int base = warp * 32; base < R; base += LINE_THREADS) {
           const int i = base + lane;
-          uint32_t nfull = 0, gf0 = 0, qf0 = 0, pe0 = 0, pe1 = 0;
-          bool qual = false;
+          uint32_t nd = 0;
           if (i < R) {
             const int j = jr0 + 2 * i;
-            qual = ((ph + (uint32_t)j) & 3) == 3;
+            const bool qual = ((ph + (uint32_t)j) & 3) == 3;
             const bool tail = j == T;  // the line still open at the tile end
             const int e = tail ? hi : (int)sm.nl[j];
             const int s = j ? (int)sm.nl[j - 1] + 1 : lo;
             const u64 pre = j ? 0ull : open;
+            uint32_t nfull = 0, gf0 = 0, qf0 = 0, pe0 = 0, pe1 = 0;
             if (j != 0 || Lrel != 0) {  // line 0 of the span is the head fragment (stitch kernel)
               int xe = e, cr = 0;
               if (e > s) {
-                if (buf[e - 1] == '\r') {  // dropped when directly before '\n'; at the launch end: decided later
+                if (lds8(bufB_s + (uint32_t)e - 1u) == '\r') {  // dropped when directly before '\n'; at the launch end: decided later
                   if (!tail) { xe = e - 1; cr = 1; }
                   else { const int nx = byte_after_tile(a, m); if (nx == '\n' || nx < 0) xe = e - 1; }
                 }
@@ -592,78 +613,55 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
                 }
               }
             }
-            uint32_t* ps = &sm.part[sb][qual ? 1 : 0][2 * (i >> 1)];
+            const int cl = qual ? 1 : 0;
+            qf0 = qf0 < 1023u ? qf0 : 1023u;
+            if (nfull == 0) gf0 = 0;  // (gf0 may be one past the tile)
+            if (nfull > (uint32_t)KMAX) {
+              const uint32_t ix = atomicAdd(&m.nlong, 1u);
+              sm.longl[sb][ix] = gf0 | (nfull << 10) | (qf0 << 21) | ((uint32_t)cl << 31);
+            } else {
+              nd = nfull;
+            }
+            sm.rec[sb][cl][i >> 1] = gf0 | (nd << 10) | (qf0 << 16);
+            uint32_t* ps = &sm.part[sb][cl][2 * (i >> 1)];
             ps[0] = pe0; ps[1] = pe1;
           }
-          // full entries: sequence entries grow from the front of the list, quality entries from its back
-          const uint32_t packed = qual ? (nfull << 16) : nfull;
-          const uint32_t inc = warp_incl_scan(packed, lane);
-          const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
-          uint32_t basep = 0;
-          if (lane == 0 && tot) basep = atomicAdd(&sm.meta[sb].nfull, tot);
-          basep = __shfl_sync(0xffffffffu, basep, 0);
-          const uint32_t excl = basep + inc - packed;
-          const uint32_t idx = qual ? (excl >> 16) : (excl & 0xFFFFu);
-          if (nfull <= 32u) {
-            for (uint32_t t = 0; t < nfull; t++) {
-              const uint32_t q = qf0 + 16u * t;
-              const uint32_t ent = (gf0 + t) | ((q < 1023u ? q : 1023u) << 10);
-              fullv[qual ? (uint32_t)(NGROUPS - 1) - (idx + t) : idx + t] = ent;
-            }
-          }
-          uint32_t longm = __ballot_sync(0xffffffffu, nfull > 32u);  // long lines: the warp writes their entries together
-          while (longm) {
-            const int src = __ffs(longm) - 1;
-            longm &= longm - 1;
-            const uint32_t n = __shfl_sync(0xffffffffu, nfull, src), g = __shfl_sync(0xffffffffu, gf0, src);
-            const uint32_t q1 = __shfl_sync(0xffffffffu, qf0, src), ix = __shfl_sync(0xffffffffu, idx, src);
-            const bool ql = __shfl_sync(0xffffffffu, (int)qual, src) != 0;
-            for (uint32_t t = lane; t < n; t += 32) {
-              const uint32_t q = q1 + 16u * t;
-              const uint32_t ent = (g + t) | ((q < 1023u ? q : 1023u) << 10);
-              fullv[ql ? (uint32_t)(NGROUPS - 1) - (ix + t) : ix + t] = ent;
-            }
-          }
+          const uint32_t kmax = __reduce_max_sync(0xffffffffu, nd);
+          if (lane == 0 && kmax) atomicMax(&m.K, kmax);
         }
       }
     } else {
       // =====================================================================================
-      // WORKER warps: byte statistics of tile C from its entry lists
+      // WORKER warps: byte statistics of tile C from its line records
       // =====================================================================================
       bar_arrive(1, THREADS);
       const TileMeta& m = sm.meta[sc];
       if (haveC && m.R > 0) {
-        const uint32_t buf_s = sm0 + (uint32_t)offsetof(Smem, buf) + (uint32_t)stC * STAGE_BYTES + PAD;
+        const uint32_t buf_s = buf0_s + (uint32_t)stC * STAGE_BYTES;
         const int ww = warp - LINE_WARPS;
-        const uint32_t nf = m.nfull;
-        const int nfs = (int)(nf & 0xFFFFu), nfq = (int)(nf >> 16);
         const int R = m.R, n_a = (R + 1) >> 1, n_b = R >> 1;  // lines of the class of task 0 / of the other class
-        const int npq = 2 * (m.first_q ? n_a : n_b), nps = 2 * (m.first_q ? n_b : n_a);
-        const int cA = (nfq + 31) >> 5, cB = cA + ((nfs + 31) >> 5), cC = cB + ((npq + 31) >> 5), cD = cC + ((nps + 31) >> 5);
-        const uint32_t* fullv = sm.full[sc];
+        const int nlq = m.first_q ? n_a : n_b, nls = m.first_q ? n_b : n_a;
+        uint32_t K = m.K;
+        K = K == 1u ? 2u : K;
+        const uint32_t inv = sm.inv[K];
+        const int sq = nlq * (int)K, ss = nls * (int)K;
+        const int cA = (sq + 31) >> 5, cB = cA + ((ss + 31) >> 5), cC = cB + ((2 * nlq + 31) >> 5), cD = cC + ((2 * nls + 31) >> 5);
         int c = ww - (it % WORK_WARPS);  // rotate the chunk -> warp map from tile to tile
         if (c < 0) c += WORK_WARPS;
         for (; c < cD; c += WORK_WARPS) {
-          if (c < cA) {            // full quality groups
-            const int x = c * 32 + lane;
-            if (x < nfq) {
-              const uint32_t ent = fullv[NGROUPS - 1 - x];
-              const uint32_t ga = buf_s + 16u * (ent & 1023u);
-              const uint4 v = lds128(ga);
-              hist16(ksel, v, hb_qual);
-              pos16(sm, ksel, v, ga, ptab_s, ent >> 10, 0u, 16u, over);
-            }
-          } else if (c < cB) {     // full sequence groups
-            const int x = (c - cA) * 32 + lane;
-            if (x < nfs) {
-              const uint32_t ent = fullv[x];
-              const uint4 v = lds128(buf_s + 16u * (ent & 1023u));
-              hist16(ksel, v, hb_seq);
+          if (c < cB) {            // full groups: slot x = K * line + group
+            const bool ql = c < cA;
+            const int x = (c - (ql ? 0 : cA)) * 32 + lane;
+            if (x < (ql ? sq : ss)) {
+              const uint32_t line = __umulhi((uint32_t)x, inv), k = (uint32_t)x - line * K;
+              const uint32_t r = sm.rec[sc][ql ? 1 : 0][line];
+              if (k < ((r >> 10) & 63u))
+                group_full(sm, ksel, buf_s + 16u * ((r & 1023u) + k), ql, hb_seq, ptab_s, (r >> 16) + 16u * k, over);
             }
           } else {                 // partial groups: bytes [lo, hi) of the group, the others masked to zero (bin 0 = junk)
             const bool ql = c < cC;
             const int x = (c - (ql ? cB : cC)) * 32 + lane;
-            const uint32_t ent = x < (ql ? npq : nps) ? sm.part[sc][ql ? 1 : 0][x] : 0u;
+            const uint32_t ent = x < 2 * (ql ? nlq : nls) ? sm.part[sc][ql ? 1 : 0][x] : 0u;
             if (ent) {
               const uint32_t ga = buf_s + 16u * (ent & 1023u);
               const uint32_t lo = (ent >> 10) & 15u, hi = (ent >> 14) & 31u;
@@ -671,7 +669,7 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
               const uint4 ml = lds128(masks_s + 16u * lo), mh = lds128(masks_s + 16u * hi);
               v.x &= mh.x & ~ml.x; v.y &= mh.y & ~ml.y; v.z &= mh.z & ~ml.z; v.w &= mh.w & ~ml.w;
               if (ql) {
-                hist16(ksel, v, hb_qual);
+                hist16(ksel, v, hb_seq + HB * 32 * 4);
                 pos16(sm, ksel, v, ga, ptab_s, ent >> 19, lo, hi, over);
                 junk_q += 16u - (hi - lo);
               } else {
@@ -681,13 +679,21 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
             }
           }
         }
+        const uint32_t nlong = m.nlong;  // long lines: every worker warp takes every WORK_WARPS-th run of 32 groups
+        for (uint32_t l = 0; l < nlong; l++) {
+          const uint32_t r = sm.longl[sc][l];
+          const uint32_t n = (r >> 10) & 2047u, g0 = r & 1023u, q0 = (r >> 21) & 1023u;
+          const bool ql = (r >> 31) != 0;
+          for (uint32_t t = (uint32_t)(ww * 32 + lane); t < n; t += WORK_WARPS * 32)
+            group_full(sm, ksel, buf_s + 16u * (g0 + t), ql, hb_seq, ptab_s, q0 + 16u * t, over);
+        }
       }
     }
 
     __syncthreads();
     // ---- dense or high-byte tile B: the whole CTA walks it now (its bitmap is still in place) ----
     if (haveB && sm.meta[sb].walker) {
-      tile_walker(sm, a, &sm.buf[stB][PAD], sm.meta[sb], phase, sm.bitmap, reinterpret_cast<const uint16_t*>(sm.full[sb]),
+      tile_walker(sm, a, &sm.buf[stB][PAD], sm.meta[sb], phase, sm.bitmap, reinterpret_cast<const uint16_t*>(&sm.part[sb][0][0]),
                   tid, THREADS, my_min, my_max, over);
       __syncthreads();
     }
