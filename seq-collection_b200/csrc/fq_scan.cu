@@ -50,7 +50,7 @@ constexpr int THREADS = 512;
 constexpr int NWARPS = THREADS / 32;
 constexpr int SCAN_WARPS = 4;
 constexpr int SCAN_THREADS = SCAN_WARPS * 32;
-constexpr int LINE_WARPS = 6;                 // warps 0..LINE_WARPS-1 run the line tasks (the scanner warps first)
+constexpr int LINE_WARPS = 4;                 // warps 0..LINE_WARPS-1 run the line tasks (the scanner warps first)
 constexpr int LINE_THREADS = LINE_WARPS * 32;
 constexpr int WORK_WARPS = NWARPS - LINE_WARPS;
 constexpr int GPT = TILE / 16 / THREADS;      // 16-byte groups per thread in K1a (2)
@@ -105,7 +105,7 @@ struct TileMeta {
 };
 
 // What a line task leaves for the workers (per class):
-//   rec   first full group | full groups (0 for long lines) << 10 | q << 16      -- the line's aligned 16-byte groups
+//   rec   first full group << 4 | full groups (0 for long lines) << 14 | q << 20 -- the line's aligned 16-byte groups
 //   part  group | lo << 10 | hi << 14 | q << 19  (0 = empty)                      -- bytes [lo, hi) of its first / last group
 //   longl first full group | full groups << 10 | q << 21 | class << 31           -- lines with more than KMAX full groups
 // q = 16 + (line position of the group's byte 0), saturated at 1023 (positions >= POS_BINS all fall into
@@ -127,7 +127,7 @@ struct __align__(128) Smem {
   uint4 masks[17];                   // masks[n]: the first n bytes of a group
   TileMeta meta[2];
   uint32_t scan_tot[SCAN_WARPS];
-  int scan_last[SCAN_WARPS];
+  int last_nl;                       // position of the tile's last newline
   u64 full_bar[NSTAGE];              // mbarriers of the stages
   u64 len_min[2], len_max[2];        // [0] seq, [1] qual
   u64 run_L, run_open;               // span-running newline count / open-line bytes
@@ -174,6 +174,9 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ void sts16(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v) : "memory");
+}
 __device__ __forceinline__ void red_inc(uint32_t addr) {
   asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
 }
@@ -201,6 +204,39 @@ __device__ __forceinline__ uint32_t nl_mask16_ascii(const uint4& v) {
   uint32_t lo = __dp4a(nl_flags_ascii(v.x), 0x08040201u, __dp4a(nl_flags_ascii(v.y), 0x80402010u, 0u));
   uint32_t hi = __dp4a(nl_flags_ascii(v.z), 0x08040201u, __dp4a(nl_flags_ascii(v.w), 0x80402010u, 0u));
   return (lo >> 7) | (hi << 1);
+}
+__device__ __forceinline__ uint32_t bfind(uint32_t m) {  // index of the highest set bit, 0xFFFFFFFF for 0
+  uint32_t k;
+  asm("bfind.u32 %0, %1;" : "=r"(k) : "r"(m));
+  return k;
+}
+// The (up to) three highest newlines of bitmap word m -> nl[] slots ending at shared address `end`
+// (exclusive), positions relative to pos0; returns the bits that are left.
+__device__ __forceinline__ uint32_t nl_extract3(uint32_t m, uint32_t end, uint32_t pos0) {
+  {
+    const uint32_t k = bfind(m);
+    if (m) asm volatile("st.shared.u16 [%0+-2], %1;" ::"r"(end), "h"((uint16_t)(pos0 + k)) : "memory");
+    m &= ~(1u << (k & 31u));
+  }
+  {
+    const uint32_t k = bfind(m);
+    if (m) asm volatile("st.shared.u16 [%0+-4], %1;" ::"r"(end), "h"((uint16_t)(pos0 + k)) : "memory");
+    m &= ~(1u << (k & 31u));
+  }
+  {
+    const uint32_t k = bfind(m);
+    if (m) asm volatile("st.shared.u16 [%0+-6], %1;" ::"r"(end), "h"((uint16_t)(pos0 + k)) : "memory");
+    m &= ~(1u << (k & 31u));
+  }
+  return m;
+}
+__device__ __forceinline__ void nl_extract_rest(uint32_t m, uint32_t end, uint32_t pos0) {
+  while (m) {
+    const uint32_t k = bfind(m);
+    end -= 2u;
+    sts16(end, pos0 + k);
+    m ^= 1u << k;
+  }
 }
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 #pragma unroll
@@ -352,15 +388,43 @@ __device__ __forceinline__ uint32_t part_entry(int g, int lo, int hi, uint32_t q
 }
 
 // One aligned 16-byte group of a quality / sequence line through the tables.
-__device__ __forceinline__ void group_full(Smem& sm, const Sel& k, uint32_t ga, bool ql, uint32_t hb_seq, uint32_t ptab_s,
-                                           uint32_t q, u64& over) {
+template <bool QL>
+__device__ __forceinline__ void group_full(Smem& sm, const Sel& k, uint32_t ga, uint32_t hb, uint32_t ptab_s, uint32_t q, u64& over) {
   const uint4 v = lds128(ga);
-  if (ql) {
-    hist16(k, v, hb_seq + HB * 32 * 4);
-    pos16(sm, k, v, ga, ptab_s, q < 1023u ? q : 1023u, 0u, 16u, over);
-  } else {
-    hist16(k, v, hb_seq);
+  hist16(k, v, hb);
+  if (QL) pos16(sm, k, v, ga, ptab_s, q, 0u, 16u, over);
+}
+// Full groups of the lines of one class: slot x = K * line + group (x16 = 16 x), 32 slots per warp step.
+template <bool QL>
+__device__ __forceinline__ void full_slots(Smem& sm, const Sel& k, uint32_t x, uint32_t nslots, uint32_t inv, uint32_t negK16,
+                                           uint32_t rec_s, uint32_t buf_s, uint32_t hb, uint32_t ptab_s, u64& over) {
+  for (; x < nslots; x += WORK_WARPS * 32) {
+    const uint32_t line = __umulhi(x, inv);
+    const uint32_t k16 = line * negK16 + (x << 4);
+    const uint32_t r = lds32(rec_s + 4u * line);
+    if (k16 < ((r >> 10) & 0x3F0u)) group_full<QL>(sm, k, buf_s + (r & 0x3FF0u) + k16, hb, ptab_s, (r >> 20) + k16, over);
   }
+}
+// First / last groups of the lines of one class: bytes [lo, hi) of the group, the others masked to zero
+// (they land in bin 0; the caller keeps the count and subtracts it at the end).
+template <bool QL>
+__device__ __forceinline__ uint32_t part_slots(Smem& sm, const Sel& k, uint32_t x, uint32_t nslots, uint32_t part_s, uint32_t masks_s,
+                                               uint32_t buf_s, uint32_t hb, uint32_t ptab_s, u64& over) {
+  uint32_t junk = 0;
+  for (; x < nslots; x += WORK_WARPS * 32) {
+    const uint32_t ent = lds32(part_s + 4u * x);
+    if (ent) {
+      const uint32_t ga = buf_s + ((ent << 4) & 0x3FF0u);
+      const uint32_t lo = (ent >> 10) & 15u, hi = (ent >> 14) & 31u;
+      uint4 v = lds128(ga);
+      const uint4 ml = lds128(masks_s + ((ent >> 6) & 0xF0u)), mh = lds128(masks_s + ((ent >> 10) & 0x1F0u));
+      v.x &= mh.x & ~ml.x; v.y &= mh.y & ~ml.y; v.z &= mh.z & ~ml.z; v.w &= mh.w & ~ml.w;
+      hist16(k, v, hb);
+      if (QL) pos16(sm, k, v, ga, ptab_s, ent >> 19, lo, hi, over);
+      junk += 16u - (hi - lo);
+    }
+  }
+  return junk;
 }
 
 __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, const int pass) {
@@ -419,6 +483,7 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
     }
   }
   u64 my_min[2] = {~0ull, ~0ull}, my_max[2] = {0, 0};  // line-length extrema seen by this thread
+  uint32_t mns = ~0u, mxs = 0, mnq = ~0u, mxq = 0;       // the same for lines that lie inside one tile
   uint32_t junk_s = 0, junk_q = 0;                      // histogram slots of masked bytes (counted in bin 0)
   u64 over = 0;                                         // quality bytes at positions >= POS_BINS
   const uint32_t hb_seq = sm0 + (uint32_t)offsetof(Smem, hist) + 4u * lane;
@@ -435,41 +500,55 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
   // pipeline: iteration `it` classifies tile B = t0+it (stage it%3, slot it&1) while the workers
   // take tile C = B-1; the TMA of tile A = B+1 is started at the top.
   const int nt = (int)(t1 - t0);
+  const int it_first = t0 == 0 ? 0 : -1;                 // iteration whose tile starts at lo0
+  const int it_last = t1 == a.ntiles ? nt - 1 : -1;      // iteration whose tile ends at a.end
+  const int hi_last = (int)(a.end - (u64)(a.ntiles - 1) * TILE);
+  const uint8_t* next_src = a.base + ((u64)t0 + 1) * TILE;  // tile B+1 (thread 0 only)
   uint32_t par_bits = 0;          // mbarrier parity per stage (bit s)
   int stB = 0, stC = 2, stA = 1;  // stages of tiles B, C, A; rotated at the end of every iteration
+#ifdef FQ_TRACE
+  unsigned long long tr[9] = {0,0,0,0,0,0,0,0,0}; long long tprev = 0;
+#define TRS() tprev = clock64()
+#define TR(i) { long long tnow = clock64(); tr[i] += (unsigned long long)(tnow - tprev); tprev = tnow; }
+#else
+#define TRS()
+#define TR(i)
+#endif
   for (int it = 0; it <= nt; it++) {
+    TRS();
     const int sb = it & 1, sc = sb ^ 1;
     const bool haveB = it < nt, haveC = it > 0;
-    const uint32_t tileB = t0 + (uint32_t)it;
     const uint32_t bufB_s = buf0_s + (uint32_t)stB * STAGE_BYTES;
 
     if (tid == 0 && it + 1 < nt) {  // stage stA held tile B-2, whose K2 finished last iteration
-      const u64 noff = (u64)(tileB + 1) * TILE;
-      const uint32_t bytes = (tileB + 2 < a.ntiles) ? (uint32_t)TILE : (uint32_t)(((a.end - noff) + 15) & ~15ull);
+      const uint32_t bytes = (it + 1 == it_last) ? (uint32_t)((hi_last + 15) & ~15) : (uint32_t)TILE;
       mbar_expect_tx(bar0_s + 8u * stA, bytes);
-      tma_load_1d(buf0_s + (uint32_t)stA * STAGE_BYTES, a.base + noff, bytes, bar0_s + 8u * stA);
+      tma_load_1d(buf0_s + (uint32_t)stA * STAGE_BYTES, next_src, bytes, bar0_s + 8u * stA);
     }
+    next_src += TILE;
 
     // ---- K1a (all warps): newline masks of tile B's 16-byte groups -> bitmap ----
-    int loB = 0, hiB = 0;
-    const u64 toffB = (u64)tileB * TILE;
+    const int loB = it == it_first ? (int)a.lo0 : 0;
+    const int hiB = it == it_last ? hi_last : TILE;
+    const u64 toffB = (u64)(t0 + (uint32_t)it) * TILE;
     if (haveB) {
-      loB = (tileB == 0) ? (int)a.lo0 : 0;
-      hiB = (tileB + 1 < a.ntiles) ? TILE : (int)(a.end - toffB);
+      TR(0);
       mbar_wait(bar0_s + 8u * stB, (par_bits >> stB) & 1u);
+      TR(1);
       par_bits ^= 1u << stB;
-      uint16_t* bm16 = reinterpret_cast<uint16_t*>(sm.bitmap);
+      const uint32_t bm_s = sm0 + (uint32_t)offsetof(Smem, bitmap) + 2u * (uint32_t)tid;
       uint32_t hib = 0;
       if (loB == 0 && hiB == TILE) {  // interior tile: no edge handling
 #pragma unroll
         for (int j = 0; j < GPT; j++) {
-          const int g = tid + j * THREADS;
-          const uint4 v = lds128(bufB_s + 16u * (uint32_t)g);
+          const uint4 v = lds128(bufB_s + 16u * (uint32_t)(tid + j * THREADS));
           const uint32_t o = (v.x | v.y) | (v.z | v.w);
           hib |= o;
-          bm16[g] = (uint16_t)((o & 0x80808080u) ? nl_mask16(v) : nl_mask16_ascii(v));
+          const uint32_t m = (o & 0x80808080u) ? nl_mask16(v) : nl_mask16_ascii(v);
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(bm_s + 2u * (uint32_t)(j * THREADS)), "h"((uint16_t)m) : "memory");
         }
       } else {
+        uint16_t* bm16 = reinterpret_cast<uint16_t*>(sm.bitmap);
 #pragma unroll
         for (int j = 0; j < GPT; j++) {
           const int g = tid + j * THREADS;
@@ -489,6 +568,7 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
         }
       }
       if (hib & 0x80808080u) sm.hiflag = 1;
+    TR(2);
     }
 
     if (liner) {
@@ -497,42 +577,43 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
       // =====================================================================================
       if (scanner) {
         bar_sync(1, THREADS);  // bitmap of tile B complete (the other warps only arrive)
+        TR(3);
         if (haveB) {
           const uint4 bw4 = *reinterpret_cast<const uint4*>(&sm.bitmap[tid * WPS]);
-          const uint32_t bw[WPS] = {bw4.x, bw4.y, bw4.z, bw4.w};
-          const uint32_t c0 = __popc(bw[0]), c1 = __popc(bw[1]), c2 = __popc(bw[2]), c3 = __popc(bw[3]);
+          const uint32_t c0 = __popc(bw4.x), c1 = __popc(bw4.y), c2 = __popc(bw4.z), c3 = __popc(bw4.w);
           const uint32_t c = c0 + c1 + c2 + c3;
           const uint32_t inc = warp_incl_scan(c, lane);
-          int my_last = -1;
-#pragma unroll
-          for (int x = 0; x < WPS; x++) if (bw[x]) my_last = (tid * WPS + x) * 32 + 31 - __clz(bw[x]);
-          my_last = __reduce_max_sync(0xffffffffu, my_last);
-          if (lane == 31) { sm.scan_tot[warp] = inc; sm.scan_last[warp] = my_last; }
+          if (lane == 31) sm.scan_tot[warp] = inc;
           bar_sync(2, SCAN_THREADS);
+          TR(4);
           uint32_t wbase = 0, T = 0;
-          int last_nl = -1;
 #pragma unroll
           for (int w = 0; w < SCAN_WARPS; w++) {
             const uint32_t x = sm.scan_tot[w];
             if (w < warp) wbase += x;
             T += x;
-            last_nl = max(last_nl, sm.scan_last[w]);
           }
-          uint32_t first = wbase + inc - c;  // index of this thread's first newline
+          const uint32_t first = wbase + inc - c;  // index of this thread's first newline
+          if (c && first + c == T) {               // the thread that holds the tile's last newline
+            const uint32_t lw = bw4.w ? bw4.w : (bw4.z ? bw4.z : (bw4.y ? bw4.y : bw4.x));
+            const int lx = bw4.w ? 3 : (bw4.z ? 2 : (bw4.y ? 1 : 0));
+            sm.last_nl = (tid * WPS + lx) * 32 + 31 - __clz(lw);
+          }
           const bool walker = T > (uint32_t)NL_CAP || sm.hiflag != 0 || (a.dbg & 2);
           if (walker) {  // the walker wants the newline count before every bitmap word (scratch: the partial-group slots)
             uint16_t* wb = reinterpret_cast<uint16_t*>(&sm.part[sb][0][0]) + tid * WPS;
             wb[0] = (uint16_t)first; wb[1] = (uint16_t)(first + c0); wb[2] = (uint16_t)(first + c0 + c1); wb[3] = (uint16_t)(first + c0 + c1 + c2);
           } else {
-#pragma unroll
-            for (int x = 0; x < WPS; x++) {
-              uint32_t m = bw[x];
-              while (m) {
-                const int k = __ffs(m) - 1;
-                m &= m - 1;
-                sm.nl[first] = (uint16_t)((tid * WPS + x) * 32 + k);
-                first++;
-              }
+            // newline index: the three highest newlines of every bitmap word without branches (one FLO
+            // each, the four words are independent chains); denser words finish in a loop
+            const uint32_t nl_s = sm0 + (uint32_t)offsetof(Smem, nl);
+            const uint32_t e0 = nl_s + 2u * (first + c0), e1 = e0 + 2u * c1, e2 = e1 + 2u * c2, e3 = e2 + 2u * c3;
+            const uint32_t pb = (uint32_t)tid * (WPS * 32u);
+            const uint32_t r0 = nl_extract3(bw4.x, e0, pb), r1 = nl_extract3(bw4.y, e1, pb + 32u);
+            const uint32_t r2 = nl_extract3(bw4.z, e2, pb + 64u), r3 = nl_extract3(bw4.w, e3, pb + 96u);
+            if (r0 | r1 | r2 | r3) {
+              nl_extract_rest(r0, e0 - 6u, pb); nl_extract_rest(r1, e1 - 6u, pb + 32u);
+              nl_extract_rest(r2, e2 - 6u, pb + 64u); nl_extract_rest(r3, e3 - 6u, pb + 96u);
             }
           }
           if (tid == 0) {
@@ -547,30 +628,38 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
             m.K = 0; m.nlong = 0;
             sm.bytes_since_flush += (uint32_t)(hiB - loB);
             sm.run_L = Lrel + T;
-            sm.run_open = T ? (u64)(hiB - (last_nl + 1)) : open + (u64)(hiB - loB);
-            if (!sm.head_done) {  // bytes of the span before its first newline (the stitch kernel's share)
-              if (T) {
-                int first_nl = 0;  // lowest set bit of the bitmap (the newline index is not built for walker tiles)
-                for (int w = 0; w < BM_WORDS; w++) { const uint32_t x = sm.bitmap[w]; if (x) { first_nl = w * 32 + __ffs(x) - 1; break; } }
-                sm.head_len = open + (u64)(first_nl - loB);
-                sm.head_done = 1;
-              } else {
-                sm.head_len = open + (u64)(hiB - loB);
-              }
-            }
           }
         }
       } else {
         bar_arrive(1, THREADS);
       }
+      TR(5);
       bar_sync(3, LINE_THREADS);  // newline index and meta of tile B are visible to all line warps
-      if (tid == 0) sm.hiflag = 0;
+      TR(6);
+      if (tid == 0) {
+        sm.hiflag = 0;
+        if (haveB) {
+          const TileMeta& m = sm.meta[sb];
+          const int T = m.T;
+          sm.run_open = T ? (u64)(hiB - (sm.last_nl + 1)) : m.open + (u64)(hiB - loB);
+          if (!sm.head_done) {  // bytes of the span before its first newline (the stitch kernel's share)
+            if (T) {
+              int first_nl = 0;  // lowest set bit of the bitmap (the newline index is not built for walker tiles)
+              for (int w = 0; w < BM_WORDS; w++) { const uint32_t x = sm.bitmap[w]; if (x) { first_nl = w * 32 + __ffs(x) - 1; break; } }
+              sm.head_len = m.open + (u64)(first_nl - loB);
+              sm.head_done = 1;
+            } else {
+              sm.head_len = m.open + (u64)(hiB - loB);
+            }
+          }
+        }
+      }
 
       // =====================================================================================
       // LINE tasks of tile B: one thread per sequence / quality line with bytes in the tile
       // =====================================================================================
       TileMeta& m = sm.meta[sb];
-      const int R = haveB ? m.R : 0;
+      const int R = (haveB && !(a.dbg & 8)) ? m.R : 0;
       if (warp * 32 < R) {
         const uint8_t* buf = &sm.buf[stB][PAD];
         const int T = m.T, lo = m.lo, hi = m.hi;
@@ -586,45 +675,48 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
             const bool tail = j == T;  // the line still open at the tile end
             const int e = tail ? hi : (int)sm.nl[j];
             const int s = j ? (int)sm.nl[j - 1] + 1 : lo;
-            const u64 pre = j ? 0ull : open;
-            uint32_t nfull = 0, gf0 = 0, qf0 = 0, pe0 = 0, pe1 = 0;
-            if (j != 0 || Lrel != 0) {  // line 0 of the span is the head fragment (stitch kernel)
-              int xe = e, cr = 0;
-              if (e > s) {
-                if (lds8(bufB_s + (uint32_t)e - 1u) == '\r') {  // dropped when directly before '\n'; at the launch end: decided later
-                  if (!tail) { xe = e - 1; cr = 1; }
-                  else { const int nx = byte_after_tile(a, m); if (nx == '\n' || nx < 0) xe = e - 1; }
-                }
-              } else if (!tail && pre > 0) {
+            const bool carried = j == 0 && open != 0;  // the line began in an earlier tile
+            const bool live = j != 0 || Lrel != 0;      // line 0 of the span is the head fragment (stitch kernel)
+            // a '\r' directly before the line end is dropped (e == 0 reads the pad byte in front of the tile)
+            const bool cr_here = lds8(bufB_s + (uint32_t)max(e, 1) - 1u) == '\r' && e > s;
+            uint32_t cr = cr_here, drop = cr_here;
+            if (tail | carried) {  // at most two lines of a tile
+              if (tail) {           // decided by the next byte; at the launch end: later
+                if (cr_here) { const int nx = byte_after_tile(a, m); drop = (nx == '\n' || nx < 0); }
+              } else if (e == s) {
                 cr = byte_before(a, buf, m, e) == '\r';  // the '\r' ended the previous tile and was dropped there
               }
-              if (!tail) account_line_len(sm, qual ? 3 : 1, pre + (u64)(e - s) - (u64)cr, my_min, my_max);
-              if (xe > s) {
-                const uint32_t poff = pre < 2048ull ? (uint32_t)pre : 2048u;
-                const int g0 = s >> 4, g1 = xe >> 4, a4 = s & 15, b4 = xe & 15;
-                const uint32_t q0 = 16u + poff - (uint32_t)a4;  // q of group g0
-                if (g0 == g1) {
-                  pe0 = part_entry(g0, a4, b4, q0);
-                } else {
-                  int gf = g0;
-                  if (a4) { pe0 = part_entry(g0, a4, 16, q0); gf = g0 + 1; }
-                  nfull = (uint32_t)(g1 - gf); gf0 = (uint32_t)gf; qf0 = q0 + 16u * (uint32_t)(gf - g0);
-                  if (b4) pe1 = part_entry(g1, 0, b4, q0 + 16u * (uint32_t)(g1 - g0));
-                }
-              }
+              if (!tail && live) account_line_len(sm, qual ? 3 : 1, open + (u64)(e - s) - (u64)cr, my_min, my_max);
+            } else if (live) {     // the common case: the whole line lies in this tile
+              const uint32_t len = (uint32_t)(e - s) - cr;
+              const uint32_t bin = len < (uint32_t)POS_BINS ? len : (uint32_t)POS_BINS;
+              atomicAdd(qual ? &sm.qual_len[bin] : &sm.seq_len[bin], 1u);
+              if (qual) { mnq = min(mnq, len); mxq = max(mxq, len); }
+              else { atomicAdd(&sm.seq_log2[32 - __clz(len)], 1u); mns = min(mns, len); mxs = max(mxs, len); }
             }
-            const int cl = qual ? 1 : 0;
+            // the line's bytes [s, xe) as 16-byte groups: head part, full groups, tail part
+            const int xe = e - (int)drop;
+            const bool has = live && xe > s;
+            const uint32_t poff = carried ? (open < 2048ull ? (uint32_t)open : 2048u) : 0u;
+            const int g0 = s >> 4, g1 = xe >> 4, a4 = s & 15, b4 = xe & 15;
+            const bool same = g0 == g1;
+            const uint32_t q0 = 16u + poff - (uint32_t)a4;  // q of group g0
+            const int gf = g0 + (a4 != 0);
+            const uint32_t pe0 = (has && (a4 != 0 || same)) ? part_entry(g0, a4, same ? b4 : 16, q0) : 0u;
+            const uint32_t pe1 = (has && !same && b4 != 0) ? part_entry(g1, 0, b4, q0 + 16u * (uint32_t)(g1 - g0)) : 0u;
+            const uint32_t nfull = (has && !same) ? (uint32_t)(g1 - gf) : 0u;
+            const uint32_t gf0 = nfull ? (uint32_t)gf : 0u;  // (gf may be one past the tile)
+            uint32_t qf0 = q0 + 16u * (uint32_t)(gf - g0);
             qf0 = qf0 < 1023u ? qf0 : 1023u;
-            if (nfull == 0) gf0 = 0;  // (gf0 may be one past the tile)
+            const int cl = qual ? 1 : 0;
+            nd = nfull;
             if (nfull > (uint32_t)KMAX) {
               const uint32_t ix = atomicAdd(&m.nlong, 1u);
               sm.longl[sb][ix] = gf0 | (nfull << 10) | (qf0 << 21) | ((uint32_t)cl << 31);
-            } else {
-              nd = nfull;
+              nd = 0;
             }
-            sm.rec[sb][cl][i >> 1] = gf0 | (nd << 10) | (qf0 << 16);
-            uint32_t* ps = &sm.part[sb][cl][2 * (i >> 1)];
-            ps[0] = pe0; ps[1] = pe1;
+            sm.rec[sb][cl][i >> 1] = (gf0 << 4) | (nd << 14) | (qf0 << 20);
+            *reinterpret_cast<uint2*>(&sm.part[sb][cl][2 * (i >> 1)]) = make_uint2(pe0, pe1);
           }
           const uint32_t kmax = __reduce_max_sync(0xffffffffu, nd);
           if (lane == 0 && kmax) atomicMax(&m.K, kmax);
@@ -636,61 +728,44 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
       // =====================================================================================
       bar_arrive(1, THREADS);
       const TileMeta& m = sm.meta[sc];
-      if (haveC && m.R > 0) {
+      if (haveC && m.R > 0 && !(a.dbg & 4)) {
         const uint32_t buf_s = buf0_s + (uint32_t)stC * STAGE_BYTES;
-        const int ww = warp - LINE_WARPS;
         const int R = m.R, n_a = (R + 1) >> 1, n_b = R >> 1;  // lines of the class of task 0 / of the other class
-        const int nlq = m.first_q ? n_a : n_b, nls = m.first_q ? n_b : n_a;
+        const uint32_t nlq = (uint32_t)(m.first_q ? n_a : n_b), nls = (uint32_t)(m.first_q ? n_b : n_a);
         uint32_t K = m.K;
         K = K == 1u ? 2u : K;
-        const uint32_t inv = sm.inv[K];
-        const int sq = nlq * (int)K, ss = nls * (int)K;
-        const int cA = (sq + 31) >> 5, cB = cA + ((ss + 31) >> 5), cC = cB + ((2 * nlq + 31) >> 5), cD = cC + ((2 * nls + 31) >> 5);
-        int c = ww - (it % WORK_WARPS);  // rotate the chunk -> warp map from tile to tile
-        if (c < 0) c += WORK_WARPS;
-        for (; c < cD; c += WORK_WARPS) {
-          if (c < cB) {            // full groups: slot x = K * line + group
-            const bool ql = c < cA;
-            const int x = (c - (ql ? 0 : cA)) * 32 + lane;
-            if (x < (ql ? sq : ss)) {
-              const uint32_t line = __umulhi((uint32_t)x, inv), k = (uint32_t)x - line * K;
-              const uint32_t r = sm.rec[sc][ql ? 1 : 0][line];
-              if (k < ((r >> 10) & 63u))
-                group_full(sm, ksel, buf_s + 16u * ((r & 1023u) + k), ql, hb_seq, ptab_s, (r >> 16) + 16u * k, over);
-            }
-          } else {                 // partial groups: bytes [lo, hi) of the group, the others masked to zero (bin 0 = junk)
-            const bool ql = c < cC;
-            const int x = (c - (ql ? cB : cC)) * 32 + lane;
-            const uint32_t ent = x < 2 * (ql ? nlq : nls) ? sm.part[sc][ql ? 1 : 0][x] : 0u;
-            if (ent) {
-              const uint32_t ga = buf_s + 16u * (ent & 1023u);
-              const uint32_t lo = (ent >> 10) & 15u, hi = (ent >> 14) & 31u;
-              uint4 v = lds128(ga);
-              const uint4 ml = lds128(masks_s + 16u * lo), mh = lds128(masks_s + 16u * hi);
-              v.x &= mh.x & ~ml.x; v.y &= mh.y & ~ml.y; v.z &= mh.z & ~ml.z; v.w &= mh.w & ~ml.w;
-              if (ql) {
-                hist16(ksel, v, hb_seq + HB * 32 * 4);
-                pos16(sm, ksel, v, ga, ptab_s, ent >> 19, lo, hi, over);
-                junk_q += 16u - (hi - lo);
-              } else {
-                hist16(ksel, v, hb_seq);
-                junk_s += 16u - (hi - lo);
-              }
-            }
-          }
-        }
+        const uint32_t inv = sm.inv[K], negK16 = 0u - 16u * K;
+        const uint32_t rec_s = sm0 + (uint32_t)offsetof(Smem, rec) + (uint32_t)sc * (2u * REC_CAP * 4u);
+        const uint32_t part_s = sm0 + (uint32_t)offsetof(Smem, part) + (uint32_t)sc * (2u * PART_CAP * 4u);
+        // the four phases start at different warps (rotating from tile to tile) so that the ragged last rounds
+        // of their 32-slot steps fall on different warps
+        const int ww = warp - LINE_WARPS;
+        int w0 = ww - (it % WORK_WARPS); w0 = w0 < 0 ? w0 + WORK_WARPS : w0;
+        int w1 = w0 - WORK_WARPS / 4;     w1 = w1 < 0 ? w1 + WORK_WARPS : w1;
+        int w2 = w0 - WORK_WARPS / 2;     w2 = w2 < 0 ? w2 + WORK_WARPS : w2;
+        int w3 = w0 - 3 * WORK_WARPS / 4; w3 = w3 < 0 ? w3 + WORK_WARPS : w3;
+        full_slots<true>(sm, ksel, (uint32_t)(w0 * 32 + lane), nlq * K, inv, negK16, rec_s + REC_CAP * 4u, buf_s, hb_seq + HB * 32 * 4, ptab_s, over);
+        full_slots<false>(sm, ksel, (uint32_t)(w1 * 32 + lane), nls * K, inv, negK16, rec_s, buf_s, hb_seq, ptab_s, over);
+        junk_q += part_slots<true>(sm, ksel, (uint32_t)(w2 * 32 + lane), 2u * nlq, part_s + PART_CAP * 4u, masks_s, buf_s, hb_seq + HB * 32 * 4, ptab_s, over);
+        junk_s += part_slots<false>(sm, ksel, (uint32_t)(w3 * 32 + lane), 2u * nls, part_s, masks_s, buf_s, hb_seq, ptab_s, over);
         const uint32_t nlong = m.nlong;  // long lines: every worker warp takes every WORK_WARPS-th run of 32 groups
         for (uint32_t l = 0; l < nlong; l++) {
           const uint32_t r = sm.longl[sc][l];
           const uint32_t n = (r >> 10) & 2047u, g0 = r & 1023u, q0 = (r >> 21) & 1023u;
-          const bool ql = (r >> 31) != 0;
-          for (uint32_t t = (uint32_t)(ww * 32 + lane); t < n; t += WORK_WARPS * 32)
-            group_full(sm, ksel, buf_s + 16u * (g0 + t), ql, hb_seq, ptab_s, q0 + 16u * t, over);
+          if (r >> 31) {
+            for (uint32_t t = (uint32_t)(ww * 32 + lane); t < n; t += WORK_WARPS * 32)
+              group_full<true>(sm, ksel, buf_s + 16u * (g0 + t), hb_seq + HB * 32 * 4, ptab_s, q0 + 16u * t, over);
+          } else {
+            for (uint32_t t = (uint32_t)(ww * 32 + lane); t < n; t += WORK_WARPS * 32)
+              group_full<false>(sm, ksel, buf_s + 16u * (g0 + t), hb_seq, ptab_s, 0u, over);
+          }
         }
       }
     }
 
+    TR(7);
     __syncthreads();
+    TR(8);
     // ---- dense or high-byte tile B: the whole CTA walks it now (its bitmap is still in place) ----
     if (haveB && sm.meta[sb].walker) {
       tile_walker(sm, a, &sm.buf[stB][PAD], sm.meta[sb], phase, sm.bitmap, reinterpret_cast<const uint16_t*>(&sm.part[sb][0][0]),
@@ -706,7 +781,12 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
     }
   }
 
+#ifdef FQ_TRACE
+  if (blockIdx.x == 7 && (tid == 0 || tid == 33 || tid == 127 || tid == 200) && pass == 0) printf("tid %d nt %d: top->mbar %llu mbar %llu k1a %llu bar1 %llu scanA %llu nlx %llu bar3 %llu lines/work %llu sync %llu\n", tid, nt, tr[0]/nt, tr[1]/nt, tr[2]/nt, tr[3]/nt, tr[4]/nt, tr[5]/nt, tr[6]/nt, tr[7]/nt, tr[8]/nt);
+#endif
   // ---- flush this span's counters into its block; pass 0 also records the span descriptor ----
+  if (mns != ~0u) { my_min[0] = min(my_min[0], (u64)mns); my_max[0] = max(my_max[0], (u64)mxs); }
+  if (mnq != ~0u) { my_min[1] = min(my_min[1], (u64)mnq); my_max[1] = max(my_max[1], (u64)mxq); }
   for (int q = 0; q < 2; q++) {
     if (my_min[q] != ~0ull) atomicMin(&sm.len_min[q], my_min[q]);
     if (my_max[q] != 0) atomicMax(&sm.len_max[q], my_max[q]);
