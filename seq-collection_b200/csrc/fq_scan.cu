@@ -53,7 +53,7 @@ constexpr int SCAN_THREADS = SCAN_WARPS * 32;
 constexpr int LINE_WARPS = 4;                 // warps 0..LINE_WARPS-1 run the line tasks (the scanner warps first)
 constexpr int LINE_THREADS = LINE_WARPS * 32;
 constexpr int WORK_WARPS = NWARPS - LINE_WARPS;
-constexpr int GPT = TILE / 16 / THREADS;      // 16-byte groups per thread in K1a (2)
+constexpr int WORK_THREADS = WORK_WARPS * 32;
 constexpr int BM_WORDS = TILE / 32;           // bitmap words per tile
 constexpr int WPS = BM_WORDS / SCAN_THREADS;  // bitmap words per scanner thread (4)
 constexpr int NL_CAP = 1024;                  // newline index capacity; denser tiles take the walker path
@@ -114,7 +114,7 @@ struct __align__(128) Smem {
   uint8_t buf[NSTAGE][STAGE_BYTES];  // tile stages; data at buf[s] + PAD
   uint32_t hist[2][HB * 32];         // [0] sequence, [1] quality; word index = byte*32 + lane
   uint32_t ghist[2][256];            // un-striped tables of the generic paths
-  uint32_t bitmap[BM_WORDS];         // bit b of word w: byte 32*w+b is '\n'
+  uint32_t bitmap[2][BM_WORDS];      // bit b of word w: byte 32*w+b is '\n'
   uint16_t nl[NL_CAP];
   uint32_t rec[2][2][REC_CAP];       // [slot][class]
   uint32_t part[2][2][PART_CAP];     // [slot][class]; walker tiles: scratch for the per-word newline counts
@@ -132,7 +132,7 @@ struct __align__(128) Smem {
   u64 len_min[2], len_max[2];        // [0] seq, [1] qual
   u64 run_L, run_open;               // span-running newline count / open-line bytes
   u64 head_len, junk[2], pos_over;
-  uint32_t bytes_since_flush, hiflag, head_done;
+  uint32_t bytes_since_flush, hiflag[2], head_done;
   uint32_t ksel[8];
 };
 
@@ -387,6 +387,37 @@ __device__ __forceinline__ uint32_t part_entry(int g, int lo, int hi, uint32_t q
   return (uint32_t)g | ((uint32_t)lo << 10) | ((uint32_t)hi << 14) | ((q < 1023u ? q : 1023u) << 19);
 }
 
+// K1a: newline masks of a tile's 16-byte groups -> bitmap slot (threads r of nthr; bytes [lo, hi) are valid).
+// Returns the OR of the valid bytes (bit 7 of any byte set: the tile takes the generic walker path).
+__device__ __forceinline__ uint32_t k1a_tile(Smem& sm, uint32_t buf_s, uint32_t bm_s, int lo, int hi, int r, int nthr) {
+  uint32_t hib = 0;
+  if (lo == 0 && hi == TILE) {  // interior tile: no edge handling
+    for (int g = r; g < TILE / 16; g += nthr) {
+      const uint4 v = lds128(buf_s + 16u * (uint32_t)g);
+      const uint32_t o = (v.x | v.y) | (v.z | v.w);
+      hib |= o;
+      sts16(bm_s + 2u * (uint32_t)g, (o & 0x80808080u) ? nl_mask16(v) : nl_mask16_ascii(v));
+    }
+  } else {
+    for (int g = r; g < TILE / 16; g += nthr) {
+      const int off = g * 16;
+      uint32_t m = 0;
+      if (off < hi && off + 16 > lo) {
+        const uint4 v = lds128(buf_s + 16u * (uint32_t)g);
+        m = nl_mask16(v);
+        int lo_k = lo - off; lo_k = lo_k < 0 ? 0 : lo_k;
+        int hi_k = hi - off; hi_k = hi_k > 16 ? 16 : hi_k;
+        m &= ((1u << hi_k) - 1u) & ~((1u << lo_k) - 1u);
+        // high bytes only matter inside the valid range (stale shared memory beyond it)
+        const uint4 ml = sm.masks[lo_k], mh = sm.masks[hi_k];
+        hib |= ((v.x & mh.x & ~ml.x) | (v.y & mh.y & ~ml.y)) | ((v.z & mh.z & ~ml.z) | (v.w & mh.w & ~ml.w));
+      }
+      sts16(bm_s + 2u * (uint32_t)g, m);
+    }
+  }
+  return hib;
+}
+
 // One aligned 16-byte group of a quality / sequence line through the tables.
 template <bool QL>
 __device__ __forceinline__ void group_full(Smem& sm, const Sel& k, uint32_t ga, uint32_t hb, uint32_t ptab_s, uint32_t q, u64& over) {
@@ -467,7 +498,7 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
     sm.len_min[0] = sm.len_min[1] = ~0ull;
     sm.len_max[0] = sm.len_max[1] = 0;
     sm.bytes_since_flush = 0;
-    sm.hiflag = 0;
+    sm.hiflag[0] = sm.hiflag[1] = 0;
     sm.run_L = 0; sm.run_open = 0; sm.head_len = 0; sm.head_done = 0;
     sm.junk[0] = sm.junk[1] = 0; sm.pos_over = 0;
     sm.meta[0].walker = sm.meta[1].walker = 0;
@@ -514,6 +545,14 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
 #define TRS()
 #define TR(i)
 #endif
+  {  // prologue: all warps classify the span's first tile
+    mbar_wait(bar0_s, 0u);
+    par_bits = 1u;
+    const uint32_t hib = k1a_tile(sm, buf0_s, sm0 + (uint32_t)offsetof(Smem, bitmap), 0 == it_first ? (int)a.lo0 : 0,
+                                  0 == it_last ? hi_last : TILE, tid, THREADS);
+    if (hib & 0x80808080u) sm.hiflag[0] = 1;
+    __syncthreads();
+  }
   for (int it = 0; it <= nt; it++) {
     TRS();
     const int sb = it & 1, sc = sb ^ 1;
@@ -527,59 +566,19 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
     }
     next_src += TILE;
 
-    // ---- K1a (all warps): newline masks of tile B's 16-byte groups -> bitmap ----
     const int loB = it == it_first ? (int)a.lo0 : 0;
     const int hiB = it == it_last ? hi_last : TILE;
     const u64 toffB = (u64)(t0 + (uint32_t)it) * TILE;
-    if (haveB) {
-      TR(0);
-      mbar_wait(bar0_s + 8u * stB, (par_bits >> stB) & 1u);
-      TR(1);
-      par_bits ^= 1u << stB;
-      const uint32_t bm_s = sm0 + (uint32_t)offsetof(Smem, bitmap) + 2u * (uint32_t)tid;
-      uint32_t hib = 0;
-      if (loB == 0 && hiB == TILE) {  // interior tile: no edge handling
-#pragma unroll
-        for (int j = 0; j < GPT; j++) {
-          const uint4 v = lds128(bufB_s + 16u * (uint32_t)(tid + j * THREADS));
-          const uint32_t o = (v.x | v.y) | (v.z | v.w);
-          hib |= o;
-          const uint32_t m = (o & 0x80808080u) ? nl_mask16(v) : nl_mask16_ascii(v);
-          asm volatile("st.shared.u16 [%0], %1;" ::"r"(bm_s + 2u * (uint32_t)(j * THREADS)), "h"((uint16_t)m) : "memory");
-        }
-      } else {
-        uint16_t* bm16 = reinterpret_cast<uint16_t*>(sm.bitmap);
-#pragma unroll
-        for (int j = 0; j < GPT; j++) {
-          const int g = tid + j * THREADS;
-          const int off = g * 16;
-          uint32_t m = 0;
-          if (off < hiB && off + 16 > loB) {
-            const uint4 v = lds128(bufB_s + 16u * (uint32_t)g);
-            m = nl_mask16(v);
-            int lo_k = loB - off; lo_k = lo_k < 0 ? 0 : lo_k;
-            int hi_k = hiB - off; hi_k = hi_k > 16 ? 16 : hi_k;
-            m &= ((1u << hi_k) - 1u) & ~((1u << lo_k) - 1u);
-            // high bytes only matter inside the valid range (stale shared memory beyond it)
-            const uint4 ml = sm.masks[lo_k], mh = sm.masks[hi_k];
-            hib |= ((v.x & mh.x & ~ml.x) | (v.y & mh.y & ~ml.y)) | ((v.z & mh.z & ~ml.z) | (v.w & mh.w & ~ml.w));
-          }
-          bm16[g] = (uint16_t)m;
-        }
-      }
-      if (hib & 0x80808080u) sm.hiflag = 1;
-    TR(2);
-    }
+    TR(0); TR(1); TR(2);
 
     if (liner) {
       // =====================================================================================
       // SCANNER warps: newline index of tile B and the span-running carry
       // =====================================================================================
       if (scanner) {
-        bar_sync(1, THREADS);  // bitmap of tile B complete (the other warps only arrive)
         TR(3);
         if (haveB) {
-          const uint4 bw4 = *reinterpret_cast<const uint4*>(&sm.bitmap[tid * WPS]);
+          const uint4 bw4 = *reinterpret_cast<const uint4*>(&sm.bitmap[sb][tid * WPS]);
           const uint32_t c0 = __popc(bw4.x), c1 = __popc(bw4.y), c2 = __popc(bw4.z), c3 = __popc(bw4.w);
           const uint32_t c = c0 + c1 + c2 + c3;
           const uint32_t inc = warp_incl_scan(c, lane);
@@ -599,7 +598,7 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
             const int lx = bw4.w ? 3 : (bw4.z ? 2 : (bw4.y ? 1 : 0));
             sm.last_nl = (tid * WPS + lx) * 32 + 31 - __clz(lw);
           }
-          const bool walker = T > (uint32_t)NL_CAP || sm.hiflag != 0 || (a.dbg & 2);
+          const bool walker = T > (uint32_t)NL_CAP || sm.hiflag[sb] != 0 || (a.dbg & 2);
           if (walker) {  // the walker wants the newline count before every bitmap word (scratch: the partial-group slots)
             uint16_t* wb = reinterpret_cast<uint16_t*>(&sm.part[sb][0][0]) + tid * WPS;
             wb[0] = (uint16_t)first; wb[1] = (uint16_t)(first + c0); wb[2] = (uint16_t)(first + c0 + c1); wb[3] = (uint16_t)(first + c0 + c1 + c2);
@@ -630,14 +629,12 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
             sm.run_L = Lrel + T;
           }
         }
-      } else {
-        bar_arrive(1, THREADS);
       }
       TR(5);
       bar_sync(3, LINE_THREADS);  // newline index and meta of tile B are visible to all line warps
       TR(6);
       if (tid == 0) {
-        sm.hiflag = 0;
+        sm.hiflag[sb] = 0;
         if (haveB) {
           const TileMeta& m = sm.meta[sb];
           const int T = m.T;
@@ -645,7 +642,7 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
           if (!sm.head_done) {  // bytes of the span before its first newline (the stitch kernel's share)
             if (T) {
               int first_nl = 0;  // lowest set bit of the bitmap (the newline index is not built for walker tiles)
-              for (int w = 0; w < BM_WORDS; w++) { const uint32_t x = sm.bitmap[w]; if (x) { first_nl = w * 32 + __ffs(x) - 1; break; } }
+              for (int w = 0; w < BM_WORDS; w++) { const uint32_t x = sm.bitmap[sb][w]; if (x) { first_nl = w * 32 + __ffs(x) - 1; break; } }
               sm.head_len = m.open + (u64)(first_nl - loB);
               sm.head_done = 1;
             } else {
@@ -680,19 +677,19 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
             // a '\r' directly before the line end is dropped (e == 0 reads the pad byte in front of the tile)
             const bool cr_here = lds8(bufB_s + (uint32_t)max(e, 1) - 1u) == '\r' && e > s;
             uint32_t cr = cr_here, drop = cr_here;
-            if (tail | carried) {  // at most two lines of a tile
-              if (tail) {           // decided by the next byte; at the launch end: later
-                if (cr_here) { const int nx = byte_after_tile(a, m); drop = (nx == '\n' || nx < 0); }
-              } else if (e == s) {
-                cr = byte_before(a, buf, m, e) == '\r';  // the '\r' ended the previous tile and was dropped there
+            if (tail) {  // decided by the next byte; at the launch end: later
+              if (cr_here) { const int nx = byte_after_tile(a, m); drop = (nx == '\n' || nx < 0); }
+            } else if (live) {
+              if (carried && e == s) cr = byte_before(a, buf, m, e) == '\r';  // the '\r' ended the previous tile and was dropped there
+              if (carried && open > 0x7FFF0000ull) {  // (a line of more than 2 GB)
+                account_line_len(sm, qual ? 3 : 1, open + (u64)(e - s) - (u64)cr, my_min, my_max);
+              } else {
+                const uint32_t len = (carried ? (uint32_t)open : 0u) + (uint32_t)(e - s) - cr;
+                const uint32_t bin = len < (uint32_t)POS_BINS ? len : (uint32_t)POS_BINS;
+                atomicAdd(qual ? &sm.qual_len[bin] : &sm.seq_len[bin], 1u);
+                if (qual) { mnq = min(mnq, len); mxq = max(mxq, len); }
+                else { atomicAdd(&sm.seq_log2[32 - __clz(len)], 1u); mns = min(mns, len); mxs = max(mxs, len); }
               }
-              if (!tail && live) account_line_len(sm, qual ? 3 : 1, open + (u64)(e - s) - (u64)cr, my_min, my_max);
-            } else if (live) {     // the common case: the whole line lies in this tile
-              const uint32_t len = (uint32_t)(e - s) - cr;
-              const uint32_t bin = len < (uint32_t)POS_BINS ? len : (uint32_t)POS_BINS;
-              atomicAdd(qual ? &sm.qual_len[bin] : &sm.seq_len[bin], 1u);
-              if (qual) { mnq = min(mnq, len); mxq = max(mxq, len); }
-              else { atomicAdd(&sm.seq_log2[32 - __clz(len)], 1u); mns = min(mns, len); mxs = max(mxs, len); }
             }
             // the line's bytes [s, xe) as 16-byte groups: head part, full groups, tail part
             const int xe = e - (int)drop;
@@ -726,7 +723,6 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
       // =====================================================================================
       // WORKER warps: byte statistics of tile C from its line records
       // =====================================================================================
-      bar_arrive(1, THREADS);
       const TileMeta& m = sm.meta[sc];
       if (haveC && m.R > 0 && !(a.dbg & 4)) {
         const uint32_t buf_s = buf0_s + (uint32_t)stC * STAGE_BYTES;
@@ -761,6 +757,14 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
           }
         }
       }
+      // ---- K1a of tile A = B+1 (its TMA was started at the top of this iteration) -> the other bitmap slot ----
+      if (it + 1 < nt) {
+        mbar_wait(bar0_s + 8u * stA, (par_bits >> stA) & 1u);
+        par_bits ^= 1u << stA;
+        const uint32_t hib = k1a_tile(sm, buf0_s + (uint32_t)stA * STAGE_BYTES, sm0 + (uint32_t)offsetof(Smem, bitmap) + (uint32_t)sc * (BM_WORDS * 4u),
+                                      it + 1 == it_first ? (int)a.lo0 : 0, it + 1 == it_last ? hi_last : TILE, tid - LINE_THREADS, WORK_THREADS);
+        if (hib & 0x80808080u) sm.hiflag[sc] = 1;
+      }
     }
 
     TR(7);
@@ -768,7 +772,7 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
     TR(8);
     // ---- dense or high-byte tile B: the whole CTA walks it now (its bitmap is still in place) ----
     if (haveB && sm.meta[sb].walker) {
-      tile_walker(sm, a, &sm.buf[stB][PAD], sm.meta[sb], phase, sm.bitmap, reinterpret_cast<const uint16_t*>(&sm.part[sb][0][0]),
+      tile_walker(sm, a, &sm.buf[stB][PAD], sm.meta[sb], phase, sm.bitmap[sb], reinterpret_cast<const uint16_t*>(&sm.part[sb][0][0]),
                   tid, THREADS, my_min, my_max, over);
       __syncthreads();
     }
