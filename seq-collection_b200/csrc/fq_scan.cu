@@ -65,8 +65,14 @@ constexpr int PAD = 16;
 constexpr int STAGE_BYTES = PAD + TILE + 16;
 constexpr int NSTAGE = 3;
 constexpr int HB = 128;                       // striped histogram bins (tiles with bytes >= 128 take the walker path)
-constexpr int PT_STRIDE = 33;                 // per-position table: cell (r, c) = position 16*(c-1) + r, r < 31, c < 33
-constexpr int PT_WORDS = 1024;
+// Per-position quality sums: 16-bit pairs.  q = position + 16; pair A = q >> 1 lives in cell (r, c) with
+// 8 c + r = A, r < 16 (rows >= 8 alias (r - 8, c + 1)); a group adds its nine pairs at immediate offsets
+// r0 + PT_STRIDE * i, consecutive groups of a line hit consecutive banks.  Two copies (alternating with the
+// line number, 16 banks apart) keep lines of equal alignment from colliding.
+constexpr int PT_STRIDE = 33;
+constexpr int PT_COPY = 16 * PT_STRIDE;       // 528 words, = 16 (mod 32)
+constexpr int PT_WORDS = 2 * PT_COPY;
+constexpr int PT_MAX_LINES = 516;             // 16-bit halves: flush before more quality lines than this have been added
 static_assert(WPS == 4, "scanner threads read their bitmap words with one LDS.128");
 static_assert(LINE_WARPS >= SCAN_WARPS && WORK_WARPS > 0, "warp roles");
 
@@ -123,7 +129,8 @@ struct __align__(128) Smem {
   uint32_t seq_len[POS_BINS + 2];
   uint32_t qual_len[POS_BINS + 2];
   uint32_t seq_log2[LOG2_BINS];
-  uint32_t ptab[PT_WORDS];           // per-position quality sums, cell (r, c) at r*PT_STRIDE + c
+  uint32_t ptab[PT_WORDS];           // per-position quality sums (16-bit pairs, two copies)
+  uint32_t gpos[POS_BINS + 2];       // the same, linear and 32-bit: generic paths (walker, groups that straddle POS_BINS)
   uint4 masks[17];                   // masks[n]: the first n bytes of a group
   TileMeta meta[2];
   uint32_t scan_tot[SCAN_WARPS];
@@ -256,23 +263,22 @@ __device__ __forceinline__ void account_byte(uint32_t (*ghist)[256], uint32_t* p
     atomicAdd(&pos_sum[p], b);
   }
 }
-// Cell of line position p (< POS_BINS) in the per-position table.
-__device__ __forceinline__ uint32_t pt_cell(uint32_t p) { return (p & 15u) * PT_STRIDE + (p >> 4) + 1u; }
 // The same byte through the scan kernel's tables (generic paths).
 __device__ __forceinline__ void account_byte_tab(Smem& sm, int cls, uint32_t b, u64 pos, u64& over) {
   atomicAdd(&sm.ghist[cls == 3][b], 1u);
   if (cls == 3) {
-    if (pos < (u64)POS_BINS) atomicAdd(&sm.ptab[pt_cell((uint32_t)pos)], b);
+    if (pos < (u64)POS_BINS) atomicAdd(&sm.gpos[(uint32_t)pos], b);
     else over += b;
   }
 }
-__device__ __forceinline__ void account_line_len(Smem& sm, int cls, u64 len, u64* my_min, u64* my_max) {
+// A line length through the shared tables (generic paths; the line tasks keep their extrema in registers).
+__device__ __forceinline__ void account_line_len(Smem& sm, int cls, u64 len) {
   const int q = cls == 3;
   const uint32_t bin = len < (u64)POS_BINS ? (uint32_t)len : (uint32_t)POS_BINS;
   if (q) atomicAdd(&sm.qual_len[bin], 1u);
   else { atomicAdd(&sm.seq_len[bin], 1u); atomicAdd(&sm.seq_log2[log2_bin(len)], 1u); }
-  if (len < my_min[q]) my_min[q] = len;
-  if (len > my_max[q]) my_max[q] = len;
+  atomicMin(&sm.len_min[q], len);
+  atomicMax(&sm.len_max[q], len);
 }
 
 // 16 bytes into the lane-striped histogram at hbase (bytes < 128): one IDP.4A and one shared atomic per byte.
@@ -282,28 +288,28 @@ __device__ __forceinline__ void hist16(const Sel& k, const uint4& v, uint32_t hb
   red_inc(__dp4a(v.z, k.h0, hbase)); red_inc(__dp4a(v.z, k.h1, hbase)); red_inc(__dp4a(v.z, k.h2, hbase)); red_inc(__dp4a(v.z, k.h3, hbase));
   red_inc(__dp4a(v.w, k.h0, hbase)); red_inc(__dp4a(v.w, k.h1, hbase)); red_inc(__dp4a(v.w, k.h2, hbase)); red_inc(__dp4a(v.w, k.h3, hbase));
 }
-// The four bytes of word w (bytes 4W..4W+3 of the group) added to the per-position cells r0 + PT_STRIDE*(4W + k).
-template <int W>
-__device__ __forceinline__ void pos4(const Sel& k, uint32_t w, uint32_t r0) {
-  red_add_at<4 * PT_STRIDE * (4 * W + 0)>(r0, w & 0xFFu);
-  red_add_at<4 * PT_STRIDE * (4 * W + 1)>(r0, __dp4a(w, k.p1, 0u));
-  red_add_at<4 * PT_STRIDE * (4 * W + 2)>(r0, __dp4a(w, k.p2, 0u));
-  red_add_at<4 * PT_STRIDE * (4 * W + 3)>(r0, w >> 24);
-}
 // Per-position sums of the bytes [lo, hi) of a quality group (bytes outside are zero in v): q = 16 + position
-// of the group's byte 0.  Inside the table: 16 atomics with immediate offsets (consecutive groups of a line hit
-// consecutive banks); beyond POS_BINS: the overflow bin; the one group per long line that straddles: byte-wise.
-__device__ __forceinline__ void pos16(Smem& sm, const Sel& k, const uint4& v, uint32_t ga, uint32_t ptab_s,
-                                      uint32_t q, uint32_t lo, uint32_t hi, u64& over) {
+// of the group's byte 0, pt_s = the table copy.  Inside the table: the group, shifted by one byte when q is odd,
+// is nine 16-bit pairs -> nine shared atomics at immediate offsets; beyond POS_BINS: the overflow bin; the one
+// group per long line that straddles POS_BINS: byte-wise into the linear table.
+__device__ __forceinline__ void pos16(Smem& sm, const uint4& v, uint32_t ga, uint32_t pt_s, uint32_t q, uint32_t lo, uint32_t hi, u64& over) {
   if (q + hi <= (uint32_t)POS_BINS + 16u) {
-    const uint32_t r0 = ptab_s + 4u * ((q & 15u) * PT_STRIDE + (q >> 4));
-    pos4<0>(k, v.x, r0); pos4<1>(k, v.y, r0); pos4<2>(k, v.z, r0); pos4<3>(k, v.w, r0);
+    const uint32_t sh = (q & 1u) << 3;
+    const uint32_t w0 = v.x << sh, w1 = __funnelshift_l(v.x, v.y, sh), w2 = __funnelshift_l(v.y, v.z, sh);
+    const uint32_t w3 = __funnelshift_l(v.z, v.w, sh), w4 = __funnelshift_l(v.w, 0u, sh);
+    const uint32_t A = q >> 1;
+    const uint32_t r0 = pt_s + 4u * ((A & 7u) * PT_STRIDE + (A >> 3));
+    red_add_at<4 * PT_STRIDE * 0>(r0, __byte_perm(w0, 0u, 0x4140)); red_add_at<4 * PT_STRIDE * 1>(r0, __byte_perm(w0, 0u, 0x4342));
+    red_add_at<4 * PT_STRIDE * 2>(r0, __byte_perm(w1, 0u, 0x4140)); red_add_at<4 * PT_STRIDE * 3>(r0, __byte_perm(w1, 0u, 0x4342));
+    red_add_at<4 * PT_STRIDE * 4>(r0, __byte_perm(w2, 0u, 0x4140)); red_add_at<4 * PT_STRIDE * 5>(r0, __byte_perm(w2, 0u, 0x4342));
+    red_add_at<4 * PT_STRIDE * 6>(r0, __byte_perm(w3, 0u, 0x4140)); red_add_at<4 * PT_STRIDE * 7>(r0, __byte_perm(w3, 0u, 0x4342));
+    if (sh) red_add_at<4 * PT_STRIDE * 8>(r0, w4);
   } else if (q + lo >= (uint32_t)POS_BINS + 16u) {
     over += __dp4a(v.x, 0x01010101u, __dp4a(v.y, 0x01010101u, __dp4a(v.z, 0x01010101u, __dp4a(v.w, 0x01010101u, 0u))));
   } else {
     for (uint32_t x = lo; x < hi; x++) {
       const uint32_t b = lds8(ga + x), p = q - 16u + x;
-      if (p < (uint32_t)POS_BINS) atomicAdd(&sm.ptab[pt_cell(p)], b);
+      if (p < (uint32_t)POS_BINS) atomicAdd(&sm.gpos[p], b);
       else over += b;
     }
   }
@@ -326,8 +332,8 @@ __device__ __forceinline__ int byte_after_tile(const ScanArgs& a, const TileMeta
 // Generic bitmap walker (dense tiles, tiles with bytes >= 128): one thread per 32-byte bitmap word,
 // bytes taken one at a time.  Exact for any content; also keeps the line-length tables.
 __device__ __noinline__ void tile_walker(Smem& sm, const ScanArgs& a, const uint8_t* buf, const TileMeta& m, uint32_t phase,
-                                         const uint32_t* bitmap, const uint16_t* wordbase, int r, int nthr,
-                                         u64* my_min, u64* my_max, u64& over) {
+                                         const uint32_t* bitmap, const uint16_t* wordbase, int r, int nthr) {
+  u64 over = 0;
   const int nwords = (m.hi + 31) >> 5;
   for (int w = r; w < nwords; w += nthr) {
     const int o0 = w * 32 > m.lo ? w * 32 : m.lo;
@@ -349,7 +355,7 @@ __device__ __noinline__ void tile_walker(Smem& sm, const ScanArgs& a, const uint
       if (b == '\n') {
         if (counted) {
           const int cr = (pos > 0 && byte_before(a, buf, m, o) == '\r') ? 1 : 0;
-          account_line_len(sm, cls, pos - (u64)cr, my_min, my_max);
+          account_line_len(sm, cls, pos - (u64)cr);
         }
         line++;
         pos = 0;
@@ -366,20 +372,31 @@ __device__ __noinline__ void tile_walker(Smem& sm, const ScanArgs& a, const uint
       pos++;
     }
   }
+  if (over) atomicAdd(&sm.pos_over, over);
 }
 
-// Adds the per-position table to the span block and clears it (position p: its cell and the alias cell).
+// Adds the packed per-position table (both copies, cell and alias cell of every pair) to the span block and clears it.
 __device__ __forceinline__ void flush_pos_tab(Smem& sm, u64* block, int tid) {
-  for (int p = tid; p < POS_BINS; p += THREADS) {
-    const uint32_t c0 = pt_cell((uint32_t)p);
-    u64 v = sm.ptab[c0];
-    sm.ptab[c0] = 0;
-    if ((p & 15) != 15) {  // row r+16 of the previous column is the same position
-      const uint32_t c1 = c0 + 16u * PT_STRIDE - 1u;
-      v += sm.ptab[c1];
-      sm.ptab[c1] = 0;
+  for (int t = tid; t < POS_BINS / 2; t += THREADS) {
+    const uint32_t A = (uint32_t)t + 8u;  // pair of q = 2A, 2A+1 -> positions 2t, 2t+1
+    const uint32_t c0 = (A & 7u) * PT_STRIDE + (A >> 3), c1 = c0 + 8u * PT_STRIDE - 1u;
+    u64 lo = 0, hi = 0;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const uint32_t x = sm.ptab[c0 + k * PT_COPY], y = sm.ptab[c1 + k * PT_COPY];
+      sm.ptab[c0 + k * PT_COPY] = 0; sm.ptab[c1 + k * PT_COPY] = 0;
+      lo += (x & 0xFFFFu) + (y & 0xFFFFu);
+      hi += (x >> 16) + (y >> 16);
     }
-    if (v) block[OFF_POS_SUM + p] += v;
+    if (lo) block[OFF_POS_SUM + 2 * t] += lo;
+    if (hi) block[OFF_POS_SUM + 2 * t + 1] += hi;
+  }
+}
+// The linear table of the generic paths.
+__device__ __forceinline__ void flush_gpos(Smem& sm, u64* block, int tid) {
+  for (int p = tid; p < POS_BINS; p += THREADS) {
+    const uint32_t v = sm.gpos[p];
+    if (v) { block[OFF_POS_SUM + p] += v; sm.gpos[p] = 0; }
   }
 }
 
@@ -423,7 +440,7 @@ template <bool QL>
 __device__ __forceinline__ void group_full(Smem& sm, const Sel& k, uint32_t ga, uint32_t hb, uint32_t ptab_s, uint32_t q, u64& over) {
   const uint4 v = lds128(ga);
   hist16(k, v, hb);
-  if (QL) pos16(sm, k, v, ga, ptab_s, q, 0u, 16u, over);
+  if (QL) pos16(sm, v, ga, ptab_s, q, 0u, 16u, over);
 }
 // Full groups of the lines of one class: slot x = K * line + group (x16 = 16 x), 32 slots per warp step.
 template <bool QL>
@@ -433,7 +450,8 @@ __device__ __forceinline__ void full_slots(Smem& sm, const Sel& k, uint32_t x, u
     const uint32_t line = __umulhi(x, inv);
     const uint32_t k16 = line * negK16 + (x << 4);
     const uint32_t r = lds32(rec_s + 4u * line);
-    if (k16 < ((r >> 10) & 0x3F0u)) group_full<QL>(sm, k, buf_s + (r & 0x3FF0u) + k16, hb, ptab_s, (r >> 20) + k16, over);
+    if (k16 < ((r >> 10) & 0x3F0u))
+      group_full<QL>(sm, k, buf_s + (r & 0x3FF0u) + k16, hb, ptab_s + ((line & 2u) ? PT_COPY * 4u : 0u), (r >> 20) + k16, over);
   }
 }
 // First / last groups of the lines of one class: bytes [lo, hi) of the group, the others masked to zero
@@ -451,7 +469,7 @@ __device__ __forceinline__ uint32_t part_slots(Smem& sm, const Sel& k, uint32_t 
       const uint4 ml = lds128(masks_s + ((ent >> 6) & 0xF0u)), mh = lds128(masks_s + ((ent >> 10) & 0x1F0u));
       v.x &= mh.x & ~ml.x; v.y &= mh.y & ~ml.y; v.z &= mh.z & ~ml.z; v.w &= mh.w & ~ml.w;
       hist16(k, v, hb);
-      if (QL) pos16(sm, k, v, ga, ptab_s, ent >> 19, lo, hi, over);
+      if (QL) pos16(sm, v, ga, ptab_s + ((x & 4u) ? PT_COPY * 4u : 0u), ent >> 19, lo, hi, over);
       junk += 16u - (hi - lo);
     }
   }
@@ -480,7 +498,7 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
 
   for (int i = tid; i < 2 * HB * 32; i += THREADS) (&sm.hist[0][0])[i] = 0;
   for (int i = tid; i < 512; i += THREADS) (&sm.ghist[0][0])[i] = 0;
-  for (int i = tid; i < POS_BINS + 2; i += THREADS) { sm.seq_len[i] = 0; sm.qual_len[i] = 0; }
+  for (int i = tid; i < POS_BINS + 2; i += THREADS) { sm.seq_len[i] = 0; sm.qual_len[i] = 0; sm.gpos[i] = 0; }
   for (int i = tid; i < PT_WORDS; i += THREADS) sm.ptab[i] = 0;
   if (tid < LOG2_BINS) sm.seq_log2[tid] = 0;
   if (tid < 17 * 4) {  // masks[n]: 0xFF in the first n bytes
@@ -513,8 +531,8 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
       tma_load_1d(buf0_s, a.base + toff, bytes, bar0_s);
     }
   }
-  u64 my_min[2] = {~0ull, ~0ull}, my_max[2] = {0, 0};  // line-length extrema seen by this thread
-  uint32_t mns = ~0u, mxs = 0, mnq = ~0u, mxq = 0;       // the same for lines that lie inside one tile
+  uint32_t mns = ~0u, mxs = 0, mnq = ~0u, mxq = 0;       // line-length extrema seen by this thread
+  uint32_t q_acc = 0;                                   // quality lines added to the packed per-position table since its last flush
   uint32_t junk_s = 0, junk_q = 0;                      // histogram slots of masked bytes (counted in bin 0)
   u64 over = 0;                                         // quality bytes at positions >= POS_BINS
   const uint32_t hb_seq = sm0 + (uint32_t)offsetof(Smem, hist) + 4u * lane;
@@ -682,7 +700,7 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
             } else if (live) {
               if (carried && e == s) cr = byte_before(a, buf, m, e) == '\r';  // the '\r' ended the previous tile and was dropped there
               if (carried && open > 0x7FFF0000ull) {  // (a line of more than 2 GB)
-                account_line_len(sm, qual ? 3 : 1, open + (u64)(e - s) - (u64)cr, my_min, my_max);
+                account_line_len(sm, qual ? 3 : 1, open + (u64)(e - s) - (u64)cr);
               } else {
                 const uint32_t len = (carried ? (uint32_t)open : 0u) + (uint32_t)(e - s) - cr;
                 const uint32_t bin = len < (uint32_t)POS_BINS ? len : (uint32_t)POS_BINS;
@@ -773,13 +791,25 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
     // ---- dense or high-byte tile B: the whole CTA walks it now (its bitmap is still in place) ----
     if (haveB && sm.meta[sb].walker) {
       tile_walker(sm, a, &sm.buf[stB][PAD], sm.meta[sb], phase, sm.bitmap[sb], reinterpret_cast<const uint16_t*>(&sm.part[sb][0][0]),
-                  tid, THREADS, my_min, my_max, over);
+                  tid, THREADS);
       __syncthreads();
     }
     // ---- end of iteration: tile C is consumed, B becomes C ----
     { const int t = stC; stC = stB; stB = stA; stA = t; }
-    if (sm.bytes_since_flush > (1u << 24)) {  // keep the 32-bit per-position sums from overflowing
-      flush_pos_tab(sm, block, tid);
+    {  // the 16-bit halves of the packed per-position table hold at most PT_MAX_LINES quality lines: tile B's
+       // lines are added in the next iteration
+      const TileMeta& mb = sm.meta[sb];
+      const uint32_t nqB = haveB ? (uint32_t)(mb.first_q ? (mb.R + 1) >> 1 : mb.R >> 1) : 0u;
+      if (q_acc + nqB > (uint32_t)PT_MAX_LINES) {
+        flush_pos_tab(sm, block, tid);
+        q_acc = 0;
+        __syncthreads();
+      }
+      q_acc += nqB;
+    }
+    if (sm.bytes_since_flush > (1u << 24)) {  // keep the 32-bit sums of the generic paths from overflowing
+      flush_gpos(sm, block, tid);
+      __syncthreads();
       if (tid == 0) sm.bytes_since_flush = 0;
       __syncthreads();
     }
@@ -789,12 +819,8 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
   if (blockIdx.x == 7 && (tid == 0 || tid == 33 || tid == 127 || tid == 200) && pass == 0) printf("tid %d nt %d: top->mbar %llu mbar %llu k1a %llu bar1 %llu scanA %llu nlx %llu bar3 %llu lines/work %llu sync %llu\n", tid, nt, tr[0]/nt, tr[1]/nt, tr[2]/nt, tr[3]/nt, tr[4]/nt, tr[5]/nt, tr[6]/nt, tr[7]/nt, tr[8]/nt);
 #endif
   // ---- flush this span's counters into its block; pass 0 also records the span descriptor ----
-  if (mns != ~0u) { my_min[0] = min(my_min[0], (u64)mns); my_max[0] = max(my_max[0], (u64)mxs); }
-  if (mnq != ~0u) { my_min[1] = min(my_min[1], (u64)mnq); my_max[1] = max(my_max[1], (u64)mxq); }
-  for (int q = 0; q < 2; q++) {
-    if (my_min[q] != ~0ull) atomicMin(&sm.len_min[q], my_min[q]);
-    if (my_max[q] != 0) atomicMax(&sm.len_max[q], my_max[q]);
-  }
+  if (mns != ~0u) { atomicMin(&sm.len_min[0], (u64)mns); atomicMax(&sm.len_max[0], (u64)mxs); }
+  if (mnq != ~0u) { atomicMin(&sm.len_min[1], (u64)mnq); atomicMax(&sm.len_max[1], (u64)mxq); }
   if (junk_s) atomicAdd(&sm.junk[0], (u64)junk_s);
   if (junk_q) atomicAdd(&sm.junk[1], (u64)junk_q);
   if (over) atomicAdd(&sm.pos_over, over);
@@ -823,6 +849,8 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
   }
   if (tid < LOG2_BINS && sm.seq_log2[tid]) block[OFF_SEQ_LOG2 + tid] += sm.seq_log2[tid];
   flush_pos_tab(sm, block, tid);
+  __syncthreads();
+  flush_gpos(sm, block, tid);
   if (tid == 0) {
     if (sm.pos_over) block[OFF_POS_SUM + POS_BINS] += sm.pos_over;
     if (sm.len_min[0] < block[OFF_SEQ_LEN_MIN]) block[OFF_SEQ_LEN_MIN] = sm.len_min[0];
