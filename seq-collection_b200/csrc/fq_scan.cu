@@ -139,7 +139,7 @@ struct __align__(128) Smem {
   u64 len_min[2], len_max[2];        // [0] seq, [1] qual
   u64 run_L, run_open;               // span-running newline count / open-line bytes
   u64 head_len, junk[2], pos_over;
-  uint32_t bytes_since_flush, hiflag[2], head_done;
+  uint32_t bytes_since_flush, hiflag[2], head_done, post[2], q_acc;
   uint32_t ksel[8];
 };
 
@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
   if (tid == 0) {
     sm.len_min[0] = sm.len_min[1] = ~0ull;
     sm.len_max[0] = sm.len_max[1] = 0;
-    sm.bytes_since_flush = 0;
+    sm.bytes_since_flush = 0; sm.post[0] = sm.post[1] = 0; sm.q_acc = 0;
     sm.hiflag[0] = sm.hiflag[1] = 0;
     sm.run_L = 0; sm.run_open = 0; sm.head_len = 0; sm.head_done = 0;
     sm.junk[0] = sm.junk[1] = 0; sm.pos_over = 0;
@@ -532,7 +532,6 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
     }
   }
   uint32_t mns = ~0u, mxs = 0, mnq = ~0u, mxq = 0;       // line-length extrema seen by this thread
-  uint32_t q_acc = 0;                                   // quality lines added to the packed per-position table since its last flush
   uint32_t junk_s = 0, junk_q = 0;                      // histogram slots of masked bytes (counted in bin 0)
   u64 over = 0;                                         // quality bytes at positions >= POS_BINS
   const uint32_t hb_seq = sm0 + (uint32_t)offsetof(Smem, hist) + 4u * lane;
@@ -653,9 +652,18 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
       TR(6);
       if (tid == 0) {
         sm.hiflag[sb] = 0;
+        uint32_t post = 0;  // what the whole CTA has to do after this iteration's barrier
         if (haveB) {
           const TileMeta& m = sm.meta[sb];
           const int T = m.T;
+          // the 16-bit halves of the packed per-position table hold at most PT_MAX_LINES quality lines; tile B's
+          // lines are added in the next iteration
+          const uint32_t nqB = (uint32_t)(m.first_q ? (m.R + 1) >> 1 : m.R >> 1);
+          uint32_t qa = sm.q_acc;
+          if (qa + nqB > (uint32_t)PT_MAX_LINES) { post |= 2u; qa = 0; }
+          sm.q_acc = qa + nqB;
+          if (m.walker) post |= 1u;
+          if (sm.bytes_since_flush > (1u << 24)) { post |= 4u; sm.bytes_since_flush = 0; }  // the 32-bit sums of the generic paths
           sm.run_open = T ? (u64)(hiB - (sm.last_nl + 1)) : m.open + (u64)(hiB - loB);
           if (!sm.head_done) {  // bytes of the span before its first newline (the stitch kernel's share)
             if (T) {
@@ -668,6 +676,7 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
             }
           }
         }
+        sm.post[sb] = post;
       }
 
       // =====================================================================================
@@ -788,29 +797,15 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
     TR(7);
     __syncthreads();
     TR(8);
-    // ---- dense or high-byte tile B: the whole CTA walks it now (its bitmap is still in place) ----
-    if (haveB && sm.meta[sb].walker) {
-      tile_walker(sm, a, &sm.buf[stB][PAD], sm.meta[sb], phase, sm.bitmap[sb], reinterpret_cast<const uint16_t*>(&sm.part[sb][0][0]),
-                  tid, THREADS);
-      __syncthreads();
-    }
-    // ---- end of iteration: tile C is consumed, B becomes C ----
-    { const int t = stC; stC = stB; stB = stA; stA = t; }
-    {  // the 16-bit halves of the packed per-position table hold at most PT_MAX_LINES quality lines: tile B's
-       // lines are added in the next iteration
-      const TileMeta& mb = sm.meta[sb];
-      const uint32_t nqB = haveB ? (uint32_t)(mb.first_q ? (mb.R + 1) >> 1 : mb.R >> 1) : 0u;
-      if (q_acc + nqB > (uint32_t)PT_MAX_LINES) {
-        flush_pos_tab(sm, block, tid);
-        q_acc = 0;
-        __syncthreads();
+    { const int t = stC; stC = stB; stB = stA; stA = t; }  // tile C is consumed, B becomes C
+    const uint32_t post = sm.post[sb];  // (slot of this iteration: thread 0 rewrites it two iterations later)
+    if (post) {
+      if (post & 1u) {  // dense or high-byte tile B: the whole CTA walks it now (its bitmap is still in place)
+        tile_walker(sm, a, &sm.buf[stC][PAD], sm.meta[sb], phase, sm.bitmap[sb], reinterpret_cast<const uint16_t*>(&sm.part[sb][0][0]),
+                    tid, THREADS);
       }
-      q_acc += nqB;
-    }
-    if (sm.bytes_since_flush > (1u << 24)) {  // keep the 32-bit sums of the generic paths from overflowing
-      flush_gpos(sm, block, tid);
-      __syncthreads();
-      if (tid == 0) sm.bytes_since_flush = 0;
+      if (post & 2u) flush_pos_tab(sm, block, tid);
+      if (post & 4u) { __syncthreads(); flush_gpos(sm, block, tid); }
       __syncthreads();
     }
   }
