@@ -254,3 +254,68 @@ def test_span_edges_with_crlf(ctx):
         rec = b"@h\r\n" + b"ACGT" * 31 + b"\r\n+\r\n" + b"IIII" * 31 + b"\r\n"  # 260 bytes
         data = b"A" * pad + b"\n" + rec * 3000
         assert_equal_stats(ctx.count_bytes(data).to_dict(), O.count(data, 100), f"pad={pad}")
+
+
+# ---- cases aimed at the mechanisms of the record-driven scan kernel (kernel K2) ----
+
+@pytest.mark.gpu
+def test_packed_position_sums_do_not_overflow(ctx):
+    """Many quality lines of the highest printable byte: the 16-bit halves of the per-position table are
+    flushed before they can carry (126 * 520 lines > 65535)."""
+    rec = b"@q\n" + b"ACGT" * 5 + b"\n+\n" + b"~" * 20 + b"\n"       # 48-byte records, 341 quality lines per tile
+    data = rec * 60000
+    assert_equal_stats(ctx.count_bytes(data).to_dict(), O.count(data, 100), "tilde short")
+    rec = b"@q\n" + b"A" * 3 + b"\n+\n" + b"~" * 3 + b"\n"             # 13-byte records: close to the newline-index cap
+    data = rec * 200000
+    assert_equal_stats(ctx.count_bytes(data).to_dict(), O.count(data, 100), "tilde dense")
+
+
+@pytest.mark.gpu
+def test_lines_around_position_bins_and_long_line_threshold(ctx):
+    """Lengths around POS_BINS (512: table / overflow / straddling group), around the long-line threshold
+    (32 full groups), and every alignment of the line start inside its 16-byte group."""
+    rng = np.random.default_rng(11)
+    recs = []
+    for L in list(range(490, 560)) + list(range(1, 40)) + [1023, 1024, 1025, 2047, 4096]:
+        s = bytes(rng.choice(list(b"ACGTN"), size=L).astype(np.uint8))
+        q = bytes(rng.integers(33, 127, size=L, dtype=np.uint8))
+        recs.append(b"@" + b"h" * int(rng.integers(1, 18)) + b"\n" + s + b"\n+\n" + q + b"\n")
+    data = b"".join(recs) * 7
+    assert_equal_stats(ctx.count_bytes(data).to_dict(), O.count(data, 100), "pos bins")
+
+
+@pytest.mark.gpu
+def test_mixed_long_and_short_lines_in_one_tile(ctx):
+    """A tile with short reads and one long read: the long line goes through the shared long-line list, the
+    short ones through the slot map with a small K."""
+    rng = np.random.default_rng(12)
+    out = []
+    for i in range(400):
+        L = 6000 if i % 37 == 5 else int(rng.integers(20, 200))
+        s = bytes(rng.choice(list(b"ACGT"), size=L).astype(np.uint8))
+        q = bytes(rng.integers(40, 80, size=L, dtype=np.uint8))
+        out.append(b"@m%d\n" % i + s + b"\n+\n" + q + b"\n")
+    data = b"".join(out)
+    assert_equal_stats(ctx.count_bytes(data).to_dict(), O.count(data, 100), "mixed")
+
+
+@pytest.mark.gpu
+def test_line_density_around_the_index_capacity(ctx):
+    """Tiles just below / above 1024 newlines (index capacity) alternate between the record path and the walker."""
+    for width in (13, 14, 15, 16, 17, 18):
+        seq = b"ACGTACGTACGTACGTAC"[:width]
+        rec = b"@\n" + seq + b"\n+\n" + (b"I" * width) + b"\n"
+        data = rec * (3 * 16384 // len(rec) * 8)
+        assert_equal_stats(ctx.count_bytes(data).to_dict(), O.count(data, 100), f"width={width}")
+
+
+@pytest.mark.gpu
+def test_cr_at_every_group_and_tile_offset(ctx):
+    """CRLF lines whose '\\r' falls on every offset of a 16-byte group, including the last byte of a tile."""
+    rec = b"@h\r\n" + b"ACGTN" * 9 + b"\r\n+\r\n" + b"FFFFF" * 9 + b"\r\n"   # 103 bytes: walks through all alignments
+    for pad in (0, 1, 5):
+        data = b"x" * pad + b"\n" + rec * 2000
+        assert_equal_stats(ctx.count_bytes(data).to_dict(), O.count(data, 100), f"pad={pad}")
+    # a lone '\r' inside lines and at line ends without '\n' right after
+    data = (b"@h\n" + b"AC\rGT" * 7 + b"\n+\n" + b"II\rII" * 7 + b"\r\n") * 3000
+    assert_equal_stats(ctx.count_bytes(data).to_dict(), O.count(data, 100), "inner cr")
