@@ -411,9 +411,11 @@ __device__ __forceinline__ uint32_t k1a_tile(Smem& sm, uint32_t buf_s, uint32_t 
   if (lo == 0 && hi == TILE) {  // interior tile: no edge handling
     for (int g = r; g < TILE / 16; g += nthr) {
       const uint4 v = lds128(buf_s + 16u * (uint32_t)g);
-      const uint32_t o = (v.x | v.y) | (v.z | v.w);
-      hib |= o;
-      sts16(bm_s + 2u * (uint32_t)g, (o & 0x80808080u) ? nl_mask16(v) : nl_mask16_ascii(v));
+      hib |= (v.x | v.y) | (v.z | v.w);
+      sts16(bm_s + 2u * (uint32_t)g, nl_mask16_ascii(v));
+    }
+    if (hib & 0x80808080u) {  // the short compare is exact only for bytes < 0x80: redo this thread's groups
+      for (int g = r; g < TILE / 16; g += nthr) sts16(bm_s + 2u * (uint32_t)g, nl_mask16(lds128(buf_s + 16u * (uint32_t)g)));
     }
   } else {
     for (int g = r; g < TILE / 16; g += nthr) {
