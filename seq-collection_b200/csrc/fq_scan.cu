@@ -1232,7 +1232,8 @@ cudaError_t launch_reset(u64* committed, int nblocks, Carry* carry, cudaStream_t
 // resync -> scan (guessed phases) -> stitch (verify, commit, head fragments, carry) -> scan pass 1
 // (only spans whose guess was wrong or unknown; exits immediately otherwise).
 cudaError_t launch_scan(const void* ptr, size_t nbytes, SpanDesc* desc, LaunchHdr* hdr, Carry* carry,
-                        u64* pending, u64* committed, ShardInfo* shard, int max_spans, u64 meta_records, cudaStream_t st) {
+                        u64* pending, u64* committed, ShardInfo* shard, int max_spans, u64 meta_records, cudaStream_t st,
+                        cudaStream_t meta_stream, cudaEvent_t ev_fork, cudaEvent_t ev_join) {
   if (nbytes == 0) return cudaSuccess;
   static const uint32_t dbg = getenv("FQGPU_DEBUG") ? (uint32_t)atoi(getenv("FQGPU_DEBUG")) : 0u;
   const uintptr_t addr = (uintptr_t)ptr;
@@ -1246,11 +1247,19 @@ cudaError_t launch_scan(const void* ptr, size_t nbytes, SpanDesc* desc, LaunchHd
   a.nspans = (a.ntiles + a.tps - 1) / a.tps;
   a.desc = desc; a.hdr = hdr; a.carry = carry; a.pending = pending; a.committed = committed; a.shard = shard; a.dbg = dbg;
 
-  if (meta_records) fq_meta_kernel<<<1, 32, 0, st>>>(a.base, a.lo0, a.end, carry, meta_records);
+  // The fq-meta prefix fold touches only its own fields of the carry: it runs beside the scan on its own stream.
+  cudaError_t e;
+  if (meta_records) {
+    if ((e = cudaEventRecord(ev_fork, st)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(meta_stream, ev_fork, 0)) != cudaSuccess) return e;
+    fq_meta_kernel<<<1, 32, 0, meta_stream>>>(a.base, a.lo0, a.end, carry, meta_records);
+    if ((e = cudaEventRecord(ev_join, meta_stream)) != cudaSuccess) return e;
+  }
   fq_resync_kernel<<<a.nspans, 32, 0, st>>>(a);
   fq_scan_kernel<<<a.nspans, THREADS, sizeof(Smem), st>>>(a, 0);
   fq_stitch_kernel<<<a.nspans, STITCH_THREADS, 0, st>>>(a);
   fq_scan_kernel<<<a.nspans, THREADS, sizeof(Smem), st>>>(a, 1);
+  if (meta_records && (e = cudaStreamWaitEvent(st, ev_join, 0)) != cudaSuccess) return e;
   return cudaGetLastError();
 }
 

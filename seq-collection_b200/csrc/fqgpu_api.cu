@@ -57,6 +57,9 @@ void fqgpu_destroy(fqgpu_ctx* ctx) {
   if (ctx->h_shard) cudaFreeHost(ctx->h_shard);
   cudaFree(ctx->d_out);
   if (ctx->h_out) cudaFreeHost(ctx->h_out);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->mstream) cudaStreamDestroy(ctx->mstream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -88,6 +91,9 @@ int fqgpu_create(fqgpu_ctx** out, const fqgpu_config* cfg) {
   CU_NEW(cudaGetDeviceProperties(&prop, dev));
   if (prop.major < 10) return bail("libfqgpu is built for sm_100a (B200); device is sm_" + std::to_string(prop.major * 10 + prop.minor));
   CU_NEW(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CU_NEW(cudaStreamCreateWithFlags(&ctx->mstream, cudaStreamNonBlocking));
+  CU_NEW(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  CU_NEW(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   CU_NEW(fq::scan_configure());
   ctx->grid = prop.multiProcessorCount * 2;
   if (ctx->grid > fq::MAX_SPANS) ctx->grid = fq::MAX_SPANS;
@@ -144,7 +150,8 @@ int fqgpu_scan_device(fqgpu_ctx* ctx, const void* dptr, size_t nbytes) {
   while (left) {
     size_t n = left < kMaxLaunchBytes ? left : kMaxLaunchBytes;
     CU_TRY(ctx, fq::launch_scan(p, n, ctx->d_desc, ctx->d_hdr, ctx->d_carry, ctx->d_pending, ctx->d_committed,
-                                ctx->d_shard, ctx->grid, ctx->shard_rank > 0 ? 0 : ctx->cfg.meta_records, ctx->stream));
+                                ctx->d_shard, ctx->grid, ctx->shard_rank > 0 ? 0 : ctx->cfg.meta_records, ctx->stream,
+                                ctx->mstream, ctx->ev_fork, ctx->ev_join));
     ctx->launches++;
     p += n;
     left -= n;

@@ -15,7 +15,8 @@ int scan_threads();
 cudaError_t scan_configure();
 cudaError_t launch_reset(u64* committed, int nblocks, Carry* carry, cudaStream_t st);
 cudaError_t launch_scan(const void* ptr, size_t nbytes, SpanDesc* desc, LaunchHdr* hdr, Carry* carry,
-                        u64* pending, u64* committed, ShardInfo* shard, int max_spans, u64 meta_records, cudaStream_t st);
+                        u64* pending, u64* committed, ShardInfo* shard, int max_spans, u64 meta_records, cudaStream_t st,
+                        cudaStream_t meta_stream, cudaEvent_t ev_fork, cudaEvent_t ev_join);
 cudaError_t launch_reduce(const u64* blocks, int nblocks, u64* out, cudaStream_t st);
 cudaError_t launch_synth_illumina(void* dptr, u64 first_byte, u64 nbytes, u64 seed, cudaStream_t st);
 cudaError_t synth_ont(void* dptr, size_t capacity, u64 first_record, u64 n_records, u64 seed, size_t* bytes_written,
@@ -38,6 +39,8 @@ struct fqgpu_ctx {
   int device = 0;
   fqgpu_config cfg{};
   cudaStream_t stream = nullptr;
+  cudaStream_t mstream = nullptr;                  // the fq-meta prefix kernel runs beside the scan
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int grid = 0;
   u64* d_pending = nullptr;    // [MAX_SPANS] blocks of the launch in flight
   u64* d_committed = nullptr;  // [MAX_SPANS] blocks accumulated since the last reset
