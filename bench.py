@@ -397,7 +397,7 @@ def main():
                          "algorithmic_bytes_per_launch": nbytes / max(1.0, scan_launches_per_step),
                          "peak_source": peak_src,
                          "note": "algorithmic bytes = input bytes (1 B read per byte); device time = CUDA events around "
-                                 "memset+meta+scan+reduce on the library stream (scan kernel > 99 %)"},
+                                 "memset+meta+scan+reduce on the library stream (scan kernel ~ 99 %; the fq-meta prefix kernel runs beside it)"},
             "clocks": clocks,
             # per scan call: meta + resync + scan + stitch + scan(pass 1); per step also reset + reduce
             "gpu_launches": int(args.steps * (scan_launches_per_step * (5 if args.meta_records else 4) + 2)),
