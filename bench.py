@@ -299,6 +299,23 @@ def main():
         assert st.reads == args.records and st.bases == 150 * args.records, (st.reads, st.bases)
         assert st.lines == 4 * args.records and sum(st.qual_counts) == 150 * args.records
 
+    # ---- the same bytes in core-only mode (FQGPU_F_CORE_ONLY: exactly what `sc fq-count` prints) ----
+    # An extra figure next to the headline (which stays the full statistics set); N=1 only.
+    core = None
+    if world == 1 and args.workload == "illumina":
+        cctx = fq.FqGpu(device=local_rank, meta_records=0, flags=fq.F_CORE_ONLY)
+        for _ in range(2):
+            cst = cctx.count_device(buf.data_ptr(), nbytes)
+        cms = 0.0
+        ncore = max(3, min(args.steps, 5))
+        for _ in range(ncore):
+            cst = cctx.count_device(buf.data_ptr(), nbytes)
+            cms += cctx.last_timing()[0]
+        assert (cst.reads, cst.bases, cst.gc_bases, cst.n_bases) == (st.reads, st.bases, st.gc_bases, st.n_bases)
+        core = {"value": nbytes / (cms / ncore * 1e6), "unit": "GB/s", "steps": ncore,
+                "stats": "reads, bases, G/C/N and sequence-length tables only (quality lines are not examined)"}
+        cctx.close()
+
     # ---- end-to-end: host (pinned) buffers through the C ABI, H2D inside the timed region ----
     # A bounded sample of the same stream (first e2e_mb MiB, byte-range sharded over the ranks like the
     # resident run) sits in pinned host memory; every step copies it to the device in 64 MiB chunks
@@ -403,6 +420,7 @@ def main():
             "gpu_launches": int(args.steps * (scan_launches_per_step * (5 if args.meta_records else 4) + 2)),
             "e2e": e2e,
             "cpu_baseline": cpu,
+            "core_only": core,
         }
         print(json.dumps(line))
     ctx.close()

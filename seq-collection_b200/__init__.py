@@ -24,6 +24,7 @@ LEN_LOG2_BINS = 64
 
 OK, ECUDA, ENCCL, EIO, EARG, ENOMEM = 0, -1, -2, -3, -4, -5
 ERETRY = 1
+F_CORE_ONLY = 1  # fqgpu_config.flags: only what `sc fq-count` prints; quality-line outputs are zero
 
 
 class FqGpuError(RuntimeError):
@@ -352,7 +353,7 @@ def fq_count(fastq: str, basename: bool = False, absolute: bool = False, ctx: Fq
     """Mirror of fq_count* (src/fq_count.nim:14-53): returns the line the reference echoes.
     Raises FqGpuError(EIO) where the reference does quit_error("Unable to open file", 2)."""
     own = ctx is None
-    ctx = ctx or FqGpu()
+    ctx = ctx or FqGpu(meta_records=0, flags=F_CORE_ONLY)  # fq-count prints reads, GC, N and bases only
     try:
         st = ctx.count_file(fastq)
     finally:

@@ -88,6 +88,7 @@ struct ScanArgs {
   u64* committed;  // [MAX_SPANS][BLOCK_WORDS] accumulated over launches
   ShardInfo* shard;  // detached head of a multi-GPU shard (rank > 0)
   uint32_t dbg;
+  uint32_t core;     // FQGPU_F_CORE_ONLY: sequence lines only (what `sc fq-count` prints)
 };
 
 // IDP.4A byte selectors.  Loaded once from shared memory into registers: as immediates or kernel
@@ -351,7 +352,7 @@ __device__ __noinline__ void tile_walker(Smem& sm, const ScanArgs& a, const uint
     for (int o = o0; o < o1; o++) {
       const uint32_t b = buf[o];
       const int cls = (int)((phase + line) & 3);
-      const bool counted = (cls & 1) && line != 0;  // line 0 of the span is the head fragment (stitch kernel)
+      const bool counted = (cls & 1) && line != 0 && !(a.core && cls == 3);  // line 0 of the span is the head fragment (stitch kernel)
       if (b == '\n') {
         if (counted) {
           const int cr = (pos > 0 && byte_before(a, buf, m, o) == '\r') ? 1 : 0;
@@ -638,10 +639,11 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
             const u64 Lrel = sm.run_L, open = sm.run_open;  // before this tile
             TileMeta& m = sm.meta[sb];
             const uint32_t ph = (uint32_t)((phase + Lrel) & 3);  // class of the tile's line 0
-            const int jr0 = (ph & 1) ? 0 : 1;                    // first line of the tile with an odd class
+            // first line of the tile that gets a task: odd class (core-only: class 1), then every 2nd (4th)
+            const int jr0 = a.core ? (int)((1u - ph) & 3u) : ((ph & 1) ? 0 : 1);
             m.Lrel = Lrel; m.open = open; m.toff = toffB; m.T = (int)T; m.lo = loB; m.hi = hiB;
             m.walker = (walker && !count_only) ? 1 : 0;
-            m.R = (walker || count_only) ? 0 : ((int)T + 2 - jr0) >> 1;
+            m.R = (walker || count_only) ? 0 : (a.core ? ((int)T + 4 - jr0) >> 2 : ((int)T + 2 - jr0) >> 1);
             m.first_q = ((ph + (uint32_t)jr0) & 3) == 3;
             m.K = 0; m.nlong = 0;
             sm.bytes_since_flush += (uint32_t)(hiB - loB);
@@ -660,7 +662,7 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
           const int T = m.T;
           // the 16-bit halves of the packed per-position table hold at most PT_MAX_LINES quality lines; tile B's
           // lines are added in the next iteration
-          const uint32_t nqB = (uint32_t)(m.first_q ? (m.R + 1) >> 1 : m.R >> 1);
+          const uint32_t nqB = a.core ? 0u : (uint32_t)(m.first_q ? (m.R + 1) >> 1 : m.R >> 1);
           uint32_t qa = sm.q_acc;
           if (qa + nqB > (uint32_t)PT_MAX_LINES) { post |= 2u; qa = 0; }
           sm.q_acc = qa + nqB;
@@ -691,12 +693,13 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
         const int T = m.T, lo = m.lo, hi = m.hi;
         const u64 Lrel = m.Lrel, open = m.open;
         const uint32_t ph = (uint32_t)((phase + Lrel) & 3);
-        const int jr0 = (ph & 1) ? 0 : 1;
+        const int jr0 = a.core ? (int)((1u - ph) & 3u) : ((ph & 1) ? 0 : 1);
+        const int jshift = a.core ? 2 : 1, cshift = a.core ? 0 : 1;  // line of task i, its index within its class
         for (int base = warp * 32; base < R; base += LINE_THREADS) {
           const int i = base + lane;
           uint32_t nd = 0;
           if (i < R) {
-            const int j = jr0 + 2 * i;
+            const int j = jr0 + (i << jshift);
             const bool qual = ((ph + (uint32_t)j) & 3) == 3;
             const bool tail = j == T;  // the line still open at the tile end
             const int e = tail ? hi : (int)sm.nl[j];
@@ -741,8 +744,8 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
               sm.longl[sb][ix] = gf0 | (nfull << 10) | (qf0 << 21) | ((uint32_t)cl << 31);
               nd = 0;
             }
-            sm.rec[sb][cl][i >> 1] = (gf0 << 4) | (nd << 14) | (qf0 << 20);
-            *reinterpret_cast<uint2*>(&sm.part[sb][cl][2 * (i >> 1)]) = make_uint2(pe0, pe1);
+            sm.rec[sb][cl][i >> cshift] = (gf0 << 4) | (nd << 14) | (qf0 << 20);
+            *reinterpret_cast<uint2*>(&sm.part[sb][cl][2 * (i >> cshift)]) = make_uint2(pe0, pe1);
           }
           const uint32_t kmax = __reduce_max_sync(0xffffffffu, nd);
           if (lane == 0 && kmax) atomicMax(&m.K, kmax);
@@ -756,7 +759,7 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
       if (haveC && m.R > 0 && !(a.dbg & 4)) {
         const uint32_t buf_s = buf0_s + (uint32_t)stC * STAGE_BYTES;
         const int R = m.R, n_a = (R + 1) >> 1, n_b = R >> 1;  // lines of the class of task 0 / of the other class
-        const uint32_t nlq = (uint32_t)(m.first_q ? n_a : n_b), nls = (uint32_t)(m.first_q ? n_b : n_a);
+        const uint32_t nlq = a.core ? 0u : (uint32_t)(m.first_q ? n_a : n_b), nls = a.core ? (uint32_t)R : (uint32_t)(m.first_q ? n_b : n_a);
         uint32_t K = m.K;
         K = K == 1u ? 2u : K;
         const uint32_t inv = sm.inv[K], negK16 = 0u - 16u * K;
@@ -1035,7 +1038,7 @@ __global__ void __launch_bounds__(STITCH_THREADS) fq_stitch_kernel(const ScanArg
     a.shard->head_len = P0 + hl;
     a.shard->head_cr = (unsigned)cr;
   }
-  if (!(cls & 1)) return;
+  if (!(cls & 1) || (a.core && cls == 3)) return;
   for (u64 o = b0 + tid; o < ve; o += STITCH_THREADS) account_byte(ghist, pos_sum, cls, a.base[o], P0 + (o - b0));
   if (tid == 0) {
     // the '\r' that ended the previous launch is content unless this launch starts with '\n'
@@ -1233,7 +1236,7 @@ cudaError_t launch_reset(u64* committed, int nblocks, Carry* carry, cudaStream_t
 // (only spans whose guess was wrong or unknown; exits immediately otherwise).
 cudaError_t launch_scan(const void* ptr, size_t nbytes, SpanDesc* desc, LaunchHdr* hdr, Carry* carry,
                         u64* pending, u64* committed, ShardInfo* shard, int max_spans, u64 meta_records, cudaStream_t st,
-                        cudaStream_t meta_stream, cudaEvent_t ev_fork, cudaEvent_t ev_join) {
+                        cudaStream_t meta_stream, cudaEvent_t ev_fork, cudaEvent_t ev_join, bool core_only) {
   if (nbytes == 0) return cudaSuccess;
   static const uint32_t dbg = getenv("FQGPU_DEBUG") ? (uint32_t)atoi(getenv("FQGPU_DEBUG")) : 0u;
   const uintptr_t addr = (uintptr_t)ptr;
@@ -1245,7 +1248,7 @@ cudaError_t launch_scan(const void* ptr, size_t nbytes, SpanDesc* desc, LaunchHd
   uint32_t nspans = a.ntiles < (uint32_t)max_spans ? a.ntiles : (uint32_t)max_spans;
   a.tps = (a.ntiles + nspans - 1) / nspans;
   a.nspans = (a.ntiles + a.tps - 1) / a.tps;
-  a.desc = desc; a.hdr = hdr; a.carry = carry; a.pending = pending; a.committed = committed; a.shard = shard; a.dbg = dbg;
+  a.desc = desc; a.hdr = hdr; a.carry = carry; a.pending = pending; a.committed = committed; a.shard = shard; a.dbg = dbg; a.core = core_only ? 1u : 0u;
 
   // The fq-meta prefix fold touches only its own fields of the carry: it runs beside the scan on its own stream.
   cudaError_t e;

@@ -209,7 +209,9 @@ int fqgpu_shard_combine(fqgpu_ctx* ctx, const uint64_t* d_blocks, fqgpu_stats* o
   const size_t bytes = (size_t)ctx->shard_world * kShardWords * sizeof(u64);
   CU_TRY(ctx, cudaMemcpyAsync(ctx->h_shard, d_blocks, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  return fqgpu_shard_combine_host(ctx->shard_world, (const uint64_t*)ctx->h_shard, ctx->cfg.meta_records, out);
+  const int rc = fqgpu_shard_combine_host(ctx->shard_world, (const uint64_t*)ctx->h_shard, ctx->cfg.meta_records, out);
+  if (rc == FQGPU_OK && (ctx->cfg.flags & FQGPU_F_CORE_ONLY)) fqgpu_zero_quality(out);
+  return rc;
 }
 
 // After a combine that returned FQGPU_ERETRY: returns FQGPU_OK when this rank's block stands (it only

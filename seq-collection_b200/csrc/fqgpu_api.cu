@@ -151,7 +151,7 @@ int fqgpu_scan_device(fqgpu_ctx* ctx, const void* dptr, size_t nbytes) {
     size_t n = left < kMaxLaunchBytes ? left : kMaxLaunchBytes;
     CU_TRY(ctx, fq::launch_scan(p, n, ctx->d_desc, ctx->d_hdr, ctx->d_carry, ctx->d_pending, ctx->d_committed,
                                 ctx->d_shard, ctx->grid, ctx->shard_rank > 0 ? 0 : ctx->cfg.meta_records, ctx->stream,
-                                ctx->mstream, ctx->ev_fork, ctx->ev_join));
+                                ctx->mstream, ctx->ev_fork, ctx->ev_join, (ctx->cfg.flags & FQGPU_F_CORE_ONLY) != 0));
     ctx->launches++;
     p += n;
     left -= n;
@@ -185,7 +185,7 @@ int fqgpu_last_timing(fqgpu_ctx* ctx, double* kernel_ms, uint64_t* launches) {
 // ---- stats assembly (host): the reduced block + the stream carry -> fqgpu_stats ----------------
 static inline unsigned log2_bin_host(u64 len) { unsigned b = 0; while (len) { b++; len >>= 1; } return b; }
 
-void fqgpu_assemble_stats(const u64* blk, const fq::Carry& c, u64 meta_records, fqgpu_stats* st) {
+void fqgpu_assemble_stats(const u64* blk, const fq::Carry& c, u64 meta_records, fqgpu_stats* st, bool core_only) {
   memset(st, 0, sizeof(*st));
   for (int i = 0; i < 256; i++) { st->base_counts[i] = blk[fq::OFF_HIST_SEQ + i]; st->qual_counts[i] = blk[fq::OFF_HIST_QUAL + i]; }
   for (int i = 0; i <= fq::POS_BINS; i++) {
@@ -258,6 +258,7 @@ void fqgpu_assemble_stats(const u64* blk, const fq::Carry& c, u64 meta_records, 
   st->meta_qual_max = qmax;
   st->meta_lines = ml;
   st->meta_status = status;
+  if (core_only) fqgpu_zero_quality(st);
 }
 
 extern "C" {
@@ -275,7 +276,7 @@ int fqgpu_finish(fqgpu_ctx* ctx, fqgpu_stats* out) {
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   fq::Carry c;
   memcpy(&c, ctx->h_out + fq::BLOCK_WORDS, sizeof(c));
-  fqgpu_assemble_stats(ctx->h_out, c, ctx->cfg.meta_records, out);
+  fqgpu_assemble_stats(ctx->h_out, c, ctx->cfg.meta_records, out, (ctx->cfg.flags & FQGPU_F_CORE_ONLY) != 0);
   return FQGPU_OK;
 }
 

@@ -1,5 +1,6 @@
 // fqgpu_ctx.h -- internal definition of fqgpu_ctx shared by fqgpu_api.cu and fq_shard.cu.
 #pragma once
+#include <string.h>
 #include <cuda_runtime.h>
 
 #include <string>
@@ -16,7 +17,7 @@ cudaError_t scan_configure();
 cudaError_t launch_reset(u64* committed, int nblocks, Carry* carry, cudaStream_t st);
 cudaError_t launch_scan(const void* ptr, size_t nbytes, SpanDesc* desc, LaunchHdr* hdr, Carry* carry,
                         u64* pending, u64* committed, ShardInfo* shard, int max_spans, u64 meta_records, cudaStream_t st,
-                        cudaStream_t meta_stream, cudaEvent_t ev_fork, cudaEvent_t ev_join);
+                        cudaStream_t meta_stream, cudaEvent_t ev_fork, cudaEvent_t ev_join, bool core_only);
 cudaError_t launch_reduce(const u64* blocks, int nblocks, u64* out, cudaStream_t st);
 cudaError_t launch_synth_illumina(void* dptr, u64 first_byte, u64 nbytes, u64 seed, cudaStream_t st);
 cudaError_t synth_ont(void* dptr, size_t capacity, u64 first_record, u64 n_records, u64 seed, size_t* bytes_written,
@@ -87,5 +88,13 @@ inline int fail(fqgpu_ctx* ctx, int code, const std::string& msg) {
   return code;
 }
 
-void fqgpu_assemble_stats(const fq::u64* blk, const fq::Carry& c, fq::u64 meta_records, fqgpu_stats* st);
+// FQGPU_F_CORE_ONLY: quality lines are not examined; their outputs are defined as zero.
+static inline void fqgpu_zero_quality(fqgpu_stats* st) {
+  memset(st->qual_counts, 0, sizeof(st->qual_counts));
+  memset(st->qual_len_hist, 0, sizeof(st->qual_len_hist));
+  memset(st->qual_pos_sum, 0, sizeof(st->qual_pos_sum));
+  memset(st->qual_pos_cnt, 0, sizeof(st->qual_pos_cnt));
+  st->qual_lines = 0; st->qual_len_min = 0; st->qual_len_max = 0;
+}
+void fqgpu_assemble_stats(const fq::u64* blk, const fq::Carry& c, fq::u64 meta_records, fqgpu_stats* st, bool core_only = false);
 cudaEvent_t fqgpu_get_event(fqgpu_ctx* ctx);

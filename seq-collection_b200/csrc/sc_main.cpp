@@ -98,12 +98,13 @@ static string nim_float(double v) {
 
 static fqgpu_ctx* g_ctx = nullptr;
 
-static fqgpu_ctx* context(uint64_t meta_records) {
+static fqgpu_ctx* context(uint64_t meta_records, uint32_t flags = 0) {
   if (g_ctx) { fqgpu_destroy(g_ctx); g_ctx = nullptr; }
   fqgpu_config cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.device = -1;
   cfg.meta_records = meta_records;
+  cfg.flags = flags;
   if (const char* e = getenv("FQGPU_CHUNK_MB")) cfg.chunk_bytes = (size_t)atol(e) << 20;
   if (fqgpu_create(&g_ctx, &cfg) != FQGPU_OK) quit_error(string("GPU unavailable: ") + fqgpu_last_error(nullptr), 1);
   return g_ctx;
@@ -361,7 +362,7 @@ int main(int argc, char** argv) {
     if (header) puts(output_header(kFqCountHeader, basename, absolute).c_str());  // sc.nim:110-111
     else if (files.empty()) quit_error("No FASTQ specified", 3);                  // :112-113
     if (!files.empty()) {
-      fqgpu_ctx* ctx = context(0);
+      fqgpu_ctx* ctx = context(0, FQGPU_F_CORE_ONLY);  // fq-count prints reads, GC, N and bases only
       for (auto& f : files) fq_count(ctx, f, basename, absolute);                 // :115-116
     }
   } else if (cmd == "fq-meta") {

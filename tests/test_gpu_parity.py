@@ -319,3 +319,27 @@ def test_cr_at_every_group_and_tile_offset(ctx):
     # a lone '\r' inside lines and at line ends without '\n' right after
     data = (b"@h\n" + b"AC\rGT" * 7 + b"\n+\n" + b"II\rII" * 7 + b"\r\n") * 3000
     assert_equal_stats(ctx.count_bytes(data).to_dict(), O.count(data, 100), "inner cr")
+
+
+QUAL_FIELDS = ("qual_counts", "qual_len_hist", "qual_pos_sum", "qual_pos_cnt", "qual_lines", "qual_len_min", "qual_len_max")
+
+
+@pytest.mark.gpu
+def test_core_only_mode():
+    """FQGPU_F_CORE_ONLY (what `sc fq-count` needs): every sequence-line output equals the oracle's, every
+    quality-line output is zero, on the same inputs as the full mode (edge corpus, CRLF, long lines, streaming)."""
+    rng = np.random.default_rng(21)
+    cases = dict(corpus.edge_cases())
+    cases["random"] = corpus.random_fastq(rng, 4000, min_len=1, max_len=400)
+    cases["crlf"] = corpus.random_fastq(rng, 3000, min_len=20, max_len=260, crlf=True, final_newline=False)
+    cases["long"] = b"".join(b"@r\n" + b"ACGTN" * n + b"\n+\n" + b"I" * (5 * n) + b"\n" for n in (1, 300, 7000, 40, 3300))
+    cases["dense"] = (b"@\nAC\n+\nII\n") * 30000
+    with fq.FqGpu(meta_records=100, flags=fq.F_CORE_ONLY) as c, fq.FqGpu(meta_records=100, flags=fq.F_CORE_ONLY, chunk_bytes=4096, n_buffers=2) as cs:
+        for name, data in cases.items():
+            want = O.count(data, 100)
+            for k in QUAL_FIELDS:
+                want[k] = [0] * len(want[k]) if isinstance(want[k], list) else 0
+            assert_equal_stats(c.count_bytes(data).to_dict(), want, f"core {name}")
+            cs.reset()
+            cs.submit_bytes(data)
+            assert_equal_stats(cs.finish().to_dict(), want, f"core streamed {name}")

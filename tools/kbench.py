@@ -16,10 +16,11 @@ ap.add_argument("--mb", type=int, default=4096)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--workload", default="illumina")
 ap.add_argument("--meta", type=int, default=100)
+ap.add_argument("--core", action="store_true", help="FQGPU_F_CORE_ONLY")
 a = ap.parse_args()
 n = (a.mb << 20)
 buf = torch.empty(n + 4096, dtype=torch.uint8, device="cuda")
-ctx = fq.FqGpu(meta_records=a.meta)
+ctx = fq.FqGpu(meta_records=a.meta, flags=fq.F_CORE_ONLY if a.core else 0)
 if a.workload == "illumina":
     n -= n % 360
     ctx.synth_illumina(buf.data_ptr(), n, 0, n // 360, 20240229)
