@@ -13,6 +13,8 @@ const
   FQGPU_OK* = 0
   FQGPU_EIO* = -3
 
+const FQGPU_F_CORE_ONLY* = 1'u32   ## fqgpu_config.flags: only what `sc fq-count` prints
+
 type
   FqgpuCtx* = pointer
   FqgpuConfig* {.bycopy.} = object
@@ -57,7 +59,7 @@ import streams
 
 proc fq_count_gpu*(stream: Stream, gc_cnt, n_cnt, total_len: var int64, n_reads: var int) =
   var ctx: FqgpuCtx
-  var cfg = FqgpuConfig(device: -1)
+  var cfg = FqgpuConfig(device: -1, flags: FQGPU_F_CORE_ONLY)   # fq-count prints reads, GC, N, bases: sequence lines only
   if fqgpu_create(addr ctx, addr cfg) != FQGPU_OK:
     raise newException(IOError, $fqgpu_last_error(nil))
   defer: fqgpu_destroy(ctx)

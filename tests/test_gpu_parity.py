@@ -343,3 +343,44 @@ def test_core_only_mode():
             cs.reset()
             cs.submit_bytes(data)
             assert_equal_stats(cs.finish().to_dict(), want, f"core streamed {name}")
+
+
+@pytest.mark.gpu
+def test_lines_longer_than_two_gigabytes():
+    """One record whose sequence and quality lines have 2.2e9 bytes each (closed-form expectations, no oracle):
+    the 64-bit carried-line paths, saturated positions and the overflow bin, in one device scan and streamed
+    in two device calls that cut both lines."""
+    torch = _torch()
+    L = 2_200_000_011
+    head, mid, tail = b"@x\n", b"\n+\n", b"\n"
+    n = len(head) + L + len(mid) + L + len(tail)
+    buf = torch.empty(n, dtype=torch.uint8, device="cuda")
+    o = 0
+    for part in (head, ord("G"), mid, ord("5"), tail):
+        if isinstance(part, int):
+            buf[o:o + L] = part
+            o += L
+        else:
+            buf[o:o + len(part)] = torch.frombuffer(bytearray(part), dtype=torch.uint8).cuda()
+            o += len(part)
+
+    def check(d):
+        assert d["bytes"] == n and d["lines"] == 4 and d["reads"] == 1
+        assert d["bases"] == L and d["gc_bases"] == L and d["n_bases"] == 0
+        assert d["base_counts"][ord("G")] == L and sum(d["base_counts"]) == L
+        assert d["qual_counts"][ord("5")] == L and sum(d["qual_counts"]) == L
+        assert d["seq_len_min"] == d["seq_len_max"] == L and d["qual_len_min"] == d["qual_len_max"] == L
+        assert d["seq_len_hist"][512] == 1 and sum(d["seq_len_hist"]) == 1 and d["qual_len_hist"][512] == 1
+        assert d["seq_len_log2"][32] == 1 and sum(d["seq_len_log2"]) == 1          # 2^31 <= L < 2^32
+        assert d["qual_pos_sum"][:512] == [ord("5")] * 512 and d["qual_pos_sum"][512] == ord("5") * (L - 512)
+        assert d["qual_pos_cnt"][:512] == [1] * 512 and d["qual_pos_cnt"][512] == L - 512
+
+    with fq.FqGpu(meta_records=0) as c:
+        check(c.count_device(buf.data_ptr(), n).to_dict())
+        c.reset()
+        cut = len(head) + L // 3 + 5
+        c.scan_device(buf.data_ptr(), cut)
+        cut2 = len(head) + L + len(mid) + L // 2 + 1
+        c.scan_device(buf.data_ptr() + cut, cut2 - cut)
+        c.scan_device(buf.data_ptr() + cut2, n - cut2)
+        check(c.finish().to_dict())
