@@ -688,14 +688,15 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
       // =====================================================================================
       TileMeta& m = sm.meta[sb];
       const int R = (haveB && !(a.dbg & 8)) ? m.R : 0;
-      if (warp * 32 < R) {
+      // warp 0 issues the TMA and does the serial bookkeeping of thread 0: it takes no line tasks
+      if (warp >= 1 && (warp - 1) * 32 < R) {
         const uint8_t* buf = &sm.buf[stB][PAD];
         const int T = m.T, lo = m.lo, hi = m.hi;
         const u64 Lrel = m.Lrel, open = m.open;
         const uint32_t ph = (uint32_t)((phase + Lrel) & 3);
         const int jr0 = a.core ? (int)((1u - ph) & 3u) : ((ph & 1) ? 0 : 1);
         const int jshift = a.core ? 2 : 1, cshift = a.core ? 0 : 1;  // line of task i, its index within its class
-        for (int base = warp * 32; base < R; base += LINE_THREADS) {
+        for (int base = (warp - 1) * 32; base < R; base += LINE_THREADS - 32) {
           const int i = base + lane;
           uint32_t nd = 0;
           if (i < R) {
