@@ -1216,6 +1216,102 @@ __global__ void fq_meta_kernel(const uint8_t* __restrict__ base, uint32_t lo0, u
   }
 }
 
+// The same fold by one CTA of 1024 threads, 16 KiB per step (long-read prefixes are megabytes): every thread
+// takes 16 bytes, a block-wide prefix sum of the newline counts gives the line index of every byte, the
+// per-line (min, max) are shared-memory atomics on keys (0 = byte outside the table, b - 32 inside, so that
+// key - 1 = qual_to_int), and thread 0 folds the lines in order at the end.  Holds up to META_CAP lines.
+constexpr int META_THREADS = 1024;
+constexpr int META_CAP = 4096;
+constexpr uint32_t META_NONE = 0xFFFFFFFFu;
+
+__global__ void __launch_bounds__(META_THREADS) fq_meta_par_kernel(const uint8_t* __restrict__ base, uint32_t lo0, u64 end,
+                                                                 Carry* __restrict__ carry, u64 meta_records) {
+  __shared__ uint32_t kmin[META_CAP + 1], kmax[META_CAP + 1];
+  __shared__ uint32_t warp_cnt[META_THREADS / 32];
+  __shared__ uint32_t s_pending;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u64 limit = meta_records * 4;
+  const u64 ml0 = carry->meta_lines;
+  if (ml0 >= limit || end <= (u64)lo0) return;
+  for (int i = tid; i <= META_CAP; i += META_THREADS) { kmin[i] = META_NONE; kmax[i] = 0; }
+  if (tid == 0) s_pending = 0;
+  __syncthreads();
+  if (tid == 0) {  // the open line carried in from the previous chunk
+    if (carry->cur_has) { kmin[0] = (uint32_t)(carry->cur_min + 1); kmax[0] = (uint32_t)(carry->cur_max + 1); }
+    if (carry->meta_pending_cr && base[lo0] != '\n') kmin[0] = 0;  // the '\r' that ended the previous chunk was content
+  }
+  __syncthreads();
+  u64 L0 = ml0;  // lines before the current window
+  for (u64 o = 0; o < end && L0 < limit; o += (u64)META_THREADS * 16) {
+    const u64 g = o + (u64)tid * 16;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    int va = 16, vb = 0;  // valid bytes of this thread: [va, vb)
+    if (g < end && g + 16 > (u64)lo0) {
+      v = *reinterpret_cast<const uint4*>(base + g);
+      va = g >= (u64)lo0 ? 0 : (int)((u64)lo0 - g);
+      vb = g + 16 <= end ? 16 : (int)(end - g);
+    }
+    const uint32_t m = va < vb ? (nl_mask16(v) & ((1u << vb) - 1u) & ~((1u << va) - 1u)) : 0u;
+    const uint32_t cnt = __popc(m);
+    const uint32_t inc = warp_incl_scan(cnt, lane);
+    if (lane == 31) warp_cnt[warp] = inc;
+    // the byte after this thread's 16 (the '\r' rule): the next lane's first byte, or memory; 0x100 = end of the chunk
+    uint32_t nxt = __shfl_down_sync(0xffffffffu, v.x & 0xFFu, 1);
+    if (lane == 31) nxt = (g + 16 < end) ? (uint32_t)base[g + 16] : 0x100u;
+    else if (g + 16 >= end) nxt = 0x100u;
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+    for (int w = 0; w < META_THREADS / 32; w++) { const uint32_t x = warp_cnt[w]; if (w < warp) wbase += x; total += x; }
+    u64 L = L0 + wbase + inc - cnt;  // line index of this thread's first byte
+    uint32_t mn = META_NONE, mx = 0;
+    const uint32_t ww[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      if (k >= va && k < vb) {
+        const uint32_t c = (ww[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+        if ((m >> k) & 1u) {
+          if (mn != META_NONE && L < limit) { atomicMin(&kmin[L - ml0], mn); atomicMax(&kmax[L - ml0], mx); }
+          mn = META_NONE; mx = 0;
+          L++;
+        } else if ((L & 3) == 3 && L < limit) {
+          bool content = true;
+          if (c == '\r') {
+            const uint32_t nx = (k + 1 < vb) ? ((ww[(k + 1) >> 2] >> (8 * ((k + 1) & 3))) & 0xFFu) : (k + 1 < 16 ? 0x100u : nxt);
+            if (nx == 0x100u) { s_pending = 1; content = false; }  // last byte of the chunk: decided by the next one
+            else if (nx == '\n') content = false;                   // dropped: directly before the newline
+          }
+          if (content) {
+            const uint32_t key = (c >= 33u && c <= 126u) ? c - 32u : 0u;
+            mn = min(mn, key); mx = max(mx, key);
+          }
+        }
+      }
+    }
+    if (mn != META_NONE && L < limit) { atomicMin(&kmin[L - ml0], mn); atomicMax(&kmax[L - ml0], mx); }
+    L0 += total;
+    __syncthreads();  // warp_cnt is rewritten by the next window
+  }
+  if (tid == 0) {
+    const u64 ml_end = L0 < limit ? L0 : limit;
+    long long qmin = carry->qual_min, qmax = carry->qual_max;
+    unsigned status = carry->meta_status;
+    for (u64 L = ml0; L < ml_end; L++) {
+      if ((L & 3) != 3 || status != FQGPU_META_OK) continue;
+      const uint32_t a = kmin[L - ml0];
+      meta_fold(qmin, qmax, status, a != META_NONE, (int)a - 1, (int)kmax[L - ml0] - 1);
+    }
+    const bool done = ml_end >= limit;
+    carry->meta_lines = ml_end;
+    carry->qual_min = qmin; carry->qual_max = qmax;
+    carry->meta_status = status;
+    carry->meta_pending_cr = done ? 0u : s_pending;
+    const uint32_t a = done ? META_NONE : kmin[ml_end - ml0];
+    carry->cur_has = a != META_NONE;
+    carry->cur_min = a != META_NONE ? (int)a - 1 : 0;
+    carry->cur_max = a != META_NONE ? (int)kmax[ml_end - ml0] - 1 : 0;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // host-callable launchers (used by fqgpu_api.cu)
 // ------------------------------------------------------------------------------------------
@@ -1256,7 +1352,8 @@ cudaError_t launch_scan(const void* ptr, size_t nbytes, SpanDesc* desc, LaunchHd
   if (meta_records) {
     if ((e = cudaEventRecord(ev_fork, st)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(meta_stream, ev_fork, 0)) != cudaSuccess) return e;
-    fq_meta_kernel<<<1, 32, 0, meta_stream>>>(a.base, a.lo0, a.end, carry, meta_records);
+    if (meta_records * 4 <= (u64)META_CAP) fq_meta_par_kernel<<<1, META_THREADS, 0, meta_stream>>>(a.base, a.lo0, a.end, carry, meta_records);
+    else fq_meta_kernel<<<1, 32, 0, meta_stream>>>(a.base, a.lo0, a.end, carry, meta_records);
     if ((e = cudaEventRecord(ev_join, meta_stream)) != cudaSuccess) return e;
   }
   fq_resync_kernel<<<a.nspans, 32, 0, st>>>(a);

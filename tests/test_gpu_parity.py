@@ -384,3 +384,28 @@ def test_lines_longer_than_two_gigabytes():
         c.scan_device(buf.data_ptr() + cut, cut2 - cut)
         c.scan_device(buf.data_ptr() + cut2, n - cut2)
         check(c.finish().to_dict())
+
+
+@pytest.mark.gpu
+def test_meta_fold_parallel_and_serial_kernels():
+    """fq-meta quality range (src/fq_meta.nim:94-102,226-248) through both prefix kernels (the one-CTA kernel up to
+    1024 sampled records, the single-warp kernel beyond), on bytes outside the table, CR / CRLF, empty quality
+    lines and chunk cuts inside the sampled prefix."""
+    rng = np.random.default_rng(33)
+    body = bytearray(corpus.random_fastq(rng, 2600, min_len=0, max_len=90, qual_lo=33, qual_hi=126))
+    for pos in rng.integers(0, len(body), size=400):  # sprinkle bytes outside the table and stray CRs
+        if body[pos] != 0x0A:
+            body[pos] = int(rng.choice([9, 13, 31, 32, 127, 200]))
+    datas = {"weird": bytes(body),
+             "crlf": corpus.random_fastq(rng, 1500, min_len=1, max_len=60, crlf=True, final_newline=False, qual_lo=40, qual_hi=110),
+             "long": b"".join(b"@r\n" + b"A" * L + b"\n+\n" + bytes(rng.integers(35, 100, size=L, dtype=np.uint8)) + b"\n"
+                              for L in (40000, 3, 70001, 1))}
+    for name, data in datas.items():
+        for n in (1, 2, 7, 100, 1024, 1025, 5000):
+            want = O.count(data, n)
+            with fq.FqGpu(meta_records=n) as c:
+                assert_equal_stats(c.count_bytes(data).to_dict(), want, f"{name} n={n}")
+            with fq.FqGpu(meta_records=n, chunk_bytes=4096, n_buffers=2) as c:
+                c.reset()
+                c.submit_bytes(data)
+                assert_equal_stats(c.finish().to_dict(), want, f"{name} n={n} streamed")
