@@ -183,6 +183,20 @@ int fqgpu_last_timing(fqgpu_ctx* ctx, double* kernel_ms, uint64_t* launches);
  * own work (e.g. a collective) after the scan without a host sync. */
 void* fqgpu_stream(fqgpu_ctx* ctx);
 
+/* Record-offset index as a product (the stand-alone output of the boundary classification,
+ * north-star kernel 1).  Record k is the line with index 4k under the reference's line rule
+ * (src/fq_count.nim:38-42: '\n'-terminated lines, a non-empty unterminated last line counts).
+ * d_offsets[k] (device memory, capacity `cap` entries) receives the byte offset of record k's first byte for
+ * k < min(*n_records, cap); *n_records is the number of records of the buffer (== fqgpu_stats.reads). */
+int fqgpu_index_device(fqgpu_ctx* ctx, const void* dptr, size_t nbytes, uint64_t* d_offsets, uint64_t cap,
+                       uint64_t* n_records);
+/* The first `n` header lines (records 0..n-1 of the index) gathered to HOST memory for fq-meta's
+ * sequencer / barcode detection (src/fq_meta.nim:229-242 reads them with readLine): row k of h_out
+ * (`stride` bytes per row) holds the line without its '\n' (and without one '\r' directly before it),
+ * truncated to `stride` bytes; h_len[k] = bytes stored. */
+int fqgpu_headers_device(fqgpu_ctx* ctx, const void* dptr, size_t nbytes, const uint64_t* d_offsets, uint64_t n,
+                         uint32_t stride, uint8_t* h_out, uint32_t* h_len);
+
 /* Synthetic FASTQ generators, counter-based so any byte range can be
  * produced independently on any GPU; used by bench.py and the parity tests.  `first_record` lets a
  * rank generate its own shard.  Both write whole records only and return the bytes written. */

@@ -265,3 +265,31 @@ def fq_meta_quality_fields(d: dict) -> list:
             phreds.append(t[1])
     return [names, ";".join(phreds), "true" if len(hits) > 1 else "false",
             str(qmin) if qmin >= 0 else "", str(qmax) if qmax >= 0 else "", str(d["meta_lines"] // 4)]
+
+
+def record_offsets(data) -> "np.ndarray":
+    """Byte offset of the first byte of every record (line 4k) under the reference's line rule
+    (src/fq_count.nim:38-42): the checker of fqgpu_index_device."""
+    import numpy as np
+    arr = np.frombuffer(bytes(data), dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+    if arr.size == 0:
+        return np.zeros(0, dtype=np.uint64)
+    nl = np.flatnonzero(arr == 10)
+    starts = nl[3::4].astype(np.uint64) + 1
+    starts = starts[starts < arr.size]
+    return np.concatenate([np.zeros(1, dtype=np.uint64), starts])
+
+
+def header_lines(data, n: int, stride: int = 256) -> list:
+    """First n header lines (lines 4k) without the newline and without one '\\r' before it, truncated to stride."""
+    b = bytes(data)
+    offs = record_offsets(b)[:n]
+    out = []
+    for o in offs:
+        o = int(o)
+        e = b.find(b"\n", o)
+        line = b[o:] if e < 0 else b[o:e]
+        if e >= 0 and line.endswith(b"\r"):
+            line = line[:-1]
+        out.append(line[:stride])
+    return out

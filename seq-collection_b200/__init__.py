@@ -129,6 +129,8 @@ def load_library(path: str | None = None):
         "fqgpu_synth_illumina": (i32, [vp, vp, sz, u64, u64, u64, C.POINTER(sz)]),
         "fqgpu_synth_illumina_bytes": (i32, [vp, vp, u64, u64, u64]),
         "fqgpu_synth_ont": (i32, [vp, vp, sz, u64, u64, u64, C.POINTER(sz)]),
+        "fqgpu_index_device": (i32, [vp, vp, sz, vp, u64, C.POINTER(u64)]),
+        "fqgpu_headers_device": (i32, [vp, vp, sz, vp, u64, C.c_uint32, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -147,7 +149,7 @@ EXPORTED_SYMBOLS = [
     "fqgpu_scan_host", "fqgpu_count_host", "fqgpu_count_file", "fqgpu_count_file_as", "fqgpu_scan_device", "fqgpu_count_device",
     "fqgpu_shard_block_words", "fqgpu_shard_begin", "fqgpu_shard_export", "fqgpu_shard_combine",
     "fqgpu_shard_rescan", "fqgpu_shard_combine_host", "fqgpu_last_timing", "fqgpu_stream", "fqgpu_synth_illumina",
-    "fqgpu_synth_illumina_bytes", "fqgpu_synth_ont",
+    "fqgpu_synth_illumina_bytes", "fqgpu_synth_ont", "fqgpu_index_device", "fqgpu_headers_device",
 ]
 
 
@@ -289,6 +291,23 @@ class FqGpu:
 
     def synth_illumina_bytes(self, dptr: int, first_byte: int, nbytes: int, seed: int):
         self._check(self.lib.fqgpu_synth_illumina_bytes(self._ctx, dptr, first_byte, nbytes, seed))
+
+    def index_device(self, dptr: int, nbytes: int, offsets_ptr: int = 0, cap: int = 0) -> int:
+        """Record-offset index of an HBM-resident buffer: writes up to `cap` uint64 offsets at `offsets_ptr`
+        (device memory) and returns the number of records (fqgpu_index_device)."""
+        n = C.c_uint64()
+        self._check(self.lib.fqgpu_index_device(self._ctx, dptr, nbytes, offsets_ptr, cap, C.byref(n)))
+        return n.value
+
+    def headers_device(self, dptr: int, nbytes: int, offsets_ptr: int, n: int, stride: int = 256) -> list:
+        """The first `n` header lines as bytes objects (truncated to `stride`), gathered on the device."""
+        if n == 0:
+            return []
+        out = (C.c_uint8 * (n * stride))()
+        lens = (C.c_uint32 * n)()
+        self._check(self.lib.fqgpu_headers_device(self._ctx, dptr, nbytes, offsets_ptr, n, stride, out, lens))
+        raw = bytes(out)
+        return [raw[k * stride:k * stride + lens[k]] for k in range(n)]
 
     def synth_ont(self, dptr: int, capacity: int, first_record: int, n_records: int, seed: int) -> int:
         w = C.c_size_t()

@@ -1,0 +1,203 @@
+// fq_index.cu -- the record-offset index as a product (the stand-alone output of the
+// boundary classification): byte offset of the first byte of every record (line 4k) of an HBM-resident
+// FASTQ buffer, and a gather of the first n header lines for fq-meta's sequencer / barcode detection
+// (src/fq_meta.nim:229-242 reads them with readLine; extract_read_info :151-178 stays on the host).
+//
+// Line semantics are those of the scan (Nim streams.lines, src/fq_count.nim:38): lines end at '\n'; the
+// trailing unterminated line exists when it is non-empty; record k is the line with index 4k.
+//
+// Three launches: newline count per 64 KiB tile -> exclusive prefix over the tiles (one CTA) -> write pass
+// that recomputes the masks and stores the successor of every newline whose index is 3 (mod 4).  The input is
+// read twice (2 bytes of HBM traffic per input byte); nothing depends on the statistics kernels.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fqgpu_ctx.h"
+
+namespace fq {
+
+constexpr int IDX_THREADS = 256;
+constexpr int IDX_ROWS = 16;                               // 16-byte groups per thread and tile
+constexpr int IDX_TILE = IDX_THREADS * IDX_ROWS * 16;      // 64 KiB
+
+__device__ __forceinline__ uint32_t idx_nl_flags(uint32_t w) {  // 0x80 in every byte lane that equals '\n' (exact)
+  const uint32_t x = w ^ 0x0A0A0A0Au;
+  return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t idx_nl_mask16(const uint4& v) {
+  const uint32_t lo = __dp4a(idx_nl_flags(v.x), 0x08040201u, __dp4a(idx_nl_flags(v.y), 0x80402010u, 0u));
+  const uint32_t hi = __dp4a(idx_nl_flags(v.z), 0x08040201u, __dp4a(idx_nl_flags(v.w), 0x80402010u, 0u));
+  return (lo >> 7) | (hi << 1);
+}
+// Newline mask of group g (16 bytes at base + 16 g), restricted to the valid bytes [lo0, end).
+__device__ __forceinline__ uint32_t idx_group_mask(const uint8_t* __restrict__ base, u64 g, uint32_t lo0, u64 end) {
+  const u64 off = g * 16;
+  if (off >= end || off + 16 <= (u64)lo0) return 0u;
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + off));
+  uint32_t m = idx_nl_mask16(v);
+  if (off + 16 > end) m &= (1u << (end - off)) - 1u;
+  if (off < (u64)lo0) m &= ~((1u << ((u64)lo0 - off)) - 1u);
+  return m;
+}
+
+__global__ void __launch_bounds__(IDX_THREADS) fq_index_count_kernel(const uint8_t* __restrict__ base, uint32_t lo0, u64 end,
+                                                                    uint32_t* __restrict__ tile_cnt) {
+  __shared__ uint32_t wsum[IDX_THREADS / 32];
+  const u64 g0 = (u64)blockIdx.x * (IDX_THREADS * IDX_ROWS);
+  uint32_t c = 0;
+#pragma unroll 4
+  for (int r = 0; r < IDX_ROWS; r++) c += __popc(idx_group_mask(base, g0 + (u64)r * IDX_THREADS + threadIdx.x, lo0, end));
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < IDX_THREADS / 32; w++) t += wsum[w];
+    tile_cnt[blockIdx.x] = t;
+  }
+}
+
+// Exclusive prefix of the tile counts (one CTA); out[0] = total newlines, out[1] = records.
+__global__ void __launch_bounds__(1024) fq_index_scan_kernel(const uint32_t* __restrict__ tile_cnt, u64* __restrict__ tile_base, u64 ntiles,
+                                                            const uint8_t* __restrict__ base, uint32_t lo0, u64 end, u64* __restrict__ out) {
+  __shared__ u64 part[1024];
+  const int tid = threadIdx.x;
+  const u64 per = (ntiles + 1023) / 1024, a = (u64)tid * per, b = a + per < ntiles ? a + per : ntiles;
+  u64 s = 0;
+  for (u64 t = a; t < b; t++) s += tile_cnt[t];
+  part[tid] = s;
+  __syncthreads();
+  if (tid == 0) {
+    u64 run = 0;
+    for (int i = 0; i < 1024; i++) { const u64 x = part[i]; part[i] = run; run += x; }
+    const u64 n = end - (u64)lo0;
+    const u64 lines = run + ((n > 0 && base[end - 1] != '\n') ? 1 : 0);
+    out[0] = run;
+    out[1] = (lines + 3) / 4;
+  }
+  __syncthreads();
+  u64 run = part[tid];
+  for (u64 t = a; t < b; t++) { tile_base[t] = run; run += tile_cnt[t]; }
+}
+
+__global__ void __launch_bounds__(IDX_THREADS) fq_index_write_kernel(const uint8_t* __restrict__ base, uint32_t lo0, u64 end,
+                                                                    const u64* __restrict__ tile_base, u64* __restrict__ offsets, u64 cap) {
+  __shared__ uint32_t wsum[IDX_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u64 g0 = (u64)blockIdx.x * (IDX_THREADS * IDX_ROWS);
+  const u64 n = end - (u64)lo0;
+  if (blockIdx.x == 0 && tid == 0 && n > 0 && cap > 0) offsets[0] = 0;
+  u64 row_base = tile_base[blockIdx.x];  // newlines before this row of 256 groups
+  for (int r = 0; r < IDX_ROWS; r++) {
+    const u64 g = g0 + (u64)r * IDX_THREADS + tid;
+    uint32_t m = idx_group_mask(base, g, lo0, end);
+    const uint32_t c = __popc(m);
+    uint32_t inc = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += x; }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    uint32_t wb = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < IDX_THREADS / 32; w++) { const uint32_t x = wsum[w]; if (w < warp) wb += x; tot += x; }
+    u64 j = row_base + wb + inc - c;  // index of this group's first newline
+    while (m) {
+      const int k = __ffs(m) - 1;
+      m &= m - 1;
+      if ((j & 3) == 3) {
+        const u64 start = g * 16 + (u64)k + 1 - (u64)lo0, rec = (j + 1) >> 2;
+        if (start < n && rec < cap) offsets[rec] = start;
+      }
+      j++;
+    }
+    row_base += tot;
+    __syncthreads();
+  }
+}
+
+// First `n` header lines (records 0..n-1) into a row-major matrix: up to `stride` bytes each; len[k] = bytes
+// copied (content up to '\n', a '\r' directly before it dropped, truncated at stride).  One warp per record.
+__global__ void fq_headers_kernel(const uint8_t* __restrict__ data, u64 nbytes, const u64* __restrict__ offsets, u64 n,
+                                  uint32_t stride, uint8_t* __restrict__ out, uint32_t* __restrict__ len) {
+  const u64 k = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (k >= n) return;
+  const u64 s = offsets[k];
+  uint32_t L = stride;  // content bytes to copy
+  bool term = false;
+  for (uint32_t o = 0; o < stride + 1 && !term; o += 32) {
+    const u64 p = s + o + lane;
+    const int c = p < nbytes ? (int)data[p] : -1;
+    const uint32_t hit = __ballot_sync(0xffffffffu, c == '\n' || c < 0);
+    if (hit) { const uint32_t e = o + (uint32_t)__ffs(hit) - 1; L = e < stride ? e : stride; term = e <= stride; }
+  }
+  if (term && L > 0 && L <= stride) {  // drop one '\r' directly before the newline
+    const u64 p = s + L;
+    if (p < nbytes && data[p] == '\n' && data[p - 1] == '\r') L--;
+  }
+  for (uint32_t o = lane; o < L; o += 32) out[k * stride + o] = data[s + o];
+  if (lane == 0) len[k] = L;
+}
+
+}  // namespace fq
+
+extern "C" {
+
+int fqgpu_index_device(fqgpu_ctx* ctx, const void* dptr, size_t nbytes, uint64_t* d_offsets, uint64_t cap, uint64_t* n_records) {
+  if (!ctx || !n_records || (cap && !d_offsets)) return FQGPU_EARG;
+  *n_records = 0;
+  if (nbytes == 0) return FQGPU_OK;
+  if (!dptr) return fail(ctx, FQGPU_EARG, "fqgpu_index_device: NULL pointer");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  const uintptr_t addr = (uintptr_t)dptr;
+  const uint32_t lo0 = (uint32_t)(addr & 15);
+  const uint8_t* base = (const uint8_t*)(addr - lo0);
+  const fq::u64 end = (fq::u64)lo0 + nbytes;
+  const fq::u64 ntiles = (end + fq::IDX_TILE - 1) / fq::IDX_TILE;
+  if (ntiles > 0x7FFFFFFFull) return fail(ctx, FQGPU_EARG, "fqgpu_index_device: buffer too large for one call");
+  uint32_t* d_cnt = nullptr;
+  fq::u64* d_base = nullptr;
+  fq::u64* d_out = nullptr;
+  CU_TRY(ctx, cudaMallocAsync((void**)&d_cnt, ntiles * sizeof(uint32_t), ctx->stream));
+  CU_TRY(ctx, cudaMallocAsync((void**)&d_base, ntiles * sizeof(fq::u64), ctx->stream));
+  CU_TRY(ctx, cudaMallocAsync((void**)&d_out, 2 * sizeof(fq::u64), ctx->stream));
+  cudaEvent_t e0 = fqgpu_get_event(ctx), e1 = fqgpu_get_event(ctx);
+  CU_TRY(ctx, cudaEventRecord(e0, ctx->stream));
+  fq::fq_index_count_kernel<<<(unsigned)ntiles, fq::IDX_THREADS, 0, ctx->stream>>>(base, lo0, end, d_cnt);
+  fq::fq_index_scan_kernel<<<1, 1024, 0, ctx->stream>>>(d_cnt, d_base, ntiles, base, lo0, end, d_out);
+  fq::fq_index_write_kernel<<<(unsigned)ntiles, fq::IDX_THREADS, 0, ctx->stream>>>(base, lo0, end, d_base, (fq::u64*)d_offsets, cap);
+  CU_TRY(ctx, cudaGetLastError());
+  CU_TRY(ctx, cudaEventRecord(e1, ctx->stream));
+  ctx->timed.emplace_back(e0, e1);
+  ctx->launches += 3;
+  fq::u64 h[2] = {0, 0};
+  CU_TRY(ctx, cudaMemcpyAsync(h, d_out, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaFreeAsync(d_cnt, ctx->stream));
+  CU_TRY(ctx, cudaFreeAsync(d_base, ctx->stream));
+  CU_TRY(ctx, cudaFreeAsync(d_out, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  *n_records = h[1];
+  return FQGPU_OK;
+}
+
+int fqgpu_headers_device(fqgpu_ctx* ctx, const void* dptr, size_t nbytes, const uint64_t* d_offsets, uint64_t n,
+                         uint32_t stride, uint8_t* h_out, uint32_t* h_len) {
+  if (!ctx || (n && (!dptr || !d_offsets || !h_out || !h_len)) || stride == 0) return FQGPU_EARG;
+  if (n == 0) return FQGPU_OK;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  uint8_t* d_out = nullptr;
+  uint32_t* d_len = nullptr;
+  CU_TRY(ctx, cudaMallocAsync((void**)&d_out, n * stride, ctx->stream));
+  CU_TRY(ctx, cudaMallocAsync((void**)&d_len, n * sizeof(uint32_t), ctx->stream));
+  CU_TRY(ctx, cudaMemsetAsync(d_out, 0, n * stride, ctx->stream));
+  fq::fq_headers_kernel<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>((const uint8_t*)dptr, nbytes, (const fq::u64*)d_offsets, n, stride, d_out, d_len);
+  CU_TRY(ctx, cudaGetLastError());
+  CU_TRY(ctx, cudaMemcpyAsync(h_out, d_out, n * stride, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaMemcpyAsync(h_len, d_len, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaFreeAsync(d_out, ctx->stream));
+  CU_TRY(ctx, cudaFreeAsync(d_len, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return FQGPU_OK;
+}
+
+}  // extern "C"

@@ -133,3 +133,31 @@ def test_ref_work_shape_file(tmp_path):
         r = O.ref_fq_count_file(str(p))
         for k in ("reads", "gc_bases", "n_bases", "bases", "lines"):
             assert r[k] == d[k], (name, k)
+
+
+def test_record_offsets_on_golden_files(golden_dir):
+    """The index checker: one offset per read of docs/fq-count.md, each record of the well-formed fixtures starts
+    with '@' (novaseq.fq is malformed on purpose: mod-4 classing, no '@' check), the brute-force definition agrees."""
+    rows = _rows(os.path.join(golden_dir, "fq_count_docs.tsv"))
+    for r in rows:
+        if r["file"].endswith(".gz"):
+            continue
+        data = open(os.path.join(golden_dir, "fastq", r["file"]), "rb").read()
+        offs = O.record_offsets(data)
+        assert len(offs) == int(r["reads"]), r["file"]
+        lines = data.split(b"\n")
+        if lines and lines[-1] == b"":
+            lines.pop()
+        brute, pos = [], 0
+        for i, ln in enumerate(lines):
+            if i % 4 == 0:
+                brute.append(pos)
+            pos += len(ln) + 1
+        assert offs.tolist() == brute, r["file"]
+        heads = O.header_lines(data, len(offs))
+        assert heads == [ln[:256] for ln in lines[0::4]], r["file"]  # (no CR in the fixtures)
+        if r["file"] != "novaseq.fq":
+            assert all(h.startswith(b"@") for h in heads), r["file"]
+    for name, data in corpus.edge_cases().items():
+        offs = O.record_offsets(data)
+        assert len(offs) == (O.count(data, 0)["reads"] if data else 0), name
