@@ -595,9 +595,12 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
       // =====================================================================================
       // SCANNER warps: newline index of tile B and the span-running carry
       // =====================================================================================
+      u64 carry_L = 0, carry_open = 0;  // span carry before tile B (read together with the bitmap: one round trip)
+      int tileT = 0, tileR = 0;
       if (scanner) {
         TR(3);
         if (haveB) {
+          carry_L = sm.run_L; carry_open = sm.run_open;
           const uint4 bw4 = *reinterpret_cast<const uint4*>(&sm.bitmap[sb][tid * WPS]);
           const uint32_t c0 = __popc(bw4.x), c1 = __popc(bw4.y), c2 = __popc(bw4.z), c3 = __popc(bw4.w);
           const uint32_t c = c0 + c1 + c2 + c3;
@@ -635,11 +638,17 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
               nl_extract_rest(r2, e2 - 6u, pb + 64u); nl_extract_rest(r3, e3 - 6u, pb + 96u);
             }
           }
-          if (tid == 0) {
-            const u64 Lrel = sm.run_L, open = sm.run_open;  // before this tile
-            TileMeta& m = sm.meta[sb];
-            const uint32_t ph = (uint32_t)((phase + Lrel) & 3);  // class of the tile's line 0
+          {
+            const uint32_t ph = (uint32_t)((phase + carry_L) & 3);  // class of the tile's line 0
             // first line of the tile that gets a task: odd class (core-only: class 1), then every 2nd (4th)
+            const int jr0 = a.core ? (int)((1u - ph) & 3u) : ((ph & 1) ? 0 : 1);
+            tileT = (int)T;
+            tileR = (walker || count_only) ? 0 : (a.core ? ((int)T + 4 - jr0) >> 2 : ((int)T + 2 - jr0) >> 1);
+          }
+          if (tid == 0) {
+            const u64 Lrel = carry_L, open = carry_open;  // before this tile
+            TileMeta& m = sm.meta[sb];
+            const uint32_t ph = (uint32_t)((phase + Lrel) & 3);
             const int jr0 = a.core ? (int)((1u - ph) & 3u) : ((ph & 1) ? 0 : 1);
             m.Lrel = Lrel; m.open = open; m.toff = toffB; m.T = (int)T; m.lo = loB; m.hi = hiB;
             m.walker = (walker && !count_only) ? 1 : 0;
@@ -687,12 +696,12 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
       // LINE tasks of tile B: one thread per sequence / quality line with bytes in the tile
       // =====================================================================================
       TileMeta& m = sm.meta[sb];
-      const int R = (haveB && !(a.dbg & 8)) ? m.R : 0;
+      const int R = (haveB && !(a.dbg & 8)) ? tileR : 0;
       // warp 0 issues the TMA and does the serial bookkeeping of thread 0: it takes no line tasks
       if (warp >= 1 && (warp - 1) * 32 < R) {
         const uint8_t* buf = &sm.buf[stB][PAD];
-        const int T = m.T, lo = m.lo, hi = m.hi;
-        const u64 Lrel = m.Lrel, open = m.open;
+        const int T = tileT, lo = loB, hi = hiB;
+        const u64 Lrel = carry_L, open = carry_open;
         const uint32_t ph = (uint32_t)((phase + Lrel) & 3);
         const int jr0 = a.core ? (int)((1u - ph) & 3u) : ((ph & 1) ? 0 : 1);
         const int jshift = a.core ? 2 : 1, cshift = a.core ? 0 : 1;  // line of task i, its index within its class
