@@ -218,9 +218,10 @@ __device__ __forceinline__ uint32_t bfind(uint32_t m) {  // index of the highest
   asm("bfind.u32 %0, %1;" : "=r"(k) : "r"(m));
   return k;
 }
-// The (up to) three highest newlines of bitmap word m -> nl[] slots ending at shared address `end`
-// (exclusive), positions relative to pos0; returns the bits that are left.
-__device__ __forceinline__ uint32_t nl_extract3(uint32_t m, uint32_t end, uint32_t pos0) {
+// The (up to) two highest newlines of bitmap word m -> nl[] slots ending at shared address `end`
+// (exclusive), positions relative to pos0; returns the bits that are left.  (Lines of 32 bytes and more put at
+// most two newlines into a 32-byte word -- "...\n+\n" -- so the loop for the rest hardly ever runs.)
+__device__ __forceinline__ uint32_t nl_extract2(uint32_t m, uint32_t end, uint32_t pos0) {
   {
     const uint32_t k = bfind(m);
     if (m) asm volatile("st.shared.u16 [%0+-2], %1;" ::"r"(end), "h"((uint16_t)(pos0 + k)) : "memory");
@@ -229,11 +230,6 @@ __device__ __forceinline__ uint32_t nl_extract3(uint32_t m, uint32_t end, uint32
   {
     const uint32_t k = bfind(m);
     if (m) asm volatile("st.shared.u16 [%0+-4], %1;" ::"r"(end), "h"((uint16_t)(pos0 + k)) : "memory");
-    m &= ~(1u << (k & 31u));
-  }
-  {
-    const uint32_t k = bfind(m);
-    if (m) asm volatile("st.shared.u16 [%0+-6], %1;" ::"r"(end), "h"((uint16_t)(pos0 + k)) : "memory");
     m &= ~(1u << (k & 31u));
   }
   return m;
@@ -626,16 +622,16 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
             uint16_t* wb = reinterpret_cast<uint16_t*>(&sm.part[sb][0][0]) + tid * WPS;
             wb[0] = (uint16_t)first; wb[1] = (uint16_t)(first + c0); wb[2] = (uint16_t)(first + c0 + c1); wb[3] = (uint16_t)(first + c0 + c1 + c2);
           } else {
-            // newline index: the three highest newlines of every bitmap word without branches (one FLO
+            // newline index: the two highest newlines of every bitmap word without branches (one FLO
             // each, the four words are independent chains); denser words finish in a loop
             const uint32_t nl_s = sm0 + (uint32_t)offsetof(Smem, nl);
             const uint32_t e0 = nl_s + 2u * (first + c0), e1 = e0 + 2u * c1, e2 = e1 + 2u * c2, e3 = e2 + 2u * c3;
             const uint32_t pb = (uint32_t)tid * (WPS * 32u);
-            const uint32_t r0 = nl_extract3(bw4.x, e0, pb), r1 = nl_extract3(bw4.y, e1, pb + 32u);
-            const uint32_t r2 = nl_extract3(bw4.z, e2, pb + 64u), r3 = nl_extract3(bw4.w, e3, pb + 96u);
+            const uint32_t r0 = nl_extract2(bw4.x, e0, pb), r1 = nl_extract2(bw4.y, e1, pb + 32u);
+            const uint32_t r2 = nl_extract2(bw4.z, e2, pb + 64u), r3 = nl_extract2(bw4.w, e3, pb + 96u);
             if (r0 | r1 | r2 | r3) {
-              nl_extract_rest(r0, e0 - 6u, pb); nl_extract_rest(r1, e1 - 6u, pb + 32u);
-              nl_extract_rest(r2, e2 - 6u, pb + 64u); nl_extract_rest(r3, e3 - 6u, pb + 96u);
+              nl_extract_rest(r0, e0 - 4u, pb); nl_extract_rest(r1, e1 - 4u, pb + 32u);
+              nl_extract_rest(r2, e2 - 4u, pb + 64u); nl_extract_rest(r3, e3 - 4u, pb + 96u);
             }
           }
           {
