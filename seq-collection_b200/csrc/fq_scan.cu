@@ -621,7 +621,7 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
           if (walker) {  // the walker wants the newline count before every bitmap word (scratch: the partial-group slots)
             uint16_t* wb = reinterpret_cast<uint16_t*>(&sm.part[sb][0][0]) + tid * WPS;
             wb[0] = (uint16_t)first; wb[1] = (uint16_t)(first + c0); wb[2] = (uint16_t)(first + c0 + c1); wb[3] = (uint16_t)(first + c0 + c1 + c2);
-          } else {
+          } else if (__any_sync(0xffffffffu, c != 0)) {  // (long reads: most warps see no newline at all)
             // newline index: the two highest newlines of every bitmap word without branches (one FLO
             // each, the four words are independent chains); denser words finish in a loop
             const uint32_t nl_s = sm0 + (uint32_t)offsetof(Smem, nl);
