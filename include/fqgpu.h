@@ -194,8 +194,21 @@ int fqgpu_index_device(fqgpu_ctx* ctx, const void* dptr, size_t nbytes, uint64_t
  * sequencer / barcode detection (src/fq_meta.nim:229-242 reads them with readLine): row k of h_out
  * (`stride` bytes per row) holds the line without its '\n' (and without one '\r' directly before it),
  * truncated to `stride` bytes; h_len[k] = bytes stored. */
+/* Lines of the buffer of the most recent fqgpu_index_device call (src/fq_dedup.nim:50 needs `lines div 4`). */
+uint64_t fqgpu_index_lines(fqgpu_ctx* ctx);
 int fqgpu_headers_device(fqgpu_ctx* ctx, const void* dptr, size_t nbytes, const uint64_t* d_offsets, uint64_t n,
                          uint32_t stride, uint8_t* h_out, uint32_t* h_len);
+
+/* Duplicate read IDs (src/fq_dedup.nim:14-84): d_keep[k] (device, one byte per record of the
+ * index) = 1 when record k is the first one with its header line, 0 when an earlier record has the same header
+ * (compared as the reference does: the line without '\n' and without one '\r' before it).  *n_dups = dropped
+ * records (the reference's "duplicates" line).  Exact: hashes only group the candidates, bytes decide. */
+int fqgpu_dedup_device(fqgpu_ctx* ctx, const void* dptr, size_t nbytes, const uint64_t* d_offsets, uint64_t n_records,
+                       uint8_t* d_keep, uint64_t* n_dups);
+/* The same for a FASTQ in HOST memory (H2D copy, index, marks, flags back): what `sc fq-dedup` calls.  h_keep
+ * receives min(*n_records, cap) flags; *n_lines = lines of the input. */
+int fqgpu_dedup_host(fqgpu_ctx* ctx, const void* host, size_t nbytes, uint8_t* h_keep, uint64_t cap,
+                     uint64_t* n_records, uint64_t* n_lines, uint64_t* n_dups);
 
 /* Synthetic FASTQ generators, counter-based so any byte range can be
  * produced independently on any GPU; used by bench.py and the parity tests.  `first_record` lets a

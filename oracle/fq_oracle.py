@@ -293,3 +293,32 @@ def header_lines(data, n: int, stride: int = 256) -> list:
             line = line[:-1]
         out.append(line[:stride])
     return out
+
+
+def fq_dedup(data: bytes):
+    """Restatement of fq_dedup* (src/fq_dedup.nim:14-84) without its Bloom filter (which only pre-selects the
+    candidates; the second pass decides with an exact table): returns (stdout bytes, n_reads, n_dups, keep flags).
+    The first record of every distinct header line (line 4k as `lines` yields it) is echoed, later ones are
+    dropped with their following lines; `echo` terminates every line with '\\n'.  n_reads = lines div 4 (:50).
+    The "false-positive" figures of the reference depend on its Bloom filter (nimble `bloom`, not vendored):
+    parity unpinned, the mirrors print 0."""
+    seen = set()
+    out = []
+    keep = []
+    n_dups = 0
+    write_ln = True
+    i = 0
+    for i, ln in enumerate(nim_lines(data), 1):
+        if (i - 1) % 4 == 0:
+            if ln in seen:
+                write_ln = False
+                n_dups += 1
+                keep.append(0)
+                continue
+            seen.add(ln)
+            keep.append(1)
+            write_ln = True
+            out.append(ln + b"\n")
+        elif write_ln:
+            out.append(ln + b"\n")
+    return b"".join(out), i // 4, n_dups, keep

@@ -131,6 +131,9 @@ def load_library(path: str | None = None):
         "fqgpu_synth_ont": (i32, [vp, vp, sz, u64, u64, u64, C.POINTER(sz)]),
         "fqgpu_index_device": (i32, [vp, vp, sz, vp, u64, C.POINTER(u64)]),
         "fqgpu_headers_device": (i32, [vp, vp, sz, vp, u64, C.c_uint32, vp, vp]),
+        "fqgpu_dedup_device": (i32, [vp, vp, sz, vp, u64, vp, C.POINTER(u64)]),
+        "fqgpu_dedup_host": (i32, [vp, vp, sz, vp, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
+        "fqgpu_index_lines": (u64, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -149,7 +152,7 @@ EXPORTED_SYMBOLS = [
     "fqgpu_scan_host", "fqgpu_count_host", "fqgpu_count_file", "fqgpu_count_file_as", "fqgpu_scan_device", "fqgpu_count_device",
     "fqgpu_shard_block_words", "fqgpu_shard_begin", "fqgpu_shard_export", "fqgpu_shard_combine",
     "fqgpu_shard_rescan", "fqgpu_shard_combine_host", "fqgpu_last_timing", "fqgpu_stream", "fqgpu_synth_illumina",
-    "fqgpu_synth_illumina_bytes", "fqgpu_synth_ont", "fqgpu_index_device", "fqgpu_headers_device",
+    "fqgpu_synth_illumina_bytes", "fqgpu_synth_ont", "fqgpu_index_device", "fqgpu_headers_device", "fqgpu_dedup_device", "fqgpu_dedup_host", "fqgpu_index_lines",
 ]
 
 
@@ -309,6 +312,21 @@ class FqGpu:
         raw = bytes(out)
         return [raw[k * stride:k * stride + lens[k]] for k in range(n)]
 
+    def dedup_device(self, dptr: int, nbytes: int, offsets_ptr: int, n_records: int, keep_ptr: int) -> int:
+        """keep[k] = 1 for the first record of every distinct header line; returns the number of dropped records."""
+        n = C.c_uint64()
+        self._check(self.lib.fqgpu_dedup_device(self._ctx, dptr, nbytes, offsets_ptr, n_records, keep_ptr, C.byref(n)))
+        return n.value
+
+    def dedup_bytes(self, data: bytes):
+        """(keep flags as bytes, n_records, n_lines, n_dups) of a FASTQ held in host memory (fqgpu_dedup_host)."""
+        cap = len(data) // 2 + 1  # a record has at least one newline between two headers... generous bound
+        keep = (C.c_uint8 * cap)()
+        nrec, nlines, ndups = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        buf = (C.c_char * len(data)).from_buffer_copy(data) if data else None
+        self._check(self.lib.fqgpu_dedup_host(self._ctx, buf, len(data), keep, cap, C.byref(nrec), C.byref(nlines), C.byref(ndups)))
+        return bytes(keep[:nrec.value]), nrec.value, nlines.value, ndups.value
+
     def synth_ont(self, dptr: int, capacity: int, first_record: int, n_records: int, seed: int) -> int:
         w = C.c_size_t()
         self._check(self.lib.fqgpu_synth_ont(self._ctx, dptr, capacity, first_record, n_records, seed, C.byref(w)))
@@ -379,6 +397,46 @@ def fq_count(fastq: str, basename: bool = False, absolute: bool = False, ctx: Fq
         if own:
             ctx.close()
     return output_w_fnames(fq_count_row(st), fastq, basename, absolute)
+
+
+def fq_dedup(fastq: str, ctx: FqGpu | None = None):
+    """Mirror of fq_dedup* (src/fq_dedup.nim:14-84): returns (stdout bytes, stderr text).  The duplicate marks come
+    from the GPU (index + hash + sort + byte compare); the host only writes the kept records.  The reference's
+    "false-positive" figures describe its Bloom filter and are printed as 0 (parity unpinned)."""
+    import gzip
+    try:
+        raw = open(fastq, "rb").read()
+    except OSError:
+        raise FqGpuError(EIO, "Unable to open file: " + fastq)
+    data = gzip.decompress(raw) if fastq[-3:] == ".gz" else raw
+    own = ctx is None
+    ctx = ctx or FqGpu(meta_records=0)
+    try:
+        keep, nrec, nlines, ndups = ctx.dedup_bytes(data)
+    finally:
+        if own:
+            ctx.close()
+    out = []
+    i = 0
+    start, n = 0, len(data)
+    write_ln = True
+    while start < n:  # Nim `lines`: split at LF, drop one CR before it, echo adds LF
+        k = data.find(b"\n", start)
+        line = data[start:] if k < 0 else data[start:k]
+        if k >= 0 and line.endswith(b"\r"):
+            line = line[:-1]
+        if i % 4 == 0:
+            write_ln = bool(keep[i // 4])
+        if write_ln:
+            out.append(line + b"\n")
+        i += 1
+        start = n if k < 0 else k + 1
+    err = []
+    if ndups == 0:
+        err += ["No Duplicates Found", "Copying fq to stdout"]
+    err += ["total_reads: %d" % (nlines // 4), "duplicates %d" % ndups, "false-positive: 0",
+            "false-positive-rate: " + nim_float_str(0.0 / ndups if ndups else float("nan"))]
+    return b"".join(out), "\n".join(err) + "\n"
 
 
 # src/fq_meta.nim:35-39 (bounds reproduced as written)

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(IDX_THREADS) fq_index_count_kernel(const uint8
   }
 }
 
-// Exclusive prefix of the tile counts (one CTA); out[0] = total newlines, out[1] = records.
+// Exclusive prefix of the tile counts (one CTA); out[0] = lines (incl. a non-empty unterminated last one), out[1] = records.
 __global__ void __launch_bounds__(1024) fq_index_scan_kernel(const uint32_t* __restrict__ tile_cnt, u64* __restrict__ tile_base, u64 ntiles,
                                                             const uint8_t* __restrict__ base, uint32_t lo0, u64 end, u64* __restrict__ out) {
   __shared__ u64 part[1024];
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(1024) fq_index_scan_kernel(const uint32_t* __r
     for (int i = 0; i < 1024; i++) { const u64 x = part[i]; part[i] = run; run += x; }
     const u64 n = end - (u64)lo0;
     const u64 lines = run + ((n > 0 && base[end - 1] != '\n') ? 1 : 0);
-    out[0] = run;
+    out[0] = lines;
     out[1] = (lines + 3) / 4;
   }
   __syncthreads();
@@ -177,8 +177,11 @@ int fqgpu_index_device(fqgpu_ctx* ctx, const void* dptr, size_t nbytes, uint64_t
   CU_TRY(ctx, cudaFreeAsync(d_out, ctx->stream));
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   *n_records = h[1];
+  ctx->index_lines = h[0];
   return FQGPU_OK;
 }
+
+uint64_t fqgpu_index_lines(fqgpu_ctx* ctx) { return ctx ? ctx->index_lines : 0; }
 
 int fqgpu_headers_device(fqgpu_ctx* ctx, const void* dptr, size_t nbytes, const uint64_t* d_offsets, uint64_t n,
                          uint32_t stride, uint8_t* h_out, uint32_t* h_len) {

@@ -65,6 +65,7 @@ struct fqgpu_ctx {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
   std::vector<cudaEvent_t> event_pool;
   double kernel_ms_done = 0.0;
+  unsigned long long index_lines = 0;  // lines of the buffer of the most recent fqgpu_index_device call
   u64 launches = 0;
   // shard mode
   int shard_rank = 0, shard_world = 1;

@@ -327,9 +327,52 @@ static void fq_meta(const string& fastq, long sample_n, bool basename, bool abso
 }
 
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// fq-dedup  (src/fq_dedup.nim:14-84)
+// ------------------------------------------------------------------------------------------------
+// The file (plain or gz, chosen like fq_count.nim:31) is read into host memory, the GPU marks the duplicate
+// records (index + header hash + sort + byte compare), the kept records are echoed line by line as the
+// reference does (Nim `lines` + echo: one '\r' before '\n' dropped, every line ends with '\n').
+static void fq_dedup(const string& fastq) {
+  if (fastq.size() < 3) quit_error("index out of bounds, the container is empty", 1);
+  const bool gz = fastq.compare(fastq.size() - 3, 3, ".gz") == 0;
+  (void)gz;  // the suffix selects GZFileStream vs FileStream in the reference (:31-34); zlib reads both transparently
+  string data;
+  {
+    char buf[1 << 16];
+    gzFile f = gzopen(fastq.c_str(), "rb");
+    if (!f) quit_error("Unable to open file: " + fastq, 2);  // fq_dedup.nim:36-37
+    int n;
+    while ((n = gzread(f, buf, sizeof buf)) > 0) data.append(buf, (size_t)n);
+    gzclose(f);
+  }
+  fqgpu_ctx* ctx = context(0);
+  vector<uint8_t> keep(data.size() / 2 + 1);
+  uint64_t nrec = 0, nlines = 0, ndups = 0;
+  if (fqgpu_dedup_host(ctx, data.data(), data.size(), keep.data(), keep.size(), &nrec, &nlines, &ndups) != FQGPU_OK)
+    quit_error(fqgpu_last_error(ctx), 1);
+  if (ndups == 0) fprintf(stderr, "No Duplicates Found\nCopying fq to stdout\n");  // :52-54 (with a Bloom filter free of false positives)
+  size_t start = 0, i = 0;
+  bool write_ln = true;
+  const size_t n = data.size();
+  while (start < n) {
+    const void* q = memchr(data.data() + start, '\n', n - start);
+    const size_t e = q ? (size_t)((const char*)q - data.data()) : n;
+    size_t len = e - start;
+    if (q && len && data[e - 1] == '\r') len--;
+    if (i % 4 == 0) write_ln = keep[i / 4] != 0;
+    if (write_ln) { fwrite(data.data() + start, 1, len, stdout); fputc('\n', stdout); }
+    i++;
+    start = q ? e + 1 : n;
+  }
+  const double fpr = (double)0 / (double)ndups;  // :82: fp.float / n_dups.float with fp = 0
+  fprintf(stderr, "total_reads: %llu\nduplicates %llu\nfalse-positive: 0\nfalse-positive-rate: %s\n", (unsigned long long)(nlines / 4),
+          (unsigned long long)ndups, nim_float(fpr).c_str());
+}
+
 static void usage() {
   printf("Sequence data utilities (Version %s)\n\nUsage:\n  sc [options] COMMAND\n\nCommands:\n\n"
-         "  fq-meta          Output metadata for FASTQ\n  fq-count         Counts lines in a FASTQ\n\n"
+         "  fq-meta          Output metadata for FASTQ\n  fq-count         Counts lines in a FASTQ\n  fq-dedup         Removes exact duplicates from FASTQ Files\n\n"
          "Options:\n  --debug                    Debug\n  -h, --help                 Show this help\n"
          "\n(B200 build: only the FASTQ scanning commands are provided; see DESIGN.md)\n", kVersion);
 }
@@ -372,10 +415,14 @@ int main(int argc, char** argv) {
     const long n = strtol(lines_opt.c_str(), &endp, 10);                            // parseInt(opts.lines), sc.nim:79
     if (!files.empty() && (endp == lines_opt.c_str() || *endp)) quit_error("invalid integer: " + lines_opt, 1);
     for (auto& f : files) fq_meta(f, n, basename, absolute);
+  } else if (cmd == "fq-dedup") {
+    if (help) { printf("Removes exact duplicates from FASTQ Files\n\nUsage:\n  fq-dedup [options] fastq\n\nArguments:\n  fastq            Input FASTQ\n\nOptions:\n  -h, --help                 Show this help\n"); return 0; }
+    if (files.size() != 1) quit_error("Error: fq-dedup takes one FASTQ", 1);  // sc.nim:120 nargs = 1
+    fq_dedup(files[0]);
   } else if (cmd == "-h" || cmd == "--help") {
     usage();
   } else {
-    quit_error("Error: Unknown command '" + cmd + "' (this build provides fq-count and fq-meta)");
+    quit_error("Error: Unknown command '" + cmd + "' (this build provides fq-count, fq-meta and fq-dedup)");
   }
   if (g_ctx) fqgpu_destroy(g_ctx);
   return 0;

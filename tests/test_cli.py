@@ -131,3 +131,28 @@ def test_fq_meta_n_option_and_gz_case():
     assert rc == 0 and out.rstrip("\n").split("\t")[15] == "2"
     rc, out, _ = run("fq-meta", os.path.join(FQ, "dup.fq.gz"))
     assert rc == 0 and out.rstrip("\n").split("\t")[13:16] == ["32", "41", "8"]
+
+
+@pytest.mark.gpu
+def test_fq_dedup_functional_tests(golden_dir, tmp_path):
+    """scripts/functional-tests.sh:86-91 (`grep -c '@'` == 4 for dup.fq and dup.fq.gz), the whole stdout against the
+    oracle's restatement of src/fq_dedup.nim, the stderr summary (:76-83) and the exit code for a missing file."""
+    import gzip
+    from oracle import fq_oracle as O
+    for f in ("dup.fq", "dup.fq.gz", "nodup.fq"):
+        path = os.path.join(golden_dir, "fastq", f)
+        raw = open(path, "rb").read()
+        want, n_reads, n_dups, _ = O.fq_dedup(gzip.decompress(raw) if f.endswith(".gz") else raw)
+        p = subprocess.run([SC, "fq-dedup", path], capture_output=True)
+        assert p.returncode == 0, p.stderr
+        assert p.stdout == want and p.stdout.count(b"@") == 4, f
+        err = p.stderr.decode()
+        assert "total_reads: %d\n" % n_reads in err and "duplicates %d\n" % n_dups in err and "false-positive: 0\n" in err
+        assert ("No Duplicates Found\nCopying fq to stdout\n" in err) == (n_dups == 0)
+        assert err.rstrip().endswith("false-positive-rate: " + ("nan" if n_dups == 0 else "0.0"))
+    crlf = tmp_path / "crlf.fq"
+    crlf.write_bytes(b"@a\r\nAC\r\n+\r\nII\r\n@a\nGG\n+\nII\n@b\nT")
+    p = subprocess.run([SC, "fq-dedup", str(crlf)], capture_output=True)
+    assert p.stdout == b"@a\nAC\n+\nII\n@b\nT\n" and b"duplicates 1\n" in p.stderr
+    code, out, err = run("fq-dedup", str(tmp_path / "missing.fq"))
+    assert code == 2 and "Unable to open file" in err

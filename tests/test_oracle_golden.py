@@ -161,3 +161,14 @@ def test_record_offsets_on_golden_files(golden_dir):
     for name, data in corpus.edge_cases().items():
         offs = O.record_offsets(data)
         assert len(offs) == (O.count(data, 0)["reads"] if data else 0), name
+
+
+def test_fq_dedup_oracle_on_golden(golden_dir):
+    """scripts/functional-tests.sh:86-91 pins `grep -c '@'` == 4 for dup.fq / dup.fq.gz."""
+    import gzip
+    for f in ("dup.fq", "dup.fq.gz"):
+        raw = open(os.path.join(golden_dir, "fastq", f), "rb").read()
+        out, n_reads, n_dups, keep = O.fq_dedup(gzip.decompress(raw) if f.endswith(".gz") else raw)
+        assert out.count(b"@") == 4 and (n_reads, n_dups) == (8, 4) and keep == [1, 1, 0, 1, 0, 1, 0, 0]
+    out, n_reads, n_dups, keep = O.fq_dedup(open(os.path.join(golden_dir, "fastq", "nodup.fq"), "rb").read())
+    assert (n_reads, n_dups) == (4, 0) and keep == [1, 1, 1, 1]
