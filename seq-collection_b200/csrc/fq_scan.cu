@@ -38,6 +38,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "fq_layout.h"
 
@@ -373,8 +374,9 @@ __device__ __noinline__ void tile_walker(Smem& sm, const ScanArgs& a, const uint
 }
 
 // Adds the packed per-position table (both copies, cell and alias cell of every pair) to the span block and clears it.
-__device__ __forceinline__ void flush_pos_tab(Smem& sm, u64* block, int tid) {
-  for (int t = tid; t < POS_BINS / 2; t += THREADS) {
+template <class S>
+__device__ __forceinline__ void flush_pos_tab(S& sm, u64* block, int tid) {
+  for (int t = tid; t < POS_BINS / 2; t += (int)blockDim.x) {
     const uint32_t A = (uint32_t)t + 8u;  // pair of q = 2A, 2A+1 -> positions 2t, 2t+1
     const uint32_t c0 = (A & 7u) * PT_STRIDE + (A >> 3), c1 = c0 + 8u * PT_STRIDE - 1u;
     u64 lo = 0, hi = 0;
@@ -390,8 +392,9 @@ __device__ __forceinline__ void flush_pos_tab(Smem& sm, u64* block, int tid) {
   }
 }
 // The linear table of the generic paths.
-__device__ __forceinline__ void flush_gpos(Smem& sm, u64* block, int tid) {
-  for (int p = tid; p < POS_BINS; p += THREADS) {
+template <class S>
+__device__ __forceinline__ void flush_gpos(S& sm, u64* block, int tid) {
+  for (int p = tid; p < POS_BINS; p += (int)blockDim.x) {
     const uint32_t v = sm.gpos[p];
     if (v) { block[OFF_POS_SUM + p] += v; sm.gpos[p] = 0; }
   }
@@ -866,6 +869,8 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
   }
 }
 
+#include "fq_scan_fast.cuh"
+
 // ---------------------------------------------------------------------------------------------
 // resync: guess the line phase at every span start.  Span-relative line j (j >= 1) starts after the
 // span's j-th newline; the first j whose line starts with '@' while line j+2 starts with '+' is a
@@ -887,7 +892,7 @@ __global__ void fq_resync_kernel(const ScanArgs a) {
     if ((cflags & CARRY_UNKNOWN_START) && a.carry->bytes == 0) a.shard->first_byte = a.base[a.lo0];
   }
   SpanDesc& d = a.desc[span];
-  if (lane == 0) { d.T = 0; d.head_len = 0; d.tail_len = 0; d.state = SPAN_PENDING; d.exact = PHASE_UNKNOWN; d.G = 0; d.P0 = 0; }
+  if (lane == 0) { d.T = 0; d.head_len = 0; d.tail_len = 0; d.state = SPAN_PENDING; d.exact = PHASE_UNKNOWN; d.G = 0; d.P0 = 0; d.pad = 0; }
   // The phase of the launch's first byte: exact from the stream carry, or (multi-GPU shard with an
   // unknown start) the shard's hypothesis plus the lines counted so far, or resynced like any span.
   const bool start_known = !(cflags & CARRY_UNKNOWN_START) || (cflags & CARRY_HYP_VALID);
@@ -994,7 +999,7 @@ __global__ void __launch_bounds__(STITCH_THREADS) fq_stitch_kernel(const ScanArg
     sP0 = P0; s_phase = exact;
     s_detached = unknown && G == 0;  // still inside the shard's first line fragment
     d.G = G; d.P0 = P0; d.exact = exact;
-    const int ok = hyp_ok && d.guess == exact;
+    const int ok = hyp_ok && d.guess == exact && !d.pad;  // pad: the fast pass abandoned the span
     d.state = ok ? SPAN_COMMITTED : SPAN_RESCAN;
     if (!ok) atomicAdd(&a.hdr->mismatches, 1u);
     s_commit = ok;
@@ -1325,6 +1330,8 @@ int scan_tile_bytes() { return TILE; }
 int scan_threads() { return THREADS; }
 
 cudaError_t scan_configure() {
+  cudaError_t e = cudaFuncSetAttribute(fq_scan_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastSmem));
+  if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(fq_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
 }
 
@@ -1362,10 +1369,21 @@ cudaError_t launch_scan(const void* ptr, size_t nbytes, SpanDesc* desc, LaunchHd
     if ((e = cudaEventRecord(ev_join, meta_stream)) != cudaSuccess) return e;
   }
   fq_resync_kernel<<<a.nspans, 32, 0, st>>>(a);
-  fq_scan_kernel<<<a.nspans, THREADS, sizeof(Smem), st>>>(a, 0);
+  // pass 0: fq_scan_kernel.  FQGPU_SCAN=fast selects the experimental register-resident fq_scan_fast_kernel
+  // instead (well-formed input only; it abandons a span otherwise and pass 1 redoes it).  Measured on B200 it is
+  // slower than the tile kernel in every mode, so it is not the default.
+  const char* scan_env = getenv("FQGPU_SCAN");
+  if (scan_env && !strcmp(scan_env, "fast")) fq_scan_fast_kernel<<<a.nspans, F_THREADS, sizeof(FastSmem), st>>>(a);
+  else fq_scan_kernel<<<a.nspans, THREADS, sizeof(Smem), st>>>(a, 0);
   fq_stitch_kernel<<<a.nspans, STITCH_THREADS, 0, st>>>(a);
   fq_scan_kernel<<<a.nspans, THREADS, sizeof(Smem), st>>>(a, 1);
   if (meta_records && (e = cudaStreamWaitEvent(st, ev_join, 0)) != cudaSuccess) return e;
+  if (dbg & 16u) {  // diagnostics: spans the stitch kernel sent to the exact second pass
+    LaunchHdr h;
+    cudaStreamSynchronize(st);
+    cudaMemcpy(&h, hdr, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "fqgpu: launch of %zu bytes, %u spans, %u rescanned\n", nbytes, a.nspans, h.mismatches);
+  }
   return cudaGetLastError();
 }
 
