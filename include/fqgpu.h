@@ -141,6 +141,18 @@ int fqgpu_count_file(fqgpu_ctx* ctx, const char* path, fqgpu_stats* out); /* pla
  * (src/fq_count.nim:31), fq_meta by a case-INsensitive one (src/fq_meta.nim:219). */
 int fqgpu_count_file_as(fqgpu_ctx* ctx, const char* path, int as_gz, fqgpu_stats* out);
 
+/* Many files at once (replaces the sequential `for fastq in files` loop of sc.nim:115-116).
+ * Files are independent streams, so up to n_threads host threads (0 = min(n, 8)) each own a private context --
+ * staging ring, stream, device-resident counters -- and count one file at a time: the host-side work of one
+ * file (read() or the zlib inflate of gzip_stream.nim:16-17, the ceiling of the .gz path) overlaps the others'
+ * and the GPU scans of all of them interleave.  cfg->device == FQGPU_DEVICE_ALL spreads the contexts round-robin
+ * over every visible GPU (one file per GPU instead of byte ranges).  as_gz: per-file stream kind, or NULL =
+ * by a case-sensitive ".gz" suffix (src/fq_count.nim:31).  out[i] and rc[i] are filled for every file; the return
+ * value is the first non-OK rc in FILE ORDER, which is where the sequential loop would have stopped. */
+#define FQGPU_DEVICE_ALL (-2)
+int fqgpu_count_files(const fqgpu_config* cfg, const char* const* paths, const int* as_gz, int n, int n_threads,
+                      fqgpu_stats* out, int* rc);
+
 /* HBM-resident interface (kernel-only measurements; data already on the context's device).
  * scan_device may be called repeatedly: each call continues the same stream of bytes (carry
  * state is kept on the device), exactly as if the buffers were concatenated. */

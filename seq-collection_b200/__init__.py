@@ -116,6 +116,7 @@ def load_library(path: str | None = None):
         "fqgpu_count_host": (i32, [vp, vp, sz, C.POINTER(Stats)]),
         "fqgpu_count_file": (i32, [vp, C.c_char_p, C.POINTER(Stats)]),
         "fqgpu_count_file_as": (i32, [vp, C.c_char_p, i32, C.POINTER(Stats)]),
+        "fqgpu_count_files": (i32, [C.POINTER(Config), C.POINTER(C.c_char_p), C.POINTER(i32), i32, i32, C.POINTER(Stats), C.POINTER(i32)]),
         "fqgpu_scan_device": (i32, [vp, vp, sz]),
         "fqgpu_count_device": (i32, [vp, vp, sz, C.POINTER(Stats)]),
         "fqgpu_shard_block_words": (sz, []),
@@ -149,7 +150,7 @@ def load_library(path: str | None = None):
 EXPORTED_SYMBOLS = [
     "fqgpu_abi_version", "fqgpu_stats_size", "fqgpu_build_info", "fqgpu_device_count", "fqgpu_create",
     "fqgpu_destroy", "fqgpu_last_error", "fqgpu_acquire", "fqgpu_submit", "fqgpu_finish", "fqgpu_reset",
-    "fqgpu_scan_host", "fqgpu_count_host", "fqgpu_count_file", "fqgpu_count_file_as", "fqgpu_scan_device", "fqgpu_count_device",
+    "fqgpu_scan_host", "fqgpu_count_host", "fqgpu_count_file", "fqgpu_count_file_as", "fqgpu_count_files", "fqgpu_scan_device", "fqgpu_count_device",
     "fqgpu_shard_block_words", "fqgpu_shard_begin", "fqgpu_shard_export", "fqgpu_shard_combine",
     "fqgpu_shard_rescan", "fqgpu_shard_combine_host", "fqgpu_last_timing", "fqgpu_stream", "fqgpu_synth_illumina",
     "fqgpu_synth_illumina_bytes", "fqgpu_synth_ont", "fqgpu_index_device", "fqgpu_headers_device", "fqgpu_dedup_device", "fqgpu_dedup_host", "fqgpu_index_lines",
@@ -397,6 +398,38 @@ def fq_count(fastq: str, basename: bool = False, absolute: bool = False, ctx: Fq
         if own:
             ctx.close()
     return output_w_fnames(fq_count_row(st), fastq, basename, absolute)
+
+
+DEVICE_ALL = -2  # fqgpu_config.device for count_files: spread the per-thread contexts over every visible GPU
+
+
+def count_files(paths, n_threads: int = 0, device: int = -1, meta_records: int = 0, flags: int = 0,
+                as_gz=None, chunk_bytes: int = 0):
+    """fqgpu_count_files: the files are counted concurrently (one host thread + private context per file in
+    flight).  Returns (first non-OK rc in file order, [(rc, Stats) per file])."""
+    lib = load_library()
+    n = len(paths)
+    cfg = Config(device, chunk_bytes, 0, meta_records, flags, 0)
+    arr = (C.c_char_p * max(n, 1))(*[os.fsencode(p) for p in paths])
+    gz = None if as_gz is None else (C.c_int * max(n, 1))(*[int(bool(x)) for x in as_gz])
+    out = (Stats * max(n, 1))()
+    rcs = (C.c_int * max(n, 1))()
+    rc = lib.fqgpu_count_files(C.byref(cfg), arr, gz, n, n_threads, out, rcs)
+    return rc, [(rcs[i], out[i]) for i in range(n)]
+
+
+def fq_count_many(files, basename: bool = False, absolute: bool = False, n_threads: int = 0) -> list:
+    """`sc fq-count a b c ...` (the loop of sc.nim:115-116) with the files counted concurrently: the rows in
+    argument order.  Raises FqGpuError at the first file the sequential loop would have failed on."""
+    rc, res = count_files(files, n_threads=n_threads, flags=F_CORE_ONLY)
+    rows = []
+    for f, (r, st) in zip(files, res):
+        if r == EIO:
+            raise FqGpuError(EIO, "Unable to open file: " + f)
+        if r != OK:
+            raise FqGpuError(r, load_library().fqgpu_last_error(None).decode())
+        rows.append(output_w_fnames(fq_count_row(st), f, basename, absolute))
+    return rows
 
 
 def fq_dedup(fastq: str, ctx: FqGpu | None = None):

@@ -406,13 +406,25 @@ __device__ __forceinline__ uint32_t part_entry(int g, int lo, int hi, uint32_t q
 
 // K1a: newline masks of a tile's 16-byte groups -> bitmap slot (threads r of nthr; bytes [lo, hi) are valid).
 // Returns the OR of the valid bytes (bit 7 of any byte set: the tile takes the generic walker path).
-__device__ __forceinline__ uint32_t k1a_tile(Smem& sm, uint32_t buf_s, uint32_t bm_s, int lo, int hi, int r, int nthr) {
+template <int NTHR>
+__device__ __forceinline__ uint32_t k1a_tile(Smem& sm, uint32_t buf_s, uint32_t bm_s, int lo, int hi, int r) {
+  constexpr int nthr = NTHR;
   uint32_t hib = 0;
-  if (lo == 0 && hi == TILE) {  // interior tile: no edge handling
-    for (int g = r; g < TILE / 16; g += nthr) {
-      const uint4 v = lds128(buf_s + 16u * (uint32_t)g);
-      hib |= (v.x | v.y) | (v.z | v.w);
-      sts16(bm_s + 2u * (uint32_t)g, nl_mask16_ascii(v));
+  if (lo == 0 && hi == TILE) {  // interior tile: no edge handling; unrolled (immediate offsets, loads first)
+    constexpr int NIT = (TILE / 16 + NTHR - 1) / NTHR;
+    const uint32_t a0 = buf_s + 16u * (uint32_t)r, b0 = bm_s + 2u * (uint32_t)r;
+    uint4 v[NIT];
+#pragma unroll
+    for (int i = 0; i < NIT; i++) {
+      v[i] = make_uint4(0u, 0u, 0u, 0u);
+      if ((i + 1) * NTHR <= TILE / 16 || r + i * NTHR < TILE / 16)
+        v[i] = lds128(a0 + (uint32_t)(16 * i * NTHR));
+    }
+#pragma unroll
+    for (int i = 0; i < NIT; i++) {
+      hib |= (v[i].x | v[i].y) | (v[i].z | v[i].w);
+      if ((i + 1) * NTHR <= TILE / 16 || r + i * NTHR < TILE / 16)
+        sts16(b0 + (uint32_t)(2 * i * NTHR), nl_mask16_ascii(v[i]));
     }
     if (hib & 0x80808080u) {  // the short compare is exact only for bytes < 0x80: redo this thread's groups
       for (int g = r; g < TILE / 16; g += nthr) sts16(bm_s + 2u * (uint32_t)g, nl_mask16(lds128(buf_s + 16u * (uint32_t)g)));
@@ -567,8 +579,8 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
   {  // prologue: all warps classify the span's first tile
     mbar_wait(bar0_s, 0u);
     par_bits = 1u;
-    const uint32_t hib = k1a_tile(sm, buf0_s, sm0 + (uint32_t)offsetof(Smem, bitmap), 0 == it_first ? (int)a.lo0 : 0,
-                                  0 == it_last ? hi_last : TILE, tid, THREADS);
+    const uint32_t hib = k1a_tile<THREADS>(sm, buf0_s, sm0 + (uint32_t)offsetof(Smem, bitmap), 0 == it_first ? (int)a.lo0 : 0,
+                                           0 == it_last ? hi_last : TILE, tid);
     if (hib & 0x80808080u) sm.hiflag[0] = 1;
     __syncthreads();
   }
@@ -802,8 +814,8 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
       if (it + 1 < nt) {
         mbar_wait(bar0_s + 8u * stA, (par_bits >> stA) & 1u);
         par_bits ^= 1u << stA;
-        const uint32_t hib = k1a_tile(sm, buf0_s + (uint32_t)stA * STAGE_BYTES, sm0 + (uint32_t)offsetof(Smem, bitmap) + (uint32_t)sc * (BM_WORDS * 4u),
-                                      it + 1 == it_first ? (int)a.lo0 : 0, it + 1 == it_last ? hi_last : TILE, tid - LINE_THREADS, WORK_THREADS);
+        const uint32_t hib = k1a_tile<WORK_THREADS>(sm, buf0_s + (uint32_t)stA * STAGE_BYTES, sm0 + (uint32_t)offsetof(Smem, bitmap) + (uint32_t)sc * (BM_WORDS * 4u),
+                                                    it + 1 == it_first ? (int)a.lo0 : 0, it + 1 == it_last ? hi_last : TILE, tid - LINE_THREADS);
         if (hib & 0x80808080u) sm.hiflag[sc] = 1;
       }
     }

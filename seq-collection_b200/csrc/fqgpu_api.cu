@@ -9,7 +9,10 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include <atomic>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "fq_layout.h"
@@ -435,6 +438,54 @@ int fqgpu_count_file_as(fqgpu_ctx* ctx, const char* path, int as_gz, fqgpu_stats
     close(fd);
   }
   return fqgpu_finish(ctx, out);
+}
+
+// ---- many files at once (sc.nim:115-116) ------------------------------------------------------------
+int fqgpu_count_files(const fqgpu_config* cfg, const char* const* paths, const int* as_gz, int n, int n_threads,
+                      fqgpu_stats* out, int* rc) {
+  if (n < 0 || (n > 0 && (!paths || !out || !rc))) return FQGPU_EARG;
+  if (n == 0) return FQGPU_OK;
+  fqgpu_config base;
+  memset(&base, 0, sizeof base);
+  base.device = -1;
+  if (cfg) base = *cfg;
+  if (base.chunk_bytes == 0) base.chunk_bytes = (size_t)16 << 20;  // several rings at once: smaller pinned chunks
+  int ndev = 1, dev0 = base.device;
+  if (base.device == FQGPU_DEVICE_ALL) {
+    ndev = fqgpu_device_count();
+    if (ndev <= 0) { g_create_error = "fqgpu_count_files: no CUDA device"; for (int i = 0; i < n; i++) rc[i] = FQGPU_ECUDA; return FQGPU_ECUDA; }
+    dev0 = 0;
+  }
+  int nthr = n_threads > 0 ? n_threads : (n < 8 ? n : 8);
+  if (nthr > n) nthr = n;
+  for (int i = 0; i < n; i++) { rc[i] = FQGPU_ECUDA; memset(&out[i], 0, sizeof(fqgpu_stats)); }
+  std::atomic<int> next(0);
+  std::mutex mu;
+  std::vector<std::string> msgs((size_t)n);  // what fqgpu_last_error(NULL) reports afterwards: the first failure in file order
+  auto worker = [&](int t) {
+    fqgpu_config c = base;
+    if (base.device == FQGPU_DEVICE_ALL) c.device = dev0 + t % ndev;
+    fqgpu_ctx* ctx = nullptr;
+    const int crc = fqgpu_create(&ctx, &c);
+    for (;;) {
+      const int i = next.fetch_add(1);
+      if (i >= n) break;
+      if (crc != FQGPU_OK) { rc[i] = crc; std::lock_guard<std::mutex> g(mu); msgs[(size_t)i] = g_create_error; continue; }
+      const char* p = paths[i];
+      if (!p) { rc[i] = FQGPU_EARG; continue; }
+      const size_t L = strlen(p);
+      const int gz = as_gz ? as_gz[i] : (L >= 3 && strcmp(p + L - 3, ".gz") == 0);
+      rc[i] = fqgpu_count_file_as(ctx, p, gz, &out[i]);
+      if (rc[i] != FQGPU_OK) { std::lock_guard<std::mutex> g(mu); msgs[(size_t)i] = ctx->err; }
+    }
+    if (ctx) fqgpu_destroy(ctx);
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < nthr; t++) pool.emplace_back(worker, t);
+  worker(0);
+  for (auto& th : pool) th.join();
+  for (int i = 0; i < n; i++) if (rc[i] != FQGPU_OK) { g_create_error = msgs[(size_t)i]; return rc[i]; }
+  return FQGPU_OK;
 }
 
 // ---- synthetic data -----------------------------------------------------------------------------

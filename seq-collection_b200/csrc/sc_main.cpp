@@ -115,13 +115,9 @@ static fqgpu_ctx* context(uint64_t meta_records, uint32_t flags = 0) {
 // ------------------------------------------------------------------------------------------------
 static const char* kFqCountHeader = "reads\tgc_content\tgc_bases\tn_bases\tbases";
 
-static void fq_count(fqgpu_ctx* ctx, const string& fastq, bool basename, bool absolute) {
-  if (fastq.size() < 3) quit_error("index out of bounds, the container is empty", 1);  // fastq[^3 .. ^1] raises (unpinned text)
-  const bool gz = fastq.compare(fastq.size() - 3, 3, ".gz") == 0;  // case-sensitive, fq_count.nim:31
-  fqgpu_stats st;
-  int rc = fqgpu_count_file_as(ctx, fastq.c_str(), gz, &st);
+static void fq_count_row(const string& fastq, int rc, const fqgpu_stats& st, const char* err, bool basename, bool absolute) {
   if (rc == FQGPU_EIO) quit_error("Unable to open file: " + fastq, 2);  // fq_count.nim:35-36
-  if (rc != FQGPU_OK) quit_error(fqgpu_last_error(ctx), 1);
+  if (rc != FQGPU_OK) quit_error(err, 1);
   const double gc_content = (double)(int64_t)st.gc_bases / (double)((int64_t)st.bases - (int64_t)st.n_bases);  // :48
   vector<string> out = {std::to_string(st.reads), nim_float(gc_content), std::to_string(st.gc_bases),
                         std::to_string(st.n_bases), std::to_string(st.bases)};
@@ -405,8 +401,29 @@ int main(int argc, char** argv) {
     if (header) puts(output_header(kFqCountHeader, basename, absolute).c_str());  // sc.nim:110-111
     else if (files.empty()) quit_error("No FASTQ specified", 3);                  // :112-113
     if (!files.empty()) {
-      fqgpu_ctx* ctx = context(0, FQGPU_F_CORE_ONLY);  // fq-count prints reads, GC, N and bases only
-      for (auto& f : files) fq_count(ctx, f, basename, absolute);                 // :115-116
+      // sc.nim:115-116 loops over the files one after the other; here they are counted concurrently (one host
+      // thread + private context each, fqgpu_count_files) and the rows are printed in argument order, stopping
+      // where the sequential loop would have stopped.  FQGPU_THREADS=1 restores the sequential order of work.
+      const int n = (int)files.size();
+      for (int i = 0; i < n; i++) if (files[i].size() < 3) { files.resize(i + 1); break; }  // fastq[^3 .. ^1] raises there
+      const int nok = files.back().size() < 3 ? (int)files.size() - 1 : (int)files.size();
+      fqgpu_config cfg;
+      memset(&cfg, 0, sizeof cfg);
+      cfg.device = -1;
+      cfg.flags = FQGPU_F_CORE_ONLY;  // fq-count prints reads, GC, N and bases only
+      if (const char* e = getenv("FQGPU_CHUNK_MB")) cfg.chunk_bytes = (size_t)atol(e) << 20;
+      if (const char* e = getenv("FQGPU_DEVICES")) if (!strcmp(e, "all")) cfg.device = FQGPU_DEVICE_ALL;
+      vector<const char*> paths;
+      for (int i = 0; i < nok; i++) paths.push_back(files[i].c_str());
+      vector<fqgpu_stats> st((size_t)nok + 1);
+      vector<int> rcs((size_t)nok + 1, FQGPU_OK);
+      const int threads = getenv("FQGPU_THREADS") ? atoi(getenv("FQGPU_THREADS")) : 0;
+      if (nok) fqgpu_count_files(&cfg, paths.data(), nullptr, nok, threads, st.data(), rcs.data());
+      for (int i = 0; i < nok; i++) {
+        if (rcs[i] == FQGPU_ECUDA && i == 0) quit_error(string("GPU unavailable: ") + fqgpu_last_error(nullptr), 1);
+        fq_count_row(files[i], rcs[i], st[i], fqgpu_last_error(nullptr), basename, absolute);
+      }
+      if (nok < (int)files.size()) quit_error("index out of bounds, the container is empty", 1);  // (unpinned text)
     }
   } else if (cmd == "fq-meta") {
     if (help) { printf("Output metadata for FASTQ\n\nUsage:\n  fq-meta [options] [fastq ...]\n\nArguments:\n  [fastq ...]      List of FASTQ files\n\nOptions:\n  -n, --lines=LINES          Number of sequences to sample (n_lines) for qual and index/barcode determination (default: 100)\n  -t, --header               Output the header\n  -b, --basename             Add basename column\n  -a, --absolute             Add column for absolute path\n  -h, --help                 Show this help\n"); return 0; }

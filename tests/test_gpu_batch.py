@@ -1,0 +1,92 @@
+"""fqgpu_count_files: many files counted concurrently (the loop of sc.nim:115-116).
+
+Each file is an independent stream with its own context, so every result must equal the oracle's for that
+file whatever the thread count, and errors must surface where the sequential loop would have stopped."""
+import gzip
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import seq_collection_b200 as fq
+from oracle import fq_oracle as O
+from tests import corpus
+from tests.test_gpu_parity import assert_equal_stats
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SC = os.path.join(ROOT, "seq-collection_b200", "sc")
+
+
+@pytest.fixture(scope="module")
+def files(tmp_path_factory, golden_dir):
+    d = tmp_path_factory.mktemp("batch")
+    rng = np.random.default_rng(21)
+    out = []
+    for i in range(6):
+        data = corpus.random_fastq(rng, 2000 + 700 * i, min_len=20, max_len=300, crlf=(i == 3), final_newline=(i != 4))
+        p = d / f"r{i}.fq"
+        if i % 2:
+            p = d / f"r{i}.fq.gz"
+            with gzip.open(p, "wb", compresslevel=1) as f:
+                f.write(data)
+        else:
+            p.write_bytes(data)
+        out.append(str(p))
+    for name in ("dup.fq.gz", "illumina_2.fq", "novaseq.fq"):
+        q = os.path.join(golden_dir, "fastq", name)
+        if os.path.exists(q):
+            out.append(q)
+    empty = d / "empty.fq"
+    empty.write_bytes(b"")
+    out.append(str(empty))
+    return out
+
+
+@pytest.mark.parametrize("threads", [0, 1, 3])
+def test_count_files_equals_oracle(files, threads):
+    rc, res = fq.count_files(files, n_threads=threads, meta_records=100)
+    assert rc == fq.OK
+    for path, (r, st) in zip(files, res):
+        assert r == fq.OK, path
+        assert_equal_stats(st.to_dict(), O.count_file(path, 100), f"{path} threads={threads}")
+
+
+def test_count_files_reports_the_first_failure_in_file_order(files):
+    paths = files[:2] + ["/nonexistent/x.fq"] + files[2:4] + ["/nonexistent/y.fq.gz"]
+    rc, res = fq.count_files(paths, n_threads=4)
+    assert rc == fq.EIO
+    assert [r for r, _ in res] == [fq.OK, fq.OK, fq.EIO, fq.OK, fq.OK, fq.EIO]
+    assert "Unable to open file: /nonexistent/x.fq" in fq.load_library().fqgpu_last_error(None).decode()
+    for path, (r, st) in zip(paths, res):
+        if r == fq.OK:
+            assert_equal_stats(st.to_dict(), O.count_file(path, 0), path)
+
+
+def test_count_files_empty_list_and_all_devices(files):
+    assert fq.count_files([])[0] == fq.OK
+    rc, res = fq.count_files(files[:3], device=fq.DEVICE_ALL, flags=fq.F_CORE_ONLY)
+    assert rc == fq.OK
+    for path, (r, st) in zip(files[:3], res):
+        assert fq.fq_count_row(st) == O.fq_count_row(O.count_file(path, 0)), path
+
+
+def test_fq_count_many_and_cli_rows(files):
+    rows = fq.fq_count_many(files, basename=True)
+    want = [fq.output_w_fnames(O.fq_count_row(O.count_file(p, 0)), p, True, False) for p in files]
+    assert rows == want
+    from importlib import import_module
+
+    b = import_module("seq-collection_b200.build")
+    b.build_lib()
+    b.build_cli()
+    par = subprocess.run([SC, "fq-count", "-t", "-b", *files], capture_output=True, text=True)
+    seq = subprocess.run([SC, "fq-count", "-t", "-b", *files], capture_output=True, text=True, env={**os.environ, "FQGPU_THREADS": "1"})
+    assert par.returncode == 0 and seq.returncode == 0, par.stderr + seq.stderr
+    assert par.stdout == seq.stdout == "reads\tgc_content\tgc_bases\tn_bases\tbases\tbasename\n" + "\n".join(want) + "\n"
+    # a missing file in the middle: the rows before it, then "Error 2" as in src/fq_count.nim:35-36
+    bad = subprocess.run([SC, "fq-count", files[0], "/nonexistent/x.fq", files[1]], capture_output=True, text=True)
+    assert bad.returncode == 2 and "Unable to open file: /nonexistent/x.fq" in bad.stderr
+    assert bad.stdout == O.fq_count_row(O.count_file(files[0], 0)) + "\n"
