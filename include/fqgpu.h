@@ -141,6 +141,13 @@ int fqgpu_count_file(fqgpu_ctx* ctx, const char* path, fqgpu_stats* out); /* pla
  * (src/fq_count.nim:31), fq_meta by a case-INsensitive one (src/fq_meta.nim:219). */
 int fqgpu_count_file_as(fqgpu_ctx* ctx, const char* path, int as_gz, fqgpu_stats* out);
 
+/* .gz input that is BGZF (blocked gzip: bgzip / htslib and many sequencer pipelines write it; every member is at
+ * most 64 KiB and carries its sizes) is not inflated through zlib on the host (gzip_stream.nim:16-17) but on the
+ * device, one thread per member, straight into the buffer the scan reads (csrc/fq_bgzf.cu).
+ * Plain gzip, or anything malformed, takes the zlib path.  FQGPU_NO_BGZF=1 in the environment disables the device
+ * path.  Returns the members the last fqgpu_count_file* call on this context inflated on the device. */
+unsigned long long fqgpu_bgzf_members(const fqgpu_ctx* ctx);
+
 /* Many files at once (replaces the sequential `for fastq in files` loop of sc.nim:115-116).
  * Files are independent streams, so up to n_threads host threads (0 = min(n, 8)) each own a private context --
  * staging ring, stream, device-resident counters -- and count one file at a time: the host-side work of one

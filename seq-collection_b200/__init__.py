@@ -116,6 +116,7 @@ def load_library(path: str | None = None):
         "fqgpu_count_host": (i32, [vp, vp, sz, C.POINTER(Stats)]),
         "fqgpu_count_file": (i32, [vp, C.c_char_p, C.POINTER(Stats)]),
         "fqgpu_count_file_as": (i32, [vp, C.c_char_p, i32, C.POINTER(Stats)]),
+        "fqgpu_bgzf_members": (C.c_ulonglong, [vp]),
         "fqgpu_count_files": (i32, [C.POINTER(Config), C.POINTER(C.c_char_p), C.POINTER(i32), i32, i32, C.POINTER(Stats), C.POINTER(i32)]),
         "fqgpu_scan_device": (i32, [vp, vp, sz]),
         "fqgpu_count_device": (i32, [vp, vp, sz, C.POINTER(Stats)]),
@@ -150,7 +151,7 @@ def load_library(path: str | None = None):
 EXPORTED_SYMBOLS = [
     "fqgpu_abi_version", "fqgpu_stats_size", "fqgpu_build_info", "fqgpu_device_count", "fqgpu_create",
     "fqgpu_destroy", "fqgpu_last_error", "fqgpu_acquire", "fqgpu_submit", "fqgpu_finish", "fqgpu_reset",
-    "fqgpu_scan_host", "fqgpu_count_host", "fqgpu_count_file", "fqgpu_count_file_as", "fqgpu_count_files", "fqgpu_scan_device", "fqgpu_count_device",
+    "fqgpu_scan_host", "fqgpu_count_host", "fqgpu_count_file", "fqgpu_count_file_as", "fqgpu_count_files", "fqgpu_bgzf_members", "fqgpu_scan_device", "fqgpu_count_device",
     "fqgpu_shard_block_words", "fqgpu_shard_begin", "fqgpu_shard_export", "fqgpu_shard_combine",
     "fqgpu_shard_rescan", "fqgpu_shard_combine_host", "fqgpu_last_timing", "fqgpu_stream", "fqgpu_synth_illumina",
     "fqgpu_synth_illumina_bytes", "fqgpu_synth_ont", "fqgpu_index_device", "fqgpu_headers_device", "fqgpu_dedup_device", "fqgpu_dedup_host", "fqgpu_index_lines",
@@ -248,6 +249,10 @@ class FqGpu:
         else:
             self._check(self.lib.fqgpu_count_file_as(self._ctx, os.fsencode(path), int(as_gz), C.byref(st)))
         return st
+
+    def bgzf_members(self) -> int:
+        """Members of the last count_file() input that were inflated on the device (0: plain gzip / host zlib)."""
+        return int(self.lib.fqgpu_bgzf_members(self._ctx))
 
     # -- HBM resident --------------------------------------------------------------------------
     def scan_device(self, dptr: int, nbytes: int):

@@ -15,6 +15,7 @@
 #include <thread>
 #include <vector>
 
+#include "fq_bgzf.h"
 #include "fq_layout.h"
 
 #include "fqgpu_ctx.h"
@@ -58,6 +59,11 @@ void fqgpu_destroy(fqgpu_ctx* ctx) {
   cudaFree(ctx->d_hdr);
   cudaFree(ctx->d_shard);
   if (ctx->h_shard) cudaFreeHost(ctx->h_shard);
+  if (ctx->h_comp) cudaFreeHost(ctx->h_comp);
+  cudaFree(ctx->d_comp);
+  cudaFree(ctx->d_inflated);
+  cudaFree(ctx->d_members);
+  cudaFree(ctx->d_mstatus);
   cudaFree(ctx->d_out);
   if (ctx->h_out) cudaFreeHost(ctx->h_out);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -125,6 +131,7 @@ int fqgpu_reset(fqgpu_ctx* ctx) {
   ctx->timed.clear();
   ctx->kernel_ms_done = 0.0;
   ctx->launches = 0;
+  ctx->bgzf_members = 0;
   ctx->shard_rank = 0;
   ctx->shard_world = 1;
   return FQGPU_OK;
@@ -388,11 +395,126 @@ int fqgpu_count_file(fqgpu_ctx* ctx, const char* path, fqgpu_stats* out) {
   return fqgpu_count_file_as(ctx, path, L >= 3 && strcmp(path + L - 3, ".gz") == 0, out);
 }
 
+}  // extern "C"
+
+// ---- BGZF input: members walked on the host, inflated on the device (fq_bgzf.cu) ---------------------------
+// Returns FQGPU_OK when the whole file went through the device path (the caller finishes the stream), 1 when the
+// file is not well-formed BGZF (or cannot be opened): the caller resets and takes the zlib path, which also
+// reports I/O errors the way the reference does.  < 0: CUDA failure.
+static const size_t kBgzfBatchBytes = (size_t)256 << 20;  // compressed bytes per batch
+static const size_t kBgzfBatchMembers = 32768;            // members (= inflating threads) per batch
+
+static int count_bgzf(fqgpu_ctx* ctx, const char* path) {
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) return 1;
+  struct stat sb;
+  uint8_t hd[18];
+  if (fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode) || sb.st_size < 28 || pread(fd, hd, 18, 0) != 18 ||
+      !(hd[0] == 0x1f && hd[1] == 0x8b && hd[2] == 8 && hd[3] == 4 && hd[12] == 'B' && hd[13] == 'C' && hd[14] == 2 && hd[15] == 0)) {
+    close(fd);
+    return 1;
+  }
+  const size_t fsize = (size_t)sb.st_size;
+  auto bail = [&](int code) { close(fd); return code; };
+#define CU_B(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return bail(FQGPU_ECUDA); } } while (0)
+  CU_B(cudaSetDevice(ctx->device));
+  const size_t want = fsize < kBgzfBatchBytes ? ((fsize + 4095) & ~(size_t)4095) : kBgzfBatchBytes;
+  if (ctx->comp_cap < want) {
+    if (ctx->h_comp) cudaFreeHost(ctx->h_comp);
+    cudaFree(ctx->d_comp);
+    ctx->h_comp = nullptr; ctx->d_comp = nullptr; ctx->comp_cap = 0;
+    CU_B(cudaMallocHost(&ctx->h_comp, want));
+    CU_B(cudaMalloc(&ctx->d_comp, want));
+    ctx->comp_cap = want;
+  }
+  if (ctx->members_cap < kBgzfBatchMembers) {
+    cudaFree(ctx->d_members); cudaFree(ctx->d_mstatus);
+    ctx->d_members = nullptr; ctx->d_mstatus = nullptr; ctx->members_cap = 0;
+    CU_B(cudaMalloc(&ctx->d_members, kBgzfBatchMembers * sizeof(fq::BgzfMember)));
+    CU_B(cudaMalloc(&ctx->d_mstatus, kBgzfBatchMembers * sizeof(uint32_t)));
+    ctx->members_cap = kBgzfBatchMembers;
+  }
+  std::vector<fq::BgzfMember> members;
+  std::vector<uint32_t> status;
+  size_t pos = 0;
+  while (pos < fsize) {
+    const size_t want_now = fsize - pos < ctx->comp_cap ? fsize - pos : ctx->comp_cap;
+    size_t got = 0;
+    while (got < want_now) {
+      const ssize_t r = pread(fd, ctx->h_comp + got, want_now - got, (off_t)(pos + got));
+      if (r < 0) return bail(1);
+      if (r == 0) break;
+      got += (size_t)r;
+    }
+    members.clear();
+    size_t off = 0;
+    u64 out_total = 0;
+    while (off + 18 <= got && members.size() < kBgzfBatchMembers) {
+      const uint8_t* h = ctx->h_comp + off;
+      if (!(h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && h[3] == 4)) return bail(1);
+      const size_t xlen = (size_t)h[10] | ((size_t)h[11] << 8);
+      if (off + 12 + xlen > got) break;  // the header continues in the next batch
+      long bsize = -1;
+      for (size_t q = 12; q + 4 <= 12 + xlen;) {
+        const size_t slen = (size_t)h[q + 2] | ((size_t)h[q + 3] << 8);
+        if (h[q] == 'B' && h[q + 1] == 'C' && slen == 2 && q + 6 <= 12 + xlen) bsize = (long)h[q + 4] | ((long)h[q + 5] << 8);
+        q += 4 + slen;
+      }
+      if (bsize < 0) return bail(1);
+      const size_t total = (size_t)bsize + 1;
+      if (total < 12 + xlen + 8) return bail(1);
+      if (off + total > got) break;  // the member continues in the next batch
+      const uint8_t* t = h + total - 4;
+      const uint32_t isize = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+      if (isize > 65536u) return bail(1);
+      fq::BgzfMember m;
+      m.in_off = off + 12 + xlen; m.out_off = out_total; m.in_len = (unsigned)(total - xlen - 12 - 8); m.out_len = isize;
+      members.push_back(m);
+      out_total += isize;
+      off += total;
+    }
+    if (off == 0) return bail(1);  // no complete member in a full batch / trailing garbage
+    if (ctx->inflated_cap < out_total + 64) {
+      cudaFree(ctx->d_inflated);
+      ctx->d_inflated = nullptr; ctx->inflated_cap = 0;
+      const size_t cap = ((size_t)out_total + 64 + ((size_t)64 << 20)) & ~(size_t)4095;
+      CU_B(cudaMalloc(&ctx->d_inflated, cap));
+      ctx->inflated_cap = cap;
+    }
+    const int n = (int)members.size();
+    status.assign((size_t)n, 0u);
+    CU_B(cudaMemcpyAsync(ctx->d_comp, ctx->h_comp, off, cudaMemcpyHostToDevice, ctx->stream));
+    CU_B(cudaMemcpyAsync(ctx->d_members, members.data(), (size_t)n * sizeof(fq::BgzfMember), cudaMemcpyHostToDevice, ctx->stream));
+    CU_B(fq::launch_bgzf_inflate(ctx->d_comp, (const fq::BgzfMember*)ctx->d_members, n, ctx->d_inflated, ctx->d_mstatus, ctx->stream));
+    CU_B(cudaMemcpyAsync(status.data(), ctx->d_mstatus, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_B(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n; i++) if (status[(size_t)i]) return bail(1);  // corrupt member: let zlib decide
+    const int rc = fqgpu_scan_device(ctx, ctx->d_inflated, (size_t)out_total);
+    if (rc != FQGPU_OK) return bail(rc);
+    CU_B(cudaStreamSynchronize(ctx->stream));  // the batch buffers are reused
+    ctx->bgzf_members += (u64)n;
+    pos += off;
+  }
+#undef CU_B
+  close(fd);
+  return FQGPU_OK;
+}
+
+extern "C" {
+
+unsigned long long fqgpu_bgzf_members(const fqgpu_ctx* ctx) { return ctx ? ctx->bgzf_members : 0; }
+
 int fqgpu_count_file_as(fqgpu_ctx* ctx, const char* path, int as_gz, fqgpu_stats* out) {
   if (!ctx || !path || !out) return FQGPU_EARG;
   const bool gz = as_gz != 0;
   int rc = fqgpu_reset(ctx);
   if (rc != FQGPU_OK) return rc;
+  if (gz && !getenv("FQGPU_NO_BGZF")) {  // BGZF (blocked gzip): inflated on the device, member by member
+    rc = count_bgzf(ctx, path);
+    if (rc == FQGPU_OK) return fqgpu_finish(ctx, out);
+    if (rc < 0) return rc;
+    if ((rc = fqgpu_reset(ctx)) != FQGPU_OK) return rc;  // not BGZF: the host zlib path below
+  }
   if (gz) {
     gzFile f = gzopen(path, "rb");
     if (!f) return fail(ctx, FQGPU_EIO, std::string("Unable to open file: ") + path);

@@ -72,6 +72,16 @@ struct fqgpu_ctx {
   bool shard_exact = false;   // this rank was rescanned with the exact carry
   fq::ShardInfo* d_shard = nullptr;
   u64* h_shard = nullptr;      // pinned: gathered shard blocks (up to 64 ranks)
+  // on-device BGZF inflate (fq_bgzf.cu): compressed batch (pinned host + device), inflated bytes, member table
+  uint8_t* h_comp = nullptr;
+  uint8_t* d_comp = nullptr;
+  size_t comp_cap = 0;
+  uint8_t* d_inflated = nullptr;
+  size_t inflated_cap = 0;
+  void* d_members = nullptr;
+  uint32_t* d_mstatus = nullptr;
+  size_t members_cap = 0;
+  u64 bgzf_members = 0;        // members inflated on the device since the last reset (diagnostics)
 };
 
 

@@ -79,3 +79,21 @@ def random_fastq(rng: np.random.Generator, n_records: int, min_len=1, max_len=30
     if not final_newline and data:
         data = data[: -len(nl)]
     return data
+
+
+def bgzf_bytes(data: bytes, block: int = 65280, level: int = 6, eof: bool = True) -> bytes:
+    """BGZF (blocked gzip, SAM spec 4.1): one gzip member per `block` input bytes, each with the 'BC' extra field
+    holding its compressed size; optionally the 28-byte empty EOF member."""
+    import struct
+    import zlib
+
+    out = bytearray()
+    for i in range(0, max(len(data), 1), block):
+        chunk = data[i:i + block]
+        co = zlib.compressobj(level, zlib.DEFLATED, -15)
+        comp = co.compress(chunk) + co.flush()
+        out += struct.pack("<BBBBIBBH", 0x1F, 0x8B, 8, 4, 0, 0, 0xFF, 6) + b"BC" + struct.pack("<HH", 2, len(comp) + 25)
+        out += comp + struct.pack("<II", zlib.crc32(chunk), len(chunk))
+    if eof:
+        out += bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+    return bytes(out)

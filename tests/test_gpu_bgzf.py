@@ -1,0 +1,101 @@
+"""On-device BGZF inflate (csrc/fq_bgzf.cu) behind fqgpu_count_file*: the statistics must equal the oracle's on
+the same .gz (which the oracle reads through zlib, like the reference), for every DEFLATE block type, and anything
+that is not well-formed BGZF must behave exactly like the host zlib path."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+import seq_collection_b200 as fq
+from oracle import fq_oracle as O
+from tests import corpus
+from tests.test_gpu_parity import assert_equal_stats
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    with fq.FqGpu(meta_records=100) as c:
+        yield c
+
+
+def _write(tmp_path, name, blob):
+    p = tmp_path / name
+    p.write_bytes(blob)
+    return str(p)
+
+
+@pytest.mark.parametrize("level,block", [(6, 65280), (1, 65280), (9, 30000), (0, 65280), (6, 61), (6, 7)])
+def test_bgzf_equals_oracle(ctx, tmp_path, level, block):
+    """level 0 = stored blocks, tiny members = fixed Huffman codes, the rest dynamic codes."""
+    rng = np.random.default_rng(100 + level + block)
+    n = 6000 if block > 1000 else 40
+    data = corpus.random_fastq(rng, n, min_len=20, max_len=300, final_newline=(level != 1))
+    path = _write(tmp_path, f"l{level}_b{block}.fq.gz", corpus.bgzf_bytes(data, block=block, level=level))
+    st = ctx.count_file(path)
+    assert ctx.bgzf_members() >= len(data) // block, "the device path was not taken"
+    assert_equal_stats(st.to_dict(), O.count(data, 100), f"level={level} block={block}")
+    assert_equal_stats(st.to_dict(), O.count_file(path, 100), "oracle through zlib")
+
+
+def test_bgzf_edge_corpus_and_no_eof_member(ctx, tmp_path):
+    for name, data in corpus.edge_cases().items():
+        path = _write(tmp_path, name + ".fq.gz", corpus.bgzf_bytes(data, block=4096, eof=(len(name) % 2 == 0)))
+        assert_equal_stats(ctx.count_file(path).to_dict(), O.count(data, 100), name)
+
+
+def test_plain_gzip_takes_the_zlib_path(ctx, tmp_path):
+    rng = np.random.default_rng(7)
+    data = corpus.random_fastq(rng, 500)
+    path = str(tmp_path / "plain.fq.gz")
+    with gzip.open(path, "wb") as f:
+        f.write(data)
+    st = ctx.count_file(path)
+    assert ctx.bgzf_members() == 0
+    assert_equal_stats(st.to_dict(), O.count(data, 100), "plain gzip")
+
+
+def test_malformed_bgzf_behaves_like_zlib(ctx, tmp_path, monkeypatch):
+    rng = np.random.default_rng(8)
+    data = corpus.random_fastq(rng, 3000)
+    good = corpus.bgzf_bytes(data, block=20000)
+    cases = {
+        "corrupt_payload": good[:300] + bytes([good[300] ^ 0x5A, good[301] ^ 0xA5]) + good[302:],
+        "truncated": good[: len(good) // 2],
+        "bgzf_then_plain_member": good + gzip.compress(b"@x\nACGT\n+\nIIII\n"),
+    }
+    for name, blob in cases.items():
+        path = _write(tmp_path, name + ".fq.gz", blob)
+
+        def outcome():
+            try:
+                return ("ok", ctx.count_file(path).to_dict())
+            except fq.FqGpuError as e:
+                return ("error", e.code)
+
+        dev = outcome()
+        monkeypatch.setenv("FQGPU_NO_BGZF", "1")
+        host = outcome()
+        monkeypatch.delenv("FQGPU_NO_BGZF")
+        assert dev == host, name
+
+
+def test_bgzf_many_members_synthetic(ctx, tmp_path):
+    """The bench shape: 100k records (36 MB) in 64 KiB members; also through fqgpu_count_files."""
+    import torch
+
+    n = 360 * 100_000
+    buf = torch.empty(n, dtype=torch.uint8, device="cuda")
+    ctx.synth_illumina(buf.data_ptr(), n, 0, 100_000, 20240229)
+    data = bytes(buf.cpu().numpy())
+    path = _write(tmp_path, "synth.fq.gz", corpus.bgzf_bytes(data, level=1))
+    st = ctx.count_file(path)
+    assert ctx.bgzf_members() == (n + 65279) // 65280 + 1
+    want = O.count(data, 100)
+    assert_equal_stats(st.to_dict(), want, "synthetic bgzf")
+    rc, res = fq.count_files([path, path], meta_records=100)
+    assert rc == fq.OK and all(r == fq.OK for r, _ in res)
+    for _, s in res:
+        assert_equal_stats(s.to_dict(), want, "count_files bgzf")
