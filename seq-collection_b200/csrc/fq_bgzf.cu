@@ -10,8 +10,7 @@
 // other -- measured 1.01 active threads per instruction -- so each member gets its own warp and the machine hides
 // the latency of ~10 k such warps behind each other) inflates its stream (RFC 1951: stored, fixed and dynamic
 // Huffman blocks; canonical-code decoding without lookup tables, the code lengths kept in local memory) straight to
-// its place in the output buffer, which fqgpu_scan_device then scans like any HBM-resident input.  Member CRC-32s are not checked (zlib's gzread does);
-// the uncompressed size is.  Anything that is not well-formed BGZF makes the caller fall back to the zlib path.
+// its place in the output buffer, which fqgpu_scan_device then scans like any HBM-resident input.  Anything that is not well-formed BGZF makes the caller fall back to the zlib path.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -73,15 +72,10 @@ __device__ __forceinline__ int huff_decode(Bits& b, const uint16_t* count, const
   return -1;
 }
 
-enum { BGZF_OK = 0, BGZF_EBLOCK = 1, BGZF_ECODE = 2, BGZF_EDIST = 3, BGZF_ESIZE = 4, BGZF_ETRUNC = 5 };
+enum { BGZF_OK = 0, BGZF_EBLOCK = 1, BGZF_ECODE = 2, BGZF_EDIST = 3, BGZF_ESIZE = 4, BGZF_ETRUNC = 5, BGZF_ECRC = 6 };
 
-constexpr int BGZF_WARPS = 4;  // members per CTA
-
-__global__ void __launch_bounds__(32 * BGZF_WARPS) bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfMember* __restrict__ members,
-                                                          int n, uint8_t* out, uint32_t* __restrict__ status) {
-  const int i = blockIdx.x * BGZF_WARPS + (threadIdx.x >> 5);
-  if (i >= n || (threadIdx.x & 31)) return;
-  const BgzfMember d = members[i];
+// The serial part: one thread inflates member d.  Returns BGZF_*.
+__device__ __noinline__ int bgzf_inflate_member(const uint8_t* __restrict__ comp, const BgzfMember& d, uint8_t* out) {
   Bits b;
   b.p = comp + d.in_off; b.end = b.p + d.in_len; b.buf = 0; b.cnt = 0;
   uint8_t* o = out + d.out_off;
@@ -167,13 +161,69 @@ __global__ void __launch_bounds__(32 * BGZF_WARPS) bgzf_inflate_kernel(const uin
   } while (!last && !err);
   if (!err && b.cnt < 0) err = BGZF_ETRUNC;
   if (!err && produced != cap) err = BGZF_ESIZE;
-  status[i] = (uint32_t)err;
+  return err;
+}
+
+constexpr int BGZF_WARPS = 4;        // members per CTA
+constexpr uint32_t CRC_SLICE = 2048;  // bytes per lane in the CRC pass (32 slices cover a 64 KiB member)
+
+// crc_shift[k] = the CRC register after CRC_SLICE zero bytes when it starts as 1 << k (a linear map over GF(2)).
+struct CrcShift { uint32_t col[32]; };
+
+__device__ __forceinline__ uint32_t crc_bytes(const uint32_t* tab, const uint8_t* p, uint32_t n, uint32_t v) {
+  for (uint32_t k = 0; k < n; k++) v = tab[(v ^ p[k]) & 0xFFu] ^ (v >> 8);
+  return v;
+}
+
+__global__ void __launch_bounds__(32 * BGZF_WARPS) bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfMember* __restrict__ members,
+                                                                       int n, uint8_t* out, uint32_t* __restrict__ status, const CrcShift sh) {
+  __shared__ uint32_t tab[256];
+  for (int t = threadIdx.x; t < 256; t += 32 * BGZF_WARPS) {  // the reflected CRC-32 table (polynomial 0xEDB88320)
+    uint32_t c = (uint32_t)t;
+    for (int k = 0; k < 8; k++) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+    tab[t] = c;
+  }
+  __syncthreads();
+  const int i = blockIdx.x * BGZF_WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const BgzfMember d = members[i];
+  int err = 0;
+  if (lane == 0) err = bgzf_inflate_member(comp, d, out);
+  err = __shfl_sync(0xffffffffu, err, 0);  // (also orders lane 0's writes before the reads below)
+  if (!err) {
+    // CRC-32 of the member's output: the first (len mod 2 KiB) bytes by lane 0 from the all-ones register, then the
+    // full slices from zero registers in parallel, folded in order: v = shift(v) ^ raw(slice).
+    const uint8_t* o = out + d.out_off;
+    const uint32_t len = d.out_len, nfull = len / CRC_SLICE, rem = len % CRC_SLICE;
+    const uint32_t raw = (uint32_t)lane < nfull ? crc_bytes(tab, o + rem + (uint32_t)lane * CRC_SLICE, CRC_SLICE, 0u) : 0u;
+    uint32_t v = 0xFFFFFFFFu;
+    if (lane == 0) v = crc_bytes(tab, o, rem, v);
+    v = __shfl_sync(0xffffffffu, v, 0);
+    for (uint32_t j = 0; j < nfull; j++) {   // every lane folds the same chain (uniform, 32 x nfull steps)
+      uint32_t w = 0;
+#pragma unroll 8
+      for (int k = 0; k < 32; k++) w ^= ((v >> k) & 1u) ? sh.col[k] : 0u;
+      v = w ^ __shfl_sync(0xffffffffu, raw, (int)j);
+    }
+    if ((v ^ 0xFFFFFFFFu) != d.crc) err = BGZF_ECRC;
+  }
+  if (lane == 0) status[i] = (uint32_t)err;
 }
 
 cudaError_t launch_bgzf_inflate(const uint8_t* d_comp, const BgzfMember* d_members, int n, uint8_t* d_out, uint32_t* d_status,
                                 cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
-  bgzf_inflate_kernel<<<(n + BGZF_WARPS - 1) / BGZF_WARPS, 32 * BGZF_WARPS, 0, st>>>(d_comp, d_members, n, d_out, d_status);
+  static const CrcShift sh = [] {
+    CrcShift s;
+    for (int k = 0; k < 32; k++) {
+      uint32_t v = 1u << k;
+      for (uint32_t b = 0; b < CRC_SLICE * 8; b++) v = (v & 1u) ? 0xEDB88320u ^ (v >> 1) : v >> 1;  // one zero bit per step
+      s.col[k] = v;
+    }
+    return s;
+  }();
+  bgzf_inflate_kernel<<<(n + BGZF_WARPS - 1) / BGZF_WARPS, 32 * BGZF_WARPS, 0, st>>>(d_comp, d_members, n, d_out, d_status, sh);
   return cudaGetLastError();
 }
 

@@ -11,6 +11,8 @@ struct BgzfMember {
   unsigned long long out_off;  // first output byte, relative to the batch's output buffer
   unsigned int in_len;         // payload bytes (without the gzip header and the CRC32 / ISIZE trailer)
   unsigned int out_len;        // ISIZE
+  unsigned int crc;            // CRC32 of the output (trailer)
+  unsigned int pad;
 };
 
 // One warp per member (lane 0 decodes); status[i] = 0 or the reason member i could not be inflated.

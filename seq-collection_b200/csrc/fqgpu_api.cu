@@ -469,6 +469,7 @@ static int count_bgzf(fqgpu_ctx* ctx, const char* path) {
       if (isize > 65536u) return bail(1);
       fq::BgzfMember m;
       m.in_off = off + 12 + xlen; m.out_off = out_total; m.in_len = (unsigned)(total - xlen - 12 - 8); m.out_len = isize;
+      m.crc = (uint32_t)t[-4] | ((uint32_t)t[-3] << 8) | ((uint32_t)t[-2] << 16) | ((uint32_t)t[-1] << 24); m.pad = 0;
       members.push_back(m);
       out_total += isize;
       off += total;

@@ -64,6 +64,9 @@ def test_malformed_bgzf_behaves_like_zlib(ctx, tmp_path, monkeypatch):
     cases = {
         "corrupt_payload": good[:300] + bytes([good[300] ^ 0x5A, good[301] ^ 0xA5]) + good[302:],
         "truncated": good[: len(good) // 2],
+        # sizes stay right, only the CRC-32 of the member tells: a literal byte of a stored block, the CRC field itself
+        "stored_byte_flip": (lambda b: b[:40] + bytes([b[40] ^ 1]) + b[41:])(corpus.bgzf_bytes(data, block=20000, level=0)),
+        "crc_field_flip": (lambda b, e: b[:e - 8] + bytes([b[e - 8] ^ 0x10]) + b[e - 7:])(good, 18 + (good[16] | good[17] << 8) - 17),
         "bgzf_then_plain_member": good + gzip.compress(b"@x\nACGT\n+\nIIII\n"),
     }
     for name, blob in cases.items():
