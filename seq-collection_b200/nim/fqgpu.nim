@@ -48,6 +48,9 @@ proc fqgpu_submit*(ctx: FqgpuCtx, chunk: pointer, nbytes: csize_t): cint
 proc fqgpu_finish*(ctx: FqgpuCtx, stats: ptr FqgpuStats): cint
 proc fqgpu_reset*(ctx: FqgpuCtx): cint
 proc fqgpu_count_file_as*(ctx: FqgpuCtx, path: cstring, as_gz: cint, stats: ptr FqgpuStats): cint
+proc fqgpu_count_files*(cfg: ptr FqgpuConfig, paths: cstringArray, as_gz: ptr cint, n, n_threads: cint,
+                        stats: ptr FqgpuStats, rc: ptr cint): cint
+proc fqgpu_bgzf_members*(ctx: FqgpuCtx): culonglong
 {.pop.}
 
 ## ------------------------------------------------------------------------------------------------
@@ -92,3 +95,18 @@ proc fq_meta_quality_gpu*(fastq: string, as_gz: bool, sample_n: int): tuple[qual
   if rc != FQGPU_OK: raise newException(IOError, $fqgpu_last_error(ctx))
   if st.meta_status == 1: raise newException(IndexError, "index out of bounds, the container is empty")
   return (st.meta_qual_min.int, st.meta_qual_max.int, st.meta_lines.int)
+
+
+## Replacement of the loop over the files, sc.nim:115-116 (`for fastq in opts.fastq: fq_count.fq_count(fastq, ...)`):
+## the files are counted concurrently (one host thread and private context per file in flight) and the rows are
+## echoed in argument order; the first failure in file order ends the run like the sequential loop would have.
+proc fq_count_many_gpu*(files: seq[string]): seq[FqgpuStats] =
+  var cfg = FqgpuConfig(device: -1, flags: FQGPU_F_CORE_ONLY)
+  result = newSeq[FqgpuStats](files.len)
+  var rcs = newSeq[cint](files.len)
+  let paths = allocCStringArray(files)
+  defer: deallocCStringArray(paths)
+  discard fqgpu_count_files(addr cfg, paths, nil, files.len.cint, 0, addr result[0], addr rcs[0])
+  for i, rc in rcs:
+    if rc == FQGPU_EIO: raise newException(IOError, "Unable to open file: " & files[i])   # quit_error(..., 2) upstream
+    if rc != FQGPU_OK: raise newException(IOError, $fqgpu_last_error(nil))
