@@ -90,3 +90,23 @@ def test_fq_count_many_and_cli_rows(files):
     bad = subprocess.run([SC, "fq-count", files[0], "/nonexistent/x.fq", files[1]], capture_output=True, text=True)
     assert bad.returncode == 2 and "Unable to open file: /nonexistent/x.fq" in bad.stderr
     assert bad.stdout == O.fq_count_row(O.count_file(files[0], 0)) + "\n"
+
+
+def test_multithreaded_file_reads_equal_oracle(tmp_path, monkeypatch):
+    """A plain file larger than the threshold of parallel_pread, several chunks per file, odd sizes: the chunk
+    filled by 1, 3 and 8 reader threads gives the same stream (FQGPU_READ_THREADS is read once per process, so
+    each setting runs in its own interpreter)."""
+    import subprocess
+    import sys
+
+    rng = np.random.default_rng(33)
+    data = corpus.random_fastq(rng, 130_000, min_len=80, max_len=200, final_newline=False)  # ~40 MB
+    path = tmp_path / "big.fq"
+    path.write_bytes(data)
+    want = O.fq_count_row(O.count(data, 0))
+    code = ("import sys; sys.path.insert(0, %r); import seq_collection_b200 as fq\n"
+            "with fq.FqGpu(chunk_bytes=(16 << 20) + 4096, flags=fq.F_CORE_ONLY) as c: print(fq.fq_count_row(c.count_file(%r)))\n") % (ROOT, str(path))
+    for threads in ("1", "3", "8"):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env={**os.environ, "FQGPU_READ_THREADS": threads})
+        assert r.returncode == 0, r.stderr
+        assert r.stdout.strip() == want, threads
