@@ -6,11 +6,12 @@
 // gzip members of at most 64 KiB, each with its compressed size in the header's "BC" extra field and its
 // uncompressed size in the trailer, so every member is an independent DEFLATE stream with a known output
 // offset: the host only walks the member headers, the compressed bytes go to the GPU as they are, and ONE WARP
-// PER MEMBER (lane 0 decodes: a DEFLATE stream is serial, and 32 members sharing a warp would run one after the
-// other -- measured 1.01 active threads per instruction -- so each member gets its own warp and the machine hides
-// the latency of ~10 k such warps behind each other) inflates its stream (RFC 1951: stored, fixed and dynamic
-// Huffman blocks; canonical-code decoding without lookup tables, the code lengths kept in local memory) straight to
-// its place in the output buffer, which fqgpu_scan_device then scans like any HBM-resident input.  Anything that is not well-formed BGZF makes the caller fall back to the zlib path.
+// PER MEMBER inflates its stream (RFC 1951: stored, fixed and dynamic Huffman blocks) straight to its place in the
+// output buffer.  A DEFLATE stream is serial, and 32 members sharing a warp run one after the other (measured
+// 1.01 active threads per instruction), so each member gets its own warp; all 32 lanes decode the same bits in
+// lockstep (broadcast loads, no divergence: 32 identical lanes cost what one costs), which leaves the warp free for
+// the parallel parts -- filling the per-warp lookup tables in shared memory (10-bit literal/length, 8-bit distance;
+// longer codes walk the canonical code), copying matches 32 bytes per step, the CRC.  The output buffer, which fqgpu_scan_device then scans like any HBM-resident input.  Anything that is not well-formed BGZF makes the caller fall back to the zlib path.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -18,47 +19,96 @@
 
 namespace fq {
 
-static __device__ const uint16_t kLenBase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59,
-                                                 67, 83, 99, 115, 131, 163, 195, 227, 258};
-static __device__ const uint8_t kLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
-static __device__ const uint16_t kDistBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769,
-                                                  1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
-static __device__ const uint8_t kDistExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
-static __device__ const uint8_t kClOrder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+static __constant__ uint16_t kLenBase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59,
+                                              67, 83, 99, 115, 131, 163, 195, 227, 258};
+static __constant__ uint8_t kLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+static __constant__ uint16_t kDistBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769,
+                                               1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+static __constant__ uint8_t kDistExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+static __constant__ uint8_t kClOrder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
-// LSB-first bit reader over [p, end).  cnt goes negative when the stream is read past its end (checked by the callers).
+constexpr int BGZF_WARPS = 4;         // members per CTA
+constexpr uint32_t CRC_SLICE = 2048;  // bytes per lane in the CRC pass (32 slices cover a 64 KiB member)
+constexpr int LBITS = 10;             // literal/length codes up to this length decode with one table lookup
+constexpr int DBITS = 8;              // distance codes
+
+// Per-warp decoding state in shared memory.  Every lane of the warp runs the same decode on the same bits (the
+// loads are broadcasts, there is no divergence, so 32 identical lanes cost what one costs) -- which makes the warp
+// available, without any hand-over, for the parts that are parallel: filling the lookup tables, copying matches,
+// the CRC.
+struct WarpTables {
+  uint16_t lit[1 << LBITS];   // symbol << 4 | code length; 0 = longer than LBITS (canonical walk)
+  uint16_t dist[1 << DBITS];
+  uint16_t lcount[16], lsym[288], dcount[16], dsym[32];
+  uint8_t lens[320];
+};
+
+// LSB-first bit reader over aligned 32-bit words.  Reads at most into the member's own 8-byte trailer; beyond it
+// the stream continues as zeros, so a truncated or corrupt stream stays inside the batch buffer and ends in a
+// decoder error, a size mismatch or a CRC mismatch.
 struct Bits {
-  const uint8_t* p;
-  const uint8_t* end;
+  const uint32_t* w;
+  const uint32_t* wend;
   unsigned long long buf;
   int cnt;
-  __device__ __forceinline__ void refill() {
-    while (cnt <= 56 && p < end) { buf |= (unsigned long long)__ldg(p++) << cnt; cnt += 8; }
+  __device__ __forceinline__ void init(const uint8_t* p, uint32_t nbytes) {
+    const uint32_t mis = (uint32_t)((uintptr_t)p & 3u);
+    w = reinterpret_cast<const uint32_t*>(p - mis);
+    wend = reinterpret_cast<const uint32_t*>(p + ((nbytes + 8u) & ~3u));
+    buf = (unsigned long long)(__ldg(w++) >> (8u * mis));
+    cnt = 32 - 8 * (int)mis;
   }
-  __device__ __forceinline__ uint32_t take(int n) {  // n <= 16; call refill() first
+  __device__ __forceinline__ void refill() {  // afterwards cnt >= 33
+    if (cnt <= 32) { buf |= (unsigned long long)(w < wend ? __ldg(w) : 0u) << cnt; w++; cnt += 32; }
+  }
+  __device__ __forceinline__ uint32_t take(int n) {  // n <= 16
     const uint32_t v = (uint32_t)buf & ((1u << n) - 1u);
     buf >>= n; cnt -= n;
     return v;
   }
 };
 
-// Canonical Huffman code from code lengths: count[l] = codes of length l, symbol[] = symbols ordered by code.
-// Returns < 0 for an over-subscribed set of lengths, > 0 for an incomplete one, 0 for a complete one.
-__device__ int huff_build(uint16_t* count, uint16_t* symbol, const uint8_t* len, int n) {
+// Canonical Huffman code from code lengths (all lanes run it; the stores are the same values to the same places):
+// count[l] = codes of length l, symbol[] = symbols ordered by code; and the lookup table `tab` of 2^bits entries
+// (filled by the 32 lanes together).  Returns < 0 for an over-subscribed set of lengths, > 0 for an incomplete one.
+__device__ int huff_build(uint16_t* count, uint16_t* symbol, uint16_t* tab, int bits, const uint8_t* len, int n, int lane) {
   for (int l = 0; l <= 15; l++) count[l] = 0;
-  for (int s = 0; s < n; s++) count[len[s]]++;
+  __syncwarp();
+  if (lane == 0) for (int s = 0; s < n; s++) count[len[s]]++;
+  __syncwarp();
+  for (int k = lane; k < (1 << bits); k += 32) tab[k] = 0;
   if (count[0] == n) return 0;
   int left = 1;
-  for (int l = 1; l <= 15; l++) { left <<= 1; left -= count[l]; if (left < 0) return left; }
+  uint32_t next[16];  // first code of every length
+  uint32_t code = 0;
+  next[0] = 0;
+  for (int l = 1; l <= 15; l++) {
+    left <<= 1; left -= count[l];
+    if (left < 0) return left;
+    code = (code + (l > 1 ? count[l - 1] : 0)) << 1;
+    next[l] = code;
+  }
   uint16_t offs[16];
   offs[1] = 0;
   for (int l = 1; l < 15; l++) offs[l + 1] = offs[l] + count[l];
-  for (int s = 0; s < n; s++) if (len[s]) symbol[offs[len[s]]++] = (uint16_t)s;
+  __syncwarp();
+  for (int s = 0; s < n; s++) {
+    const int l = len[s];
+    if (!l) continue;
+    if (lane == 0) symbol[offs[l]] = (uint16_t)s;
+    offs[l]++;
+    const uint32_t c = next[l]++;
+    if (l <= bits) {  // every table slot whose low l bits are the reversed code
+      const uint32_t r = __brev(c) >> (32 - l);
+      const uint16_t e = (uint16_t)((s << 4) | l);
+      for (uint32_t k = r + ((uint32_t)lane << l); k < (1u << bits); k += 32u << l) tab[k] = e;
+    }
+  }
+  __syncwarp();
   return left;
 }
-// Next symbol: walks the code one bit at a time on a copy of the bit buffer.
-__device__ __forceinline__ int huff_decode(Bits& b, const uint16_t* count, const uint16_t* symbol) {
-  b.refill();
+// Codes longer than the table: walk the canonical code one bit at a time.
+__device__ __noinline__ int huff_walk(Bits& b, const uint16_t* count, const uint16_t* symbol) {
   unsigned long long bb = b.buf;
   int code = 0, first = 0, index = 0;
   for (int l = 1; l <= 15; l++) {
@@ -71,19 +121,24 @@ __device__ __forceinline__ int huff_decode(Bits& b, const uint16_t* count, const
   }
   return -1;
 }
+__device__ __forceinline__ int huff_decode(Bits& b, const uint16_t* tab, int bits, const uint16_t* count, const uint16_t* symbol) {
+  b.refill();
+  const uint32_t e = tab[(uint32_t)b.buf & ((1u << bits) - 1u)];
+  const int l = (int)(e & 15u);
+  if (l) { b.buf >>= l; b.cnt -= l; return (int)(e >> 4); }
+  return huff_walk(b, count, symbol);
+}
 
 enum { BGZF_OK = 0, BGZF_EBLOCK = 1, BGZF_ECODE = 2, BGZF_EDIST = 3, BGZF_ESIZE = 4, BGZF_ETRUNC = 5, BGZF_ECRC = 6 };
 
-// The serial part: one thread inflates member d.  Returns BGZF_*.
-__device__ __noinline__ int bgzf_inflate_member(const uint8_t* __restrict__ comp, const BgzfMember& d, uint8_t* out) {
+// Inflates member d (all 32 lanes in lockstep).  Returns BGZF_*.
+__device__ __noinline__ int bgzf_inflate_member(const uint8_t* __restrict__ comp, const BgzfMember& d, uint8_t* out, WarpTables& t, int lane) {
   Bits b;
-  b.p = comp + d.in_off; b.end = b.p + d.in_len; b.buf = 0; b.cnt = 0;
+  b.init(comp + d.in_off, d.in_len);
   uint8_t* o = out + d.out_off;
   const uint32_t cap = d.out_len;
   uint32_t produced = 0;
-  uint16_t lcount[16], lsym[288], dcount[16], dsym[32];
-  uint8_t lens[320];
-  int err = BGZF_OK, last = 0;
+  int last = 0;
   do {
     b.refill();
     last = (int)b.take(1);
@@ -91,81 +146,94 @@ __device__ __noinline__ int bgzf_inflate_member(const uint8_t* __restrict__ comp
     if (type == 0) {  // stored
       b.take(b.cnt & 7);
       b.refill();
-      const uint32_t len = b.take(16), nlen = b.take(16);
-      if (b.cnt < 0 || (len ^ 0xFFFFu) != nlen) { err = BGZF_EBLOCK; break; }
-      if (produced + len > cap) { err = BGZF_ESIZE; break; }
-      for (uint32_t k = 0; k < len; k++) { b.refill(); o[produced++] = (uint8_t)b.take(8); }
-      if (b.cnt < 0) { err = BGZF_ETRUNC; break; }
+      const uint32_t len = b.take(16);
+      b.refill();
+      const uint32_t nlen = b.take(16);
+      if ((len ^ 0xFFFFu) != nlen) return BGZF_EBLOCK;
+      if (produced + len > cap) return BGZF_ESIZE;
+      for (uint32_t k = 0; k < len; k++) { b.refill(); const uint32_t v = b.take(8); if (lane == 0) o[produced + k] = (uint8_t)v; }
+      produced += len;
       continue;
     }
-    if (type == 3) { err = BGZF_EBLOCK; break; }
+    if (type == 3) return BGZF_EBLOCK;
+    __syncwarp();
     if (type == 1) {  // fixed codes
-      for (int s = 0; s < 144; s++) lens[s] = 8;
-      for (int s = 144; s < 256; s++) lens[s] = 9;
-      for (int s = 256; s < 280; s++) lens[s] = 7;
-      for (int s = 280; s < 288; s++) lens[s] = 8;
-      huff_build(lcount, lsym, lens, 288);
-      for (int s = 0; s < 30; s++) lens[s] = 5;
-      huff_build(dcount, dsym, lens, 30);
+      for (int s = lane; s < 288; s += 32) t.lens[s] = s < 144 ? 8 : (s < 256 ? 9 : (s < 280 ? 7 : 8));
+      __syncwarp();
+      huff_build(t.lcount, t.lsym, t.lit, LBITS, t.lens, 288, lane);
+      for (int s = lane; s < 30; s += 32) t.lens[s] = 5;
+      __syncwarp();
+      huff_build(t.dcount, t.dsym, t.dist, DBITS, t.lens, 30, lane);
     } else {  // dynamic codes
       b.refill();
       const int nlen = (int)b.take(5) + 257, ndist = (int)b.take(5) + 1, ncode = (int)b.take(4) + 4;
-      if (nlen > 286 || ndist > 30) { err = BGZF_ECODE; break; }
-      for (int k = 0; k < 19; k++) lens[k] = 0;
-      for (int k = 0; k < ncode; k++) { b.refill(); lens[kClOrder[k]] = (uint8_t)b.take(3); }
-      if (huff_build(lcount, lsym, lens, 19) != 0) { err = BGZF_ECODE; break; }  // the code-length code must be complete
+      if (nlen > 286 || ndist > 30) return BGZF_ECODE;
+      for (int k = lane; k < 19; k += 32) t.lens[k] = 0;
+      __syncwarp();
+      for (int k = 0; k < ncode; k++) { b.refill(); const uint32_t v = b.take(3); if (lane == 0) t.lens[kClOrder[k]] = (uint8_t)v; }
+      __syncwarp();
+      // the code-length code (19 symbols, at most 7 bits) goes through the distance table's slots
+      if (huff_build(t.dcount, t.dsym, t.dist, 7, t.lens, 19, lane) != 0) return BGZF_ECODE;
       int idx = 0;
-      while (idx < nlen + ndist && !err) {
-        int sym = huff_decode(b, lcount, lsym);
-        if (sym < 0 || b.cnt < 0) { err = BGZF_ECODE; break; }
-        if (sym < 16) { lens[idx++] = (uint8_t)sym; continue; }
+      while (idx < nlen + ndist) {
+        const int sym = huff_decode(b, t.dist, 7, t.dcount, t.dsym);
+        if (sym < 0) return BGZF_ECODE;
+        if (sym < 16) { if (lane == 0) t.lens[idx] = (uint8_t)sym; idx++; continue; }
         int prev = 0, rep;
         b.refill();
-        if (sym == 16) { if (idx == 0) { err = BGZF_ECODE; break; } prev = lens[idx - 1]; rep = 3 + (int)b.take(2); }
+        __syncwarp();
+        if (sym == 16) { if (idx == 0) return BGZF_ECODE; prev = t.lens[idx - 1]; rep = 3 + (int)b.take(2); }
         else if (sym == 17) rep = 3 + (int)b.take(3);
         else rep = 11 + (int)b.take(7);
-        if (idx + rep > nlen + ndist) { err = BGZF_ECODE; break; }
-        while (rep--) lens[idx++] = (uint8_t)prev;
+        if (idx + rep > nlen + ndist) return BGZF_ECODE;
+        if (lane == 0) for (int k = 0; k < rep; k++) t.lens[idx + k] = (uint8_t)prev;
+        idx += rep;
+        __syncwarp();
       }
-      if (err) break;
-      if (lens[256] == 0) { err = BGZF_ECODE; break; }
-      // (the distance lengths follow the literal/length lengths in lens[]; build the distance code first: the
-      //  literal/length build overwrites nothing it needs)
-      if (huff_build(dcount, dsym, lens + nlen, ndist) < 0) { err = BGZF_ECODE; break; }
-      if (huff_build(lcount, lsym, lens, nlen) < 0) { err = BGZF_ECODE; break; }
+      __syncwarp();
+      if (t.lens[256] == 0) return BGZF_ECODE;
+      if (huff_build(t.dcount, t.dsym, t.dist, DBITS, t.lens + nlen, ndist, lane) < 0) return BGZF_ECODE;
+      if (huff_build(t.lcount, t.lsym, t.lit, LBITS, t.lens, nlen, lane) < 0) return BGZF_ECODE;
     }
     for (;;) {  // literals and matches of this DEFLATE block
-      int sym = huff_decode(b, lcount, lsym);
-      if (sym < 0 || b.cnt < 0) { err = BGZF_ECODE; break; }
+      int sym = huff_decode(b, t.lit, LBITS, t.lcount, t.lsym);
+      if (sym < 0) return BGZF_ECODE;
       if (sym < 256) {
-        if (produced >= cap) { err = BGZF_ESIZE; break; }
-        o[produced++] = (uint8_t)sym;
+        if (produced >= cap) return BGZF_ESIZE;
+        if (lane == 0) o[produced] = (uint8_t)sym;
+        produced++;
       } else if (sym == 256) {
         break;
       } else {
         sym -= 257;
-        if (sym >= 29) { err = BGZF_ECODE; break; }
-        b.refill();
-        const uint32_t len = kLenBase[sym] + b.take(kLenExtra[sym]);
-        const int ds = huff_decode(b, dcount, dsym);
-        if (ds < 0 || ds >= 30 || b.cnt < 0) { err = BGZF_EDIST; break; }
-        b.refill();
+        if (sym >= 29) return BGZF_ECODE;
+        const uint32_t len = kLenBase[sym] + b.take(kLenExtra[sym]);  // (>= 33 bits were there: 15 + 5 used)
+        const int ds = huff_decode(b, t.dist, DBITS, t.dcount, t.dsym);
+        if (ds < 0 || ds >= 30) return BGZF_EDIST;
         const uint32_t dist = kDistBase[ds] + b.take(kDistExtra[ds]);
-        if (dist > produced) { err = BGZF_EDIST; break; }
-        if (produced + len > cap) { err = BGZF_ESIZE; break; }
-        const uint8_t* src = o + produced - dist;
-        for (uint32_t k = 0; k < len; k++) o[produced + k] = src[k];
+        if (dist > produced) return BGZF_EDIST;
+        if (produced + len > cap) return BGZF_ESIZE;
+        uint8_t* dst = o + produced;
+        const uint8_t* src = dst - dist;
+        __syncwarp();  // earlier bytes (lane 0's literals, other lanes' match bytes) are visible to every lane
+        if (dist >= len) {
+          for (uint32_t k = (uint32_t)lane; k < len; k += 32u) dst[k] = src[k];
+        } else if (dist >= 32u) {  // overlapping, period >= one round: rounds read what earlier rounds wrote
+          for (uint32_t k0 = 0; k0 < len; k0 += 32u) {
+            const uint32_t k = k0 + (uint32_t)lane;
+            if (k < len) dst[k] = src[k];
+            __syncwarp();
+          }
+        } else {  // a run with a short period: every byte is one of the dist bytes before it
+          for (uint32_t k = (uint32_t)lane; k < len; k += 32u) dst[k] = src[k % dist];
+        }
         produced += len;
       }
     }
-  } while (!last && !err);
-  if (!err && b.cnt < 0) err = BGZF_ETRUNC;
-  if (!err && produced != cap) err = BGZF_ESIZE;
-  return err;
+  } while (!last);
+  if (produced != cap) return BGZF_ESIZE;
+  return BGZF_OK;
 }
-
-constexpr int BGZF_WARPS = 4;        // members per CTA
-constexpr uint32_t CRC_SLICE = 2048;  // bytes per lane in the CRC pass (32 slices cover a 64 KiB member)
 
 // crc_shift[k] = the CRC register after CRC_SLICE zero bytes when it starts as 1 << k (a linear map over GF(2)).
 struct CrcShift { uint32_t col[32]; };
@@ -178,6 +246,7 @@ __device__ __forceinline__ uint32_t crc_bytes(const uint32_t* tab, const uint8_t
 __global__ void __launch_bounds__(32 * BGZF_WARPS) bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfMember* __restrict__ members,
                                                                        int n, uint8_t* out, uint32_t* __restrict__ status, const CrcShift sh) {
   __shared__ uint32_t tab[256];
+  __shared__ WarpTables tables[BGZF_WARPS];
   for (int t = threadIdx.x; t < 256; t += 32 * BGZF_WARPS) {  // the reflected CRC-32 table (polynomial 0xEDB88320)
     uint32_t c = (uint32_t)t;
     for (int k = 0; k < 8; k++) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
@@ -188,9 +257,8 @@ __global__ void __launch_bounds__(32 * BGZF_WARPS) bgzf_inflate_kernel(const uin
   const int lane = threadIdx.x & 31;
   if (i >= n) return;
   const BgzfMember d = members[i];
-  int err = 0;
-  if (lane == 0) err = bgzf_inflate_member(comp, d, out);
-  err = __shfl_sync(0xffffffffu, err, 0);  // (also orders lane 0's writes before the reads below)
+  int err = bgzf_inflate_member(comp, d, out, tables[threadIdx.x >> 5], lane);
+  __syncwarp();
   if (!err) {
     // CRC-32 of the member's output: the first (len mod 2 KiB) bytes by lane 0 from the all-ones register, then the
     // full slices from zero registers in parallel, folded in order: v = shift(v) ^ raw(slice).

@@ -471,7 +471,7 @@ static int count_bgzf(fqgpu_ctx* ctx, const char* path) {
     cudaFree(ctx->d_comp);
     ctx->h_comp = nullptr; ctx->d_comp = nullptr; ctx->comp_cap = 0;
     CU_B(cudaMallocHost(&ctx->h_comp, want));
-    CU_B(cudaMalloc(&ctx->d_comp, want));
+    CU_B(cudaMalloc(&ctx->d_comp, want + 64));
     ctx->comp_cap = want;
   }
   if (ctx->members_cap < kBgzfBatchMembers) {
