@@ -49,7 +49,7 @@ struct __align__(128) FastSmem {
   uint2 entry[2][32];                    // (newlines of the chunk, bytes after its last newline / valid bytes when none); slots >= F_NW stay 0
   uint32_t first[2][F_NW];               // offset of the chunk's first newline (while the span's head fragment is open)
   u64 len_min[2], len_max[2], pos_over;
-  uint32_t abandon_a;                    // set before the tile barrier (phase A): the span is only counted from here on
+  uint32_t abandon_a[2];                 // set before the tile barrier (phase A, slot = tile parity) and read after it: the span is only counted from there on
   uint32_t abandon_b;                    // set anywhere; read at the end
   uint32_t ksel[8];
 };
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(F_THREADS, 2) fq_scan_fast_kernel(const ScanAr
   if (tid == 0) {
     sm.len_min[0] = sm.len_min[1] = ~0ull;
     sm.len_max[0] = sm.len_max[1] = 0;
-    sm.pos_over = 0; sm.abandon_a = 0; sm.abandon_b = 0;
+    sm.pos_over = 0; sm.abandon_a[0] = sm.abandon_a[1] = 0; sm.abandon_b = 0;
     for (int k = 0; k < 4; k++) { sm.ksel[k] = 0x80u << (8 * k); sm.ksel[4 + k] = 1u << (8 * k); }
   }
   __syncthreads();
@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(F_THREADS, 2) fq_scan_fast_kernel(const ScanAr
   uint32_t L_tile = 0;                               // newlines of the span before the tile
   uint32_t head_len = 0;
   uint32_t qacc = 0, qcount = 0;
+  bool abandoned = false;                            // phase A left the well-formed case (sticky, the same in every warp)
   uint32_t mns = ~0u, mxs = 0, mnq = ~0u, mxq = 0;
   u64 over = 0;
   uint32_t par = 0, ent_s = sm0 + FS_OFF(entry), first_s = sm0 + FS_OFF(first);  // slots of the current tile (toggle per tile)
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(F_THREADS, 2) fq_scan_fast_kernel(const ScanAr
     uint32_t m = nl_mask16_ascii(lo) | (nl_mask16_ascii(hi) << 16);
     if (__any_sync(0xffffffffu, (hib & 0x80808080u) != 0)) {  // the short compare is exact only for bytes < 0x80
       m = nl_mask16(lo) | (nl_mask16(hi) << 16);
-      if (lane == 0) sts32(sm0 + FS_OFF(abandon_a), 1u);
+      if (lane == 0) sts32(sm0 + FS_OFF(abandon_a) + 4u * par, 1u);
     }
     const uint32_t b1 = __ballot_sync(0xffffffffu, m != 0);
     const uint32_t b2 = __ballot_sync(0xffffffffu, (m & (m - 1u)) != 0);
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(F_THREADS, 2) fq_scan_fast_kernel(const ScanAr
       const uint32_t wl = b1 ? 31u - (uint32_t)__clz(b1) : 0u;  // the lane that holds the chunk's last newline writes the entry
       const uint32_t tail = b1 ? nvalid - (32u * (uint32_t)lane + hp + 1u) : nvalid;
       if ((uint32_t)lane == wl) sts64(ent_s + 8u * (uint32_t)warp, Tw, tail);
-      if (Tw != (uint32_t)(__popc(b1) + __popc(b2)) && lane == 0) sts32(sm0 + FS_OFF(abandon_a), 1u);  // three newlines and more in a group
+      if (Tw != (uint32_t)(__popc(b1) + __popc(b2)) && lane == 0) sts32(sm0 + FS_OFF(abandon_a) + 4u * par, 1u);  // three newlines and more in a group
     }
     if (L_tile == 0 && b1) {  // the span's head fragment may end in this chunk
       const uint32_t pf = (uint32_t)__ffs(b1) - 1u;
@@ -264,7 +265,8 @@ __global__ void __launch_bounds__(F_THREADS, 2) fq_scan_fast_kernel(const ScanAr
     const uint32_t open_next = (nz ? __shfl_sync(0xffffffffu, e.y, ja & 31) : open_tile) + rest;
     const bool too_long = (int)open_tile > 0x70000000;
     if (too_long && tid == 0) sts32(sm0 + FS_OFF(abandon_b), 1u);
-    const bool skip = count_only || too_long || lds32(sm0 + FS_OFF(abandon_a)) != 0;
+    abandoned |= lds32(sm0 + FS_OFF(abandon_a) + 4u * par) != 0;  // (this slot is written again two tiles later, after two barriers)
+    const bool skip = count_only || too_long || abandoned;
 
     // the 16-bit halves of the packed per-position table take PT_MAX_LINES quality lines between two flushes
     const uint32_t qneed = (Ttot >> 2) + 2u;
@@ -369,6 +371,6 @@ __global__ void __launch_bounds__(F_THREADS, 2) fq_scan_fast_kernel(const ScanAr
     if (sm.len_max[0] > block[OFF_SEQ_LEN_MAX]) block[OFF_SEQ_LEN_MAX] = sm.len_max[0];
     if (sm.len_min[1] < block[OFF_QUAL_LEN_MIN]) block[OFF_QUAL_LEN_MIN] = sm.len_min[1];
     if (sm.len_max[1] > block[OFF_QUAL_LEN_MAX]) block[OFF_QUAL_LEN_MAX] = sm.len_max[1];
-    if (sm.abandon_a | sm.abandon_b) desc.pad = 1;
+    if (abandoned || sm.abandon_b) desc.pad = 1;
   }
 }
