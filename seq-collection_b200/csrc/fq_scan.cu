@@ -490,6 +490,9 @@ __device__ __forceinline__ uint32_t part_slots(Smem& sm, const Sel& k, uint32_t 
   return junk;
 }
 
+// CORE: FQGPU_F_CORE_ONLY (sequence lines only).  A template parameter, not a runtime flag: the kernel is sensitive to
+// code size, and each instantiation drops the other mode's code.
+template <bool CORE>
 __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, const int pass) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
@@ -632,7 +635,7 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
             const int lx = bw4.w ? 3 : (bw4.z ? 2 : (bw4.y ? 1 : 0));
             sm.last_nl = (tid * WPS + lx) * 32 + 31 - __clz(lw);
           }
-          const bool walker = T > (uint32_t)NL_CAP || sm.hiflag[sb] != 0 || (a.dbg & 2);
+          const bool walker = T > (uint32_t)NL_CAP || sm.hiflag[sb] != 0;
           if (walker) {  // the walker wants the newline count before every bitmap word (scratch: the partial-group slots)
             uint16_t* wb = reinterpret_cast<uint16_t*>(&sm.part[sb][0][0]) + tid * WPS;
             wb[0] = (uint16_t)first; wb[1] = (uint16_t)(first + c0); wb[2] = (uint16_t)(first + c0 + c1); wb[3] = (uint16_t)(first + c0 + c1 + c2);
@@ -652,18 +655,18 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
           {
             const uint32_t ph = (uint32_t)((phase + carry_L) & 3);  // class of the tile's line 0
             // first line of the tile that gets a task: odd class (core-only: class 1), then every 2nd (4th)
-            const int jr0 = a.core ? (int)((1u - ph) & 3u) : ((ph & 1) ? 0 : 1);
+            const int jr0 = CORE ? (int)((1u - ph) & 3u) : ((ph & 1) ? 0 : 1);
             tileT = (int)T;
-            tileR = (walker || count_only) ? 0 : (a.core ? ((int)T + 4 - jr0) >> 2 : ((int)T + 2 - jr0) >> 1);
+            tileR = (walker || count_only) ? 0 : (CORE ? ((int)T + 4 - jr0) >> 2 : ((int)T + 2 - jr0) >> 1);
           }
           if (tid == 0) {
             const u64 Lrel = carry_L, open = carry_open;  // before this tile
             TileMeta& m = sm.meta[sb];
             const uint32_t ph = (uint32_t)((phase + Lrel) & 3);
-            const int jr0 = a.core ? (int)((1u - ph) & 3u) : ((ph & 1) ? 0 : 1);
+            const int jr0 = CORE ? (int)((1u - ph) & 3u) : ((ph & 1) ? 0 : 1);
             m.Lrel = Lrel; m.open = open; m.toff = toffB; m.T = (int)T; m.lo = loB; m.hi = hiB;
             m.walker = (walker && !count_only) ? 1 : 0;
-            m.R = (walker || count_only) ? 0 : (a.core ? ((int)T + 4 - jr0) >> 2 : ((int)T + 2 - jr0) >> 1);
+            m.R = (walker || count_only) ? 0 : (CORE ? ((int)T + 4 - jr0) >> 2 : ((int)T + 2 - jr0) >> 1);
             m.first_q = ((ph + (uint32_t)jr0) & 3) == 3;
             m.K = 0; m.nlong = 0;
             sm.bytes_since_flush += (uint32_t)(hiB - loB);
@@ -682,7 +685,7 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
           const int T = m.T;
           // the 16-bit halves of the packed per-position table hold at most PT_MAX_LINES quality lines; tile B's
           // lines are added in the next iteration
-          const uint32_t nqB = a.core ? 0u : (uint32_t)(m.first_q ? (m.R + 1) >> 1 : m.R >> 1);
+          const uint32_t nqB = CORE ? 0u : (uint32_t)(m.first_q ? (m.R + 1) >> 1 : m.R >> 1);
           uint32_t qa = sm.q_acc;
           if (qa + nqB > (uint32_t)PT_MAX_LINES) { post |= 2u; qa = 0; }
           sm.q_acc = qa + nqB;
@@ -707,15 +710,15 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
       // LINE tasks of tile B: one thread per sequence / quality line with bytes in the tile
       // =====================================================================================
       TileMeta& m = sm.meta[sb];
-      const int R = (haveB && !(a.dbg & 8)) ? tileR : 0;
+      const int R = haveB ? tileR : 0;
       // warp 0 issues the TMA and does the serial bookkeeping of thread 0: it takes no line tasks
       if (warp >= 1 && (warp - 1) * 32 < R) {
         const uint8_t* buf = &sm.buf[stB][PAD];
         const int T = tileT, lo = loB, hi = hiB;
         const u64 Lrel = carry_L, open = carry_open;
         const uint32_t ph = (uint32_t)((phase + Lrel) & 3);
-        const int jr0 = a.core ? (int)((1u - ph) & 3u) : ((ph & 1) ? 0 : 1);
-        const int jshift = a.core ? 2 : 1, cshift = a.core ? 0 : 1;  // line of task i, its index within its class
+        const int jr0 = CORE ? (int)((1u - ph) & 3u) : ((ph & 1) ? 0 : 1);
+        const int jshift = CORE ? 2 : 1, cshift = CORE ? 0 : 1;  // line of task i, its index within its class
         for (int base = (warp - 1) * 32; base < R; base += LINE_THREADS - 32) {
           const int i = base + lane;
           uint32_t nd = 0;
@@ -777,10 +780,10 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
       // WORKER warps: byte statistics of tile C from its line records
       // =====================================================================================
       const TileMeta& m = sm.meta[sc];
-      if (haveC && m.R > 0 && !(a.dbg & 4)) {
+      if (haveC && m.R > 0) {
         const uint32_t buf_s = buf0_s + (uint32_t)stC * STAGE_BYTES;
         const int R = m.R, n_a = (R + 1) >> 1, n_b = R >> 1;  // lines of the class of task 0 / of the other class
-        const uint32_t nlq = a.core ? 0u : (uint32_t)(m.first_q ? n_a : n_b), nls = a.core ? (uint32_t)R : (uint32_t)(m.first_q ? n_b : n_a);
+        const uint32_t nlq = CORE ? 0u : (uint32_t)(m.first_q ? n_a : n_b), nls = CORE ? (uint32_t)R : (uint32_t)(m.first_q ? n_b : n_a);
         uint32_t K = m.K;
         K = K == 1u ? 2u : K;
         const uint32_t inv = sm.inv[K], negK16 = 0u - 16u * K;
@@ -1344,7 +1347,8 @@ int scan_threads() { return THREADS; }
 cudaError_t scan_configure() {
   cudaError_t e = cudaFuncSetAttribute(fq_scan_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastSmem));
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(fq_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+  if ((e = cudaFuncSetAttribute(fq_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem))) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(fq_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
 }
 
 cudaError_t launch_reset(u64* committed, int nblocks, Carry* carry, cudaStream_t st) {
@@ -1386,9 +1390,11 @@ cudaError_t launch_scan(const void* ptr, size_t nbytes, SpanDesc* desc, LaunchHd
   // slower than the tile kernel in every mode, so it is not the default.
   const char* scan_env = getenv("FQGPU_SCAN");
   if (scan_env && !strcmp(scan_env, "fast")) fq_scan_fast_kernel<<<a.nspans, F_THREADS, sizeof(FastSmem), st>>>(a);
-  else fq_scan_kernel<<<a.nspans, THREADS, sizeof(Smem), st>>>(a, 0);
+  else if (core_only) fq_scan_kernel<true><<<a.nspans, THREADS, sizeof(Smem), st>>>(a, 0);
+  else fq_scan_kernel<false><<<a.nspans, THREADS, sizeof(Smem), st>>>(a, 0);
   fq_stitch_kernel<<<a.nspans, STITCH_THREADS, 0, st>>>(a);
-  fq_scan_kernel<<<a.nspans, THREADS, sizeof(Smem), st>>>(a, 1);
+  if (core_only) fq_scan_kernel<true><<<a.nspans, THREADS, sizeof(Smem), st>>>(a, 1);
+  else fq_scan_kernel<false><<<a.nspans, THREADS, sizeof(Smem), st>>>(a, 1);
   if (meta_records && (e = cudaStreamWaitEvent(st, ev_join, 0)) != cudaSuccess) return e;
   if (dbg & 16u) {  // diagnostics: spans the stitch kernel sent to the exact second pass
     LaunchHdr h;
