@@ -235,7 +235,7 @@ __device__ __forceinline__ uint32_t nl_extract2(uint32_t m, uint32_t end, uint32
   }
   return m;
 }
-__device__ __forceinline__ void nl_extract_rest(uint32_t m, uint32_t end, uint32_t pos0) {
+__device__ __noinline__ void nl_extract_rest(uint32_t m, uint32_t end, uint32_t pos0) {  // (rare: kept out of the hot code)
   while (m) {
     const uint32_t k = bfind(m);
     end -= 2u;
@@ -270,7 +270,7 @@ __device__ __forceinline__ void account_byte_tab(Smem& sm, int cls, uint32_t b, 
   }
 }
 // A line length through the shared tables (generic paths; the line tasks keep their extrema in registers).
-__device__ __forceinline__ void account_line_len(Smem& sm, int cls, u64 len) {
+__device__ __noinline__ void account_line_len(Smem& sm, int cls, u64 len) {
   const int q = cls == 3;
   const uint32_t bin = len < (u64)POS_BINS ? (uint32_t)len : (uint32_t)POS_BINS;
   if (q) atomicAdd(&sm.qual_len[bin], 1u);
@@ -400,8 +400,36 @@ __device__ __forceinline__ void flush_gpos(S& sm, u64* block, int tid) {
   }
 }
 
+__device__ __noinline__ void flush_pos_tab_cold(Smem& sm, u64* block, int tid) { flush_pos_tab(sm, block, tid); }
+__device__ __noinline__ void flush_gpos_cold(Smem& sm, u64* block, int tid) { flush_gpos(sm, block, tid); }
+
 __device__ __forceinline__ uint32_t part_entry(int g, int lo, int hi, uint32_t q) {
   return (uint32_t)g | ((uint32_t)lo << 10) | ((uint32_t)hi << 14) | ((q < 1023u ? q : 1023u) << 19);
+}
+
+// Rare forms of K1a, kept out of the hot code: this thread's groups again with the exact compare; an edge tile
+// (bytes [lo, hi) valid).
+__device__ __noinline__ void k1a_redo(uint32_t buf_s, uint32_t bm_s, int r, int nthr) {
+  for (int g = r; g < TILE / 16; g += nthr) sts16(bm_s + 2u * (uint32_t)g, nl_mask16(lds128(buf_s + 16u * (uint32_t)g)));
+}
+__device__ __noinline__ uint32_t k1a_edge(Smem& sm, uint32_t buf_s, uint32_t bm_s, int lo, int hi, int r, int nthr) {
+  uint32_t hib = 0;
+  for (int g = r; g < TILE / 16; g += nthr) {
+    const int off = g * 16;
+    uint32_t m = 0;
+    if (off < hi && off + 16 > lo) {
+      const uint4 v = lds128(buf_s + 16u * (uint32_t)g);
+      m = nl_mask16(v);
+      int lo_k = lo - off; lo_k = lo_k < 0 ? 0 : lo_k;
+      int hi_k = hi - off; hi_k = hi_k > 16 ? 16 : hi_k;
+      m &= ((1u << hi_k) - 1u) & ~((1u << lo_k) - 1u);
+      // high bytes only matter inside the valid range (stale shared memory beyond it)
+      const uint4 ml = sm.masks[lo_k], mh = sm.masks[hi_k];
+      hib |= ((v.x & mh.x & ~ml.x) | (v.y & mh.y & ~ml.y)) | ((v.z & mh.z & ~ml.z) | (v.w & mh.w & ~ml.w));
+    }
+    sts16(bm_s + 2u * (uint32_t)g, m);
+  }
+  return hib;
 }
 
 // K1a: newline masks of a tile's 16-byte groups -> bitmap slot (threads r of nthr; bytes [lo, hi) are valid).
@@ -426,25 +454,9 @@ __device__ __forceinline__ uint32_t k1a_tile(Smem& sm, uint32_t buf_s, uint32_t 
       if ((i + 1) * NTHR <= TILE / 16 || r + i * NTHR < TILE / 16)
         sts16(b0 + (uint32_t)(2 * i * NTHR), nl_mask16_ascii(v[i]));
     }
-    if (hib & 0x80808080u) {  // the short compare is exact only for bytes < 0x80: redo this thread's groups
-      for (int g = r; g < TILE / 16; g += nthr) sts16(bm_s + 2u * (uint32_t)g, nl_mask16(lds128(buf_s + 16u * (uint32_t)g)));
-    }
+    if (hib & 0x80808080u) k1a_redo(buf_s, bm_s, r, nthr);  // the short compare is exact only for bytes < 0x80
   } else {
-    for (int g = r; g < TILE / 16; g += nthr) {
-      const int off = g * 16;
-      uint32_t m = 0;
-      if (off < hi && off + 16 > lo) {
-        const uint4 v = lds128(buf_s + 16u * (uint32_t)g);
-        m = nl_mask16(v);
-        int lo_k = lo - off; lo_k = lo_k < 0 ? 0 : lo_k;
-        int hi_k = hi - off; hi_k = hi_k > 16 ? 16 : hi_k;
-        m &= ((1u << hi_k) - 1u) & ~((1u << lo_k) - 1u);
-        // high bytes only matter inside the valid range (stale shared memory beyond it)
-        const uint4 ml = sm.masks[lo_k], mh = sm.masks[hi_k];
-        hib |= ((v.x & mh.x & ~ml.x) | (v.y & mh.y & ~ml.y)) | ((v.z & mh.z & ~ml.z) | (v.w & mh.w & ~ml.w));
-      }
-      sts16(bm_s + 2u * (uint32_t)g, m);
-    }
+    hib = k1a_edge(sm, buf_s, bm_s, lo, hi, r, nthr);
   }
   return hib;
 }
@@ -833,8 +845,8 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a, c
         tile_walker(sm, a, &sm.buf[stC][PAD], sm.meta[sb], phase, sm.bitmap[sb], reinterpret_cast<const uint16_t*>(&sm.part[sb][0][0]),
                     tid, THREADS);
       }
-      if (post & 2u) flush_pos_tab(sm, block, tid);
-      if (post & 4u) { __syncthreads(); flush_gpos(sm, block, tid); }
+      if (post & 2u) flush_pos_tab_cold(sm, block, tid);
+      if (post & 4u) { __syncthreads(); flush_gpos_cold(sm, block, tid); }
       __syncthreads();
     }
   }
