@@ -170,6 +170,75 @@ def run_reference_arm(args):
     return 0
 
 
+def _bgzf_member(chunk: bytes) -> bytes:
+    import struct
+    import zlib
+
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    comp = co.compress(chunk) + co.flush()
+    return (struct.pack("<BBBBIBBH", 0x1F, 0x8B, 8, 4, 0, 0, 0xFF, 6) + b"BC" + struct.pack("<HH", 2, len(comp) + 25)
+            + comp + struct.pack("<II", zlib.crc32(chunk), len(chunk)))
+
+
+def ingest_leg(fq, ctx, buf, nbytes):
+    """Wall-clock GB/s of fqgpu_count_file on files holding a prefix of the benchmark stream; every result is
+    checked against the HBM-resident scan of the same bytes."""
+    import shutil
+    import tempfile
+    from concurrent.futures import ThreadPoolExecutor
+
+    tmp = tempfile.mkdtemp(prefix="fqgpu_bench_")
+    out = {}
+    try:
+        fctx = fq.FqGpu(meta_records=100)
+        # plain file, page cache
+        n_plain = min(nbytes, 4 << 30)
+        n_plain -= n_plain % REC_BYTES
+        want = ctx.count_device(buf.data_ptr(), n_plain)
+        path = os.path.join(tmp, "plain.fq")
+        buf[:n_plain].cpu().numpy().tofile(path)
+        best = 1e9
+        for _ in range(3):
+            t0 = time.perf_counter()
+            st = fctx.count_file(path)
+            best = min(best, time.perf_counter() - t0)
+        assert st.to_dict() == want.to_dict(), "plain file: result differs from the HBM-resident scan"
+        out["plain_file"] = {"value": n_plain / best / 1e9, "unit": "GB/s", "bytes": n_plain,
+                             "note": "uncompressed .fq in the page cache -> pinned ring (multi-threaded reads) -> H2D -> scan; wall clock, best of 3"}
+        os.remove(path)
+        # BGZF: 64 KiB members, zlib level 6 (compressed here by a thread pool; zlib releases the GIL)
+        n_gz = min(nbytes, 360 * 1_000_000)
+        n_gz -= n_gz % REC_BYTES
+        want = ctx.count_device(buf.data_ptr(), n_gz)
+        raw = buf[:n_gz].cpu().numpy().tobytes()
+        with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as pool:
+            parts = list(pool.map(_bgzf_member, [raw[i:i + 65280] for i in range(0, n_gz, 65280)]))
+        path = os.path.join(tmp, "bgzf.fq.gz")
+        with open(path, "wb") as f:
+            for p in parts:
+                f.write(p)
+            f.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+        for name, env in (("bgzf_device_inflate", None), ("bgzf_host_zlib", "1")):
+            if env:
+                os.environ["FQGPU_NO_BGZF"] = env
+            try:
+                best = 1e9
+                for _ in range(2):
+                    t0 = time.perf_counter()
+                    st = fctx.count_file(path)
+                    best = min(best, time.perf_counter() - t0)
+            finally:
+                os.environ.pop("FQGPU_NO_BGZF", None)
+            assert st.to_dict() == want.to_dict(), name + ": result differs from the HBM-resident scan"
+            out[name] = {"value": n_gz / best / 1e9, "unit": "GB/s of uncompressed bytes", "bytes": n_gz,
+                         "members_on_device": fctx.bgzf_members()}
+        out["bgzf_host_zlib"]["note"] = "the same file with FQGPU_NO_BGZF=1: zlib on one host thread, the reference's gzip_stream path"
+        fctx.close()
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -184,6 +253,7 @@ def main():
     ap.add_argument("--ref-sample-mb", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-ingest", action="store_true", help="skip the file-ingest figures (plain file and BGZF through fqgpu_count_file)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "fqgpu" else args.warmup
     args.workload_name = ("synthetic Illumina 2x150 bp uncompressed FASTQ, %d reads, phred+33" % args.records
@@ -391,6 +461,16 @@ def main():
                "sample": f"{used / 1e9:.2f} GB prefix of the same stream; C restatement of the reference loop "
                          "(oracle/fq_oracle.c fqo_ref_fq_count_mem); result equals the GPU's on that prefix"}
 
+    # ---- file ingest beside it (N=1 only): the same bytes as FILES through fqgpu_count_file ----
+    # A plain .fq from the page cache (multi-threaded reads into the pinned ring) and a BGZF .fq.gz (members inflated
+    # on the device, csrc/fq_bgzf.cu) against the same file through host zlib (the reference's gzip_stream path).
+    ingest = None
+    if not args.no_ingest and world == 1 and rank == 0 and args.workload == "illumina":
+        try:
+            ingest = ingest_leg(fq, ctx, buf, nbytes)
+        except Exception as e:  # never lets the extra figures break the contract line
+            ingest = {"error": repr(e)[:200]}
+
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         tr = measured_traffic_ratio()
@@ -421,6 +501,7 @@ def main():
             "e2e": e2e,
             "cpu_baseline": cpu,
             "core_only": core,
+            "ingest": ingest,
         }
         print(json.dumps(line))
     ctx.close()
