@@ -141,6 +141,12 @@ int fqgpu_count_file(fqgpu_ctx* ctx, const char* path, fqgpu_stats* out); /* pla
  * (src/fq_count.nim:31), fq_meta by a case-INsensitive one (src/fq_meta.nim:219). */
 int fqgpu_count_file_as(fqgpu_ctx* ctx, const char* path, int as_gz, fqgpu_stats* out);
 
+/* fq-meta reads only the head of the file: `while not stream.atEnd() and i < sample_n * 4: line = stream.readLine()`
+ * (src/fq_meta.nim:226-248).  Same as fqgpu_count_file_as, but the stream ends with the line that completes
+ * 4 * cfg.meta_records lines (the host counts newlines while it fills the pinned chunk), so the cost is that of the
+ * sampled head, not of the file; every field of `out` describes that head.  meta_records == 0 reads nothing. */
+int fqgpu_meta_file_as(fqgpu_ctx* ctx, const char* path, int as_gz, fqgpu_stats* out);
+
 /* .gz input that is BGZF (blocked gzip: bgzip / htslib and many sequencer pipelines write it; every member is at
  * most 64 KiB and carries its sizes) is not inflated through zlib on the host (gzip_stream.nim:16-17) but on the
  * device, one thread per member, straight into the buffer the scan reads (csrc/fq_bgzf.cu).

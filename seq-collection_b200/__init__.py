@@ -117,6 +117,7 @@ def load_library(path: str | None = None):
         "fqgpu_count_file": (i32, [vp, C.c_char_p, C.POINTER(Stats)]),
         "fqgpu_count_file_as": (i32, [vp, C.c_char_p, i32, C.POINTER(Stats)]),
         "fqgpu_bgzf_members": (C.c_ulonglong, [vp]),
+        "fqgpu_meta_file_as": (i32, [vp, C.c_char_p, i32, C.POINTER(Stats)]),
         "fqgpu_count_files": (i32, [C.POINTER(Config), C.POINTER(C.c_char_p), C.POINTER(i32), i32, i32, C.POINTER(Stats), C.POINTER(i32)]),
         "fqgpu_scan_device": (i32, [vp, vp, sz]),
         "fqgpu_count_device": (i32, [vp, vp, sz, C.POINTER(Stats)]),
@@ -151,7 +152,7 @@ def load_library(path: str | None = None):
 EXPORTED_SYMBOLS = [
     "fqgpu_abi_version", "fqgpu_stats_size", "fqgpu_build_info", "fqgpu_device_count", "fqgpu_create",
     "fqgpu_destroy", "fqgpu_last_error", "fqgpu_acquire", "fqgpu_submit", "fqgpu_finish", "fqgpu_reset",
-    "fqgpu_scan_host", "fqgpu_count_host", "fqgpu_count_file", "fqgpu_count_file_as", "fqgpu_count_files", "fqgpu_bgzf_members", "fqgpu_scan_device", "fqgpu_count_device",
+    "fqgpu_scan_host", "fqgpu_count_host", "fqgpu_count_file", "fqgpu_count_file_as", "fqgpu_count_files", "fqgpu_bgzf_members", "fqgpu_meta_file_as", "fqgpu_scan_device", "fqgpu_count_device",
     "fqgpu_shard_block_words", "fqgpu_shard_begin", "fqgpu_shard_export", "fqgpu_shard_combine",
     "fqgpu_shard_rescan", "fqgpu_shard_combine_host", "fqgpu_last_timing", "fqgpu_stream", "fqgpu_synth_illumina",
     "fqgpu_synth_illumina_bytes", "fqgpu_synth_ont", "fqgpu_index_device", "fqgpu_headers_device", "fqgpu_dedup_device", "fqgpu_dedup_host", "fqgpu_index_lines",
@@ -248,6 +249,13 @@ class FqGpu:
             self._check(self.lib.fqgpu_count_file(self._ctx, os.fsencode(path), C.byref(st)))
         else:
             self._check(self.lib.fqgpu_count_file_as(self._ctx, os.fsencode(path), int(as_gz), C.byref(st)))
+        return st
+
+    def meta_file(self, path: str, as_gz: bool | None = None) -> Stats:
+        """fqgpu_meta_file_as: the head of the file that the fq-meta sampling loop consumes (4 * meta_records lines)."""
+        st = Stats()
+        gz = path.lower().endswith(".gz") if as_gz is None else as_gz  # case-insensitive, src/fq_meta.nim:219
+        self._check(self.lib.fqgpu_meta_file_as(self._ctx, os.fsencode(path), int(gz), C.byref(st)))
         return st
 
     def bgzf_members(self) -> int:
@@ -502,4 +510,4 @@ def fq_meta_quality_fields(st) -> list:
 def fq_meta_quality(fastq: str, sample_n: int = 20) -> list:
     """Quality part of fq_meta* (src/fq_meta.nim:197, default sample_n = 20; the CLI passes 100)."""
     with FqGpu(meta_records=sample_n) as ctx:
-        return fq_meta_quality_fields(ctx.count_file(fastq, as_gz=fastq.lower().endswith(".gz")))
+        return fq_meta_quality_fields(ctx.meta_file(fastq))  # reads the sampled head only, like the reference

@@ -616,6 +616,53 @@ int fqgpu_count_file_as(fqgpu_ctx* ctx, const char* path, int as_gz, fqgpu_stats
   return fqgpu_finish(ctx, out);
 }
 
+// ---- the head of a file: what the fq-meta sampling loop consumes (src/fq_meta.nim:226-248) -----------------
+int fqgpu_meta_file_as(fqgpu_ctx* ctx, const char* path, int as_gz, fqgpu_stats* out) {
+  if (!ctx || !path || !out) return FQGPU_EARG;
+  int rc = fqgpu_reset(ctx);
+  if (rc != FQGPU_OK) return rc;
+  const u64 want_lines = ctx->cfg.meta_records * 4ull;
+  gzFile gf = nullptr;
+  int fd = -1;
+  if (as_gz) {
+    gf = gzopen(path, "rb");
+    if (!gf) return fail(ctx, FQGPU_EIO, std::string("Unable to open file: ") + path);
+  } else {
+    fd = open(path, O_RDONLY);
+    if (fd < 0) return fail(ctx, FQGPU_EIO, std::string("Unable to open file: ") + path);
+  }
+  auto done = [&](int code) { if (gf) gzclose(gf); if (fd >= 0) close(fd); return code; };
+  u64 lines = 0;
+  bool eof = want_lines == 0;
+  while (!eof && lines < want_lines) {
+    size_t cap = 0;
+    uint8_t* chunk = (uint8_t*)fqgpu_acquire(ctx, &cap);
+    if (!chunk) return done(FQGPU_ECUDA);
+    size_t got = 0;
+    while (got < cap && lines < want_lines) {  // small reads: the head is a few KB to MB
+      const size_t piece = cap - got < ((size_t)1 << 20) ? cap - got : ((size_t)1 << 20);
+      long r = gf ? (long)gzread(gf, chunk + got, (unsigned)piece) : (long)read(fd, chunk + got, piece);
+      if (r < 0) return done(fail(ctx, FQGPU_EIO, std::string(gf ? "gzread failed: " : "read failed: ") + path));
+      if (r == 0) { eof = true; break; }
+      const uint8_t* p = chunk + got;
+      const uint8_t* end = p + r;
+      while (p < end && lines < want_lines) {  // the stream ends with the newline that completes the last sampled line
+        const uint8_t* nl = (const uint8_t*)memchr(p, '\n', (size_t)(end - p));
+        if (!nl) { p = end; break; }
+        lines++;
+        p = nl + 1;
+      }
+      got = (size_t)(p - chunk);
+    }
+    if (got) {
+      rc = fqgpu_submit(ctx, chunk, got);
+      if (rc != FQGPU_OK) return done(rc);
+    }
+  }
+  done(0);
+  return fqgpu_finish(ctx, out);
+}
+
 // ---- many files at once (sc.nim:115-116) ------------------------------------------------------------
 int fqgpu_count_files(const fqgpu_config* cfg, const char* const* paths, const int* as_gz, int n, int n_threads,
                       fqgpu_stats* out, int* rc) {

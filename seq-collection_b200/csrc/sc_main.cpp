@@ -305,7 +305,7 @@ static void fq_meta(const string& fastq, long sample_n, bool basename, bool abso
   // ---- quality range: the GPU scan (replaces fq_meta.nim:245-246) ----
   fqgpu_ctx* ctx = context((uint64_t)std::max(0L, sample_n));
   fqgpu_stats st;
-  int rc = fqgpu_count_file_as(ctx, fastq.c_str(), gz, &st);
+  int rc = fqgpu_meta_file_as(ctx, fastq.c_str(), gz, &st);  // only the sampled head is read, like the loop at :226
   if (rc == FQGPU_EIO) quit_error("Unable to open file: " + fastq, 2);
   if (rc != FQGPU_OK) quit_error(fqgpu_last_error(ctx), 1);
   if (st.meta_status == FQGPU_META_EMPTY_QUAL) quit_error("index out of bounds, the container is empty", 1);  // min() of an empty seq

@@ -51,6 +51,7 @@ proc fqgpu_count_file_as*(ctx: FqgpuCtx, path: cstring, as_gz: cint, stats: ptr 
 proc fqgpu_count_files*(cfg: ptr FqgpuConfig, paths: cstringArray, as_gz: ptr cint, n, n_threads: cint,
                         stats: ptr FqgpuStats, rc: ptr cint): cint
 proc fqgpu_bgzf_members*(ctx: FqgpuCtx): culonglong
+proc fqgpu_meta_file_as*(ctx: FqgpuCtx, path: cstring, as_gz: cint, stats: ptr FqgpuStats): cint
 {.pop.}
 
 ## ------------------------------------------------------------------------------------------------
@@ -90,7 +91,7 @@ proc fq_meta_quality_gpu*(fastq: string, as_gz: bool, sample_n: int): tuple[qual
     raise newException(IOError, $fqgpu_last_error(nil))
   defer: fqgpu_destroy(ctx)
   var st: FqgpuStats
-  let rc = fqgpu_count_file_as(ctx, fastq.cstring, as_gz.cint, addr st)
+  let rc = fqgpu_meta_file_as(ctx, fastq.cstring, as_gz.cint, addr st)   # reads the sampled head only, like the loop at :226
   if rc == FQGPU_EIO: raise newException(IOError, "Unable to open file: " & fastq)   # quit_error(..., 2) upstream
   if rc != FQGPU_OK: raise newException(IOError, $fqgpu_last_error(ctx))
   if st.meta_status == 1: raise newException(IndexError, "index out of bounds, the container is empty")

@@ -110,3 +110,29 @@ def test_multithreaded_file_reads_equal_oracle(tmp_path, monkeypatch):
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env={**os.environ, "FQGPU_READ_THREADS": threads})
         assert r.returncode == 0, r.stderr
         assert r.stdout.strip() == want, threads
+
+
+@pytest.mark.parametrize("n", [1, 7, 100, 5000])
+def test_meta_file_reads_only_the_sampled_head(tmp_path, n):
+    """fqgpu_meta_file_as stops where the reference's sampling loop stops (src/fq_meta.nim:226): the quality fields
+    equal the oracle's for the whole file, and the bytes scanned are those of the first 4 n lines."""
+    rng = np.random.default_rng(40 + n)
+    cases = {
+        "lf": corpus.random_fastq(rng, 900, min_len=20, max_len=120),
+        "crlf_open_end": corpus.random_fastq(rng, 900, min_len=20, max_len=120, crlf=True, final_newline=False),
+        "short": corpus.random_fastq(rng, 3, min_len=5, max_len=9, final_newline=False),
+        "empty": b"",
+    }
+    with fq.FqGpu(meta_records=n) as c:
+        for name, data in cases.items():
+            for gz in (False, True):
+                p = tmp_path / (f"{name}_{n}.fq" + (".GZ" if gz else ""))
+                p.write_bytes(gzip.compress(data) if gz else data)
+                st = c.meta_file(str(p))
+                want = O.count(data, n)
+                assert fq.fq_meta_quality_fields(st) == O.fq_meta_quality_fields(want), (name, gz)
+                head = b"".join(data.splitlines(keepends=True)[: 4 * n]) if b"\r\n" not in data else None
+                if head is not None:
+                    assert st.bytes == len(head), (name, gz, st.bytes, len(head))
+                else:
+                    assert st.bytes <= len(data)
