@@ -1,4 +1,5 @@
-// fq_scan_fast.cuh -- pass 0 of the FASTQ scan for well-formed input (included by fq_scan.cu inside namespace fq).
+// fq_scan_fast.cuh -- EXPERIMENTAL pass 0 of the FASTQ scan for well-formed input (included by fq_scan.cu inside
+// namespace fq; selected by FQGPU_SCAN=fast only: measured slower than fq_scan_kernel).
 //
 // Same contract as fq_scan_kernel pass 0 (src/fq_count.nim:38-45 over one span: counter block into `pending`,
 // SpanDesc T / head_len / tail_len), but built for the common case only and ABANDONING the span -- SpanDesc.pad = 1,
@@ -8,13 +9,13 @@
 // of 2 GB and more.  The newline counts (T, head_len, tail_len) are exact on any input, so the stitch kernel's
 // prefix and the exact phases of the rescanned spans do not depend on the abandoned statistics.
 //
-// Layout of the work: no shared-memory tile and no warp roles.  A tile is 16 KiB; warp w owns bytes
+// Layout of the work: no shared-memory tile and no warp roles.  A tile is 12 KiB (12 warps); warp w owns bytes
 // [1024 w, 1024 w + 1024) of it and every lane one aligned 32-byte GROUP, loaded straight from global memory
 // into registers one tile ahead.
 //   phase A  newline mask of the group (SWAR compare + IDP.4A movemask), warp ballots of "has a newline" /
 //            "has two", the chunk's newline count and the bytes after its last newline -> entry[w].
 //   barrier  (the only one per tile)
-//   phase B  every warp folds the 16 entries into its own start (lines before the chunk, bytes of the open
+//   phase B  every warp folds the 12 entries into its own start (lines before the chunk, bytes of the open
 //            line), every lane derives the line class and line position of its group from the two ballots,
 //            and the group goes through the statistics with ONE byte mask: a group holds at most one counted
 //            segment besides the "\n+\n" case -- bytes before the first newline when the class of byte 0 is
