@@ -166,6 +166,16 @@ unsigned long long fqgpu_bgzf_members(const fqgpu_ctx* ctx);
 int fqgpu_count_files(const fqgpu_config* cfg, const char* const* paths, const int* as_gz, int n, int n_threads,
                       fqgpu_stats* out, int* rc);
 
+/* One uncompressed regular file, byte-range sharded over `world` contexts in ONE process (the "file mode" of SURVEY 8e;
+ * the multi-process form is the fqgpu_shard_* protocol below, which this call drives itself).  devices[g] = CUDA
+ * ordinal of shard g (an ordinal may repeat); NULL = round-robin over every visible device, world <= 0 = one shard
+ * per visible device.  Shard g has its own host thread, pinned ring and context, reads bytes [g*N/world, (g+1)*N/world)
+ * of the file, resyncs to the first record start and exports its block; the blocks are gathered in host memory and
+ * combined exactly (fqgpu_shard_combine_host).  Gzip input, pipes, small files and input on which a shard's phase
+ * hypothesis fails (malformed FASTQ) are counted by one context on devices[0] instead, so the result is always
+ * the one fqgpu_count_file_as gives. */
+int fqgpu_count_file_sharded(const fqgpu_config* cfg, const char* path, const int* devices, int world, fqgpu_stats* out);
+
 /* HBM-resident interface (kernel-only measurements; data already on the context's device).
  * scan_device may be called repeatedly: each call continues the same stream of bytes (carry
  * state is kept on the device), exactly as if the buffers were concatenated. */

@@ -118,6 +118,7 @@ def load_library(path: str | None = None):
         "fqgpu_count_file_as": (i32, [vp, C.c_char_p, i32, C.POINTER(Stats)]),
         "fqgpu_bgzf_members": (C.c_ulonglong, [vp]),
         "fqgpu_meta_file_as": (i32, [vp, C.c_char_p, i32, C.POINTER(Stats)]),
+        "fqgpu_count_file_sharded": (i32, [C.POINTER(Config), C.c_char_p, C.POINTER(i32), i32, C.POINTER(Stats)]),
         "fqgpu_count_files": (i32, [C.POINTER(Config), C.POINTER(C.c_char_p), C.POINTER(i32), i32, i32, C.POINTER(Stats), C.POINTER(i32)]),
         "fqgpu_scan_device": (i32, [vp, vp, sz]),
         "fqgpu_count_device": (i32, [vp, vp, sz, C.POINTER(Stats)]),
@@ -152,7 +153,7 @@ def load_library(path: str | None = None):
 EXPORTED_SYMBOLS = [
     "fqgpu_abi_version", "fqgpu_stats_size", "fqgpu_build_info", "fqgpu_device_count", "fqgpu_create",
     "fqgpu_destroy", "fqgpu_last_error", "fqgpu_acquire", "fqgpu_submit", "fqgpu_finish", "fqgpu_reset",
-    "fqgpu_scan_host", "fqgpu_count_host", "fqgpu_count_file", "fqgpu_count_file_as", "fqgpu_count_files", "fqgpu_bgzf_members", "fqgpu_meta_file_as", "fqgpu_scan_device", "fqgpu_count_device",
+    "fqgpu_scan_host", "fqgpu_count_host", "fqgpu_count_file", "fqgpu_count_file_as", "fqgpu_count_files", "fqgpu_bgzf_members", "fqgpu_meta_file_as", "fqgpu_count_file_sharded", "fqgpu_scan_device", "fqgpu_count_device",
     "fqgpu_shard_block_words", "fqgpu_shard_begin", "fqgpu_shard_export", "fqgpu_shard_combine",
     "fqgpu_shard_rescan", "fqgpu_shard_combine_host", "fqgpu_last_timing", "fqgpu_stream", "fqgpu_synth_illumina",
     "fqgpu_synth_illumina_bytes", "fqgpu_synth_ont", "fqgpu_index_device", "fqgpu_headers_device", "fqgpu_dedup_device", "fqgpu_dedup_host", "fqgpu_index_lines",
@@ -429,6 +430,23 @@ def count_files(paths, n_threads: int = 0, device: int = -1, meta_records: int =
     rcs = (C.c_int * max(n, 1))()
     rc = lib.fqgpu_count_files(C.byref(cfg), arr, gz, n, n_threads, out, rcs)
     return rc, [(rcs[i], out[i]) for i in range(n)]
+
+
+def count_file_sharded(path: str, devices=None, world: int = 0, meta_records: int = 0, flags: int = 0, chunk_bytes: int = 0) -> Stats:
+    """fqgpu_count_file_sharded: one plain file, byte-range sharded over several contexts / GPUs in this process
+    (devices = CUDA ordinal per shard, repeats allowed; None = round-robin over all visible devices)."""
+    lib = load_library()
+    cfg = Config(-1, chunk_bytes, 0, meta_records, flags, 0)
+    st = Stats()
+    if devices is not None:
+        world = len(devices)
+        arr = (C.c_int * world)(*devices)
+    else:
+        arr = None
+    rc = lib.fqgpu_count_file_sharded(C.byref(cfg), os.fsencode(path), arr, world, C.byref(st))
+    if rc < 0:
+        raise FqGpuError(rc, lib.fqgpu_last_error(None).decode())
+    return st
 
 
 def fq_count_many(files, basename: bool = False, absolute: bool = False, n_threads: int = 0) -> list:

@@ -411,8 +411,8 @@ static int read_threads() {
   return t;
 }
 
-static size_t parallel_pread(int fd, uint8_t* dst, size_t n, size_t off, bool* io_error) {
-  const int T = read_threads();
+static size_t parallel_pread(int fd, uint8_t* dst, size_t n, size_t off, bool* io_error, int threads = 0) {
+  const int T = threads > 0 ? threads : read_threads();
   std::atomic<bool> bad(false);
   auto slice_read = [&](size_t b, size_t e) {
     size_t g = 0;
@@ -661,6 +661,96 @@ int fqgpu_meta_file_as(fqgpu_ctx* ctx, const char* path, int as_gz, fqgpu_stats*
   }
   done(0);
   return fqgpu_finish(ctx, out);
+}
+
+// ---- one file over several contexts / GPUs in one process (file mode) -------------------------------
+int fqgpu_count_file_sharded(const fqgpu_config* cfg, const char* path, const int* devices, int world, fqgpu_stats* out) {
+  if (!path || !out) return FQGPU_EARG;
+  fqgpu_config base;
+  memset(&base, 0, sizeof base);
+  base.device = -1;
+  if (cfg) base = *cfg;
+  const bool own_chunk = base.chunk_bytes != 0;
+  const int ndev = fqgpu_device_count();
+  if (world <= 0) world = ndev > 0 ? ndev : 1;
+  if (world > 64) world = 64;
+  auto dev_of = [&](int g) { return devices ? devices[g] : (ndev > 0 ? g % ndev : 0); };
+  auto single = [&]() {  // everything the sharded path does not take
+    fqgpu_config c = base;
+    c.device = devices ? devices[0] : (base.device >= 0 ? base.device : -1);
+    fqgpu_ctx* ctx = nullptr;
+    int rc = fqgpu_create(&ctx, &c);
+    if (rc != FQGPU_OK) return rc;
+    rc = fqgpu_count_file(ctx, path, out);
+    if (rc != FQGPU_OK) g_create_error = ctx->err;
+    fqgpu_destroy(ctx);
+    return rc;
+  };
+  const size_t L = strlen(path);
+  const bool gz = L >= 3 && strcmp(path + L - 3, ".gz") == 0;
+  struct stat sb;
+  const int fd = gz ? -1 : open(path, O_RDONLY);
+  if (fd < 0 || fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode) || world == 1 || (size_t)sb.st_size < (size_t)world * ((size_t)4 << 20)) {
+    if (fd >= 0) close(fd);
+    return single();
+  }
+  const size_t N = (size_t)sb.st_size;
+  const size_t bw = fqgpu_shard_block_words();
+  std::vector<uint64_t> blocks((size_t)world * bw, 0);
+  std::vector<int> rcs((size_t)world, FQGPU_OK);
+  std::vector<std::string> msgs((size_t)world);
+  const int rthreads = read_threads() >= 2 * world ? read_threads() / world : 2;  // the reader threads are shared out
+  auto shard = [&](int g) {
+    fqgpu_config c = base;
+    c.device = dev_of(g);
+    if (!own_chunk) c.chunk_bytes = (size_t)16 << 20;  // several rings at once, each created for this call: smaller pinned chunks
+    fqgpu_ctx* ctx = nullptr;
+    int rc = fqgpu_create(&ctx, &c);
+    if (rc != FQGPU_OK) { rcs[(size_t)g] = rc; msgs[(size_t)g] = g_create_error; return; }
+    uint64_t* d_blocks = nullptr;
+    auto finish = [&](int code) {
+      if (code != FQGPU_OK) msgs[(size_t)g] = ctx->err;
+      if (d_blocks) cudaFree(d_blocks);
+      fqgpu_destroy(ctx);
+      rcs[(size_t)g] = code;
+    };
+    if ((rc = fqgpu_shard_begin(ctx, g, world)) != FQGPU_OK) return finish(rc);
+    size_t pos = g ? ((N * (size_t)g / (size_t)world) & ~(size_t)4095) : 0;
+    const size_t end = g + 1 < world ? ((N * (size_t)(g + 1) / (size_t)world) & ~(size_t)4095) : N;
+    while (pos < end) {
+      size_t cap = 0;
+      uint8_t* chunk = (uint8_t*)fqgpu_acquire(ctx, &cap);
+      if (!chunk) return finish(FQGPU_ECUDA);
+      const size_t want = end - pos < cap ? end - pos : cap;
+      bool io_bad = false;
+      const size_t got = parallel_pread(fd, chunk, want, pos, &io_bad, rthreads);
+      if (io_bad || got != want) { ctx->err = std::string("read failed: ") + path; return finish(FQGPU_EIO); }
+      if ((rc = fqgpu_submit(ctx, chunk, got)) != FQGPU_OK) return finish(rc);
+      pos += got;
+    }
+    if (cudaSetDevice(ctx->device) != cudaSuccess || cudaMalloc(&d_blocks, (size_t)world * bw * sizeof(uint64_t)) != cudaSuccess) {
+      ctx->err = "fqgpu_count_file_sharded: cudaMalloc failed";
+      return finish(FQGPU_ECUDA);
+    }
+    cudaMemsetAsync(d_blocks, 0, (size_t)world * bw * sizeof(uint64_t), ctx->stream);
+    if ((rc = fqgpu_shard_export(ctx, d_blocks)) != FQGPU_OK) return finish(rc);
+    if (cudaMemcpyAsync(blocks.data() + (size_t)g * bw, d_blocks + (size_t)g * bw, bw * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                        ctx->stream) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+      ctx->err = "fqgpu_count_file_sharded: copying the shard block failed";
+      return finish(FQGPU_ECUDA);
+    }
+    finish(FQGPU_OK);
+  };
+  std::vector<std::thread> pool;
+  for (int g = 1; g < world; g++) pool.emplace_back(shard, g);
+  shard(0);
+  for (auto& th : pool) th.join();
+  close(fd);
+  for (int g = 0; g < world; g++) if (rcs[(size_t)g] != FQGPU_OK) { g_create_error = msgs[(size_t)g]; return rcs[(size_t)g]; }
+  const int rc = fqgpu_shard_combine_host(world, blocks.data(), base.meta_records, out);
+  if (rc == FQGPU_ERETRY) return single();  // a shard resynced to a wrong phase (malformed input): one exact pass
+  if (rc == FQGPU_OK && (base.flags & FQGPU_F_CORE_ONLY)) fqgpu_zero_quality(out);
+  return rc;
 }
 
 // ---- many files at once (sc.nim:115-116) ------------------------------------------------------------

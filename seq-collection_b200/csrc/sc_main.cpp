@@ -418,7 +418,12 @@ int main(int argc, char** argv) {
       vector<fqgpu_stats> st((size_t)nok + 1);
       vector<int> rcs((size_t)nok + 1, FQGPU_OK);
       const int threads = getenv("FQGPU_THREADS") ? atoi(getenv("FQGPU_THREADS")) : 0;
-      if (nok) fqgpu_count_files(&cfg, paths.data(), nullptr, nok, threads, st.data(), rcs.data());
+      if (nok == 1 && cfg.device == FQGPU_DEVICE_ALL) {  // one file, all GPUs: byte-range shards in this process
+        cfg.device = -1;
+        rcs[0] = fqgpu_count_file_sharded(&cfg, paths[0], nullptr, 0, &st[0]);
+      } else if (nok) {
+        fqgpu_count_files(&cfg, paths.data(), nullptr, nok, threads, st.data(), rcs.data());
+      }
       for (int i = 0; i < nok; i++) {
         if (rcs[i] == FQGPU_ECUDA && i == 0) quit_error(string("GPU unavailable: ") + fqgpu_last_error(nullptr), 1);
         fq_count_row(files[i], rcs[i], st[i], fqgpu_last_error(nullptr), basename, absolute);

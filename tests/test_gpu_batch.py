@@ -136,3 +136,34 @@ def test_meta_file_reads_only_the_sampled_head(tmp_path, n):
                     assert st.bytes == len(head), (name, gz, st.bytes, len(head))
                 else:
                     assert st.bytes <= len(data)
+
+
+def test_count_file_sharded_equals_oracle(tmp_path):
+    """One plain file over several contexts in one process (devices may repeat: runs on a single GPU too); also the
+    inputs that must fall back to a single context (small, .gz, a phase hypothesis that fails)."""
+    import torch
+
+    ndev = torch.cuda.device_count()
+    rng = np.random.default_rng(55)
+    big = corpus.random_fastq(rng, 150_000, min_len=80, max_len=200, final_newline=False)                 # ~47 MB
+    crlf = corpus.random_fastq(rng, 120_000, min_len=50, max_len=150, crlf=True)
+    # quality lines that look like headers and sequence lines that look like '+' lines: resync may guess wrong
+    nasty = b"".join(b"@r%d\n+ACGT%d\n+\n@III%d\n" % (i, i, i) for i in range(700_000))
+    small = corpus.random_fastq(rng, 100)
+    cases = {"big": big, "crlf": crlf, "nasty": nasty, "small": small}
+    for name, data in cases.items():
+        p = tmp_path / (name + ".fq")
+        p.write_bytes(data)
+        want = O.count(data, 100)
+        for devices in ([0, 0], [0, 0, 0], [g % ndev for g in range(5)]):
+            st = fq.count_file_sharded(str(p), devices=devices, meta_records=100, chunk_bytes=8 << 20)
+            assert_equal_stats(st.to_dict(), want, f"{name} devices={devices}")
+    gz = tmp_path / "big.fq.gz"
+    with gzip.open(gz, "wb", compresslevel=1) as f:
+        f.write(big[: 6 << 20])
+    assert_equal_stats(fq.count_file_sharded(str(gz), devices=[0, 0], meta_records=100).to_dict(), O.count(big[: 6 << 20], 100), "gz")
+    st = fq.count_file_sharded(str(tmp_path / "big.fq"), world=0, flags=fq.F_CORE_ONLY)  # one shard per visible device
+    assert fq.fq_count_row(st) == O.fq_count_row(O.count(big, 0))
+    with pytest.raises(fq.FqGpuError) as ei:
+        fq.count_file_sharded("/nonexistent/file.fq", devices=[0, 0])
+    assert ei.value.code == fq.EIO
