@@ -400,14 +400,16 @@ int fqgpu_count_file(fqgpu_ctx* ctx, const char* path, fqgpu_stats* out) {
 // ---- host ingest: a regular file is read by several threads at once -------------------------------------------
 // One thread copies page-cache bytes into pinned memory at a few GB/s, an order of magnitude below what the H2D
 // copy behind it moves; T threads pread() disjoint slices of the same chunk.  FQGPU_READ_THREADS overrides T
-// (default: half the hardware threads, at most 8).  Returns the contiguous bytes read from `off` (short at EOF).
+// (default: three quarters of the hardware threads, at most 16; shared out among the workers of fqgpu_count_files).  Returns the contiguous bytes read from `off` (short at EOF).
+static thread_local int g_read_threads_share = 0;  // > 0: this thread is one of several ingesting at once (count_files)
 static int read_threads() {
   static const int t = [] {
     if (const char* e = getenv("FQGPU_READ_THREADS")) return atoi(e) > 0 ? atoi(e) : 1;
     const unsigned hw = std::thread::hardware_concurrency();
-    const int d = (int)(hw / 2);
-    return d < 1 ? 1 : (d > 8 ? 8 : d);
+    const int d = (int)(hw * 3 / 4);  // measured on a 16-thread host: 4 -> 24, 8 -> 34, 12 -> 43, 16 -> 44, 24 -> 39 GB/s
+    return d < 1 ? 1 : (d > 16 ? 16 : d);
   }();
+  if (g_read_threads_share > 0) return t / g_read_threads_share > 0 ? t / g_read_threads_share : 1;
   return t;
 }
 
@@ -776,6 +778,7 @@ int fqgpu_count_files(const fqgpu_config* cfg, const char* const* paths, const i
   std::mutex mu;
   std::vector<std::string> msgs((size_t)n);  // what fqgpu_last_error(NULL) reports afterwards: the first failure in file order
   auto worker = [&](int t) {
+    g_read_threads_share = nthr;  // the reader threads are shared out among the files in flight
     fqgpu_config c = base;
     if (base.device == FQGPU_DEVICE_ALL) c.device = dev0 + t % ndev;
     fqgpu_ctx* ctx = nullptr;
@@ -792,6 +795,7 @@ int fqgpu_count_files(const fqgpu_config* cfg, const char* const* paths, const i
       if (rc[i] != FQGPU_OK) { std::lock_guard<std::mutex> g(mu); msgs[(size_t)i] = ctx->err; }
     }
     if (ctx) fqgpu_destroy(ctx);
+    g_read_threads_share = 0;
   };
   std::vector<std::thread> pool;
   for (int t = 1; t < nthr; t++) pool.emplace_back(worker, t);
