@@ -81,7 +81,7 @@ def random_fastq(rng: np.random.Generator, n_records: int, min_len=1, max_len=30
     return data
 
 
-def bgzf_bytes(data: bytes, block: int = 65280, level: int = 6, eof: bool = True) -> bytes:
+def bgzf_bytes(data: bytes, block: int = 65280, level: int = 6, eof: bool = True, strategy: int = 0) -> bytes:
     """BGZF (blocked gzip, SAM spec 4.1): one gzip member per `block` input bytes, each with the 'BC' extra field
     holding its compressed size; optionally the 28-byte empty EOF member."""
     import struct
@@ -90,7 +90,7 @@ def bgzf_bytes(data: bytes, block: int = 65280, level: int = 6, eof: bool = True
     out = bytearray()
     for i in range(0, max(len(data), 1), block):
         chunk = data[i:i + block]
-        co = zlib.compressobj(level, zlib.DEFLATED, -15)
+        co = zlib.compressobj(level, zlib.DEFLATED, -15, 9, strategy)
         comp = co.compress(chunk) + co.flush()
         out += struct.pack("<BBBBIBBH", 0x1F, 0x8B, 8, 4, 0, 0, 0xFF, 6) + b"BC" + struct.pack("<HH", 2, len(comp) + 25)
         out += comp + struct.pack("<II", zlib.crc32(chunk), len(chunk))

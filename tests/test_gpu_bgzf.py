@@ -102,3 +102,29 @@ def test_bgzf_many_members_synthetic(ctx, tmp_path):
     assert rc == fq.OK and all(r == fq.OK for r, _ in res)
     for _, s in res:
         assert_equal_stats(s.to_dict(), want, "count_files bgzf")
+
+
+def _inflate_stress_payloads():
+    """Byte streams that reach the corners of the DEFLATE decoder: literal codes longer than the 10-bit table
+    (geometric distribution over 256 byte values), distance codes longer than the 8-bit table and far matches
+    (a 30 KB period), overlapping matches with every short period and with periods >= 32, maximal runs,
+    incompressible noise (stored blocks at any level), and all of it glued together."""
+    rng = np.random.default_rng(77)
+    geo = np.minimum(rng.geometric(0.08, size=200_000) - 1, 255).astype(np.uint8).tobytes()
+    base = rng.integers(0, 256, size=30_000, dtype=np.uint8).tobytes()
+    far = base * 5
+    periods = b"".join((bytes(rng.integers(65, 91, size=p, dtype=np.uint8)) * (700 // p + 2))[:700] for p in list(range(1, 40)) + [47, 63, 64, 65, 129, 257, 300])
+    runs = b"A" * 70_000 + b"\n" + b"#" * 1000 + b"\n"
+    noise = rng.integers(0, 256, size=150_000, dtype=np.uint8).tobytes()
+    text = corpus.random_fastq(rng, 800, min_len=30, max_len=300)
+    return {"geometric": geo, "far_matches": far, "periods": periods, "runs": runs, "noise": noise, "mix": text + geo[:50_000] + far[:70_000] + periods + text}
+
+
+@pytest.mark.parametrize("strategy,level", [(0, 9), (0, 1), (1, 6), (2, 6), (3, 6), (4, 9)])  # default, filtered, huffman-only, rle, fixed
+def test_bgzf_inflate_stress(ctx, tmp_path, strategy, level):
+    for name, data in _inflate_stress_payloads().items():
+        for block in (65280, 9973):
+            path = _write(tmp_path, f"{name}_{strategy}_{level}_{block}.fq.gz", corpus.bgzf_bytes(data, block=block, level=level, strategy=strategy))
+            st = ctx.count_file(path)
+            assert ctx.bgzf_members() >= len(data) // block, f"{name}: the device path was not taken (decoder rejected a valid stream)"
+            assert_equal_stats(st.to_dict(), O.count(data, 100), f"{name} strategy={strategy} level={level} block={block}")
