@@ -78,3 +78,54 @@ def test_fast_synthetic_illumina(fast):
     got = fast.count_device(buf.data_ptr(), n)
     data = bytes(buf[:n].cpu().numpy())
     assert_equal_stats(got.to_dict(), O.count(data, 100), "illumina 64 MiB")
+
+
+def _soup(rng, size):
+    """Random bytes with FASTQ-like structure broken in random ways: the alphabet is heavy with the bytes the scan
+    treats specially ('\\n', '\\r', '@', '+'), plus a few high bytes and NULs."""
+    mode = int(rng.integers(0, 4))
+    if mode == 0:
+        alphabet = np.frombuffer(b"\n\n\r@+ACGTNI#5", dtype=np.uint8)
+        return bytes(rng.choice(alphabet, size=size))
+    data = bytearray(corpus.random_fastq(rng, max(1, size // 160), min_len=1, max_len=300, crlf=bool(rng.integers(0, 2)),
+                                         final_newline=bool(rng.integers(0, 2))))
+    n_mut = int(rng.integers(0, 12)) if mode < 3 else 0
+    for _ in range(n_mut):
+        if not data:
+            break
+        pos = int(rng.integers(0, len(data)))
+        kind = int(rng.integers(0, 5))
+        if kind == 0:
+            data[pos:pos] = b"\n"
+        elif kind == 1:
+            del data[pos:pos + int(rng.integers(1, 40))]
+        elif kind == 2:
+            data[pos] = int(rng.choice([0x80, 0xFF, 0x00, 0x0D, 0x40, 0x2B]))
+        elif kind == 3:
+            data[pos:pos] = b"\r"
+        else:
+            data[pos:pos] = b"\n" * int(rng.integers(2, 6))
+    return bytes(data)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_byte_soup_both_kernels(seed, monkeypatch):
+    """Differential fuzz: default pass 0 and the fast pass 0 against the oracle, whole and split in two scans."""
+    import torch
+
+    rng = np.random.default_rng(1000 + seed)
+    data = _soup(rng, int(rng.integers(1, 400_000)))
+    want = O.count(data, 100)
+    buf = torch.frombuffer(bytearray(data) + bytearray(64), dtype=torch.uint8).cuda()
+    cut = int(rng.integers(0, len(data) + 1))
+    for mode in ("", "fast"):
+        if mode:
+            monkeypatch.setenv("FQGPU_SCAN", mode)
+        else:
+            monkeypatch.delenv("FQGPU_SCAN", raising=False)
+        with fq.FqGpu(meta_records=100) as c:
+            assert_equal_stats(c.count_bytes(data).to_dict(), want, f"seed={seed} mode={mode or 'default'} whole")
+            c.reset()
+            c.scan_device(buf.data_ptr(), cut)
+            c.scan_device(buf.data_ptr() + cut, len(data) - cut)
+            assert_equal_stats(c.finish().to_dict(), want, f"seed={seed} mode={mode or 'default'} cut={cut}")
