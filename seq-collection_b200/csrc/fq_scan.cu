@@ -1364,8 +1364,22 @@ cudaError_t scan_configure() {
 }
 
 cudaError_t launch_reset(u64* committed, int nblocks, Carry* carry, cudaStream_t st) {
-  fq_reset_kernel<<<64, 256, 0, st>>>(committed, nblocks, carry);
+  fq_reset_kernel<<<nblocks > 296 ? 592 : 64, 256, 0, st>>>(committed, nblocks, carry);
   return cudaGetLastError();
+}
+
+// Spans of a launch over `bytes` bytes (incl. the alignment slack in front) with `resident` CTAs resident at once.
+// Large launches get several spans per resident CTA, handed out by the hardware as CTAs finish: of the two CTAs of an
+// SM the one that started first runs ~1.2x faster, so with one span each the slower half
+// finishes late and alone; with shorter spans the tail is one short span (+2 % on 17 GB).  Spans stay >= 2 MiB.
+uint32_t scan_span_count(u64 bytes, int resident) {
+  static const uint32_t waves = getenv("FQGPU_SPAN_WAVES") ? (uint32_t)atoi(getenv("FQGPU_SPAN_WAVES")) : (uint32_t)SPAN_WAVES;
+  const u64 ntiles = (bytes + TILE - 1) / TILE;
+  if (ntiles < (u64)resident) return (uint32_t)ntiles;
+  u64 f = ntiles / ((u64)resident * 128u);
+  f = f < 1 ? 1 : (f > waves ? waves : f);
+  if (f > (u64)SPAN_WAVES) f = SPAN_WAVES;
+  return (uint32_t)((u64)resident * f);
 }
 
 // Scans `nbytes` at `ptr` (any alignment) as the continuation of the stream described by `carry`:
@@ -1382,7 +1396,7 @@ cudaError_t launch_scan(const void* ptr, size_t nbytes, SpanDesc* desc, LaunchHd
   a.base = (const uint8_t*)(addr - a.lo0);
   a.end = (u64)a.lo0 + nbytes;
   a.ntiles = (uint32_t)((a.end + TILE - 1) / TILE);
-  uint32_t nspans = a.ntiles < (uint32_t)max_spans ? a.ntiles : (uint32_t)max_spans;
+  const uint32_t nspans = scan_span_count((u64)a.lo0 + nbytes, max_spans);
   a.tps = (a.ntiles + nspans - 1) / nspans;
   a.nspans = (a.ntiles + a.tps - 1) / a.tps;
   a.desc = desc; a.hdr = hdr; a.carry = carry; a.pending = pending; a.committed = committed; a.shard = shard; a.dbg = dbg; a.core = core_only ? 1u : 0u;

@@ -177,7 +177,7 @@ int fqgpu_shard_export(fqgpu_ctx* ctx, uint64_t* d_blocks) {
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   cudaEvent_t e0 = fqgpu_get_event(ctx), e1 = fqgpu_get_event(ctx);
   CU_TRY(ctx, cudaEventRecord(e0, ctx->stream));
-  CU_TRY(ctx, launch_reduce(ctx->d_committed, MAX_SPANS, ctx->d_out, ctx->stream));
+  CU_TRY(ctx, launch_reduce(ctx->d_committed, ctx->span_hwm, ctx->d_out, ctx->stream));
   u64* slot = (u64*)d_blocks + (size_t)ctx->shard_rank * kShardWords;
   fq_shard_pack_kernel<<<(BLOCK_WORDS + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_out, ctx->d_carry, ctx->d_shard,
                                                                            ctx->shard_exact ? 1 : 0, slot);
@@ -231,7 +231,7 @@ int fqgpu_shard_rescan(fqgpu_ctx* ctx, const uint64_t* d_blocks) {
   // known exactly up to the first wrong shard, so one shard is repaired per round
   if (g != bad) return FQGPU_OK;
   const Chain c = before[g];
-  CU_TRY(ctx, launch_reset(ctx->d_committed, MAX_SPANS, ctx->d_carry, ctx->stream));
+  CU_TRY(ctx, launch_reset(ctx->d_committed, ctx->span_hwm, ctx->d_carry, ctx->stream));
   fq_shard_begin_kernel<<<(POS_BINS + 256) / 256, 256, 0, ctx->stream>>>(ctx->d_carry, ctx->d_shard, 0);
   fq_shard_set_carry_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_carry, c.lines, c.open, c.bytes, c.last_byte);
   CU_TRY(ctx, cudaGetLastError());

@@ -105,7 +105,7 @@ int fqgpu_create(fqgpu_ctx** out, const fqgpu_config* cfg) {
   CU_NEW(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   CU_NEW(fq::scan_configure());
   ctx->grid = prop.multiProcessorCount * 2;
-  if (ctx->grid > fq::MAX_SPANS) ctx->grid = fq::MAX_SPANS;
+  if (ctx->grid > fq::BASE_SPANS) ctx->grid = fq::BASE_SPANS;
   CU_NEW(cudaMalloc(&ctx->d_pending, (size_t)fq::MAX_SPANS * fq::BLOCK_WORDS * sizeof(u64)));
   CU_NEW(cudaMalloc(&ctx->d_committed, (size_t)fq::MAX_SPANS * fq::BLOCK_WORDS * sizeof(u64)));
   CU_NEW(cudaMalloc(&ctx->d_carry, sizeof(fq::Carry)));
@@ -118,7 +118,9 @@ int fqgpu_create(fqgpu_ctx** out, const fqgpu_config* cfg) {
   ctx->ring.resize(nbuf);  // pinned chunks are allocated lazily by the first acquire()
 #undef CU_NEW
   *out = ctx;
+  ctx->span_hwm = fq::MAX_SPANS;  // the first reset initialises every block; later ones only those that were used
   int rc = fqgpu_reset(ctx);
+  ctx->span_hwm = fq::BASE_SPANS;
   if (rc != FQGPU_OK) { g_create_error = ctx->err; fqgpu_destroy(ctx); *out = nullptr; return rc; }
   return FQGPU_OK;
 }
@@ -126,7 +128,7 @@ int fqgpu_create(fqgpu_ctx** out, const fqgpu_config* cfg) {
 int fqgpu_reset(fqgpu_ctx* ctx) {
   if (!ctx) return FQGPU_EARG;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
-  CU_TRY(ctx, fq::launch_reset(ctx->d_committed, fq::MAX_SPANS, ctx->d_carry, ctx->stream));
+  CU_TRY(ctx, fq::launch_reset(ctx->d_committed, ctx->span_hwm, ctx->d_carry, ctx->stream));
   for (auto& p : ctx->timed) { ctx->event_pool.push_back(p.first); ctx->event_pool.push_back(p.second); }
   ctx->timed.clear();
   ctx->kernel_ms_done = 0.0;
@@ -159,6 +161,8 @@ int fqgpu_scan_device(fqgpu_ctx* ctx, const void* dptr, size_t nbytes) {
   size_t left = nbytes;
   while (left) {
     size_t n = left < kMaxLaunchBytes ? left : kMaxLaunchBytes;
+    const int spans = (int)fq::scan_span_count((u64)((uintptr_t)p & 15) + n, ctx->grid);
+    if (spans > ctx->span_hwm) ctx->span_hwm = spans;
     CU_TRY(ctx, fq::launch_scan(p, n, ctx->d_desc, ctx->d_hdr, ctx->d_carry, ctx->d_pending, ctx->d_committed,
                                 ctx->d_shard, ctx->grid, ctx->shard_rank > 0 ? 0 : ctx->cfg.meta_records, ctx->stream,
                                 ctx->mstream, ctx->ev_fork, ctx->ev_join, (ctx->cfg.flags & FQGPU_F_CORE_ONLY) != 0));
@@ -278,7 +282,7 @@ int fqgpu_finish(fqgpu_ctx* ctx, fqgpu_stats* out) {
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   cudaEvent_t e0 = fqgpu_get_event(ctx), e1 = fqgpu_get_event(ctx);
   CU_TRY(ctx, cudaEventRecord(e0, ctx->stream));
-  CU_TRY(ctx, fq::launch_reduce(ctx->d_committed, fq::MAX_SPANS, ctx->d_out, ctx->stream));
+  CU_TRY(ctx, fq::launch_reduce(ctx->d_committed, ctx->span_hwm, ctx->d_out, ctx->stream));
   CU_TRY(ctx, cudaEventRecord(e1, ctx->stream));
   ctx->timed.emplace_back(e0, e1);
   CU_TRY(ctx, cudaMemcpyAsync(ctx->h_out, ctx->d_out, fq::BLOCK_WORDS * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));

@@ -19,6 +19,7 @@ cudaError_t launch_scan(const void* ptr, size_t nbytes, SpanDesc* desc, LaunchHd
                         u64* pending, u64* committed, ShardInfo* shard, int max_spans, u64 meta_records, cudaStream_t st,
                         cudaStream_t meta_stream, cudaEvent_t ev_fork, cudaEvent_t ev_join, bool core_only);
 cudaError_t launch_reduce(const u64* blocks, int nblocks, u64* out, cudaStream_t st);
+uint32_t scan_span_count(u64 bytes, int resident);
 cudaError_t launch_synth_illumina(void* dptr, u64 first_byte, u64 nbytes, u64 seed, cudaStream_t st);
 cudaError_t synth_ont(void* dptr, size_t capacity, u64 first_record, u64 n_records, u64 seed, size_t* bytes_written,
                       cudaStream_t st);
@@ -27,7 +28,7 @@ cudaError_t synth_ont(void* dptr, size_t capacity, u64 first_record, u64 n_recor
 using fq::u64;
 
 // one launch = up to MAX_SPANS spans; a span stays below 2 GiB so its 32-bit shared-memory counters are exact
-static const size_t kMaxLaunchBytes = (size_t)fq::MAX_SPANS * ((size_t)2 << 30) - ((size_t)64 << 20);
+static const size_t kMaxLaunchBytes = (size_t)fq::BASE_SPANS * ((size_t)2 << 30) - ((size_t)64 << 20);
 inline thread_local std::string g_create_error;
 
 struct StageBuf {
@@ -43,6 +44,7 @@ struct fqgpu_ctx {
   cudaStream_t mstream = nullptr;                  // the fq-meta prefix kernel runs beside the scan
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int grid = 0;
+  int span_hwm = fq::BASE_SPANS;  // most span blocks any launch of this context has used: reset / reduce cover [0, span_hwm)
   u64* d_pending = nullptr;    // [MAX_SPANS] blocks of the launch in flight
   u64* d_committed = nullptr;  // [MAX_SPANS] blocks accumulated since the last reset
   fq::Carry* d_carry = nullptr;
