@@ -1371,12 +1371,13 @@ cudaError_t launch_reset(u64* committed, int nblocks, Carry* carry, cudaStream_t
 // Spans of a launch over `bytes` bytes (incl. the alignment slack in front) with `resident` CTAs resident at once.
 // Large launches get several spans per resident CTA, handed out by the hardware as CTAs finish: of the two CTAs of an
 // SM the one that started first runs ~1.2x faster, so with one span each the slower half
-// finishes late and alone; with shorter spans the tail is one short span (+2 % on 17 GB).  Spans stay >= 2 MiB.
+// finishes late and alone; with shorter spans the tail is one short span (+3 % at 36 GB).  Spans stay >= 16 MiB: below
+// that the longer stitch / reduce over more span blocks costs more than the tail (measured on 4.5 GB shards).
 uint32_t scan_span_count(u64 bytes, int resident) {
   static const uint32_t waves = getenv("FQGPU_SPAN_WAVES") ? (uint32_t)atoi(getenv("FQGPU_SPAN_WAVES")) : (uint32_t)SPAN_WAVES;
   const u64 ntiles = (bytes + TILE - 1) / TILE;
   if (ntiles < (u64)resident) return (uint32_t)ntiles;
-  u64 f = ntiles / ((u64)resident * 128u);
+  u64 f = ntiles / ((u64)resident * 1024u);
   f = f < 1 ? 1 : (f > waves ? waves : f);
   if (f > (u64)SPAN_WAVES) f = SPAN_WAVES;
   return (uint32_t)((u64)resident * f);
