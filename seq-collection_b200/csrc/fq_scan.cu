@@ -1377,7 +1377,8 @@ uint32_t scan_span_count(u64 bytes, int resident) {
   static const uint32_t waves = getenv("FQGPU_SPAN_WAVES") ? (uint32_t)atoi(getenv("FQGPU_SPAN_WAVES")) : (uint32_t)SPAN_WAVES;
   const u64 ntiles = (bytes + TILE - 1) / TILE;
   if (ntiles < (u64)resident) return (uint32_t)ntiles;
-  u64 f = ntiles / ((u64)resident * 1024u);
+  static const u64 min_tiles = getenv("FQGPU_SPAN_MIN_TILES") && atoi(getenv("FQGPU_SPAN_MIN_TILES")) > 0 ? (u64)atoi(getenv("FQGPU_SPAN_MIN_TILES")) : 1024u;  // (tests force waves on small inputs)
+  u64 f = ntiles / ((u64)resident * min_tiles);
   f = f < 1 ? 1 : (f > waves ? waves : f);
   if (f > (u64)SPAN_WAVES) f = SPAN_WAVES;
   return (uint32_t)((u64)resident * f);
