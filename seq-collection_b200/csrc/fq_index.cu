@@ -7,7 +7,8 @@
 // trailing unterminated line exists when it is non-empty; record k is the line with index 4k.
 //
 // Three launches: newline count per 64 KiB tile -> exclusive prefix over the tiles (one CTA) -> write pass
-// that recomputes the masks and stores the successor of every newline whose index is 3 (mod 4).  The input is
+// that recomputes the masks (a bitmap of the tile in shared memory) and stores the successor of every newline
+// whose index is 3 (mod 4).  The input is
 // read twice (2 bytes of HBM traffic per input byte); nothing depends on the statistics kernels.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -73,59 +74,84 @@ __global__ void __launch_bounds__(IDX_THREADS) fq_index_count_kernel(const uint8
 // Exclusive prefix of the tile counts (one CTA); out[0] = lines (incl. a non-empty unterminated last one), out[1] = records.
 __global__ void __launch_bounds__(1024) fq_index_scan_kernel(const uint32_t* __restrict__ tile_cnt, u64* __restrict__ tile_base, u64 ntiles,
                                                             const uint8_t* __restrict__ base, uint32_t lo0, u64 end, u64* __restrict__ out) {
-  __shared__ u64 part[1024];
-  const int tid = threadIdx.x;
+  __shared__ u64 wtot[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u64 per = (ntiles + 1023) / 1024, a = (u64)tid * per, b = a + per < ntiles ? a + per : ntiles;
   u64 s = 0;
+#pragma unroll 8
   for (u64 t = a; t < b; t++) s += tile_cnt[t];
-  part[tid] = s;
+  u64 inc = s;  // inclusive prefix over the 1024 slices: inside the warp, then over the 32 warp totals
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const u64 x = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += x; }
+  if (lane == 31) wtot[warp] = inc;
   __syncthreads();
-  if (tid == 0) {
-    u64 run = 0;
-    for (int i = 0; i < 1024; i++) { const u64 x = part[i]; part[i] = run; run += x; }
-    const u64 n = end - (u64)lo0;
-    const u64 lines = run + ((n > 0 && base[end - 1] != '\n') ? 1 : 0);
-    out[0] = lines;
-    out[1] = (lines + 3) / 4;
+  if (warp == 0) {
+    const u64 w = wtot[lane];
+    u64 winc = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const u64 x = __shfl_up_sync(0xffffffffu, winc, d); if (lane >= d) winc += x; }
+    wtot[lane] = winc - w;
+    if (lane == 31) {
+      const u64 n = end - (u64)lo0;
+      const u64 lines = winc + ((n > 0 && base[end - 1] != '\n') ? 1 : 0);
+      out[0] = lines;
+      out[1] = (lines + 3) / 4;
+    }
   }
   __syncthreads();
-  u64 run = part[tid];
+  u64 run = wtot[warp] + inc - s;
   for (u64 t = a; t < b; t++) { tile_base[t] = run; run += tile_cnt[t]; }
 }
 
+// Write pass.  Phase 1 turns the tile into its newline bitmap in shared memory (coalesced 16-byte loads, one 16-bit mask
+// per group); phase 2 hands every thread 256 consecutive bytes of it (8 words), so the tile needs ONE block-wide prefix
+// of the per-thread newline counts instead of one per row of 256 groups, and a thread walks its own few newlines.
 __global__ void __launch_bounds__(IDX_THREADS) fq_index_write_kernel(const uint8_t* __restrict__ base, uint32_t lo0, u64 end,
                                                                     const u64* __restrict__ tile_base, u64* __restrict__ offsets, u64 cap) {
+  __shared__ __align__(16) uint32_t bits[IDX_TILE / 32];  // bit b = byte b of the tile is '\n'
   __shared__ uint32_t wsum[IDX_THREADS / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u64 g0 = (u64)blockIdx.x * (IDX_THREADS * IDX_ROWS);
   const u64 n = end - (u64)lo0;
   if (blockIdx.x == 0 && tid == 0 && n > 0 && cap > 0) offsets[0] = 0;
-  u64 row_base = tile_base[blockIdx.x];  // newlines before this row of 256 groups
-  const bool interior = g0 * 16 >= (u64)lo0 && (g0 + IDX_THREADS * IDX_ROWS) * 16 <= end;
-  for (int r = 0; r < IDX_ROWS; r++) {
-    const u64 g = g0 + (u64)r * IDX_THREADS + tid;
-    uint32_t m = interior ? idx_nl_mask16(__ldg(reinterpret_cast<const uint4*>(base) + g)) : idx_group_mask(base, g, lo0, end);
-    const uint32_t c = __popc(m);
-    uint32_t inc = c;
+  uint16_t* b16 = reinterpret_cast<uint16_t*>(bits);
+  if (g0 * 16 >= (u64)lo0 && (g0 + IDX_THREADS * IDX_ROWS) * 16 <= end) {  // interior tile: no range checks
+    const uint4* p = reinterpret_cast<const uint4*>(base) + g0 + tid;
+#pragma unroll 8
+    for (int r = 0; r < IDX_ROWS; r++) b16[r * IDX_THREADS + tid] = (uint16_t)idx_nl_mask16(__ldg(p + (size_t)r * IDX_THREADS));
+  } else {
+#pragma unroll 4
+    for (int r = 0; r < IDX_ROWS; r++) b16[r * IDX_THREADS + tid] = (uint16_t)idx_group_mask(base, g0 + (u64)r * IDX_THREADS + tid, lo0, end);
+  }
+  __syncthreads();
+  const uint4 lo4 = reinterpret_cast<const uint4*>(bits)[2 * tid], hi4 = reinterpret_cast<const uint4*>(bits)[2 * tid + 1];
+  const uint32_t w[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+  uint32_t c = 0;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += x; }
-    if (lane == 31) wsum[warp] = inc;
-    __syncthreads();
-    uint32_t wb = 0, tot = 0;
+  for (int i = 0; i < 8; i++) c += __popc(w[i]);
+  uint32_t inc = c;
 #pragma unroll
-    for (int w = 0; w < IDX_THREADS / 32; w++) { const uint32_t x = wsum[w]; if (w < warp) wb += x; tot += x; }
-    u64 j = row_base + wb + inc - c;  // index of this group's first newline
+  for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += x; }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  uint32_t wb = 0;
+#pragma unroll
+  for (int i = 0; i < IDX_THREADS / 32; i++) { const uint32_t x = wsum[i]; if (i < warp) wb += x; }
+  if (c == 0) return;
+  u64 j = tile_base[blockIdx.x] + wb + inc - c;        // index of this thread's first newline
+  const u64 byte0 = g0 * 16 + (u64)tid * 256 + 1 - (u64)lo0;  // successor of the thread's byte 0, relative to the data
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint32_t m = w[i];
     while (m) {
       const int k = __ffs(m) - 1;
       m &= m - 1;
-      if ((j & 3) == 3) {
-        const u64 start = g * 16 + (u64)k + 1 - (u64)lo0, rec = (j + 1) >> 2;
+      if (((uint32_t)j & 3u) == 3u) {
+        const u64 start = byte0 + (u64)(32 * i + k), rec = (j + 1) >> 2;
         if (start < n && rec < cap) offsets[rec] = start;
       }
       j++;
     }
-    row_base += tot;
-    __syncthreads();
   }
 }
 
