@@ -12,6 +12,8 @@
 // read twice (2 bytes of HBM traffic per input byte); nothing depends on the statistics kernels.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "fqgpu_ctx.h"
 
@@ -155,6 +157,101 @@ __global__ void __launch_bounds__(IDX_THREADS) fq_index_write_kernel(const uint8
   }
 }
 
+// ---- single pass: the same tile work with a chained ("decoupled look-back") prefix, so the input is read once ------------
+// state[t]: bits 63..62 = 0 nothing yet, 1 = newlines of tile t alone, 2 = newlines of tiles 0..t; tiles are handed out by a
+// ticket counter (state[ntiles]), so a tile only ever waits for tiles that have already started.  state[ntiles + 1], [ntiles + 2]
+// receive lines and records.  The host zeroes the whole array before the launch.
+constexpr u64 IDX_AGG = 1ull << 62, IDX_INC = 2ull << 62, IDX_VAL = IDX_AGG - 1;
+__device__ __forceinline__ u64 idx_ld_relaxed(const u64* p) {
+  u64 v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void idx_st_relaxed(u64* p, u64 v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+
+__global__ void __launch_bounds__(IDX_THREADS) fq_index_onepass_kernel(const uint8_t* __restrict__ base, uint32_t lo0, u64 end, u64* state, u64 ntiles,
+                                                                      u64* __restrict__ offsets, u64 cap) {
+  __shared__ __align__(16) uint32_t bits[IDX_TILE / 32];  // bit b = byte b of the tile is '\n'
+  __shared__ uint32_t wsum[IDX_THREADS / 32];
+  __shared__ u64 s_tile, s_prefix;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(reinterpret_cast<unsigned long long*>(state + ntiles), 1ull);
+  __syncthreads();
+  const u64 tile = s_tile;
+  const u64 g0 = tile * (IDX_THREADS * IDX_ROWS);
+  const u64 n = end - (u64)lo0;
+  if (tile == 0 && tid == 0 && n > 0 && cap > 0) offsets[0] = 0;
+  uint16_t* b16 = reinterpret_cast<uint16_t*>(bits);
+  if (g0 * 16 >= (u64)lo0 && (g0 + IDX_THREADS * IDX_ROWS) * 16 <= end) {  // interior tile: no range checks
+    const uint4* p = reinterpret_cast<const uint4*>(base) + g0 + tid;
+#pragma unroll 8
+    for (int r = 0; r < IDX_ROWS; r++) b16[r * IDX_THREADS + tid] = (uint16_t)idx_nl_mask16(__ldg(p + (size_t)r * IDX_THREADS));
+  } else {
+#pragma unroll 4
+    for (int r = 0; r < IDX_ROWS; r++) b16[r * IDX_THREADS + tid] = (uint16_t)idx_group_mask(base, g0 + (u64)r * IDX_THREADS + tid, lo0, end);
+  }
+  __syncthreads();
+  const uint4 lo4 = reinterpret_cast<const uint4*>(bits)[2 * tid], hi4 = reinterpret_cast<const uint4*>(bits)[2 * tid + 1];
+  const uint32_t w[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+  uint32_t c = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) c += __popc(w[i]);
+  uint32_t inc = c;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += x; }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  uint32_t wb = 0, tot = 0;
+#pragma unroll
+  for (int i = 0; i < IDX_THREADS / 32; i++) { const uint32_t x = wsum[i]; if (i < warp) wb += x; tot += x; }
+  if (warp == 0) {  // publish this tile's count, then walk back over the predecessors, 32 at a time
+    if (lane == 0 && tile > 0) idx_st_relaxed(state + tile, IDX_AGG | (u64)tot);
+    u64 excl = 0;
+    if (tile > 0) {
+      long long i = (long long)tile - 1;
+      for (;;) {
+        const long long p = i - lane;
+        u64 st;
+        do { st = p >= 0 ? idx_ld_relaxed(state + p) : IDX_INC; } while (__any_sync(0xffffffffu, (st >> 62) == 0));
+        const uint32_t pm = __ballot_sync(0xffffffffu, (st >> 62) == 2);
+        const int first = pm ? __ffs(pm) - 1 : 31;  // the nearest predecessor that already knows its inclusive prefix
+        u64 v = lane <= first ? (st & IDX_VAL) : 0;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        excl += v;
+        if (pm) break;
+        i -= 32;
+      }
+    }
+    if (lane == 0) {
+      idx_st_relaxed(state + tile, IDX_INC | (excl + (u64)tot));
+      s_prefix = excl;
+      if (tile + 1 == ntiles) {
+        const u64 lines = excl + (u64)tot + ((n > 0 && base[end - 1] != '\n') ? 1 : 0);
+        state[ntiles + 1] = lines;
+        state[ntiles + 2] = (lines + 3) / 4;
+      }
+    }
+  }
+  __syncthreads();
+  if (c == 0) return;
+  u64 j = s_prefix + wb + inc - c;                            // index of this thread's first newline
+  const u64 byte0 = g0 * 16 + (u64)tid * 256 + 1 - (u64)lo0;  // successor of the thread's byte 0, relative to the data
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint32_t m = w[i];
+    while (m) {
+      const int k = __ffs(m) - 1;
+      m &= m - 1;
+      if (((uint32_t)j & 3u) == 3u) {
+        const u64 start = byte0 + (u64)(32 * i + k), rec = (j + 1) >> 2;
+        if (start < n && rec < cap) offsets[rec] = start;
+      }
+      j++;
+    }
+  }
+}
+
 // First `n` header lines (records 0..n-1) into a row-major matrix: up to `stride` bytes each; len[k] = bytes
 // copied (content up to '\n', a '\r' directly before it dropped, truncated at stride).  One warp per record.
 __global__ void fq_headers_kernel(const uint8_t* __restrict__ data, u64 nbytes, const u64* __restrict__ offsets, u64 n,
@@ -195,27 +292,44 @@ int fqgpu_index_device(fqgpu_ctx* ctx, const void* dptr, size_t nbytes, uint64_t
   const fq::u64 end = (fq::u64)lo0 + nbytes;
   const fq::u64 ntiles = (end + fq::IDX_TILE - 1) / fq::IDX_TILE;
   if (ntiles > 0x7FFFFFFFull) return fail(ctx, FQGPU_EARG, "fqgpu_index_device: buffer too large for one call");
-  uint32_t* d_cnt = nullptr;
-  fq::u64* d_base = nullptr;
-  fq::u64* d_out = nullptr;
-  CU_TRY(ctx, cudaMallocAsync((void**)&d_cnt, ntiles * sizeof(uint32_t), ctx->stream));
-  CU_TRY(ctx, cudaMallocAsync((void**)&d_base, ntiles * sizeof(fq::u64), ctx->stream));
-  CU_TRY(ctx, cudaMallocAsync((void**)&d_out, 2 * sizeof(fq::u64), ctx->stream));
-  cudaEvent_t e0 = fqgpu_get_event(ctx), e1 = fqgpu_get_event(ctx);
-  CU_TRY(ctx, cudaEventRecord(e0, ctx->stream));
-  fq::fq_index_count_kernel<<<(unsigned)ntiles, fq::IDX_THREADS, 0, ctx->stream>>>(base, lo0, end, d_cnt);
-  fq::fq_index_scan_kernel<<<1, 1024, 0, ctx->stream>>>(d_cnt, d_base, ntiles, base, lo0, end, d_out);
-  fq::fq_index_write_kernel<<<(unsigned)ntiles, fq::IDX_THREADS, 0, ctx->stream>>>(base, lo0, end, d_base, (fq::u64*)d_offsets, cap);
-  CU_TRY(ctx, cudaGetLastError());
-  CU_TRY(ctx, cudaEventRecord(e1, ctx->stream));
-  ctx->timed.emplace_back(e0, e1);
-  ctx->launches += 3;
+  const char* mode = getenv("FQGPU_INDEX");
+  const bool two_pass = mode && strcmp(mode, "2pass") == 0;
   fq::u64 h[2] = {0, 0};
-  CU_TRY(ctx, cudaMemcpyAsync(h, d_out, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
-  CU_TRY(ctx, cudaFreeAsync(d_cnt, ctx->stream));
-  CU_TRY(ctx, cudaFreeAsync(d_base, ctx->stream));
-  CU_TRY(ctx, cudaFreeAsync(d_out, ctx->stream));
-  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaEvent_t e0 = fqgpu_get_event(ctx), e1 = fqgpu_get_event(ctx);
+  if (!two_pass) {  // one launch: chained prefix over the tiles, the input is read once
+    fq::u64* d_state = nullptr;  // [ntiles] tile states, then the ticket counter, lines, records
+    CU_TRY(ctx, cudaMallocAsync((void**)&d_state, (ntiles + 3) * sizeof(fq::u64), ctx->stream));
+    CU_TRY(ctx, cudaEventRecord(e0, ctx->stream));
+    CU_TRY(ctx, cudaMemsetAsync(d_state, 0, (ntiles + 3) * sizeof(fq::u64), ctx->stream));
+    fq::fq_index_onepass_kernel<<<(unsigned)ntiles, fq::IDX_THREADS, 0, ctx->stream>>>(base, lo0, end, d_state, ntiles, (fq::u64*)d_offsets, cap);
+    CU_TRY(ctx, cudaGetLastError());
+    CU_TRY(ctx, cudaEventRecord(e1, ctx->stream));
+    ctx->timed.emplace_back(e0, e1);
+    ctx->launches += 1;
+    CU_TRY(ctx, cudaMemcpyAsync(h, d_state + ntiles + 1, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaFreeAsync(d_state, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  } else {  // count per tile -> prefix (one CTA) -> write pass: two reads of the input
+    uint32_t* d_cnt = nullptr;
+    fq::u64* d_base = nullptr;
+    fq::u64* d_out = nullptr;
+    CU_TRY(ctx, cudaMallocAsync((void**)&d_cnt, ntiles * sizeof(uint32_t), ctx->stream));
+    CU_TRY(ctx, cudaMallocAsync((void**)&d_base, ntiles * sizeof(fq::u64), ctx->stream));
+    CU_TRY(ctx, cudaMallocAsync((void**)&d_out, 2 * sizeof(fq::u64), ctx->stream));
+    CU_TRY(ctx, cudaEventRecord(e0, ctx->stream));
+    fq::fq_index_count_kernel<<<(unsigned)ntiles, fq::IDX_THREADS, 0, ctx->stream>>>(base, lo0, end, d_cnt);
+    fq::fq_index_scan_kernel<<<1, 1024, 0, ctx->stream>>>(d_cnt, d_base, ntiles, base, lo0, end, d_out);
+    fq::fq_index_write_kernel<<<(unsigned)ntiles, fq::IDX_THREADS, 0, ctx->stream>>>(base, lo0, end, d_base, (fq::u64*)d_offsets, cap);
+    CU_TRY(ctx, cudaGetLastError());
+    CU_TRY(ctx, cudaEventRecord(e1, ctx->stream));
+    ctx->timed.emplace_back(e0, e1);
+    ctx->launches += 3;
+    CU_TRY(ctx, cudaMemcpyAsync(h, d_out, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaFreeAsync(d_cnt, ctx->stream));
+    CU_TRY(ctx, cudaFreeAsync(d_base, ctx->stream));
+    CU_TRY(ctx, cudaFreeAsync(d_out, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   *n_records = h[1];
   ctx->index_lines = h[0];
   return FQGPU_OK;

@@ -16,6 +16,13 @@ import seq_collection_b200 as fq
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["onepass", "2pass"], autouse=True)
+def index_mode(request, monkeypatch):
+    """Both index paths: the single launch with the chained tile prefix (default) and count -> prefix -> write."""
+    monkeypatch.setenv("FQGPU_INDEX", request.param)
+    return request.param
+
+
 def _check(c, torch, data: bytes, misalign: int = 0, n_headers: int = 25):
     want = O.record_offsets(data)
     buf = torch.zeros(len(data) + 64, dtype=torch.uint8, device="cuda")
@@ -45,6 +52,8 @@ def test_index_edge_corpus_and_random():
     cases["dense"] = b"\n" * 70001 + b"x"
     cases["long"] = b"@a\n" + b"A" * 200000 + b"\n+\n" + b"I" * 200000 + b"\n@b\nAC\n+\nII"
     cases["nonl"] = b"ACGT" * 50000
+    # several hundred 64 KiB tiles with ragged lines: the chained prefix walks back over many predecessors
+    cases["many_tiles"] = corpus.random_fastq(rng, 60000, min_len=0, max_len=600, final_newline=False)
     with fq.FqGpu(meta_records=0) as c:
         for name, data in cases.items():
             for mis in (0, 5):
