@@ -169,33 +169,39 @@ __device__ __forceinline__ u64 idx_ld_relaxed(const u64* p) {
 }
 __device__ __forceinline__ void idx_st_relaxed(u64* p, u64 v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
 
+template <int ROWS>  // 16-byte groups per thread: the tile is 4 KiB * ROWS
 __global__ void __launch_bounds__(IDX_THREADS) fq_index_onepass_kernel(const uint8_t* __restrict__ base, uint32_t lo0, u64 end, u64* state, u64 ntiles,
                                                                       u64* __restrict__ offsets, u64 cap) {
-  __shared__ __align__(16) uint32_t bits[IDX_TILE / 32];  // bit b = byte b of the tile is '\n'
+  __shared__ __align__(16) uint32_t bits[IDX_THREADS * ROWS / 2];  // bit b = byte b of the tile is '\n'
   __shared__ uint32_t wsum[IDX_THREADS / 32];
   __shared__ u64 s_tile, s_prefix;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(reinterpret_cast<unsigned long long*>(state + ntiles), 1ull);
   __syncthreads();
   const u64 tile = s_tile;
-  const u64 g0 = tile * (IDX_THREADS * IDX_ROWS);
+  const u64 g0 = tile * (IDX_THREADS * ROWS);
   const u64 n = end - (u64)lo0;
   if (tile == 0 && tid == 0 && n > 0 && cap > 0) offsets[0] = 0;
   uint16_t* b16 = reinterpret_cast<uint16_t*>(bits);
-  if (g0 * 16 >= (u64)lo0 && (g0 + IDX_THREADS * IDX_ROWS) * 16 <= end) {  // interior tile: no range checks
+  if (g0 * 16 >= (u64)lo0 && (g0 + IDX_THREADS * ROWS) * 16 <= end) {  // interior tile: no range checks
     const uint4* p = reinterpret_cast<const uint4*>(base) + g0 + tid;
 #pragma unroll 8
-    for (int r = 0; r < IDX_ROWS; r++) b16[r * IDX_THREADS + tid] = (uint16_t)idx_nl_mask16(__ldg(p + (size_t)r * IDX_THREADS));
+    for (int r = 0; r < ROWS; r++) b16[r * IDX_THREADS + tid] = (uint16_t)idx_nl_mask16(__ldg(p + (size_t)r * IDX_THREADS));
   } else {
 #pragma unroll 4
-    for (int r = 0; r < IDX_ROWS; r++) b16[r * IDX_THREADS + tid] = (uint16_t)idx_group_mask(base, g0 + (u64)r * IDX_THREADS + tid, lo0, end);
+    for (int r = 0; r < ROWS; r++) b16[r * IDX_THREADS + tid] = (uint16_t)idx_group_mask(base, g0 + (u64)r * IDX_THREADS + tid, lo0, end);
   }
   __syncthreads();
-  const uint4 lo4 = reinterpret_cast<const uint4*>(bits)[2 * tid], hi4 = reinterpret_cast<const uint4*>(bits)[2 * tid + 1];
-  const uint32_t w[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+  constexpr int WPT = ROWS / 2;  // bitmap words per thread: 16 * ROWS consecutive bytes
+  uint32_t w[WPT];
+#pragma unroll
+  for (int i = 0; i < WPT / 4; i++) {
+    const uint4 q = reinterpret_cast<const uint4*>(bits)[(WPT / 4) * tid + i];
+    w[4 * i] = q.x; w[4 * i + 1] = q.y; w[4 * i + 2] = q.z; w[4 * i + 3] = q.w;
+  }
   uint32_t c = 0;
 #pragma unroll
-  for (int i = 0; i < 8; i++) c += __popc(w[i]);
+  for (int i = 0; i < WPT; i++) c += __popc(w[i]);
   uint32_t inc = c;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += x; }
@@ -236,9 +242,9 @@ __global__ void __launch_bounds__(IDX_THREADS) fq_index_onepass_kernel(const uin
   __syncthreads();
   if (c == 0) return;
   u64 j = s_prefix + wb + inc - c;                            // index of this thread's first newline
-  const u64 byte0 = g0 * 16 + (u64)tid * 256 + 1 - (u64)lo0;  // successor of the thread's byte 0, relative to the data
+  const u64 byte0 = g0 * 16 + (u64)tid * (16 * ROWS) + 1 - (u64)lo0;  // successor of the thread's byte 0, relative to the data
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
+  for (int i = 0; i < WPT; i++) {
     uint32_t m = w[i];
     while (m) {
       const int k = __ffs(m) - 1;
@@ -297,11 +303,20 @@ int fqgpu_index_device(fqgpu_ctx* ctx, const void* dptr, size_t nbytes, uint64_t
   fq::u64 h[2] = {0, 0};
   cudaEvent_t e0 = fqgpu_get_event(ctx), e1 = fqgpu_get_event(ctx);
   if (!two_pass) {  // one launch: chained prefix over the tiles, the input is read once
+    // per-tile costs (ticket, four barriers, the walk back) are spread over larger tiles once there are enough of them
+    // to fill the machine: 256 KiB tiles from 320 MiB, 128 KiB from 160 MiB, else 64 KiB (measured 4.4 / 4.8 / 5.0 TB/s
+    // with 64 / 128 / 256 KiB tiles at 8.6 GB); FQGPU_INDEX_ROWS = 16 | 32 | 64 forces one (tests)
+    const char* re = getenv("FQGPU_INDEX_ROWS");
+    const int rows = re ? atoi(re) : nbytes >= ((size_t)320 << 20) ? 64 : nbytes >= ((size_t)160 << 20) ? 32 : 16;
+    const fq::u64 tile_bytes = (fq::u64)fq::IDX_THREADS * 16 * (fq::u64)rows;
+    const fq::u64 ntiles = (end + tile_bytes - 1) / tile_bytes;
     fq::u64* d_state = nullptr;  // [ntiles] tile states, then the ticket counter, lines, records
     CU_TRY(ctx, cudaMallocAsync((void**)&d_state, (ntiles + 3) * sizeof(fq::u64), ctx->stream));
     CU_TRY(ctx, cudaEventRecord(e0, ctx->stream));
     CU_TRY(ctx, cudaMemsetAsync(d_state, 0, (ntiles + 3) * sizeof(fq::u64), ctx->stream));
-    fq::fq_index_onepass_kernel<<<(unsigned)ntiles, fq::IDX_THREADS, 0, ctx->stream>>>(base, lo0, end, d_state, ntiles, (fq::u64*)d_offsets, cap);
+    if (rows == 32) fq::fq_index_onepass_kernel<32><<<(unsigned)ntiles, fq::IDX_THREADS, 0, ctx->stream>>>(base, lo0, end, d_state, ntiles, (fq::u64*)d_offsets, cap);
+    else if (rows == 64) fq::fq_index_onepass_kernel<64><<<(unsigned)ntiles, fq::IDX_THREADS, 0, ctx->stream>>>(base, lo0, end, d_state, ntiles, (fq::u64*)d_offsets, cap);
+    else fq::fq_index_onepass_kernel<16><<<(unsigned)ntiles, fq::IDX_THREADS, 0, ctx->stream>>>(base, lo0, end, d_state, ntiles, (fq::u64*)d_offsets, cap);
     CU_TRY(ctx, cudaGetLastError());
     CU_TRY(ctx, cudaEventRecord(e1, ctx->stream));
     ctx->timed.emplace_back(e0, e1);

@@ -16,10 +16,13 @@ import seq_collection_b200 as fq
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["onepass", "2pass"], autouse=True)
+@pytest.fixture(params=["onepass", "onepass16", "onepass32", "onepass64", "2pass"], autouse=True)
 def index_mode(request, monkeypatch):
-    """Both index paths: the single launch with the chained tile prefix (default) and count -> prefix -> write."""
+    """Both index paths: the single launch with the chained tile prefix (default; tile size by input size, or each of
+    the 64 / 128 / 256 KiB instantiations forced) and count -> prefix -> write."""
     monkeypatch.setenv("FQGPU_INDEX", request.param)
+    if request.param[7:]:
+        monkeypatch.setenv("FQGPU_INDEX_ROWS", request.param[7:])
     return request.param
 
 
