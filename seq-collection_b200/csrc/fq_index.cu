@@ -6,10 +6,12 @@
 // Line semantics are those of the scan (Nim streams.lines, src/fq_count.nim:38): lines end at '\n'; the
 // trailing unterminated line exists when it is non-empty; record k is the line with index 4k.
 //
-// Three launches: newline count per 64 KiB tile -> exclusive prefix over the tiles (one CTA) -> write pass
-// that recomputes the masks (a bitmap of the tile in shared memory) and stores the successor of every newline
-// whose index is 3 (mod 4).  The input is
-// read twice (2 bytes of HBM traffic per input byte); nothing depends on the statistics kernels.
+// One launch (fq_index_onepass_kernel): tiles of 64 / 128 / 256 KiB are handed out by a ticket counter; a tile becomes
+// its newline bitmap in shared memory, one block-wide prefix gives its newline count, the count is published and the
+// predecessors' counts are summed by a chained (decoupled look-back) prefix, and the successor of every newline whose
+// index is 3 (mod 4) is stored.  The input is read once (1 byte of HBM traffic per input byte).
+// FQGPU_INDEX=2pass keeps the earlier three launches: newline count per 64 KiB tile -> exclusive prefix over the
+// tiles (one CTA) -> write pass (the same bitmap phase), two reads of the input.  Nothing depends on the statistics kernels.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
