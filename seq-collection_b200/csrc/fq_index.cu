@@ -172,7 +172,7 @@ __device__ __forceinline__ u64 idx_ld_relaxed(const u64* p) {
 __device__ __forceinline__ void idx_st_relaxed(u64* p, u64 v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
 
 template <int ROWS>  // 16-byte groups per thread: the tile is 4 KiB * ROWS
-__global__ void __launch_bounds__(IDX_THREADS) fq_index_onepass_kernel(const uint8_t* __restrict__ base, uint32_t lo0, u64 end, u64* state, u64 ntiles,
+__global__ void __launch_bounds__(IDX_THREADS, ROWS == 64 ? 5 : ROWS == 32 ? 6 : 8) fq_index_onepass_kernel(const uint8_t* __restrict__ base, uint32_t lo0, u64 end, u64* state, u64 ntiles,
                                                                       u64* __restrict__ offsets, u64 cap) {
   __shared__ __align__(16) uint32_t bits[IDX_THREADS * ROWS / 2];  // bit b = byte b of the tile is '\n'
   __shared__ uint32_t wsum[IDX_THREADS / 32];
