@@ -1,6 +1,6 @@
 // fq_layout.h -- constants shared by the device kernels and the host side of libfqgpu.
-// Counter blocks are arrays of uint64 words; every span (one persistent CTA per span and launch)
-// owns one block, the reduction kernel (K3) folds them into one block of the same layout.
+// The counter block is an array of uint64 words; every persistent CTA of a scan launch adds its shared-memory
+// tables into the context's one block (K3 is this reduction by 64-bit atomics at CTA exit).
 #pragma once
 #include <stdint.h>
 
@@ -25,9 +25,21 @@ constexpr int OFF_QUAL_LEN_MAX = OFF_QUAL_LEN_MIN + 1;
 constexpr int BLOCK_WORDS = ((OFF_QUAL_LEN_MAX + 1 + 31) / 32) * 32;
 constexpr int N_SUM_WORDS = OFF_SEQ_LEN_MIN;  // words [0, N_SUM_WORDS) are sum-reduced
 
-constexpr int BASE_SPANS = 296;             // CTAs resident at once: 2 per SM on a 148-SM B200
-constexpr int SPAN_WAVES = 8;               // large launches are cut into up to this many spans per resident CTA (see launch_scan)
-constexpr int MAX_SPANS = BASE_SPANS * SPAN_WAVES;
+constexpr int RESIDENT_CTAS = 296;         // persistent CTAs of a scan launch: 2 per SM on a 148-SM B200
+
+// ---- launch control words (device, u64[CTL_WORDS]); zeroed by the reset kernel, left clean by every launch --------
+enum {
+  CTL_TICKET = 0,   // next tile to hand out
+  CTL_DONE,         // CTAs that have finished
+  CTL_TOTAL_T,      // newlines of the launch
+  CTL_OPEN_OUT,     // open-line bytes after the launch's last tile
+  CTL_FIRST_NL,     // shards with an unknown start: offset of the stream's first newline + 1 (0 = none in this launch)
+  CTL_HEAD,         // shards: HEAD_* flags of this launch | P0 << 8 is kept in CTL_HEAD_P0
+  CTL_HEAD_P0,      // shards: bytes of the detached head before this launch
+  CTL_ERROR,        // sticky: internal consistency check failed (item queue bound)
+  CTL_WORDS = 16
+};
+enum { HEAD_ACTIVE = 1u, HEAD_QUAL = 2u, HEAD_PENDING_CR = 4u };
 
 // ---- stream carry: device-resident state that makes consecutive scans one logical stream ----
 struct Carry {
@@ -50,7 +62,9 @@ struct Carry {
 //   CARRY_UNKNOWN_START  the shard started with an unknown phase; `lines` counts from the shard start
 //   CARRY_HYP_VALID      flags >> 8 & 3 is the phase hypothesis (resynced from the content) the shard
 //                        was scanned with; verified by fqgpu_shard_combine against the exact counts
-enum { CARRY_UNKNOWN_START = 1u, CARRY_HYP_VALID = 2u, CARRY_HYP_SHIFT = 8 };
+//   CARRY_HYP_FAILED     no record start was found where the hypothesis was needed: the shard's block is not usable
+//                        (fqgpu_shard_combine reports FQGPU_ERETRY and the rank is rescanned with the exact carry)
+enum { CARRY_UNKNOWN_START = 1u, CARRY_HYP_VALID = 2u, CARRY_HYP_FAILED = 4u, CARRY_HYP_SHIFT = 8 };
 
 // What a shard exports besides its counter block (one slot of the all-reduced buffer).
 constexpr int SH_OFF_HEAD_POS = 0;                         // [POS_BINS+1] per-position sums of the detached head fragment
@@ -69,31 +83,6 @@ struct ShardInfo {
   unsigned int head_cr;                       // the byte before that newline is '\r' (and inside the shard)
   unsigned int first_byte;                    // first byte of the shard
   unsigned int pad[2];
-};
-
-// One span = the contiguous run of tiles one CTA scans in a launch.  The line phase at a span start
-// is GUESSED from the content (first '@' line whose line+2 starts with '+') so that no CTA ever
-// waits for another; the stitch kernel verifies every guess against the exact line counts.
-enum { SPAN_PENDING = 0, SPAN_COMMITTED = 1, SPAN_RESCAN = 2 };
-constexpr unsigned int PHASE_UNKNOWN = 4;
-struct SpanDesc {
-  unsigned long long T;         // newlines in the span
-  unsigned long long head_len;  // bytes before the first newline (span length when T == 0)
-  unsigned long long tail_len;  // bytes after the last newline (T > 0)
-  unsigned long long G, P0;     // exact lines / open-line bytes before the span (stitch kernel)
-  unsigned int guess;           // (lines before the span) mod 4 used by pass 0; PHASE_UNKNOWN = count only
-  unsigned int state;           // SPAN_*
-  unsigned int exact;           // exact phase (stitch kernel)
-  unsigned int pad;
-  unsigned long long pad2[2];
-};
-
-// Snapshot of the carry taken at the start of a launch (read by every stitch CTA while the last
-// one writes the new carry).
-struct LaunchHdr {
-  unsigned long long lines0, open0, bytes0;
-  unsigned int last_byte0, flags0;   // flags0 = Carry.flags at the start of the launch
-  unsigned int mismatches, pad;
 };
 
 }  // namespace fq

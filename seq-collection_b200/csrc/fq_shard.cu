@@ -1,8 +1,8 @@
 // fq_shard.cu -- multi-GPU byte-range shard protocol (include/fqgpu.h).
 //
 // Rank g of `world` scans bytes [g*N/world, (g+1)*N/world) of one logical stream.  A rank > 0 does not
-// know the line phase of its first byte: its launch resynchronises on the content like any span start
-// (fq_resync_kernel), scans under that hypothesis, and keeps what depends on the previous shards
+// know the line phase of its first byte: the CTA that takes the shard's first tile resynchronises on the content
+// (resync_guess in fq_scan.cu), the shard is scanned under that hypothesis, and keeps what depends on the previous shards
 // detached (fq::ShardInfo): the per-position sums and the length of its first line fragment.  Every
 // rank exports one block of uint64 words into its slot of a buffer that the caller SUM-all-reduces
 // (disjoint slots, so the sum is a gather) -- the one collective of the path.  The combine step then
@@ -36,7 +36,7 @@ __global__ void fq_shard_pack_kernel(const u64* __restrict__ reduced, const Carr
     sc[SH_HEAD_LEN] = shard->head_len;
     sc[SH_HEAD_CR] = shard->head_cr;
     sc[SH_HYP] = (f >> CARRY_HYP_SHIFT) & 3u;
-    sc[SH_HYP_VALID] = (f & CARRY_HYP_VALID) ? 1 : 0;
+    sc[SH_HYP_VALID] = ((f & CARRY_HYP_VALID) && !(f & CARRY_HYP_FAILED)) ? 1 : 0;
     sc[SH_EXACT] = (exact || !(f & CARRY_UNKNOWN_START)) ? 1 : 0;
     sc[SH_META_LINES] = carry->meta_lines;
     sc[SH_META_QMIN] = (u64)carry->qual_min;
@@ -177,9 +177,8 @@ int fqgpu_shard_export(fqgpu_ctx* ctx, uint64_t* d_blocks) {
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   cudaEvent_t e0 = fqgpu_get_event(ctx), e1 = fqgpu_get_event(ctx);
   CU_TRY(ctx, cudaEventRecord(e0, ctx->stream));
-  CU_TRY(ctx, launch_reduce(ctx->d_committed, ctx->span_hwm, ctx->d_out, ctx->stream));
   u64* slot = (u64*)d_blocks + (size_t)ctx->shard_rank * kShardWords;
-  fq_shard_pack_kernel<<<(BLOCK_WORDS + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_out, ctx->d_carry, ctx->d_shard,
+  fq_shard_pack_kernel<<<(BLOCK_WORDS + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_acc, ctx->d_carry, ctx->d_shard,
                                                                            ctx->shard_exact ? 1 : 0, slot);
   CU_TRY(ctx, cudaGetLastError());
   CU_TRY(ctx, cudaEventRecord(e1, ctx->stream));
@@ -231,7 +230,7 @@ int fqgpu_shard_rescan(fqgpu_ctx* ctx, const uint64_t* d_blocks) {
   // known exactly up to the first wrong shard, so one shard is repaired per round
   if (g != bad) return FQGPU_OK;
   const Chain c = before[g];
-  CU_TRY(ctx, launch_reset(ctx->d_committed, ctx->span_hwm, ctx->d_carry, ctx->stream));
+  CU_TRY(ctx, launch_reset(ctx->d_acc, ctx->d_carry, ctx->d_ctl, ctx->stream));
   fq_shard_begin_kernel<<<(POS_BINS + 256) / 256, 256, 0, ctx->stream>>>(ctx->d_carry, ctx->d_shard, 0);
   fq_shard_set_carry_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_carry, c.lines, c.open, c.bytes, c.last_byte);
   CU_TRY(ctx, cudaGetLastError());

@@ -25,7 +25,7 @@ extern "C" {
 int fqgpu_abi_version(void) { return FQGPU_ABI_VERSION; }
 size_t fqgpu_stats_size(void) { return sizeof(fqgpu_stats); }
 const char* fqgpu_build_info(void) {
-  return "libfqgpu sm_100a; scan tile " "16 KiB" "; built " __DATE__;
+  return "libfqgpu sm_100a; scan tile " "32 KiB" "; built " __DATE__;
 }
 int fqgpu_device_count(void) {
   int n = 0;
@@ -52,11 +52,10 @@ void fqgpu_destroy(fqgpu_ctx* ctx) {
     if (ctx->ev_scanned[b]) cudaEventDestroy(ctx->ev_scanned[b]);
   }
   if (ctx->cstream) cudaStreamDestroy(ctx->cstream);
-  cudaFree(ctx->d_pending);
-  cudaFree(ctx->d_committed);
+  cudaFree(ctx->d_acc);
+  cudaFree(ctx->d_state);
+  cudaFree(ctx->d_ctl);
   cudaFree(ctx->d_carry);
-  cudaFree(ctx->d_desc);
-  cudaFree(ctx->d_hdr);
   cudaFree(ctx->d_shard);
   if (ctx->h_shard) cudaFreeHost(ctx->h_shard);
   if (ctx->h_comp) cudaFreeHost(ctx->h_comp);
@@ -64,7 +63,6 @@ void fqgpu_destroy(fqgpu_ctx* ctx) {
   cudaFree(ctx->d_inflated);
   cudaFree(ctx->d_members);
   cudaFree(ctx->d_mstatus);
-  cudaFree(ctx->d_out);
   if (ctx->h_out) cudaFreeHost(ctx->h_out);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -105,22 +103,16 @@ int fqgpu_create(fqgpu_ctx** out, const fqgpu_config* cfg) {
   CU_NEW(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   CU_NEW(fq::scan_configure());
   ctx->grid = prop.multiProcessorCount * 2;
-  if (ctx->grid > fq::BASE_SPANS) ctx->grid = fq::BASE_SPANS;
-  CU_NEW(cudaMalloc(&ctx->d_pending, (size_t)fq::MAX_SPANS * fq::BLOCK_WORDS * sizeof(u64)));
-  CU_NEW(cudaMalloc(&ctx->d_committed, (size_t)fq::MAX_SPANS * fq::BLOCK_WORDS * sizeof(u64)));
+  CU_NEW(cudaMalloc(&ctx->d_acc, fq::BLOCK_WORDS * sizeof(u64)));
+  CU_NEW(cudaMalloc(&ctx->d_ctl, fq::CTL_WORDS * sizeof(u64)));
   CU_NEW(cudaMalloc(&ctx->d_carry, sizeof(fq::Carry)));
-  CU_NEW(cudaMalloc(&ctx->d_desc, fq::MAX_SPANS * sizeof(fq::SpanDesc)));
-  CU_NEW(cudaMalloc(&ctx->d_hdr, sizeof(fq::LaunchHdr)));
   CU_NEW(cudaMalloc(&ctx->d_shard, sizeof(fq::ShardInfo)));
   CU_NEW(cudaMallocHost(&ctx->h_shard, (size_t)64 * fqgpu_shard_block_words() * sizeof(u64)));
-  CU_NEW(cudaMalloc(&ctx->d_out, fq::BLOCK_WORDS * sizeof(u64)));
-  CU_NEW(cudaMallocHost(&ctx->h_out, fq::BLOCK_WORDS * sizeof(u64) + sizeof(fq::Carry)));
+  CU_NEW(cudaMallocHost(&ctx->h_out, fq::BLOCK_WORDS * sizeof(u64) + sizeof(fq::Carry) + sizeof(u64)));
   ctx->ring.resize(nbuf);  // pinned chunks are allocated lazily by the first acquire()
 #undef CU_NEW
   *out = ctx;
-  ctx->span_hwm = fq::MAX_SPANS;  // the first reset initialises every block; later ones only those that were used
   int rc = fqgpu_reset(ctx);
-  ctx->span_hwm = fq::BASE_SPANS;
   if (rc != FQGPU_OK) { g_create_error = ctx->err; fqgpu_destroy(ctx); *out = nullptr; return rc; }
   return FQGPU_OK;
 }
@@ -128,7 +120,7 @@ int fqgpu_create(fqgpu_ctx** out, const fqgpu_config* cfg) {
 int fqgpu_reset(fqgpu_ctx* ctx) {
   if (!ctx) return FQGPU_EARG;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
-  CU_TRY(ctx, fq::launch_reset(ctx->d_committed, ctx->span_hwm, ctx->d_carry, ctx->stream));
+  CU_TRY(ctx, fq::launch_reset(ctx->d_acc, ctx->d_carry, ctx->d_ctl, ctx->stream));
   for (auto& p : ctx->timed) { ctx->event_pool.push_back(p.first); ctx->event_pool.push_back(p.second); }
   ctx->timed.clear();
   ctx->kernel_ms_done = 0.0;
@@ -136,6 +128,7 @@ int fqgpu_reset(fqgpu_ctx* ctx) {
   ctx->bgzf_members = 0;
   ctx->shard_rank = 0;
   ctx->shard_world = 1;
+  ctx->shard_exact = false;
   return FQGPU_OK;
 }
 
@@ -150,6 +143,41 @@ cudaEvent_t fqgpu_get_event(fqgpu_ctx* ctx) {
 
 extern "C" {
 
+// One scan launch over [p, p + n) as the continuation of the context's stream; the fq-meta prefix fold (which touches
+// only its own fields of the carry) runs beside it on its own stream.
+static int fqgpu_launch_scan(fqgpu_ctx* ctx, const uint8_t* p, size_t n, u64 meta_records) {
+  const u64 ntiles = fq::scan_tiles(p, n);
+  if (ntiles > ctx->state_cap) {  // look-back words: grown to the largest launch so far (8 bytes per 32 KiB of input)
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_state) CU_TRY(ctx, cudaFree(ctx->d_state));
+    ctx->d_state = nullptr;
+    ctx->state_cap = 0;
+    const u64 cap = ntiles + ntiles / 4 + 1024;
+    CU_TRY(ctx, cudaMalloc(&ctx->d_state, cap * sizeof(u64)));
+    CU_TRY(ctx, cudaMemsetAsync(ctx->d_state, 0, cap * sizeof(u64), ctx->stream));
+    ctx->state_cap = cap;
+    ctx->epoch = 0;
+  }
+  if (++ctx->epoch > 255) {  // epochs are about to repeat: forget every word written so far
+    CU_TRY(ctx, cudaMemsetAsync(ctx->d_state, 0, ctx->state_cap * sizeof(u64), ctx->stream));
+    ctx->epoch = 1;
+  }
+  if (meta_records) {
+    const uintptr_t addr = (uintptr_t)p;
+    const uint32_t lo0 = (uint32_t)(addr & 15);
+    CU_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    CU_TRY(ctx, cudaStreamWaitEvent(ctx->mstream, ctx->ev_fork, 0));
+    CU_TRY(ctx, fq::launch_meta((const uint8_t*)(addr - lo0), lo0, (u64)lo0 + n, ctx->d_carry, meta_records, ctx->mstream));
+    CU_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->mstream));
+  }
+  CU_TRY(ctx, fq::launch_scan(p, n, ctx->d_carry, ctx->d_shard, ctx->d_acc, ctx->d_state, ctx->d_ctl, ctx->epoch,
+                              ctx->shard_rank > 0 && !ctx->shard_exact, ctx->grid, (ctx->cfg.flags & FQGPU_F_CORE_ONLY) != 0,
+                              ctx->stream));
+  if (meta_records) CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+  ctx->launches++;
+  return FQGPU_OK;
+}
+
 int fqgpu_scan_device(fqgpu_ctx* ctx, const void* dptr, size_t nbytes) {
   if (!ctx) return FQGPU_EARG;
   if (nbytes == 0) return FQGPU_OK;
@@ -159,14 +187,11 @@ int fqgpu_scan_device(fqgpu_ctx* ctx, const void* dptr, size_t nbytes) {
   CU_TRY(ctx, cudaEventRecord(e0, ctx->stream));
   const uint8_t* p = (const uint8_t*)dptr;
   size_t left = nbytes;
+  const u64 meta_records = ctx->shard_rank > 0 ? 0 : ctx->cfg.meta_records;
   while (left) {
     size_t n = left < kMaxLaunchBytes ? left : kMaxLaunchBytes;
-    const int spans = (int)fq::scan_span_count((u64)((uintptr_t)p & 15) + n, ctx->grid);
-    if (spans > ctx->span_hwm) ctx->span_hwm = spans;
-    CU_TRY(ctx, fq::launch_scan(p, n, ctx->d_desc, ctx->d_hdr, ctx->d_carry, ctx->d_pending, ctx->d_committed,
-                                ctx->d_shard, ctx->grid, ctx->shard_rank > 0 ? 0 : ctx->cfg.meta_records, ctx->stream,
-                                ctx->mstream, ctx->ev_fork, ctx->ev_join, (ctx->cfg.flags & FQGPU_F_CORE_ONLY) != 0));
-    ctx->launches++;
+    int rc = fqgpu_launch_scan(ctx, p, n, meta_records);
+    if (rc != FQGPU_OK) return rc;
     p += n;
     left -= n;
   }
@@ -280,14 +305,13 @@ extern "C" {
 int fqgpu_finish(fqgpu_ctx* ctx, fqgpu_stats* out) {
   if (!ctx || !out) return FQGPU_EARG;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
-  cudaEvent_t e0 = fqgpu_get_event(ctx), e1 = fqgpu_get_event(ctx);
-  CU_TRY(ctx, cudaEventRecord(e0, ctx->stream));
-  CU_TRY(ctx, fq::launch_reduce(ctx->d_committed, ctx->span_hwm, ctx->d_out, ctx->stream));
-  CU_TRY(ctx, cudaEventRecord(e1, ctx->stream));
-  ctx->timed.emplace_back(e0, e1);
-  CU_TRY(ctx, cudaMemcpyAsync(ctx->h_out, ctx->d_out, fq::BLOCK_WORDS * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+  static_assert(sizeof(fq::Carry) % sizeof(u64) == 0, "h_out layout");
+  u64* h_err = ctx->h_out + fq::BLOCK_WORDS + sizeof(fq::Carry) / sizeof(u64);
+  CU_TRY(ctx, cudaMemcpyAsync(ctx->h_out, ctx->d_acc, fq::BLOCK_WORDS * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
   CU_TRY(ctx, cudaMemcpyAsync(ctx->h_out + fq::BLOCK_WORDS, ctx->d_carry, sizeof(fq::Carry), cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaMemcpyAsync(h_err, ctx->d_ctl + fq::CTL_ERROR, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (*h_err) return fail(ctx, FQGPU_ECUDA, "fqgpu_finish: the scan kernel reported an internal consistency error");
   fq::Carry c;
   memcpy(&c, ctx->h_out + fq::BLOCK_WORDS, sizeof(c));
   fqgpu_assemble_stats(ctx->h_out, c, ctx->cfg.meta_records, out, (ctx->cfg.flags & FQGPU_F_CORE_ONLY) != 0);

@@ -14,12 +14,11 @@ size_t scan_smem_bytes();
 int scan_tile_bytes();
 int scan_threads();
 cudaError_t scan_configure();
-cudaError_t launch_reset(u64* committed, int nblocks, Carry* carry, cudaStream_t st);
-cudaError_t launch_scan(const void* ptr, size_t nbytes, SpanDesc* desc, LaunchHdr* hdr, Carry* carry,
-                        u64* pending, u64* committed, ShardInfo* shard, int max_spans, u64 meta_records, cudaStream_t st,
-                        cudaStream_t meta_stream, cudaEvent_t ev_fork, cudaEvent_t ev_join, bool core_only);
-cudaError_t launch_reduce(const u64* blocks, int nblocks, u64* out, cudaStream_t st);
-uint32_t scan_span_count(u64 bytes, int resident);
+cudaError_t launch_reset(u64* acc, Carry* carry, u64* ctl, cudaStream_t st);
+u64 scan_tiles(const void* ptr, size_t nbytes);
+cudaError_t launch_scan(const void* ptr, size_t nbytes, Carry* carry, ShardInfo* shard, u64* acc, u64* state, u64* ctl,
+                        uint32_t epoch, bool unknown_start, int resident, bool core_only, cudaStream_t st);
+cudaError_t launch_meta(const uint8_t* base, uint32_t lo0, u64 end, Carry* carry, u64 meta_records, cudaStream_t st);
 cudaError_t launch_synth_illumina(void* dptr, u64 first_byte, u64 nbytes, u64 seed, cudaStream_t st);
 cudaError_t synth_ont(void* dptr, size_t capacity, u64 first_record, u64 n_records, u64 seed, size_t* bytes_written,
                       cudaStream_t st);
@@ -27,8 +26,8 @@ cudaError_t synth_ont(void* dptr, size_t capacity, u64 first_record, u64 n_recor
 
 using fq::u64;
 
-// one launch = up to MAX_SPANS spans; a span stays below 2 GiB so its 32-bit shared-memory counters are exact
-static const size_t kMaxLaunchBytes = (size_t)fq::BASE_SPANS * ((size_t)2 << 30) - ((size_t)64 << 20);
+// one launch: the tile index is 32-bit and the look-back array (8 bytes per 32 KiB tile) is sized for the largest launch so far
+static const size_t kMaxLaunchBytes = (size_t)64 << 30;
 inline thread_local std::string g_create_error;
 
 struct StageBuf {
@@ -43,15 +42,14 @@ struct fqgpu_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t mstream = nullptr;                  // the fq-meta prefix kernel runs beside the scan
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  int grid = 0;
-  int span_hwm = fq::BASE_SPANS;  // most span blocks any launch of this context has used: reset / reduce cover [0, span_hwm)
-  u64* d_pending = nullptr;    // [MAX_SPANS] blocks of the launch in flight
-  u64* d_committed = nullptr;  // [MAX_SPANS] blocks accumulated since the last reset
+  int grid = 0;                // persistent CTAs of a scan launch (2 per SM)
+  u64* d_acc = nullptr;        // [BLOCK_WORDS] counter block accumulated since the last reset
+  u64* d_state = nullptr;      // look-back words of the scan launches (one per 32 KiB tile)
+  u64 state_cap = 0;           // ... capacity in tiles
+  u64* d_ctl = nullptr;        // [CTL_WORDS] ticket / done counters and launch scratch
+  uint32_t epoch = 0;          // epoch of the most recent launch (1..255)
   fq::Carry* d_carry = nullptr;
-  fq::SpanDesc* d_desc = nullptr;
-  fq::LaunchHdr* d_hdr = nullptr;
-  u64* d_out = nullptr;
-  u64* h_out = nullptr;  // pinned: reduced block followed by the carry
+  u64* h_out = nullptr;  // pinned: counter block followed by the carry
   std::vector<StageBuf> ring;
   // device landing buffers of the host paths: H2D of chunk k+1 (copy stream) overlaps the scan of
   // chunk k (compute stream)
