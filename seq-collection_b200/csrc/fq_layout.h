@@ -25,21 +25,40 @@ constexpr int OFF_QUAL_LEN_MAX = OFF_QUAL_LEN_MIN + 1;
 constexpr int BLOCK_WORDS = ((OFF_QUAL_LEN_MAX + 1 + 31) / 32) * 32;
 constexpr int N_SUM_WORDS = OFF_SEQ_LEN_MIN;  // words [0, N_SUM_WORDS) are sum-reduced
 
-constexpr int RESIDENT_CTAS = 296;         // persistent CTAs of a scan launch: 2 per SM on a 148-SM B200
+constexpr int RESIDENT_CTAS = 296;         // CTAs resident at once: 2 per SM on a 148-SM B200
+constexpr int SPAN_WAVES = 8;              // large launches are cut into up to this many spans per resident CTA
+constexpr int MAX_SPANS = RESIDENT_CTAS * SPAN_WAVES;
 
 // ---- launch control words (device, u64[CTL_WORDS]); zeroed by the reset kernel, left clean by every launch --------
 enum {
-  CTL_TICKET = 0,   // next tile to hand out
-  CTL_DONE,         // CTAs that have finished
-  CTL_TOTAL_T,      // newlines of the launch
-  CTL_OPEN_OUT,     // open-line bytes after the launch's last tile
+  CTL_DONE = 0,     // CTAs of the launch that have finished
+  CTL_REDO,         // spans whose guessed line phase was wrong (malformed input): the second pass redoes them
   CTL_FIRST_NL,     // shards with an unknown start: offset of the stream's first newline + 1 (0 = none in this launch)
-  CTL_HEAD,         // shards: HEAD_* flags of this launch | P0 << 8 is kept in CTL_HEAD_P0
+  CTL_HEAD,         // shards: HEAD_* flags of this launch
   CTL_HEAD_P0,      // shards: bytes of the detached head before this launch
-  CTL_ERROR,        // sticky: internal consistency check failed (item queue bound)
+  CTL_ERROR,        // sticky: an internal consistency check failed
   CTL_WORDS = 16
 };
 enum { HEAD_ACTIVE = 1u, HEAD_QUAL = 2u, HEAD_PENDING_CR = 4u };
+
+// One span = the run of whole lines one CTA scans in a launch: the lines that START inside its nominal byte range
+// (span 0 also owns the line that is open at the launch start).  The line phase at a span start is GUESSED from the
+// content (first '@' line whose line+2 starts with '+') so that no CTA ever waits for another; the CTA that exits
+// last verifies every guess against the exact line counts.
+enum { SPAN_OK = 0, SPAN_REDO = 1 };
+struct SpanDesc {
+  unsigned long long T;            // newlines of the span
+  unsigned long long start;        // offset of its first byte (relative to the launch base)
+  unsigned long long end_open;     // open-line bytes where the span stopped (meaningful when reached_end)
+  unsigned long long len_min[2], len_max[2];  // line-length extrema of the span ([0] seq, [1] qual), committed once the guess is verified
+  unsigned int guess;              // (lines before the span) mod 4 used by pass 0
+  unsigned int guess_valid;        // 0: the content gave no guess (the span is redone with the exact phase)
+  unsigned int nonempty;           // a line starts inside the span
+  unsigned int reached_end;        // the span ran to the end of the launch
+  unsigned int exact;              // exact (lines before the span) mod 4 (written by the last CTA)
+  unsigned int state;              // SPAN_*
+  unsigned int pad[2];
+};
 
 // ---- stream carry: device-resident state that makes consecutive scans one logical stream ----
 struct Carry {

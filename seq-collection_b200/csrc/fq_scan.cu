@@ -1,33 +1,42 @@
-// fq_scan.cu -- the FASTQ scanning hot path on sm_100a: ONE launch per buffer.
+// fq_scan.cu -- the FASTQ scanning hot path on sm_100a.
 //
 // Replaces the per-line loop of the reference (src/fq_count.nim:38-45: `for line in lines(stream)`,
 // i mod 4 classing, count("G")+count("C"), count("N"), line.len) with one pass over the bytes; the quality fold
 // of src/fq_meta.nim:245-246 is fq_meta.cu, beside it on a second stream.
 //
-// Persistent CTAs (2 per SM) take 32 KiB tiles from a ticket counter; a tile is brought into shared memory by a
-// 1-D TMA copy (cp.async.bulk + mbarrier, two stages: the copy of the next tile runs under the work on this one)
-// and goes through five phases, all warps together:
+// A launch cuts its byte range into SPANS, one CTA each (2 CTAs per SM resident; large launches get several spans
+// per resident CTA).  A span is the run of whole lines that START inside its nominal byte range: the CTA finds the
+// first line start at or after the range start itself (the first newline from there on) and runs past the range end
+// to the end of its last line, so no line is ever shared between CTAs and no CTA ever waits for another.  What a
+// span cannot know is the line PHASE (line number mod 4) of its first line: it is guessed from the content (the
+// first line that starts with '@' and whose line+2 starts with '+' is a header) and the CTA that exits last verifies
+// every guess against the exact newline counts of the spans before it; a span whose guess was wrong (malformed
+// input: the reference classes lines purely by their number) is redone by the second pass, which first takes the
+// wrong counts back.  Results are therefore exact on any input.
+//
+// Inside a span the CTA streams 32 KiB tiles through shared memory (1-D TMA, cp.async.bulk + mbarrier, two stages:
+// the copy of the next tile runs under the work on this one), all warps moving through the phases together:
 //
 //   A   boundary classification: coalesced 16-byte groups -> 16-bit '\n' masks (SWAR compare, IDP.4A movemask)
 //       -> the tile's newline bitmap in shared memory.
-//   B1  every thread owns 64 CONSECUTIVE bytes of the bitmap: popc, one block-wide prefix (newline count and
-//       position of the last newline) -> the tile total; warp 0 publishes it and walks back over the predecessor
-//       tiles' words (chained "decoupled look-back" prefix; a tile only ever waits for tiles whose ticket was
-//       taken earlier, i.e. that are running): exact line number (mod 256) and open-line length at the tile start.
-//       This is the tile-edge / chunk-edge record carry, resolved on the device.
-//   B2  every thread walks its four groups: a group without a newline gets a 16-bit descriptor (line class =
-//       line number mod 4, record parity, line position of its first byte); a group with newlines is cut into
-//       ITEMS (group, byte range, class, position, "ends its line") appended to a tile-wide queue.
-//   C   one lane per group: LDS.128, histogram of sequence / quality bytes by one IDP.4A (address) + one shared
+//   B   every thread owns 64 CONSECUTIVE bytes of the bitmap: popc, ONE block-wide prefix of the counts, then the
+//       thread stores the offsets of its own newlines at their exact slots of the tile's newline index nl[].
+//       The running (lines, open-line bytes) of the span is the tile-edge record carry.
+//   L   line tasks, one thread per sequence / quality line with bytes in the tile (classes from the line number):
+//       the line's first / last ragged 16-byte groups are counted right here under byte masks, its aligned full
+//       groups are left to the workers as one record (first group, groups, line position); line-length tables and
+//       the '\r' rule at the line's newline.
+//   W   workers: slot x of a class maps to (line x / K, group x % K), K = the tile's largest group count, so every
+//       lane takes one aligned 16-byte group (LDS.128) of some line: histogram by one IDP.4A (address) + one shared
 //       atomic (ATOMS.POPC.INC, which merges equal addresses: un-striped 256-bin tables) per byte; per-position
-//       quality sums as eight packed 16-bit-pair atomics into a bank-skewed table (even / odd position tables,
-//       no alignment shifts).
-//   D   the item queue, one lane per item: masked histogram / per-position sums, line lengths, the '\r' rule.
+//       quality sums as eight packed 16-bit-pair atomics into a bank-skewed table (even / odd position tables, no
+//       alignment shifts).  Lines of more than 63 groups (long reads) are taken by all threads together.
 //
 // Counter tables live in shared memory for the life of the CTA and are added to the context's block by 64-bit
-// atomics at CTA exit (K3); the CTA that exits last advances the stream carry (fq::Carry).  Every input byte is
-// read from HBM once.  Line semantics are Nim's streams.lines: split at '\n', drop one '\r' directly before it;
-// the trailing unterminated line is accounted by the host from fq::Carry at finish().
+// atomics (K3); the CTA that exits last advances the stream carry (fq::Carry): chunk-edge carry on the device.
+// Every input byte is read from HBM once (a span reads a few bytes of its successor's range to finish its last
+// line).  Line semantics are Nim's streams.lines: split at '\n', drop one '\r' directly before it; the trailing
+// unterminated line is accounted by the host from fq::Carry at finish().
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -45,9 +54,12 @@ constexpr int GPT = 4;                        // 16-byte groups per thread and t
 constexpr int NG = THREADS * GPT;             // groups per tile
 constexpr int TILE = NG * 16;                 // 32 KiB
 constexpr int NSTAGE = 2;
-constexpr int QCAP = 2048;                    // item queue; tiles with more newlines take the byte walker
-constexpr uint32_t QPOS_MAX = 1023;           // line positions saturate here (>= POS_BINS is the overflow bin anyway)
-constexpr int OPEN_CLIP = 1 << 30;
+constexpr int NL_CAP = 2048;                  // newline index; tiles with more newlines take the byte walker
+constexpr int REC_CAP = NL_CAP / 4 + 8;       // lines of one class with bytes in a tile
+constexpr int KMAX = 63;                      // lines with more full groups are "long"
+constexpr int LONG_CAP = TILE / (16 * (KMAX + 1)) + 2;
+constexpr int OPEN_CLIP = 1 << 30;            // line positions saturate here (>= POS_BINS is the overflow bin anyway)
+constexpr int MIN_SPAN_TILES = 32;            // spans are at least this long (1 MiB)
 // Per-position quality sums, 16-bit pairs.  Q = position + 16.  Even Q: pair A = Q >> 1 of the EVEN table holds
 // (Q, Q+1); odd Q: pair A = (Q+1) >> 1 of the ODD table holds (Q, Q+1).  Pair A lives in cell (r, c) with
 // 8 c + r = A, r < 8, at word r * PT_STRIDE + c; a group adds its eight pairs at immediate offsets PT_STRIDE * i,
@@ -62,39 +74,45 @@ struct ScanArgs {
   const uint8_t* base;  // 16-byte aligned; the launch covers bytes [lo0, end) relative to base
   uint32_t lo0;
   u64 end;
-  uint32_t ntiles;
+  uint32_t ntiles, tps, nspans;  // tiles, tiles per span (nominal), spans
   Carry* carry;
   ShardInfo* shard;  // detached head of a multi-GPU shard (rank > 0)
   u64* acc;          // [BLOCK_WORDS] the context's counter block
-  u64* state;        // [>= ntiles] look-back words
+  SpanDesc* desc;    // [nspans]
   u64* ctl;          // [CTL_WORDS]
-  uint32_t epoch;    // 1..255, changes with every launch: stale look-back words read as "nothing yet"
   uint32_t unknown;  // shard with an unknown start (fqgpu_shard_begin, rank > 0, not rescanned)
-  uint32_t dbg;      // 1: EXPERIMENT -- analytic prefix of the synthetic Illumina stream instead of the look-back
+  uint32_t pass;     // 0: every span under its guessed phase; 1: only the spans whose guess was wrong, exactly
 };
-
-// look-back word: epoch << 56 | flag << 54 | payload
-//   flag 1 (tile alone):  T << 18 | tail      T = newlines of the tile, tail = bytes after the last one (T == 0: tile length)
-//   flag 2 (inclusive):   seen << 53 | cnt << 45 | open     cnt = lines so far mod 256, open = open-line bytes, seen = any newline so far
-constexpr u64 ST_AGG = 1ull << 54, ST_INC = 2ull << 54;
-constexpr u64 OPEN_MASK = (1ull << 45) - 1;
 
 struct Sel { uint32_t h0, h1, h2, h3; };  // IDP.4A selectors 4 << 8k: histogram address = byte_k * 4 + base
 
-struct TileIn {
+// The span's running state (shared memory; advanced by thread 0 at the end of every tile).
+struct Run {
   u64 open;          // bytes of the open line before the tile
-  u64 open_out;      // ... after it
-  uint32_t cnt;      // lines before the tile (mod 256; shards with an unknown start: under the hypothesis)
+  u64 totalT;        // newlines of the span so far
+  u64 proc_end;      // offset behind the last byte processed
+  uint32_t cnt;      // lines before the tile (low bits; shards with an unknown start: under the hypothesis)
   uint32_t seen;     // a newline has been seen in the stream before the tile
-  uint32_t T;        // newlines of the tile
   int prev_byte;     // byte before the tile's first valid byte (0x100: none)
+  uint32_t prev_counted;  // ... and it was scanned by this launch (a '\r' there has been counted)
+  uint32_t stop;     // the span ends with this tile
+};
+struct TileInfo {
+  uint32_t T;        // newlines of the tile
+  uint32_t first;    // extension tiles: offset of the first newline
+  uint32_t K[2];     // most full groups of a (not long) line, per class
+  uint32_t nlong;
+  uint32_t nlines[2];
+  uint32_t last1;    // walker tiles: offset of the last newline + 1
 };
 
 struct __align__(128) Smem {
   uint8_t buf[NSTAGE][TILE];
-  u64 queue[QCAP];
   uint16_t bitmap[NG];               // bit b of entry g: byte 16 g + b is '\n'
-  uint16_t ginfo[NG];                // (line number & 7) | position << 3 for groups without a newline inside counted lines' reach; 0 = nothing to do
+  uint16_t nl[NL_CAP + 8];           // offsets of the tile's newlines, ascending
+  uint32_t rec[2][REC_CAP];          // per class and line: first full group | full groups << 11 | position << 17 | parity << 27
+  u64 longl[LONG_CAP];               // lines of more than KMAX full groups: first | groups << 11 | class << 23 | parity << 24 | position << 32
+  uint32_t inv[KMAX + 1];            // ceil(2^32 / K)
   uint32_t hist[2][256];             // [0] sequence, [1] quality
   uint32_t ptab[PT_WORDS];
   uint32_t pos32[POS_BINS + 2];      // per-position sums, 32-bit (second level of ptab; generic paths)
@@ -102,16 +120,17 @@ struct __align__(128) Smem {
   uint32_t qual_len[POS_BINS + 2];
   uint32_t seq_log2[LOG2_BINS];
   uint4 masks[17];                   // masks[n]: 0xFF in the first n bytes of a group
-  u64 wtot[NWARPS];                  // per warp: newlines << 32 | (offset of its last newline + 1)
+  uint32_t wtot[NWARPS];             // newlines per warp, then their exclusive prefix
+  int wlast[NWARPS];                 // walker tiles: offset of the last newline of the warps before, + 1
   u64 full_bar[NSTAGE];
   u64 big_min[2], big_max[2];        // line lengths >= 2^32
   u64 over;                          // quality bytes at positions >= POS_BINS
   uint32_t len_min[2], len_max[2];   // [0] seq, [1] qual
   uint32_t junk[2];                  // masked bytes counted in bin 0
   uint32_t ksel[4];
-  uint32_t tile[2];
-  uint32_t nitems, pt_lines, hiflag, bytes_since_flush;
-  TileIn in;
+  uint32_t pt_lines, hiflag, bytes_since_flush, flag;
+  Run run;
+  TileInfo ti;
 };
 static_assert(sizeof(Smem) <= 115712, "two CTAs per SM");
 
@@ -176,8 +195,10 @@ __device__ __forceinline__ void flush_ptab(Smem& sm, int tid) {
   for (int i = tid; i < PT_WORDS; i += THREADS) sm.ptab[i] = 0;
 }
 
-// Everything the CTA holds in shared memory -> the context's block (64-bit atomics), tables cleared.
-__device__ __noinline__ void flush_all(Smem& sm, u64* acc, int tid, u64& over) {
+
+// Everything the CTA holds in the 32-bit tables -> the context's block (64-bit atomics; sign < 0 takes the counts
+// back: second pass), tables cleared.  The line-length extrema stay in shared memory.
+__device__ __noinline__ void flush_tables(Smem& sm, u64* acc, int tid, u64& over, int sign) {
   __syncthreads();
   flush_ptab(sm, tid);
   if (over) { atomicAdd(&sm.over, over); over = 0; }
@@ -185,33 +206,28 @@ __device__ __noinline__ void flush_all(Smem& sm, u64* acc, int tid, u64& over) {
   for (int i = tid; i < 512; i += THREADS) {
     uint32_t v = (&sm.hist[0][0])[i];
     if ((i & 255) == 0) v -= sm.junk[i >> 8];  // masked bytes were counted in bin 0
-    if (v) { atomicAdd(&acc[OFF_HIST_SEQ + i], (u64)v); }
+    if (v) atomicAdd(&acc[OFF_HIST_SEQ + i], sign > 0 ? (u64)v : 0ull - (u64)v);
     (&sm.hist[0][0])[i] = 0;
   }
   for (int i = tid; i <= POS_BINS; i += THREADS) {
     uint32_t v = sm.pos32[i];
-    if (v) { atomicAdd(&acc[OFF_POS_SUM + i], (u64)v); sm.pos32[i] = 0; }
+    if (v) { atomicAdd(&acc[OFF_POS_SUM + i], sign > 0 ? (u64)v : 0ull - (u64)v); sm.pos32[i] = 0; }
     v = sm.seq_len[i];
-    if (v) { atomicAdd(&acc[OFF_SEQ_LEN + i], (u64)v); sm.seq_len[i] = 0; }
+    if (v) { atomicAdd(&acc[OFF_SEQ_LEN + i], sign > 0 ? (u64)v : 0ull - (u64)v); sm.seq_len[i] = 0; }
     v = sm.qual_len[i];
-    if (v) { atomicAdd(&acc[OFF_QUAL_LEN + i], (u64)v); sm.qual_len[i] = 0; }
+    if (v) { atomicAdd(&acc[OFF_QUAL_LEN + i], sign > 0 ? (u64)v : 0ull - (u64)v); sm.qual_len[i] = 0; }
   }
-  if (tid < LOG2_BINS) { const uint32_t v = sm.seq_log2[tid]; if (v) { atomicAdd(&acc[OFF_SEQ_LOG2 + tid], (u64)v); sm.seq_log2[tid] = 0; } }
+  if (tid < LOG2_BINS) {
+    const uint32_t v = sm.seq_log2[tid];
+    if (v) { atomicAdd(&acc[OFF_SEQ_LOG2 + tid], sign > 0 ? (u64)v : 0ull - (u64)v); sm.seq_log2[tid] = 0; }
+  }
   __syncthreads();
   if (tid == 0) {
-    if (sm.over) { atomicAdd(&acc[OFF_POS_SUM + POS_BINS], sm.over); sm.over = 0; }
+    if (sm.over) { atomicAdd(&acc[OFF_POS_SUM + POS_BINS], sign > 0 ? sm.over : 0ull - sm.over); sm.over = 0; }
     sm.junk[0] = sm.junk[1] = 0;
     sm.bytes_since_flush = 0;
     sm.pt_lines = 0;
     sm.hiflag = 0;
-    for (int q = 0; q < 2; q++) {
-      u64 mn = sm.len_min[q] != 0xFFFFFFFFu ? (u64)sm.len_min[q] : ~0ull, mx = sm.len_max[q];
-      if (sm.big_min[q] < mn) mn = sm.big_min[q];
-      if (sm.big_max[q] > mx) mx = sm.big_max[q];
-      if (mn != ~0ull) atomicMin(&acc[q ? OFF_QUAL_LEN_MIN : OFF_SEQ_LEN_MIN], mn);
-      if (mx) atomicMax(&acc[q ? OFF_QUAL_LEN_MAX : OFF_SEQ_LEN_MAX], mx);
-      sm.len_min[q] = 0xFFFFFFFFu; sm.len_max[q] = 0; sm.big_min[q] = ~0ull; sm.big_max[q] = 0;
-    }
   }
   __syncthreads();
 }
@@ -220,20 +236,18 @@ __device__ __noinline__ void flush_all(Smem& sm, u64* acc, int tid, u64& over) {
 // tables.  ql: 0 sequence, 1 quality.  fn: the line started before the tile.
 template <bool CORE>
 __device__ __forceinline__ void line_end(Smem& sm, const ScanArgs& a, const TileCtx& t, int off, u64 rawlen, bool fn, uint32_t ql) {
-  const int prev = off > t.vlo ? (int)lds8(t.buf_s + (uint32_t)off - 1u) : sm.in.prev_byte;
+  const int prev = off > t.vlo ? (int)lds8(t.buf_s + (uint32_t)off - 1u) : sm.run.prev_byte;
   const u64 cr = (rawlen > 0 && prev == '\r') ? 1 : 0;
-  if (cr) {  // the '\r' was counted as content where it stands: take it back
-    const uint32_t p = (rawlen - 1) < (u64)POS_BINS ? (uint32_t)(rawlen - 1) : (uint32_t)POS_BINS;
-    if (off > t.vlo) {
-      atomicSub(&sm.hist[ql]['\r'], 1u);
-      if (!CORE && ql) { if (p < (uint32_t)POS_BINS) atomicSub(&sm.pos32[p], (uint32_t)'\r'); else atomicAdd(&sm.over, (u64)(0ull - '\r')); }
-    } else if (t.tile > 0) {  // it is the last byte of the previous tile: another CTA counted it
-      atomicAdd(&a.acc[(ql ? OFF_HIST_QUAL : OFF_HIST_SEQ) + '\r'], ~0ull);
-      if (!CORE && ql) atomicAdd(&a.acc[OFF_POS_SUM + p], 0ull - '\r');
-    }  // else: the last byte of the previous launch, never counted (its fate was left to this launch)
+  if (cr && (off > t.vlo || sm.run.prev_counted)) {  // the '\r' was counted as content where it stands: take it back
+    // (not counted: the last byte of the previous launch, whose fate was left to this one)
+    atomicSub(&sm.hist[ql]['\r'], 1u);
+    if (!CORE && ql) {
+      if (rawlen - 1 < (u64)POS_BINS) atomicSub(&sm.pos32[(uint32_t)(rawlen - 1)], (uint32_t)'\r');
+      else atomicAdd(&sm.over, 0ull - '\r');
+    }
   }
   const u64 len = rawlen - cr;
-  if (a.unknown && fn && !sm.in.seen) {  // the shard's first line: its length is stitched by the combine step
+  if (a.unknown && fn && !sm.run.seen) {  // the shard's first line: its length is stitched by the combine step
     a.shard->head_len = rawlen;
     a.shard->head_cr = (unsigned)cr;
     a.ctl[CTL_FIRST_NL] = t.toff + (u64)off + 1;
@@ -272,71 +286,27 @@ __device__ __noinline__ uint32_t phase_a_edge(uint32_t buf_s, uint32_t bm_s, int
   return hib;
 }
 
-// Appends an item to the tile's queue.
-//   lo32: group | lo << 11 | hi << 16 | quality << 21 | ends-its-line << 22 | started-before-the-tile << 23 | parity << 24
-//   hi32: line position of byte lo (saturated at OPEN_CLIP)
-__device__ __forceinline__ void push_item(Smem& sm, const ScanArgs& a, uint32_t e0, uint32_t pos) {
-  const uint32_t slot = atomicAdd(&sm.nitems, 1u);
-  if (slot < (uint32_t)QCAP) sm.queue[slot] = (u64)e0 | ((u64)pos << 32);
-  else a.ctl[CTL_ERROR] = 1;  // cannot happen: the caller checked T + 4 <= QCAP
-}
-
-// Phase B2 for one thread: descriptors of its four groups, items for the groups with newlines.
-// cnt = lines before the run (low bits), lc = newlines of the tile before the run, last = tile offset of the last
-// newline before the run (negative: the line started before the tile).
-template <bool CORE, bool EDGE>
-__device__ __forceinline__ void phase_b2(Smem& sm, const ScanArgs& a, const TileCtx& t, uint32_t gi_s, int tid, uint32_t wl, uint32_t wh,
-                                         uint32_t cnt, uint32_t lc, int last) {
-  u64 gpack = 0;
-#pragma unroll
-  for (int k = 0; k < GPT; k++) {
-    const uint32_t m = ((k < 2 ? wl : wh) >> (16 * (k & 1))) & 0xFFFFu;
-    const int o = 64 * tid + 16 * k;
-    int lo = 0, hi_end = 16;
-    bool ragged = false;
-    if (EDGE) {
-      lo = t.vlo - o; lo = lo < 0 ? 0 : lo;
-      hi_end = t.vhi - o; hi_end = hi_end > 16 ? 16 : hi_end;
-      if (lo >= hi_end) continue;  // nothing valid in this group (its mask is zero)
-      ragged = lo > 0 || hi_end < 16;
-    }
-    if (m == 0 && !ragged) {
-      uint32_t q = (uint32_t)(o - last - 1);
-      q = q < QPOS_MAX ? q : QPOS_MAX;
-      gpack |= (u64)((cnt & 7u) | (q << 3)) << (16 * k);
-    } else {
-      uint32_t mm = m;
-      int posi = o + lo - last - 1;
-      uint32_t pos = (uint32_t)(posi < OPEN_CLIP ? posi : OPEN_CLIP);
-      const uint32_t g = (uint32_t)(GPT * tid + k);
-      for (;;) {
-        const int hi = mm ? __ffs(mm) - 1 : hi_end;
-        const uint32_t cls = cnt & 3u;
-        const bool counted = CORE ? cls == 1u : (cls & 1u) != 0;
-        if (counted && (mm || hi > lo))
-          push_item(sm, a, g | ((uint32_t)lo << 11) | ((uint32_t)hi << 16) | ((cls >> 1) << 21) | (mm ? 1u << 22 : 0u) | (lc == 0 ? 1u << 23 : 0u) |
-                               (((cnt >> 2) & 1u) << 24), pos);
-        if (!mm) break;
-        mm &= mm - 1;
-        cnt++; lc++;
-        last = o + hi;
-        lo = hi + 1;
-        pos = 0;
-      }
-    }
-  }
-  sts64(gi_s + 8u * (uint32_t)tid, gpack);
-}
+// The byte walker: tiles with more newlines than the index holds.  Every thread takes its own 64 bytes one at a time
+// (exact for any content); '\r' is counted where it stands and taken back by line_end like everywhere else.
+// c / inc: newlines of this thread's run and their inclusive prefix inside the warp; sm.wtot holds the exclusive
+// prefix over the warps.
 template <bool CORE>
-__device__ __noinline__ void phase_b2_edge(Smem& sm, const ScanArgs& a, const TileCtx& t, uint32_t gi_s, int tid, uint32_t wl, uint32_t wh,
-                                           uint32_t cnt, uint32_t lc, int last) {
-  phase_b2<CORE, true>(sm, a, t, gi_s, tid, wl, wh, cnt, lc, last);
-}
-
-// The byte walker: tiles with too many newlines for the item queue.  Every thread takes its own 64 bytes one at
-// a time (exact for any content); '\r' is counted where it stands and taken back by line_end like everywhere else.
-template <bool CORE>
-__device__ __noinline__ void phase_walk(Smem& sm, const ScanArgs& a, const TileCtx& t, int tid, uint32_t cnt, uint32_t lc, int last) {
+__device__ __noinline__ void phase_walk(Smem& sm, const ScanArgs& a, const TileCtx& t, int tid, u64 w64, uint32_t c, uint32_t inc) {
+  const int lane = tid & 31, warp = tid >> 5;
+  // offset of the last newline before this thread's run: inside the warp, else of the warps before, else none
+  const uint32_t wl = (uint32_t)w64, wh = (uint32_t)(w64 >> 32);
+  const int mylast = 64 * tid + (wh ? 63 - __clz(wh) : 31 - __clz(wl));
+  const uint32_t hasb = __ballot_sync(0xffffffffu, c != 0);
+  const uint32_t lower = hasb & lanemask_lt();
+  const int lastW = __shfl_sync(0xffffffffu, mylast, (31 - __clz(lower)) & 31);
+  const int warp_last = __shfl_sync(0xffffffffu, mylast, (31 - __clz(hasb)) & 31);
+  if (lane == 0) sm.wlast[warp] = hasb ? warp_last + 1 : 0;
+  __syncthreads();
+  int last = -1;
+  if (lower) last = lastW;
+  else for (int w = warp - 1; w >= 0; w--) if (sm.wlast[w]) { last = sm.wlast[w] - 1; break; }
+  uint32_t lc = sm.wtot[warp] + inc - c;
+  uint32_t cnt = sm.run.cnt + lc;
   u64 over = 0;
   for (int x = 0; x < 16 * GPT; x++) {
     const int off = 16 * GPT * tid + x;
@@ -344,7 +314,7 @@ __device__ __noinline__ void phase_walk(Smem& sm, const ScanArgs& a, const TileC
     const uint32_t b = lds8(t.buf_s + (uint32_t)off);
     const uint32_t cls = cnt & 3u;
     const bool counted = CORE ? cls == 1u : (cls & 1u) != 0;
-    const u64 pos = lc == 0 ? sm.in.open + (u64)(off - t.vlo) : (u64)(off - last - 1);
+    const u64 pos = lc == 0 ? sm.run.open + (u64)(off - t.vlo) : (u64)(off - last - 1);
     if (b == '\n') {
       if (counted) line_end<CORE>(sm, a, t, off, pos, lc == 0, cls >> 1);
       cnt++; lc++;
@@ -358,27 +328,39 @@ __device__ __noinline__ void phase_walk(Smem& sm, const ScanArgs& a, const TileC
     }
   }
   if (over) atomicAdd(&sm.over, over);
+  // the tile's last newline, for the running open-line length: kept where the index would have it
+  __syncthreads();
+  if (tid == 0) {
+    int tl = 0;
+    for (int w = NWARPS - 1; w >= 0; w--) if (sm.wlast[w]) { tl = sm.wlast[w]; break; }
+    sm.ti.last1 = (uint32_t)tl;
+  }
 }
 
-// resync: guess the line phase at the start of a shard whose predecessor is on another GPU.  Launch-relative line j
-// (j >= 1) starts after the launch's j-th newline; the first j whose line starts with '@' while line j+2 starts with
-// '+' is a header, so (lines before the launch) = -j (mod 4).  For valid 4-line FASTQ this is unambiguous (a quality
-// line starting with '@' is followed two lines later by a sequence line).  One warp; returns 0..3, or 4 = no guess.
+// Where a span starts and the line phase there.  The span owns the lines that start inside [N, Nend): its first byte
+// is the successor of the first newline at offset >= N - 1.  Launch-relative: line j (j >= 1) starts after the j-th
+// newline found; the first j whose line starts with '@' while line j+2 starts with '+' is a header, so the line at
+// the span start has phase (1 - j) mod 4.  For valid 4-line FASTQ this is unambiguous (a quality line starting with
+// '@' is followed two lines later by a sequence line, which cannot start with '+').  One warp.
+// Returns the start offset (~0: no line starts inside the span); guess 0..3 or 4 = none.
 constexpr int RESYNC_LINES = 40;
 constexpr u64 RESYNC_BYTES = 4ull << 20;
-__device__ __noinline__ uint32_t resync_guess(const ScanArgs& a, int lane) {
-  const u64 stop = RESYNC_BYTES < a.end ? RESYNC_BYTES : a.end;
+__device__ __noinline__ u64 resync_span(const ScanArgs& a, u64 N, u64 Nend, int lane, uint32_t& guess_out) {
   uint32_t first[RESYNC_LINES + 1];
   int nlines = 0;
   uint32_t guess = 4;
-  for (u64 o = 0; o < stop && guess == 4 && nlines < RESYNC_LINES; o += 512) {
+  u64 start = ~0ull;
+  const u64 o0 = (N - 1) & ~15ull;
+  for (u64 o = o0; o < a.end && guess == 4 && nlines < RESYNC_LINES; o += 512) {
+    if (start == ~0ull && o >= Nend) break;                     // no line starts inside the span
+    if (start != ~0ull && o > start + RESYNC_BYTES) break;      // no guess within reach
     const u64 g = o + (u64)lane * 16;
     uint32_t m = 0;
     if (g < a.end) {
       const uint4 v = *reinterpret_cast<const uint4*>(a.base + g);
       m = nl_mask16(v);
       if (g + 16 > a.end) m &= (1u << (a.end - g)) - 1u;
-      if (g < (u64)a.lo0) m &= ~((1u << min((u64)16, (u64)a.lo0 - g)) - 1u);
+      if (g < N - 1) m &= ~((1u << min((u64)16, N - 1 - g)) - 1u);
     }
     uint32_t any = __ballot_sync(0xffffffffu, m != 0);
     while (any && nlines < RESYNC_LINES) {
@@ -388,18 +370,32 @@ __device__ __noinline__ uint32_t resync_guess(const ScanArgs& a, int lane) {
       while (mm && nlines < RESYNC_LINES) {
         const int k = __ffs(mm) - 1;
         mm &= mm - 1;
-        const u64 start = o + (u64)src * 16 + (u64)k + 1;  // line starts after this newline
+        const u64 ls = o + (u64)src * 16 + (u64)k + 1;  // a line starts after this newline
+        if (nlines == 0) {
+          if (ls >= Nend || ls >= a.end) { guess_out = 4; return ~0ull; }
+          start = ls;
+        }
         nlines++;
-        first[nlines] = start < a.end ? (uint32_t)a.base[start] : 0x100u;
+        first[nlines] = ls < a.end ? (uint32_t)a.base[ls] : 0x100u;
         if (nlines >= 3 && first[nlines - 2] == '@' && first[nlines] == '+') {
-          guess = (uint32_t)((4 - ((nlines - 2) & 3)) & 3);
+          guess = (uint32_t)((1 - (nlines - 2)) & 3);
           break;
         }
       }
       if (guess != 4) break;
     }
   }
-  return guess;
+  guess_out = guess;
+  return start;
+}
+
+// The guess at the start of a LAUNCH whose predecessor is on another GPU (shards with an unknown start): the phase of
+// the line that contains the launch's first byte.
+__device__ __noinline__ uint32_t resync_launch(const ScanArgs& a, int lane) {
+  uint32_t g;
+  const u64 start = resync_span(a, (u64)a.lo0 + 1, a.end, lane, g);  // first newline at or after the first byte
+  (void)start;
+  return g < 4 ? (g - 1u) & 3u : 4u;  // the line before the first line start
 }
 
 // The detached head of a shard with an unknown start (the bytes before the stream's first newline): the scan has
@@ -407,12 +403,12 @@ __device__ __noinline__ uint32_t resync_guess(const ScanArgs& a, int lane) {
 // ShardInfo::head_pos, which fqgpu_shard_combine shifts by the bytes the line had on the previous ranks.
 // Run by the CTA that exits last.
 __device__ __noinline__ void detach_head(const ScanArgs& a, int tid) {
-  const u64 fl = a.ctl[CTL_HEAD];
+  const u64 fl = ld_relaxed_gpu(a.ctl + CTL_HEAD);
   if (!(fl & HEAD_ACTIVE) || !(fl & HEAD_QUAL)) return;
-  const u64 P0 = a.ctl[CTL_HEAD_P0];
-  const u64 fnl = a.ctl[CTL_FIRST_NL];                  // offset of the first newline + 1, 0 = none
-  u64 ve = fnl ? fnl - 1 : a.end;                       // content end
-  if (ve > (u64)a.lo0 && a.base[ve - 1] == '\r') ve--;  // dropped before the newline / left to the next launch at the end
+  const u64 P0 = ld_relaxed_gpu(a.ctl + CTL_HEAD_P0);
+  const u64 fnl = ld_relaxed_gpu(a.ctl + CTL_FIRST_NL);  // offset of the first newline + 1, 0 = none
+  u64 ve = fnl ? fnl - 1 : a.end;                        // content end
+  if (ve > (u64)a.lo0 && a.base[ve - 1] == '\r') ve--;   // dropped before the newline / left to the next launch at the end
   for (u64 o = (u64)a.lo0 + tid; o < ve; o += THREADS) {
     const u64 b = a.base[o], p = P0 + (o - a.lo0);
     const u64 bin = p < (u64)POS_BINS ? p : (u64)POS_BINS;
@@ -426,102 +422,313 @@ __device__ __noinline__ void detach_head(const ScanArgs& a, int tid) {
   }
 }
 
-__device__ __forceinline__ u64 warp_sum_u64(u64 v) {
+// Bytes [lo, hi) of group g belong to a counted line; posLo = line position of byte lo.
+template <bool CORE>
+__device__ __forceinline__ void masked_group(Smem& sm, const Sel& ksel, const TileCtx& t, uint32_t hist_s, uint32_t ptab_s, uint32_t masks_s,
+                                             uint32_t g, uint32_t lo, uint32_t hi, uint32_t posLo, uint32_t ql, uint32_t par, bool dense, u64& over) {
+  const uint32_t ga = t.buf_s + 16u * g;
+  uint4 v = lds128(ga);
+  const uint4 ml = lds128(masks_s + 16u * lo), mh = lds128(masks_s + 16u * hi);
+  v.x &= mh.x & ~ml.x; v.y &= mh.y & ~ml.y; v.z &= mh.z & ~ml.z; v.w &= mh.w & ~ml.w;
+  hist16(ksel, v, hist_s + (ql << 10));
+  atomicAdd(&sm.junk[ql], 16u - (hi - lo));
+  if (!CORE && ql) pos16(sm, v, ga, ptab_s, posLo + 16u - lo, lo, hi, par, dense, over);
+}
+
+// One span under the line phase `cnt0` at its first byte `start` (open0 bytes of that line lie before it).
+// par_bits: mbarrier parities of the two stages (kept across calls).
+template <bool CORE>
+__device__ __forceinline__ void run_span(Smem& sm, const ScanArgs& a, const Sel& ksel, uint32_t sm0, int tid, u64 start, uint32_t t1,
+                                         uint32_t& par_bits, u64& over, int sign) {
+  const int lane = tid & 31, warp = tid >> 5;
+  const uint32_t buf0_s = sm0 + (uint32_t)offsetof(Smem, buf);
+  const uint32_t bar0_s = sm0 + (uint32_t)offsetof(Smem, full_bar);
+  const uint32_t bm_s = sm0 + (uint32_t)offsetof(Smem, bitmap);
+  const uint32_t nl_s = sm0 + (uint32_t)offsetof(Smem, nl);
+  const uint32_t hist_s = sm0 + (uint32_t)offsetof(Smem, hist);
+  const uint32_t ptab_s = sm0 + (uint32_t)offsetof(Smem, ptab);
+  const uint32_t masks_s = sm0 + (uint32_t)offsetof(Smem, masks);
+  const uint32_t rec_s = sm0 + (uint32_t)offsetof(Smem, rec);
+  const uint32_t t_first = (uint32_t)(start / TILE);
+  auto tile_bytes = [&](uint32_t tile) -> uint32_t {
+    const u64 toff = (u64)tile * TILE;
+    return (uint32_t)((((a.end - toff) < (u64)TILE ? (a.end - toff) : (u64)TILE) + 15) & ~15ull);
+  };
+  int stage = 0;
+  if (tid == 0) {
+    mbar_expect_tx(bar0_s, tile_bytes(t_first));
+    tma_load_1d(buf0_s, a.base + (u64)t_first * TILE, tile_bytes(t_first), bar0_s);
+  }
+  for (uint32_t tile = t_first;; tile++, stage ^= 1) {
+    TileCtx t;
+    t.tile = tile;
+    t.toff = (u64)tile * TILE;
+    t.vlo = tile == t_first ? (int)(start - t.toff) : 0;
+    t.vhi = (a.end - t.toff) < (u64)TILE ? (int)(a.end - t.toff) : TILE;
+    t.buf_s = buf0_s + (uint32_t)stage * TILE;
+    const bool ext = tile >= t1;   // beyond the span's nominal range: only up to the first newline
+    const bool have_next = tile + 1 < a.ntiles;
+    if (tid == 0 && have_next) {  // the copy of the next tile into the other stage (free since the end of the last iteration)
+      mbar_expect_tx(bar0_s + 8u * (stage ^ 1), tile_bytes(tile + 1));
+      tma_load_1d(buf0_s + (uint32_t)(stage ^ 1) * TILE, a.base + t.toff + TILE, tile_bytes(tile + 1), bar0_s + 8u * (stage ^ 1));
+    }
+    mbar_wait(bar0_s + 8u * stage, (par_bits >> stage) & 1u);
+    par_bits ^= 1u << stage;
+
+    u64 w64;
+    uint32_t c, inc, T;
+#pragma unroll 1
+    for (int round = 0;; round++) {
+      // ---- A: newline masks of the tile's groups -> bitmap ----
+      if (t.vlo == 0 && t.vhi == TILE) {
+        uint4 v[GPT];
 #pragma unroll
-  for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        for (int k = 0; k < GPT; k++) v[k] = lds128(t.buf_s + 16u * (uint32_t)(k * THREADS + tid));
+        uint32_t hib = 0;
+#pragma unroll
+        for (int k = 0; k < GPT; k++) {
+          hib |= (v[k].x | v[k].y) | (v[k].z | v[k].w);
+          sts16(bm_s + 2u * (uint32_t)(k * THREADS + tid), nl_mask16_ascii(v[k]));
+        }
+        if (hib & 0x80808080u) { phase_a_redo(t.buf_s, bm_s, tid); sm.hiflag = 1; }  // the short compare is exact only for bytes < 0x80
+      } else {
+        if (phase_a_edge(t.buf_s, bm_s, t.vlo, t.vhi, tid) & 0x80808080u) sm.hiflag = 1;
+      }
+      __syncthreads();
+      // ---- B: this thread's 64 consecutive bytes of the bitmap; block-wide prefix of the newline counts ----
+      w64 = lds64(bm_s + 8u * (uint32_t)tid);
+      c = (uint32_t)__popcll(w64);
+      inc = warp_incl_scan(c, lane);
+      if (lane == 31) sm.wtot[warp] = inc;
+      __syncthreads();
+      if (warp == 0) {
+        const uint32_t e = lane < NWARPS ? sm.wtot[lane] : 0u;
+        const uint32_t einc = warp_incl_scan(e, lane);
+        if (lane < NWARPS) sm.wtot[lane] = einc - e;
+        if (lane == NWARPS - 1) { sm.ti.T = einc; sm.ti.K[0] = sm.ti.K[1] = 0; sm.ti.nlong = 0; }
+        if (ext && lane == 0) {  // offset of the tile's first newline (rare path: one thread walks the bitmap)
+          uint32_t f = 0xFFFFFFFFu;
+          for (int i = 0; i < NG / 4; i++) { const u64 w = reinterpret_cast<const u64*>(sm.bitmap)[i]; if (w) { f = 64u * i + (uint32_t)__ffsll((long long)w) - 1u; break; } }
+          sm.ti.first = f;
+        }
+      }
+      __syncthreads();
+      T = sm.ti.T;
+      if (!ext || T == 0 || round == 1 || (int)sm.ti.first + 1 >= t.vhi) break;
+      t.vhi = (int)sm.ti.first + 1;  // the span ends with this newline: classify the tile again up to it
+      __syncthreads();
+    }
+    const uint32_t ex = sm.wtot[warp] + inc - c;  // newlines of the tile before this thread's run
+    const bool walker = T > (uint32_t)NL_CAP;
+    const uint32_t line_bound = (T >> 2) + 2u;                      // quality lines with bytes in this tile, at most
+    const uint32_t pt_limit = sm.hiflag ? 257u : 516u;              // 16-bit halves: lines a cell can take
+    const bool dense = line_bound > pt_limit;
+    const bool pt_flush = !CORE && !dense && sm.pt_lines + line_bound > pt_limit;
+    const uint32_t cnt_in = sm.run.cnt;
+    if (pt_flush) flush_ptab(sm, tid);
+    if (walker) {
+      phase_walk<CORE>(sm, a, t, tid, w64, c, inc);
+      __syncthreads();
+    } else {
+      // ---- B: the thread's newlines at their slots of the index ----
+      {
+        uint32_t slot = nl_s + 2u * ex;
+        uint32_t wl = (uint32_t)w64, wh = (uint32_t)(w64 >> 32);
+        while (wl) { const uint32_t b = (uint32_t)__ffs(wl) - 1u; wl &= wl - 1u; sts16(slot, 64u * tid + b); slot += 2u; }
+        while (wh) { const uint32_t b = (uint32_t)__ffs(wh) - 1u; wh &= wh - 1u; sts16(slot, 64u * tid + 32u + b); slot += 2u; }
+      }
+      __syncthreads();
+      // ---- L: line tasks (lines j = 0..T of the tile; j = T is the open line behind the last newline) ----
+      const uint32_t step = CORE ? 4u : 2u;
+      const uint32_t j0 = CORE ? (1u - cnt_in) & 3u : ((cnt_in & 1u) ? 0u : 1u);
+      const uint32_t ntasks = j0 <= T ? (T - j0) / step + 1u : 0u;
+      if (tid == 0) {
+        if (CORE) { sm.ti.nlines[0] = ntasks; sm.ti.nlines[1] = 0; }
+        else { const uint32_t qa = ((cnt_in + j0) & 3u) >> 1; sm.ti.nlines[qa] = (ntasks + 1u) >> 1; sm.ti.nlines[qa ^ 1u] = ntasks >> 1; }
+      }
+      for (uint32_t i = (uint32_t)tid; i < ntasks; i += THREADS) {
+        const uint32_t j = j0 + step * i;
+        const int s = j > 0 ? (int)lds16(nl_s + 2u * (j - 1u)) + 1 : t.vlo;
+        const int e = j < T ? (int)lds16(nl_s + 2u * j) : t.vhi;
+        const uint32_t ln = cnt_in + j, ql = (ln >> 1) & 1u, par = (ln >> 2) & 1u;
+        const uint32_t ord = CORE ? i : i >> 1;
+        const bool fn = j == 0;
+        uint32_t pos0 = 0;
+        if (fn) { const u64 op = sm.run.open; pos0 = (uint32_t)(op < (u64)OPEN_CLIP ? op : (u64)OPEN_CLIP); }
+        uint32_t rec = 0;
+        if (e > s) {
+          const uint32_t gs = (uint32_t)s >> 4, ge = (uint32_t)e >> 4, ls = (uint32_t)s & 15u, le = (uint32_t)e & 15u;
+          if (gs == ge) {
+            masked_group<CORE>(sm, ksel, t, hist_s, ptab_s, masks_s, gs, ls, le, pos0, ql, par, dense, over);
+          } else {
+            uint32_t ff = gs;
+            if (ls) { masked_group<CORE>(sm, ksel, t, hist_s, ptab_s, masks_s, gs, ls, 16u, pos0, ql, par, dense, over); ff++; }
+            if (le) masked_group<CORE>(sm, ksel, t, hist_s, ptab_s, masks_s, ge, 0u, le, pos0 + (16u * ge - (uint32_t)s), ql, par, dense, over);
+            const uint32_t nfull = ge - ff;
+            const uint32_t qff = pos0 + (16u * ff - (uint32_t)s);
+            if (nfull > (uint32_t)KMAX) {
+              const uint32_t slot = atomicAdd(&sm.ti.nlong, 1u);
+              if (slot < (uint32_t)LONG_CAP) sm.longl[slot] = (u64)(ff | (nfull << 11) | (ql << 23) | (par << 24)) | ((u64)qff << 32);
+              else a.ctl[CTL_ERROR] = 2;
+            } else if (nfull) {
+              rec = ff | (nfull << 11) | ((qff < 1023u ? qff : 1023u) << 17) | (par << 27);
+              atomicMax(&sm.ti.K[ql], nfull);
+            }
+          }
+        }
+        if (ord < (uint32_t)REC_CAP) sm.rec[ql][ord] = rec; else a.ctl[CTL_ERROR] = 3;
+        if (j < T) line_end<CORE>(sm, a, t, e, fn ? sm.run.open + (u64)(e - t.vlo) : (u64)(e - s), fn, ql);
+      }
+      __syncthreads();
+      // ---- W: the lines' full groups, one lane per group ----
+#pragma unroll
+      for (uint32_t ql = 0; ql < (CORE ? 1u : 2u); ql++) {
+        uint32_t K = sm.ti.K[ql];
+        if (K == 0) continue;
+        if (K == 1) K = 2;  // (the reciprocal table starts at 2)
+        const uint32_t nslots = sm.ti.nlines[ql] * K, inv = sm.inv[K];
+        const uint32_t hb = hist_s + (ql << 10);
+        for (uint32_t x = (uint32_t)tid; x < nslots; x += THREADS) {
+          const uint32_t line = __umulhi(x, inv);
+          const uint32_t k = x - line * K;
+          const uint32_t r = lds32(rec_s + 4u * (ql * REC_CAP + line));
+          if (k < ((r >> 11) & 63u)) {
+            const uint32_t ga = t.buf_s + 16u * ((r & 2047u) + k);
+            const uint4 v = lds128(ga);
+            hist16(ksel, v, hb);
+            if (!CORE && ql) pos16(sm, v, ga, ptab_s, ((r >> 17) & 1023u) + 16u * k + 16u, 0u, 16u, (r >> 27) & 1u, dense, over);
+          }
+        }
+      }
+      {
+        const uint32_t nlong = sm.ti.nlong < (uint32_t)LONG_CAP ? sm.ti.nlong : (uint32_t)LONG_CAP;
+        for (uint32_t li = 0; li < nlong; li++) {
+          const u64 e = sm.longl[li];
+          const uint32_t e0 = (uint32_t)e, qff = (uint32_t)(e >> 32);
+          const uint32_t ff = e0 & 2047u, nfull = (e0 >> 11) & 4095u, ql = (e0 >> 23) & 1u, par = (e0 >> 24) & 1u;
+          for (uint32_t k = (uint32_t)tid; k < nfull; k += THREADS) {
+            const uint32_t ga = t.buf_s + 16u * (ff + k);
+            const uint4 v = lds128(ga);
+            hist16(ksel, v, hist_s + (ql << 10));
+            if (!CORE && ql) pos16(sm, v, ga, ptab_s, qff + 16u * k + 16u, 0u, 16u, par, dense, over);
+          }
+        }
+      }
+    }
+    // ---- end of the tile: launch edges ('\r' whose successor lies in another launch), the running state ----
+    if (tid == 0) {
+      Run& r = sm.run;
+      if (!r.prev_counted && t.vlo == (int)a.lo0 && tile == 0 && r.prev_byte == '\r' && r.open) {
+        // the '\r' that ended the previous launch is content unless this launch starts with '\n'
+        const uint32_t cls = cnt_in & 3u;
+        const bool counted = CORE ? cls == 1u : (cls & 1u) != 0;
+        if (counted && lds8(t.buf_s + (uint32_t)t.vlo) != '\n') {
+          atomicAdd(&sm.hist[cls >> 1]['\r'], 1u);
+          if (!CORE && cls == 3u) {
+            const u64 p = r.open - 1;
+            if (p < (u64)POS_BINS) atomicAdd(&sm.pos32[(uint32_t)p], (uint32_t)'\r'); else atomicAdd(&sm.over, (u64)'\r');
+          }
+        }
+      }
+      const int last1 = T ? (walker ? (int)sm.ti.last1 : (int)sm.nl[T - 1] + 1) : 0;  // offset of the last newline + 1
+      const u64 open_out = T ? (u64)(t.vhi - last1) : r.open + (u64)(t.vhi - t.vlo);
+      const u64 proc_end = t.toff + (u64)t.vhi;
+      if (proc_end == a.end && lds8(t.buf_s + (uint32_t)t.vhi - 1u) == '\r') {  // counted where it stands: left to the next launch / finish()
+        const uint32_t cls = (cnt_in + T) & 3u;
+        const bool counted = CORE ? cls == 1u : (cls & 1u) != 0;
+        if (counted) {
+          atomicSub(&sm.hist[cls >> 1]['\r'], 1u);
+          if (!CORE && cls == 3u) {
+            const u64 p = open_out - 1;
+            if (p < (u64)POS_BINS) atomicSub(&sm.pos32[(uint32_t)p], (uint32_t)'\r'); else atomicAdd(&sm.over, 0ull - '\r');
+          }
+        }
+      }
+      r.prev_byte = (int)lds8(t.buf_s + (uint32_t)t.vhi - 1u);
+      r.prev_counted = 1;
+      r.cnt = cnt_in + T;
+      r.seen |= T != 0;
+      r.open = open_out;
+      r.totalT += T;
+      r.proc_end = proc_end;
+      // the span ends behind the newline that closes the last line starting inside its nominal range
+      r.stop = (ext && T) || (!ext && tile + 1 == t1 && T && last1 == t.vhi) || !have_next;
+      if (!CORE) sm.pt_lines = dense ? sm.pt_lines : (pt_flush ? line_bound : sm.pt_lines + line_bound);
+      sm.bytes_since_flush += TILE;
+    }
+    __syncthreads();
+    if (sm.run.stop) {
+      if (have_next) {  // the copy of the next tile is in flight: it must have landed before the buffer is reused or the CTA exits
+        mbar_wait(bar0_s + 8u * (stage ^ 1), (par_bits >> (stage ^ 1)) & 1u);
+        par_bits ^= 1u << (stage ^ 1);
+      }
+      break;
+    }
+    if (sm.bytes_since_flush >= FLUSH_BYTES) flush_tables(sm, a.acc, tid, over, sign);
+  }
+}
+
+__device__ __forceinline__ u64 warp_incl_scan64(u64 v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const u64 n = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += n;
+  }
   return v;
 }
 
-// Warp 0: the tile's place in the stream.  Tile 0 takes it from the carry (or the shard hypothesis); every other
-// tile publishes its own totals and sums its predecessors' words, 32 at a time, back to the nearest inclusive one.
-__device__ __forceinline__ void tile_prefix(Smem& sm, const ScanArgs& a, const TileCtx& t, int lane, uint32_t T, uint32_t tail) {
-  const u64 ep = (u64)a.epoch << 56;
-  uint32_t cnt_in = 0, seen_in = 0;
-  u64 open_in = 0;
-  int prev_byte = 0x100;
-  if (t.tile == 0) {
-    const Carry c = *a.carry;
-    unsigned fl = c.flags;
-    uint32_t hyp = 0;
-    if (fl & CARRY_UNKNOWN_START) {
-      if (fl & CARRY_HYP_VALID) hyp = (fl >> CARRY_HYP_SHIFT) & 3u;
-      else if (!(fl & CARRY_HYP_FAILED)) {
-        const uint32_t guess = resync_guess(a, lane);
-        if (guess < 4) { hyp = (guess - (uint32_t)c.lines) & 3u; fl |= CARRY_HYP_VALID | (hyp << CARRY_HYP_SHIFT); }
-        else fl |= CARRY_HYP_FAILED;
-        if (lane == 0) a.carry->flags = fl;
+// The CTA that exits last: exact line count in front of every span, verification of the guessed phases, the
+// line-length extrema of the verified spans, the new stream carry.
+__device__ __noinline__ void stitch(Smem& sm, const ScanArgs& a, int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
+  u64* wsum = reinterpret_cast<u64*>(sm.buf[0]);        // scratch: the tile buffers are idle now
+  u64* mm = wsum + 64;                                   // [0..1] min seq/qual, [2..3] max
+  uint32_t* nredo = reinterpret_cast<uint32_t*>(mm + 8);
+  const int per = ((int)a.nspans + THREADS - 1) / THREADS;
+  const int s0 = tid * per, s1 = min((int)a.nspans, s0 + per);
+  u64 mine = 0;
+  for (int s = s0; s < s1; s++) mine += a.desc[s].T;
+  const u64 inc = warp_incl_scan64(mine, lane);
+  if (lane == 31) wsum[warp] = inc;
+  if (tid == 0) { mm[0] = mm[1] = ~0ull; mm[2] = mm[3] = 0; *nredo = 0; }
+  __syncthreads();
+  u64 before = inc - mine, total = 0;
+  for (int w = 0; w < NWARPS; w++) { const u64 x = wsum[w]; if (w < warp) before += x; total += x; }
+  const Carry c = *a.carry;
+  const unsigned fl = c.flags;
+  const bool unknown = (fl & CARRY_UNKNOWN_START) != 0;
+  const bool hyp_ok = !unknown || ((fl & CARRY_HYP_VALID) && !(fl & CARRY_HYP_FAILED));
+  const uint32_t hyp = unknown ? (fl >> CARRY_HYP_SHIFT) & 3u : 0u;
+  u64 G = c.lines + before;  // lines in front of span s0
+  for (int s = s0; s < s1; s++) {
+    SpanDesc& d = a.desc[s];
+    const uint32_t exact = (uint32_t)((G + hyp) & 3u);
+    d.exact = exact;
+    // (a shard whose hypothesis failed is rescanned as a whole with the exact carry: nothing to verify)
+    const bool ok = !d.nonempty || s == 0 || !hyp_ok || (d.guess_valid && d.guess == exact);
+    d.state = ok ? SPAN_OK : SPAN_REDO;
+    if (!ok) atomicAdd(nredo, 1u);
+    else if (d.nonempty) {
+      for (int q = 0; q < 2; q++) {
+        if (d.len_min[q] != ~0ull) atomicMin(&mm[q], d.len_min[q]);
+        if (d.len_max[q]) atomicMax(&mm[2 + q], d.len_max[q]);
       }
     }
-    cnt_in = (uint32_t)((c.lines + hyp) & 255u);
-    seen_in = c.lines != 0;
-    open_in = c.open_len;
-    prev_byte = c.bytes ? (int)c.last_byte : 0x100;
-    if (lane == 0) {
-      if ((fl & CARRY_UNKNOWN_START) && c.bytes == 0) a.shard->first_byte = a.base[a.lo0];
-      const bool pending_cr = c.bytes && c.open_len && c.last_byte == '\r' && a.base[a.lo0] != '\n';
-      if (a.unknown && c.lines == 0) {
-        a.ctl[CTL_HEAD] = HEAD_ACTIVE | ((cnt_in & 3u) == 3u ? HEAD_QUAL : 0u) | (pending_cr ? HEAD_PENDING_CR : 0u);
-        a.ctl[CTL_HEAD_P0] = c.open_len;
-      }
-    }
-  } else if (a.dbg == 1) {
-    const u64 X = t.toff - a.lo0, rec = X / 360, r = X % 360;
-    const uint32_t line = r < 56 ? 0u : r < 207 ? 1u : r < 209 ? 2u : 3u;
-    const uint32_t ls = line == 0 ? 0u : line == 1 ? 56u : line == 2 ? 207u : 209u;
-    cnt_in = (uint32_t)((rec * 4 + line) & 255u); seen_in = 1; open_in = r - ls;
-    prev_byte = (int)a.base[t.toff - 1];
-  } else {
-    if (lane == 0) {
-      st_relaxed_gpu(a.state + t.tile, ep | ST_AGG | ((u64)T << 18) | (u64)tail);
-      prev_byte = (int)a.base[t.toff - 1];
-    }
-    uint32_t cnt_acc = 0;
-    u64 open_acc = 0;
-    bool found = false;
-    long long i = (long long)t.tile - 1;
-    for (;;) {
-      const long long p = i - lane;
-      u64 st = 0;
-      bool ready;
-      do {
-        if (p >= 0) st = ld_relaxed_gpu(a.state + p);
-        ready = p < 0 || ((st >> 56) == (u64)a.epoch && ((st >> 54) & 3u) != 0);
-      } while (!__all_sync(0xffffffffu, ready));
-      const bool isinc = p >= 0 && ((st >> 54) & 3u) == 2u;
-      const uint32_t pm = __ballot_sync(0xffffffffu, isinc);
-      const bool act = pm ? lane <= __ffs(pm) - 1 : true;  // (tile 0 is inclusive from the start, so lanes with p < 0 lie behind it)
-      const uint32_t Tl = (uint32_t)(st >> 18) & 0x3FFFFu, taill = (uint32_t)st & 0x3FFFFu;
-      const uint32_t hb = __ballot_sync(0xffffffffu, act && !isinc && Tl != 0);
-      const int nearest = hb ? __ffs(hb) - 1 : 32;
-      uint32_t vc = 0;
-      u64 vo = 0;
-      if (act) {
-        if (isinc) {
-          vc = (uint32_t)(st >> 45) & 0xFFu;
-          if (nearest == 32) vo = st & OPEN_MASK;
-          seen_in |= (uint32_t)(st >> 53) & 1u;
-        } else {
-          vc = Tl;
-          if (lane <= nearest) vo = taill;
-        }
-      }
-      cnt_acc += __reduce_add_sync(0xffffffffu, vc);
-      vo = warp_sum_u64(vo);
-      if (!found) { open_acc += vo; found = nearest < 32; }
-      if (pm) break;
-      i -= 32;
-    }
-    seen_in = __any_sync(0xffffffffu, seen_in != 0) || found;
-    cnt_in = cnt_acc & 255u;
-    open_in = open_acc;
-    prev_byte = __shfl_sync(0xffffffffu, prev_byte, 0);
+    if (d.reached_end) mm[4] = d.end_open;  // exactly one span runs to the end of the launch
+    G += d.T;
   }
-  const u64 open_out = T ? (u64)tail : open_in + (u64)tail;
-  if (lane == 0) {
-    st_relaxed_gpu(a.state + t.tile, ep | ST_INC | ((u64)((seen_in || T) ? 1 : 0) << 53) | ((u64)((cnt_in + T) & 255u) << 45) | (open_out & OPEN_MASK));
-    sm.in.open = open_in; sm.in.open_out = open_out; sm.in.cnt = cnt_in; sm.in.seen = seen_in; sm.in.T = T; sm.in.prev_byte = prev_byte;
-    sm.nitems = 0;
-    if (t.tile + 1 == a.ntiles) a.ctl[CTL_OPEN_OUT] = open_out;
+  __syncthreads();
+  if (tid == 0) {
+    for (int q = 0; q < 2; q++) {
+      if (mm[q] != ~0ull) atomicMin(&a.acc[q ? OFF_QUAL_LEN_MIN : OFF_SEQ_LEN_MIN], mm[q]);
+      if (mm[2 + q]) atomicMax(&a.acc[q ? OFF_QUAL_LEN_MAX : OFF_SEQ_LEN_MAX], mm[2 + q]);
+    }
+    a.carry->lines = c.lines + total;
+    a.carry->open_len = mm[4];
+    a.carry->bytes = c.bytes + (a.end - (u64)a.lo0);
+    a.carry->last_byte = a.base[a.end - 1];
+    a.ctl[CTL_REDO] = *nredo;
+    a.ctl[CTL_DONE] = 0; a.ctl[CTL_FIRST_NL] = 0; a.ctl[CTL_HEAD] = 0; a.ctl[CTL_HEAD_P0] = 0;
   }
 }
 
@@ -531,17 +738,12 @@ template <bool CORE>
 __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint32_t span = blockIdx.x;
+  SpanDesc& desc = a.desc[span];
+  if (a.pass == 1 && desc.state != SPAN_REDO) return;
   const uint32_t sm0 = smem_u32(smem_raw);
-  const uint32_t buf0_s = sm0 + (uint32_t)offsetof(Smem, buf);
   const uint32_t bar0_s = sm0 + (uint32_t)offsetof(Smem, full_bar);
-  const uint32_t bm_s = sm0 + (uint32_t)offsetof(Smem, bitmap);
-  const uint32_t gi_s = sm0 + (uint32_t)offsetof(Smem, ginfo);
-  const uint32_t hist_s = sm0 + (uint32_t)offsetof(Smem, hist);
-  const uint32_t ptab_s = sm0 + (uint32_t)offsetof(Smem, ptab);
-  const uint32_t masks_s = sm0 + (uint32_t)offsetof(Smem, masks);
-  const uint32_t queue_s = sm0 + (uint32_t)offsetof(Smem, queue);
-  unsigned long long* ticket = reinterpret_cast<unsigned long long*>(a.ctl + CTL_TICKET);
 
   for (int i = tid; i < 512; i += THREADS) (&sm.hist[0][0])[i] = 0;
   for (int i = tid; i < POS_BINS + 2; i += THREADS) { sm.seq_len[i] = 0; sm.qual_len[i] = 0; sm.pos32[i] = 0; }
@@ -551,222 +753,121 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a) {
     const int n = tid >> 2, w = tid & 3, k = n - 4 * w;
     (&sm.masks[0].x)[tid] = k >= 4 ? 0xFFFFFFFFu : (k <= 0 ? 0u : ((1u << (8 * k)) - 1u));
   }
-  uint32_t next_tile = 0;  // thread 0: the ticket of the tile after the one in flight
+  if (tid >= 128 && tid <= 128 + KMAX) {
+    const uint32_t k = (uint32_t)(tid - 128);
+    sm.inv[k] = k >= 2 ? (uint32_t)(((1ull << 32) + k - 1) / k) : 0u;
+  }
+  const uint32_t t1 = min(a.ntiles, (span + 1u) * a.tps);  // nominal end of the span (tiles)
   if (tid == 0) {
     sm.len_min[0] = sm.len_min[1] = 0xFFFFFFFFu; sm.len_max[0] = sm.len_max[1] = 0;
     sm.big_min[0] = sm.big_min[1] = ~0ull; sm.big_max[0] = sm.big_max[1] = 0;
     sm.over = 0; sm.junk[0] = sm.junk[1] = 0;
-    sm.nitems = 0; sm.pt_lines = 0; sm.hiflag = 0; sm.bytes_since_flush = 0;
+    sm.pt_lines = 0; sm.hiflag = 0; sm.bytes_since_flush = 0; sm.flag = 0;
     for (int k = 0; k < 4; k++) sm.ksel[k] = 4u << (8 * k);
     for (int s = 0; s < NSTAGE; s++) mbar_init(bar0_s + 8u * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    const uint32_t t0 = (uint32_t)atomicAdd(ticket, 1ull);
-    sm.tile[0] = t0;
-    if (t0 < a.ntiles) {
-      const u64 toff = (u64)t0 * TILE;
-      const uint32_t bytes = (uint32_t)((((a.end - toff) < (u64)TILE ? (a.end - toff) : (u64)TILE) + 15) & ~15ull);
-      mbar_expect_tx(bar0_s, bytes);
-      tma_load_1d(buf0_s, a.base + toff, bytes, bar0_s);
-      next_tile = (uint32_t)atomicAdd(ticket, 1ull);
-    } else {
-      next_tile = a.ntiles;
-    }
   }
-  u64 over = 0;     // quality bytes at positions >= POS_BINS
-  u64 totalT = 0;   // newlines of this CTA's tiles (warp 0)
+  // ---- where the span starts and the line phase there ----
+  u64 start = ~0ull;
+  uint32_t guess = 0, guess_valid = 1;
+  if (tid < 32) {
+    Run r;
+    r.totalT = 0; r.proc_end = 0; r.stop = 0;
+    if (a.pass == 1) {
+      start = desc.start;
+      r.open = 0; r.cnt = desc.guess_valid ? desc.guess : 0u; r.seen = 1; r.prev_byte = '\n'; r.prev_counted = 1;
+    } else if (span == 0) {
+      const Carry c = *a.carry;
+      unsigned fl = c.flags;
+      uint32_t hyp = 0;
+      if (fl & CARRY_UNKNOWN_START) {
+        if (fl & CARRY_HYP_VALID) hyp = (fl >> CARRY_HYP_SHIFT) & 3u;
+        else if (!(fl & CARRY_HYP_FAILED)) {
+          const uint32_t g = resync_launch(a, lane);  // phase of the line that holds the launch's first byte
+          if (g < 4) { hyp = (g - (uint32_t)c.lines) & 3u; fl |= CARRY_HYP_VALID | (hyp << CARRY_HYP_SHIFT); }
+          else fl |= CARRY_HYP_FAILED;
+          if (lane == 0) a.carry->flags = fl;
+        }
+      }
+      start = (u64)a.lo0;
+      r.open = c.open_len; r.cnt = (uint32_t)((c.lines + hyp) & 255u); r.seen = c.lines != 0;
+      r.prev_byte = c.bytes ? (int)c.last_byte : 0x100; r.prev_counted = 0;
+      guess = r.cnt & 3u;
+      if (lane == 0) {
+        if ((fl & CARRY_UNKNOWN_START) && c.bytes == 0) a.shard->first_byte = a.base[a.lo0];
+        if (a.unknown && c.lines == 0) {
+          const bool pending_cr = c.bytes && c.open_len && c.last_byte == '\r' && a.base[a.lo0] != '\n';
+          a.ctl[CTL_HEAD] = HEAD_ACTIVE | ((r.cnt & 3u) == 3u ? HEAD_QUAL : 0u) | (pending_cr ? HEAD_PENDING_CR : 0u);
+          a.ctl[CTL_HEAD_P0] = c.open_len;
+        }
+      }
+    } else {
+      uint32_t g;
+      start = resync_span(a, (u64)span * a.tps * TILE, (u64)t1 * TILE, lane, g);
+      guess_valid = g < 4;
+      guess = guess_valid ? g : 0u;
+      r.open = 0; r.cnt = guess; r.seen = 1; r.prev_byte = '\n'; r.prev_counted = 1;
+    }
+    if (lane == 0) { sm.run = r; sm.longl[0] = start; sm.longl[1] = ((u64)guess_valid << 32) | guess; }
+  }
+  __syncthreads();
+  start = sm.longl[0];
+  guess = (uint32_t)sm.longl[1]; guess_valid = (uint32_t)(sm.longl[1] >> 32);
   __syncthreads();
   Sel ksel;
   {
     const uint32_t ks = sm0 + (uint32_t)offsetof(Smem, ksel);
     ksel.h0 = lds32(ks); ksel.h1 = lds32(ks + 4); ksel.h2 = lds32(ks + 8); ksel.h3 = lds32(ks + 12);
   }
-
-  for (int it = 0;; it++) {
-    TileCtx t;
-    t.tile = sm.tile[it & 1];
-    if (t.tile >= a.ntiles) break;
-    const int stage = it & 1;
-    t.toff = (u64)t.tile * TILE;
-    t.vlo = t.tile == 0 ? (int)a.lo0 : 0;
-    t.vhi = (a.end - t.toff) < (u64)TILE ? (int)(a.end - t.toff) : TILE;
-    t.buf_s = buf0_s + (uint32_t)stage * TILE;
-    const bool edge = t.vlo != 0 || t.vhi != TILE;
-    if (tid == 0) {  // the copy of the next tile into the other stage (free since the end of the last iteration)
-      sm.tile[(it + 1) & 1] = next_tile;
-      if (next_tile < a.ntiles) {
-        const u64 toff = (u64)next_tile * TILE;
-        const uint32_t bytes = (uint32_t)((((a.end - toff) < (u64)TILE ? (a.end - toff) : (u64)TILE) + 15) & ~15ull);
-        mbar_expect_tx(bar0_s + 8u * (stage ^ 1), bytes);
-        tma_load_1d(buf0_s + (uint32_t)(stage ^ 1) * TILE, a.base + toff, bytes, bar0_s + 8u * (stage ^ 1));
-        next_tile = (uint32_t)atomicAdd(ticket, 1ull);  // consumed in the next iteration: the round trip is off the critical path
-      }
-    }
-    mbar_wait(bar0_s + 8u * stage, (uint32_t)(it >> 1) & 1u);
-
-    // ---- A: newline masks of the tile's groups -> bitmap ----
-    if (!edge) {
-      uint4 v[GPT];
-#pragma unroll
-      for (int k = 0; k < GPT; k++) v[k] = lds128(t.buf_s + 16u * (uint32_t)(k * THREADS + tid));
-      uint32_t hib = 0;
-#pragma unroll
-      for (int k = 0; k < GPT; k++) {
-        hib |= (v[k].x | v[k].y) | (v[k].z | v[k].w);
-        sts16(bm_s + 2u * (uint32_t)(k * THREADS + tid), nl_mask16_ascii(v[k]));
-      }
-      if (hib & 0x80808080u) { phase_a_redo(t.buf_s, bm_s, tid); sm.hiflag = 1; }  // the short compare is exact only for bytes < 0x80
-    } else {
-      if (phase_a_edge(t.buf_s, bm_s, t.vlo, t.vhi, tid) & 0x80808080u) sm.hiflag = 1;
-    }
-    __syncthreads();
-
-    // ---- B1: this thread's 64 consecutive bytes of the bitmap; block-wide prefix ----
-    const u64 w64 = lds64(bm_s + 8u * (uint32_t)tid);
-    const uint32_t wl = (uint32_t)w64, wh = (uint32_t)(w64 >> 32);
-    const uint32_t c = (uint32_t)__popc(wl) + (uint32_t)__popc(wh);
-    const int mylast = 64 * tid + (wh ? 63 - __clz(wh) : 31 - __clz(wl));  // offset of the run's last newline (if c)
-    const uint32_t inc = warp_incl_scan(c, lane);
-    const uint32_t hasb = __ballot_sync(0xffffffffu, c != 0);
-    const uint32_t lower = hasb & lanemask_lt();
-    const int lastW = __shfl_sync(0xffffffffu, mylast, (31 - __clz(lower)) & 31);      // valid if lower
-    const int warp_last = __shfl_sync(0xffffffffu, mylast, (31 - __clz(hasb)) & 31);   // valid if hasb
-    if (lane == 31) sm.wtot[warp] = ((u64)inc << 32) | (u64)(uint32_t)(hasb ? warp_last + 1 : 0);
-    __syncthreads();
-    uint32_t wbase, T;
-    int prevw_last1;  // (offset of the last newline of the earlier warps) + 1, 0 = none
-    {
-      const u64 e = lane < NWARPS ? sm.wtot[lane] : 0ull;
-      const uint32_t ec = (uint32_t)(e >> 32), el = (uint32_t)e;
-      const uint32_t einc = warp_incl_scan(ec, lane);
-      T = __shfl_sync(0xffffffffu, einc, NWARPS - 1);
-      wbase = __shfl_sync(0xffffffffu, einc - ec, warp);
-      const uint32_t hw = __ballot_sync(0xffffffffu, el != 0);
-      const uint32_t lw = hw & ((1u << warp) - 1u);
-      prevw_last1 = lw ? (int)__shfl_sync(0xffffffffu, el, (31 - __clz(lw)) & 31) : 0;
-      if (warp == 0) {
-        const int tile_last1 = hw ? (int)__shfl_sync(0xffffffffu, el, (31 - __clz(hw)) & 31) : 0;
-        const uint32_t tail = T ? (uint32_t)(t.vhi - tile_last1) : (uint32_t)(t.vhi - t.vlo);
-        tile_prefix(sm, a, t, lane, T, tail);
-        totalT += T;
-      }
-    }
-    __syncthreads();
-
-    // ---- B2: group descriptors and items ----
-    const bool walker = T + 4u > (uint32_t)QCAP;
-    const uint32_t line_bound = (T >> 2) + 2u;                      // quality lines with bytes in this tile, at most
-    const uint32_t pt_limit = sm.hiflag ? 257u : 516u;              // 16-bit halves: lines a cell can take
-    const bool dense = line_bound > pt_limit;
-    const bool pt_flush = !CORE && !dense && sm.pt_lines + line_bound > pt_limit;
-    const uint32_t cnt0 = sm.in.cnt + wbase + inc - c;
-    const uint32_t lc0 = wbase + inc - c;
-    int last0;
-    if (lower) last0 = lastW;
-    else if (prevw_last1) last0 = prevw_last1 - 1;
-    else { const u64 op = sm.in.open; last0 = t.vlo - 1 - (int)(op < (u64)OPEN_CLIP ? op : (u64)OPEN_CLIP); }
-    if (pt_flush) flush_ptab(sm, tid);
-    if (walker) {
-      phase_walk<CORE>(sm, a, t, tid, cnt0, lc0, last0);
-    } else {
-      if (!edge) phase_b2<CORE, false>(sm, a, t, gi_s, tid, wl, wh, cnt0, lc0, last0);
-      else phase_b2_edge<CORE>(sm, a, t, gi_s, tid, wl, wh, cnt0, lc0, last0);
-    }
-    __syncthreads();
-    if (tid == 0 && !CORE) sm.pt_lines = dense ? sm.pt_lines : (pt_flush ? line_bound : sm.pt_lines + line_bound);
-
-    if (!walker) {
-      // ---- C: one lane per group without a newline ----
-      {
-        const uint32_t g0 = (uint32_t)(warp * (GPT * 32) + lane);
-        uint32_t gi[GPT];
-#pragma unroll
-        for (int j = 0; j < GPT; j++) gi[j] = lds16(gi_s + 2u * (g0 + 32u * j));
-#pragma unroll
-        for (int j = 0; j < GPT; j++) {
-          const bool on = CORE ? (gi[j] & 3u) == 1u : (gi[j] & 1u) != 0;
-          if (on) {
-            const uint32_t ga = t.buf_s + 16u * (g0 + 32u * j);
-            const uint4 v = lds128(ga);
-            hist16(ksel, v, hist_s + ((gi[j] & 2u) << 9));
-            if (!CORE && (gi[j] & 2u)) pos16(sm, v, ga, ptab_s, (gi[j] >> 3) + 16u, 0u, 16u, (gi[j] >> 2) & 1u, dense, over);
-          }
-        }
-      }
-      // ---- D: the items ----
-      const uint32_t nitems = sm.nitems < (uint32_t)QCAP ? sm.nitems : (uint32_t)QCAP;
-      for (uint32_t i = (uint32_t)tid; i < nitems; i += THREADS) {
-        const u64 e = lds64(queue_s + 8u * i);
-        const uint32_t e0 = (uint32_t)e, pos = (uint32_t)(e >> 32);
-        const uint32_t g = e0 & 2047u, lo = (e0 >> 11) & 31u, hi = (e0 >> 16) & 31u, ql = (e0 >> 21) & 1u;
-        const uint32_t ga = t.buf_s + 16u * g;
-        if (hi > lo) {
-          uint4 v = lds128(ga);
-          const uint4 ml = lds128(masks_s + 16u * lo), mh = lds128(masks_s + 16u * hi);
-          v.x &= mh.x & ~ml.x; v.y &= mh.y & ~ml.y; v.z &= mh.z & ~ml.z; v.w &= mh.w & ~ml.w;
-          hist16(ksel, v, hist_s + (ql << 10));
-          atomicAdd(&sm.junk[ql], 16u - (hi - lo));
-          if (!CORE && ql) pos16(sm, v, ga, ptab_s, pos + 16u - lo, lo, hi, (e0 >> 24) & 1u, dense, over);
-        }
-        if (e0 & (1u << 22)) {
-          const bool fn = (e0 >> 23) & 1u;
-          const int off = (int)(16u * g + hi);
-          const u64 rawlen = fn ? sm.in.open + (u64)(off - t.vlo) : (u64)(pos + (hi - lo));
-          line_end<CORE>(sm, a, t, off, rawlen, fn, ql);
-        }
-      }
-    }
-    // ---- launch edges: a '\r' whose successor lies in another launch ----
+  u64 over = 0;
+  uint32_t par_bits = 0;
+  const bool nonempty = start != ~0ull;
+  if (a.pass == 0) {
+    if (nonempty) run_span<CORE>(sm, a, ksel, sm0, tid, start, t1, par_bits, over, 1);
+    flush_tables(sm, a.acc, tid, over, 1);
     if (tid == 0) {
-      if (t.tile == 0) {  // the '\r' that ended the previous launch is content unless this launch starts with '\n'
-        const Carry& c = *a.carry;  // (bytes, open_len, last_byte are rewritten only by the CTA that exits last)
-        const uint32_t cls = sm.in.cnt & 3u;
-        const bool counted = CORE ? cls == 1u : (cls & 1u) != 0;
-        if (counted && c.bytes && c.open_len && c.last_byte == '\r' && lds8(t.buf_s + (uint32_t)t.vlo) != '\n') {
-          atomicAdd(&sm.hist[cls >> 1]['\r'], 1u);
-          if (!CORE && cls == 3u) {
-            const u64 p = c.open_len - 1;
-            if (p < (u64)POS_BINS) atomicAdd(&sm.pos32[(uint32_t)p], (uint32_t)'\r'); else atomicAdd(&sm.over, (u64)'\r');
-          }
-        }
+      const Run& r = sm.run;
+      desc.T = r.totalT; desc.start = start; desc.end_open = r.open;
+      for (int q = 0; q < 2; q++) {
+        u64 mn = sm.len_min[q] != 0xFFFFFFFFu ? (u64)sm.len_min[q] : ~0ull, mx = sm.len_max[q];
+        if (sm.big_min[q] < mn) mn = sm.big_min[q];
+        if (sm.big_max[q] > mx) mx = sm.big_max[q];
+        desc.len_min[q] = mn; desc.len_max[q] = mx;
       }
-      if (t.tile + 1 == a.ntiles && lds8(t.buf_s + (uint32_t)t.vhi - 1u) == '\r') {  // counted where it stands: left to the next launch / finish()
-        const uint32_t cls = (sm.in.cnt + T) & 3u;
-        const bool counted = CORE ? cls == 1u : (cls & 1u) != 0;
-        if (counted) {
-          atomicSub(&sm.hist[cls >> 1]['\r'], 1u);
-          if (!CORE && cls == 3u) {
-            const u64 p = sm.in.open_out - 1;
-            if (p < (u64)POS_BINS) atomicSub(&sm.pos32[(uint32_t)p], (uint32_t)'\r'); else atomicAdd(&sm.over, 0ull - '\r');
-          }
-        }
-      }
-      sm.bytes_since_flush += TILE;
+      desc.guess = guess; desc.guess_valid = guess_valid; desc.nonempty = nonempty ? 1u : 0u;
+      desc.reached_end = nonempty && r.proc_end == a.end;
+      // ---- the CTA that exits last verifies the guesses and advances the stream carry ----
+      __threadfence();
+      const u64 prev = atomicAdd(reinterpret_cast<unsigned long long*>(a.ctl + CTL_DONE), 1ull);
+      sm.flag = prev + 1 == (u64)gridDim.x;
     }
     __syncthreads();
-    if (sm.bytes_since_flush >= FLUSH_BYTES) flush_all(sm, a.acc, tid, over);
-  }
-  flush_all(sm, a.acc, tid, over);
-  // ---- the CTA that exits last advances the stream carry and leaves the control words clean ----
-  if (tid == 0) {
-    if (totalT) atomicAdd(reinterpret_cast<unsigned long long*>(a.ctl + CTL_TOTAL_T), totalT);
+    if (!sm.flag) return;
     __threadfence();
-    const u64 prev = atomicAdd(reinterpret_cast<unsigned long long*>(a.ctl + CTL_DONE), 1ull);
-    sm.tile[0] = prev + 1 == (u64)gridDim.x;
-  }
-  __syncthreads();
-  if (!sm.tile[0]) return;
-  __threadfence();
-  if (a.unknown && !CORE) detach_head(a, tid);
-  __syncthreads();
-  if (tid == 0) {
-    __threadfence();
-    Carry* c = a.carry;
-    c->lines += ld_relaxed_gpu(a.ctl + CTL_TOTAL_T);
-    c->open_len = ld_relaxed_gpu(a.ctl + CTL_OPEN_OUT);
-    c->bytes += a.end - (u64)a.lo0;
-    c->last_byte = a.base[a.end - 1];
-    a.ctl[CTL_TICKET] = 0; a.ctl[CTL_DONE] = 0; a.ctl[CTL_TOTAL_T] = 0; a.ctl[CTL_OPEN_OUT] = 0;
-    a.ctl[CTL_FIRST_NL] = 0; a.ctl[CTL_HEAD] = 0; a.ctl[CTL_HEAD_P0] = 0;
+    if (a.unknown && !CORE) detach_head(a, tid);
+    stitch(sm, a, tid);
+  } else {
+    // second pass: take back what pass 0 counted under the wrong phase, then count under the exact one
+    run_span<CORE>(sm, a, ksel, sm0, tid, start, t1, par_bits, over, -1);
+    flush_tables(sm, a.acc, tid, over, -1);
+    if (tid == 0) {
+      Run& r = sm.run;
+      r.totalT = 0; r.proc_end = 0; r.stop = 0; r.open = 0; r.cnt = desc.exact; r.seen = 1; r.prev_byte = '\n'; r.prev_counted = 1;
+      sm.len_min[0] = sm.len_min[1] = 0xFFFFFFFFu; sm.len_max[0] = sm.len_max[1] = 0;
+      sm.big_min[0] = sm.big_min[1] = ~0ull; sm.big_max[0] = sm.big_max[1] = 0;
+    }
+    __syncthreads();
+    run_span<CORE>(sm, a, ksel, sm0, tid, start, t1, par_bits, over, 1);
+    flush_tables(sm, a.acc, tid, over, 1);
+    if (tid == 0) {
+      for (int q = 0; q < 2; q++) {
+        u64 mn = sm.len_min[q] != 0xFFFFFFFFu ? (u64)sm.len_min[q] : ~0ull, mx = sm.len_max[q];
+        if (sm.big_min[q] < mn) mn = sm.big_min[q];
+        if (sm.big_max[q] > mx) mx = sm.big_max[q];
+        if (mn != ~0ull) atomicMin(&a.acc[q ? OFF_QUAL_LEN_MIN : OFF_SEQ_LEN_MIN], mn);
+        if (mx) atomicMax(&a.acc[q ? OFF_QUAL_LEN_MAX : OFF_SEQ_LEN_MAX], mx);
+      }
+    }
   }
 }
 
@@ -801,13 +902,26 @@ cudaError_t launch_reset(u64* acc, Carry* carry, u64* ctl, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-u64 scan_tiles(const void* ptr, size_t nbytes) { return (((u64)((uintptr_t)ptr & 15) + nbytes) + TILE - 1) / TILE; }
+// Spans of a launch over `bytes` bytes (incl. the alignment slack in front) with `resident` CTAs resident at once.
+// Large launches get several spans per resident CTA, handed out by the hardware as CTAs finish: of the two CTAs of an
+// SM the one that started first runs faster, so with one span each the slower half finishes late and alone; with
+// shorter spans the tail is one short span.  Spans stay >= MIN_SPAN_TILES tiles (FQGPU_SPAN_MIN_TILES: tests).
+uint32_t scan_span_count(u64 bytes, int resident) {
+  static const u64 min_tiles = getenv("FQGPU_SPAN_MIN_TILES") && atoi(getenv("FQGPU_SPAN_MIN_TILES")) > 0 ? (u64)atoi(getenv("FQGPU_SPAN_MIN_TILES")) : (u64)MIN_SPAN_TILES;
+  static const u64 waves = getenv("FQGPU_SPAN_WAVES") && atoi(getenv("FQGPU_SPAN_WAVES")) > 0 ? (u64)atoi(getenv("FQGPU_SPAN_WAVES")) : (u64)SPAN_WAVES;
+  const u64 ntiles = (bytes + TILE - 1) / TILE;
+  u64 n = ntiles / min_tiles;
+  const u64 cap = (u64)resident * (waves < (u64)SPAN_WAVES ? waves : (u64)SPAN_WAVES);
+  n = n < 1 ? 1 : (n > cap ? cap : n);
+  if (n > (u64)resident) n = (n / (u64)resident) * (u64)resident;  // whole waves
+  return (uint32_t)n;
+}
 
-// Scans `nbytes` at `ptr` (any alignment) as the continuation of the stream described by `carry`: ONE launch.
-// `state` holds at least scan_tiles(ptr, nbytes) words; `epoch` (1..255) differs from that of every earlier launch
-// since the words were last zeroed.
-cudaError_t launch_scan(const void* ptr, size_t nbytes, Carry* carry, ShardInfo* shard, u64* acc, u64* state, u64* ctl,
-                        uint32_t epoch, bool unknown_start, int resident, bool core_only, cudaStream_t st) {
+// Scans `nbytes` at `ptr` (any alignment) as the continuation of the stream described by `carry`: pass 0 (every span
+// under its guessed phase; its last CTA verifies and advances the carry) and pass 1 (the spans whose guess was wrong;
+// exits at once otherwise).
+cudaError_t launch_scan(const void* ptr, size_t nbytes, Carry* carry, ShardInfo* shard, u64* acc, SpanDesc* desc, u64* ctl,
+                        bool unknown_start, int resident, bool core_only, cudaStream_t st) {
   if (nbytes == 0) return cudaSuccess;
   const uintptr_t addr = (uintptr_t)ptr;
   ScanArgs a;
@@ -815,12 +929,16 @@ cudaError_t launch_scan(const void* ptr, size_t nbytes, Carry* carry, ShardInfo*
   a.base = (const uint8_t*)(addr - a.lo0);
   a.end = (u64)a.lo0 + nbytes;
   a.ntiles = (uint32_t)((a.end + TILE - 1) / TILE);
-  a.carry = carry; a.shard = shard; a.acc = acc; a.state = state; a.ctl = ctl;
-  a.epoch = epoch; a.unknown = unknown_start ? 1u : 0u;
-  a.dbg = getenv("FQGPU_DBG") ? (uint32_t)atoi(getenv("FQGPU_DBG")) : 0u;
-  const unsigned grid = a.ntiles < (uint32_t)resident ? a.ntiles : (unsigned)resident;
-  if (core_only) fq_scan_kernel<true><<<grid, THREADS, sizeof(Smem), st>>>(a);
-  else fq_scan_kernel<false><<<grid, THREADS, sizeof(Smem), st>>>(a);
+  const uint32_t nspans = scan_span_count(a.end, resident);
+  a.tps = (a.ntiles + nspans - 1) / nspans;
+  a.nspans = (a.ntiles + a.tps - 1) / a.tps;
+  a.carry = carry; a.shard = shard; a.acc = acc; a.desc = desc; a.ctl = ctl;
+  a.unknown = unknown_start ? 1u : 0u;
+  for (uint32_t pass = 0; pass < 2; pass++) {
+    a.pass = pass;
+    if (core_only) fq_scan_kernel<true><<<a.nspans, THREADS, sizeof(Smem), st>>>(a);
+    else fq_scan_kernel<false><<<a.nspans, THREADS, sizeof(Smem), st>>>(a);
+  }
   return cudaGetLastError();
 }
 

@@ -53,7 +53,7 @@ void fqgpu_destroy(fqgpu_ctx* ctx) {
   }
   if (ctx->cstream) cudaStreamDestroy(ctx->cstream);
   cudaFree(ctx->d_acc);
-  cudaFree(ctx->d_state);
+  cudaFree(ctx->d_desc);
   cudaFree(ctx->d_ctl);
   cudaFree(ctx->d_carry);
   cudaFree(ctx->d_shard);
@@ -103,8 +103,10 @@ int fqgpu_create(fqgpu_ctx** out, const fqgpu_config* cfg) {
   CU_NEW(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   CU_NEW(fq::scan_configure());
   ctx->grid = prop.multiProcessorCount * 2;
+  if (ctx->grid > fq::RESIDENT_CTAS) ctx->grid = fq::RESIDENT_CTAS;
   CU_NEW(cudaMalloc(&ctx->d_acc, fq::BLOCK_WORDS * sizeof(u64)));
   CU_NEW(cudaMalloc(&ctx->d_ctl, fq::CTL_WORDS * sizeof(u64)));
+  CU_NEW(cudaMalloc(&ctx->d_desc, fq::MAX_SPANS * sizeof(fq::SpanDesc)));
   CU_NEW(cudaMalloc(&ctx->d_carry, sizeof(fq::Carry)));
   CU_NEW(cudaMalloc(&ctx->d_shard, sizeof(fq::ShardInfo)));
   CU_NEW(cudaMallocHost(&ctx->h_shard, (size_t)64 * fqgpu_shard_block_words() * sizeof(u64)));
@@ -143,25 +145,10 @@ cudaEvent_t fqgpu_get_event(fqgpu_ctx* ctx) {
 
 extern "C" {
 
-// One scan launch over [p, p + n) as the continuation of the context's stream; the fq-meta prefix fold (which touches
-// only its own fields of the carry) runs beside it on its own stream.
+// The scan of [p, p + n) as the continuation of the context's stream (two launches: every span, then the spans whose
+// guessed line phase was wrong -- none on well-formed input); the fq-meta prefix fold (which touches only its own fields
+// of the carry) runs beside it on its own stream.
 static int fqgpu_launch_scan(fqgpu_ctx* ctx, const uint8_t* p, size_t n, u64 meta_records) {
-  const u64 ntiles = fq::scan_tiles(p, n);
-  if (ntiles > ctx->state_cap) {  // look-back words: grown to the largest launch so far (8 bytes per 32 KiB of input)
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ctx->d_state) CU_TRY(ctx, cudaFree(ctx->d_state));
-    ctx->d_state = nullptr;
-    ctx->state_cap = 0;
-    const u64 cap = ntiles + ntiles / 4 + 1024;
-    CU_TRY(ctx, cudaMalloc(&ctx->d_state, cap * sizeof(u64)));
-    CU_TRY(ctx, cudaMemsetAsync(ctx->d_state, 0, cap * sizeof(u64), ctx->stream));
-    ctx->state_cap = cap;
-    ctx->epoch = 0;
-  }
-  if (++ctx->epoch > 255) {  // epochs are about to repeat: forget every word written so far
-    CU_TRY(ctx, cudaMemsetAsync(ctx->d_state, 0, ctx->state_cap * sizeof(u64), ctx->stream));
-    ctx->epoch = 1;
-  }
   if (meta_records) {
     const uintptr_t addr = (uintptr_t)p;
     const uint32_t lo0 = (uint32_t)(addr & 15);
@@ -170,11 +157,11 @@ static int fqgpu_launch_scan(fqgpu_ctx* ctx, const uint8_t* p, size_t n, u64 met
     CU_TRY(ctx, fq::launch_meta((const uint8_t*)(addr - lo0), lo0, (u64)lo0 + n, ctx->d_carry, meta_records, ctx->mstream));
     CU_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->mstream));
   }
-  CU_TRY(ctx, fq::launch_scan(p, n, ctx->d_carry, ctx->d_shard, ctx->d_acc, ctx->d_state, ctx->d_ctl, ctx->epoch,
+  CU_TRY(ctx, fq::launch_scan(p, n, ctx->d_carry, ctx->d_shard, ctx->d_acc, ctx->d_desc, ctx->d_ctl,
                               ctx->shard_rank > 0 && !ctx->shard_exact, ctx->grid, (ctx->cfg.flags & FQGPU_F_CORE_ONLY) != 0,
                               ctx->stream));
   if (meta_records) CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
-  ctx->launches++;
+  ctx->launches += 2;
   return FQGPU_OK;
 }
 

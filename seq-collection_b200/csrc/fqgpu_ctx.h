@@ -15,9 +15,8 @@ int scan_tile_bytes();
 int scan_threads();
 cudaError_t scan_configure();
 cudaError_t launch_reset(u64* acc, Carry* carry, u64* ctl, cudaStream_t st);
-u64 scan_tiles(const void* ptr, size_t nbytes);
-cudaError_t launch_scan(const void* ptr, size_t nbytes, Carry* carry, ShardInfo* shard, u64* acc, u64* state, u64* ctl,
-                        uint32_t epoch, bool unknown_start, int resident, bool core_only, cudaStream_t st);
+cudaError_t launch_scan(const void* ptr, size_t nbytes, Carry* carry, ShardInfo* shard, u64* acc, SpanDesc* desc, u64* ctl,
+                        bool unknown_start, int resident, bool core_only, cudaStream_t st);
 cudaError_t launch_meta(const uint8_t* base, uint32_t lo0, u64 end, Carry* carry, u64 meta_records, cudaStream_t st);
 cudaError_t launch_synth_illumina(void* dptr, u64 first_byte, u64 nbytes, u64 seed, cudaStream_t st);
 cudaError_t synth_ont(void* dptr, size_t capacity, u64 first_record, u64 n_records, u64 seed, size_t* bytes_written,
@@ -26,7 +25,7 @@ cudaError_t synth_ont(void* dptr, size_t capacity, u64 first_record, u64 n_recor
 
 using fq::u64;
 
-// one launch: the tile index is 32-bit and the look-back array (8 bytes per 32 KiB tile) is sized for the largest launch so far
+// one launch: the tile index is 32-bit
 static const size_t kMaxLaunchBytes = (size_t)64 << 30;
 inline thread_local std::string g_create_error;
 
@@ -42,12 +41,10 @@ struct fqgpu_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t mstream = nullptr;                  // the fq-meta prefix kernel runs beside the scan
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  int grid = 0;                // persistent CTAs of a scan launch (2 per SM)
+  int grid = 0;                // CTAs of a scan launch resident at once (2 per SM)
   u64* d_acc = nullptr;        // [BLOCK_WORDS] counter block accumulated since the last reset
-  u64* d_state = nullptr;      // look-back words of the scan launches (one per 32 KiB tile)
-  u64 state_cap = 0;           // ... capacity in tiles
-  u64* d_ctl = nullptr;        // [CTL_WORDS] ticket / done counters and launch scratch
-  uint32_t epoch = 0;          // epoch of the most recent launch (1..255)
+  fq::SpanDesc* d_desc = nullptr;  // [MAX_SPANS] span descriptors of the launch in flight
+  u64* d_ctl = nullptr;        // [CTL_WORDS] done counter and launch scratch
   fq::Carry* d_carry = nullptr;
   u64* h_out = nullptr;  // pinned: counter block followed by the carry
   std::vector<StageBuf> ring;

@@ -163,3 +163,20 @@ def test_repeated_use_of_one_context_many_epochs(full):
         st = full.count_device(buf.data_ptr(), len(data))
         if i % 50 == 0 or i > 250:
             assert_equal_stats(st.to_dict(), want, f"iteration {i}")
+
+
+@pytest.mark.parametrize("min_tiles", ["1", "3"])
+def test_everything_again_with_tiny_spans(min_tiles):
+    """FQGPU_SPAN_MIN_TILES (read once per process, hence the subprocess) cuts small inputs into spans of one / three
+    tiles: span starts found from the content, spans that run past their range to finish a line, empty spans inside
+    long lines, guessed phases verified by the last CTA and wrong ones (adversarial and malformed inputs) redone."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = {**os.environ, "FQGPU_SPAN_MIN_TILES": min_tiles, "FQGPU_TINY_SPANS_CHILD": "1"}
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_scan_tiles.py", "tests/test_gpu_parity.py", "tests/test_gpu_shards.py",
+                        "-q", "-x", "-m", "gpu", "-k", "not tiny_spans and not two_gigabytes", "-p", "no:cacheprovider"],
+                       cwd=root, env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1500:]
