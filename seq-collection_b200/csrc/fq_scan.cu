@@ -95,14 +95,12 @@ struct Run {
   uint32_t seen;     // a newline has been seen in the stream before the tile
   int prev_byte;     // byte before the tile's first valid byte (0x100: none)
   uint32_t prev_counted;  // ... and it was scanned by this launch (a '\r' there has been counted)
-  uint32_t stop;     // the span ends with this tile
 };
 struct TileInfo {
   uint32_t T;        // newlines of the tile
   uint32_t first;    // extension tiles: offset of the first newline
   uint32_t K[2];     // most full groups of a (not long) line, per class
   uint32_t nlong;
-  uint32_t nlines[2];
   uint32_t last1;    // walker tiles: offset of the last newline + 1
 };
 
@@ -110,7 +108,8 @@ struct __align__(128) Smem {
   uint8_t buf[NSTAGE][TILE];
   uint16_t bitmap[NG];               // bit b of entry g: byte 16 g + b is '\n'
   uint16_t nl[NL_CAP + 8];           // offsets of the tile's newlines, ascending
-  uint32_t rec[2][REC_CAP];          // per class and line: first full group | full groups << 11 | position << 17 | parity << 27
+  u64 rec[2][REC_CAP];               // per class and line: first full group | full groups << 11 | fast << 17 | table cell << 18 | parity << 30 | position << 32
+  uint32_t part[2][2 * REC_CAP];     // per class and line: its two ragged groups: group | lo << 11 | hi << 15 | parity << 20 | position of byte lo << 21
   u64 longl[LONG_CAP];               // lines of more than KMAX full groups: first | groups << 11 | class << 23 | parity << 24 | position << 32
   uint32_t inv[KMAX + 1];            // ceil(2^32 / K)
   uint32_t hist[2][256];             // [0] sequence, [1] quality
@@ -128,18 +127,12 @@ struct __align__(128) Smem {
   uint32_t len_min[2], len_max[2];   // [0] seq, [1] qual
   uint32_t junk[2];                  // masked bytes counted in bin 0
   uint32_t ksel[4];
-  uint32_t pt_lines, hiflag, bytes_since_flush, flag;
+  uint32_t hiflag, flag;
   Run run;
   TileInfo ti;
 };
 static_assert(sizeof(Smem) <= 115712, "two CTAs per SM");
 
-struct TileCtx {
-  uint32_t tile;
-  int vlo, vhi;     // valid bytes of the tile
-  u64 toff;         // offset of the tile relative to base
-  uint32_t buf_s;
-};
 
 // ---------------------------------------------------------------------------------------------
 // 16 bytes into the histogram at hbase: one IDP.4A and one shared atomic per byte
@@ -225,8 +218,6 @@ __device__ __noinline__ void flush_tables(Smem& sm, u64* acc, int tid, u64& over
   if (tid == 0) {
     if (sm.over) { atomicAdd(&acc[OFF_POS_SUM + POS_BINS], sign > 0 ? sm.over : 0ull - sm.over); sm.over = 0; }
     sm.junk[0] = sm.junk[1] = 0;
-    sm.bytes_since_flush = 0;
-    sm.pt_lines = 0;
     sm.hiflag = 0;
   }
   __syncthreads();
@@ -235,10 +226,10 @@ __device__ __noinline__ void flush_tables(Smem& sm, u64* acc, int tid, u64& over
 // A counted line of raw length `rawlen` ends with the newline at tile offset `off`: the '\r' rule and the length
 // tables.  ql: 0 sequence, 1 quality.  fn: the line started before the tile.
 template <bool CORE>
-__device__ __forceinline__ void line_end(Smem& sm, const ScanArgs& a, const TileCtx& t, int off, u64 rawlen, bool fn, uint32_t ql) {
-  const int prev = off > t.vlo ? (int)lds8(t.buf_s + (uint32_t)off - 1u) : sm.run.prev_byte;
+__device__ __forceinline__ void line_end(Smem& sm, const ScanArgs& a, uint32_t buf_s, int vlo, u64 toff, int off, u64 rawlen, bool fn, uint32_t ql) {
+  const int prev = off > vlo ? (int)lds8(buf_s + (uint32_t)off - 1u) : sm.run.prev_byte;
   const u64 cr = (rawlen > 0 && prev == '\r') ? 1 : 0;
-  if (cr && (off > t.vlo || sm.run.prev_counted)) {  // the '\r' was counted as content where it stands: take it back
+  if (cr && (off > vlo || sm.run.prev_counted)) {  // the '\r' was counted as content where it stands: take it back
     // (not counted: the last byte of the previous launch, whose fate was left to this one)
     atomicSub(&sm.hist[ql]['\r'], 1u);
     if (!CORE && ql) {
@@ -250,7 +241,7 @@ __device__ __forceinline__ void line_end(Smem& sm, const ScanArgs& a, const Tile
   if (a.unknown && fn && !sm.run.seen) {  // the shard's first line: its length is stitched by the combine step
     a.shard->head_len = rawlen;
     a.shard->head_cr = (unsigned)cr;
-    a.ctl[CTL_FIRST_NL] = t.toff + (u64)off + 1;
+    a.ctl[CTL_FIRST_NL] = toff + (u64)off + 1;
     return;
   }
   const uint32_t bin = len < (u64)POS_BINS ? (uint32_t)len : (uint32_t)POS_BINS;
@@ -261,16 +252,16 @@ __device__ __forceinline__ void line_end(Smem& sm, const ScanArgs& a, const Tile
 }
 
 // Phase A, rare forms (kept out of the hot code): this thread's groups again with the exact compare; an edge tile.
-__device__ __noinline__ void phase_a_redo(uint32_t buf_s, uint32_t bm_s, int tid) {
+__device__ __noinline__ void phase_a_redo(uint32_t buf_s, uint32_t bm_s, int warp, int lane) {
   for (int k = 0; k < GPT; k++) {
-    const uint32_t g = (uint32_t)(k * THREADS + tid);
+    const uint32_t g = (uint32_t)(warp * (GPT * 32) + k * 32 + lane);
     sts16(bm_s + 2u * g, nl_mask16(lds128(buf_s + 16u * g)));
   }
 }
-__device__ __noinline__ uint32_t phase_a_edge(uint32_t buf_s, uint32_t bm_s, int lo, int hi, int tid) {
+__device__ __noinline__ uint32_t phase_a_edge(uint32_t buf_s, uint32_t bm_s, int lo, int hi, int warp, int lane) {
   uint32_t hib = 0;
   for (int k = 0; k < GPT; k++) {
-    const int g = k * THREADS + tid, off = g * 16;
+    const int g = warp * (GPT * 32) + k * 32 + lane, off = g * 16;
     uint32_t m = 0;
     if (off < hi && off + 16 > lo) {
       const uint4 v = lds128(buf_s + 16u * (uint32_t)g);
@@ -279,7 +270,10 @@ __device__ __noinline__ uint32_t phase_a_edge(uint32_t buf_s, uint32_t bm_s, int
       int hi_k = hi - off; hi_k = hi_k > 16 ? 16 : hi_k;
       m &= ((1u << hi_k) - 1u) & ~((1u << lo_k) - 1u);
       if (lo_k == 0 && hi_k == 16) hib |= (v.x | v.y) | (v.z | v.w);
-      else hib |= 0x80u;  // ragged group: stale bytes beside the valid ones; be conservative
+      else {  // ragged group: only the valid bytes count (stale shared memory beside them)
+        const uint32_t ww[4] = {v.x, v.y, v.z, v.w};
+        for (int x = lo_k; x < hi_k; x++) hib |= (ww[x >> 2] >> (8 * (x & 3))) & 0x80u;
+      }
     }
     sts16(bm_s + 2u * (uint32_t)g, m);
   }
@@ -288,10 +282,9 @@ __device__ __noinline__ uint32_t phase_a_edge(uint32_t buf_s, uint32_t bm_s, int
 
 // The byte walker: tiles with more newlines than the index holds.  Every thread takes its own 64 bytes one at a time
 // (exact for any content); '\r' is counted where it stands and taken back by line_end like everywhere else.
-// c / inc: newlines of this thread's run and their inclusive prefix inside the warp; sm.wtot holds the exclusive
-// prefix over the warps.
+// c / inc: newlines of this thread's run and their inclusive prefix inside the warp; wbase: newlines of the warps before.
 template <bool CORE>
-__device__ __noinline__ void phase_walk(Smem& sm, const ScanArgs& a, const TileCtx& t, int tid, u64 w64, uint32_t c, uint32_t inc) {
+__device__ __noinline__ void phase_walk(Smem& sm, const ScanArgs& a, uint32_t buf_s, int vlo, int vhi, u64 toff, int tid, u64 w64, uint32_t c, uint32_t inc, uint32_t wbase) {
   const int lane = tid & 31, warp = tid >> 5;
   // offset of the last newline before this thread's run: inside the warp, else of the warps before, else none
   const uint32_t wl = (uint32_t)w64, wh = (uint32_t)(w64 >> 32);
@@ -305,18 +298,18 @@ __device__ __noinline__ void phase_walk(Smem& sm, const ScanArgs& a, const TileC
   int last = -1;
   if (lower) last = lastW;
   else for (int w = warp - 1; w >= 0; w--) if (sm.wlast[w]) { last = sm.wlast[w] - 1; break; }
-  uint32_t lc = sm.wtot[warp] + inc - c;
+  uint32_t lc = wbase + inc - c;
   uint32_t cnt = sm.run.cnt + lc;
   u64 over = 0;
   for (int x = 0; x < 16 * GPT; x++) {
     const int off = 16 * GPT * tid + x;
-    if (off < t.vlo || off >= t.vhi) continue;
-    const uint32_t b = lds8(t.buf_s + (uint32_t)off);
+    if (off < vlo || off >= vhi) continue;
+    const uint32_t b = lds8(buf_s + (uint32_t)off);
     const uint32_t cls = cnt & 3u;
     const bool counted = CORE ? cls == 1u : (cls & 1u) != 0;
-    const u64 pos = lc == 0 ? sm.run.open + (u64)(off - t.vlo) : (u64)(off - last - 1);
+    const u64 pos = lc == 0 ? sm.run.open + (u64)(off - vlo) : (u64)(off - last - 1);
     if (b == '\n') {
-      if (counted) line_end<CORE>(sm, a, t, off, pos, lc == 0, cls >> 1);
+      if (counted) line_end<CORE>(sm, a, buf_s, vlo, toff, off, pos, lc == 0, cls >> 1);
       cnt++; lc++;
       last = off;
     } else if (counted) {
@@ -424,9 +417,9 @@ __device__ __noinline__ void detach_head(const ScanArgs& a, int tid) {
 
 // Bytes [lo, hi) of group g belong to a counted line; posLo = line position of byte lo.
 template <bool CORE>
-__device__ __forceinline__ void masked_group(Smem& sm, const Sel& ksel, const TileCtx& t, uint32_t hist_s, uint32_t ptab_s, uint32_t masks_s,
+__device__ __forceinline__ void masked_group(Smem& sm, const Sel& ksel, uint32_t buf_s, uint32_t hist_s, uint32_t ptab_s, uint32_t masks_s,
                                              uint32_t g, uint32_t lo, uint32_t hi, uint32_t posLo, uint32_t ql, uint32_t par, bool dense, u64& over) {
-  const uint32_t ga = t.buf_s + 16u * g;
+  const uint32_t ga = buf_s + 16u * g;
   uint4 v = lds128(ga);
   const uint4 ml = lds128(masks_s + 16u * lo), mh = lds128(masks_s + 16u * hi);
   v.x &= mh.x & ~ml.x; v.y &= mh.y & ~ml.y; v.z &= mh.z & ~ml.z; v.w &= mh.w & ~ml.w;
@@ -434,9 +427,20 @@ __device__ __forceinline__ void masked_group(Smem& sm, const Sel& ksel, const Ti
   atomicAdd(&sm.junk[ql], 16u - (hi - lo));
   if (!CORE && ql) pos16(sm, v, ga, ptab_s, posLo + 16u - lo, lo, hi, par, dense, over);
 }
+__device__ __forceinline__ uint32_t part_entry(uint32_t g, uint32_t lo, uint32_t hi, uint32_t posLo, uint32_t par) {
+  return g | (lo << 11) | (hi << 15) | (par << 20) | ((posLo < 1023u ? posLo : 1023u) << 21);
+}
+// The eight packed pairs of a quality group whose table cell address is known (pos16 without the case analysis).
+__device__ __forceinline__ void pos16_fast(const uint4& v, uint32_t r0) {
+  red_add_at<4 * PT_STRIDE * 0>(r0, __byte_perm(v.x, 0u, 0x4140)); red_add_at<4 * PT_STRIDE * 1>(r0, __byte_perm(v.x, 0u, 0x4342));
+  red_add_at<4 * PT_STRIDE * 2>(r0, __byte_perm(v.y, 0u, 0x4140)); red_add_at<4 * PT_STRIDE * 3>(r0, __byte_perm(v.y, 0u, 0x4342));
+  red_add_at<4 * PT_STRIDE * 4>(r0, __byte_perm(v.z, 0u, 0x4140)); red_add_at<4 * PT_STRIDE * 5>(r0, __byte_perm(v.z, 0u, 0x4342));
+  red_add_at<4 * PT_STRIDE * 6>(r0, __byte_perm(v.w, 0u, 0x4140)); red_add_at<4 * PT_STRIDE * 7>(r0, __byte_perm(v.w, 0u, 0x4342));
+}
 
-// One span under the line phase `cnt0` at its first byte `start` (open0 bytes of that line lie before it).
-// par_bits: mbarrier parities of the two stages (kept across calls).
+// One span under the line phase sm.run.cnt at its first byte `start`.  par_bits: mbarrier parities of the two stages
+// (kept across calls).  Three CTA-wide barriers per tile; the copy of the next tile is started behind the first one
+// (every thread is then done with the tile before this one, whose stage it overwrites).
 template <bool CORE>
 __device__ __forceinline__ void run_span(Smem& sm, const ScanArgs& a, const Sel& ksel, uint32_t sm0, int tid, u64 start, uint32_t t1,
                                          uint32_t& par_bits, u64& over, int sign) {
@@ -449,85 +453,90 @@ __device__ __forceinline__ void run_span(Smem& sm, const ScanArgs& a, const Sel&
   const uint32_t ptab_s = sm0 + (uint32_t)offsetof(Smem, ptab);
   const uint32_t masks_s = sm0 + (uint32_t)offsetof(Smem, masks);
   const uint32_t rec_s = sm0 + (uint32_t)offsetof(Smem, rec);
+  const uint32_t part_s = sm0 + (uint32_t)offsetof(Smem, part);
   const uint32_t t_first = (uint32_t)(start / TILE);
-  auto tile_bytes = [&](uint32_t tile) -> uint32_t {
-    const u64 toff = (u64)tile * TILE;
-    return (uint32_t)((((a.end - toff) < (u64)TILE ? (a.end - toff) : (u64)TILE) + 15) & ~15ull);
-  };
+  uint32_t pt_lines = 0, since_flush = 0;  // (uniform) quality lines in ptab since its last flush; bytes since the tables' last flush
   int stage = 0;
   if (tid == 0) {
-    mbar_expect_tx(bar0_s, tile_bytes(t_first));
-    tma_load_1d(buf0_s, a.base + (u64)t_first * TILE, tile_bytes(t_first), bar0_s);
+    const u64 toff = (u64)t_first * TILE;
+    const uint32_t bytes = (uint32_t)((((a.end - toff) < (u64)TILE ? (a.end - toff) : (u64)TILE) + 15) & ~15ull);
+    mbar_expect_tx(bar0_s, bytes);
+    tma_load_1d(buf0_s, a.base + toff, bytes, bar0_s);
   }
   for (uint32_t tile = t_first;; tile++, stage ^= 1) {
-    TileCtx t;
-    t.tile = tile;
-    t.toff = (u64)tile * TILE;
-    t.vlo = tile == t_first ? (int)(start - t.toff) : 0;
-    t.vhi = (a.end - t.toff) < (u64)TILE ? (int)(a.end - t.toff) : TILE;
-    t.buf_s = buf0_s + (uint32_t)stage * TILE;
+    const u64 toff = (u64)tile * TILE;
+    const int vlo = tile == t_first ? (int)(start - toff) : 0;
+    int vhi = (a.end - toff) < (u64)TILE ? (int)(a.end - toff) : TILE;
+    const uint32_t buf_s = buf0_s + (uint32_t)stage * TILE;
     const bool ext = tile >= t1;   // beyond the span's nominal range: only up to the first newline
     const bool have_next = tile + 1 < a.ntiles;
-    if (tid == 0 && have_next) {  // the copy of the next tile into the other stage (free since the end of the last iteration)
-      mbar_expect_tx(bar0_s + 8u * (stage ^ 1), tile_bytes(tile + 1));
-      tma_load_1d(buf0_s + (uint32_t)(stage ^ 1) * TILE, a.base + t.toff + TILE, tile_bytes(tile + 1), bar0_s + 8u * (stage ^ 1));
-    }
     mbar_wait(bar0_s + 8u * stage, (par_bits >> stage) & 1u);
     par_bits ^= 1u << stage;
 
     u64 w64;
-    uint32_t c, inc, T;
+    uint32_t c, inc, T, wbase;
 #pragma unroll 1
     for (int round = 0;; round++) {
-      // ---- A: newline masks of the tile's groups -> bitmap ----
-      if (t.vlo == 0 && t.vhi == TILE) {
+      // ---- A: newline masks -> bitmap.  Warp w classifies bytes [2048 w, 2048 w + 2048): coalesced 16-byte groups ----
+      if (vlo == 0 && vhi == TILE) {
+        const uint32_t g0 = (uint32_t)(warp * (GPT * 32) + lane);
         uint4 v[GPT];
 #pragma unroll
-        for (int k = 0; k < GPT; k++) v[k] = lds128(t.buf_s + 16u * (uint32_t)(k * THREADS + tid));
+        for (int k = 0; k < GPT; k++) v[k] = lds128(buf_s + 16u * (g0 + 32u * k));
         uint32_t hib = 0;
 #pragma unroll
         for (int k = 0; k < GPT; k++) {
           hib |= (v[k].x | v[k].y) | (v[k].z | v[k].w);
-          sts16(bm_s + 2u * (uint32_t)(k * THREADS + tid), nl_mask16_ascii(v[k]));
+          sts16(bm_s + 2u * (g0 + 32u * k), nl_mask16_ascii(v[k]));
         }
-        if (hib & 0x80808080u) { phase_a_redo(t.buf_s, bm_s, tid); sm.hiflag = 1; }  // the short compare is exact only for bytes < 0x80
+        if (hib & 0x80808080u) { phase_a_redo(buf_s, bm_s, warp, lane); sm.hiflag = 1; }  // the short compare is exact only for bytes < 0x80
       } else {
-        if (phase_a_edge(t.buf_s, bm_s, t.vlo, t.vhi, tid) & 0x80808080u) sm.hiflag = 1;
+        if (phase_a_edge(buf_s, bm_s, vlo, vhi, warp, lane) & 0x80808080u) sm.hiflag = 1;
       }
-      __syncthreads();
-      // ---- B: this thread's 64 consecutive bytes of the bitmap; block-wide prefix of the newline counts ----
+      __syncwarp();
+      // ---- B: this thread's 64 consecutive bytes of the bitmap (written by its own warp); prefix of the newline counts ----
       w64 = lds64(bm_s + 8u * (uint32_t)tid);
       c = (uint32_t)__popcll(w64);
       inc = warp_incl_scan(c, lane);
       if (lane == 31) sm.wtot[warp] = inc;
       __syncthreads();
-      if (warp == 0) {
+      {
         const uint32_t e = lane < NWARPS ? sm.wtot[lane] : 0u;
         const uint32_t einc = warp_incl_scan(e, lane);
-        if (lane < NWARPS) sm.wtot[lane] = einc - e;
-        if (lane == NWARPS - 1) { sm.ti.T = einc; sm.ti.K[0] = sm.ti.K[1] = 0; sm.ti.nlong = 0; }
-        if (ext && lane == 0) {  // offset of the tile's first newline (rare path: one thread walks the bitmap)
-          uint32_t f = 0xFFFFFFFFu;
-          for (int i = 0; i < NG / 4; i++) { const u64 w = reinterpret_cast<const u64*>(sm.bitmap)[i]; if (w) { f = 64u * i + (uint32_t)__ffsll((long long)w) - 1u; break; } }
-          sm.ti.first = f;
-        }
+        T = __shfl_sync(0xffffffffu, einc, NWARPS - 1);
+        wbase = __shfl_sync(0xffffffffu, einc - e, warp);
+      }
+      if (!ext || T == 0 || round == 1) break;
+      // the span ends with the tile's first newline: classify the tile again up to it (rare: once per span)
+      if (tid == 0) {
+        uint32_t f = 0;
+        for (int i = 0; i < NG / 4; i++) { const u64 w = reinterpret_cast<const u64*>(sm.bitmap)[i]; if (w) { f = 64u * i + (uint32_t)__ffsll((long long)w) - 1u; break; } }
+        sm.ti.first = f;
       }
       __syncthreads();
-      T = sm.ti.T;
-      if (!ext || T == 0 || round == 1 || (int)sm.ti.first + 1 >= t.vhi) break;
-      t.vhi = (int)sm.ti.first + 1;  // the span ends with this newline: classify the tile again up to it
+      if ((int)sm.ti.first + 1 >= vhi) break;
+      vhi = (int)sm.ti.first + 1;
       __syncthreads();
     }
-    const uint32_t ex = sm.wtot[warp] + inc - c;  // newlines of the tile before this thread's run
+    // the span ends behind the newline that closes the last line starting inside its nominal range
+    const bool ends_nl = (lds16(bm_s + 2u * ((uint32_t)(vhi - 1) >> 4)) >> ((vhi - 1) & 15)) & 1u;
+    const bool stop = (ext && T) || (!ext && tile + 1 == t1 && ends_nl) || !have_next;
+    if (tid == 0 && have_next && !stop) {  // the copy of the next tile into the other stage: every thread has left the tile before this one
+      const uint32_t bytes = (uint32_t)((((a.end - toff - TILE) < (u64)TILE ? (a.end - toff - TILE) : (u64)TILE) + 15) & ~15ull);
+      mbar_expect_tx(bar0_s + 8u * (stage ^ 1), bytes);
+      tma_load_1d(buf0_s + (uint32_t)(stage ^ 1) * TILE, a.base + toff + TILE, bytes, bar0_s + 8u * (stage ^ 1));
+    }
+    const uint32_t ex = wbase + inc - c;  // newlines of the tile before this thread's run
     const bool walker = T > (uint32_t)NL_CAP;
     const uint32_t line_bound = (T >> 2) + 2u;                      // quality lines with bytes in this tile, at most
     const uint32_t pt_limit = sm.hiflag ? 257u : 516u;              // 16-bit halves: lines a cell can take
     const bool dense = line_bound > pt_limit;
-    const bool pt_flush = !CORE && !dense && sm.pt_lines + line_bound > pt_limit;
+    const bool pt_flush = !CORE && !dense && pt_lines + line_bound > pt_limit;
     const uint32_t cnt_in = sm.run.cnt;
-    if (pt_flush) flush_ptab(sm, tid);
+    if (pt_flush) { flush_ptab(sm, tid); pt_lines = 0; }
+    if (!dense) pt_lines += line_bound;
     if (walker) {
-      phase_walk<CORE>(sm, a, t, tid, w64, c, inc);
+      phase_walk<CORE>(sm, a, buf_s, vlo, vhi, toff, tid, w64, c, inc, wbase);
       __syncthreads();
     } else {
       // ---- B: the thread's newlines at their slots of the index ----
@@ -537,33 +546,34 @@ __device__ __forceinline__ void run_span(Smem& sm, const ScanArgs& a, const Sel&
         while (wl) { const uint32_t b = (uint32_t)__ffs(wl) - 1u; wl &= wl - 1u; sts16(slot, 64u * tid + b); slot += 2u; }
         while (wh) { const uint32_t b = (uint32_t)__ffs(wh) - 1u; wh &= wh - 1u; sts16(slot, 64u * tid + 32u + b); slot += 2u; }
       }
-      __syncthreads();
-      // ---- L: line tasks (lines j = 0..T of the tile; j = T is the open line behind the last newline) ----
       const uint32_t step = CORE ? 4u : 2u;
       const uint32_t j0 = CORE ? (1u - cnt_in) & 3u : ((cnt_in & 1u) ? 0u : 1u);
       const uint32_t ntasks = j0 <= T ? (T - j0) / step + 1u : 0u;
-      if (tid == 0) {
-        if (CORE) { sm.ti.nlines[0] = ntasks; sm.ti.nlines[1] = 0; }
-        else { const uint32_t qa = ((cnt_in + j0) & 3u) >> 1; sm.ti.nlines[qa] = (ntasks + 1u) >> 1; sm.ti.nlines[qa ^ 1u] = ntasks >> 1; }
-      }
+      uint32_t nlines0, nlines1;  // lines per class with bytes in the tile
+      if (CORE) { nlines0 = ntasks; nlines1 = 0; }
+      else { const uint32_t qa = ((cnt_in + j0) & 3u) >> 1; nlines0 = qa ? ntasks >> 1 : (ntasks + 1u) >> 1; nlines1 = ntasks - nlines0; }
+      if (tid == 0) { sm.ti.K[0] = sm.ti.K[1] = 0; sm.ti.nlong = 0; }
+      __syncthreads();
+      // ---- L: line tasks (lines j = 0..T of the tile; j = T is the open line behind the last newline) ----
       for (uint32_t i = (uint32_t)tid; i < ntasks; i += THREADS) {
         const uint32_t j = j0 + step * i;
-        const int s = j > 0 ? (int)lds16(nl_s + 2u * (j - 1u)) + 1 : t.vlo;
-        const int e = j < T ? (int)lds16(nl_s + 2u * j) : t.vhi;
+        const int s = j > 0 ? (int)lds16(nl_s + 2u * (j - 1u)) + 1 : vlo;
+        const int e = j < T ? (int)lds16(nl_s + 2u * j) : vhi;
         const uint32_t ln = cnt_in + j, ql = (ln >> 1) & 1u, par = (ln >> 2) & 1u;
         const uint32_t ord = CORE ? i : i >> 1;
         const bool fn = j == 0;
         uint32_t pos0 = 0;
         if (fn) { const u64 op = sm.run.open; pos0 = (uint32_t)(op < (u64)OPEN_CLIP ? op : (u64)OPEN_CLIP); }
-        uint32_t rec = 0;
+        u64 rec = 0;
+        uint32_t p0 = 0, p1 = 0;
         if (e > s) {
           const uint32_t gs = (uint32_t)s >> 4, ge = (uint32_t)e >> 4, ls = (uint32_t)s & 15u, le = (uint32_t)e & 15u;
           if (gs == ge) {
-            masked_group<CORE>(sm, ksel, t, hist_s, ptab_s, masks_s, gs, ls, le, pos0, ql, par, dense, over);
+            p0 = part_entry(gs, ls, le, pos0, par);
           } else {
             uint32_t ff = gs;
-            if (ls) { masked_group<CORE>(sm, ksel, t, hist_s, ptab_s, masks_s, gs, ls, 16u, pos0, ql, par, dense, over); ff++; }
-            if (le) masked_group<CORE>(sm, ksel, t, hist_s, ptab_s, masks_s, ge, 0u, le, pos0 + (16u * ge - (uint32_t)s), ql, par, dense, over);
+            if (ls) { p0 = part_entry(gs, ls, 16u, pos0, par); ff++; }
+            if (le) p1 = part_entry(ge, 0u, le, pos0 + (16u * ge - (uint32_t)s), par);
             const uint32_t nfull = ge - ff;
             const uint32_t qff = pos0 + (16u * ff - (uint32_t)s);
             if (nfull > (uint32_t)KMAX) {
@@ -571,33 +581,51 @@ __device__ __forceinline__ void run_span(Smem& sm, const ScanArgs& a, const Sel&
               if (slot < (uint32_t)LONG_CAP) sm.longl[slot] = (u64)(ff | (nfull << 11) | (ql << 23) | (par << 24)) | ((u64)qff << 32);
               else a.ctl[CTL_ERROR] = 2;
             } else if (nfull) {
-              rec = ff | (nfull << 11) | ((qff < 1023u ? qff : 1023u) << 17) | (par << 27);
+              uint32_t lo32 = ff | (nfull << 11) | (par << 30);
+              if (!CORE && ql && !dense && qff + 16u * nfull <= (uint32_t)POS_BINS) {  // every full group inside the packed table
+                const uint32_t Q = qff + 16u, odd = Q & 1u, A = (Q + odd) >> 1;
+                lo32 |= (1u << 17) | (((A & 7u) * PT_STRIDE + (A >> 3) + odd * (2u * PT_COPY) + par * PT_COPY) << 18);
+              }
+              rec = (u64)lo32 | ((u64)qff << 32);
               atomicMax(&sm.ti.K[ql], nfull);
             }
           }
         }
-        if (ord < (uint32_t)REC_CAP) sm.rec[ql][ord] = rec; else a.ctl[CTL_ERROR] = 3;
-        if (j < T) line_end<CORE>(sm, a, t, e, fn ? sm.run.open + (u64)(e - t.vlo) : (u64)(e - s), fn, ql);
+        if (ord < (uint32_t)REC_CAP) {
+          sts64(rec_s + 8u * (ql * REC_CAP + ord), rec);
+          sts64(part_s + 8u * (ql * REC_CAP + ord), (u64)p0 | ((u64)p1 << 32));
+        } else a.ctl[CTL_ERROR] = 3;
+        if (j < T) line_end<CORE>(sm, a, buf_s, vlo, toff, e, fn ? sm.run.open + (u64)(e - vlo) : (u64)(e - s), fn, ql);
       }
       __syncthreads();
-      // ---- W: the lines' full groups, one lane per group ----
+      // ---- W: one lane per 16-byte group: the lines' full groups (slot x -> line x / K, group x % K), their ragged ends ----
 #pragma unroll
       for (uint32_t ql = 0; ql < (CORE ? 1u : 2u); ql++) {
-        uint32_t K = sm.ti.K[ql];
-        if (K == 0) continue;
-        if (K == 1) K = 2;  // (the reciprocal table starts at 2)
-        const uint32_t nslots = sm.ti.nlines[ql] * K, inv = sm.inv[K];
+        const uint32_t nlines = ql ? nlines1 : nlines0;
         const uint32_t hb = hist_s + (ql << 10);
-        for (uint32_t x = (uint32_t)tid; x < nslots; x += THREADS) {
-          const uint32_t line = __umulhi(x, inv);
-          const uint32_t k = x - line * K;
-          const uint32_t r = lds32(rec_s + 4u * (ql * REC_CAP + line));
-          if (k < ((r >> 11) & 63u)) {
-            const uint32_t ga = t.buf_s + 16u * ((r & 2047u) + k);
-            const uint4 v = lds128(ga);
-            hist16(ksel, v, hb);
-            if (!CORE && ql) pos16(sm, v, ga, ptab_s, ((r >> 17) & 1023u) + 16u * k + 16u, 0u, 16u, (r >> 27) & 1u, dense, over);
+        uint32_t K = sm.ti.K[ql];
+        if (K == 1) K = 2;  // (the reciprocal table starts at 2)
+        if (K) {
+          const uint32_t nslots = nlines * K, inv = sm.inv[K];
+          for (uint32_t x = (uint32_t)tid; x < nslots; x += THREADS) {
+            const uint32_t line = __umulhi(x, inv);
+            const uint32_t k = x - line * K;
+            const u64 r = lds64(rec_s + 8u * (ql * REC_CAP + line));
+            const uint32_t r0 = (uint32_t)r;
+            if (k < ((r0 >> 11) & 63u)) {
+              const uint32_t ga = buf_s + 16u * ((r0 & 2047u) + k);
+              const uint4 v = lds128(ga);
+              hist16(ksel, v, hb);
+              if (!CORE && ql) {
+                if (r0 & (1u << 17)) pos16_fast(v, ptab_s + 4u * (((r0 >> 18) & 4095u) + k));
+                else pos16(sm, v, ga, ptab_s, (uint32_t)(r >> 32) + 16u * k + 16u, 0u, 16u, (r0 >> 30) & 1u, dense, over);
+              }
+            }
           }
+        }
+        for (uint32_t x = (uint32_t)tid; x < 2u * nlines; x += THREADS) {
+          const uint32_t ent = lds32(part_s + 4u * (2u * ql * REC_CAP + x));
+          if (ent) masked_group<CORE>(sm, ksel, buf_s, hist_s, ptab_s, masks_s, ent & 2047u, (ent >> 11) & 15u, (ent >> 15) & 31u, ent >> 21, ql, (ent >> 20) & 1u, dense, over);
         }
       }
       {
@@ -607,7 +635,7 @@ __device__ __forceinline__ void run_span(Smem& sm, const ScanArgs& a, const Sel&
           const uint32_t e0 = (uint32_t)e, qff = (uint32_t)(e >> 32);
           const uint32_t ff = e0 & 2047u, nfull = (e0 >> 11) & 4095u, ql = (e0 >> 23) & 1u, par = (e0 >> 24) & 1u;
           for (uint32_t k = (uint32_t)tid; k < nfull; k += THREADS) {
-            const uint32_t ga = t.buf_s + 16u * (ff + k);
+            const uint32_t ga = buf_s + 16u * (ff + k);
             const uint4 v = lds128(ga);
             hist16(ksel, v, hist_s + (ql << 10));
             if (!CORE && ql) pos16(sm, v, ga, ptab_s, qff + 16u * k + 16u, 0u, 16u, par, dense, over);
@@ -618,11 +646,11 @@ __device__ __forceinline__ void run_span(Smem& sm, const ScanArgs& a, const Sel&
     // ---- end of the tile: launch edges ('\r' whose successor lies in another launch), the running state ----
     if (tid == 0) {
       Run& r = sm.run;
-      if (!r.prev_counted && t.vlo == (int)a.lo0 && tile == 0 && r.prev_byte == '\r' && r.open) {
+      if (!r.prev_counted && tile == 0 && vlo == (int)a.lo0 && r.prev_byte == '\r' && r.open) {
         // the '\r' that ended the previous launch is content unless this launch starts with '\n'
         const uint32_t cls = cnt_in & 3u;
         const bool counted = CORE ? cls == 1u : (cls & 1u) != 0;
-        if (counted && lds8(t.buf_s + (uint32_t)t.vlo) != '\n') {
+        if (counted && lds8(buf_s + (uint32_t)vlo) != '\n') {
           atomicAdd(&sm.hist[cls >> 1]['\r'], 1u);
           if (!CORE && cls == 3u) {
             const u64 p = r.open - 1;
@@ -631,9 +659,9 @@ __device__ __forceinline__ void run_span(Smem& sm, const ScanArgs& a, const Sel&
         }
       }
       const int last1 = T ? (walker ? (int)sm.ti.last1 : (int)sm.nl[T - 1] + 1) : 0;  // offset of the last newline + 1
-      const u64 open_out = T ? (u64)(t.vhi - last1) : r.open + (u64)(t.vhi - t.vlo);
-      const u64 proc_end = t.toff + (u64)t.vhi;
-      if (proc_end == a.end && lds8(t.buf_s + (uint32_t)t.vhi - 1u) == '\r') {  // counted where it stands: left to the next launch / finish()
+      const u64 open_out = T ? (u64)(vhi - last1) : r.open + (u64)(vhi - vlo);
+      const u64 proc_end = toff + (u64)vhi;
+      if (proc_end == a.end && lds8(buf_s + (uint32_t)vhi - 1u) == '\r') {  // counted where it stands: left to the next launch / finish()
         const uint32_t cls = (cnt_in + T) & 3u;
         const bool counted = CORE ? cls == 1u : (cls & 1u) != 0;
         if (counted) {
@@ -644,27 +672,17 @@ __device__ __forceinline__ void run_span(Smem& sm, const ScanArgs& a, const Sel&
           }
         }
       }
-      r.prev_byte = (int)lds8(t.buf_s + (uint32_t)t.vhi - 1u);
+      r.prev_byte = (int)lds8(buf_s + (uint32_t)vhi - 1u);
       r.prev_counted = 1;
       r.cnt = cnt_in + T;
       r.seen |= T != 0;
       r.open = open_out;
       r.totalT += T;
       r.proc_end = proc_end;
-      // the span ends behind the newline that closes the last line starting inside its nominal range
-      r.stop = (ext && T) || (!ext && tile + 1 == t1 && T && last1 == t.vhi) || !have_next;
-      if (!CORE) sm.pt_lines = dense ? sm.pt_lines : (pt_flush ? line_bound : sm.pt_lines + line_bound);
-      sm.bytes_since_flush += TILE;
     }
-    __syncthreads();
-    if (sm.run.stop) {
-      if (have_next) {  // the copy of the next tile is in flight: it must have landed before the buffer is reused or the CTA exits
-        mbar_wait(bar0_s + 8u * (stage ^ 1), (par_bits >> (stage ^ 1)) & 1u);
-        par_bits ^= 1u << (stage ^ 1);
-      }
-      break;
-    }
-    if (sm.bytes_since_flush >= FLUSH_BYTES) flush_tables(sm, a.acc, tid, over, sign);
+    if (stop) break;
+    since_flush += TILE;
+    if (since_flush >= FLUSH_BYTES) { flush_tables(sm, a.acc, tid, over, sign); since_flush = 0; pt_lines = 0; }
   }
 }
 
@@ -762,7 +780,7 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a) {
     sm.len_min[0] = sm.len_min[1] = 0xFFFFFFFFu; sm.len_max[0] = sm.len_max[1] = 0;
     sm.big_min[0] = sm.big_min[1] = ~0ull; sm.big_max[0] = sm.big_max[1] = 0;
     sm.over = 0; sm.junk[0] = sm.junk[1] = 0;
-    sm.pt_lines = 0; sm.hiflag = 0; sm.bytes_since_flush = 0; sm.flag = 0;
+    sm.hiflag = 0; sm.flag = 0;
     for (int k = 0; k < 4; k++) sm.ksel[k] = 4u << (8 * k);
     for (int s = 0; s < NSTAGE; s++) mbar_init(bar0_s + 8u * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -772,7 +790,7 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a) {
   uint32_t guess = 0, guess_valid = 1;
   if (tid < 32) {
     Run r;
-    r.totalT = 0; r.proc_end = 0; r.stop = 0;
+    r.totalT = 0; r.proc_end = 0;
     if (a.pass == 1) {
       start = desc.start;
       r.open = 0; r.cnt = desc.guess_valid ? desc.guess : 0u; r.seen = 1; r.prev_byte = '\n'; r.prev_counted = 1;
@@ -852,7 +870,7 @@ __global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a) {
     flush_tables(sm, a.acc, tid, over, -1);
     if (tid == 0) {
       Run& r = sm.run;
-      r.totalT = 0; r.proc_end = 0; r.stop = 0; r.open = 0; r.cnt = desc.exact; r.seen = 1; r.prev_byte = '\n'; r.prev_counted = 1;
+      r.totalT = 0; r.proc_end = 0; r.open = 0; r.cnt = desc.exact; r.seen = 1; r.prev_byte = '\n'; r.prev_counted = 1;
       sm.len_min[0] = sm.len_min[1] = 0xFFFFFFFFu; sm.len_max[0] = sm.len_max[1] = 0;
       sm.big_min[0] = sm.big_min[1] = ~0ull; sm.big_max[0] = sm.big_max[1] = 0;
     }
