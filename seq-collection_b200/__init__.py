@@ -94,7 +94,7 @@ def load_library(path: str | None = None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("FQGPU_LIB") or LIB_PATH   # (FQGPU_LIB: tuning builds)
     if not os.path.exists(p):
         raise FqGpuError(ECUDA, f"{p} not found: build it with `python seq-collection_b200/build.py` "
                                 "(there is no CPU fallback)")

@@ -497,14 +497,18 @@ __device__ __forceinline__ void run_span(Smem& sm, const ScanArgs& a, const Sel&
       // ---- B: this thread's 64 consecutive bytes of the bitmap (written by its own warp); prefix of the newline counts ----
       w64 = lds64(bm_s + 8u * (uint32_t)tid);
       c = (uint32_t)__popcll(w64);
-      inc = warp_incl_scan(c, lane);
+      if (!__any_sync(0xffffffffu, c > 3u)) {  // counts of 0..3: the prefix from two ballots
+        const uint32_t le = lanemask_lt() | (1u << lane);
+        inc = (uint32_t)__popc(__ballot_sync(0xffffffffu, c & 1u) & le) + 2u * (uint32_t)__popc(__ballot_sync(0xffffffffu, c & 2u) & le);
+      } else {
+        inc = warp_incl_scan(c, lane);
+      }
       if (lane == 31) sm.wtot[warp] = inc;
       __syncthreads();
       {
         const uint32_t e = lane < NWARPS ? sm.wtot[lane] : 0u;
-        const uint32_t einc = warp_incl_scan(e, lane);
-        T = __shfl_sync(0xffffffffu, einc, NWARPS - 1);
-        wbase = __shfl_sync(0xffffffffu, einc - e, warp);
+        T = __reduce_add_sync(0xffffffffu, e);
+        wbase = __reduce_add_sync(0xffffffffu, lane < warp ? e : 0u);
       }
       if (!ext || T == 0 || round == 1) break;
       // the span ends with the tile's first newline: classify the tile again up to it (rare: once per span)
@@ -540,11 +544,15 @@ __device__ __forceinline__ void run_span(Smem& sm, const ScanArgs& a, const Sel&
       __syncthreads();
     } else {
       // ---- B: the thread's newlines at their slots of the index ----
-      {
-        uint32_t slot = nl_s + 2u * ex;
-        uint32_t wl = (uint32_t)w64, wh = (uint32_t)(w64 >> 32);
-        while (wl) { const uint32_t b = (uint32_t)__ffs(wl) - 1u; wl &= wl - 1u; sts16(slot, 64u * tid + b); slot += 2u; }
-        while (wh) { const uint32_t b = (uint32_t)__ffs(wh) - 1u; wh &= wh - 1u; sts16(slot, 64u * tid + 32u + b); slot += 2u; }
+      if (c) {
+        uint32_t slot = nl_s + 2u * ex, wl = (uint32_t)w64, wh = (uint32_t)(w64 >> 32);
+        const uint32_t base = 64u * (uint32_t)tid;
+        sts16(slot, base + (wl ? (uint32_t)__ffs(wl) - 1u : 31u + (uint32_t)__ffs(wh)));
+        for (uint32_t k = 1; k < c; k++) {
+          if (wl) wl &= wl - 1u; else wh &= wh - 1u;
+          slot += 2u;
+          sts16(slot, base + (wl ? (uint32_t)__ffs(wl) - 1u : 31u + (uint32_t)__ffs(wh)));
+        }
       }
       const uint32_t step = CORE ? 4u : 2u;
       const uint32_t j0 = CORE ? (1u - cnt_in) & 3u : ((cnt_in & 1u) ? 0u : 1u);
@@ -607,7 +615,8 @@ __device__ __forceinline__ void run_span(Smem& sm, const ScanArgs& a, const Sel&
         if (K == 1) K = 2;  // (the reciprocal table starts at 2)
         if (K) {
           const uint32_t nslots = nlines * K, inv = sm.inv[K];
-          for (uint32_t x = (uint32_t)tid; x < nslots; x += THREADS) {
+          // (the threads of the warps that ran the line tasks come last: the second round of slots goes to the others)
+          for (uint32_t x = ((uint32_t)tid + THREADS - 192u) & (THREADS - 1); x < nslots; x += THREADS) {
             const uint32_t line = __umulhi(x, inv);
             const uint32_t k = x - line * K;
             const u64 r = lds64(rec_s + 8u * (ql * REC_CAP + line));
@@ -623,7 +632,7 @@ __device__ __forceinline__ void run_span(Smem& sm, const ScanArgs& a, const Sel&
             }
           }
         }
-        for (uint32_t x = (uint32_t)tid; x < 2u * nlines; x += THREADS) {
+        for (uint32_t x = ((uint32_t)tid + THREADS - (ql ? 320u : 192u)) & (THREADS - 1); x < 2u * nlines; x += THREADS) {
           const uint32_t ent = lds32(part_s + 4u * (2u * ql * REC_CAP + x));
           if (ent) masked_group<CORE>(sm, ksel, buf_s, hist_s, ptab_s, masks_s, ent & 2047u, (ent >> 11) & 15u, (ent >> 15) & 31u, ent >> 21, ql, (ent >> 20) & 1u, dense, over);
         }
@@ -643,8 +652,9 @@ __device__ __forceinline__ void run_span(Smem& sm, const ScanArgs& a, const Sel&
         }
       }
     }
-    // ---- end of the tile: launch edges ('\r' whose successor lies in another launch), the running state ----
-    if (tid == 0) {
+    // ---- end of the tile: launch edges ('\r' whose successor lies in another launch), the running state (one thread of the
+    // last warp, which has no line tasks) ----
+    if (tid == THREADS - 32) {
       Run& r = sm.run;
       if (!r.prev_counted && tile == 0 && vlo == (int)a.lo0 && r.prev_byte == '\r' && r.open) {
         // the '\r' that ended the previous launch is content unless this launch starts with '\n'

@@ -15,6 +15,6 @@ for args in "" "--core" "--workload ont" "--workload ont --core"; do
   timeout 180 python tools/kbench.py --mb 8192 --reps 5 $args >> gpurun_out/kbench.log 2>&1
 done
 timeout 1200 python -m pytest tests/test_gpu_scan_tiles.py tests/test_gpu_parity.py tests/test_gpu_shards.py -q -m gpu --timeout 600 -x 2>&1 | tail -60 > gpurun_out/t1.log
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:fq_scan_kernel -c 1 -o gpurun_out/r2_span2_full python tools/kbench.py --mb 2048 --reps 1 > gpurun_out/ncu_full.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:fq_scan_kernel -c 1 -o gpurun_out/r2_span2_core python tools/kbench.py --mb 2048 --reps 1 --core > gpurun_out/ncu_core.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:fq_scan_kernel -c 1 -o gpurun_out/r2_span3_full python tools/kbench.py --mb 2048 --reps 1 > gpurun_out/ncu_full.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:fq_scan_kernel -c 1 -o gpurun_out/r2_span3_core python tools/kbench.py --mb 2048 --reps 1 --core > gpurun_out/ncu_core.log 2>&1
 cat gpurun_out/smoke.log gpurun_out/kbench.log; tail -25 gpurun_out/t1.log
