@@ -25,7 +25,7 @@ constexpr int OFF_QUAL_LEN_MAX = OFF_QUAL_LEN_MIN + 1;
 constexpr int BLOCK_WORDS = ((OFF_QUAL_LEN_MAX + 1 + 31) / 32) * 32;
 constexpr int N_SUM_WORDS = OFF_SEQ_LEN_MIN;  // words [0, N_SUM_WORDS) are sum-reduced
 
-constexpr int RESIDENT_CTAS = 296;         // CTAs resident at once: 2 per SM on a 148-SM B200
+constexpr int RESIDENT_CTAS = 592;         // most CTAs resident at once (up to 4 per SM on a 148-SM B200)
 constexpr int SPAN_WAVES = 8;              // large launches are cut into up to this many spans per resident CTA
 constexpr int MAX_SPANS = RESIDENT_CTAS * SPAN_WAVES;
 

@@ -48,13 +48,20 @@
 
 namespace fq {
 
-constexpr int THREADS = 512;
+#ifndef FQ_THREADS
+#define FQ_THREADS 512
+#endif
+#ifndef FQ_CTAS
+#define FQ_CTAS 2
+#endif
+constexpr int THREADS = FQ_THREADS;
+constexpr int CTAS_PER_SM = FQ_CTAS;
 constexpr int NWARPS = THREADS / 32;
 constexpr int GPT = 4;                        // 16-byte groups per thread and tile
 constexpr int NG = THREADS * GPT;             // groups per tile
 constexpr int TILE = NG * 16;                 // 32 KiB
 constexpr int NSTAGE = 2;
-constexpr int NL_CAP = 2048;                  // newline index; tiles with more newlines take the byte walker
+constexpr int NL_CAP = THREADS * 4;            // newline index; tiles with more newlines take the byte walker
 constexpr int REC_CAP = NL_CAP / 4 + 8;       // lines of one class with bytes in a tile
 constexpr int KMAX = 63;                      // lines with more full groups are "long"
 constexpr int LONG_CAP = TILE / (16 * (KMAX + 1)) + 2;
@@ -68,6 +75,9 @@ constexpr int MIN_SPAN_TILES = 32;            // spans are at least this long (1
 constexpr int PT_STRIDE = 33;
 constexpr int PT_COPY = 16 * PT_STRIDE;       // 528 words
 constexpr int PT_WORDS = 4 * PT_COPY;         // [odd][copy]
+// The second round of the full-group slots starts behind the warps that ran the line tasks (about 3/8 of the CTA); the
+// ragged ends of the sequence lines go to those warps, the ragged ends of the quality lines to the ones behind them.
+constexpr uint32_t ROT_FULL = (THREADS * 3 / 8) & ~31u, ROT_SPART = 0, ROT_QPART = (THREADS * 3 / 8) & ~31u;
 constexpr uint32_t FLUSH_BYTES = 4u << 20;    // 32-bit tables are added to the block at least this often
 
 struct ScanArgs {
@@ -131,7 +141,7 @@ struct __align__(128) Smem {
   Run run;
   TileInfo ti;
 };
-static_assert(sizeof(Smem) <= 115712, "two CTAs per SM");
+static_assert(sizeof(Smem) <= (CTAS_PER_SM == 2 ? 115712 : 76800), "CTAs per SM");
 
 
 // ---------------------------------------------------------------------------------------------
@@ -616,7 +626,7 @@ __device__ __forceinline__ void run_span(Smem& sm, const ScanArgs& a, const Sel&
         if (K) {
           const uint32_t nslots = nlines * K, inv = sm.inv[K];
           // (the threads of the warps that ran the line tasks come last: the second round of slots goes to the others)
-          for (uint32_t x = ((uint32_t)tid + THREADS - 192u) & (THREADS - 1); x < nslots; x += THREADS) {
+          for (uint32_t x = ((uint32_t)tid + THREADS - ROT_FULL) % THREADS; x < nslots; x += THREADS) {
             const uint32_t line = __umulhi(x, inv);
             const uint32_t k = x - line * K;
             const u64 r = lds64(rec_s + 8u * (ql * REC_CAP + line));
@@ -632,7 +642,7 @@ __device__ __forceinline__ void run_span(Smem& sm, const ScanArgs& a, const Sel&
             }
           }
         }
-        for (uint32_t x = ((uint32_t)tid + THREADS - (ql ? 320u : 192u)) & (THREADS - 1); x < 2u * nlines; x += THREADS) {
+        for (uint32_t x = ((uint32_t)tid + THREADS - (ql ? ROT_QPART : ROT_SPART)) % THREADS; x < 2u * nlines; x += THREADS) {
           const uint32_t ent = lds32(part_s + 4u * (2u * ql * REC_CAP + x));
           if (ent) masked_group<CORE>(sm, ksel, buf_s, hist_s, ptab_s, masks_s, ent & 2047u, (ent >> 11) & 15u, (ent >> 15) & 31u, ent >> 21, ql, (ent >> 20) & 1u, dense, over);
         }
@@ -763,7 +773,7 @@ __device__ __noinline__ void stitch(Smem& sm, const ScanArgs& a, int tid) {
 // CORE: FQGPU_F_CORE_ONLY (sequence lines only: what `sc fq-count` prints).  A template parameter, not a runtime
 // flag: each instantiation drops the other mode's code.
 template <bool CORE>
-__global__ void __launch_bounds__(THREADS, 2) fq_scan_kernel(const ScanArgs a) {
+__global__ void __launch_bounds__(THREADS, CTAS_PER_SM) fq_scan_kernel(const ScanArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31;
@@ -918,6 +928,7 @@ __global__ void fq_reset_kernel(u64* acc, Carry* carry, u64* ctl) {
 size_t scan_smem_bytes() { return sizeof(Smem); }
 int scan_tile_bytes() { return TILE; }
 int scan_threads() { return THREADS; }
+int scan_ctas_per_sm() { return CTAS_PER_SM; }
 
 cudaError_t scan_configure() {
   cudaError_t e = cudaFuncSetAttribute(fq_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));

@@ -102,7 +102,7 @@ int fqgpu_create(fqgpu_ctx** out, const fqgpu_config* cfg) {
   CU_NEW(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
   CU_NEW(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   CU_NEW(fq::scan_configure());
-  ctx->grid = prop.multiProcessorCount * 2;
+  ctx->grid = prop.multiProcessorCount * fq::scan_ctas_per_sm();
   if (ctx->grid > fq::RESIDENT_CTAS) ctx->grid = fq::RESIDENT_CTAS;
   CU_NEW(cudaMalloc(&ctx->d_acc, fq::BLOCK_WORDS * sizeof(u64)));
   CU_NEW(cudaMalloc(&ctx->d_ctl, fq::CTL_WORDS * sizeof(u64)));

@@ -13,6 +13,7 @@ typedef unsigned long long u64;
 size_t scan_smem_bytes();
 int scan_tile_bytes();
 int scan_threads();
+int scan_ctas_per_sm();
 cudaError_t scan_configure();
 cudaError_t launch_reset(u64* acc, Carry* carry, u64* ctl, cudaStream_t st);
 cudaError_t launch_scan(const void* ptr, size_t nbytes, Carry* carry, ShardInfo* shard, u64* acc, SpanDesc* desc, u64* ctl,
