@@ -14,6 +14,11 @@ is needed between steps.
 `e2e`     : the same metric through the C ABI with HOST buffers (pinned), H2D inside the timed region.
 `roofline`: algorithmic bytes (1 per input byte) / device time, against the measured HBM
             peak of MEASURED_PEAKS.json.
+`stats_digest`: sha256 of the fqgpu_stats struct the timed steps produced.  The N-GPU runs scan the same 36.0 GB stream, so
+            the digests of N = 1, 2, 4, 8 must be identical (BASELINE configs[2]: "must equal config 2's bit-for-bit"); on
+            top of that every run asserts the FULL struct against the generator's own tallies (fqgpu_synth_illumina_tally:
+            derived from the random numbers, no byte is read; pinned by the CPU twin oracle/fq_synth_twin.c).
+`ont`, `gz` : BASELINE configs[3] and [4] next to the headline (N = 1 only).
 `cpu_baseline` / `--impl reference`: the reference's own work shape (oracle/fq_oracle.c
             fqo_ref_fq_count_mem: line reader + three count passes, src/fq_count.nim:38-45) on the host
             cores of this box.  The Nim reference itself cannot be built here (no Nim toolchain), and it is
@@ -38,6 +43,46 @@ REC_BYTES = 360
 SEED_ILLUMINA = 20240229
 SEED_ONT = 20240301
 METRIC = "fastq_scan_throughput"
+
+
+def workload_config(args, world: int) -> dict:
+    """The `config` object of the JSON line: identical for the repo arm and the reference arm."""
+    total_bytes = args.records * REC_BYTES if args.workload == "illumina" else int(args.ont_gb * 1e9)
+    return {"workload": args.workload_name, "bytes": total_bytes, "record_bytes": REC_BYTES,
+            "seed": SEED_ILLUMINA if args.workload == "illumina" else SEED_ONT,
+            "sharding": f"byte ranges over {world} rank(s), one SUM all-reduce" if world > 1 else "none",
+            "l2": "input >> 126 MB L2, no flush needed", "meta_records": args.meta_records,
+            "stats": "full (fq-count + A/C/G/T/N, length tables, quality histogram, per-position sums, fq-meta range)"}
+
+
+def stats_digest(st) -> str:
+    import hashlib
+
+    return hashlib.sha256(bytes(st)).hexdigest()
+
+
+def twin_sample(nbytes: int):
+    """`nbytes` of the synthetic stream from the CPU twin of the generator (oracle/fq_synth_twin.c), in parallel slices."""
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import fq_oracle as O
+    import ctypes as C
+
+    out = np.empty(nbytes, dtype=np.uint8)
+    L = O.lib()
+    nthr = max(1, min(16, os.cpu_count() or 1))
+    step = -(-nbytes // nthr)
+    step += -step % REC_BYTES
+
+    def fill(i):
+        lo = i * step
+        n = max(0, min(step, nbytes - lo))
+        if n:
+            L.fqo_synth_illumina_bytes(C.c_void_p(out.ctypes.data + lo), lo, n, SEED_ILLUMINA)
+
+    with ThreadPoolExecutor(max_workers=nthr) as pool:
+        list(pool.map(fill, range(nthr)))
+    return out
 
 
 def measured_traffic_ratio():
@@ -128,25 +173,16 @@ def cpu_reference_leg(sample, seconds_budget: float = 20.0):
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU path (restated; see module docstring) on this box's host cores."""
+    """--impl reference: the reference's CPU path (restated; see module docstring) on this box's host cores.  Nothing of
+    libfqgpu is loaded: the sample comes from the CPU twin of the generator."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return 0
-    import numpy as np
-    import torch
-
-    import seq_collection_b200 as fq
-
-    # the same synthetic bytes as our arm (generated on the GPU, copied back once), bounded sample
-    sample_bytes = min(args.records * REC_BYTES, REC_BYTES * (args.ref_sample_mb << 20) // REC_BYTES)
+    # the same synthetic bytes as our arm, bounded sample
+    sample_bytes = min(args.records * REC_BYTES, REC_BYTES * ((args.ref_sample_mb << 20) // REC_BYTES))
     sample_bytes -= sample_bytes % REC_BYTES
-    torch.cuda.set_device(0)
-    buf = torch.empty(sample_bytes, dtype=torch.uint8, device="cuda")
-    with fq.FqGpu(device=0) as ctx:
-        ctx.synth_illumina(buf.data_ptr(), sample_bytes, 0, sample_bytes // REC_BYTES, SEED_ILLUMINA)
-    host = buf.cpu().numpy()
-    del buf
-    from oracle import fq_oracle as O
+    host = twin_sample(sample_bytes)
 
     vals, reads_s = [], []
     per_step_budget = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
@@ -160,14 +196,109 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "GB/s", "reads_per_s": statistics.mean(reads_s),
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": used / v / 1e6,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": args.workload_name, "records": args.records, "record_bytes": REC_BYTES},
+        "config": workload_config(args, max(world, args.gpus)),
         "cpu_baseline": {"value": v, "unit": "GB/s", "cores": 1, "kind": "port",
-                         "sample": f"{used / 1e9:.2f} GB prefix of the same synthetic stream, in host RAM; C restatement of "
-                                   "src/fq_count.nim:38-45 (Nim toolchain absent; reference is single-threaded)"},
+                         "sample": f"{used / 1e9:.2f} GB prefix of the same synthetic stream (CPU twin of the generator), in host RAM; "
+                                   "C restatement of src/fq_count.nim:38-45 (Nim toolchain absent; the reference is single-threaded "
+                                   "for this command, so one core is all it can use)"},
         "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
     return 0
+
+
+def single_member_gzip(raw: bytes, level: int = 6) -> bytes:
+    """ONE gzip member holding `raw` (what `gzip -6` writes, compressed pigz-style by a thread pool: independent raw-deflate
+    pieces joined at sync-flush boundaries are one valid DEFLATE stream)."""
+    import struct
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+
+    piece = 8 << 20
+    chunks = [raw[i:i + piece] for i in range(0, len(raw), piece)] or [b""]
+
+    def comp(args):
+        i, c = args
+        co = zlib.compressobj(level, zlib.DEFLATED, -15)
+        return co.compress(c) + co.flush(zlib.Z_FINISH if i == len(chunks) - 1 else zlib.Z_SYNC_FLUSH)
+
+    with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as pool:
+        parts = list(pool.map(comp, enumerate(chunks)))
+    return (struct.pack("<BBBBIBB", 0x1F, 0x8B, 8, 0, 0, 0, 0xFF) + b"".join(parts)
+            + struct.pack("<II", zlib.crc32(raw) & 0xFFFFFFFF, len(raw) & 0xFFFFFFFF))
+
+
+def gz_leg(fq, ctx, n_records: int):
+    """BASELINE configs[4]: gzip-compressed 2x150 bp FASTQ end to end (a single-member .fq.gz inflated on the host through
+    zlib into the pinned ring -- the reference's gzip_stream path), fq-count row + fq-meta quality range with
+    -n <all records>; reported in GB/s of UNCOMPRESSED bytes.  The rows are checked against the generator's tallies."""
+    import shutil
+    import tempfile
+
+    import torch
+
+    tmp = tempfile.mkdtemp(prefix="fqgpu_gz_")
+    try:
+        n = n_records * REC_BYTES
+        dev = torch.empty(n + 256, dtype=torch.uint8, device="cuda")
+        ctx.synth_illumina(dev.data_ptr(), n, 0, n_records, SEED_ILLUMINA)
+        raw = dev[:n].cpu().numpy().tobytes()
+        del dev
+        path = os.path.join(tmp, "reads.fq.gz")
+        t0 = time.perf_counter()
+        blob = single_member_gzip(raw)
+        with open(path, "wb") as f:
+            f.write(blob)
+        t_comp = time.perf_counter() - t0
+        with fq.FqGpu(meta_records=n_records) as g:
+            want = g.synth_illumina_tally(0, n_records, SEED_ILLUMINA)
+            best = 1e9
+            for _ in range(2):
+                t0 = time.perf_counter()
+                st = g.count_file(path)
+                best = min(best, time.perf_counter() - t0)
+            assert bytes(st) == bytes(want), "gz end to end: result differs from the generator's tallies"
+            members = g.bgzf_members()
+        return {"value": n / best / 1e9, "unit": "GB/s of uncompressed bytes", "records": n_records, "raw_bytes": n, "gz_bytes": len(blob),
+                "seconds": best, "fq_count_row": fq.fq_count_row(st), "fq_meta": {"min_qual": st.meta_qual_min, "max_qual": st.meta_qual_max, "n_lines": st.meta_lines // 4},
+                "members_inflated_on_device": members,
+                "note": "single-member gzip (level 6): one serial DEFLATE stream, inflated by zlib on ONE host thread (the reference's "
+                        f"gzip_stream path) into the pinned ring; the scan overlaps the inflate; wall clock, best of 2 (the file was written in {t_comp:.1f} s)"}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def ont_leg(fq, device: int, gb: float, meta_records: int, steps: int, peak: float):
+    """BASELINE configs[3]: synthetic ONT-style long reads (lengths 1-100 kb log-normal), HBM-resident, full statistics."""
+    import torch
+
+    cap = int(gb * 1e9)
+    buf = torch.empty(cap + (1 << 20), dtype=torch.uint8, device="cuda")
+    n_rec = int(cap / 27200)  # mean record ~ 2*13.5 kB + header
+    with fq.FqGpu(device=device, meta_records=meta_records) as c:
+        nbytes = c.synth_ont(buf.data_ptr(), cap + (1 << 20), 0, n_rec, SEED_ONT)
+        for _ in range(2):
+            st = c.count_device(buf.data_ptr(), nbytes)
+        ms = 0.0
+        for _ in range(steps):
+            st = c.count_device(buf.data_ptr(), nbytes)
+            ms += c.last_timing()[0]
+        # invariants of the shape (every line of a record is whole: chunk-edge record carry)
+        assert st.reads == n_rec and st.lines == 4 * n_rec and st.bytes == nbytes, (st.reads, st.lines, st.bytes)
+        assert st.bases == sum(st.qual_counts) == sum(st.base_counts) and st.seq_lines == st.qual_lines == n_rec
+        assert 1000 <= st.seq_len_min <= st.seq_len_max <= 100000 and (st.seq_len_min, st.seq_len_max) == (st.qual_len_min, st.qual_len_max)
+        assert sum(st.base_counts[ord(ch)] for ch in "ACGT") == st.bases and st.n_bases == 0
+        assert sum(st.qual_pos_sum) == sum(i * v for i, v in enumerate(st.qual_counts))
+        # the same stream in two launches cut at an awkward offset (8 MiB + 13) gives the same struct
+        c.reset()
+        cut = (8 << 20) + 13
+        c.scan_device(buf.data_ptr(), cut)
+        c.scan_device(buf.data_ptr() + cut, nbytes - cut)
+        assert bytes(c.finish()) == bytes(st), "ONT: split scan differs"
+        v = nbytes / (ms / steps * 1e6)
+        return {"value": v, "unit": "GB/s", "frac_of_hbm_peak": v / peak, "bytes": nbytes, "reads": n_rec, "steps": steps,
+                "reads_per_s": n_rec / (ms / steps / 1e3), "stats_digest": stats_digest(st),
+                "note": "full statistics, HBM-resident, CUDA events on the library stream; invariants of the shape and a split scan asserted"}
 
 
 def _bgzf_member(chunk: bytes) -> bytes:
@@ -254,6 +385,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ingest", action="store_true", help="skip the file-ingest figures (plain file and BGZF through fqgpu_count_file)")
+    ap.add_argument("--no-ont", action="store_true", help="skip the ONT figure (BASELINE configs[3]) of the N=1 line")
+    ap.add_argument("--no-gz", action="store_true", help="skip the gzip end-to-end figure (BASELINE configs[4]) of the N=1 line")
+    ap.add_argument("--gz-records", type=int, default=4_000_000, help="records of the gzip end-to-end file (SURVEY 8d config 5: 4 M = 1.44 GB raw)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "fqgpu" else args.warmup
     args.workload_name = ("synthetic Illumina 2x150 bp uncompressed FASTQ, %d reads, phred+33" % args.records
@@ -278,6 +412,24 @@ def main():
 
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    if args.workload == "ont":  # BASELINE configs[3] as the headline of this run (single GPU)
+        assert world == 1, "the ONT workload is a single-GPU config (BASELINE.json configs[3])"
+        peak, peak_src = measured_hbm_peak()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        o = ont_leg(fq, local_rank, args.ont_gb, args.meta_records, args.steps, peak)
+        clocks = sampler.stop()
+        ms = o["bytes"] / o["value"] / 1e6
+        cfg = workload_config(args, 1)
+        cfg["bytes"] = o["bytes"]
+        print(json.dumps({"metric": METRIC, "value": o["value"], "unit": "GB/s", "reads_per_s": o["reads_per_s"], "n_gpus": 1, "steps": args.steps,
+                          "warmup": 2, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+                          "data": "synthetic", "config": cfg, "stats_digest": o["stats_digest"], "clocks": clocks,
+                          "roofline": {"bound": "hbm", "achieved": o["value"], "peak": peak, "unit": "GB/s", "frac": o["value"] / peak,
+                                       "traffic": None, "peak_source": peak_src}, "gpu_launches": int(args.steps * 4),
+                          "e2e": None, "cpu_baseline": None, "note": o["note"]}))
+        return 0
 
     ctx = fq.FqGpu(device=local_rank, meta_records=args.meta_records)
 
@@ -364,10 +516,15 @@ def main():
     ms_per_step = span_ms / args.steps
     value = total_bytes / (ms_per_step * 1e6)
 
-    # sanity of the result (size-independent invariants; full parity lives in tests/)
-    if args.workload == "illumina":
-        assert st.reads == args.records and st.bases == 150 * args.records, (st.reads, st.bases)
-        assert st.lines == 4 * args.records and sum(st.qual_counts) == 150 * args.records
+    # ---- the result: the FULL fqgpu_stats of the whole stream against the generator's own tallies (derived from the
+    # random numbers, no byte read; oracle/fq_synth_twin.c pins the tally kernel) -- at every N, so that the digests of
+    # N = 1, 2, 4, 8 are provably the digest of the same struct ----
+    digest = stats_digest(st)
+    tally = ctx.synth_illumina_tally(0, args.records, SEED_ILLUMINA)
+    if bytes(st) != bytes(tally):
+        got, want = st.to_dict(), tally.to_dict()
+        bad = [k for k in want if got[k] != want[k]]
+        raise AssertionError(f"scan result differs from the generator's tallies in {bad[:8]}")
 
     # ---- the same bytes in core-only mode (FQGPU_F_CORE_ONLY: exactly what `sc fq-count` prints) ----
     # An extra figure next to the headline (which stays the full statistics set); N=1 only.
@@ -382,7 +539,9 @@ def main():
             cst = cctx.count_device(buf.data_ptr(), nbytes)
             cms += cctx.last_timing()[0]
         assert (cst.reads, cst.bases, cst.gc_bases, cst.n_bases) == (st.reads, st.bases, st.gc_bases, st.n_bases)
-        core = {"value": nbytes / (cms / ncore * 1e6), "unit": "GB/s", "steps": ncore,
+        assert bytes(cst) == bytes(cctx.synth_illumina_tally(0, args.records, SEED_ILLUMINA)), "core-only result differs from the generator's tallies"
+        core = {"value": nbytes / (cms / ncore * 1e6), "unit": "GB/s", "steps": ncore, "frac_of_hbm_peak": nbytes / (cms / ncore * 1e6) / measured_hbm_peak()[0],
+                "stats_digest": stats_digest(cst), "fq_count_row": fq.fq_count_row(cst),
                 "stats": "reads, bases, G/C/N and sequence-length tables only (quality lines are not examined)"}
         cctx.close()
 
@@ -402,6 +561,22 @@ def main():
         host = torch.empty(sample, dtype=torch.uint8, pin_memory=True)
         host.copy_(dev[:sample])
         torch.cuda.synchronize()
+        # the ceiling of this leg: the pinned host -> device copy rate of this box, measured here (one rank alone would see
+        # the PCIe link; with every rank copying at once it is the host memory / root-complex share of each)
+        h2d_n = min(sample, 2 << 30)
+        barrier()
+        h2d_best = 0.0
+        for _ in range(3):
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            dev[:h2d_n].copy_(host[:h2d_n], non_blocking=True)
+            c1.record()
+            torch.cuda.synchronize()
+            h2d_best = max(h2d_best, h2d_n / (c0.elapsed_time(c1) * 1e6))
+        th = torch.tensor([h2d_best], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(th, op=dist.ReduceOp.SUM)
+        h2d_total = float(th.cpu()[0])
         ectx = fq.FqGpu(device=local_rank, meta_records=args.meta_records)
         e_lib_stream = torch.cuda.ExternalStream(ectx.stream)
 
@@ -443,6 +618,8 @@ def main():
         e2e = {"value": total_sample / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": sample,
                "d2h_bytes_per_step": 8 * 2144 + 80 if world == 1 else 8 * world * ctx.shard_block_words(),
                "reads_per_s": est.reads / e2e_s,
+               "roofline": {"bound": "pinned host->device copy", "peak": h2d_total, "unit": "GB/s", "frac": total_sample / e2e_s / 1e9 / h2d_total,
+                            "how": f"cudaMemcpyAsync of {h2d_n / 1e9:.2f} GB pinned -> device per rank, CUDA events, best of 3, all {world} rank(s) copying at once; sum over ranks"},
                "sample": f"{total_sample / 1e9:.2f} GB prefix of the stream in pinned host memory ({sample / 1e9:.2f} GB per rank), "
                          "streamed in 64 MiB chunks (copy stream overlaps the scan stream); wall clock, max over ranks"}
         ectx.close()
@@ -493,6 +670,21 @@ def main():
         except Exception as e:  # never lets the extra figures break the contract line
             index = {"error": repr(e)[:200]}
 
+    ont = gz = None
+    if world == 1 and rank == 0 and args.workload == "illumina":
+        del buf
+        torch.cuda.empty_cache()
+        if not args.no_ont:
+            try:
+                ont = ont_leg(fq, local_rank, args.ont_gb, args.meta_records, max(3, min(args.steps, 5)), measured_hbm_peak()[0])
+            except Exception as e:  # never lets the extra figures break the contract line
+                ont = {"error": repr(e)[:300]}
+        if not args.no_gz:
+            try:
+                gz = gz_leg(fq, ctx, args.gz_records)
+            except Exception as e:
+                gz = {"error": repr(e)[:300]}
+
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         tr = measured_traffic_ratio()
@@ -505,26 +697,27 @@ def main():
             "wall_ms_per_step": wall_ms / args.steps,
             "higher_is_better": True, "scaling": "strong" if args.workload == "illumina" else "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": args.workload_name, "bytes": total_bytes, "record_bytes": REC_BYTES,
-                       "seed": SEED_ILLUMINA if args.workload == "illumina" else SEED_ONT,
-                       "sharding": f"byte ranges over {world} rank(s), one SUM all-reduce" if world > 1 else "none",
-                       "l2": "input >> 126 MB L2, no flush needed", "meta_records": args.meta_records,
-                       "stats": "full (fq-count + A/C/G/T/N, length tables, quality histogram, per-position sums, fq-meta range)"},
+            "config": workload_config(args, world),
+            "stats_digest": digest,
+            "result_check": "the full fqgpu_stats struct equals the generator's tallies (fqgpu_synth_illumina_tally) for the whole stream",
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (tr[0] * nbytes / max(1.0, scan_launches_per_step)) if tr else None,
                          "traffic_unit": "bytes per launch", "traffic_source": tr[1] if tr else None,
                          "algorithmic_bytes_per_launch": nbytes / max(1.0, scan_launches_per_step),
                          "peak_source": peak_src,
                          "note": "algorithmic bytes = input bytes (1 B read per byte); device time = CUDA events around "
-                                 "memset+meta+scan+reduce on the library stream (scan kernel ~ 99 %; the fq-meta prefix kernel runs beside it)"},
+                                 "the two scan launches (every span; the spans whose guessed phase was wrong -- none here) on the library "
+                                 "stream, the fq-meta prefix kernel beside them"},
             "clocks": clocks,
-            # per scan call: meta + resync + scan + stitch + scan(pass 1); per step also reset + reduce
-            "gpu_launches": int(args.steps * (scan_launches_per_step * (5 if args.meta_records else 4) + 2)),
+            # per step: reset + fq-meta prefix + the two scan launches (+ the pack kernel of a shard)
+            "gpu_launches": int(args.steps * (scan_launches_per_step + (1 if args.meta_records else 0) + 1 + (1 if world > 1 else 0))),
             "e2e": e2e,
             "cpu_baseline": cpu,
             "core_only": core,
             "ingest": ingest,
             "index": index,
+            "ont": ont,
+            "gz": gz,
         }
         print(json.dumps(line))
     ctx.close()

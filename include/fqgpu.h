@@ -136,7 +136,8 @@ int fqgpu_scan_host(fqgpu_ctx* ctx, const void* buf, size_t nbytes);
 
 /* Whole-buffer conveniences on top of the streaming interface. */
 int fqgpu_count_host(fqgpu_ctx* ctx, const void* buf, size_t nbytes, fqgpu_stats* out); /* pageable host memory */
-int fqgpu_count_file(fqgpu_ctx* ctx, const char* path, fqgpu_stats* out); /* plain or .gz (zlib inflate on host) */
+int fqgpu_count_file(fqgpu_ctx* ctx, const char* path, fqgpu_stats* out); /* plain or .gz (zlib inflate on host); FQGPU_EIO only when the
+   file cannot be OPENED (exit 2 in the reference); a gz stream that turns out truncated / corrupt ends where zlib stops, like the reference's */
 /* Same with the stream kind chosen by the caller: fq_count picks gz by a case-SENSITIVE ".gz" suffix
  * (src/fq_count.nim:31), fq_meta by a case-INsensitive one (src/fq_meta.nim:219). */
 int fqgpu_count_file_as(fqgpu_ctx* ctx, const char* path, int as_gz, fqgpu_stats* out);
@@ -250,6 +251,11 @@ int fqgpu_dedup_host(fqgpu_ctx* ctx, const void* host, size_t nbytes, uint8_t* h
  * rank generate its own shard.  Both write whole records only and return the bytes written. */
 int fqgpu_synth_illumina(fqgpu_ctx* ctx, void* dptr, size_t capacity, uint64_t first_record,
                          uint64_t n_records, uint64_t seed, size_t* bytes_written);
+/* The generator's own tallies: what the scan must report for records [first_record, first_record + n_records) of the
+ * Illumina stream as one whole stream (every field of fqgpu_stats, the fq-meta fields for the context's meta_records),
+ * derived from the random numbers alone -- no byte is generated or read.  An independent check of the scan at any size
+ * (bench.py asserts it on the 36 GB run); oracle/fq_synth_twin.c is its CPU twin. */
+int fqgpu_synth_illumina_tally(fqgpu_ctx* ctx, uint64_t first_record, uint64_t n_records, uint64_t seed, fqgpu_stats* out);
 int fqgpu_synth_ont(fqgpu_ctx* ctx, void* dptr, size_t capacity, uint64_t first_record,
                     uint64_t n_records, uint64_t seed, size_t* bytes_written);
 /* Arbitrary byte range [first_byte, first_byte+nbytes) of the Illumina stream (a shard may start

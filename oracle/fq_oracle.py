@@ -82,8 +82,8 @@ def lib():
     global _lib
     if _lib is None:
         path = os.path.join(HERE, "libfqoracle.so")
-        src = os.path.join(HERE, "fq_oracle.c")
-        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+        srcs = [os.path.join(HERE, f) for f in ("fq_oracle.c", "fq_synth_twin.c")]
+        if not os.path.exists(path) or any(os.path.getmtime(path) < os.path.getmtime(f) for f in srcs):
             build()
         L = C.CDLL(path)
         L.fqo_stats_size.restype = C.c_size_t
@@ -102,6 +102,10 @@ def lib():
         L.fqo_ref_fq_count_file.restype = C.c_int
         L.fqo_ref_fq_count_mem.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]
         L.fqo_ref_fq_count_mem.restype = None
+        L.fqo_synth_illumina_bytes.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]
+        L.fqo_synth_illumina_bytes.restype = None
+        L.fqo_synth_illumina_tally.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(Stats)]
+        L.fqo_synth_illumina_tally.restype = None
         _lib = L
     return _lib
 
@@ -130,6 +134,24 @@ def count(data, meta_records: int = 0, chunk: int = 0) -> dict:
     else:
         lib().fqo_count_buffer(addr, n, meta_records, C.byref(st))
     del keep
+    return stats_to_dict(st)
+
+
+def synth_illumina_bytes(first_byte: int, nbytes: int, seed: int = 20240229):
+    """CPU twin of the GPU generator (oracle/fq_synth_twin.c): bytes [first_byte, first_byte + nbytes) of the synthetic
+    Illumina 2x150 stream as a numpy uint8 array."""
+    import numpy as np
+
+    out = np.empty(nbytes, dtype=np.uint8)
+    lib().fqo_synth_illumina_bytes(out.ctypes.data, first_byte, nbytes, seed)
+    return out
+
+
+def synth_illumina_tally(first_record: int, n_records: int, seed: int = 20240229, meta_records: int = 0) -> dict:
+    """Expected statistics of records [first_record, first_record + n_records) of that stream, derived from the random
+    numbers alone (no bytes are read back): an independent check of the scan at any size."""
+    st = Stats()
+    lib().fqo_synth_illumina_tally(first_record, n_records, seed, meta_records, C.byref(st))
     return stats_to_dict(st)
 
 

@@ -132,6 +132,7 @@ def load_library(path: str | None = None):
         "fqgpu_stream": (vp, [vp]),
         "fqgpu_synth_illumina": (i32, [vp, vp, sz, u64, u64, u64, C.POINTER(sz)]),
         "fqgpu_synth_illumina_bytes": (i32, [vp, vp, u64, u64, u64]),
+        "fqgpu_synth_illumina_tally": (i32, [vp, u64, u64, u64, C.POINTER(Stats)]),
         "fqgpu_synth_ont": (i32, [vp, vp, sz, u64, u64, u64, C.POINTER(sz)]),
         "fqgpu_index_device": (i32, [vp, vp, sz, vp, u64, C.POINTER(u64)]),
         "fqgpu_headers_device": (i32, [vp, vp, sz, vp, u64, C.c_uint32, vp, vp]),
@@ -156,7 +157,7 @@ EXPORTED_SYMBOLS = [
     "fqgpu_scan_host", "fqgpu_count_host", "fqgpu_count_file", "fqgpu_count_file_as", "fqgpu_count_files", "fqgpu_bgzf_members", "fqgpu_meta_file_as", "fqgpu_count_file_sharded", "fqgpu_scan_device", "fqgpu_count_device",
     "fqgpu_shard_block_words", "fqgpu_shard_begin", "fqgpu_shard_export", "fqgpu_shard_combine",
     "fqgpu_shard_rescan", "fqgpu_shard_combine_host", "fqgpu_last_timing", "fqgpu_stream", "fqgpu_synth_illumina",
-    "fqgpu_synth_illumina_bytes", "fqgpu_synth_ont", "fqgpu_index_device", "fqgpu_headers_device", "fqgpu_dedup_device", "fqgpu_dedup_host", "fqgpu_index_lines",
+    "fqgpu_synth_illumina_bytes", "fqgpu_synth_illumina_tally", "fqgpu_synth_ont", "fqgpu_index_device", "fqgpu_headers_device", "fqgpu_dedup_device", "fqgpu_dedup_host", "fqgpu_index_lines",
 ]
 
 
@@ -306,6 +307,12 @@ class FqGpu:
         w = C.c_size_t()
         self._check(self.lib.fqgpu_synth_illumina(self._ctx, dptr, capacity, first_record, n_records, seed, C.byref(w)))
         return w.value
+
+    def synth_illumina_tally(self, first_record: int, n_records: int, seed: int) -> "Stats":
+        """The generator's own tallies for records [first_record, first_record + n_records): see fqgpu.h."""
+        st = Stats()
+        self._check(self.lib.fqgpu_synth_illumina_tally(self._ctx, first_record, n_records, seed, C.byref(st)))
+        return st
 
     def synth_illumina_bytes(self, dptr: int, first_byte: int, nbytes: int, seed: int):
         self._check(self.lib.fqgpu_synth_illumina_bytes(self._ctx, dptr, first_byte, nbytes, seed))

@@ -309,7 +309,8 @@ int fqgpu_index_device(fqgpu_ctx* ctx, const void* dptr, size_t nbytes, uint64_t
     // to fill the machine: 256 KiB tiles from 320 MiB, 128 KiB from 160 MiB, else 64 KiB (measured 4.4 / 4.8 / 5.0 TB/s
     // with 64 / 128 / 256 KiB tiles at 8.6 GB); FQGPU_INDEX_ROWS = 16 | 32 | 64 forces one (tests)
     const char* re = getenv("FQGPU_INDEX_ROWS");
-    const int rows = re ? atoi(re) : nbytes >= ((size_t)320 << 20) ? 64 : nbytes >= ((size_t)160 << 20) ? 32 : 16;
+    int rows = re ? atoi(re) : nbytes >= ((size_t)320 << 20) ? 64 : nbytes >= ((size_t)160 << 20) ? 32 : 16;
+    if (rows != 16 && rows != 32 && rows != 64) rows = 16;  // (only these three are instantiated)
     const fq::u64 tile_bytes = (fq::u64)fq::IDX_THREADS * 16 * (fq::u64)rows;
     const fq::u64 ntiles = (end + tile_bytes - 1) / tile_bytes;
     fq::u64* d_state = nullptr;  // [ntiles] tile states, then the ticket counter, lines, records

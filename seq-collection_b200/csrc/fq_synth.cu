@@ -86,6 +86,56 @@ cudaError_t launch_synth_illumina(void* dptr, u64 first_byte, u64 nbytes, u64 se
   return cudaGetLastError();
 }
 
+// The generator's own tallies ("emitting their own expected tallies as a third, independent
+// check"): the statistics of records [first, first + n) from the random numbers alone -- no byte is written or read,
+// nothing of the scan is involved.  out[0..4] = A C G T N, out[5..8] = F : , #, out[16 + p] = sum of the quality bytes
+// at position p.  Thread (r, q) takes quad q of records r, r + R, ...
+constexpr int ILL_QUADS = (ILL_LEN + 3) / 4;
+__global__ void synth_illumina_tally_kernel(u64 first_record, u64 n_records, u64 seed, u64* __restrict__ out) {
+  const u64 gt = (u64)blockIdx.x * blockDim.x + threadIdx.x, total = (u64)gridDim.x * blockDim.x;
+  const u64 R = total / ILL_QUADS;
+  if (gt >= R * ILL_QUADS) return;
+  const int q = (int)(gt % ILL_QUADS);
+  unsigned long long cb[5] = {0, 0, 0, 0, 0}, cq[4] = {0, 0, 0, 0}, ps[4] = {0, 0, 0, 0};
+  for (u64 i = gt / ILL_QUADS; i < n_records; i += R) {
+    const u64 rec = first_record + i;
+    const u64 rb = splitmix64(seed ^ (rec * 128ull + (u64)q) * 0x9E3779B97F4A7C15ull);
+    const u64 rq = splitmix64(seed ^ (rec * 128ull + 64ull + (u64)q) * 0x9E3779B97F4A7C15ull);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      if (4 * q + j >= ILL_LEN) break;
+      const uint32_t ub = (uint32_t)(rb >> (16 * j)) & 0xFFFFu, uq = (uint32_t)(rq >> (16 * j)) & 0xFFFFu;
+      cb[ub < 19300u ? 0 : ub < 32735u ? 1 : ub < 46170u ? 2 : ub < 65470u ? 3 : 4]++;
+      const int qi = uq < 58982u ? 0 : uq < 62914u ? 1 : uq < 65208u ? 2 : 3;
+      cq[qi]++;
+      ps[j] += qi == 0 ? 'F' : qi == 1 ? ':' : qi == 2 ? ',' : '#';
+    }
+  }
+  for (int k = 0; k < 5; k++) if (cb[k]) atomicAdd(&out[k], cb[k]);
+  for (int k = 0; k < 4; k++) if (cq[k]) atomicAdd(&out[5 + k], cq[k]);
+  for (int j = 0; j < 4; j++) if (ps[j]) atomicAdd(&out[16 + 4 * q + j], ps[j]);
+}
+// quality range of the first m records (the fq-meta fold), on the host
+void synth_illumina_meta_range(u64 first_record, u64 m, u64 seed, long long* qmin, long long* qmax) {
+  int mn = 1000, mx = -1;
+  for (u64 i = 0; i < m; i++) {
+    const u64 rec = first_record + i;
+    for (int q = 0; q < ILL_QUADS; q++) {
+      const u64 rq = splitmix64(seed ^ (rec * 128ull + 64ull + (u64)q) * 0x9E3779B97F4A7C15ull);
+      for (int j = 0; j < 4 && 4 * q + j < ILL_LEN; j++) {
+        const uint32_t uq = (uint32_t)(rq >> (16 * j)) & 0xFFFFu;
+        const int v = (uq < 58982u ? 'F' : uq < 62914u ? ':' : uq < 65208u ? ',' : '#') - 33;
+        mn = v < mn ? v : mn; mx = v > mx ? v : mx;
+      }
+    }
+  }
+  *qmin = m ? mn : -1; *qmax = m ? mx : -1;
+}
+cudaError_t launch_synth_illumina_tally(u64 first_record, u64 n_records, u64 seed, u64* d_out /* [16 + 152] zeroed */, cudaStream_t st) {
+  synth_illumina_tally_kernel<<<148 * 8, 256, 0, st>>>(first_record, n_records, seed, d_out);
+  return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------
 // ONT-style long reads: L = clip(round(exp(N(ln 9000, 0.9))), 1000, 100000); header
 //   "@<32 hex> runid=<40 hex> read=<n> ch=<1..512> start_time=2026-01-01T00:00:00Z"

@@ -589,8 +589,9 @@ int fqgpu_count_file_as(fqgpu_ctx* ctx, const char* path, int as_gz, fqgpu_stats
         size_t want = cap - got;
         if (want > ((size_t)1 << 30)) want = (size_t)1 << 30;
         int r = gzread(f, chunk + got, (unsigned)want);
-        if (r < 0) { gzclose(f); return fail(ctx, FQGPU_EIO, std::string("gzread failed: ") + path); }
-        if (r == 0) break;
+        // a truncated / corrupt stream simply ENDS, as in the reference (gzip_stream.nim:16-17 hands gzread's result to the
+        // stream, whose atEnd() then holds): the lines inflated so far are counted and the row is printed
+        if (r <= 0) break;
         got += (size_t)r;
       }
       if (got == 0) break;
@@ -659,8 +660,8 @@ int fqgpu_meta_file_as(fqgpu_ctx* ctx, const char* path, int as_gz, fqgpu_stats*
     while (got < cap && lines < want_lines) {  // small reads: the head is a few KB to MB
       const size_t piece = cap - got < ((size_t)1 << 20) ? cap - got : ((size_t)1 << 20);
       long r = gf ? (long)gzread(gf, chunk + got, (unsigned)piece) : (long)read(fd, chunk + got, piece);
-      if (r < 0) return done(fail(ctx, FQGPU_EIO, std::string(gf ? "gzread failed: " : "read failed: ") + path));
-      if (r == 0) { eof = true; break; }
+      if (r < 0 && !gf) return done(fail(ctx, FQGPU_EIO, std::string("read failed: ") + path));
+      if (r <= 0) { eof = true; break; }  // (a corrupt gz stream ends here, like the reference's)
       const uint8_t* p = chunk + got;
       const uint8_t* end = p + r;
       while (p < end && lines < want_lines) {  // the stream ends with the newline that completes the last sampled line
@@ -838,6 +839,40 @@ int fqgpu_synth_illumina_bytes(fqgpu_ctx* ctx, void* dptr, uint64_t first_byte, 
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   CU_TRY(ctx, fq::launch_synth_illumina(dptr, first_byte, nbytes, seed, ctx->stream));
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return FQGPU_OK;
+}
+
+int fqgpu_synth_illumina_tally(fqgpu_ctx* ctx, uint64_t first_record, uint64_t n_records, uint64_t seed, fqgpu_stats* out) {
+  if (!ctx || !out) return FQGPU_EARG;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t words = 16 + 152;
+  u64* d_t = nullptr;
+  CU_TRY(ctx, cudaMallocAsync((void**)&d_t, words * sizeof(u64), ctx->stream));
+  std::vector<u64> h(words);
+  cudaError_t e = cudaMemsetAsync(d_t, 0, words * sizeof(u64), ctx->stream);
+  if (e == cudaSuccess) e = fq::launch_synth_illumina_tally(first_record, n_records, seed, d_t, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h.data(), d_t, words * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream);
+  cudaFreeAsync(d_t, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  CU_TRY(ctx, e);
+  fqgpu_stats* st = out;
+  memset(st, 0, sizeof(*st));
+  static const char bases[5] = {'A', 'C', 'G', 'T', 'N'}, quals[4] = {'F', ':', ',', '#'};
+  for (int k = 0; k < 5; k++) st->base_counts[(unsigned char)bases[k]] = h[k];
+  for (int k = 0; k < 4; k++) st->qual_counts[(unsigned char)quals[k]] = h[5 + k];
+  for (int p = 0; p < 150; p++) { st->qual_pos_sum[p] = h[16 + p]; st->qual_pos_cnt[p] = n_records; }
+  st->bytes = n_records * 360ull; st->lines = 4 * n_records; st->reads = n_records; st->bases = 150ull * n_records;
+  st->gc_bases = st->base_counts['G'] + st->base_counts['C']; st->n_bases = st->base_counts['N'];
+  st->seq_lines = st->qual_lines = n_records;
+  st->seq_len_min = st->qual_len_min = n_records ? 150 : UINT64_MAX;
+  st->seq_len_max = st->qual_len_max = n_records ? 150 : 0;
+  st->seq_len_hist[150] = st->qual_len_hist[150] = n_records;
+  st->seq_len_log2[8] = n_records;
+  const u64 m = ctx->cfg.meta_records < n_records ? ctx->cfg.meta_records : n_records;
+  long long qmin, qmax;
+  fq::synth_illumina_meta_range(first_record, m, seed, &qmin, &qmax);
+  st->meta_qual_min = qmin; st->meta_qual_max = qmax; st->meta_lines = 4 * m;
+  if (ctx->cfg.flags & FQGPU_F_CORE_ONLY) fqgpu_zero_quality(st);
   return FQGPU_OK;
 }
 

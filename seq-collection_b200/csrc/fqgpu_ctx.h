@@ -20,6 +20,8 @@ cudaError_t launch_scan(const void* ptr, size_t nbytes, Carry* carry, ShardInfo*
                         bool unknown_start, int resident, bool core_only, cudaStream_t st);
 cudaError_t launch_meta(const uint8_t* base, uint32_t lo0, u64 end, Carry* carry, u64 meta_records, cudaStream_t st);
 cudaError_t launch_synth_illumina(void* dptr, u64 first_byte, u64 nbytes, u64 seed, cudaStream_t st);
+cudaError_t launch_synth_illumina_tally(u64 first_record, u64 n_records, u64 seed, u64* d_out, cudaStream_t st);
+void synth_illumina_meta_range(u64 first_record, u64 m, u64 seed, long long* qmin, long long* qmax);
 cudaError_t synth_ont(void* dptr, size_t capacity, u64 first_record, u64 n_records, u64 seed, size_t* bytes_written,
                       cudaStream_t st);
 }  // namespace fq

@@ -278,7 +278,9 @@ static void fq_meta(const string& fastq, long sample_n, bool basename, bool abso
   // ---- header-derived columns: unchanged host logic (fq_meta.nim:229-242, 251-258) ----
   ReadInfo info;
   vector<string> barcodes;
-  static const std::regex barcode_re("[ATCGN+\\-]{3,12}");
+  // re"[ATCGN\+\-]{3,12}+" (fq_meta.nim:210): nim-regex reads the trailing '+' as one more repetition of the bounded group, so
+  // dual-index barcodes such as AACGCTTA+GGTTCAGT (17 characters) match as a whole
+  static const std::regex barcode_re("([ATCGN+\\-]{3,12})+");
   for (size_t i = 0; i < lines.size(); i += 4) {
     if (i == 0) info = extract_read_info(lines[0]);
     vector<string> q = split_any(lines[i], ":/#");

@@ -126,6 +126,22 @@ def test_fq_meta_docs_rows(golden_dir):
 
 
 @pytest.mark.gpu
+def test_fq_meta_dual_index_barcode(tmp_path):
+    """src/fq_meta.nim:210 `[ATCGN\\+\\-]{3,12}+`: the trailing '+' repeats the bounded group, so a dual-index barcode
+    (8 + 1 + 8 characters) is reported whole in the index1 column."""
+    f = tmp_path / "dual.fq"
+    rec = b"@A00156:217:HKJWGDSXX:1:1101:1000:1000 1:N:0:AACGCTTA+GGTTCAGT\nACGT\n+\nFFFF\n"
+    f.write_bytes(rec * 3)
+    rc, out, err = run("fq-meta", str(f))
+    assert rc == 0, err
+    assert out.rstrip("\n").split("\t")[8] == "AACGCTTA+GGTTCAGT"
+    g = tmp_path / "short.fq"
+    g.write_bytes(rec.replace(b"AACGCTTA+GGTTCAGT", b"AC") * 2)  # shorter than 3: no barcode
+    rc, out, err = run("fq-meta", str(g))
+    assert rc == 0 and out.rstrip("\n").split("\t")[8] == ""
+
+
+@pytest.mark.gpu
 def test_fq_meta_n_option_and_gz_case():
     rc, out, _ = run("fq-meta", "-n", "2", os.path.join(FQ, "illumina_3.fq"))
     assert rc == 0 and out.rstrip("\n").split("\t")[15] == "2"

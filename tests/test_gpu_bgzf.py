@@ -128,3 +128,18 @@ def test_bgzf_inflate_stress(ctx, tmp_path, strategy, level):
             st = ctx.count_file(path)
             assert ctx.bgzf_members() >= len(data) // block, f"{name}: the device path was not taken (decoder rejected a valid stream)"
             assert_equal_stats(st.to_dict(), O.count(data, 100), f"{name} strategy={strategy} level={level} block={block}")
+
+
+def test_truncated_gzip_ends_like_the_reference_stream(ctx, tmp_path):
+    """A gz file cut in the middle opens fine; the reference's stream simply ends where zlib stops (gzip_stream.nim:16-17)
+    and the row of what was read is printed.  Same here: no error, the counts of the inflatable prefix."""
+    import zlib
+
+    rng = np.random.default_rng(21)
+    data = corpus.random_fastq(rng, 4000)
+    blob = gzip.compress(data)
+    cut = blob[: len(blob) // 2]
+    prefix = zlib.decompressobj(31).decompress(cut)
+    assert 0 < len(prefix) < len(data)
+    path = _write(tmp_path, "cut.fq.gz", cut)
+    assert_equal_stats(ctx.count_file(path).to_dict(), O.count(prefix, 100), "truncated gzip")
