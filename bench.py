@@ -6,7 +6,7 @@
 One "step" = one pass of the hot path (reset, scan, counter reduction, 20 KB result read-back)
 over the whole synthetic input.  N=1 workload = BASELINE.json configs[1]: synthetic Illumina
 2x150 bp uncompressed FASTQ, 100 M reads (36.0 GB), phred+33, resident in HBM.  N>1 = configs[2]:
-the same bytes sharded by byte range over the ranks (generated in place), one SUM all-reduce of the
+the same bytes sharded by byte range over the ranks (generated in place), one peer-memory all-gather + device combine of the
 counter blocks per step (strong scaling).  The input is far larger than the 126 MB L2, so no flush
 is needed between steps.
 
@@ -50,7 +50,8 @@ def workload_config(args, world: int) -> dict:
     total_bytes = args.records * REC_BYTES if args.workload == "illumina" else int(args.ont_gb * 1e9)
     return {"workload": args.workload_name, "bytes": total_bytes, "record_bytes": REC_BYTES,
             "seed": SEED_ILLUMINA if args.workload == "illumina" else SEED_ONT,
-            "sharding": f"byte ranges over {world} rank(s), one SUM all-reduce" if world > 1 else "none",
+            "sharding": (f"byte ranges over {world} rank(s); one launch per rank all-gathers the counter blocks through peer memory "
+                         "(NVLink P2P stores) and combines them on the device") if world > 1 else "none",
             "l2": "input >> 126 MB L2, no flush needed", "meta_records": args.meta_records,
             "stats": "full (fq-count + A/C/G/T/N, length tables, quality histogram, per-position sums, fq-meta range)"}
 
@@ -455,32 +456,39 @@ def main():
         total_reads = n_rec
     torch.cuda.synchronize()
 
-    blocks = None
+    def open_exchange(c):
+        """The library's own collective (fqgpu_shard_exchange_*): every rank's exchange buffer is opened by the others through
+        CUDA IPC; the 64-byte handles are all-gathered once, outside the timed region."""
+        h = c.shard_exchange_create(rank, world)
+        mine = torch.frombuffer(bytearray(h), dtype=torch.uint8).cuda()
+        allh = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        c.shard_exchange_open(b"".join(bytes(t.cpu().numpy()) for t in allh))
+
     if world > 1:
-        bw = ctx.shard_block_words()
-        blocks = torch.zeros(world * bw, dtype=torch.int64, device="cuda")
+        open_exchange(ctx)
 
     lib_stream = torch.cuda.ExternalStream(ctx.stream)
+
+    def sharded_step(c, scan):
+        """shard_begin -> scan -> ONE launch that all-gathers the blocks through peer memory (NVLink P2P stores) and
+        combines them on the device -> one read-back.  A wrong phase hypothesis (malformed input) repeats the exchange
+        after the first wrong rank has scanned again with the exact carry."""
+        c.shard_begin(rank, world)
+        scan()
+        while True:
+            c.shard_exchange_start()
+            rc, st_ = c.shard_exchange_finish()
+            if rc == 0:
+                return st_
+            if c.shard_rescan(c.shard_gathered()) == fq.ERETRY:
+                scan()
 
     def step():
         """One pass of the hot path over this rank's bytes; returns Stats."""
         if world == 1:
             return ctx.count_device(buf.data_ptr(), nbytes)
-        ctx.shard_begin(rank, world)
-        ctx.scan_device(buf.data_ptr(), nbytes)
-        while True:
-            blocks.zero_()
-            lib_stream.wait_stream(torch.cuda.current_stream())  # the library runs on its own non-blocking stream
-            ctx.shard_export(blocks.data_ptr())
-            torch.cuda.current_stream().wait_stream(lib_stream)
-            dist.all_reduce(blocks)  # the ONE collective: SUM of disjoint slots == gather
-            torch.cuda.current_stream().synchronize()
-            rc, st = ctx.shard_combine(blocks.data_ptr())
-            if rc == 0:
-                return st
-            # malformed input only: a rank resynced to a wrong phase; it scans again with the exact carry
-            if ctx.shard_rescan(blocks.data_ptr()) == fq.ERETRY:
-                ctx.scan_device(buf.data_ptr(), nbytes)
+        return sharded_step(ctx, lambda: ctx.scan_device(buf.data_ptr(), nbytes))
 
     def barrier():
         torch.cuda.synchronize()
@@ -580,23 +588,13 @@ def main():
         ectx = fq.FqGpu(device=local_rank, meta_records=args.meta_records)
         e_lib_stream = torch.cuda.ExternalStream(ectx.stream)
 
+        if world > 1:
+            open_exchange(ectx)
+
         def e2e_step():
             if world == 1:
                 return ectx.count_host_ptr(host.data_ptr(), sample)  # returns after the result is on the host
-            ectx.shard_begin(rank, world)
-            ectx.scan_host_ptr(host.data_ptr(), sample)
-            while True:
-                blocks.zero_()
-                e_lib_stream.wait_stream(torch.cuda.current_stream())
-                ectx.shard_export(blocks.data_ptr())
-                torch.cuda.current_stream().wait_stream(e_lib_stream)
-                dist.all_reduce(blocks)
-                torch.cuda.current_stream().synchronize()
-                rc, est_ = ectx.shard_combine(blocks.data_ptr())
-                if rc == 0:
-                    return est_
-                if ectx.shard_rescan(blocks.data_ptr()) == fq.ERETRY:
-                    ectx.scan_host_ptr(host.data_ptr(), sample)
+            return sharded_step(ectx, lambda: ectx.scan_host_ptr(host.data_ptr(), sample))
 
         for _ in range(2):
             est = e2e_step()
@@ -616,7 +614,7 @@ def main():
             want = ctx.count_device(buf.data_ptr(), sample)
             assert est.to_dict() == want.to_dict(), "end-to-end result differs from the HBM-resident result"
         e2e = {"value": total_sample / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": sample,
-               "d2h_bytes_per_step": 8 * 2144 + 80 if world == 1 else 8 * world * ctx.shard_block_words(),
+               "d2h_bytes_per_step": 8 * 2144 + 80 + 40,
                "reads_per_s": est.reads / e2e_s,
                "roofline": {"bound": "pinned host->device copy", "peak": h2d_total, "unit": "GB/s", "frac": total_sample / e2e_s / 1e9 / h2d_total,
                             "how": f"cudaMemcpyAsync of {h2d_n / 1e9:.2f} GB pinned -> device per rank, CUDA events, best of 3, all {world} rank(s) copying at once; sum over ranks"},
@@ -709,8 +707,8 @@ def main():
                                  "the two scan launches (every span; the spans whose guessed phase was wrong -- none here) on the library "
                                  "stream, the fq-meta prefix kernel beside them"},
             "clocks": clocks,
-            # per step: reset + fq-meta prefix + the two scan launches (+ the pack kernel of a shard)
-            "gpu_launches": int(args.steps * (scan_launches_per_step + (1 if args.meta_records else 0) + 1 + (1 if world > 1 else 0))),
+            # per step: reset + fq-meta prefix + the two scan launches (+ shard begin and the exchange kernel of a shard)
+            "gpu_launches": int(args.steps * (2 + (1 if args.meta_records and rank == 0 else 0) + 1 + (2 if world > 1 else 0))),
             "e2e": e2e,
             "cpu_baseline": cpu,
             "core_only": core,

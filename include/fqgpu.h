@@ -38,7 +38,7 @@ extern "C" {
 enum {
   FQGPU_OK = 0,
   FQGPU_ECUDA = -1, /* CUDA runtime / no device / kernel failure              */
-  FQGPU_ENCCL = -2, /* collective failure (multi-GPU)                         */
+  FQGPU_ENCCL = -2, /* collective failure (multi-GPU): a peer buffer cannot be opened, a rank is missing */
   FQGPU_EIO = -3,   /* file could not be opened / read  (maps to exit code 2, src/fq_count.nim:36) */
   FQGPU_EARG = -4,  /* bad argument / call sequence                           */
   FQGPU_ENOMEM = -5
@@ -210,6 +210,31 @@ int fqgpu_shard_combine(fqgpu_ctx* ctx, const uint64_t* d_blocks, fqgpu_stats* o
 int fqgpu_shard_rescan(fqgpu_ctx* ctx, const uint64_t* d_blocks);
 /* The combine step alone, over gathered blocks in HOST memory (pure host arithmetic, needs no GPU). */
 int fqgpu_shard_combine_host(int world, const uint64_t* h_blocks, uint64_t meta_records, fqgpu_stats* out);
+
+/* The collective inside the library (no NCCL, no host arithmetic): every rank owns an EXCHANGE BUFFER in device memory
+ * that the other ranks open (CUDA IPC between processes, plain pointers inside one process).  One launch per rank then
+ * packs the rank's block, stores it into its slot of every rank's buffer through peer-mapped memory (NVLink / NVSwitch
+ * P2P stores), publishes a flag, waits for the other ranks' flags in its own memory and combines the gathered blocks on
+ * the device (same arithmetic as fqgpu_shard_combine_host); the host reads back one block: one kernel and one host
+ * synchronisation per step.
+ *   fqgpu_shard_exchange_create(): allocate this rank's buffer; ipc_handle_out (fqgpu_ipc_handle_bytes() bytes, may be
+ *                                  NULL) receives the handle the other processes need
+ *   fqgpu_shard_exchange_open():   handles of all ranks, rank-major (the caller all-gathers them once -- any transport)
+ *   fqgpu_shard_exchange_set_peers(): the same inside one process: device pointers (fqgpu_shard_xbuf) of all ranks
+ *   per step: fqgpu_shard_begin, scans, then fqgpu_shard_exchange_start() on EVERY rank (asynchronous: no rank can
+ *             finish before all have started) and fqgpu_shard_exchange_finish() -> FQGPU_OK, FQGPU_ERETRY (a wrong
+ *             hypothesis: fqgpu_shard_rescan(ctx, fqgpu_shard_gathered(ctx)) as above) or FQGPU_ENCCL (a rank is missing) */
+size_t fqgpu_ipc_handle_bytes(void);
+size_t fqgpu_shard_xbuf_bytes(int world);
+int fqgpu_shard_exchange_create(fqgpu_ctx* ctx, int rank, int world, void* ipc_handle_out);
+int fqgpu_shard_exchange_open(fqgpu_ctx* ctx, const void* ipc_handles);
+void* fqgpu_shard_xbuf(fqgpu_ctx* ctx);
+int fqgpu_shard_exchange_set_peers(fqgpu_ctx* ctx, void* const* xbufs);
+int fqgpu_shard_exchange_start(fqgpu_ctx* ctx);
+int fqgpu_shard_exchange_finish(fqgpu_ctx* ctx, fqgpu_stats* out);
+int fqgpu_shard_exchange_combine(fqgpu_ctx* ctx, fqgpu_stats* out); /* start + finish */
+const uint64_t* fqgpu_shard_gathered(fqgpu_ctx* ctx);
+void fqgpu_shard_exchange_destroy(fqgpu_ctx* ctx);
 
 /* Timing of the most recent scan launches on this context (CUDA events on the context's stream):
  * kernel_ms = sum of scan-kernel durations since the last reset, launches = how many kernels. */

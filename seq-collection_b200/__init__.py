@@ -128,6 +128,17 @@ def load_library(path: str | None = None):
         "fqgpu_shard_combine": (i32, [vp, vp, C.POINTER(Stats)]),
         "fqgpu_shard_rescan": (i32, [vp, vp]),
         "fqgpu_shard_combine_host": (i32, [i32, vp, u64, C.POINTER(Stats)]),
+        "fqgpu_ipc_handle_bytes": (sz, []),
+        "fqgpu_shard_xbuf_bytes": (sz, [i32]),
+        "fqgpu_shard_exchange_create": (i32, [vp, i32, i32, vp]),
+        "fqgpu_shard_exchange_open": (i32, [vp, vp]),
+        "fqgpu_shard_xbuf": (vp, [vp]),
+        "fqgpu_shard_exchange_set_peers": (i32, [vp, C.POINTER(vp)]),
+        "fqgpu_shard_exchange_start": (i32, [vp]),
+        "fqgpu_shard_exchange_finish": (i32, [vp, C.POINTER(Stats)]),
+        "fqgpu_shard_exchange_combine": (i32, [vp, C.POINTER(Stats)]),
+        "fqgpu_shard_gathered": (vp, [vp]),
+        "fqgpu_shard_exchange_destroy": (None, [vp]),
         "fqgpu_last_timing": (i32, [vp, C.POINTER(C.c_double), C.POINTER(u64)]),
         "fqgpu_stream": (vp, [vp]),
         "fqgpu_synth_illumina": (i32, [vp, vp, sz, u64, u64, u64, C.POINTER(sz)]),
@@ -156,7 +167,9 @@ EXPORTED_SYMBOLS = [
     "fqgpu_destroy", "fqgpu_last_error", "fqgpu_acquire", "fqgpu_submit", "fqgpu_finish", "fqgpu_reset",
     "fqgpu_scan_host", "fqgpu_count_host", "fqgpu_count_file", "fqgpu_count_file_as", "fqgpu_count_files", "fqgpu_bgzf_members", "fqgpu_meta_file_as", "fqgpu_count_file_sharded", "fqgpu_scan_device", "fqgpu_count_device",
     "fqgpu_shard_block_words", "fqgpu_shard_begin", "fqgpu_shard_export", "fqgpu_shard_combine",
-    "fqgpu_shard_rescan", "fqgpu_shard_combine_host", "fqgpu_last_timing", "fqgpu_stream", "fqgpu_synth_illumina",
+    "fqgpu_shard_rescan", "fqgpu_shard_combine_host", "fqgpu_ipc_handle_bytes", "fqgpu_shard_xbuf_bytes", "fqgpu_shard_exchange_create",
+    "fqgpu_shard_exchange_open", "fqgpu_shard_xbuf", "fqgpu_shard_exchange_set_peers", "fqgpu_shard_exchange_start", "fqgpu_shard_exchange_finish",
+    "fqgpu_shard_exchange_combine", "fqgpu_shard_gathered", "fqgpu_shard_exchange_destroy", "fqgpu_last_timing", "fqgpu_stream", "fqgpu_synth_illumina",
     "fqgpu_synth_illumina_bytes", "fqgpu_synth_illumina_tally", "fqgpu_synth_ont", "fqgpu_index_device", "fqgpu_headers_device", "fqgpu_dedup_device", "fqgpu_dedup_host", "fqgpu_index_lines",
 ]
 
@@ -301,6 +314,37 @@ class FqGpu:
     def shard_rescan(self, d_blocks: int) -> int:
         """ERETRY (1): the exact carry was installed, scan this rank's range again; OK (0): just export again."""
         return self._check(self.lib.fqgpu_shard_rescan(self._ctx, d_blocks))
+
+    # -- the collective inside the library (peer-memory all-gather + device combine; include/fqgpu.h) ----------
+    def shard_exchange_create(self, rank: int, world: int) -> bytes:
+        """Allocates this rank's exchange buffer; returns its CUDA IPC handle (bytes) for the other processes."""
+        h = C.create_string_buffer(self.lib.fqgpu_ipc_handle_bytes())
+        self._check(self.lib.fqgpu_shard_exchange_create(self._ctx, rank, world, h))
+        return h.raw
+
+    def shard_exchange_open(self, handles: bytes):
+        """`handles`: the IPC handles of all ranks, concatenated in rank order."""
+        buf = C.create_string_buffer(handles, len(handles))
+        self._check(self.lib.fqgpu_shard_exchange_open(self._ctx, buf))
+
+    def shard_xbuf(self) -> int:
+        return int(self.lib.fqgpu_shard_xbuf(self._ctx) or 0)
+
+    def shard_exchange_set_peers(self, xbufs):
+        arr = (C.c_void_p * len(xbufs))(*xbufs)
+        self._check(self.lib.fqgpu_shard_exchange_set_peers(self._ctx, arr))
+
+    def shard_exchange_start(self):
+        self._check(self.lib.fqgpu_shard_exchange_start(self._ctx))
+
+    def shard_exchange_finish(self):
+        """(rc, Stats): rc 0 = done, ERETRY = a rank's phase hypothesis was wrong (shard_rescan(shard_gathered()))."""
+        st = Stats()
+        rc = self._check(self.lib.fqgpu_shard_exchange_finish(self._ctx, C.byref(st)))
+        return rc, st
+
+    def shard_gathered(self) -> int:
+        return int(self.lib.fqgpu_shard_gathered(self._ctx) or 0)
 
     # -- synthetic data --------------------------------------------------------------------------
     def synth_illumina(self, dptr: int, capacity: int, first_record: int, n_records: int, seed: int) -> int:

@@ -156,6 +156,190 @@ static int combine_walk(int world, const u64* blocks, u64* total, Carry* end_car
   return bad;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The collective inside the library: ONE launch per rank packs the rank's block, stores it into slot `rank` of EVERY
+// rank's exchange buffer through peer-mapped memory (NVLink / NVSwitch P2P stores: an all-gather with no library
+// call), publishes a flag behind a system-scope fence, waits for the other ranks' flags in its own memory, and
+// combines the gathered blocks right there (same arithmetic as combine_walk, spread over the CTA).  The host reads
+// back one block + the carry: one kernel, one host synchronisation per step.
+//
+// Exchange buffer of a rank (device memory, opened by the peers through CUDA IPC or handed over as pointers):
+//   slots  [2 parities][world][kShardWords] u64   blocks of the step, double-buffered by the step's parity: a peer can
+//                                                 be one step ahead (it needs this rank's flag for the step after)
+//   flags  [2][64] u64                            step number each rank has published for that parity
+//   result [BLOCK_WORDS] u64 + Carry + 4 u64      the combined block, the end carry, first wrong rank + 1 (0: none)
+// ---------------------------------------------------------------------------------------------------------------
+static constexpr int kMaxWorld = 64;
+struct XbufLayout {
+  size_t slots, flags, result, bytes;
+};
+static inline XbufLayout xbuf_layout(int world) {
+  XbufLayout L;
+  L.slots = 0;
+  L.flags = 2 * (size_t)world * kShardWords * sizeof(u64);
+  L.result = L.flags + 2 * kMaxWorld * sizeof(u64);
+  L.bytes = L.result + (BLOCK_WORDS + 4) * sizeof(u64) + sizeof(Carry);
+  return L;
+}
+struct PeerPtrs { uint8_t* p[kMaxWorld]; };
+
+__device__ __forceinline__ void st_release_sys(u64* p, u64 v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ u64 ld_acquire_sys(const u64* p) {
+  u64 v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned log2_bin_d(u64 len) { return len ? 64 - __clzll((long long)len) : 0; }
+
+__global__ void __launch_bounds__(512) fq_shard_exchange_kernel(const u64* __restrict__ acc, const Carry* __restrict__ carry,
+                                                              const ShardInfo* __restrict__ shard, int exact, int rank, int world, u64 step,
+                                                              PeerPtrs peers, size_t off_flags, size_t off_result, u64 meta_records, u64 spin_limit) {
+  __shared__ u64 sc_all[kMaxWorld][8];   // per rank: lines, bytes, open_len, last_byte, first_byte, head_len, head_cr, flags (exact | hyp_valid << 1 | hyp << 2 | present << 4)
+  __shared__ u64 before[kMaxWorld][4];   // chain in front of each rank: lines, open, bytes, last_byte
+  __shared__ int s_timeout;
+  const int tid = threadIdx.x;
+  const u64 par = step & 1;
+  // ---- 1. this rank's block into slot `rank` of every rank's buffer ----
+  for (int i = tid; i < (int)kShardWords; i += blockDim.x) {
+    u64 v = 0;
+    if (i < BLOCK_WORDS) v = acc[i];
+    else {
+      const int e = i - BLOCK_WORDS;
+      if (e <= POS_BINS) v = shard->head_pos[e];
+      else if (e >= SH_OFF_SCALARS && e < SH_OFF_SCALARS + SH_NSCALARS) {
+        const unsigned f = carry->flags;
+        switch (e - SH_OFF_SCALARS) {
+          case SH_LINES: v = carry->lines; break;
+          case SH_BYTES: v = carry->bytes; break;
+          case SH_OPEN_LEN: v = carry->open_len; break;
+          case SH_LAST_BYTE: v = carry->last_byte; break;
+          case SH_FIRST_BYTE: v = shard->first_byte; break;
+          case SH_HEAD_LEN: v = shard->head_len; break;
+          case SH_HEAD_CR: v = shard->head_cr; break;
+          case SH_HYP: v = (f >> CARRY_HYP_SHIFT) & 3u; break;
+          case SH_HYP_VALID: v = ((f & CARRY_HYP_VALID) && !(f & CARRY_HYP_FAILED)) ? 1 : 0; break;
+          case SH_EXACT: v = (exact || !(f & CARRY_UNKNOWN_START)) ? 1 : 0; break;
+          case SH_META_LINES: v = carry->meta_lines; break;
+          case SH_META_QMIN: v = (u64)carry->qual_min; break;
+          case SH_META_QMAX: v = (u64)carry->qual_max; break;
+          case SH_META_STATUS: v = carry->meta_status; break;
+          case SH_META_PENDING_CR: v = carry->meta_pending_cr; break;
+          case SH_META_CUR_HAS: v = (u64)(long long)carry->cur_has; break;
+          case SH_META_CUR_MIN: v = (u64)(long long)carry->cur_min; break;
+          case SH_META_CUR_MAX: v = (u64)(long long)carry->cur_max; break;
+          case SH_PRESENT: v = 1; break;
+        }
+      }
+    }
+    for (int p = 0; p < world; p++)
+      reinterpret_cast<u64*>(peers.p[p])[(par * world + rank) * kShardWords + i] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < world) st_release_sys(reinterpret_cast<u64*>(peers.p[tid] + off_flags) + par * kMaxWorld + rank, step);
+  // ---- 2. wait for everybody's block of this step in this rank's own memory ----
+  if (tid == 0) s_timeout = 0;
+  __syncthreads();
+  if (tid < world) {
+    const u64* fl = reinterpret_cast<const u64*>(peers.p[rank] + off_flags) + par * kMaxWorld + tid;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(fl) != step) {
+      if ((u64)(clock64() - t0) > spin_limit) { s_timeout = 1; break; }
+      __nanosleep(100);
+    }
+  }
+  __syncthreads();
+  const u64* slots = reinterpret_cast<const u64*>(peers.p[rank]) + par * world * kShardWords;
+  u64* res = reinterpret_cast<u64*>(peers.p[rank] + off_result);
+  // ---- 3. the chain in front of every rank (scalars, in rank order) ----
+  if (tid < world) {
+    const u64* sc = slots + (size_t)tid * kShardWords + BLOCK_WORDS + SH_OFF_SCALARS;
+    sc_all[tid][0] = sc[SH_LINES]; sc_all[tid][1] = sc[SH_BYTES]; sc_all[tid][2] = sc[SH_OPEN_LEN]; sc_all[tid][3] = sc[SH_LAST_BYTE];
+    sc_all[tid][4] = sc[SH_FIRST_BYTE]; sc_all[tid][5] = sc[SH_HEAD_LEN]; sc_all[tid][6] = sc[SH_HEAD_CR];
+    sc_all[tid][7] = (sc[SH_EXACT] ? 1 : 0) | (sc[SH_HYP_VALID] ? 2 : 0) | ((sc[SH_HYP] & 3) << 2) | (sc[SH_PRESENT] ? 16 : 0);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    u64 lines = 0, open = 0, bytes = 0, last_byte = 0;
+    int bad = s_timeout ? 0 : -1;
+    for (int g = 0; g < world; g++) {
+      before[g][0] = lines; before[g][1] = open; before[g][2] = bytes; before[g][3] = last_byte;
+      const u64* s = sc_all[g];
+      const bool present = (s[7] & 16) != 0, exact_g = (s[7] & 1) != 0;
+      if (!present) { if (bad < 0) bad = g; continue; }
+      if (!exact_g && (!(s[7] & 2) || ((s[7] >> 2) & 3) != (lines & 3))) { if (bad < 0) bad = g; }
+      if (exact_g && g > 0) { lines = s[0]; open = s[2]; bytes = s[1]; }
+      else {
+        if (s[0]) { lines += s[0]; open = s[2]; } else open += s[1];
+        bytes += s[1];
+      }
+      if (s[1]) last_byte = s[3];
+    }
+    Carry c;
+    memset(&c, 0, sizeof(c));
+    c.lines = lines; c.open_len = open; c.bytes = bytes; c.last_byte = (unsigned)last_byte;
+    const u64* sc0 = slots + BLOCK_WORDS + SH_OFF_SCALARS;  // fq-meta fold: shard 0's state
+    c.meta_lines = sc0[SH_META_LINES]; c.qual_min = (long long)sc0[SH_META_QMIN]; c.qual_max = (long long)sc0[SH_META_QMAX];
+    c.meta_status = (unsigned)sc0[SH_META_STATUS]; c.meta_pending_cr = (unsigned)sc0[SH_META_PENDING_CR];
+    c.cur_has = (int)(long long)sc0[SH_META_CUR_HAS]; c.cur_min = (int)(long long)sc0[SH_META_CUR_MIN]; c.cur_max = (int)(long long)sc0[SH_META_CUR_MAX];
+    // the sampled prefix extends beyond shard 0: flagged by the host AFTER the trailing line has been folded
+    res[BLOCK_WORDS + 2] = (meta_records && c.meta_lines < meta_records * 4 && world > 1 && sc_all[0][1] < bytes) ? 1 : 0;
+    *reinterpret_cast<Carry*>(res + BLOCK_WORDS + 4) = c;
+    res[BLOCK_WORDS] = (u64)(bad + 1);
+    res[BLOCK_WORDS + 1] = (u64)s_timeout;
+  }
+  __syncthreads();
+  // ---- 4. the blocks, word by word; then the first line fragment of every hypothesis shard stitched to the stream ----
+  for (int w = tid; w < BLOCK_WORDS; w += blockDim.x) {
+    const bool is_min = w == OFF_SEQ_LEN_MIN || w == OFF_QUAL_LEN_MIN, is_max = w == OFF_SEQ_LEN_MAX || w == OFF_QUAL_LEN_MAX;
+    u64 t = is_min ? ~0ull : 0ull;
+    for (int g = 0; g < world; g++) {
+      if (!(sc_all[g][7] & 16)) continue;
+      const u64 x = slots[(size_t)g * kShardWords + w];
+      if (is_min) t = x < t ? x : t; else if (is_max) t = x > t ? x : t; else t += x;
+    }
+    res[w] = t;
+  }
+  __syncthreads();
+  for (int g = 0; g < world; g++) {
+    const u64* s = sc_all[g];
+    if (!(s[7] & 16) || (s[7] & 1) || !s[1]) continue;  // absent, exact, or empty
+    const int cls = (int)(before[g][0] & 3);
+    const u64 P0 = before[g][1];
+    const bool prev_cr = before[g][2] && before[g][1] && before[g][3] == '\r';
+    if (cls == 3) {  // the head's per-position sums move by the bytes the line had on the ranks before
+      const u64* hp = slots + (size_t)g * kShardWords + BLOCK_WORDS + SH_OFF_HEAD_POS;
+      for (int p = tid; p <= POS_BINS; p += blockDim.x) {
+        const u64 v = hp[p];
+        if (!v) continue;
+        const u64 q = (u64)p + P0;
+        atomicAdd(&res[OFF_POS_SUM + (p < POS_BINS && q < (u64)POS_BINS ? q : (u64)POS_BINS)], v);
+      }
+    }
+    if (tid == 0) {
+      if (prev_cr && s[4] != '\n' && (cls & 1)) {  // the '\r' that ended the previous shard is content unless this shard starts with '\n'
+        atomicAdd(&res[(cls == 3 ? OFF_HIST_QUAL : OFF_HIST_SEQ) + '\r'], 1ull);
+        if (cls == 3) atomicAdd(&res[OFF_POS_SUM + ((P0 - 1) < (u64)POS_BINS ? (P0 - 1) : (u64)POS_BINS)], (u64)'\r');
+      }
+      if (s[0] && (cls & 1)) {  // the line ends in this shard: its length
+        const u64 raw = P0 + s[5];
+        const u64 cr = s[5] ? s[6] : ((prev_cr && raw > 0) ? 1 : 0);
+        const u64 len = raw - cr;
+        const u64 bin = len < (u64)POS_BINS ? len : (u64)POS_BINS;
+        if (cls == 3) {
+          atomicAdd(&res[OFF_QUAL_LEN + bin], 1ull);
+          atomicMin(&res[OFF_QUAL_LEN_MIN], len); atomicMax(&res[OFF_QUAL_LEN_MAX], len);
+        } else {
+          atomicAdd(&res[OFF_SEQ_LEN + bin], 1ull);
+          atomicAdd(&res[OFF_SEQ_LOG2 + log2_bin_d(len)], 1ull);
+          atomicMin(&res[OFF_SEQ_LEN_MIN], len); atomicMax(&res[OFF_SEQ_LEN_MAX], len);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 extern "C" {
 
 size_t fqgpu_shard_block_words(void) { return kShardWords; }
@@ -236,6 +420,124 @@ int fqgpu_shard_rescan(fqgpu_ctx* ctx, const uint64_t* d_blocks) {
   CU_TRY(ctx, cudaGetLastError());
   ctx->shard_exact = true;
   return FQGPU_ERETRY;
+}
+
+
+// ---- the collective inside the library (see fq_shard_exchange_kernel) ---------------------------------------------
+size_t fqgpu_shard_xbuf_bytes(int world) { return world >= 1 && world <= kMaxWorld ? xbuf_layout(world).bytes : 0; }
+size_t fqgpu_ipc_handle_bytes(void) { return sizeof(cudaIpcMemHandle_t); }
+
+static void xbuf_release(fqgpu_ctx* ctx) {
+  for (int g = 0; g < kMaxWorld; g++) {
+    if (ctx->x_peer_ipc[g]) cudaIpcCloseMemHandle(ctx->x_peers[g]);
+    ctx->x_peer_ipc[g] = false;
+    ctx->x_peers[g] = nullptr;
+  }
+  if (ctx->x_buf) cudaFree(ctx->x_buf);
+  ctx->x_buf = nullptr;
+  ctx->x_world = 0;
+  ctx->x_step = 0;
+}
+extern "C" void fqgpu_shard_exchange_destroy(fqgpu_ctx* ctx) { if (ctx) { cudaSetDevice(ctx->device); xbuf_release(ctx); } }
+
+int fqgpu_shard_exchange_create(fqgpu_ctx* ctx, int rank, int world, void* ipc_handle_out) {
+  if (!ctx || world < 1 || world > kMaxWorld || rank < 0 || rank >= world) return fail(ctx, FQGPU_EARG, "fqgpu_shard_exchange_create: bad rank/world");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  xbuf_release(ctx);
+  const XbufLayout L = xbuf_layout(world);
+  CU_TRY(ctx, cudaMalloc(&ctx->x_buf, L.bytes));
+  CU_TRY(ctx, cudaMemset(ctx->x_buf, 0, L.bytes));
+  ctx->x_world = world; ctx->x_rank = rank; ctx->x_step = 0;
+  ctx->x_peers[rank] = ctx->x_buf;
+  if (!ctx->h_xres) CU_TRY(ctx, cudaMallocHost(&ctx->h_xres, (BLOCK_WORDS + 4) * sizeof(u64) + sizeof(Carry)));
+  if (ipc_handle_out) {
+    cudaIpcMemHandle_t h;
+    CU_TRY(ctx, cudaIpcGetMemHandle(&h, ctx->x_buf));
+    memcpy(ipc_handle_out, &h, sizeof h);
+  }
+  return FQGPU_OK;
+}
+
+int fqgpu_shard_exchange_open(fqgpu_ctx* ctx, const void* ipc_handles) {
+  if (!ctx || !ipc_handles || !ctx->x_buf) return fail(ctx, FQGPU_EARG, "fqgpu_shard_exchange_open: create the exchange buffer first");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  for (int g = 0; g < ctx->x_world; g++) {
+    if (g == ctx->x_rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const uint8_t*)ipc_handles + (size_t)g * sizeof h, sizeof h);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { ctx->err = std::string("cudaIpcOpenMemHandle(rank ") + std::to_string(g) + "): " + cudaGetErrorString(e); cudaGetLastError(); return FQGPU_ENCCL; }
+    ctx->x_peers[g] = p;
+    ctx->x_peer_ipc[g] = true;
+  }
+  return FQGPU_OK;
+}
+
+void* fqgpu_shard_xbuf(fqgpu_ctx* ctx) { return ctx ? ctx->x_buf : nullptr; }
+
+int fqgpu_shard_exchange_set_peers(fqgpu_ctx* ctx, void* const* xbufs) {
+  if (!ctx || !xbufs || !ctx->x_buf) return fail(ctx, FQGPU_EARG, "fqgpu_shard_exchange_set_peers: create the exchange buffer first");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  for (int g = 0; g < ctx->x_world; g++) {
+    if (g == ctx->x_rank) continue;
+    if (!xbufs[g]) return fail(ctx, FQGPU_EARG, "fqgpu_shard_exchange_set_peers: NULL peer buffer");
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, xbufs[g]) == cudaSuccess && at.device != ctx->device) {
+      cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { ctx->err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e); cudaGetLastError(); return FQGPU_ENCCL; }
+      cudaGetLastError();
+    }
+    ctx->x_peers[g] = xbufs[g];
+  }
+  return FQGPU_OK;
+}
+
+// Starts this rank's part of the collective (asynchronous: every rank must start it before any can finish).
+int fqgpu_shard_exchange_start(fqgpu_ctx* ctx) {
+  if (!ctx || !ctx->x_buf) return fail(ctx, FQGPU_EARG, "fqgpu_shard_exchange: no exchange buffer");
+  for (int g = 0; g < ctx->x_world; g++) if (!ctx->x_peers[g]) return fail(ctx, FQGPU_EARG, "fqgpu_shard_exchange: peers not opened");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  const XbufLayout L = xbuf_layout(ctx->x_world);
+  PeerPtrs pp;
+  memset(&pp, 0, sizeof pp);
+  for (int g = 0; g < ctx->x_world; g++) pp.p[g] = (uint8_t*)ctx->x_peers[g];
+  ctx->x_step++;
+  cudaEvent_t e0 = fqgpu_get_event(ctx), e1 = fqgpu_get_event(ctx);
+  CU_TRY(ctx, cudaEventRecord(e0, ctx->stream));
+  fq_shard_exchange_kernel<<<1, 512, 0, ctx->stream>>>(ctx->d_acc, ctx->d_carry, ctx->d_shard, ctx->shard_exact ? 1 : 0, ctx->x_rank, ctx->x_world,
+                                                    ctx->x_step, pp, L.flags, L.result, ctx->cfg.meta_records, 20ull * 2000000000ull);
+  CU_TRY(ctx, cudaGetLastError());
+  CU_TRY(ctx, cudaEventRecord(e1, ctx->stream));
+  ctx->timed.emplace_back(e0, e1);
+  CU_TRY(ctx, cudaMemcpyAsync(ctx->h_xres, (uint8_t*)ctx->x_buf + L.result, (BLOCK_WORDS + 4) * sizeof(u64) + sizeof(Carry), cudaMemcpyDeviceToHost, ctx->stream));
+  return FQGPU_OK;
+}
+// Waits for it and assembles the statistics: FQGPU_OK, or FQGPU_ERETRY when a rank's hypothesis was wrong (then
+// fqgpu_shard_rescan(ctx, fqgpu_shard_gathered(ctx)) as after fqgpu_shard_combine), or FQGPU_ENCCL when a rank never showed up.
+int fqgpu_shard_exchange_finish(fqgpu_ctx* ctx, fqgpu_stats* out) {
+  if (!ctx || !out || !ctx->x_buf) return FQGPU_EARG;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  const u64* r = ctx->h_xres;
+  if (r[BLOCK_WORDS + 1]) return fail(ctx, FQGPU_ENCCL, "fqgpu_shard_exchange: a rank did not publish its block (20 s)");
+  if (r[BLOCK_WORDS]) return FQGPU_ERETRY;  // rank r[BLOCK_WORDS] - 1 scanned under a wrong phase hypothesis
+  Carry c;
+  memcpy(&c, r + BLOCK_WORDS + 4, sizeof c);
+  fqgpu_assemble_stats(r, c, ctx->cfg.meta_records, out);
+  if (r[BLOCK_WORDS + 2]) out->meta_status |= 0x100u;  // incomplete fq-meta range (see fqgpu_shard_combine_host)
+  if (ctx->cfg.flags & FQGPU_F_CORE_ONLY) fqgpu_zero_quality(out);
+  return FQGPU_OK;
+}
+int fqgpu_shard_exchange_combine(fqgpu_ctx* ctx, fqgpu_stats* out) {
+  int rc = fqgpu_shard_exchange_start(ctx);
+  return rc == FQGPU_OK ? fqgpu_shard_exchange_finish(ctx, out) : rc;
+}
+// The blocks gathered by the most recent exchange (device memory of this rank; what fqgpu_shard_rescan takes).
+const uint64_t* fqgpu_shard_gathered(fqgpu_ctx* ctx) {
+  if (!ctx || !ctx->x_buf) return nullptr;
+  return (const uint64_t*)ctx->x_buf + (ctx->x_step & 1) * (size_t)ctx->x_world * kShardWords;
 }
 
 }  // extern "C"

@@ -20,6 +20,8 @@
 
 #include "fqgpu_ctx.h"
 
+extern "C" void fqgpu_shard_exchange_destroy(fqgpu_ctx* ctx);
+
 extern "C" {
 
 int fqgpu_abi_version(void) { return FQGPU_ABI_VERSION; }
@@ -57,6 +59,8 @@ void fqgpu_destroy(fqgpu_ctx* ctx) {
   cudaFree(ctx->d_ctl);
   cudaFree(ctx->d_carry);
   cudaFree(ctx->d_shard);
+  fqgpu_shard_exchange_destroy(ctx);
+  if (ctx->h_xres) cudaFreeHost(ctx->h_xres);
   if (ctx->h_shard) cudaFreeHost(ctx->h_shard);
   if (ctx->h_comp) cudaFreeHost(ctx->h_comp);
   cudaFree(ctx->d_comp);

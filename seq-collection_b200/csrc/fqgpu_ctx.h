@@ -72,6 +72,13 @@ struct fqgpu_ctx {
   bool shard_exact = false;   // this rank was rescanned with the exact carry
   fq::ShardInfo* d_shard = nullptr;
   u64* h_shard = nullptr;      // pinned: gathered shard blocks (up to 64 ranks)
+  // the collective inside the library (fq_shard.cu): exchange buffer, the peers' buffers, step counter
+  void* x_buf = nullptr;
+  void* x_peers[64] = {};
+  bool x_peer_ipc[64] = {};
+  int x_world = 0, x_rank = 0;
+  u64 x_step = 0;
+  u64* h_xres = nullptr;       // pinned: combined block + first wrong rank + end carry
   // on-device BGZF inflate (fq_bgzf.cu): compressed batch (pinned host + device), inflated bytes, member table
   uint8_t* h_comp = nullptr;
   uint8_t* d_comp = nullptr;

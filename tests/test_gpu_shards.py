@@ -35,6 +35,58 @@ def check(got: dict, data: bytes, first_cut: int, msg: str, meta: int = 100):
 
 
 def sharded_count(data: bytes, cuts, meta=100, max_rounds=None):
+    """Both forms of the exchange step must agree: the caller's collective + fqgpu_shard_combine (host arithmetic), and the
+    library's own collective (peer-memory all-gather + device combine, fqgpu_shard_exchange_*)."""
+    a = _sharded_count_allreduce(data, cuts, meta)
+    b = _sharded_count_exchange(data, cuts, meta)
+    assert a == b, "the in-library collective disagrees with all-reduce + host combine"
+    return a
+
+
+def _sharded_count_exchange(data: bytes, cuts, meta=100):
+    import torch
+
+    world = len(cuts) + 1
+    edges = [0] + list(cuts) + [len(data)]
+    buf = torch.frombuffer(bytearray(data) if data else bytearray(b"\0"), dtype=torch.uint8).cuda()
+    ctxs = [fq.FqGpu(meta_records=meta) for _ in range(world)]
+    try:
+        for g, c in enumerate(ctxs):
+            c.shard_exchange_create(g, world)
+        xbufs = [c.shard_xbuf() for c in ctxs]
+        for c in ctxs:
+            c.shard_exchange_set_peers(xbufs)
+        for step in range(2):  # twice: the exchange buffers are double-buffered by the step's parity
+            for g, c in enumerate(ctxs):
+                c.shard_begin(g, world)
+                c.scan_device(buf.data_ptr() + edges[g], edges[g + 1] - edges[g])
+            rounds = 0
+            while True:
+                for c in ctxs:
+                    c.shard_exchange_start()  # asynchronous: the kernels of all ranks wait for each other on the device
+                results = [c.shard_exchange_finish() for c in ctxs]
+                rcs = {rc for rc, _ in results}
+                assert len(rcs) == 1, "every rank must reach the same verdict"
+                if rcs == {0}:
+                    dicts = [st.to_dict() for _, st in results]
+                    assert all(d == dicts[0] for d in dicts), "every rank must compute the same stats"
+                    break
+                rounds += 1
+                assert rounds <= world, "rescan did not converge"
+                for g, c in enumerate(ctxs):
+                    if c.shard_rescan(c.shard_gathered()) == fq.ERETRY:
+                        c.scan_device(buf.data_ptr() + edges[g], edges[g + 1] - edges[g])
+            if step == 0:
+                first = (dicts[0], rounds)
+            else:
+                assert dicts[0] == first[0], "second step differs"
+        return first
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def _sharded_count_allreduce(data: bytes, cuts, meta=100, max_rounds=None):
     import torch
 
     world = len(cuts) + 1
