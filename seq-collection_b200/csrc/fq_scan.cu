@@ -67,6 +67,7 @@ constexpr int KMAX = 63;                      // lines with more full groups are
 constexpr int LONG_CAP = TILE / (16 * (KMAX + 1)) + 2;
 constexpr int OPEN_CLIP = 1 << 30;            // line positions saturate here (>= POS_BINS is the overflow bin anyway)
 constexpr int MIN_SPAN_TILES = 32;            // spans are at least this long (1 MiB)
+constexpr int WAVE_SPAN_TILES = 512;          // ... and 16 MiB before a launch gets more spans than resident CTAs
 // Per-position quality sums, 16-bit pairs.  Q = position + 16.  Even Q: pair A = Q >> 1 of the EVEN table holds
 // (Q, Q+1); odd Q: pair A = (Q+1) >> 1 of the ODD table holds (Q, Q+1).  Pair A lives in cell (r, c) with
 // 8 c + r = A, r < 8, at word r * PT_STRIDE + c; a group adds its eight pairs at immediate offsets PT_STRIDE * i,
@@ -946,14 +947,26 @@ cudaError_t launch_reset(u64* acc, Carry* carry, u64* ctl, cudaStream_t st) {
 // SM the one that started first runs faster, so with one span each the slower half finishes late and alone; with
 // shorter spans the tail is one short span.  Spans stay >= MIN_SPAN_TILES tiles (FQGPU_SPAN_MIN_TILES: tests).
 uint32_t scan_span_count(u64 bytes, int resident) {
-  static const u64 min_tiles = getenv("FQGPU_SPAN_MIN_TILES") && atoi(getenv("FQGPU_SPAN_MIN_TILES")) > 0 ? (u64)atoi(getenv("FQGPU_SPAN_MIN_TILES")) : (u64)MIN_SPAN_TILES;
+  static const u64 env_min = getenv("FQGPU_SPAN_MIN_TILES") && atoi(getenv("FQGPU_SPAN_MIN_TILES")) > 0 ? (u64)atoi(getenv("FQGPU_SPAN_MIN_TILES")) : 0;
   static const u64 waves = getenv("FQGPU_SPAN_WAVES") && atoi(getenv("FQGPU_SPAN_WAVES")) > 0 ? (u64)atoi(getenv("FQGPU_SPAN_WAVES")) : (u64)SPAN_WAVES;
   const u64 ntiles = (bytes + TILE - 1) / TILE;
-  u64 n = ntiles / min_tiles;
-  const u64 cap = (u64)resident * (waves < (u64)SPAN_WAVES ? waves : (u64)SPAN_WAVES);
-  n = n < 1 ? 1 : (n > cap ? cap : n);
-  if (n > (u64)resident) n = (n / (u64)resident) * (u64)resident;  // whole waves
-  return (uint32_t)n;
+  const u64 max_waves = waves < (u64)SPAN_WAVES ? waves : (u64)SPAN_WAVES;
+  if (env_min) {  // tests: spans of env_min tiles wherever the input allows
+    u64 n = ntiles / env_min;
+    const u64 cap = (u64)resident * max_waves;
+    n = n < 1 ? 1 : (n > cap ? cap : n);
+    if (n > (u64)resident) n = (n / (u64)resident) * (u64)resident;
+    return (uint32_t)n;
+  }
+  // up to one span per resident CTA while spans stay >= MIN_SPAN_TILES; further waves only once every span of every
+  // wave is >= WAVE_SPAN_TILES (a span costs its start-up -- the phase guess, the tables -- and its flush: on 4.5 GB
+  // shards eight short spans per CTA cost more than the tail they save)
+  u64 n = ntiles / (u64)MIN_SPAN_TILES;
+  if (n < 1) n = 1;
+  if (n <= (u64)resident) return (uint32_t)n;
+  u64 w = ntiles / ((u64)resident * (u64)WAVE_SPAN_TILES);
+  w = w < 1 ? 1 : (w > max_waves ? max_waves : w);
+  return (uint32_t)((u64)resident * w);
 }
 
 // Scans `nbytes` at `ptr` (any alignment) as the continuation of the stream described by `carry`: pass 0 (every span
