@@ -699,9 +699,10 @@ def main():
             "stats_digest": digest,
             "result_check": "the full fqgpu_stats struct equals the generator's tallies (fqgpu_synth_illumina_tally) for the whole stream",
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (tr[0] * nbytes / max(1.0, scan_launches_per_step)) if tr else None,
+                         # the dominant kernel (pass 0 of fq_scan_kernel) covers this rank's bytes in ONE launch
+                         "traffic": (tr[0] * nbytes) if tr else None,
                          "traffic_unit": "bytes per launch", "traffic_source": tr[1] if tr else None,
-                         "algorithmic_bytes_per_launch": nbytes / max(1.0, scan_launches_per_step),
+                         "algorithmic_bytes_per_launch": nbytes,
                          "peak_source": peak_src,
                          "note": "algorithmic bytes = input bytes (1 B read per byte); device time = CUDA events around "
                                  "the two scan launches (every span; the spans whose guessed phase was wrong -- none here) on the library "

@@ -167,6 +167,11 @@ unsigned long long fqgpu_bgzf_members(const fqgpu_ctx* ctx);
 int fqgpu_count_files(const fqgpu_config* cfg, const char* const* paths, const int* as_gz, int n, int n_threads,
                       fqgpu_stats* out, int* rc);
 
+/* Paired files (R1 / R2 of one library) as one job: both mates are scanned at the same time (two contexts), rows in
+ * argument order exactly as two iterations of the reference's loop (sc.nim:115-116) would print them; *paired (may be
+ * NULL) = the files have the same number of records and lines, i.e. can be mates.  Returns the first non-OK rc. */
+int fqgpu_count_pair(const fqgpu_config* cfg, const char* r1, const char* r2, fqgpu_stats* out1, fqgpu_stats* out2, int* paired);
+
 /* One uncompressed regular file, byte-range sharded over `world` contexts in ONE process (the "file mode" of SURVEY 8e;
  * the multi-process form is the fqgpu_shard_* protocol below, which this call drives itself).  devices[g] = CUDA
  * ordinal of shard g (an ordinal may repeat); NULL = round-robin over every visible device, world <= 0 = one shard

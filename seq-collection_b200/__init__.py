@@ -128,6 +128,7 @@ def load_library(path: str | None = None):
         "fqgpu_shard_combine": (i32, [vp, vp, C.POINTER(Stats)]),
         "fqgpu_shard_rescan": (i32, [vp, vp]),
         "fqgpu_shard_combine_host": (i32, [i32, vp, u64, C.POINTER(Stats)]),
+        "fqgpu_count_pair": (i32, [C.POINTER(Config), C.c_char_p, C.c_char_p, C.POINTER(Stats), C.POINTER(Stats), C.POINTER(i32)]),
         "fqgpu_ipc_handle_bytes": (sz, []),
         "fqgpu_shard_xbuf_bytes": (sz, [i32]),
         "fqgpu_shard_exchange_create": (i32, [vp, i32, i32, vp]),
@@ -167,7 +168,7 @@ EXPORTED_SYMBOLS = [
     "fqgpu_destroy", "fqgpu_last_error", "fqgpu_acquire", "fqgpu_submit", "fqgpu_finish", "fqgpu_reset",
     "fqgpu_scan_host", "fqgpu_count_host", "fqgpu_count_file", "fqgpu_count_file_as", "fqgpu_count_files", "fqgpu_bgzf_members", "fqgpu_meta_file_as", "fqgpu_count_file_sharded", "fqgpu_scan_device", "fqgpu_count_device",
     "fqgpu_shard_block_words", "fqgpu_shard_begin", "fqgpu_shard_export", "fqgpu_shard_combine",
-    "fqgpu_shard_rescan", "fqgpu_shard_combine_host", "fqgpu_ipc_handle_bytes", "fqgpu_shard_xbuf_bytes", "fqgpu_shard_exchange_create",
+    "fqgpu_shard_rescan", "fqgpu_shard_combine_host", "fqgpu_count_pair", "fqgpu_ipc_handle_bytes", "fqgpu_shard_xbuf_bytes", "fqgpu_shard_exchange_create",
     "fqgpu_shard_exchange_open", "fqgpu_shard_xbuf", "fqgpu_shard_exchange_set_peers", "fqgpu_shard_exchange_start", "fqgpu_shard_exchange_finish",
     "fqgpu_shard_exchange_combine", "fqgpu_shard_gathered", "fqgpu_shard_exchange_destroy", "fqgpu_last_timing", "fqgpu_stream", "fqgpu_synth_illumina",
     "fqgpu_synth_illumina_bytes", "fqgpu_synth_illumina_tally", "fqgpu_synth_ont", "fqgpu_index_device", "fqgpu_headers_device", "fqgpu_dedup_device", "fqgpu_dedup_host", "fqgpu_index_lines",
@@ -481,6 +482,16 @@ def count_files(paths, n_threads: int = 0, device: int = -1, meta_records: int =
     rcs = (C.c_int * max(n, 1))()
     rc = lib.fqgpu_count_files(C.byref(cfg), arr, gz, n, n_threads, out, rcs)
     return rc, [(rcs[i], out[i]) for i in range(n)]
+
+
+def count_pair(r1: str, r2: str, device: int = -1, meta_records: int = 0, flags: int = 0):
+    """fqgpu_count_pair: R1 / R2 of one library as one job (both mates scanned at the same time).
+    Returns (rc, Stats of r1, Stats of r2, paired) -- paired: same number of records and lines."""
+    lib = load_library()
+    cfg = Config(device, 0, 0, meta_records, flags, 0)
+    a, b, ok = Stats(), Stats(), C.c_int(0)
+    rc = lib.fqgpu_count_pair(C.byref(cfg), os.fsencode(r1), os.fsencode(r2), C.byref(a), C.byref(b), C.byref(ok))
+    return rc, a, b, bool(ok.value)
 
 
 def count_file_sharded(path: str, devices=None, world: int = 0, meta_records: int = 0, flags: int = 0, chunk_bytes: int = 0) -> Stats:

@@ -44,7 +44,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
                 cmd.insert(1, "-Xptxas=-v")
             subprocess.run(cmd, check=True)
             objs.append(obj)
-        subprocess.run([NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-lz"], check=True)
+        subprocess.run([NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-lz", "-ldl"], check=True)
     return LIB
 
 

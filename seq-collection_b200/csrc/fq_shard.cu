@@ -496,6 +496,7 @@ int fqgpu_shard_exchange_set_peers(fqgpu_ctx* ctx, void* const* xbufs) {
 
 // Starts this rank's part of the collective (asynchronous: every rank must start it before any can finish).
 int fqgpu_shard_exchange_start(fqgpu_ctx* ctx) {
+  NvtxRange nvtx_("fqgpu_shard_exchange_start");
   if (!ctx || !ctx->x_buf) return fail(ctx, FQGPU_EARG, "fqgpu_shard_exchange: no exchange buffer");
   for (int g = 0; g < ctx->x_world; g++) if (!ctx->x_peers[g]) return fail(ctx, FQGPU_EARG, "fqgpu_shard_exchange: peers not opened");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
@@ -517,6 +518,7 @@ int fqgpu_shard_exchange_start(fqgpu_ctx* ctx) {
 // Waits for it and assembles the statistics: FQGPU_OK, or FQGPU_ERETRY when a rank's hypothesis was wrong (then
 // fqgpu_shard_rescan(ctx, fqgpu_shard_gathered(ctx)) as after fqgpu_shard_combine), or FQGPU_ENCCL when a rank never showed up.
 int fqgpu_shard_exchange_finish(fqgpu_ctx* ctx, fqgpu_stats* out) {
+  NvtxRange nvtx_("fqgpu_shard_exchange_finish");
   if (!ctx || !out || !ctx->x_buf) return FQGPU_EARG;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));

@@ -170,6 +170,7 @@ static int fqgpu_launch_scan(fqgpu_ctx* ctx, const uint8_t* p, size_t n, u64 met
 }
 
 int fqgpu_scan_device(fqgpu_ctx* ctx, const void* dptr, size_t nbytes) {
+  NvtxRange nvtx_("fqgpu_scan_device");
   if (!ctx) return FQGPU_EARG;
   if (nbytes == 0) return FQGPU_OK;
   if (!dptr) return fail(ctx, FQGPU_EARG, "fqgpu_scan_device: NULL pointer");
@@ -294,6 +295,7 @@ void fqgpu_assemble_stats(const u64* blk, const fq::Carry& c, u64 meta_records, 
 extern "C" {
 
 int fqgpu_finish(fqgpu_ctx* ctx, fqgpu_stats* out) {
+  NvtxRange nvtx_("fqgpu_finish");
   if (!ctx || !out) return FQGPU_EARG;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   static_assert(sizeof(fq::Carry) % sizeof(u64) == 0, "h_out layout");
@@ -350,6 +352,7 @@ static int stage_and_scan(fqgpu_ctx* ctx, const void* host, size_t nbytes, cudaE
 
 // ---- staging ring -------------------------------------------------------------------------------
 void* fqgpu_acquire(fqgpu_ctx* ctx, size_t* capacity) {
+  NvtxRange nvtx_("fqgpu_acquire");
   if (!ctx) return nullptr;
   if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return nullptr; }
   StageBuf& b = ctx->ring[ctx->next];
@@ -368,6 +371,7 @@ void* fqgpu_acquire(fqgpu_ctx* ctx, size_t* capacity) {
 }
 
 int fqgpu_submit(fqgpu_ctx* ctx, void* chunk, size_t nbytes) {
+  NvtxRange nvtx_("fqgpu_submit");
   if (!ctx) return FQGPU_EARG;
   int slot = -1;
   for (size_t i = 0; i < ctx->ring.size(); i++) if (ctx->ring[i].host == chunk && chunk) slot = (int)i;
@@ -382,6 +386,7 @@ int fqgpu_submit(fqgpu_ctx* ctx, void* chunk, size_t nbytes) {
 }
 
 int fqgpu_scan_host(fqgpu_ctx* ctx, const void* buf, size_t nbytes) {
+  NvtxRange nvtx_("fqgpu_scan_host");
   if (!ctx || (!buf && nbytes)) return FQGPU_EARG;
   // H2D straight from the caller's buffer (asynchronous when it is pinned), double-buffered on
   // the device so the copy of chunk k+1 overlaps the scan of chunk k
@@ -570,6 +575,7 @@ extern "C" {
 unsigned long long fqgpu_bgzf_members(const fqgpu_ctx* ctx) { return ctx ? ctx->bgzf_members : 0; }
 
 int fqgpu_count_file_as(fqgpu_ctx* ctx, const char* path, int as_gz, fqgpu_stats* out) {
+  NvtxRange nvtx_("fqgpu_count_file_as");
   if (!ctx || !path || !out) return FQGPU_EARG;
   const bool gz = as_gz != 0;
   int rc = fqgpu_reset(ctx);
@@ -823,6 +829,22 @@ int fqgpu_count_files(const fqgpu_config* cfg, const char* const* paths, const i
   for (auto& th : pool) th.join();
   for (int i = 0; i < n; i++) if (rc[i] != FQGPU_OK) { g_create_error = msgs[(size_t)i]; return rc[i]; }
   return FQGPU_OK;
+}
+
+// ---- paired files: R1 / R2 as ONE job -------------------------------------------------------
+// The reference has no paired mode: `sc fq-count R1.fq.gz R2.fq.gz` is two passes of the sequential loop (sc.nim:115-116),
+// one row per file.  Here both mates are scanned at the same time by two contexts (two host threads, two pinned rings,
+// two streams on the same GPU, or one GPU each with FQGPU_DEVICE_ALL) and the rows come back in argument order; `paired`
+// tells whether the two files can be mates at all (same number of records and of lines).
+int fqgpu_count_pair(const fqgpu_config* cfg, const char* r1, const char* r2, fqgpu_stats* out1, fqgpu_stats* out2, int* paired) {
+  if (!r1 || !r2 || !out1 || !out2) return FQGPU_EARG;
+  const char* paths[2] = {r1, r2};
+  fqgpu_stats st[2];
+  int rc[2] = {FQGPU_ECUDA, FQGPU_ECUDA};
+  const int r = fqgpu_count_files(cfg, paths, nullptr, 2, 2, st, rc);
+  *out1 = st[0]; *out2 = st[1];
+  if (paired) *paired = rc[0] == FQGPU_OK && rc[1] == FQGPU_OK && st[0].reads == st[1].reads && st[0].lines == st[1].lines;
+  return r;
 }
 
 // ---- synthetic data -----------------------------------------------------------------------------

@@ -2,6 +2,7 @@
 #pragma once
 #include <string.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <string>
 #include <vector>
@@ -100,6 +101,12 @@ struct fqgpu_ctx {
       return FQGPU_ECUDA;                                                              \
     }                                                                                  \
   } while (0)
+
+// NVTX range over a C-ABI call (nsys / ncu timelines: fill, submit, scan, finish, exchange)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 inline int fail(fqgpu_ctx* ctx, int code, const std::string& msg) {
   if (ctx) ctx->err = msg; else g_create_error = msg;

@@ -167,3 +167,27 @@ def test_count_file_sharded_equals_oracle(tmp_path):
     with pytest.raises(fq.FqGpuError) as ei:
         fq.count_file_sharded("/nonexistent/file.fq", devices=[0, 0])
     assert ei.value.code == fq.EIO
+
+
+def test_paired_files_as_one_job(tmp_path):
+    """R1 / R2: both mates scanned at the same time, one row per file as the reference's loop over the
+    two files would print them (sc.nim:115-116), and the mate check."""
+    import gzip
+
+    rng = np.random.default_rng(77)
+    r1 = corpus.random_fastq(rng, 5000, min_len=100, max_len=151)
+    r2 = corpus.random_fastq(rng, 5000, min_len=100, max_len=151)
+    p1, p2 = tmp_path / "lib_R1.fq", tmp_path / "lib_R2.fq.gz"
+    p1.write_bytes(r1)
+    p2.write_bytes(gzip.compress(r2))
+    rc, a, b, paired = fq.count_pair(str(p1), str(p2), meta_records=100)
+    assert rc == 0 and paired
+    assert_equal_stats(a.to_dict(), O.count(r1, 100), "R1")
+    assert_equal_stats(b.to_dict(), O.count(r2, 100), "R2")
+    assert fq.fq_count_row(a) == O.fq_count_row(O.count(r1, 100)) and fq.fq_count_row(b) == O.fq_count_row(O.count(r2, 100))
+    p3 = tmp_path / "short_R2.fq"
+    p3.write_bytes(corpus.random_fastq(rng, 4999, min_len=100, max_len=151))
+    rc, a, b, paired = fq.count_pair(str(p1), str(p3))
+    assert rc == 0 and not paired and a.reads == 5000 and b.reads == 4999
+    rc, a, b, paired = fq.count_pair(str(p1), str(tmp_path / "missing.fq"))
+    assert rc == fq.EIO and not paired
