@@ -54,12 +54,6 @@ namespace fq {
 #ifndef FQ_CTAS
 #define FQ_CTAS 2
 #endif
-#ifndef FQ_LISTS
-#define FQ_LISTS 0   // 1: per-class lists of full groups written by the line tasks (measured slower: the task phase gets longer)
-#endif
-#ifndef FQ_DYN
-#define FQ_DYN 0     // 1: the workers take batches of 32 slots from a shared counter (measured slower: 1588 vs 1946 GB/s); 0: fixed rounds, rotated
-#endif
 constexpr int THREADS = FQ_THREADS;
 constexpr int CTAS_PER_SM = FQ_CTAS;
 constexpr int NWARPS = THREADS / 32;
@@ -118,8 +112,6 @@ struct TileInfo {
   uint32_t first;    // extension tiles: offset of the first newline
   uint32_t K[2];     // most full groups of a (not long) line, per class
   uint32_t nlong;
-  uint32_t ns, nq;   // entries of slist / qlist
-  uint32_t wq;       // next batch of worker slots
   uint32_t last1;    // walker tiles: offset of the last newline + 1
 };
 
@@ -127,12 +119,7 @@ struct __align__(128) Smem {
   uint8_t buf[NSTAGE][TILE];
   uint16_t bitmap[NG];               // bit b of entry g: byte 16 g + b is '\n'
   uint16_t nl[NL_CAP + 8];           // offsets of the tile's newlines, ascending
-#if FQ_LISTS
-  uint16_t slist[NG];                // the aligned full groups of the tile's sequence lines (group index), in no particular order
-  uint32_t qlist[NG];                // ... of its quality lines: group | table cell << 11 | 1 << 31, or group | (position + 16) << 11 | parity << 22
-#else
   u64 rec[2][REC_CAP];               // per class and line: first full group | full groups << 11 | fast << 17 | table cell << 18 | parity << 30 | position << 32
-#endif
   uint32_t part[2][2 * REC_CAP];     // per class and line: its two ragged groups: group | lo << 11 | hi << 15 | parity << 20 | position of byte lo << 21
   u64 longl[LONG_CAP];               // lines of more than KMAX full groups: first | groups << 11 | class << 23 | parity << 24 | position << 32
   uint32_t inv[KMAX + 1];            // ceil(2^32 / K)
@@ -476,11 +463,7 @@ __device__ __forceinline__ void run_span(Smem& sm, const ScanArgs& a, const Sel&
   const uint32_t hist_s = sm0 + (uint32_t)offsetof(Smem, hist);
   const uint32_t ptab_s = sm0 + (uint32_t)offsetof(Smem, ptab);
   const uint32_t masks_s = sm0 + (uint32_t)offsetof(Smem, masks);
-#if FQ_LISTS
-  const uint32_t slist_s = sm0 + (uint32_t)offsetof(Smem, slist), qlist_s = sm0 + (uint32_t)offsetof(Smem, qlist);
-#else
   const uint32_t rec_s = sm0 + (uint32_t)offsetof(Smem, rec);
-#endif
   const uint32_t part_s = sm0 + (uint32_t)offsetof(Smem, part);
   const uint32_t t_first = (uint32_t)(start / TILE);
   uint32_t pt_lines = 0, since_flush = 0;  // (uniform) quality lines in ptab since its last flush; bytes since the tables' last flush
@@ -588,7 +571,7 @@ __device__ __forceinline__ void run_span(Smem& sm, const ScanArgs& a, const Sel&
       uint32_t nlines0, nlines1;  // lines per class with bytes in the tile
       if (CORE) { nlines0 = ntasks; nlines1 = 0; }
       else { const uint32_t qa = ((cnt_in + j0) & 3u) >> 1; nlines0 = qa ? ntasks >> 1 : (ntasks + 1u) >> 1; nlines1 = ntasks - nlines0; }
-      if (tid == 0) { sm.ti.K[0] = sm.ti.K[1] = 0; sm.ti.nlong = 0; sm.ti.ns = sm.ti.nq = 0; sm.ti.wq = 0; }
+      if (tid == 0) { sm.ti.K[0] = sm.ti.K[1] = 0; sm.ti.nlong = 0; }
       __syncthreads();
       // ---- L: line tasks (lines j = 0..T of the tile; j = T is the open line behind the last newline) ----
       for (uint32_t i = (uint32_t)tid; i < ntasks; i += THREADS) {
@@ -600,9 +583,7 @@ __device__ __forceinline__ void run_span(Smem& sm, const ScanArgs& a, const Sel&
         const bool fn = j == 0;
         uint32_t pos0 = 0;
         if (fn) { const u64 op = sm.run.open; pos0 = (uint32_t)(op < (u64)OPEN_CLIP ? op : (u64)OPEN_CLIP); }
-#if !FQ_LISTS
         u64 rec = 0;
-#endif
         uint32_t p0 = 0, p1 = 0;
         if (e > s) {
           const uint32_t gs = (uint32_t)s >> 4, ge = (uint32_t)e >> 4, ls = (uint32_t)s & 15u, le = (uint32_t)e & 15u;
@@ -619,25 +600,6 @@ __device__ __forceinline__ void run_span(Smem& sm, const ScanArgs& a, const Sel&
               if (slot < (uint32_t)LONG_CAP) sm.longl[slot] = (u64)(ff | (nfull << 11) | (ql << 23) | (par << 24)) | ((u64)qff << 32);
               else a.ctl[CTL_ERROR] = 2;
             } else if (nfull) {
-#if FQ_LISTS
-              // the line's full groups into the class's list (the workers take one entry per lane, whatever line it is of)
-              if (!ql) {
-                uint32_t at = slist_s + 2u * atomicAdd(&sm.ti.ns, nfull);
-                for (uint32_t k = 0; k < nfull; k++, at += 2u) sts16(at, ff + k);
-              } else if (!CORE) {
-                uint32_t at = qlist_s + 4u * atomicAdd(&sm.ti.nq, nfull);
-                if (!dense && qff + 16u * nfull <= (uint32_t)POS_BINS) {  // every full group inside the packed table: its cell
-                  const uint32_t Q = qff + 16u, odd = Q & 1u, A = (Q + odd) >> 1;
-                  uint32_t ent = ff | (((A & 7u) * PT_STRIDE + (A >> 3) + odd * (2u * PT_COPY) + par * PT_COPY) << 11) | (1u << 31);
-                  for (uint32_t k = 0; k < nfull; k++, at += 4u, ent += (1u << 11) + 1u) asm volatile("st.shared.u32 [%0], %1;" ::"r"(at), "r"(ent) : "memory");
-                } else {
-                  for (uint32_t k = 0; k < nfull; k++, at += 4u) {
-                    const uint32_t Qk = qff + 16u * k + 16u;
-                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(at), "r"((ff + k) | ((Qk < 2047u ? Qk : 2047u) << 11) | (par << 22)) : "memory");
-                  }
-                }
-              }
-#else
               uint32_t lo32 = ff | (nfull << 11) | (par << 30);
               if (!CORE && ql && !dense && qff + 16u * nfull <= (uint32_t)POS_BINS) {  // every full group inside the packed table
                 const uint32_t Q = qff + 16u, odd = Q & 1u, A = (Q + odd) >> 1;
@@ -645,88 +607,21 @@ __device__ __forceinline__ void run_span(Smem& sm, const ScanArgs& a, const Sel&
               }
               rec = (u64)lo32 | ((u64)qff << 32);
               atomicMax(&sm.ti.K[ql], nfull);
-#endif
             }
           }
         }
         if (ord < (uint32_t)REC_CAP) {
-#if !FQ_LISTS
           sts64(rec_s + 8u * (ql * REC_CAP + ord), rec);
-#endif
           sts64(part_s + 8u * (ql * REC_CAP + ord), (u64)p0 | ((u64)p1 << 32));
         } else a.ctl[CTL_ERROR] = 3;
         if (j < T) line_end<CORE>(sm, a, buf_s, vlo, toff, e, fn ? sm.run.open + (u64)(e - vlo) : (u64)(e - s), fn, ql);
       }
       __syncthreads();
-#if FQ_DYN && !FQ_LISTS
-      // ---- W: one lane per 16-byte group: the lines' full groups (slot x -> line x / K, group x % K) and their ragged ends,
-      // as batches of 32 slots that the warps take from a shared counter (the next batch is fetched while this one is
-      // worked on), so that every warp is busy until the work is gone whatever it did in the line-task phase ----
-      {
-        uint32_t K0 = sm.ti.K[0], K1 = CORE ? 0u : sm.ti.K[1];
-        if (K0 == 1) K0 = 2;  // (the reciprocal table starts at 2)
-        if (K1 == 1) K1 = 2;
-        const uint32_t inv0 = sm.inv[K0], inv1 = sm.inv[K1];
-        const uint32_t nq_full = nlines1 * K1, ns_full = nlines0 * K0, nq_part = 2u * nlines1, ns_part = 2u * nlines0;
-        const uint32_t bA = (nq_full + 31u) >> 5, bB = bA + ((ns_full + 31u) >> 5), bC = bB + ((nq_part + 31u) >> 5), bD = bC + ((ns_part + 31u) >> 5);
-        uint32_t b = 0, nb = 0;
-        if (lane == 0) b = atomicAdd(&sm.ti.wq, 1u);
-        b = __shfl_sync(0xffffffffu, b, 0);
-        while (b < bD) {
-          if (lane == 0) nb = atomicAdd(&sm.ti.wq, 1u);
-          if (b < bB) {
-            const uint32_t ql = b < bA ? 1u : 0u;
-            const uint32_t x = ((ql ? b : b - bA) << 5) + (uint32_t)lane, K = ql ? K1 : K0;
-            if (x < (ql ? nq_full : ns_full)) {
-              const uint32_t line = __umulhi(x, ql ? inv1 : inv0);
-              const uint32_t k = x - line * K;
-              const u64 r = lds64(rec_s + 8u * (ql * REC_CAP + line));
-              const uint32_t r0 = (uint32_t)r;
-              if (k < ((r0 >> 11) & 63u)) {
-                const uint32_t ga = buf_s + 16u * ((r0 & 2047u) + k);
-                const uint4 v = lds128(ga);
-                hist16(ksel, v, hist_s + (ql << 10));
-                if (!CORE && ql) {
-                  if (r0 & (1u << 17)) pos16_fast(v, ptab_s + 4u * (((r0 >> 18) & 4095u) + k));
-                  else pos16(sm, v, ga, ptab_s, (uint32_t)(r >> 32) + 16u * k + 16u, 0u, 16u, (r0 >> 30) & 1u, dense, over);
-                }
-              }
-            }
-          } else {
-            const uint32_t ql = b < bC ? 1u : 0u;
-            const uint32_t x = ((ql ? b - bB : b - bC) << 5) + (uint32_t)lane;
-            if (x < (ql ? nq_part : ns_part)) {
-              const uint32_t ent = lds32(part_s + 4u * (2u * ql * REC_CAP + x));
-              if (ent) masked_group<CORE>(sm, ksel, buf_s, hist_s, ptab_s, masks_s, ent & 2047u, (ent >> 11) & 15u, (ent >> 15) & 31u, ent >> 21, ql, (ent >> 20) & 1u, dense, over);
-            }
-          }
-          b = __shfl_sync(0xffffffffu, nb, 0);
-        }
-      }
-#else
       // ---- W: one lane per 16-byte group: the lines' full groups (slot x -> line x / K, group x % K), their ragged ends ----
 #pragma unroll
       for (uint32_t ql = 0; ql < (CORE ? 1u : 2u); ql++) {
         const uint32_t nlines = ql ? nlines1 : nlines0;
         const uint32_t hb = hist_s + (ql << 10);
-#if FQ_LISTS
-        {
-          // (the threads of the warps that ran the line tasks come last: the second round of entries goes to the others)
-          const uint32_t n = ql ? sm.ti.nq : sm.ti.ns;
-          for (uint32_t x = ((uint32_t)tid + THREADS - ROT_FULL) % THREADS; x < n; x += THREADS) {
-            if (!ql) {
-              hist16(ksel, lds128(buf_s + 16u * lds16(slist_s + 2u * x)), hb);
-            } else if (!CORE) {
-              const uint32_t e = lds32(qlist_s + 4u * x);
-              const uint32_t ga = buf_s + 16u * (e & 2047u);
-              const uint4 v = lds128(ga);
-              hist16(ksel, v, hb);
-              if (e >> 31) pos16_fast(v, ptab_s + 4u * ((e >> 11) & 4095u));
-              else pos16(sm, v, ga, ptab_s, (e >> 11) & 2047u, 0u, 16u, (e >> 22) & 1u, dense, over);
-            }
-          }
-        }
-#else
         uint32_t K = sm.ti.K[ql];
         if (K == 1) K = 2;  // (the reciprocal table starts at 2)
         if (K) {
@@ -748,13 +643,11 @@ __device__ __forceinline__ void run_span(Smem& sm, const ScanArgs& a, const Sel&
             }
           }
         }
-#endif
         for (uint32_t x = ((uint32_t)tid + THREADS - (ql ? ROT_QPART : ROT_SPART)) % THREADS; x < 2u * nlines; x += THREADS) {
           const uint32_t ent = lds32(part_s + 4u * (2u * ql * REC_CAP + x));
           if (ent) masked_group<CORE>(sm, ksel, buf_s, hist_s, ptab_s, masks_s, ent & 2047u, (ent >> 11) & 15u, (ent >> 15) & 31u, ent >> 21, ql, (ent >> 20) & 1u, dense, over);
         }
       }
-#endif
       {
         const uint32_t nlong = sm.ti.nlong < (uint32_t)LONG_CAP ? sm.ti.nlong : (uint32_t)LONG_CAP;
         for (uint32_t li = 0; li < nlong; li++) {
