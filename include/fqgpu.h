@@ -154,6 +154,13 @@ int fqgpu_meta_file_as(fqgpu_ctx* ctx, const char* path, int as_gz, fqgpu_stats*
  * Plain gzip, or anything malformed, takes the zlib path.  FQGPU_NO_BGZF=1 in the environment disables the device
  * path.  Returns the members the last fqgpu_count_file* call on this context inflated on the device. */
 unsigned long long fqgpu_bgzf_members(const fqgpu_ctx* ctx);
+/* Ordinary (single-member or concatenated) gzip that is not BGZF is inflated on the device too: chunks of the one
+ * DEFLATE stream in parallel from guessed block starts, the guesses proven by the chunk before landing on them
+ * (csrc/fq_gzip.cu).  What cannot be proven goes through gzread() as before (FQGPU_NO_GZIP_DEVICE=1 forces that).
+ * Diagnostics since the last reset: chunks inflated on the device (0 = the host path ran), and block starts the
+ * search proposed that were not block boundaries. */
+unsigned long long fqgpu_gzip_chunks(const fqgpu_ctx* ctx);
+unsigned long long fqgpu_gzip_false_starts(const fqgpu_ctx* ctx);
 
 /* Many files at once (replaces the sequential `for fastq in files` loop of sc.nim:115-116).
  * Files are independent streams, so up to n_threads host threads (0 = min(n, 8)) each own a private context --

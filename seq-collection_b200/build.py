@@ -18,7 +18,7 @@ SC = os.path.join(HERE, "sc")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function"] + os.environ.get("FQGPU_NVCC_EXTRA", "").split()
-LIB_SOURCES = ["fq_scan.cu", "fq_meta.cu", "fqgpu_api.cu", "fq_synth.cu", "fq_shard.cu", "fq_index.cu", "fq_dedup.cu", "fq_bgzf.cu"]
+LIB_SOURCES = ["fq_scan.cu", "fq_meta.cu", "fqgpu_api.cu", "fq_synth.cu", "fq_shard.cu", "fq_index.cu", "fq_dedup.cu", "fq_bgzf.cu", "fq_gzip.cu"]
 
 
 def _stale(target: str, deps: list[str]) -> bool:

@@ -1,0 +1,536 @@
+// fq_gzip.cu -- on-device inflate of ordinary (single-member) gzip input, feeding the scan kernels (SURVEY 8f
+// rank 3; BASELINE configs[4]).
+//
+// The reference inflates .gz input on the host, one byte stream through zlib's gzread (src/utils/gzip_stream.nim:
+// 16-17, opened at src/fq_count.nim:31-32 and src/fq_meta.nim:219-220): one thread, 0.45 GB/s of FASTQ on this
+// box, the GPU idle.  A gzip member is ONE DEFLATE stream -- a block's first bit is known only when the block
+// before it has been decoded, and a match may reach 32 KiB back into bytes another block produced -- so there is
+// nothing to hand to a second thread, unless both are guessed and the guesses are then proven:
+//
+//   1. gz_sync_kernel   the compressed batch is cut into chunks; one warp per chunk looks for the first bit
+//                       position that holds a well-formed dynamic-Huffman block header (BFINAL = 0, BTYPE = 2,
+//                       counts in range, a complete code-length code, a complete literal/length code with an
+//                       end-of-block symbol, a usable distance code).  32 lanes test 32 positions at once on the
+//                       17 fixed bits and the Kraft sum of the code-length code; the few survivors are parsed by
+//                       the whole warp.
+//   2. gz_count_kernel  every chunk that found a start decodes from it WITHOUT writing, until a block ends exactly
+//                       on the next chunk's start: that proves the next start (a start the decode runs over in
+//                       mid-block was a false positive and is skipped).  The chunk records where it came to rest,
+//                       how many bytes it produced and how far back its matches reached.
+//   3. gz_chain_kernel  follows the landings from the batch's first block (whose position IS known: the end of
+//                       the gzip header, or where the batch before stopped), gives the chunks on that chain
+//                       their output offsets, and checks every look-back against the bytes that exist.
+//   4. gz_write_kernel  the chain's chunks decode again, now writing 16-bit symbols: a byte, or -- for a match
+//                       that reaches behind the chunk's first byte -- a MARKER holding the position in the
+//                       32 KiB window before the chunk.  Matches copy symbols, so markers propagate.
+//   5. gz_window_kernel one CTA walks the chain in order and turns "window before chunk i" into "window before
+//                       chunk i+1" (the only serial step: 32 KiB per chunk, in shared memory).
+//   6. gz_resolve_kernel every marker is replaced through its chunk's window; bytes go to the buffer
+//                       fqgpu_scan_device reads.
+//
+// The decoder (fq_inflate.cuh) is the BGZF path's: a warp per stream in lockstep, lookup tables in shared memory,
+// cooperative match copies.  Whatever is not proven -- a broken chain, a stream zlib would reject, a truncated
+// file -- makes the caller fall back to gzread, so results and error behaviour stay the reference's.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fq_gzip.h"
+#include "fq_inflate.cuh"
+
+namespace fq {
+
+typedef unsigned long long u64;
+
+constexpr int GZ_WARPS = 4;        // chunks per CTA
+constexpr int GZ_MAX_PASSED = 6;   // false starts one chunk may run over before it gives up
+constexpr uint32_t GZ_MAX_OUT = 0xF0000000u;
+
+// LSB-first bit reader over the batch's 32-bit words that knows its position.  Beyond `wend` the stream reads as
+// zeros, so a decode that runs off the end stays inside the buffer.
+struct GzBits {
+  const uint32_t* w0;
+  const uint32_t* w;
+  const uint32_t* wend;
+  u64 buf;
+  int cnt;
+  __device__ __forceinline__ void init(const uint32_t* base, const uint32_t* end, u64 bit) {
+    w0 = base; wend = end;
+    w = base + (bit >> 5);
+    const uint32_t sh = (uint32_t)bit & 31u;
+    buf = (u64)((w < wend ? __ldg(w) : 0u) >> sh);
+    w++;
+    cnt = 32 - (int)sh;
+  }
+  __device__ __forceinline__ void refill() {  // afterwards cnt >= 33
+    if (cnt <= 32) { buf |= (u64)(w < wend ? __ldg(w) : 0u) << cnt; w++; cnt += 32; }
+  }
+  __device__ __forceinline__ uint32_t take(int n) {  // n <= 16
+    const uint32_t v = (uint32_t)buf & ((1u << n) - 1u);
+    buf >>= n; cnt -= n;
+    return v;
+  }
+  __device__ __forceinline__ u64 bitpos() const { return (u64)(w - w0) * 32ull - (u64)cnt; }
+};
+
+// The code lengths of a dynamic block (RFC 1951 3.2.7) into t.lens[0 .. nlen + ndist); the reader stands behind
+// the three block-header bits.  Returns nonzero for what zlib's inflate() calls an invalid block.
+__device__ int gz_dyn_lengths(GzBits& b, WarpTables& t, int lane, int& nlen, int& ndist) {
+  b.refill();
+  nlen = (int)b.take(5) + 257; ndist = (int)b.take(5) + 1;
+  const int ncode = (int)b.take(4) + 4;
+  if (nlen > 286 || ndist > 30) return 1;
+  for (int k = lane; k < 19; k += 32) t.lens[k] = 0;
+  __syncwarp();
+  for (int k = 0; k < ncode; k++) { b.refill(); const uint32_t v = b.take(3); if (lane == 0) t.lens[kClOrder[k]] = (uint8_t)v; }
+  __syncwarp();
+  if (huff_build(t.dcount, t.dsym, t.dist, 7, t.lens, 19, lane) != 0) return 1;  // the code-length code must be complete
+  int idx = 0;
+  while (idx < nlen + ndist) {
+    const int sym = huff_decode(b, t.dist, 7, t.dcount, t.dsym);
+    if (sym < 0) return 1;
+    if (sym < 16) { if (lane == 0) t.lens[idx] = (uint8_t)sym; idx++; continue; }
+    int prev = 0, rep;
+    b.refill();
+    __syncwarp();
+    if (sym == 16) { if (idx == 0) return 1; prev = t.lens[idx - 1]; rep = 3 + (int)b.take(2); }
+    else if (sym == 17) rep = 3 + (int)b.take(3);
+    else rep = 11 + (int)b.take(7);
+    if (idx + rep > nlen + ndist) return 1;
+    if (lane == 0) for (int k = 0; k < rep; k++) t.lens[idx + k] = (uint8_t)prev;
+    idx += rep;
+    __syncwarp();
+  }
+  __syncwarp();
+  if (t.lens[256] == 0) return 1;  // no end-of-block code
+  return 0;
+}
+
+// ---- 1. block-start search ---------------------------------------------------------------------------------------
+// Is bit t the first bit of a dynamic block the way a compressor writes one?  (Stricter than inflate(): both codes
+// complete -- zlib, libdeflate, igzip and pigz always emit complete codes -- or a distance code of at most one
+// symbol.  A real start that fails this is merely not used: the chunk before decodes through it.)
+__device__ bool gz_header_plausible(const uint32_t* words, const uint32_t* wend, u64 t, WarpTables& tb, int lane) {
+  GzBits b;
+  b.init(words, wend, t + 3);
+  int nlen, ndist;
+  if (gz_dyn_lengths(b, tb, lane, nlen, ndist)) return false;
+  uint32_t sl = 0, sd = 0, nd = 0;
+  for (int s = lane; s < nlen; s += 32) { const int l = tb.lens[s]; if (l) sl += 32768u >> l; }
+  for (int s = lane; s < ndist; s += 32) { const int l = tb.lens[nlen + s]; if (l) { sd += 32768u >> l; nd++; } }
+  sl = __reduce_add_sync(0xffffffffu, sl);
+  sd = __reduce_add_sync(0xffffffffu, sd);
+  nd = __reduce_add_sync(0xffffffffu, nd);
+  __syncwarp();
+  if (sl != 32768u) return false;
+  return sd == 32768u || nd == 0 || (nd == 1 && sd == 16384u);
+}
+
+__global__ void __launch_bounds__(32 * GZ_WARPS) gz_sync_kernel(const uint32_t* __restrict__ words, u64 nbytes, uint32_t chunk_bytes,
+                                                                int nchunks, u64 start_bit, GzChunk* __restrict__ chunks, uint32_t* nfound) {
+  __shared__ WarpTables tables[GZ_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * GZ_WARPS + warp;
+  if (c >= nchunks) return;
+  const uint32_t* wend = words + ((nbytes + 3) >> 2);
+  const u64 end_bits = nbytes * 8ull;
+  u64 found = GZ_NONE;
+  if (c == 0) {
+    found = start_bit;
+  } else {
+    u64 lo = (u64)c * chunk_bytes * 8ull, hi = lo + (u64)chunk_bytes * 8ull;
+    if (lo <= start_bit) lo = start_bit + 1;
+    const u64 last = end_bits > 96 ? end_bits - 96 : 0;  // a block header and an end-of-block do not fit behind this
+    if (hi > last) hi = last;
+    for (u64 t0 = lo & ~31ull; t0 < hi; t0 += 32) {
+      const uint32_t* p = words + (t0 >> 5);
+      const uint32_t w0 = __ldg(p), w1 = p + 1 < wend ? __ldg(p + 1) : 0u, w2 = p + 2 < wend ? __ldg(p + 2) : 0u,
+                     w3 = p + 3 < wend ? __ldg(p + 3) : 0u;
+      const uint32_t a = __funnelshift_r(w0, w1, lane), bq = __funnelshift_r(w1, w2, lane), cq = __funnelshift_r(w2, w3, lane);
+      const u64 t = t0 + (u64)lane;
+      // BFINAL = 0, BTYPE = 2 (bits 1-2, LSB first), HLIT <= 29, HDIST <= 29
+      bool ok = (a & 7u) == 4u && ((a >> 3) & 31u) <= 29u && ((a >> 8) & 31u) <= 29u && t >= lo && t < hi;
+      if (ok) {  // the (HCLEN + 4) code lengths of 3 bits from bit 17: Kraft sum of a complete code = 128
+        const int ncode = (int)((a >> 13) & 15u) + 4;
+        u64 pre = ((((u64)bq << 32) | a) >> 17) | ((u64)cq << 47);
+        uint32_t kraft = 0;
+        for (int k = 0; k < ncode; k++) { kraft += (128u >> (pre & 7u)) & 127u; pre >>= 3; }
+        ok = kraft == 128u;
+      }
+      uint32_t m = __ballot_sync(0xffffffffu, ok);
+      while (m) {
+        const int j = __ffs((int)m) - 1;
+        m &= m - 1;
+        if (gz_header_plausible(words, wend, t0 + (u64)j, tables[warp], lane)) { found = t0 + (u64)j; break; }
+      }
+      if (found != GZ_NONE) break;
+    }
+  }
+  if (lane == 0) {
+    GzChunk k;
+    k.start_bit = found; k.end_bit = 0; k.out_off = 0; k.out_len = 0; k.flags = 0; k.need = 0; k.land = -1;
+    chunks[c] = k;
+    if (found != GZ_NONE) atomicAdd(nfound, 1u);
+  }
+}
+
+// ---- 2. / 4. the chunk decoder -----------------------------------------------------------------------------------------
+// COUNT (WRITE = false): decode from the chunk's start until a block ends on a later chunk's start (or the
+// stream / the batch ends); nothing is written.  WRITE: decode the same blocks again, up to the recorded end, as
+// 16-bit symbols into m[]: a byte, or 0x8000 | (position in the 32 KiB window before the chunk).  With `win` the
+// window is known (the batch's first chunk) and bytes are taken from it directly.
+template <bool WRITE>
+__device__ __noinline__ void gz_chunk(const uint32_t* __restrict__ words, u64 nbytes, u64 chunk_bits, GzChunk* chunks, int nchunks, int c,
+                                      uint16_t* m, const uint8_t* __restrict__ win, uint32_t wvalid, WarpTables& t, int lane, uint32_t* err) {
+  const bool known = c == 0;  // the batch's first chunk: the window before it is known (wvalid bytes of it exist)
+  const GzChunk ck = chunks[c];
+  if (ck.start_bit == GZ_NONE) return;
+  if (WRITE && !(ck.flags & GZC_CHAIN)) return;
+  const uint32_t* wend = words + ((nbytes + 3) >> 2);
+  const u64 end_bits = nbytes * 8ull;
+  const uint8_t* bytes = reinterpret_cast<const uint8_t*>(words);
+  GzBits b;
+  b.init(words, wend, ck.start_bit);
+  int nextc = c;
+  u64 limit;
+  if (WRITE) {
+    limit = ck.end_bit;
+  } else {
+    nextc = c + 1;
+    while (nextc < nchunks && chunks[nextc].start_bit == GZ_NONE) nextc++;
+    limit = nextc < nchunks ? chunks[nextc].start_bit : GZ_NONE;
+  }
+  // (w - w0) <= pos / 32 + 2 always, so b.w > wstop proves pos > limit
+  const uint32_t* wstop = limit == GZ_NONE ? wend + 2 : words + (limit >> 5) + 2;
+  uint32_t produced = 0, need = 0, flags = 0;
+  u64 bpos = ck.start_bit;  // the last block boundary and the bytes produced up to it
+  uint32_t bout = 0;
+  int passed = 0, land = -1;
+
+  // moves the limit past `pos` (COUNT): the starts in between were not block boundaries
+  auto advance_limit = [&](u64 pos) -> bool {
+    while (limit != GZ_NONE && pos > limit) {
+      if (++passed > GZ_MAX_PASSED) return false;
+      int k = (int)(pos / chunk_bits);
+      if (k <= nextc) k = nextc + 1;
+      while (k < nchunks && (chunks[k].start_bit == GZ_NONE || chunks[k].start_bit < pos)) k++;
+      nextc = k;
+      limit = k < nchunks ? chunks[k].start_bit : GZ_NONE;
+    }
+    wstop = limit == GZ_NONE ? wend + 2 : words + (limit >> 5) + 2;
+    return true;
+  };
+
+  for (;;) {
+    const u64 pos = b.bitpos();
+    if (pos > end_bits) { produced = bout; flags |= GZC_INCOMPLETE; break; }  // the block "ended" in the padding
+    bpos = pos; bout = produced;
+    if (WRITE) {
+      if (pos == limit) break;
+      if (pos > limit) { flags |= GZC_ERROR; break; }
+    } else {
+      if (!advance_limit(pos)) { flags |= GZC_GIVEUP; break; }
+      if (pos == limit) { land = nextc; break; }
+      if (pos + 10 > end_bits) { flags |= GZC_INCOMPLETE; break; }  // (the shortest block: 3 + 7 bits)
+    }
+    b.refill();
+    const int last = (int)b.take(1);
+    const int type = (int)b.take(2);
+    if (type == 3) { flags |= GZC_ERROR; break; }
+    if (type == 0) {  // stored: LEN, ~LEN, LEN bytes from the next byte boundary
+      b.take(b.cnt & 7);
+      b.refill();
+      const uint32_t len = b.take(16);
+      b.refill();
+      const uint32_t nlen = b.take(16);
+      if ((len ^ 0xFFFFu) != nlen) { flags |= GZC_ERROR; break; }
+      const u64 src = b.bitpos() >> 3;
+      if (src + len > nbytes) {  // runs past the batch
+        if (!WRITE && advance_limit(end_bits + 1) && limit == GZ_NONE) { produced = bout; flags |= GZC_INCOMPLETE; }
+        else flags |= WRITE ? GZC_ERROR : GZC_GIVEUP;
+        break;
+      }
+      if (produced > GZ_MAX_OUT - len) { flags |= GZC_GIVEUP; break; }
+      if (WRITE) for (uint32_t k = (uint32_t)lane; k < len; k += 32u) m[produced + k] = bytes[src + k];
+      produced += len;
+      b.init(words, wend, (src + len) * 8ull);
+    } else {
+      __syncwarp();
+      if (type == 1) {  // fixed codes
+        for (int s = lane; s < 288; s += 32) t.lens[s] = s < 144 ? 8 : (s < 256 ? 9 : (s < 280 ? 7 : 8));
+        __syncwarp();
+        huff_build(t.lcount, t.lsym, t.lit, LBITS, t.lens, 288, lane);
+        for (int s = lane; s < 30; s += 32) t.lens[s] = 5;
+        __syncwarp();
+        huff_build(t.dcount, t.dsym, t.dist, DBITS, t.lens, 30, lane);
+      } else {
+        int nl, ndist;
+        if (gz_dyn_lengths(b, t, lane, nl, ndist)) { flags |= GZC_ERROR; break; }
+        if (!huff_acceptable(huff_build(t.dcount, t.dsym, t.dist, DBITS, t.lens + nl, ndist, lane), t.dcount, ndist) ||
+            !huff_acceptable(huff_build(t.lcount, t.lsym, t.lit, LBITS, t.lens, nl, lane), t.lcount, nl)) { flags |= GZC_ERROR; break; }
+      }
+      bool stop = false;
+      for (;;) {  // literals and matches of this block
+        if (b.w > wstop) {  // ran over the limit in mid-block
+          if (WRITE) { flags |= GZC_ERROR; stop = true; break; }
+          if (limit == GZ_NONE) { produced = bout; flags |= GZC_INCOMPLETE; stop = true; break; }
+          if (!advance_limit(b.bitpos())) { flags |= GZC_GIVEUP; stop = true; break; }
+          if (b.w > wstop) continue;
+        }
+        int sym = huff_decode(b, t.lit, LBITS, t.lcount, t.lsym);
+        if (sym < 0) { flags |= GZC_ERROR; stop = true; break; }
+        if (sym < 256) {
+          if (WRITE && lane == 0) m[produced] = (uint16_t)sym;
+          produced++;
+        } else if (sym == 256) {
+          break;
+        } else {
+          sym -= 257;
+          if (sym >= 29) { flags |= GZC_ERROR; stop = true; break; }
+          const uint32_t len = kLenBase[sym] + b.take(kLenExtra[sym]);  // (>= 33 bits were there: 15 + 5 used)
+          const int ds = huff_decode(b, t.dist, DBITS, t.dcount, t.dsym);
+          if (ds < 0 || ds >= 30) { flags |= GZC_ERROR; stop = true; break; }
+          const uint32_t dist = kDistBase[ds] + b.take(kDistExtra[ds]);
+          if (dist > produced) {  // reaches behind the chunk's first byte
+            const uint32_t back = dist - produced;
+            if (known && back > wvalid) { flags |= GZC_ERROR; stop = true; break; }  // zlib: "invalid distance too far back"
+            need = back > need ? back : need;
+          }
+          if (produced > GZ_MAX_OUT) { flags |= GZC_GIVEUP; stop = true; break; }
+          if (WRITE) {
+            __syncwarp();  // earlier symbols (lane 0's literals, other lanes' match symbols) are visible to every lane
+            for (uint32_t k = (uint32_t)lane; k < len; k += 32u) {
+              const uint32_t kk = dist >= len ? k : k % dist;  // a run shorter than its length repeats with period dist
+              uint16_t v;
+              if (produced + kk >= dist) {
+                v = m[produced + kk - dist];
+              } else {
+                const uint32_t idx = GZ_WINDOW - (dist - produced - kk);
+                v = known ? (uint16_t)win[idx] : (uint16_t)(0x8000u | idx);
+              }
+              m[produced + k] = v;
+            }
+          }
+          produced += len;
+        }
+      }
+      if (stop) break;
+    }
+    if (last) {
+      const u64 e = b.bitpos();
+      if (e > end_bits) { produced = bout; flags |= GZC_INCOMPLETE; }
+      else { bpos = e; bout = produced; flags |= GZC_FINAL; }
+      break;
+    }
+  }
+  __syncwarp();
+  if (WRITE) {
+    if (lane == 0 && ((flags & (GZC_ERROR | GZC_GIVEUP)) || bout != ck.out_len || bpos != ck.end_bit)) atomicOr(err, 1u);
+  } else if (lane == 0) {
+    GzChunk& o = chunks[c];
+    o.end_bit = bpos; o.out_len = bout; o.flags = flags; o.need = need; o.land = land;
+  }
+}
+
+__global__ void __launch_bounds__(32 * GZ_WARPS) gz_count_kernel(const uint32_t* __restrict__ words, u64 nbytes, u64 chunk_bits, GzChunk* chunks,
+                                                                 int nchunks, uint32_t wvalid) {
+  __shared__ WarpTables tables[GZ_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * GZ_WARPS + warp;
+  if (c >= nchunks) return;
+  gz_chunk<false>(words, nbytes, chunk_bits, chunks, nchunks, c, nullptr, nullptr, wvalid, tables[warp], lane, nullptr);
+}
+
+__global__ void __launch_bounds__(32 * GZ_WARPS) gz_write_kernel(const uint32_t* __restrict__ words, u64 nbytes, u64 chunk_bits, GzChunk* chunks,
+                                                                 int nchunks, uint16_t* markers, const uint8_t* __restrict__ window, uint32_t wvalid,
+                                                                 uint32_t* err) {
+  __shared__ WarpTables tables[GZ_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * GZ_WARPS + warp;
+  if (c >= nchunks) return;
+  gz_chunk<true>(words, nbytes, chunk_bits, chunks, nchunks, c, markers + chunks[c].out_off, window, wvalid, tables[warp], lane, err);
+}
+
+// ---- 3. the chain ------------------------------------------------------------------------------------------------------
+// One CTA.  Thread 0 follows the landings through shared memory; then all threads give the chain's chunks their
+// output offsets (an exclusive scan) and check them.
+constexpr int CHAIN_THREADS = 1024;
+__global__ void __launch_bounds__(CHAIN_THREADS) gz_chain_kernel(GzChunk* chunks, int nchunks, u64 prior_out, GzResult* res, uint32_t* order, u64* coff) {
+  extern __shared__ int land_s[];  // nchunks landings
+  __shared__ uint32_t nchain_s, bad_s;
+  __shared__ u64 wsum[CHAIN_THREADS / 32], carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int c = tid; c < nchunks; c += CHAIN_THREADS) land_s[c] = chunks[c].land;
+  if (tid == 0) { bad_s = 0; carry_s = 0; }
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t n = 0;
+    int c = 0;
+    while (c >= 0 && n < (uint32_t)nchunks) { order[n++] = (uint32_t)c; const int nx = land_s[c]; c = nx > c ? nx : -1; }
+    nchain_s = n;
+  }
+  __syncthreads();
+  const uint32_t nchain = nchain_s;
+  uint32_t passed = 0;
+  for (uint32_t i0 = 0; i0 < nchain; i0 += CHAIN_THREADS) {
+    const uint32_t i = i0 + (uint32_t)tid;
+    u64 len = 0;
+    uint32_t flags = 0, need = 0;
+    int c = -1;
+    if (i < nchain) {
+      c = (int)order[i];
+      len = chunks[c].out_len; flags = chunks[c].flags; need = chunks[c].need;
+      // only the chain's last chunk may lack a landing
+      if ((flags & (GZC_ERROR | GZC_GIVEUP)) || (i + 1 < nchain ? (flags & (GZC_FINAL | GZC_INCOMPLETE)) != 0 : !(flags & (GZC_FINAL | GZC_INCOMPLETE))))
+        atomicOr(&bad_s, 1u);
+      if (i + 1 < nchain) {  // chunks with a start between this one and its landing: starts that were run over
+        for (int k = c + 1; k < (int)order[i + 1]; k++) passed += chunks[k].start_bit != GZ_NONE;
+      }
+    }
+    u64 incl = len;
+    for (int d = 1; d < 32; d <<= 1) { const u64 nb = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += nb; }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    u64 base = carry_s;
+    for (int w = 0; w < warp; w++) base += wsum[w];
+    const u64 off = base + incl - len;
+    if (i < nchain) {
+      chunks[c].out_off = off;
+      chunks[c].flags = flags | GZC_CHAIN;
+      coff[i] = off;
+      if (i > 0 && (u64)need > off + prior_out) atomicOr(&bad_s, 1u);  // a match reaches behind the first byte of the stream
+      if (i + 1 == nchain) {
+        coff[nchain] = off + len;
+        res->total_out = off + len; res->end_bit = chunks[c].end_bit; res->final_block = (flags & GZC_FINAL) ? 1u : 0u;
+      }
+    }
+    __syncthreads();
+    if (tid == CHAIN_THREADS - 1) carry_s = base + incl;
+    __syncthreads();
+  }
+  passed = __reduce_add_sync(0xffffffffu, passed);
+  __shared__ uint32_t passed_s;
+  if (tid == 0) passed_s = 0;
+  __syncthreads();
+  if (lane == 0 && passed) atomicAdd(&passed_s, passed);
+  __syncthreads();
+  if (tid == 0) { res->status = bad_s ? GZR_BROKEN : GZR_OK; res->nchain = nchain; res->passed = passed_s; }
+}
+
+// ---- 5. windows ----------------------------------------------------------------------------------------------------------
+// One CTA walks the chain: the 32 KiB before chunk i+1 are the tail of (window before chunk i) ++ (chunk i's symbols
+// resolved through that window).  Row i of wbuf is the window before chain chunk i; the window after the last chunk
+// goes to `window` for the next batch.
+constexpr int WIN_THREADS = 1024;
+constexpr int WIN_PER = GZ_WINDOW / WIN_THREADS;  // 32 window bytes per thread
+__global__ void __launch_bounds__(WIN_THREADS) gz_window_kernel(const u64* __restrict__ coff, uint32_t nchain, const uint16_t* __restrict__ markers,
+                                                                uint8_t* __restrict__ wbuf, uint8_t* window) {
+  extern __shared__ uint8_t win_s[];  // 2 x 32 KiB
+  const int tid = threadIdx.x;
+  for (int r = 0; r < WIN_PER; r++) win_s[tid + r * WIN_THREADS] = window[tid + r * WIN_THREADS];
+  __syncthreads();
+  uint32_t cur = 0;
+  uint16_t sym[WIN_PER];
+  for (uint32_t i = 0; i < nchain; i++) {
+    const u64 off = coff[i], end = coff[i + 1];
+    const u64 len = end - off;
+    const uint8_t* wi = win_s + cur * GZ_WINDOW;
+    uint8_t* wo = win_s + (cur ^ 1u) * GZ_WINDOW;
+    // position j of the new window is output byte end - 32768 + j
+#pragma unroll
+    for (int r = 0; r < WIN_PER; r++) {
+      const uint32_t j = (uint32_t)tid + (uint32_t)r * WIN_THREADS;
+      sym[r] = (u64)(GZ_WINDOW - j) <= len ? markers[end - GZ_WINDOW + j] : (uint16_t)0xFFFFu;
+    }
+    uint8_t* row = i + 1 < nchain ? wbuf + (size_t)(i + 1) * GZ_WINDOW : window;
+#pragma unroll
+    for (int r = 0; r < WIN_PER; r++) {
+      const uint32_t j = (uint32_t)tid + (uint32_t)r * WIN_THREADS;
+      uint8_t v;
+      if ((u64)(GZ_WINDOW - j) <= len) v = sym[r] < 256u ? (uint8_t)sym[r] : wi[sym[r] & 0x7FFFu];
+      else v = wi[j + (uint32_t)len];  // still inside the old window (len < 32768 here)
+      wo[j] = v;
+      row[j] = v;
+    }
+    cur ^= 1u;
+    __syncthreads();
+  }
+}
+
+// ---- 6. resolve ------------------------------------------------------------------------------------------------------------
+constexpr int RES_THREADS = 256;
+__global__ void __launch_bounds__(RES_THREADS) gz_resolve_kernel(const uint16_t* __restrict__ markers, const uint8_t* __restrict__ wbuf,
+                                                                 const u64* __restrict__ coff, uint32_t nchain, u64 total, uint8_t* __restrict__ out) {
+  const u64 ngroups = (total + 7) / 8;
+  for (u64 g = (u64)blockIdx.x * RES_THREADS + threadIdx.x; g < ngroups; g += (u64)gridDim.x * RES_THREADS) {
+    const u64 p0 = g * 8;
+    uint32_t lo = 0, hi = nchain;  // the chain chunk holding p0: the last i with coff[i] <= p0
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (coff[mid] <= p0) lo = mid; else hi = mid; }
+    uint32_t i = lo;
+    u64 next = coff[i + 1];
+    const uint4 q = *reinterpret_cast<const uint4*>(markers + p0);  // (the buffer is padded to a multiple of 8 symbols)
+    const uint32_t s[8] = {q.x & 0xFFFFu, q.x >> 16, q.y & 0xFFFFu, q.y >> 16, q.z & 0xFFFFu, q.z >> 16, q.w & 0xFFFFu, q.w >> 16};
+    u64 packed = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const u64 p = p0 + (u64)k;
+      while (p >= next && i + 1 < nchain) { i++; next = coff[i + 1]; }
+      uint32_t v = s[k];
+      if (v >= 256u) v = p < total ? wbuf[(size_t)i * GZ_WINDOW + (v & 0x7FFFu)] : 0u;
+      packed |= (u64)(v & 0xFFu) << (8 * k);
+    }
+    *reinterpret_cast<u64*>(out + p0) = packed;  // (padded likewise)
+  }
+}
+
+// ---- launchers ---------------------------------------------------------------------------------------------------------------
+cudaError_t launch_gz_sync(const uint8_t* d_comp, size_t nbytes, uint32_t chunk_bytes, int nchunks, unsigned long long start_bit,
+                           GzChunk* chunks, uint32_t* nfound, cudaStream_t st) {
+  gz_sync_kernel<<<(nchunks + GZ_WARPS - 1) / GZ_WARPS, 32 * GZ_WARPS, 0, st>>>(reinterpret_cast<const uint32_t*>(d_comp), (u64)nbytes, chunk_bytes,
+                                                                                nchunks, start_bit, chunks, nfound);
+  return cudaGetLastError();
+}
+cudaError_t launch_gz_count(const uint8_t* d_comp, size_t nbytes, uint32_t chunk_bytes, GzChunk* chunks, int nchunks, uint32_t wvalid,
+                            cudaStream_t st) {
+  gz_count_kernel<<<(nchunks + GZ_WARPS - 1) / GZ_WARPS, 32 * GZ_WARPS, 0, st>>>(reinterpret_cast<const uint32_t*>(d_comp), (u64)nbytes,
+                                                                                 (u64)chunk_bytes * 8ull, chunks, nchunks, wvalid);
+  return cudaGetLastError();
+}
+cudaError_t launch_gz_chain(GzChunk* chunks, int nchunks, unsigned long long prior_out, GzResult* res, uint32_t* order,
+                            unsigned long long* coff, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gz_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GZ_MAX_CHUNKS * (int)sizeof(int));
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  if (nchunks > GZ_MAX_CHUNKS) return cudaErrorInvalidValue;
+  gz_chain_kernel<<<1, CHAIN_THREADS, (size_t)nchunks * sizeof(int), st>>>(chunks, nchunks, prior_out, res, order, coff);
+  return cudaGetLastError();
+}
+cudaError_t launch_gz_write(const uint8_t* d_comp, size_t nbytes, uint32_t chunk_bytes, GzChunk* chunks, int nchunks, uint16_t* markers,
+                            const uint8_t* window, uint32_t wvalid, uint32_t* err, cudaStream_t st) {
+  gz_write_kernel<<<(nchunks + GZ_WARPS - 1) / GZ_WARPS, 32 * GZ_WARPS, 0, st>>>(reinterpret_cast<const uint32_t*>(d_comp), (u64)nbytes,
+                                                                                 (u64)chunk_bytes * 8ull, chunks, nchunks, markers, window, wvalid, err);
+  return cudaGetLastError();
+}
+cudaError_t launch_gz_windows(const unsigned long long* coff, uint32_t nchain, const uint16_t* markers, uint8_t* wbuf, uint8_t* window,
+                              cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gz_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)GZ_WINDOW);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  gz_window_kernel<<<1, WIN_THREADS, 2 * GZ_WINDOW, st>>>(coff, nchain, markers, wbuf, window);
+  return cudaGetLastError();
+}
+cudaError_t launch_gz_resolve(const uint16_t* markers, const uint8_t* wbuf, const unsigned long long* coff, uint32_t nchain,
+                              unsigned long long total_out, uint8_t* out, int sms, cudaStream_t st) {
+  if (total_out == 0) return cudaSuccess;
+  const u64 want = (total_out / 8 + RES_THREADS - 1) / RES_THREADS;
+  const int grid = (int)(want < (u64)sms * 8 ? (want ? want : 1) : (u64)sms * 8);
+  gz_resolve_kernel<<<grid, RES_THREADS, 0, st>>>(markers, wbuf, coff, nchain, total_out, out);
+  return cudaGetLastError();
+}
+
+}  // namespace fq

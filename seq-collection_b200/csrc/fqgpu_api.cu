@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "fq_bgzf.h"
+#include "fq_gzip.h"
 #include "fq_layout.h"
 
 #include "fqgpu_ctx.h"
@@ -67,6 +68,14 @@ void fqgpu_destroy(fqgpu_ctx* ctx) {
   cudaFree(ctx->d_inflated);
   cudaFree(ctx->d_members);
   cudaFree(ctx->d_mstatus);
+  cudaFree(ctx->d_gzchunks);
+  cudaFree(ctx->d_gzorder);
+  cudaFree(ctx->d_gzcoff);
+  cudaFree(ctx->d_gzres);
+  if (ctx->h_gzres) cudaFreeHost(ctx->h_gzres);
+  cudaFree(ctx->d_gzsym);
+  cudaFree(ctx->d_gzwbuf);
+  cudaFree(ctx->d_gzwindow);
   if (ctx->h_out) cudaFreeHost(ctx->h_out);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -132,6 +141,8 @@ int fqgpu_reset(fqgpu_ctx* ctx) {
   ctx->kernel_ms_done = 0.0;
   ctx->launches = 0;
   ctx->bgzf_members = 0;
+  ctx->gzip_chunks = 0;
+  ctx->gzip_passed = 0;
   ctx->shard_rank = 0;
   ctx->shard_world = 1;
   ctx->shard_exact = false;
@@ -570,9 +581,175 @@ static int count_bgzf(fqgpu_ctx* ctx, const char* path) {
   return FQGPU_OK;
 }
 
+// ---- ordinary gzip input: inflated on the device in parallel (fq_gzip.cu) ------------------------------------
+// Same contract as count_bgzf: FQGPU_OK = the whole file went through the device path, 1 = anything the device
+// path does not prove (not gzip, a chain that does not close, a stream zlib would reject, a truncated file, a
+// wrong ISIZE): the caller resets and lets gzread decide, which keeps the reference's behaviour for broken input.
+// The compressed file is taken in batches (FQGPU_GZ_BATCH_MB, default 256 MiB); a batch starts at the block
+// boundary where the one before stopped, with the 32 KiB before it as its window.
+static size_t env_size(const char* name, size_t dflt, size_t lo, size_t hi) {
+  const char* e = getenv(name);
+  if (!e) return dflt;
+  const long long v = atoll(e);
+  return v < (long long)lo ? lo : (v > (long long)hi ? hi : (size_t)v);
+}
+
+// the first payload byte of the gzip member at `off` (RFC 1952), or 0 when there is no member header there
+static size_t gzip_payload_offset(int fd, size_t off, size_t fsize) {
+  uint8_t h[10];
+  if (off + 18 > fsize || pread(fd, h, 10, (off_t)off) != 10) return 0;
+  if (!(h[0] == 0x1f && h[1] == 0x8b && h[2] == 8) || (h[3] & 0xE0)) return 0;
+  size_t p = off + 10;
+  const int flg = h[3];
+  if (flg & 4) {  // FEXTRA
+    uint8_t x[2];
+    if (pread(fd, x, 2, (off_t)p) != 2) return 0;
+    p += 2 + ((size_t)x[0] | ((size_t)x[1] << 8));
+  }
+  for (int pass = 0; pass < 2; pass++) {  // FNAME, FCOMMENT: zero-terminated
+    if (!(flg & (pass == 0 ? 8 : 16))) continue;
+    for (;;) {
+      uint8_t buf[256];
+      const ssize_t r = p < fsize ? pread(fd, buf, sizeof buf, (off_t)p) : 0;
+      if (r <= 0) return 0;
+      const void* z = memchr(buf, 0, (size_t)r);
+      if (z) { p += (size_t)((const uint8_t*)z - buf) + 1; break; }
+      p += (size_t)r;
+    }
+  }
+  if (flg & 2) p += 2;  // FHCRC
+  return p + 8 < fsize ? p : 0;
+}
+
+static int count_gzip(fqgpu_ctx* ctx, const char* path) {
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) return 1;
+  struct stat sb;
+  if (fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode)) { close(fd); return 1; }
+  const size_t fsize = (size_t)sb.st_size;
+  size_t payload = gzip_payload_offset(fd, 0, fsize);
+  if (!payload) { close(fd); return 1; }
+  auto bail = [&](int code) { close(fd); return code; };
+#define CU_B(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return bail(FQGPU_ECUDA); } } while (0)
+  CU_B(cudaSetDevice(ctx->device));
+  const size_t batch_cap = env_size("FQGPU_GZ_BATCH_MB", 256, 1, 1024) << 20;
+  const size_t want = fsize + 4096 < batch_cap ? ((fsize + 8191) & ~(size_t)4095) : batch_cap;
+  if (ctx->comp_cap < want) {
+    if (ctx->h_comp) cudaFreeHost(ctx->h_comp);
+    cudaFree(ctx->d_comp);
+    ctx->h_comp = nullptr; ctx->d_comp = nullptr; ctx->comp_cap = 0;
+    CU_B(cudaMallocHost(&ctx->h_comp, want));
+    CU_B(cudaMalloc(&ctx->d_comp, want + 64));
+    ctx->comp_cap = want;
+  }
+  if (!ctx->d_gzchunks) {
+    CU_B(cudaMalloc(&ctx->d_gzchunks, (size_t)fq::GZ_MAX_CHUNKS * sizeof(fq::GzChunk)));
+    CU_B(cudaMalloc(&ctx->d_gzorder, (size_t)fq::GZ_MAX_CHUNKS * sizeof(uint32_t)));
+    CU_B(cudaMalloc(&ctx->d_gzcoff, ((size_t)fq::GZ_MAX_CHUNKS + 1) * sizeof(u64)));
+    CU_B(cudaMalloc(&ctx->d_gzres, sizeof(fq::GzResult) + 16));
+    CU_B(cudaMallocHost(&ctx->h_gzres, sizeof(fq::GzResult) + 16));
+    CU_B(cudaMalloc(&ctx->d_gzwindow, fq::GZ_WINDOW));
+  }
+  fq::GzChunk* chunks = (fq::GzChunk*)ctx->d_gzchunks;
+  fq::GzResult* d_res = (fq::GzResult*)ctx->d_gzres;
+  uint32_t* d_err = (uint32_t*)((uint8_t*)ctx->d_gzres + sizeof(fq::GzResult));
+  const fq::GzResult* h_res = (const fq::GzResult*)ctx->h_gzres;
+  const uint32_t* h_err = (const uint32_t*)((const uint8_t*)ctx->h_gzres + sizeof(fq::GzResult));
+  const size_t chunk_min = env_size("FQGPU_GZ_CHUNK_KB", 16, 1, 1024) << 10;
+
+  u64 abs_bit = (u64)payload * 8ull;  // the next block's first bit, in the file
+  u64 prior_out = 0;                  // bytes of this member already inflated
+  for (;;) {
+    const size_t fpos = (size_t)(abs_bit >> 3) & ~(size_t)4095;
+    const size_t want_now = fsize - fpos < ctx->comp_cap ? fsize - fpos : ctx->comp_cap;
+    bool io_bad = false;
+    const size_t got = parallel_pread(fd, ctx->h_comp, want_now, fpos, &io_bad);
+    if (io_bad) return bail(1);
+    const u64 start_bit = abs_bit - (u64)fpos * 8ull;
+    if (start_bit + 10 > (u64)got * 8ull) return bail(1);  // the stream ends without a last block: truncated
+    size_t chunk_bytes = (got / 12288 + 4095) & ~(size_t)4095;
+    if (chunk_bytes < chunk_min) chunk_bytes = chunk_min;
+    if ((got + chunk_bytes - 1) / chunk_bytes > (size_t)fq::GZ_MAX_CHUNKS) chunk_bytes = ((got + fq::GZ_MAX_CHUNKS - 1) / fq::GZ_MAX_CHUNKS + 4095) & ~(size_t)4095;
+    const int nchunks = (int)((got + chunk_bytes - 1) / chunk_bytes);
+    const uint32_t wvalid = prior_out < fq::GZ_WINDOW ? (uint32_t)prior_out : fq::GZ_WINDOW;
+    CU_B(cudaMemcpyAsync(ctx->d_comp, ctx->h_comp, got, cudaMemcpyHostToDevice, ctx->stream));
+    CU_B(cudaMemsetAsync(ctx->d_comp + got, 0, 64, ctx->stream));
+    CU_B(cudaMemsetAsync(d_err, 0, 16, ctx->stream));
+    CU_B(fq::launch_gz_sync(ctx->d_comp, got, (uint32_t)chunk_bytes, nchunks, start_bit, chunks, d_err + 1, ctx->stream));
+    CU_B(cudaMemcpyAsync((uint8_t*)ctx->h_gzres + sizeof(fq::GzResult) + 4, d_err + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_B(cudaStreamSynchronize(ctx->stream));
+    // blocks longer than 64 chunks on average (stored or fixed-code streams, no dynamic headers to find): one warp
+    // would decode nearly everything alone -- zlib on the host is faster than that
+    if (nchunks >= 64 && (size_t)h_err[1] * 64 < (size_t)nchunks) return bail(1);
+    CU_B(fq::launch_gz_count(ctx->d_comp, got, (uint32_t)chunk_bytes, chunks, nchunks, wvalid, ctx->stream));
+    CU_B(fq::launch_gz_chain(chunks, nchunks, prior_out, d_res, ctx->d_gzorder, ctx->d_gzcoff, ctx->stream));
+    CU_B(cudaMemcpyAsync(ctx->h_gzres, ctx->d_gzres, sizeof(fq::GzResult), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_B(cudaStreamSynchronize(ctx->stream));
+    ctx->launches += 3;
+    const fq::GzResult res = *h_res;
+    if (res.status != fq::GZR_OK) return bail(1);
+    if (res.total_out == 0 && !res.final_block) return bail(1);  // no complete block in a whole batch, or a truncated file
+    const u64 total = res.total_out;
+    if (total) {
+      if (ctx->gzsym_cap < total + 16) {
+        cudaFree(ctx->d_gzsym);
+        ctx->d_gzsym = nullptr; ctx->gzsym_cap = 0;
+        const size_t cap = (size_t)total + ((size_t)total >> 3) + 4096;
+        CU_B(cudaMalloc(&ctx->d_gzsym, cap * sizeof(uint16_t)));
+        ctx->gzsym_cap = cap;
+      }
+      if (ctx->inflated_cap < total + 64) {
+        cudaFree(ctx->d_inflated);
+        ctx->d_inflated = nullptr; ctx->inflated_cap = 0;
+        const size_t cap = ((size_t)total + ((size_t)total >> 3) + 8192) & ~(size_t)4095;
+        CU_B(cudaMalloc(&ctx->d_inflated, cap));
+        ctx->inflated_cap = cap;
+      }
+      if (ctx->gzwbuf_cap < (size_t)res.nchain + 1) {
+        cudaFree(ctx->d_gzwbuf);
+        ctx->d_gzwbuf = nullptr; ctx->gzwbuf_cap = 0;
+        const size_t rows = (size_t)res.nchain + 1 + ((size_t)res.nchain >> 2);
+        CU_B(cudaMalloc(&ctx->d_gzwbuf, rows * fq::GZ_WINDOW));
+        ctx->gzwbuf_cap = rows;
+      }
+      CU_B(fq::launch_gz_write(ctx->d_comp, got, (uint32_t)chunk_bytes, chunks, nchunks, ctx->d_gzsym, ctx->d_gzwindow, wvalid, d_err, ctx->stream));
+      CU_B(fq::launch_gz_windows(ctx->d_gzcoff, res.nchain, ctx->d_gzsym, ctx->d_gzwbuf, ctx->d_gzwindow, ctx->stream));
+      CU_B(fq::launch_gz_resolve(ctx->d_gzsym, ctx->d_gzwbuf, ctx->d_gzcoff, res.nchain, total, ctx->d_inflated, ctx->grid / 2, ctx->stream));
+      CU_B(cudaMemcpyAsync((uint8_t*)ctx->h_gzres + sizeof(fq::GzResult), d_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+      ctx->launches += 3;
+      const int rc = fqgpu_scan_device(ctx, ctx->d_inflated, (size_t)total);
+      if (rc != FQGPU_OK) return bail(rc);
+      CU_B(cudaStreamSynchronize(ctx->stream));  // the batch buffers are reused
+      if (*h_err) return bail(1);
+    }
+    ctx->gzip_chunks += res.nchain;
+    ctx->gzip_passed += res.passed;
+    prior_out += total;
+    abs_bit = (u64)fpos * 8ull + res.end_bit;
+    if (!res.final_block) continue;
+    // the member's trailer: CRC-32 and ISIZE.  ISIZE is checked; the CRC is not recomputed (gzread hands the bytes out
+    // before it looks at the trailer, so the reference's counts do not depend on it either)
+    const size_t tpos = (size_t)((abs_bit + 7) >> 3);
+    uint8_t tr[8];
+    if (tpos + 8 > fsize || pread(fd, tr, 8, (off_t)tpos) != 8) return bail(1);
+    const uint32_t isize = (uint32_t)tr[4] | ((uint32_t)tr[5] << 8) | ((uint32_t)tr[6] << 16) | ((uint32_t)tr[7] << 24);
+    if (isize != (uint32_t)prior_out) return bail(1);
+    // another member behind it (`cat a.gz b.gz`) continues the stream; anything else is ignored, as gzread does
+    payload = gzip_payload_offset(fd, tpos + 8, fsize);
+    if (!payload) break;
+    abs_bit = (u64)payload * 8ull;
+    prior_out = 0;
+  }
+#undef CU_B
+  close(fd);
+  return FQGPU_OK;
+}
+
 extern "C" {
 
 unsigned long long fqgpu_bgzf_members(const fqgpu_ctx* ctx) { return ctx ? ctx->bgzf_members : 0; }
+unsigned long long fqgpu_gzip_chunks(const fqgpu_ctx* ctx) { return ctx ? ctx->gzip_chunks : 0; }
+unsigned long long fqgpu_gzip_false_starts(const fqgpu_ctx* ctx) { return ctx ? ctx->gzip_passed : 0; }
 
 int fqgpu_count_file_as(fqgpu_ctx* ctx, const char* path, int as_gz, fqgpu_stats* out) {
   NvtxRange nvtx_("fqgpu_count_file_as");
@@ -584,7 +761,13 @@ int fqgpu_count_file_as(fqgpu_ctx* ctx, const char* path, int as_gz, fqgpu_stats
     rc = count_bgzf(ctx, path);
     if (rc == FQGPU_OK) return fqgpu_finish(ctx, out);
     if (rc < 0) return rc;
-    if ((rc = fqgpu_reset(ctx)) != FQGPU_OK) return rc;  // not BGZF: the host zlib path below
+    if ((rc = fqgpu_reset(ctx)) != FQGPU_OK) return rc;  // not BGZF
+  }
+  if (gz && !getenv("FQGPU_NO_GZIP_DEVICE")) {  // ordinary gzip: chunks of the one DEFLATE stream inflated in parallel
+    rc = count_gzip(ctx, path);
+    if (rc == FQGPU_OK) return fqgpu_finish(ctx, out);
+    if (rc < 0) return rc;
+    if ((rc = fqgpu_reset(ctx)) != FQGPU_OK) return rc;  // not proven: the host zlib path below
   }
   if (gz) {
     gzFile f = gzopen(path, "rb");

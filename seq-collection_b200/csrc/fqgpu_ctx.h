@@ -90,6 +90,19 @@ struct fqgpu_ctx {
   uint32_t* d_mstatus = nullptr;
   size_t members_cap = 0;
   u64 bgzf_members = 0;        // members inflated on the device since the last reset (diagnostics)
+  // on-device inflate of ordinary gzip (fq_gzip.cu): chunk table, chain, 16-bit symbols, windows
+  void* d_gzchunks = nullptr;
+  uint32_t* d_gzorder = nullptr;
+  u64* d_gzcoff = nullptr;
+  void* d_gzres = nullptr;     // GzResult + the write pass's error word
+  void* h_gzres = nullptr;     // pinned copy
+  uint16_t* d_gzsym = nullptr;
+  size_t gzsym_cap = 0;        // symbols
+  uint8_t* d_gzwbuf = nullptr;
+  size_t gzwbuf_cap = 0;       // rows of 32 KiB
+  uint8_t* d_gzwindow = nullptr;
+  u64 gzip_chunks = 0;         // chunks of single-member gzip inflated on the device since the last reset (diagnostics)
+  u64 gzip_passed = 0;         // block starts the search found that turned out not to be block boundaries
 };
 
 

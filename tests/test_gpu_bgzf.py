@@ -46,7 +46,7 @@ def test_bgzf_edge_corpus_and_no_eof_member(ctx, tmp_path):
         assert_equal_stats(ctx.count_file(path).to_dict(), O.count(data, 100), name)
 
 
-def test_plain_gzip_takes_the_zlib_path(ctx, tmp_path):
+def test_plain_gzip_is_not_taken_for_bgzf(ctx, tmp_path):
     rng = np.random.default_rng(7)
     data = corpus.random_fastq(rng, 500)
     path = str(tmp_path / "plain.fq.gz")
