@@ -24,9 +24,10 @@
 //                       that reaches behind the chunk's first byte -- a MARKER holding the position in the
 //                       32 KiB window before the chunk.  Matches copy symbols, so markers propagate.
 //   5. gz_window_kernel one CTA walks the chain in order and turns "window before chunk i" into "window before
-//                       chunk i+1" (the only serial step: 32 KiB per chunk, in shared memory).
+//                       chunk i+1" (the only serial step: 32 KiB per chunk, in shared memory, fed by TMA).
 //   6. gz_resolve_kernel every marker is replaced through its chunk's window; bytes go to the buffer
 //                       fqgpu_scan_device reads.
+//   7. gz_crc_*         the CRC-32 of those bytes, which the host compares with the member's trailer like gzread.
 //
 // The decoder (fq_inflate.cuh) is the BGZF path's: a warp per stream in lockstep, lookup tables in shared memory,
 // cooperative match copies.  Whatever is not proven -- a broken chain, a stream zlib would reject, a truncated
@@ -34,12 +35,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "fq_dev.cuh"
 #include "fq_gzip.h"
 #include "fq_inflate.cuh"
 
 namespace fq {
-
-typedef unsigned long long u64;
 
 constexpr int GZ_WARPS = 4;        // chunks per CTA
 constexpr int GZ_MAX_PASSED = 6;   // false starts one chunk may run over before it gives up
@@ -417,43 +417,72 @@ __global__ void __launch_bounds__(CHAIN_THREADS) gz_chain_kernel(GzChunk* chunks
 }
 
 // ---- 5. windows ----------------------------------------------------------------------------------------------------------
-// One CTA walks the chain: the 32 KiB before chunk i+1 are the tail of (window before chunk i) ++ (chunk i's symbols
-// resolved through that window).  Row i of wbuf is the window before chain chunk i; the window after the last chunk
-// goes to `window` for the next batch.
+// Row i of wbuf is the 32 KiB before chain chunk i; row i+1 is the tail of (row i) ++ (chunk i's symbols resolved
+// through row i).  This is the one serial step of the whole scheme -- in FASTQ a fifth of a chunk's last symbols
+// are still markers (every header is a match on the header before it, back to the chunk's first record) -- so one
+// CTA walks the chain with everything it touches in shared memory: the symbols of the next two chunks' tails
+// arrive by bulk copies (TMA) while the current one is resolved, rows leave by bulk stores.
 constexpr int WIN_THREADS = 1024;
-constexpr int WIN_PER = GZ_WINDOW / WIN_THREADS;  // 32 window bytes per thread
+constexpr uint32_t WIN_SYM_SLOTS = GZ_WINDOW + 16;  // symbols per staging buffer (the tail, from a 16-byte boundary)
+constexpr size_t WIN_SMEM = 2 * GZ_WINDOW + 2 * WIN_SYM_SLOTS * sizeof(uint16_t) + 16;
 __global__ void __launch_bounds__(WIN_THREADS) gz_window_kernel(const u64* __restrict__ coff, uint32_t nchain, const uint16_t* __restrict__ markers,
-                                                                uint8_t* __restrict__ wbuf, uint8_t* window) {
-  extern __shared__ uint8_t win_s[];  // 2 x 32 KiB
+                                                                uint8_t* __restrict__ wbuf) {
+  extern __shared__ __align__(128) uint8_t win_smem[];
+  uint8_t* row_s = win_smem;                                                     // 2 rows
+  uint16_t* sym_s = reinterpret_cast<uint16_t*>(win_smem + 2 * GZ_WINDOW);       // 2 staging buffers
+  const uint32_t bar_s = smem_u32(win_smem + 2 * GZ_WINDOW + 2 * WIN_SYM_SLOTS * sizeof(uint16_t));
   const int tid = threadIdx.x;
-  for (int r = 0; r < WIN_PER; r++) win_s[tid + r * WIN_THREADS] = window[tid + r * WIN_THREADS];
+  // the symbols of chunk i's tail: output positions [max(off, end - 32768), end), fetched from the 16-byte boundary below
+  auto fetch = [&](uint32_t i) {
+    const u64 off = coff[i], end = coff[i + 1];
+    const u64 lo = end - off > GZ_WINDOW ? end - GZ_WINDOW : off;
+    const u64 a = lo & ~7ull;
+    uint32_t bytes = (uint32_t)(((end - a) * 2 + 15) & ~15ull);
+    if (bytes == 0) bytes = 16;  // (an empty chunk on a 16-byte boundary: every step has its copy, the phases stay in step)
+    mbar_expect_tx(bar_s + 8u * (i & 1u), bytes);
+    tma_load_1d(smem_u32(sym_s + (size_t)(i & 1u) * WIN_SYM_SLOTS), markers + a, bytes, bar_s + 8u * (i & 1u));
+  };
+  for (int j = tid; j < (int)GZ_WINDOW / 16; j += WIN_THREADS)
+    reinterpret_cast<uint4*>(row_s)[j] = reinterpret_cast<const uint4*>(wbuf)[j];  // row 0: the window before the batch
+  if (tid == 0) {
+    mbar_init(bar_s, 1);
+    mbar_init(bar_s + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
-  uint32_t cur = 0;
-  uint16_t sym[WIN_PER];
+  if (tid == 0) { fetch(0); if (nchain > 1) fetch(1); }
   for (uint32_t i = 0; i < nchain; i++) {
     const u64 off = coff[i], end = coff[i + 1];
     const u64 len = end - off;
-    const uint8_t* wi = win_s + cur * GZ_WINDOW;
-    uint8_t* wo = win_s + (cur ^ 1u) * GZ_WINDOW;
-    // position j of the new window is output byte end - 32768 + j
-#pragma unroll
-    for (int r = 0; r < WIN_PER; r++) {
-      const uint32_t j = (uint32_t)tid + (uint32_t)r * WIN_THREADS;
-      sym[r] = (u64)(GZ_WINDOW - j) <= len ? markers[end - GZ_WINDOW + j] : (uint16_t)0xFFFFu;
+    const u64 lo = len > GZ_WINDOW ? end - GZ_WINDOW : off;
+    const uint8_t* prev = row_s + (size_t)(i & 1u) * GZ_WINDOW;
+    uint8_t* cur = row_s + (size_t)((i + 1) & 1u) * GZ_WINDOW;
+    const uint16_t* sy = sym_s + (size_t)(i & 1u) * WIN_SYM_SLOTS + (lo & 7ull);  // sy[k] = the symbol at output position lo + k
+    mbar_wait(bar_s + 8u * (i & 1u), (i >> 1) & 1u);
+    const uint32_t keep = len >= GZ_WINDOW ? 0u : GZ_WINDOW - (uint32_t)len;  // positions of the new window still inside the old one
+#pragma unroll 8
+    for (int r = 0; r < (int)GZ_WINDOW / WIN_THREADS; r++) {
+      const uint32_t j = (uint32_t)tid + (uint32_t)r * WIN_THREADS;  // position j of the new window is output byte end - 32768 + j
+      uint32_t v;
+      if (j >= keep) {
+        const uint32_t s2 = sy[j - keep];
+        v = s2 < 256u ? s2 : prev[s2 & 0x7FFFu];
+      } else {
+        v = prev[j + (uint32_t)len];
+      }
+      cur[j] = (uint8_t)v;
     }
-    uint8_t* row = i + 1 < nchain ? wbuf + (size_t)(i + 1) * GZ_WINDOW : window;
-#pragma unroll
-    for (int r = 0; r < WIN_PER; r++) {
-      const uint32_t j = (uint32_t)tid + (uint32_t)r * WIN_THREADS;
-      uint8_t v;
-      if ((u64)(GZ_WINDOW - j) <= len) v = sym[r] < 256u ? (uint8_t)sym[r] : wi[sym[r] & 0x7FFFu];
-      else v = wi[j + (uint32_t)len];  // still inside the old window (len < 32768 here)
-      wo[j] = v;
-      row[j] = v;
-    }
-    cur ^= 1u;
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the row stored a step ago has left shared memory
     __syncthreads();
+    if (tid == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(wbuf + (size_t)(i + 1) * GZ_WINDOW), "r"(smem_u32(cur)),
+                   "r"(GZ_WINDOW) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      if (i + 2 < nchain) fetch(i + 2);
+    }
   }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ---- 6. resolve ------------------------------------------------------------------------------------------------------------
@@ -480,6 +509,88 @@ __global__ void __launch_bounds__(RES_THREADS) gz_resolve_kernel(const uint16_t*
     }
     *reinterpret_cast<u64*>(out + p0) = packed;  // (padded likewise)
   }
+}
+
+// ---- 7. CRC-32 of the inflated bytes --------------------------------------------------------------------------------------
+// gzread() checks the member's CRC-32; so does this path, which makes zlib's own criterion the last word on
+// everything above (a wrong chain or a wrong window cannot produce the right CRC).  The register is linear in the
+// data: for a register that starts at zero, raw(A ++ B) = raw(A) * x^(8|B|) + raw(B) over GF(2) modulo the CRC
+// polynomial.  Slices of 4 KiB are summed by one thread each (table in shared memory), then folded in order:
+// 1024 threads Horner-fold equal runs of slices, a tree joins the runs.  The host adds the tail, the bytes of the
+// batches before, and the initial all-ones register (crc_* in fqgpu_api.cu).
+constexpr uint32_t CRC_POLY = 0xEDB88320u;
+constexpr uint32_t CRC_SLICE_BYTES = 4096;
+constexpr int CRCA_THREADS = 128;
+constexpr int CRCB_THREADS = 1024;
+
+// a * b modulo the CRC polynomial; bit 31 is the coefficient of x^0 (the reflected form the register is in)
+__device__ __forceinline__ uint32_t gf_mul(uint32_t a, uint32_t b) {
+  uint32_t p = 0;
+#pragma unroll
+  for (int i = 0; i < 32; i++) {
+    p ^= (a & (0x80000000u >> i)) ? b : 0u;
+    b = (b >> 1) ^ ((b & 1u) ? CRC_POLY : 0u);
+  }
+  return p;
+}
+
+// raw[k] = the register after slice k when it starts at zero; raw[nfull] = the same for the bytes behind the last
+// full slice
+__global__ void __launch_bounds__(CRCA_THREADS) gz_crc_slices_kernel(const uint8_t* __restrict__ data, u64 total, uint32_t* __restrict__ raw) {
+  __shared__ uint32_t tab[256];
+  for (int t = threadIdx.x; t < 256; t += CRCA_THREADS) {
+    uint32_t c = (uint32_t)t;
+    for (int k = 0; k < 8; k++) c = (c & 1u) ? CRC_POLY ^ (c >> 1) : c >> 1;
+    tab[t] = c;
+  }
+  __syncthreads();
+  const u64 nfull = total / CRC_SLICE_BYTES;
+  const u64 k = (u64)blockIdx.x * CRCA_THREADS + threadIdx.x;
+  if (k > nfull) return;
+  uint32_t v = 0;
+  if (k < nfull) {
+    const uint4* p = reinterpret_cast<const uint4*>(data + k * CRC_SLICE_BYTES);
+    for (uint32_t q = 0; q < CRC_SLICE_BYTES / 16; q++) {
+      const uint4 w = __ldg(p + q);
+      const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        v ^= ws[e];  // four bytes at once into the low end of the register, then four table steps
+#pragma unroll
+        for (int b = 0; b < 4; b++) v = tab[v & 0xFFu] ^ (v >> 8);
+      }
+    }
+  } else {
+    for (u64 q = nfull * CRC_SLICE_BYTES; q < total; q++) v = tab[(v ^ data[q]) & 0xFFu] ^ (v >> 8);
+  }
+  raw[k] = v;
+}
+
+// the nfull slice registers folded in order into one: thread t folds slices [t q - pad, (t + 1) q - pad) (q = slices per
+// thread, the slices before the first are zeros and change nothing), then the 1024 runs are joined pairwise.
+// xs = x^(8 * 4096), xq = x^(8 * 4096 * q).
+__global__ void __launch_bounds__(CRCB_THREADS) gz_crc_fold_kernel(const uint32_t* __restrict__ raw, u64 nfull, uint32_t q, uint32_t xs, uint32_t xq,
+                                                                   uint32_t* out) {
+  __shared__ uint32_t part[CRCB_THREADS];
+  const int tid = threadIdx.x;
+  const u64 pad = (u64)CRCB_THREADS * q - nfull;
+  uint32_t v = 0;
+  for (uint32_t j = 0; j < q; j++) {
+    const u64 virt = (u64)tid * q + j;
+    if (virt >= pad) v = gf_mul(xs, v) ^ raw[virt - pad];
+  }
+  part[tid] = v;
+  uint32_t op = xq;  // x^(8 * bytes of the right-hand run)
+  for (int d = 1; d < CRCB_THREADS; d <<= 1) {
+    __syncthreads();
+    uint32_t joined = 0;
+    const bool mine = (tid & (2 * d - 1)) == 0;
+    if (mine) joined = gf_mul(op, part[tid]) ^ part[tid + d];
+    __syncthreads();
+    if (mine) part[tid] = joined;
+    op = gf_mul(op, op);
+  }
+  if (tid == 0) { out[0] = part[0]; out[1] = raw[nfull]; }
 }
 
 // ---- launchers ---------------------------------------------------------------------------------------------------------------
@@ -517,12 +628,16 @@ cudaError_t launch_gz_windows(const unsigned long long* coff, uint32_t nchain, c
                               cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gz_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)GZ_WINDOW);
+    cudaError_t e = cudaFuncSetAttribute(gz_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN_SMEM);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  gz_window_kernel<<<1, WIN_THREADS, 2 * GZ_WINDOW, st>>>(coff, nchain, markers, wbuf, window);
-  return cudaGetLastError();
+  if (nchain == 0) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemcpyAsync(wbuf, window, GZ_WINDOW, cudaMemcpyDeviceToDevice, st);  // row 0: the window before the batch
+  if (e != cudaSuccess) return e;
+  gz_window_kernel<<<1, WIN_THREADS, WIN_SMEM, st>>>(coff, nchain, markers, wbuf);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  return cudaMemcpyAsync(window, wbuf + (size_t)nchain * GZ_WINDOW, GZ_WINDOW, cudaMemcpyDeviceToDevice, st);  // the window behind the batch
 }
 cudaError_t launch_gz_resolve(const uint16_t* markers, const uint8_t* wbuf, const unsigned long long* coff, uint32_t nchain,
                               unsigned long long total_out, uint8_t* out, int sms, cudaStream_t st) {
@@ -530,6 +645,14 @@ cudaError_t launch_gz_resolve(const uint16_t* markers, const uint8_t* wbuf, cons
   const u64 want = (total_out / 8 + RES_THREADS - 1) / RES_THREADS;
   const int grid = (int)(want < (u64)sms * 8 ? (want ? want : 1) : (u64)sms * 8);
   gz_resolve_kernel<<<grid, RES_THREADS, 0, st>>>(markers, wbuf, coff, nchain, total_out, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gz_crc(const uint8_t* d_out, unsigned long long total, uint32_t* d_raw, uint32_t xs, uint32_t xq, uint32_t q, uint32_t* d_crc2,
+                          cudaStream_t st) {
+  const u64 nfull = total / CRC_SLICE_BYTES;
+  gz_crc_slices_kernel<<<(unsigned)((nfull + 1 + CRCA_THREADS - 1) / CRCA_THREADS), CRCA_THREADS, 0, st>>>(d_out, total, d_raw);
+  gz_crc_fold_kernel<<<1, CRCB_THREADS, 0, st>>>(d_raw, nfull, q, xs, xq, d_crc2);
   return cudaGetLastError();
 }
 

@@ -51,9 +51,17 @@ cudaError_t launch_gz_chain(GzChunk* chunks, int nchunks, unsigned long long pri
                             unsigned long long* coff, cudaStream_t st);
 cudaError_t launch_gz_write(const uint8_t* d_comp, size_t nbytes, uint32_t chunk_bytes, GzChunk* chunks, int nchunks, uint16_t* markers,
                             const uint8_t* window, uint32_t wvalid, uint32_t* err, cudaStream_t st);
+// wbuf: (nchain + 1) rows of 32 KiB
 cudaError_t launch_gz_windows(const unsigned long long* coff, uint32_t nchain, const uint16_t* markers, uint8_t* wbuf, uint8_t* window,
                               cudaStream_t st);
 cudaError_t launch_gz_resolve(const uint16_t* markers, const uint8_t* wbuf, const unsigned long long* coff, uint32_t nchain,
                               unsigned long long total_out, uint8_t* out, int sms, cudaStream_t st);
+
+// CRC-32 pieces of the batch's output: d_crc2[0] = the register (from zero) over the full 4 KiB slices, d_crc2[1] = over
+// the bytes behind them.  d_raw: total / 4096 + 1 words; xs = x^(8 * 4096), xq = x^(8 * 4096 * q) modulo the CRC
+// polynomial, q = ceil(slices / 1024).
+constexpr uint32_t GZ_CRC_SLICE = 4096;
+cudaError_t launch_gz_crc(const uint8_t* d_out, unsigned long long total, uint32_t* d_raw, uint32_t xs, uint32_t xq, uint32_t q, uint32_t* d_crc2,
+                          cudaStream_t st);
 
 }  // namespace fq

@@ -75,6 +75,7 @@ void fqgpu_destroy(fqgpu_ctx* ctx) {
   if (ctx->h_gzres) cudaFreeHost(ctx->h_gzres);
   cudaFree(ctx->d_gzsym);
   cudaFree(ctx->d_gzwbuf);
+  cudaFree(ctx->d_gzraw);
   cudaFree(ctx->d_gzwindow);
   if (ctx->h_out) cudaFreeHost(ctx->h_out);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -621,6 +622,25 @@ static size_t gzip_payload_offset(int fd, size_t off, size_t fsize) {
   return p + 8 < fsize ? p : 0;
 }
 
+// CRC-32 arithmetic for joining the pieces the device computes (fq_gzip.cu, step 7): polynomials over GF(2) modulo
+// the CRC polynomial, bit 31 = the coefficient of x^0.
+static uint32_t crc_mul(uint32_t a, uint32_t b) {
+  uint32_t p = 0;
+  for (int i = 0; i < 32; i++) {
+    if (a & (0x80000000u >> i)) p ^= b;
+    b = (b >> 1) ^ ((b & 1u) ? 0xEDB88320u : 0u);
+  }
+  return p;
+}
+static uint32_t crc_xpow8(u64 nbytes) {  // x^(8 nbytes)
+  uint32_t r = 0x80000000u, sq = 0x00800000u;  // 1, x^8
+  for (u64 n = nbytes; n; n >>= 1) {
+    if (n & 1) r = crc_mul(sq, r);
+    sq = crc_mul(sq, sq);
+  }
+  return r;
+}
+
 static int count_gzip(fqgpu_ctx* ctx, const char* path) {
   const int fd = open(path, O_RDONLY);
   if (fd < 0) return 1;
@@ -659,6 +679,7 @@ static int count_gzip(fqgpu_ctx* ctx, const char* path) {
 
   u64 abs_bit = (u64)payload * 8ull;  // the next block's first bit, in the file
   u64 prior_out = 0;                  // bytes of this member already inflated
+  uint32_t crc_reg = 0xFFFFFFFFu;     // the member's CRC-32 register so far
   for (;;) {
     const size_t fpos = (size_t)(abs_bit >> 3) & ~(size_t)4095;
     const size_t want_now = fsize - fpos < ctx->comp_cap ? fsize - fpos : ctx->comp_cap;
@@ -715,30 +736,43 @@ static int count_gzip(fqgpu_ctx* ctx, const char* path) {
       CU_B(fq::launch_gz_write(ctx->d_comp, got, (uint32_t)chunk_bytes, chunks, nchunks, ctx->d_gzsym, ctx->d_gzwindow, wvalid, d_err, ctx->stream));
       CU_B(fq::launch_gz_windows(ctx->d_gzcoff, res.nchain, ctx->d_gzsym, ctx->d_gzwbuf, ctx->d_gzwindow, ctx->stream));
       CU_B(fq::launch_gz_resolve(ctx->d_gzsym, ctx->d_gzwbuf, ctx->d_gzcoff, res.nchain, total, ctx->d_inflated, ctx->grid / 2, ctx->stream));
-      CU_B(cudaMemcpyAsync((uint8_t*)ctx->h_gzres + sizeof(fq::GzResult), d_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
-      ctx->launches += 3;
+      const u64 nslices = total / fq::GZ_CRC_SLICE;
+      const uint32_t q = (uint32_t)((nslices + 1023) / 1024);
+      if (ctx->gzraw_cap < nslices + 1) {
+        cudaFree(ctx->d_gzraw);
+        ctx->d_gzraw = nullptr; ctx->gzraw_cap = 0;
+        CU_B(cudaMalloc(&ctx->d_gzraw, (nslices + 1 + (nslices >> 3)) * sizeof(uint32_t)));
+        ctx->gzraw_cap = nslices + 1 + (nslices >> 3);
+      }
+      CU_B(fq::launch_gz_crc(ctx->d_inflated, total, ctx->d_gzraw, crc_xpow8(fq::GZ_CRC_SLICE), crc_xpow8((u64)fq::GZ_CRC_SLICE * q), q, d_err + 2, ctx->stream));
+      CU_B(cudaMemcpyAsync((uint8_t*)ctx->h_gzres + sizeof(fq::GzResult), d_err, 16, cudaMemcpyDeviceToHost, ctx->stream));
+      ctx->launches += 6;
       const int rc = fqgpu_scan_device(ctx, ctx->d_inflated, (size_t)total);
       if (rc != FQGPU_OK) return bail(rc);
       CU_B(cudaStreamSynchronize(ctx->stream));  // the batch buffers are reused
       if (*h_err) return bail(1);
+      // the register over this batch's bytes (full slices, then the tail), behind the bytes before it
+      const uint32_t batch_reg = crc_mul(crc_xpow8(total % fq::GZ_CRC_SLICE), h_err[2]) ^ h_err[3];
+      crc_reg = crc_mul(crc_xpow8(total), crc_reg) ^ batch_reg;
     }
     ctx->gzip_chunks += res.nchain;
     ctx->gzip_passed += res.passed;
     prior_out += total;
     abs_bit = (u64)fpos * 8ull + res.end_bit;
     if (!res.final_block) continue;
-    // the member's trailer: CRC-32 and ISIZE.  ISIZE is checked; the CRC is not recomputed (gzread hands the bytes out
-    // before it looks at the trailer, so the reference's counts do not depend on it either)
+    // the member's trailer: CRC-32 and ISIZE, both checked like gzread does
     const size_t tpos = (size_t)((abs_bit + 7) >> 3);
     uint8_t tr[8];
     if (tpos + 8 > fsize || pread(fd, tr, 8, (off_t)tpos) != 8) return bail(1);
     const uint32_t isize = (uint32_t)tr[4] | ((uint32_t)tr[5] << 8) | ((uint32_t)tr[6] << 16) | ((uint32_t)tr[7] << 24);
-    if (isize != (uint32_t)prior_out) return bail(1);
+    const uint32_t crc = (uint32_t)tr[0] | ((uint32_t)tr[1] << 8) | ((uint32_t)tr[2] << 16) | ((uint32_t)tr[3] << 24);
+    if (isize != (uint32_t)prior_out || crc != (crc_reg ^ 0xFFFFFFFFu)) return bail(1);
     // another member behind it (`cat a.gz b.gz`) continues the stream; anything else is ignored, as gzread does
     payload = gzip_payload_offset(fd, tpos + 8, fsize);
     if (!payload) break;
     abs_bit = (u64)payload * 8ull;
     prior_out = 0;
+    crc_reg = 0xFFFFFFFFu;
   }
 #undef CU_B
   close(fd);

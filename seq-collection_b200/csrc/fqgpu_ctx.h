@@ -100,6 +100,8 @@ struct fqgpu_ctx {
   size_t gzsym_cap = 0;        // symbols
   uint8_t* d_gzwbuf = nullptr;
   size_t gzwbuf_cap = 0;       // rows of 32 KiB
+  uint32_t* d_gzraw = nullptr;   // CRC-32 registers of the output's 4 KiB slices
+  size_t gzraw_cap = 0;
   uint8_t* d_gzwindow = nullptr;
   u64 gzip_chunks = 0;         // chunks of single-member gzip inflated on the device since the last reset (diagnostics)
   u64 gzip_passed = 0;         // block starts the search found that turned out not to be block boundaries
