@@ -23,10 +23,11 @@
 //   4. gz_write_kernel  the chain's chunks decode again, now writing 16-bit symbols: a byte, or -- for a match
 //                       that reaches behind the chunk's first byte -- a MARKER holding the position in the
 //                       32 KiB window before the chunk.  Matches copy symbols, so markers propagate.
-//   5. gz_window_kernel one CTA walks the chain in order and turns "window before chunk i" into "window before
-//                       chunk i+1" (the only serial step: 32 KiB per chunk, in shared memory, fed by TMA).
-//   6. gz_resolve_kernel every marker is replaced through its chunk's window; bytes go to the buffer
-//                       fqgpu_scan_device reads.
+//   5. gz_rows_kernel   "the 32 KiB before chunk i+1" from "the 32 KiB before chunk i" is a serial recurrence; windows of
+//                       symbols compose, so groups of chunks are walked in parallel relative to their own first
+//                       window and only the groups are walked in series (shared memory, fed by TMA).
+//   6. gz_resolve_kernel every marker is replaced through its chunk's window and its group's; bytes go to the
+//                       buffer fqgpu_scan_device reads.
 //   7. gz_crc_*         the CRC-32 of those bytes, which the host compares with the member's trailer like gzread.
 //
 // The decoder (fq_inflate.cuh) is the BGZF path's: a warp per stream in lockstep, lookup tables in shared memory,
@@ -34,6 +35,8 @@
 // file -- makes the caller fall back to gzread, so results and error behaviour stay the reference's.
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <type_traits>
 
 #include "fq_dev.cuh"
 #include "fq_gzip.h"
@@ -128,6 +131,10 @@ __device__ bool gz_header_plausible(const uint32_t* words, const uint32_t* wend,
 __global__ void __launch_bounds__(32 * GZ_WARPS) gz_sync_kernel(const uint32_t* __restrict__ words, u64 nbytes, uint32_t chunk_bytes,
                                                                 int nchunks, u64 start_bit, GzChunk* __restrict__ chunks, uint32_t* nfound) {
   __shared__ WarpTables tables[GZ_WARPS];
+  __shared__ uint8_t kraft3[512];  // three 3-bit code lengths -> their Kraft terms (2^(7 - len), 0 for an unused symbol)
+  for (int x = threadIdx.x; x < 512; x += 32 * GZ_WARPS)
+    kraft3[x] = (uint8_t)(((128u >> (x & 7)) & 127u) + ((128u >> ((x >> 3) & 7)) & 127u) + ((128u >> (x >> 6)) & 127u));
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x * GZ_WARPS + warp;
   if (c >= nchunks) return;
@@ -141,19 +148,22 @@ __global__ void __launch_bounds__(32 * GZ_WARPS) gz_sync_kernel(const uint32_t* 
     if (lo <= start_bit) lo = start_bit + 1;
     const u64 last = end_bits > 96 ? end_bits - 96 : 0;  // a block header and an end-of-block do not fit behind this
     if (hi > last) hi = last;
-    for (u64 t0 = lo & ~31ull; t0 < hi; t0 += 32) {
-      const uint32_t* p = words + (t0 >> 5);
-      const uint32_t w0 = __ldg(p), w1 = p + 1 < wend ? __ldg(p + 1) : 0u, w2 = p + 2 < wend ? __ldg(p + 2) : 0u,
-                     w3 = p + 3 < wend ? __ldg(p + 3) : 0u;
+    const uint32_t* p = words + (lo >> 5);
+    uint32_t w0 = p < wend ? __ldg(p) : 0u, w1 = p + 1 < wend ? __ldg(p + 1) : 0u, w2 = p + 2 < wend ? __ldg(p + 2) : 0u,
+             w3 = p + 3 < wend ? __ldg(p + 3) : 0u;
+    for (u64 t0 = lo & ~31ull; t0 < hi; t0 += 32, p++) {
+      const uint32_t w4 = p + 4 < wend ? __ldg(p + 4) : 0u;  // (for the next round)
       const uint32_t a = __funnelshift_r(w0, w1, lane), bq = __funnelshift_r(w1, w2, lane), cq = __funnelshift_r(w2, w3, lane);
+      w0 = w1; w1 = w2; w2 = w3; w3 = w4;
       const u64 t = t0 + (u64)lane;
       // BFINAL = 0, BTYPE = 2 (bits 1-2, LSB first), HLIT <= 29, HDIST <= 29
       bool ok = (a & 7u) == 4u && ((a >> 3) & 31u) <= 29u && ((a >> 8) & 31u) <= 29u && t >= lo && t < hi;
-      if (ok) {  // the (HCLEN + 4) code lengths of 3 bits from bit 17: Kraft sum of a complete code = 128
+      if (ok) {  // the (HCLEN + 4) code lengths of 3 bits from bit 17, three at a time: the Kraft sum of a complete code is 128
         const int ncode = (int)((a >> 13) & 15u) + 4;
-        u64 pre = ((((u64)bq << 32) | a) >> 17) | ((u64)cq << 47);
+        u64 pre = (((((u64)bq << 32) | a) >> 17) | ((u64)cq << 47)) & ((1ull << (3 * ncode)) - 1ull);
         uint32_t kraft = 0;
-        for (int k = 0; k < ncode; k++) { kraft += (128u >> (pre & 7u)) & 127u; pre >>= 3; }
+#pragma unroll
+        for (int k = 0; k < 7; k++) { kraft += kraft3[(uint32_t)pre & 511u]; pre >>= 9; }
         ok = kraft == 128u;
       }
       uint32_t m = __ballot_sync(0xffffffffu, ok);
@@ -417,80 +427,137 @@ __global__ void __launch_bounds__(CHAIN_THREADS) gz_chain_kernel(GzChunk* chunks
 }
 
 // ---- 5. windows ----------------------------------------------------------------------------------------------------------
-// Row i of wbuf is the 32 KiB before chain chunk i; row i+1 is the tail of (row i) ++ (chunk i's symbols resolved
-// through row i).  This is the one serial step of the whole scheme -- in FASTQ a fifth of a chunk's last symbols
-// are still markers (every header is a match on the header before it, back to the chunk's first record) -- so one
-// CTA walks the chain with everything it touches in shared memory: the symbols of the next two chunks' tails
-// arrive by bulk copies (TMA) while the current one is resolved, rows leave by bulk stores.
+// The 32 KiB before chain chunk i+1 are the tail of (the 32 KiB before chunk i) ++ (chunk i's symbols resolved through
+// those).  That recurrence is the one serial step of the whole scheme, and it does not thin out: in FASTQ a fifth of a
+// chunk's last symbols are still markers (every header is a match on the header before it, back to the chunk's first
+// record).  But a window whose entries are "a byte, or a position in some earlier window" composes: the chain is cut
+// into GROUPS of K chunks, and
+//   gz_rows_kernel<true>   one CTA per group, all groups at once, walks its K chunks starting from the identity window
+//                          (entry j = "position j of the window before the group"): symrows[i] = the window before
+//                          chunk i as 16-bit symbols relative to the group's window; grows[g] = the same for the window
+//                          behind the group;
+//   gz_rows_kernel<false>  one CTA walks the GROUPS: trows[g + 1] = grows[g] resolved through trows[g], in bytes.
+// K steps in parallel plus nchain / K steps in series instead of nchain.  One step, for either kernel: the row before in
+// shared memory, the symbols arriving by bulk copies (TMA) in halves of 16 Ki while the half before is resolved, the new
+// row leaving by a bulk store.
 constexpr int WIN_THREADS = 1024;
-constexpr uint32_t WIN_SYM_SLOTS = GZ_WINDOW + 16;  // symbols per staging buffer (the tail, from a 16-byte boundary)
-constexpr size_t WIN_SMEM = 2 * GZ_WINDOW + 2 * WIN_SYM_SLOTS * sizeof(uint16_t) + 16;
-__global__ void __launch_bounds__(WIN_THREADS) gz_window_kernel(const u64* __restrict__ coff, uint32_t nchain, const uint16_t* __restrict__ markers,
-                                                                uint8_t* __restrict__ wbuf) {
+constexpr uint32_t WIN_HALF = GZ_WINDOW / 2;
+constexpr uint32_t WIN_STAGE = WIN_HALF + 16;  // symbols per staging buffer (half a window, from a 16-byte boundary)
+template <typename T>
+constexpr size_t win_smem_bytes() { return 2 * GZ_WINDOW * sizeof(T) + 2 * WIN_STAGE * sizeof(uint16_t) + 16; }
+
+// SYMBOLIC: CTA g walks chain chunks [g K, min((g + 1) K, nchain)); its symbols are the chunks' tails in `markers`.
+// otherwise: one CTA walks the groups; the symbols of step g are the row grows[g].
+template <bool SYMBOLIC>
+__global__ void __launch_bounds__(WIN_THREADS) gz_rows_kernel(const u64* __restrict__ coff, uint32_t nchain, uint32_t K, uint32_t ngroups,
+                                                              const uint16_t* __restrict__ markers, uint16_t* __restrict__ symrows,
+                                                              uint16_t* __restrict__ grows, uint8_t* __restrict__ trows) {
+  typedef typename std::conditional<SYMBOLIC, uint16_t, uint8_t>::type T;
   extern __shared__ __align__(128) uint8_t win_smem[];
-  uint8_t* row_s = win_smem;                                                     // 2 rows
-  uint16_t* sym_s = reinterpret_cast<uint16_t*>(win_smem + 2 * GZ_WINDOW);       // 2 staging buffers
-  const uint32_t bar_s = smem_u32(win_smem + 2 * GZ_WINDOW + 2 * WIN_SYM_SLOTS * sizeof(uint16_t));
+  T* row_s = reinterpret_cast<T*>(win_smem);                                                   // 2 rows
+  uint16_t* stage_s = reinterpret_cast<uint16_t*>(win_smem + 2 * GZ_WINDOW * sizeof(T));     // 2 staging buffers
+  const uint32_t bar_s = smem_u32(win_smem + 2 * GZ_WINDOW * sizeof(T) + 2 * WIN_STAGE * sizeof(uint16_t));
   const int tid = threadIdx.x;
-  // the symbols of chunk i's tail: output positions [max(off, end - 32768), end), fetched from the 16-byte boundary below
-  auto fetch = [&](uint32_t i) {
-    const u64 off = coff[i], end = coff[i + 1];
-    const u64 lo = end - off > GZ_WINDOW ? end - GZ_WINDOW : off;
-    const u64 a = lo & ~7ull;
-    uint32_t bytes = (uint32_t)(((end - a) * 2 + 15) & ~15ull);
-    if (bytes == 0) bytes = 16;  // (an empty chunk on a 16-byte boundary: every step has its copy, the phases stay in step)
-    mbar_expect_tx(bar_s + 8u * (i & 1u), bytes);
-    tma_load_1d(smem_u32(sym_s + (size_t)(i & 1u) * WIN_SYM_SLOTS), markers + a, bytes, bar_s + 8u * (i & 1u));
+  const uint32_t first = SYMBOLIC ? blockIdx.x * K : 0u;
+  const uint32_t nsteps = SYMBOLIC ? (first + K <= nchain ? K : nchain - first) : ngroups;
+
+  // step k, half h: the symbols of window positions [h * 16Ki, (h + 1) * 16Ki) that come from the step's own output
+  // (the others are still inside the row before).  `off`, `end` = the output range of the step's chunk.
+  auto src_of = [&](uint32_t k, u64 off, u64 end, uint32_t h, u64& lo, uint32_t& keep) -> const uint16_t* {
+    const u64 len = end - off;
+    keep = len >= GZ_WINDOW ? 0u : GZ_WINDOW - (uint32_t)len;  // positions of the new window still inside the old one
+    const uint32_t j0 = keep > h * WIN_HALF ? keep : h * WIN_HALF;  // the half's first position that is a symbol of this step
+    lo = end - GZ_WINDOW + j0;                                      // ... and that symbol's index
+    return SYMBOLIC ? markers : grows + (size_t)k * GZ_WINDOW;
   };
-  for (int j = tid; j < (int)GZ_WINDOW / 16; j += WIN_THREADS)
-    reinterpret_cast<uint4*>(row_s)[j] = reinterpret_cast<const uint4*>(wbuf)[j];  // row 0: the window before the batch
+  auto fetch = [&](uint32_t hs, u64 off, u64 end) {  // half-step hs = 2 k + h
+    u64 lo; uint32_t keep;
+    const uint32_t k = hs >> 1, h = hs & 1u;
+    const uint16_t* src = src_of(k, off, end, h, lo, keep);
+    const u64 a = lo & ~7ull;
+    const bool any = (keep > h * WIN_HALF ? keep : h * WIN_HALF) < (h + 1) * WIN_HALF;  // does any position of this half come from the step?
+    const u64 hi = any ? end - GZ_WINDOW + (u64)(h + 1) * WIN_HALF : 0;                 // (one past the half's last symbol)
+    // nothing from the step: a dummy copy all the same, so that every half-step has one and the phases stay in step
+    const uint32_t bytes = any ? (uint32_t)(((hi - a) * 2 + 15) & ~15ull) : 16u;
+    mbar_expect_tx(bar_s + 8u * (hs & 1u), bytes);
+    tma_load_1d(smem_u32(stage_s + (size_t)(hs & 1u) * WIN_STAGE), src + (any ? a : 0), bytes, bar_s + 8u * (hs & 1u));
+  };
+  // the output range of step k: a chunk of the chain, or (group walk) a whole row that replaces the window
+  auto range_of = [&](uint32_t k, u64& off, u64& end) {
+    if (SYMBOLIC) { off = coff[first + k]; end = coff[first + k + 1]; }
+    else { off = 0; end = GZ_WINDOW; }
+  };
+
+  if (SYMBOLIC) {
+    for (uint32_t j = (uint32_t)tid; j < GZ_WINDOW; j += WIN_THREADS) row_s[j] = (T)(0x8000u | j);  // the identity window
+  } else {
+    for (int j = tid; j < (int)GZ_WINDOW / 16; j += WIN_THREADS)
+      reinterpret_cast<uint4*>(row_s)[j] = reinterpret_cast<const uint4*>(trows)[j];  // row 0: the window before the batch
+  }
   if (tid == 0) {
     mbar_init(bar_s, 1);
     mbar_init(bar_s + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (tid == 0) { fetch(0); if (nchain > 1) fetch(1); }
-  for (uint32_t i = 0; i < nchain; i++) {
-    const u64 off = coff[i], end = coff[i + 1];
-    const u64 len = end - off;
-    const u64 lo = len > GZ_WINDOW ? end - GZ_WINDOW : off;
-    const uint8_t* prev = row_s + (size_t)(i & 1u) * GZ_WINDOW;
-    uint8_t* cur = row_s + (size_t)((i + 1) & 1u) * GZ_WINDOW;
-    const uint16_t* sy = sym_s + (size_t)(i & 1u) * WIN_SYM_SLOTS + (lo & 7ull);  // sy[k] = the symbol at output position lo + k
-    mbar_wait(bar_s + 8u * (i & 1u), (i >> 1) & 1u);
-    const uint32_t keep = len >= GZ_WINDOW ? 0u : GZ_WINDOW - (uint32_t)len;  // positions of the new window still inside the old one
-#pragma unroll 8
-    for (int r = 0; r < (int)GZ_WINDOW / WIN_THREADS; r++) {
-      const uint32_t j = (uint32_t)tid + (uint32_t)r * WIN_THREADS;  // position j of the new window is output byte end - 32768 + j
-      uint32_t v;
-      if (j >= keep) {
-        const uint32_t s2 = sy[j - keep];
-        v = s2 < 256u ? s2 : prev[s2 & 0x7FFFu];
-      } else {
-        v = prev[j + (uint32_t)len];
+  if (nsteps == 0) return;
+  u64 off, end, off1 = 0, end1 = 0;  // this step's range and the next one's
+  range_of(0, off, end);
+  if (nsteps > 1) range_of(1, off1, end1);
+  if (tid == 0) { fetch(0, off, end); fetch(1, off, end); }
+  for (uint32_t k = 0; k < nsteps; k++) {
+    u64 off2 = 0, end2 = 0;
+    if (k + 2 < nsteps) range_of(k + 2, off2, end2);  // (two steps ahead: nothing in this step waits for it)
+    const T* prev = row_s + (size_t)(k & 1u) * GZ_WINDOW;
+    T* cur = row_s + (size_t)((k + 1) & 1u) * GZ_WINDOW;
+    for (uint32_t h = 0; h < 2; h++) {
+      const uint32_t hs = 2 * k + h;
+      u64 lo; uint32_t keep;
+      src_of(k, off, end, h, lo, keep);
+      const uint16_t* sy = stage_s + (size_t)(hs & 1u) * WIN_STAGE + (lo & 7ull);  // sy[q] = symbol lo + q
+      const uint32_t j0 = keep > h * WIN_HALF ? keep : h * WIN_HALF;
+      mbar_wait(bar_s + 8u * (hs & 1u), (hs >> 1) & 1u);
+      // position j of the new window: a symbol of this step, or -- in front of a chunk shorter than the window -- position
+      // j + len of the old window, which reads like a marker
+      uint32_t s2[WIN_HALF / WIN_THREADS];
+#pragma unroll
+      for (int r = 0; r < (int)(WIN_HALF / WIN_THREADS); r++) {
+        const uint32_t j = h * WIN_HALF + (uint32_t)tid + (uint32_t)r * WIN_THREADS;
+        s2[r] = j >= keep ? (uint32_t)sy[j - j0] : 0x8000u | (j + (GZ_WINDOW - keep));
       }
-      cur[j] = (uint8_t)v;
+#pragma unroll
+      for (int r = 0; r < (int)(WIN_HALF / WIN_THREADS); r++)
+        if (s2[r] >= 256u) s2[r] = prev[s2[r] & 0x7FFFu];
+#pragma unroll
+      for (int r = 0; r < (int)(WIN_HALF / WIN_THREADS); r++) cur[h * WIN_HALF + (uint32_t)tid + (uint32_t)r * WIN_THREADS] = (T)s2[r];
+      if (h == 1 && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the row stored a step ago has left shared memory
+      __syncthreads();
+      if (tid == 0) {
+        if (h == 1) {  // the row is complete: out it goes
+          void* dst;  // the window before the next chunk of the group / behind the group / before the next group
+          if (SYMBOLIC) dst = k + 1 < nsteps ? symrows + (size_t)(first + k + 1) * GZ_WINDOW : grows + (size_t)blockIdx.x * GZ_WINDOW;
+          else dst = trows + (size_t)(k + 1) * GZ_WINDOW;
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(cur)),
+                       "r"((uint32_t)(GZ_WINDOW * sizeof(T))) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        // the staging buffer just read is free: the half-step after the next one goes there
+        if (k + 1 < nsteps) fetch(hs + 2, off1, end1);
+      }
     }
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the row stored a step ago has left shared memory
-    __syncthreads();
-    if (tid == 0) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(wbuf + (size_t)(i + 1) * GZ_WINDOW), "r"(smem_u32(cur)),
-                   "r"(GZ_WINDOW) : "memory");
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      if (i + 2 < nchain) fetch(i + 2);
-    }
+    off = off1; end = end1; off1 = off2; end1 = end2;
   }
   if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ---- 6. resolve ------------------------------------------------------------------------------------------------------------
 constexpr int RES_THREADS = 256;
-__global__ void __launch_bounds__(RES_THREADS) gz_resolve_kernel(const uint16_t* __restrict__ markers, const uint8_t* __restrict__ wbuf,
-                                                                 const u64* __restrict__ coff, uint32_t nchain, u64 total, uint8_t* __restrict__ out) {
-  const u64 ngroups = (total + 7) / 8;
-  for (u64 g = (u64)blockIdx.x * RES_THREADS + threadIdx.x; g < ngroups; g += (u64)gridDim.x * RES_THREADS) {
+__global__ void __launch_bounds__(RES_THREADS) gz_resolve_kernel(const uint16_t* __restrict__ markers, const uint16_t* __restrict__ symrows,
+                                                                 const uint8_t* __restrict__ trows, uint32_t K, const u64* __restrict__ coff,
+                                                                 uint32_t nchain, u64 total, uint8_t* __restrict__ out) {
+  const u64 ngroups8 = (total + 7) / 8;
+  for (u64 g = (u64)blockIdx.x * RES_THREADS + threadIdx.x; g < ngroups8; g += (u64)gridDim.x * RES_THREADS) {
     const u64 p0 = g * 8;
     uint32_t lo = 0, hi = nchain;  // the chain chunk holding p0: the last i with coff[i] <= p0
     while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (coff[mid] <= p0) lo = mid; else hi = mid; }
@@ -504,7 +571,11 @@ __global__ void __launch_bounds__(RES_THREADS) gz_resolve_kernel(const uint16_t*
       const u64 p = p0 + (u64)k;
       while (p >= next && i + 1 < nchain) { i++; next = coff[i + 1]; }
       uint32_t v = s[k];
-      if (v >= 256u) v = p < total ? wbuf[(size_t)i * GZ_WINDOW + (v & 0x7FFFu)] : 0u;
+      if (v >= 256u && p < total) {
+        // through the chunk's window relative to its group's, then through the group's window
+        if (i % K) v = symrows[(size_t)i * GZ_WINDOW + (v & 0x7FFFu)];
+        if (v >= 256u) v = trows[(size_t)(i / K) * GZ_WINDOW + (v & 0x7FFFu)];
+      }
       packed |= (u64)(v & 0xFFu) << (8 * k);
     }
     *reinterpret_cast<u64*>(out + p0) = packed;  // (padded likewise)
@@ -624,30 +695,36 @@ cudaError_t launch_gz_write(const uint8_t* d_comp, size_t nbytes, uint32_t chunk
                                                                                  (u64)chunk_bytes * 8ull, chunks, nchunks, markers, window, wvalid, err);
   return cudaGetLastError();
 }
-cudaError_t launch_gz_windows(const unsigned long long* coff, uint32_t nchain, const uint16_t* markers, uint8_t* wbuf, uint8_t* window,
-                              cudaStream_t st) {
+uint32_t gz_group_chunks(uint32_t nchain, int sms) {
+  const uint32_t k = (nchain + (uint32_t)sms - 1) / (uint32_t)sms;
+  return k < 8 ? 8 : k;
+}
+cudaError_t launch_gz_windows(const unsigned long long* coff, uint32_t nchain, uint32_t K, const uint16_t* markers, uint16_t* symrows,
+                              uint16_t* grows, uint8_t* trows, uint8_t* window, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gz_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIN_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gz_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem_bytes<uint16_t>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gz_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem_bytes<uint8_t>());
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  if (nchain == 0) return cudaErrorInvalidValue;
-  cudaError_t e = cudaMemcpyAsync(wbuf, window, GZ_WINDOW, cudaMemcpyDeviceToDevice, st);  // row 0: the window before the batch
+  if (nchain == 0 || K == 0) return cudaErrorInvalidValue;
+  const uint32_t ngroups = (nchain + K - 1) / K;
+  cudaError_t e = cudaMemcpyAsync(trows, window, GZ_WINDOW, cudaMemcpyDeviceToDevice, st);  // row 0: the window before the batch
   if (e != cudaSuccess) return e;
-  gz_window_kernel<<<1, WIN_THREADS, WIN_SMEM, st>>>(coff, nchain, markers, wbuf);
+  gz_rows_kernel<true><<<ngroups, WIN_THREADS, win_smem_bytes<uint16_t>(), st>>>(coff, nchain, K, ngroups, markers, symrows, grows, trows);
+  gz_rows_kernel<false><<<1, WIN_THREADS, win_smem_bytes<uint8_t>(), st>>>(coff, nchain, K, ngroups, markers, symrows, grows, trows);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  return cudaMemcpyAsync(window, wbuf + (size_t)nchain * GZ_WINDOW, GZ_WINDOW, cudaMemcpyDeviceToDevice, st);  // the window behind the batch
+  return cudaMemcpyAsync(window, trows + (size_t)ngroups * GZ_WINDOW, GZ_WINDOW, cudaMemcpyDeviceToDevice, st);  // the window behind the batch
 }
-cudaError_t launch_gz_resolve(const uint16_t* markers, const uint8_t* wbuf, const unsigned long long* coff, uint32_t nchain,
-                              unsigned long long total_out, uint8_t* out, int sms, cudaStream_t st) {
+cudaError_t launch_gz_resolve(const uint16_t* markers, const uint16_t* symrows, const uint8_t* trows, uint32_t K, const unsigned long long* coff,
+                              uint32_t nchain, unsigned long long total_out, uint8_t* out, int sms, cudaStream_t st) {
   if (total_out == 0) return cudaSuccess;
   const u64 want = (total_out / 8 + RES_THREADS - 1) / RES_THREADS;
   const int grid = (int)(want < (u64)sms * 8 ? (want ? want : 1) : (u64)sms * 8);
-  gz_resolve_kernel<<<grid, RES_THREADS, 0, st>>>(markers, wbuf, coff, nchain, total_out, out);
+  gz_resolve_kernel<<<grid, RES_THREADS, 0, st>>>(markers, symrows, trows, K, coff, nchain, total_out, out);
   return cudaGetLastError();
 }
-
 cudaError_t launch_gz_crc(const uint8_t* d_out, unsigned long long total, uint32_t* d_raw, uint32_t xs, uint32_t xq, uint32_t q, uint32_t* d_crc2,
                           cudaStream_t st) {
   const u64 nfull = total / CRC_SLICE_BYTES;

@@ -51,11 +51,13 @@ cudaError_t launch_gz_chain(GzChunk* chunks, int nchunks, unsigned long long pri
                             unsigned long long* coff, cudaStream_t st);
 cudaError_t launch_gz_write(const uint8_t* d_comp, size_t nbytes, uint32_t chunk_bytes, GzChunk* chunks, int nchunks, uint16_t* markers,
                             const uint8_t* window, uint32_t wvalid, uint32_t* err, cudaStream_t st);
-// wbuf: (nchain + 1) rows of 32 KiB
-cudaError_t launch_gz_windows(const unsigned long long* coff, uint32_t nchain, const uint16_t* markers, uint8_t* wbuf, uint8_t* window,
-                              cudaStream_t st);
-cudaError_t launch_gz_resolve(const uint16_t* markers, const uint8_t* wbuf, const unsigned long long* coff, uint32_t nchain,
-                              unsigned long long total_out, uint8_t* out, int sms, cudaStream_t st);
+// The windows: K = gz_group_chunks(nchain, SMs) chunks per group, ngroups = ceil(nchain / K).
+// symrows: (nchain + 1) rows of 32768 symbols; grows: ngroups rows of 32768 symbols; trows: (ngroups + 1) rows of 32 KiB.
+uint32_t gz_group_chunks(uint32_t nchain, int sms);
+cudaError_t launch_gz_windows(const unsigned long long* coff, uint32_t nchain, uint32_t K, const uint16_t* markers, uint16_t* symrows,
+                              uint16_t* grows, uint8_t* trows, uint8_t* window, cudaStream_t st);
+cudaError_t launch_gz_resolve(const uint16_t* markers, const uint16_t* symrows, const uint8_t* trows, uint32_t K, const unsigned long long* coff,
+                              uint32_t nchain, unsigned long long total_out, uint8_t* out, int sms, cudaStream_t st);
 
 // CRC-32 pieces of the batch's output: d_crc2[0] = the register (from zero) over the full 4 KiB slices, d_crc2[1] = over
 // the bytes behind them.  d_raw: total / 4096 + 1 words; xs = x^(8 * 4096), xq = x^(8 * 4096 * q) modulo the CRC

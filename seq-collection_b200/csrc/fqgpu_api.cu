@@ -726,16 +726,23 @@ static int count_gzip(fqgpu_ctx* ctx, const char* path) {
         CU_B(cudaMalloc(&ctx->d_inflated, cap));
         ctx->inflated_cap = cap;
       }
-      if (ctx->gzwbuf_cap < (size_t)res.nchain + 1) {
+      const uint32_t K = fq::gz_group_chunks(res.nchain, ctx->grid / 2);
+      const size_t ngroups = ((size_t)res.nchain + K - 1) / K;
+      if (ctx->gzwbuf_cap < (size_t)res.nchain + 1) {  // rows of the window walk
         cudaFree(ctx->d_gzwbuf);
         ctx->d_gzwbuf = nullptr; ctx->gzwbuf_cap = 0;
         const size_t rows = (size_t)res.nchain + 1 + ((size_t)res.nchain >> 2);
-        CU_B(cudaMalloc(&ctx->d_gzwbuf, rows * fq::GZ_WINDOW));
+        // per chunk a row of symbols; per group (at most one per 8 chunks) a row of symbols and a row of bytes
+        CU_B(cudaMalloc(&ctx->d_gzwbuf, rows * fq::GZ_WINDOW * 2 + (rows / 8 + 2) * fq::GZ_WINDOW * 3));
         ctx->gzwbuf_cap = rows;
       }
+      uint16_t* symrows = (uint16_t*)ctx->d_gzwbuf;
+      uint16_t* grows = symrows + ctx->gzwbuf_cap * fq::GZ_WINDOW;
+      uint8_t* trows = (uint8_t*)(grows + (ctx->gzwbuf_cap / 8 + 2) * fq::GZ_WINDOW);
+      (void)ngroups;
       CU_B(fq::launch_gz_write(ctx->d_comp, got, (uint32_t)chunk_bytes, chunks, nchunks, ctx->d_gzsym, ctx->d_gzwindow, wvalid, d_err, ctx->stream));
-      CU_B(fq::launch_gz_windows(ctx->d_gzcoff, res.nchain, ctx->d_gzsym, ctx->d_gzwbuf, ctx->d_gzwindow, ctx->stream));
-      CU_B(fq::launch_gz_resolve(ctx->d_gzsym, ctx->d_gzwbuf, ctx->d_gzcoff, res.nchain, total, ctx->d_inflated, ctx->grid / 2, ctx->stream));
+      CU_B(fq::launch_gz_windows(ctx->d_gzcoff, res.nchain, K, ctx->d_gzsym, symrows, grows, trows, ctx->d_gzwindow, ctx->stream));
+      CU_B(fq::launch_gz_resolve(ctx->d_gzsym, symrows, trows, K, ctx->d_gzcoff, res.nchain, total, ctx->d_inflated, ctx->grid / 2, ctx->stream));
       const u64 nslices = total / fq::GZ_CRC_SLICE;
       const uint32_t q = (uint32_t)((nslices + 1023) / 1024);
       if (ctx->gzraw_cap < nslices + 1) {
@@ -746,7 +753,7 @@ static int count_gzip(fqgpu_ctx* ctx, const char* path) {
       }
       CU_B(fq::launch_gz_crc(ctx->d_inflated, total, ctx->d_gzraw, crc_xpow8(fq::GZ_CRC_SLICE), crc_xpow8((u64)fq::GZ_CRC_SLICE * q), q, d_err + 2, ctx->stream));
       CU_B(cudaMemcpyAsync((uint8_t*)ctx->h_gzres + sizeof(fq::GzResult), d_err, 16, cudaMemcpyDeviceToHost, ctx->stream));
-      ctx->launches += 6;
+      ctx->launches += 7;
       const int rc = fqgpu_scan_device(ctx, ctx->d_inflated, (size_t)total);
       if (rc != FQGPU_OK) return bail(rc);
       CU_B(cudaStreamSynchronize(ctx->stream));  // the batch buffers are reused
