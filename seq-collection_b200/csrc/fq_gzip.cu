@@ -44,6 +44,9 @@
 
 namespace fq {
 
+#ifndef GZ_MINB
+#define GZ_MINB 10  // resident CTAs per SM the decode kernels are compiled for (register cap)
+#endif
 constexpr int GZ_WARPS = 4;        // chunks per CTA
 constexpr int GZ_MAX_PASSED = 6;   // false starts one chunk may run over before it gives up
 constexpr uint32_t GZ_MAX_OUT = 0xF0000000u;
@@ -52,20 +55,28 @@ constexpr uint32_t GZ_MAX_OUT = 0xF0000000u;
 // zeros, so a decode that runs off the end stays inside the buffer.
 struct GzBits {
   const uint32_t* w0;
-  const uint32_t* w;
+  const uint32_t* w;     // the next word to put into `buf`
   const uint32_t* wend;
   u64 buf;
+  uint32_t ahead;        // *w, loaded one refill early so that the load's latency is not waited for
   int cnt;
+  __device__ __forceinline__ uint32_t word(const uint32_t* p) const { return p < wend ? __ldg(p) : 0u; }
   __device__ __forceinline__ void init(const uint32_t* base, const uint32_t* end, u64 bit) {
     w0 = base; wend = end;
     w = base + (bit >> 5);
     const uint32_t sh = (uint32_t)bit & 31u;
-    buf = (u64)((w < wend ? __ldg(w) : 0u) >> sh);
+    buf = (u64)(word(w) >> sh);
     w++;
+    ahead = word(w);
     cnt = 32 - (int)sh;
   }
   __device__ __forceinline__ void refill() {  // afterwards cnt >= 33
-    if (cnt <= 32) { buf |= (u64)(w < wend ? __ldg(w) : 0u) << cnt; w++; cnt += 32; }
+    if (cnt <= 32) {
+      buf |= (u64)ahead << cnt;
+      w++;
+      cnt += 32;
+      ahead = word(w);
+    }
   }
   __device__ __forceinline__ uint32_t take(int n) {  // n <= 16
     const uint32_t v = (uint32_t)buf & ((1u << n) - 1u);
@@ -75,9 +86,21 @@ struct GzBits {
   __device__ __forceinline__ u64 bitpos() const { return (u64)(w - w0) * 32ull - (u64)cnt; }
 };
 
+// Base and extra bits of length symbol s (0..28) and distance symbol d (0..29), RFC 1951 3.2.5, computed rather than
+// looked up: an indexed load from constant memory sits on the critical path of every match.
+__device__ __forceinline__ void len_code(int s, uint32_t& base, int& extra) {
+  extra = s < 8 ? 0 : (s - 4) >> 2;
+  base = s < 8 ? 3u + (uint32_t)s : (((4u + ((uint32_t)s & 3u)) << extra) + 3u);
+  if (s == 28) { base = 258; extra = 0; }
+}
+__device__ __forceinline__ void dist_code(int d, uint32_t& base, int& extra) {
+  extra = d < 4 ? 0 : (d - 2) >> 1;
+  base = d < 4 ? 1u + (uint32_t)d : (((2u + ((uint32_t)d & 1u)) << extra) + 1u);
+}
+
 // The code lengths of a dynamic block (RFC 1951 3.2.7) into t.lens[0 .. nlen + ndist); the reader stands behind
 // the three block-header bits.  Returns nonzero for what zlib's inflate() calls an invalid block.
-__device__ int gz_dyn_lengths(GzBits& b, WarpTables& t, int lane, int& nlen, int& ndist) {
+__device__ __forceinline__ int gz_dyn_lengths(GzBits& b, WarpTables& t, int lane, int& nlen, int& ndist) {
   b.refill();
   nlen = (int)b.take(5) + 257; ndist = (int)b.take(5) + 1;
   const int ncode = (int)b.take(4) + 4;
@@ -296,10 +319,14 @@ __device__ __noinline__ void gz_chunk(const uint32_t* __restrict__ words, u64 nb
         } else {
           sym -= 257;
           if (sym >= 29) { flags |= GZC_ERROR; stop = true; break; }
-          const uint32_t len = kLenBase[sym] + b.take(kLenExtra[sym]);  // (>= 33 bits were there: 15 + 5 used)
+          uint32_t len, dist;
+          int extra;
+          len_code(sym, len, extra);
+          len += b.take(extra);  // (>= 33 bits were there: 15 + 5 used)
           const int ds = huff_decode(b, t.dist, DBITS, t.dcount, t.dsym);
           if (ds < 0 || ds >= 30) { flags |= GZC_ERROR; stop = true; break; }
-          const uint32_t dist = kDistBase[ds] + b.take(kDistExtra[ds]);
+          dist_code(ds, dist, extra);
+          dist += b.take(extra);
           if (dist > produced) {  // reaches behind the chunk's first byte
             const uint32_t back = dist - produced;
             if (known && back > wvalid) { flags |= GZC_ERROR; stop = true; break; }  // zlib: "invalid distance too far back"
@@ -341,7 +368,7 @@ __device__ __noinline__ void gz_chunk(const uint32_t* __restrict__ words, u64 nb
   }
 }
 
-__global__ void __launch_bounds__(32 * GZ_WARPS) gz_count_kernel(const uint32_t* __restrict__ words, u64 nbytes, u64 chunk_bits, GzChunk* chunks,
+__global__ void __launch_bounds__(32 * GZ_WARPS, GZ_MINB) gz_count_kernel(const uint32_t* __restrict__ words, u64 nbytes, u64 chunk_bits, GzChunk* chunks,
                                                                  int nchunks, uint32_t wvalid) {
   __shared__ WarpTables tables[GZ_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -350,7 +377,7 @@ __global__ void __launch_bounds__(32 * GZ_WARPS) gz_count_kernel(const uint32_t*
   gz_chunk<false>(words, nbytes, chunk_bits, chunks, nchunks, c, nullptr, nullptr, wvalid, tables[warp], lane, nullptr);
 }
 
-__global__ void __launch_bounds__(32 * GZ_WARPS) gz_write_kernel(const uint32_t* __restrict__ words, u64 nbytes, u64 chunk_bits, GzChunk* chunks,
+__global__ void __launch_bounds__(32 * GZ_WARPS, GZ_MINB) gz_write_kernel(const uint32_t* __restrict__ words, u64 nbytes, u64 chunk_bits, GzChunk* chunks,
                                                                  int nchunks, uint16_t* markers, const uint8_t* __restrict__ window, uint32_t wvalid,
                                                                  uint32_t* err) {
   __shared__ WarpTables tables[GZ_WARPS];

@@ -58,7 +58,7 @@ struct Bits {
 // Canonical Huffman code from code lengths (all lanes run it; the stores are the same values to the same places):
 // count[l] = codes of length l, symbol[] = symbols ordered by code; and the lookup table `tab` of 2^bits entries
 // (filled by the 32 lanes together).  Returns < 0 for an over-subscribed set of lengths, > 0 for an incomplete one.
-static __device__ int huff_build(uint16_t* count, uint16_t* symbol, uint16_t* tab, int bits, const uint8_t* len, int n, int lane) {
+static __device__ __noinline__ int huff_build(uint16_t* count, uint16_t* symbol, uint16_t* tab, int bits, const uint8_t* len, int n, int lane) {
   for (int l = 0; l <= 15; l++) count[l] = 0;
   __syncwarp();
   if (lane == 0) for (int s = 0; s < n; s++) count[len[s]]++;
@@ -99,16 +99,16 @@ static __device__ int huff_build(uint16_t* count, uint16_t* symbol, uint16_t* ta
 __device__ __forceinline__ bool huff_acceptable(int left, const uint16_t* count, int n) {
   return left == 0 || (left > 0 && count[1] == 1 && count[0] == n - 1);
 }
-// Codes longer than the table: walk the canonical code one bit at a time.
-template <class B>
-__device__ __noinline__ int huff_walk(B& b, const uint16_t* count, const uint16_t* symbol) {
-  unsigned long long bb = b.buf;
+// Codes longer than the table: walk the canonical code one bit at a time.  Takes the bits BY VALUE and returns
+// symbol | length << 16 (or -1): a reader passed by reference to a function that is not inlined would live in local
+// memory for the whole decode loop (measured: a third of the loop's stalls were loads of the reader's own fields).
+static __device__ __noinline__ int huff_walk(unsigned long long bb, const uint16_t* count, const uint16_t* symbol) {
   int code = 0, first = 0, index = 0;
   for (int l = 1; l <= 15; l++) {
     code |= (int)(bb & 1ull);
     bb >>= 1;
     const int c = count[l];
-    if (code - c < first) { b.buf = bb; b.cnt -= l; return symbol[index + (code - first)]; }
+    if (code - c < first) return (int)symbol[index + (code - first)] | (l << 16);
     index += c; first += c;
     first <<= 1; code <<= 1;
   }
@@ -118,9 +118,15 @@ template <class B>
 __device__ __forceinline__ int huff_decode(B& b, const uint16_t* tab, int bits, const uint16_t* count, const uint16_t* symbol) {
   b.refill();
   const uint32_t e = tab[(uint32_t)b.buf & ((1u << bits) - 1u)];
-  const int l = (int)(e & 15u);
-  if (l) { b.buf >>= l; b.cnt -= l; return (int)(e >> 4); }
-  return huff_walk(b, count, symbol);
+  int l = (int)(e & 15u);
+  int sym = (int)(e >> 4);
+  if (!l) {
+    const int r = huff_walk(b.buf, count, symbol);
+    if (r < 0) return -1;
+    l = r >> 16; sym = r & 0xFFFF;
+  }
+  b.buf >>= l; b.cnt -= l;
+  return sym;
 }
 
 }  // namespace fq

@@ -10,6 +10,7 @@
 #include <zlib.h>
 
 #include <atomic>
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -677,6 +678,16 @@ static int count_gzip(fqgpu_ctx* ctx, const char* path) {
   const uint32_t* h_err = (const uint32_t*)((const uint8_t*)ctx->h_gzres + sizeof(fq::GzResult));
   const size_t chunk_min = env_size("FQGPU_GZ_CHUNK_KB", 16, 1, 1024) << 10;
 
+  const bool trace = getenv("FQGPU_GZ_TRACE") != nullptr;  // per-stage wall clock (adds stream syncs; diagnostics only)
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t_mark = now();
+  auto mark = [&](const char* what) {
+    if (!trace) return;
+    cudaStreamSynchronize(ctx->stream);
+    const double t = now();
+    fprintf(stderr, "[gz] %-10s %8.3f ms\n", what, t - t_mark);
+    t_mark = t;
+  };
   u64 abs_bit = (u64)payload * 8ull;  // the next block's first bit, in the file
   u64 prior_out = 0;                  // bytes of this member already inflated
   uint32_t crc_reg = 0xFFFFFFFFu;     // the member's CRC-32 register so far
@@ -686,6 +697,7 @@ static int count_gzip(fqgpu_ctx* ctx, const char* path) {
     bool io_bad = false;
     const size_t got = parallel_pread(fd, ctx->h_comp, want_now, fpos, &io_bad);
     if (io_bad) return bail(1);
+    mark("pread");
     const u64 start_bit = abs_bit - (u64)fpos * 8ull;
     if (start_bit + 10 > (u64)got * 8ull) return bail(1);  // the stream ends without a last block: truncated
     size_t chunk_bytes = (got / 12288 + 4095) & ~(size_t)4095;
@@ -696,17 +708,20 @@ static int count_gzip(fqgpu_ctx* ctx, const char* path) {
     CU_B(cudaMemcpyAsync(ctx->d_comp, ctx->h_comp, got, cudaMemcpyHostToDevice, ctx->stream));
     CU_B(cudaMemsetAsync(ctx->d_comp + got, 0, 64, ctx->stream));
     CU_B(cudaMemsetAsync(d_err, 0, 16, ctx->stream));
+    mark("h2d");
     CU_B(fq::launch_gz_sync(ctx->d_comp, got, (uint32_t)chunk_bytes, nchunks, start_bit, chunks, d_err + 1, ctx->stream));
     CU_B(cudaMemcpyAsync((uint8_t*)ctx->h_gzres + sizeof(fq::GzResult) + 4, d_err + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU_B(cudaStreamSynchronize(ctx->stream));
     // blocks longer than 64 chunks on average (stored or fixed-code streams, no dynamic headers to find): one warp
     // would decode nearly everything alone -- zlib on the host is faster than that
     if (nchunks >= 64 && (size_t)h_err[1] * 64 < (size_t)nchunks) return bail(1);
+    mark("sync");
     CU_B(fq::launch_gz_count(ctx->d_comp, got, (uint32_t)chunk_bytes, chunks, nchunks, wvalid, ctx->stream));
     CU_B(fq::launch_gz_chain(chunks, nchunks, prior_out, d_res, ctx->d_gzorder, ctx->d_gzcoff, ctx->stream));
     CU_B(cudaMemcpyAsync(ctx->h_gzres, ctx->d_gzres, sizeof(fq::GzResult), cudaMemcpyDeviceToHost, ctx->stream));
     CU_B(cudaStreamSynchronize(ctx->stream));
     ctx->launches += 3;
+    mark("count");
     const fq::GzResult res = *h_res;
     if (res.status != fq::GZR_OK) return bail(1);
     if (res.total_out == 0 && !res.final_block) return bail(1);  // no complete block in a whole batch, or a truncated file
@@ -740,9 +755,12 @@ static int count_gzip(fqgpu_ctx* ctx, const char* path) {
       uint16_t* grows = symrows + ctx->gzwbuf_cap * fq::GZ_WINDOW;
       uint8_t* trows = (uint8_t*)(grows + (ctx->gzwbuf_cap / 8 + 2) * fq::GZ_WINDOW);
       (void)ngroups;
+      mark("alloc");
       CU_B(fq::launch_gz_write(ctx->d_comp, got, (uint32_t)chunk_bytes, chunks, nchunks, ctx->d_gzsym, ctx->d_gzwindow, wvalid, d_err, ctx->stream));
+      mark("write");
       CU_B(fq::launch_gz_windows(ctx->d_gzcoff, res.nchain, K, ctx->d_gzsym, symrows, grows, trows, ctx->d_gzwindow, ctx->stream));
       CU_B(fq::launch_gz_resolve(ctx->d_gzsym, symrows, trows, K, ctx->d_gzcoff, res.nchain, total, ctx->d_inflated, ctx->grid / 2, ctx->stream));
+      mark("windows");
       const u64 nslices = total / fq::GZ_CRC_SLICE;
       const uint32_t q = (uint32_t)((nslices + 1023) / 1024);
       if (ctx->gzraw_cap < nslices + 1) {
@@ -757,6 +775,7 @@ static int count_gzip(fqgpu_ctx* ctx, const char* path) {
       const int rc = fqgpu_scan_device(ctx, ctx->d_inflated, (size_t)total);
       if (rc != FQGPU_OK) return bail(rc);
       CU_B(cudaStreamSynchronize(ctx->stream));  // the batch buffers are reused
+      mark("crc+scan");
       if (*h_err) return bail(1);
       // the register over this batch's bytes (full slices, then the tail), behind the bytes before it
       const uint32_t batch_reg = crc_mul(crc_xpow8(total % fq::GZ_CRC_SLICE), h_err[2]) ^ h_err[3];
