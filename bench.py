@@ -368,8 +368,9 @@ def ingest_leg(fq, ctx, buf, nbytes):
                 f.write(p)
             f.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
         for name, env in (("bgzf_device_inflate", None), ("bgzf_host_zlib", "1")):
-            if env:
+            if env:  # neither device inflater: gzread on the host, the reference's path
                 os.environ["FQGPU_NO_BGZF"] = env
+                os.environ["FQGPU_NO_GZIP_DEVICE"] = env
             try:
                 best = 1e9
                 for _ in range(2):
@@ -378,10 +379,11 @@ def ingest_leg(fq, ctx, buf, nbytes):
                     best = min(best, time.perf_counter() - t0)
             finally:
                 os.environ.pop("FQGPU_NO_BGZF", None)
+                os.environ.pop("FQGPU_NO_GZIP_DEVICE", None)
             assert st.to_dict() == want.to_dict(), name + ": result differs from the HBM-resident scan"
             out[name] = {"value": n_gz / best / 1e9, "unit": "GB/s of uncompressed bytes", "bytes": n_gz,
                          "members_on_device": fctx.bgzf_members()}
-        out["bgzf_host_zlib"]["note"] = "the same file with FQGPU_NO_BGZF=1: zlib on one host thread, the reference's gzip_stream path"
+        out["bgzf_host_zlib"]["note"] = "the same file with FQGPU_NO_BGZF=1 FQGPU_NO_GZIP_DEVICE=1: zlib on one host thread, the reference's gzip_stream path"
         fctx.close()
     finally:
         shutil.rmtree(tmp, ignore_errors=True)

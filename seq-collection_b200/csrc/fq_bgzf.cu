@@ -20,6 +20,9 @@
 
 namespace fq {
 
+#ifndef BGZF_MINB
+#define BGZF_MINB 10  // resident CTAs per SM the kernel is compiled for (register cap)
+#endif
 constexpr int BGZF_WARPS = 4;         // members per CTA
 constexpr uint32_t CRC_SLICE = 2048;  // bytes per lane in the CRC pass (32 slices cover a 64 KiB member)
 
@@ -27,8 +30,9 @@ enum { BGZF_OK = 0, BGZF_EBLOCK = 1, BGZF_ECODE = 2, BGZF_EDIST = 3, BGZF_ESIZE 
 
 // Inflates member d (all 32 lanes in lockstep).  Returns BGZF_*.
 __device__ __noinline__ int bgzf_inflate_member(const uint8_t* __restrict__ comp, const BgzfMember& d, uint8_t* out, WarpTables& t, int lane) {
-  Bits b;
-  b.init(comp + d.in_off, d.in_len);
+  // (the batch buffer is 4-byte aligned; the reader may run into the member's own 8-byte trailer, not beyond)
+  GzBits b;
+  b.init(reinterpret_cast<const uint32_t*>(comp), reinterpret_cast<const uint32_t*>(comp) + ((d.in_off + d.in_len + 8u + 3u) >> 2), d.in_off * 8ull);
   uint8_t* o = out + d.out_off;
   const uint32_t cap = d.out_len;
   uint32_t produced = 0;
@@ -54,10 +58,10 @@ __device__ __noinline__ int bgzf_inflate_member(const uint8_t* __restrict__ comp
     if (type == 1) {  // fixed codes
       for (int s = lane; s < 288; s += 32) t.lens[s] = s < 144 ? 8 : (s < 256 ? 9 : (s < 280 ? 7 : 8));
       __syncwarp();
-      huff_build(t.lcount, t.lsym, t.lit, LBITS, t.lens, 288, lane);
+      huff_build<HUFF_LITLEN>(t.lcount, t.lsym, t.lit, LBITS, t.lens, 288, lane);
       for (int s = lane; s < 30; s += 32) t.lens[s] = 5;
       __syncwarp();
-      huff_build(t.dcount, t.dsym, t.dist, DBITS, t.lens, 30, lane);
+      huff_build<HUFF_DIST>(t.dcount, t.dsym, t.dist, DBITS, t.lens, 30, lane);
     } else {  // dynamic codes
       b.refill();
       const int nlen = (int)b.take(5) + 257, ndist = (int)b.take(5) + 1, ncode = (int)b.take(4) + 4;
@@ -67,11 +71,12 @@ __device__ __noinline__ int bgzf_inflate_member(const uint8_t* __restrict__ comp
       for (int k = 0; k < ncode; k++) { b.refill(); const uint32_t v = b.take(3); if (lane == 0) t.lens[kClOrder[k]] = (uint8_t)v; }
       __syncwarp();
       // the code-length code (19 symbols, at most 7 bits) goes through the distance table's slots
-      if (huff_build(t.dcount, t.dsym, t.dist, 7, t.lens, 19, lane) != 0) return BGZF_ECODE;
+      if (huff_build<HUFF_PRECODE>(t.dcount, t.dsym, t.dist, PBITS, t.lens, 19, lane) != 0) return BGZF_ECODE;
       int idx = 0;
       while (idx < nlen + ndist) {
-        const int sym = huff_decode(b, t.dist, 7, t.dcount, t.dsym);
-        if (sym < 0) return BGZF_ECODE;
+        const uint32_t pe = huff_peek<HUFF_PRECODE, PBITS>(b, t.dist, t.dcount, t.dsym);
+        if (!(pe & 15u)) return BGZF_ECODE;
+        const int sym = (int)huff_take(b, pe);
         if (sym < 16) { if (lane == 0) t.lens[idx] = (uint8_t)sym; idx++; continue; }
         int prev = 0, rep;
         b.refill();
@@ -87,25 +92,27 @@ __device__ __noinline__ int bgzf_inflate_member(const uint8_t* __restrict__ comp
       __syncwarp();
       if (t.lens[256] == 0) return BGZF_ECODE;
       // (zlib rejects incomplete codes other than a single code of length 1: so does this, and the file goes to zlib)
-      if (!huff_acceptable(huff_build(t.dcount, t.dsym, t.dist, DBITS, t.lens + nlen, ndist, lane), t.dcount, ndist)) return BGZF_ECODE;
-      if (!huff_acceptable(huff_build(t.lcount, t.lsym, t.lit, LBITS, t.lens, nlen, lane), t.lcount, nlen)) return BGZF_ECODE;
+      if (!huff_acceptable(huff_build<HUFF_DIST>(t.dcount, t.dsym, t.dist, DBITS, t.lens + nlen, ndist, lane), t.dcount, ndist)) return BGZF_ECODE;
+      if (!huff_acceptable(huff_build<HUFF_LITLEN>(t.lcount, t.lsym, t.lit, LBITS, t.lens, nlen, lane), t.lcount, nlen)) return BGZF_ECODE;
     }
     for (;;) {  // literals and matches of this DEFLATE block
-      int sym = huff_decode(b, t.lit, LBITS, t.lcount, t.lsym);
-      if (sym < 0) return BGZF_ECODE;
-      if (sym < 256) {
+      const uint32_t e = huff_peek<HUFF_LITLEN, LBITS>(b, t.lit, t.lcount, t.lsym);
+      const uint32_t kind = e & HK_MASK;
+      if (kind == HK_LITERAL) {
+        huff_take(b, e);
         if (produced >= cap) return BGZF_ESIZE;
-        if (lane == 0) o[produced] = (uint8_t)sym;
+        if (lane == 0) o[produced] = (uint8_t)(e >> 16);
         produced++;
-      } else if (sym == 256) {
+      } else if (kind == HK_END) {
+        huff_take(b, e);
         break;
+      } else if (kind == HK_INVALID) {
+        return BGZF_ECODE;
       } else {
-        sym -= 257;
-        if (sym >= 29) return BGZF_ECODE;
-        const uint32_t len = kLenBase[sym] + b.take(kLenExtra[sym]);  // (>= 33 bits were there: 15 + 5 used)
-        const int ds = huff_decode(b, t.dist, DBITS, t.dcount, t.dsym);
-        if (ds < 0 || ds >= 30) return BGZF_EDIST;
-        const uint32_t dist = kDistBase[ds] + b.take(kDistExtra[ds]);
+        const uint32_t len = huff_take(b, e);  // (>= 33 bits were there: 15 + 5 used)
+        const uint32_t de = huff_peek<HUFF_DIST, DBITS>(b, t.dist, t.dcount, t.dsym);
+        if ((de & HK_MASK) == HK_INVALID) return BGZF_EDIST;
+        const uint32_t dist = huff_take(b, de);
         if (dist > produced) return BGZF_EDIST;
         if (produced + len > cap) return BGZF_ESIZE;
         uint8_t* dst = o + produced;
@@ -138,7 +145,7 @@ __device__ __forceinline__ uint32_t crc_bytes(const uint32_t* tab, const uint8_t
   return v;
 }
 
-__global__ void __launch_bounds__(32 * BGZF_WARPS) bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfMember* __restrict__ members,
+__global__ void __launch_bounds__(32 * BGZF_WARPS, BGZF_MINB) bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfMember* __restrict__ members,
                                                                        int n, uint8_t* out, uint32_t* __restrict__ status, const CrcShift sh) {
   __shared__ uint32_t tab[256];
   __shared__ WarpTables tables[BGZF_WARPS];

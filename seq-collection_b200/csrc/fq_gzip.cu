@@ -51,53 +51,6 @@ constexpr int GZ_WARPS = 4;        // chunks per CTA
 constexpr int GZ_MAX_PASSED = 6;   // false starts one chunk may run over before it gives up
 constexpr uint32_t GZ_MAX_OUT = 0xF0000000u;
 
-// LSB-first bit reader over the batch's 32-bit words that knows its position.  Beyond `wend` the stream reads as
-// zeros, so a decode that runs off the end stays inside the buffer.
-struct GzBits {
-  const uint32_t* w0;
-  const uint32_t* w;     // the next word to put into `buf`
-  const uint32_t* wend;
-  u64 buf;
-  uint32_t ahead;        // *w, loaded one refill early so that the load's latency is not waited for
-  int cnt;
-  __device__ __forceinline__ uint32_t word(const uint32_t* p) const { return p < wend ? __ldg(p) : 0u; }
-  __device__ __forceinline__ void init(const uint32_t* base, const uint32_t* end, u64 bit) {
-    w0 = base; wend = end;
-    w = base + (bit >> 5);
-    const uint32_t sh = (uint32_t)bit & 31u;
-    buf = (u64)(word(w) >> sh);
-    w++;
-    ahead = word(w);
-    cnt = 32 - (int)sh;
-  }
-  __device__ __forceinline__ void refill() {  // afterwards cnt >= 33
-    if (cnt <= 32) {
-      buf |= (u64)ahead << cnt;
-      w++;
-      cnt += 32;
-      ahead = word(w);
-    }
-  }
-  __device__ __forceinline__ uint32_t take(int n) {  // n <= 16
-    const uint32_t v = (uint32_t)buf & ((1u << n) - 1u);
-    buf >>= n; cnt -= n;
-    return v;
-  }
-  __device__ __forceinline__ u64 bitpos() const { return (u64)(w - w0) * 32ull - (u64)cnt; }
-};
-
-// Base and extra bits of length symbol s (0..28) and distance symbol d (0..29), RFC 1951 3.2.5, computed rather than
-// looked up: an indexed load from constant memory sits on the critical path of every match.
-__device__ __forceinline__ void len_code(int s, uint32_t& base, int& extra) {
-  extra = s < 8 ? 0 : (s - 4) >> 2;
-  base = s < 8 ? 3u + (uint32_t)s : (((4u + ((uint32_t)s & 3u)) << extra) + 3u);
-  if (s == 28) { base = 258; extra = 0; }
-}
-__device__ __forceinline__ void dist_code(int d, uint32_t& base, int& extra) {
-  extra = d < 4 ? 0 : (d - 2) >> 1;
-  base = d < 4 ? 1u + (uint32_t)d : (((2u + ((uint32_t)d & 1u)) << extra) + 1u);
-}
-
 // The code lengths of a dynamic block (RFC 1951 3.2.7) into t.lens[0 .. nlen + ndist); the reader stands behind
 // the three block-header bits.  Returns nonzero for what zlib's inflate() calls an invalid block.
 __device__ __forceinline__ int gz_dyn_lengths(GzBits& b, WarpTables& t, int lane, int& nlen, int& ndist) {
@@ -109,11 +62,12 @@ __device__ __forceinline__ int gz_dyn_lengths(GzBits& b, WarpTables& t, int lane
   __syncwarp();
   for (int k = 0; k < ncode; k++) { b.refill(); const uint32_t v = b.take(3); if (lane == 0) t.lens[kClOrder[k]] = (uint8_t)v; }
   __syncwarp();
-  if (huff_build(t.dcount, t.dsym, t.dist, 7, t.lens, 19, lane) != 0) return 1;  // the code-length code must be complete
+  if (huff_build<HUFF_PRECODE>(t.dcount, t.dsym, t.dist, PBITS, t.lens, 19, lane) != 0) return 1;  // the code-length code must be complete
   int idx = 0;
   while (idx < nlen + ndist) {
-    const int sym = huff_decode(b, t.dist, 7, t.dcount, t.dsym);
-    if (sym < 0) return 1;
+    const uint32_t pe = huff_peek<HUFF_PRECODE, PBITS>(b, t.dist, t.dcount, t.dsym);
+    if (!(pe & 15u)) return 1;
+    const int sym = (int)huff_take(b, pe);
     if (sym < 16) { if (lane == 0) t.lens[idx] = (uint8_t)sym; idx++; continue; }
     int prev = 0, rep;
     b.refill();
@@ -291,15 +245,15 @@ __device__ __noinline__ void gz_chunk(const uint32_t* __restrict__ words, u64 nb
       if (type == 1) {  // fixed codes
         for (int s = lane; s < 288; s += 32) t.lens[s] = s < 144 ? 8 : (s < 256 ? 9 : (s < 280 ? 7 : 8));
         __syncwarp();
-        huff_build(t.lcount, t.lsym, t.lit, LBITS, t.lens, 288, lane);
+        huff_build<HUFF_LITLEN>(t.lcount, t.lsym, t.lit, LBITS, t.lens, 288, lane);
         for (int s = lane; s < 30; s += 32) t.lens[s] = 5;
         __syncwarp();
-        huff_build(t.dcount, t.dsym, t.dist, DBITS, t.lens, 30, lane);
+        huff_build<HUFF_DIST>(t.dcount, t.dsym, t.dist, DBITS, t.lens, 30, lane);
       } else {
         int nl, ndist;
         if (gz_dyn_lengths(b, t, lane, nl, ndist)) { flags |= GZC_ERROR; break; }
-        if (!huff_acceptable(huff_build(t.dcount, t.dsym, t.dist, DBITS, t.lens + nl, ndist, lane), t.dcount, ndist) ||
-            !huff_acceptable(huff_build(t.lcount, t.lsym, t.lit, LBITS, t.lens, nl, lane), t.lcount, nl)) { flags |= GZC_ERROR; break; }
+        if (!huff_acceptable(huff_build<HUFF_DIST>(t.dcount, t.dsym, t.dist, DBITS, t.lens + nl, ndist, lane), t.dcount, ndist) ||
+            !huff_acceptable(huff_build<HUFF_LITLEN>(t.lcount, t.lsym, t.lit, LBITS, t.lens, nl, lane), t.lcount, nl)) { flags |= GZC_ERROR; break; }
       }
       bool stop = false;
       for (;;) {  // literals and matches of this block
@@ -309,24 +263,22 @@ __device__ __noinline__ void gz_chunk(const uint32_t* __restrict__ words, u64 nb
           if (!advance_limit(b.bitpos())) { flags |= GZC_GIVEUP; stop = true; break; }
           if (b.w > wstop) continue;
         }
-        int sym = huff_decode(b, t.lit, LBITS, t.lcount, t.lsym);
-        if (sym < 0) { flags |= GZC_ERROR; stop = true; break; }
-        if (sym < 256) {
-          if (WRITE && lane == 0) m[produced] = (uint16_t)sym;
+        const uint32_t e = huff_peek<HUFF_LITLEN, LBITS>(b, t.lit, t.lcount, t.lsym);
+        const uint32_t kind = e & HK_MASK;
+        if (kind == HK_LITERAL) {
+          huff_take(b, e);
+          if (WRITE && lane == 0) m[produced] = (uint16_t)(e >> 16);
           produced++;
-        } else if (sym == 256) {
+        } else if (kind == HK_END) {
+          huff_take(b, e);
           break;
+        } else if (kind == HK_INVALID) {
+          flags |= GZC_ERROR; stop = true; break;
         } else {
-          sym -= 257;
-          if (sym >= 29) { flags |= GZC_ERROR; stop = true; break; }
-          uint32_t len, dist;
-          int extra;
-          len_code(sym, len, extra);
-          len += b.take(extra);  // (>= 33 bits were there: 15 + 5 used)
-          const int ds = huff_decode(b, t.dist, DBITS, t.dcount, t.dsym);
-          if (ds < 0 || ds >= 30) { flags |= GZC_ERROR; stop = true; break; }
-          dist_code(ds, dist, extra);
-          dist += b.take(extra);
+          const uint32_t len = huff_take(b, e);  // (>= 33 bits were there: 15 + 5 used)
+          const uint32_t de = huff_peek<HUFF_DIST, DBITS>(b, t.dist, t.dcount, t.dsym);
+          if ((de & HK_MASK) == HK_INVALID) { flags |= GZC_ERROR; stop = true; break; }
+          const uint32_t dist = huff_take(b, de);
           if (dist > produced) {  // reaches behind the chunk's first byte
             const uint32_t back = dist - produced;
             if (known && back > wvalid) { flags |= GZC_ERROR; stop = true; break; }  // zlib: "invalid distance too far back"

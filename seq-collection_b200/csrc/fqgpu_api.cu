@@ -691,6 +691,7 @@ static int count_gzip(fqgpu_ctx* ctx, const char* path) {
   u64 abs_bit = (u64)payload * 8ull;  // the next block's first bit, in the file
   u64 prior_out = 0;                  // bytes of this member already inflated
   uint32_t crc_reg = 0xFFFFFFFFu;     // the member's CRC-32 register so far
+  size_t members = 0;                 // members finished
   for (;;) {
     const size_t fpos = (size_t)(abs_bit >> 3) & ~(size_t)4095;
     const size_t want_now = fsize - fpos < ctx->comp_cap ? fsize - fpos : ctx->comp_cap;
@@ -796,6 +797,8 @@ static int count_gzip(fqgpu_ctx* ctx, const char* path) {
     // another member behind it (`cat a.gz b.gz`) continues the stream; anything else is ignored, as gzread does
     payload = gzip_payload_offset(fd, tpos + 8, fsize);
     if (!payload) break;
+    // a long row of small members (each one costs a batch of its own): gzread is no slower on those
+    if (++members >= 64 && (tpos + 8) / members < ((size_t)256 << 10)) return bail(1);
     abs_bit = (u64)payload * 8ull;
     prior_out = 0;
     crc_reg = 0xFFFFFFFFu;
