@@ -64,11 +64,17 @@ void fqgpu_destroy(fqgpu_ctx* ctx) {
   fqgpu_shard_exchange_destroy(ctx);
   if (ctx->h_xres) cudaFreeHost(ctx->h_xres);
   if (ctx->h_shard) cudaFreeHost(ctx->h_shard);
-  if (ctx->h_comp) cudaFreeHost(ctx->h_comp);
-  cudaFree(ctx->d_comp);
+  for (auto& c : ctx->comp) {
+    if (c.h) cudaFreeHost(c.h);
+    if (c.h_members) cudaFreeHost(c.h_members);
+    if (c.h_status) cudaFreeHost(c.h_status);
+    cudaFree(c.d);
+    cudaFree(c.d_members);
+    cudaFree(c.d_status);
+    if (c.h2d) cudaEventDestroy(c.h2d);
+    if (c.done) cudaEventDestroy(c.done);
+  }
   cudaFree(ctx->d_inflated);
-  cudaFree(ctx->d_members);
-  cudaFree(ctx->d_mstatus);
   cudaFree(ctx->d_gzchunks);
   cudaFree(ctx->d_gzorder);
   cudaFree(ctx->d_gzcoff);
@@ -335,7 +341,7 @@ int fqgpu_count_device(fqgpu_ctx* ctx, const void* dptr, size_t nbytes, fqgpu_st
 // ---- host -> device staging ------------------------------------------------------------------
 static int ensure_stage(fqgpu_ctx* ctx) {
   if (ctx->d_stage[0]) return FQGPU_OK;
-  CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->cstream, cudaStreamNonBlocking));
+  if (!ctx->cstream) CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->cstream, cudaStreamNonBlocking));
   for (int b = 0; b < 2; b++) {
     CU_TRY(ctx, cudaMalloc(&ctx->d_stage[b], ctx->chunk_bytes));
     CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_copied[b], cudaEventDisableTiming));
@@ -487,8 +493,37 @@ static size_t parallel_pread(int fd, uint8_t* dst, size_t n, size_t off, bool* i
 // Returns FQGPU_OK when the whole file went through the device path (the caller finishes the stream), 1 when the
 // file is not well-formed BGZF (or cannot be opened): the caller resets and takes the zlib path, which also
 // reports I/O errors the way the reference does.  < 0: CUDA failure.
-static const size_t kBgzfBatchBytes = (size_t)256 << 20;  // compressed bytes per batch
-static const size_t kBgzfBatchMembers = 32768;            // members (= inflating threads) per batch
+static size_t env_size(const char* name, size_t dflt, size_t lo, size_t hi) {
+  const char* e = getenv(name);
+  if (!e) return dflt;
+  const long long v = atoll(e);
+  return v < (long long)lo ? lo : (v > (long long)hi ? hi : (size_t)v);
+}
+
+static const size_t kBgzfBatchBytes = (size_t)64 << 20;  // compressed bytes per batch (about 4000 members: one wave of warps)
+static const size_t kBgzfBatchMembers = 32768;           // members (= inflating warps) per batch
+
+// the two staging slots for compressed input (shared by the BGZF and the gzip path)
+static cudaError_t ensure_comp_slots(fqgpu_ctx* ctx, size_t want) {
+  cudaError_t e = cudaSuccess;
+  if (!ctx->cstream && (e = cudaStreamCreateWithFlags(&ctx->cstream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+  for (auto& c : ctx->comp) {
+    if (!c.h2d && (e = cudaEventCreateWithFlags(&c.h2d, cudaEventDisableTiming)) != cudaSuccess) return e;
+    if (!c.done && (e = cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming)) != cudaSuccess) return e;
+  }
+  if (ctx->comp_cap >= want) return cudaSuccess;
+  if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return e;
+  ctx->comp_cap = 0;
+  for (auto& c : ctx->comp) {
+    if (c.h) cudaFreeHost(c.h);
+    cudaFree(c.d);
+    c.h = nullptr; c.d = nullptr;
+    if ((e = cudaMallocHost(&c.h, want)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&c.d, want + 64)) != cudaSuccess) return e;
+  }
+  ctx->comp_cap = want;
+  return cudaSuccess;
+}
 
 static int count_bgzf(fqgpu_ctx* ctx, const char* path) {
   const int fd = open(path, O_RDONLY);
@@ -501,38 +536,46 @@ static int count_bgzf(fqgpu_ctx* ctx, const char* path) {
     return 1;
   }
   const size_t fsize = (size_t)sb.st_size;
-  auto bail = [&](int code) { close(fd); return code; };
+  // (on every way out the stream is drained: the slots may still be in use by copies and kernels in flight)
+  auto bail = [&](int code) { cudaStreamSynchronize(ctx->cstream); cudaStreamSynchronize(ctx->stream); close(fd); return code; };
 #define CU_B(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return bail(FQGPU_ECUDA); } } while (0)
   CU_B(cudaSetDevice(ctx->device));
-  const size_t want = fsize < kBgzfBatchBytes ? ((fsize + 4095) & ~(size_t)4095) : kBgzfBatchBytes;
-  if (ctx->comp_cap < want) {
-    if (ctx->h_comp) cudaFreeHost(ctx->h_comp);
-    cudaFree(ctx->d_comp);
-    ctx->h_comp = nullptr; ctx->d_comp = nullptr; ctx->comp_cap = 0;
-    CU_B(cudaMallocHost(&ctx->h_comp, want));
-    CU_B(cudaMalloc(&ctx->d_comp, want + 64));
-    ctx->comp_cap = want;
-  }
+  const size_t batch_cap = env_size("FQGPU_BGZF_BATCH_MB", kBgzfBatchBytes >> 20, 1, 1024) << 20;
+  CU_B(ensure_comp_slots(ctx, fsize < batch_cap ? ((fsize + 4095) & ~(size_t)4095) : batch_cap));
   if (ctx->members_cap < kBgzfBatchMembers) {
-    cudaFree(ctx->d_members); cudaFree(ctx->d_mstatus);
-    ctx->d_members = nullptr; ctx->d_mstatus = nullptr; ctx->members_cap = 0;
-    CU_B(cudaMalloc(&ctx->d_members, kBgzfBatchMembers * sizeof(fq::BgzfMember)));
-    CU_B(cudaMalloc(&ctx->d_mstatus, kBgzfBatchMembers * sizeof(uint32_t)));
+    for (auto& c : ctx->comp) {
+      CU_B(cudaMallocHost(&c.h_members, kBgzfBatchMembers * sizeof(fq::BgzfMember)));
+      CU_B(cudaMalloc(&c.d_members, kBgzfBatchMembers * sizeof(fq::BgzfMember)));
+      CU_B(cudaMallocHost(&c.h_status, kBgzfBatchMembers * sizeof(uint32_t)));
+      CU_B(cudaMalloc(&c.d_status, kBgzfBatchMembers * sizeof(uint32_t)));
+    }
     ctx->members_cap = kBgzfBatchMembers;
   }
-  std::vector<fq::BgzfMember> members;
-  std::vector<uint32_t> status;
+  // Batch k: read and walked on the host while the device still inflates and scans batch k - 1; its H2D copy runs on
+  // the copy stream.  A member that failed to inflate is noticed one or two batches later -- what was scanned in between
+  // is thrown away with everything else when the caller resets for the zlib path.
+  int pending[2] = {0, 0};  // members of the batch last sent through the slot, not yet checked
+  auto settle = [&](int s) -> int {  // 1: some member of that batch did not inflate; < 0: CUDA failure
+    if (!pending[s]) return 0;
+    if (cudaEventSynchronize(ctx->comp[s].done) != cudaSuccess) return FQGPU_ECUDA;
+    for (int i = 0; i < pending[s]; i++) if (ctx->comp[s].h_status[i]) return 1;
+    pending[s] = 0;
+    return 0;
+  };
   size_t pos = 0;
-  while (pos < fsize) {
+  for (int k = 0; pos < fsize; k++) {
+    const int s = k & 1;
+    fqgpu_ctx::CompSlot& c = ctx->comp[s];
+    if (int r = settle(s)) return bail(r);  // (also: the slot's buffers are free again)
     const size_t want_now = fsize - pos < ctx->comp_cap ? fsize - pos : ctx->comp_cap;
     bool io_bad = false;
-    const size_t got = parallel_pread(fd, ctx->h_comp, want_now, pos, &io_bad);
+    const size_t got = parallel_pread(fd, c.h, want_now, pos, &io_bad);
     if (io_bad) return bail(1);  // let the zlib path report it
-    members.clear();
-    size_t off = 0;
+    fq::BgzfMember* members = (fq::BgzfMember*)c.h_members;
+    size_t n = 0, off = 0;
     u64 out_total = 0;
-    while (off + 18 <= got && members.size() < kBgzfBatchMembers) {
-      const uint8_t* h = ctx->h_comp + off;
+    while (off + 18 <= got && n < kBgzfBatchMembers) {
+      const uint8_t* h = c.h + off;
       if (!(h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && h[3] == 4)) return bail(1);
       const size_t xlen = (size_t)h[10] | ((size_t)h[11] << 8);
       if (off + 12 + xlen > got) break;  // the header continues in the next batch
@@ -549,35 +592,36 @@ static int count_bgzf(fqgpu_ctx* ctx, const char* path) {
       const uint8_t* t = h + total - 4;
       const uint32_t isize = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
       if (isize > 65536u) return bail(1);
-      fq::BgzfMember m;
+      fq::BgzfMember& m = members[n++];
       m.in_off = off + 12 + xlen; m.out_off = out_total; m.in_len = (unsigned)(total - xlen - 12 - 8); m.out_len = isize;
       m.crc = (uint32_t)t[-4] | ((uint32_t)t[-3] << 8) | ((uint32_t)t[-2] << 16) | ((uint32_t)t[-1] << 24); m.pad = 0;
-      members.push_back(m);
       out_total += isize;
       off += total;
     }
     if (off == 0) return bail(1);  // no complete member in a full batch / trailing garbage
     if (ctx->inflated_cap < out_total + 64) {
+      CU_B(cudaStreamSynchronize(ctx->stream));  // (the scan of the batch before reads the old buffer)
       cudaFree(ctx->d_inflated);
       ctx->d_inflated = nullptr; ctx->inflated_cap = 0;
       const size_t cap = ((size_t)out_total + 64 + ((size_t)64 << 20)) & ~(size_t)4095;
       CU_B(cudaMalloc(&ctx->d_inflated, cap));
       ctx->inflated_cap = cap;
     }
-    const int n = (int)members.size();
-    status.assign((size_t)n, 0u);
-    CU_B(cudaMemcpyAsync(ctx->d_comp, ctx->h_comp, off, cudaMemcpyHostToDevice, ctx->stream));
-    CU_B(cudaMemcpyAsync(ctx->d_members, members.data(), (size_t)n * sizeof(fq::BgzfMember), cudaMemcpyHostToDevice, ctx->stream));
-    CU_B(fq::launch_bgzf_inflate(ctx->d_comp, (const fq::BgzfMember*)ctx->d_members, n, ctx->d_inflated, ctx->d_mstatus, ctx->stream));
-    CU_B(cudaMemcpyAsync(status.data(), ctx->d_mstatus, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CU_B(cudaStreamSynchronize(ctx->stream));
-    for (int i = 0; i < n; i++) if (status[(size_t)i]) return bail(1);  // corrupt member: let zlib decide
+    CU_B(cudaMemcpyAsync(c.d, c.h, off, cudaMemcpyHostToDevice, ctx->cstream));
+    CU_B(cudaMemcpyAsync(c.d_members, c.h_members, n * sizeof(fq::BgzfMember), cudaMemcpyHostToDevice, ctx->cstream));
+    CU_B(cudaEventRecord(c.h2d, ctx->cstream));
+    CU_B(cudaStreamWaitEvent(ctx->stream, c.h2d, 0));
+    CU_B(fq::launch_bgzf_inflate(c.d, (const fq::BgzfMember*)c.d_members, (int)n, ctx->d_inflated, c.d_status, ctx->stream));
+    CU_B(cudaMemcpyAsync(c.h_status, c.d_status, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     const int rc = fqgpu_scan_device(ctx, ctx->d_inflated, (size_t)out_total);
     if (rc != FQGPU_OK) return bail(rc);
-    CU_B(cudaStreamSynchronize(ctx->stream));  // the batch buffers are reused
+    CU_B(cudaEventRecord(c.done, ctx->stream));
+    pending[s] = (int)n;
+    ctx->launches += 1;
     ctx->bgzf_members += (u64)n;
     pos += off;
   }
+  for (int s = 0; s < 2; s++) if (int r = settle(s)) return bail(r);
 #undef CU_B
   close(fd);
   return FQGPU_OK;
@@ -587,14 +631,8 @@ static int count_bgzf(fqgpu_ctx* ctx, const char* path) {
 // Same contract as count_bgzf: FQGPU_OK = the whole file went through the device path, 1 = anything the device
 // path does not prove (not gzip, a chain that does not close, a stream zlib would reject, a truncated file, a
 // wrong ISIZE): the caller resets and lets gzread decide, which keeps the reference's behaviour for broken input.
-// The compressed file is taken in batches (FQGPU_GZ_BATCH_MB, default 256 MiB); a batch starts at the block
+// The compressed file is taken in batches (FQGPU_GZ_BATCH_MB, default 512 MiB); a batch starts at the block
 // boundary where the one before stopped, with the 32 KiB before it as its window.
-static size_t env_size(const char* name, size_t dflt, size_t lo, size_t hi) {
-  const char* e = getenv(name);
-  if (!e) return dflt;
-  const long long v = atoll(e);
-  return v < (long long)lo ? lo : (v > (long long)hi ? hi : (size_t)v);
-}
 
 // the first payload byte of the gzip member at `off` (RFC 1952), or 0 when there is no member header there
 static size_t gzip_payload_offset(int fd, size_t off, size_t fsize) {
@@ -650,19 +688,12 @@ static int count_gzip(fqgpu_ctx* ctx, const char* path) {
   const size_t fsize = (size_t)sb.st_size;
   size_t payload = gzip_payload_offset(fd, 0, fsize);
   if (!payload) { close(fd); return 1; }
-  auto bail = [&](int code) { close(fd); return code; };
+  // (on every way out the streams are drained: the slots may still be in use by copies in flight)
+  auto bail = [&](int code) { if (ctx->cstream) cudaStreamSynchronize(ctx->cstream); cudaStreamSynchronize(ctx->stream); close(fd); return code; };
 #define CU_B(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return bail(FQGPU_ECUDA); } } while (0)
   CU_B(cudaSetDevice(ctx->device));
-  const size_t batch_cap = env_size("FQGPU_GZ_BATCH_MB", 256, 1, 1024) << 20;
-  const size_t want = fsize + 4096 < batch_cap ? ((fsize + 8191) & ~(size_t)4095) : batch_cap;
-  if (ctx->comp_cap < want) {
-    if (ctx->h_comp) cudaFreeHost(ctx->h_comp);
-    cudaFree(ctx->d_comp);
-    ctx->h_comp = nullptr; ctx->d_comp = nullptr; ctx->comp_cap = 0;
-    CU_B(cudaMallocHost(&ctx->h_comp, want));
-    CU_B(cudaMalloc(&ctx->d_comp, want + 64));
-    ctx->comp_cap = want;
-  }
+  const size_t batch_cap = env_size("FQGPU_GZ_BATCH_MB", 512, 1, 1024) << 20;
+  CU_B(ensure_comp_slots(ctx, fsize + 4096 < batch_cap ? ((fsize + 8191) & ~(size_t)4095) : batch_cap));
   if (!ctx->d_gzchunks) {
     CU_B(cudaMalloc(&ctx->d_gzchunks, (size_t)fq::GZ_MAX_CHUNKS * sizeof(fq::GzChunk)));
     CU_B(cudaMalloc(&ctx->d_gzorder, (size_t)fq::GZ_MAX_CHUNKS * sizeof(uint32_t)));
@@ -688,17 +719,47 @@ static int count_gzip(fqgpu_ctx* ctx, const char* path) {
     fprintf(stderr, "[gz] %-10s %8.3f ms\n", what, t - t_mark);
     t_mark = t;
   };
+  // file bytes [at, at + cap) into a slot: read into its pinned buffer, copied on the copy stream once the kernels
+  // that still read the slot's device buffer are through.  Returns the bytes read, SIZE_MAX on an I/O error.
+  cudaError_t load_err = cudaSuccess;
+  const size_t kPiece = (size_t)32 << 20;
+  auto load = [&](int slot, size_t at) -> size_t {
+    fqgpu_ctx::CompSlot& c = ctx->comp[slot];
+    if ((load_err = cudaEventSynchronize(c.h2d)) != cudaSuccess) return 0;  // (the pinned buffer's last copy has left it)
+    const size_t want_now = fsize - at < ctx->comp_cap ? fsize - at : ctx->comp_cap;
+    if ((load_err = cudaStreamWaitEvent(ctx->cstream, c.done, 0)) != cudaSuccess) return 0;
+    size_t n = 0;
+    while (n < want_now) {  // in pieces: the copy of one piece runs under the read of the next
+      const size_t piece = want_now - n < kPiece ? want_now - n : kPiece;
+      bool io_bad = false;
+      const size_t r = parallel_pread(fd, c.h + n, piece, at + n, &io_bad);
+      if (io_bad) return SIZE_MAX;
+      if (r && (load_err = cudaMemcpyAsync(c.d + n, c.h + n, r, cudaMemcpyHostToDevice, ctx->cstream)) != cudaSuccess) return 0;
+      n += r;
+      if (r < piece) break;
+    }
+    if ((load_err = cudaMemsetAsync(c.d + n, 0, 64, ctx->cstream)) != cudaSuccess) return 0;
+    load_err = cudaEventRecord(c.h2d, ctx->cstream);
+    return n;
+  };
   u64 abs_bit = (u64)payload * 8ull;  // the next block's first bit, in the file
   u64 prior_out = 0;                  // bytes of this member already inflated
   uint32_t crc_reg = 0xFFFFFFFFu;     // the member's CRC-32 register so far
   size_t members = 0;                 // members finished
+  // Batch k is decoded from slot s while the bytes of batch k + 1 are read and copied into the other slot.  Where
+  // batch k + 1 has to start is known only when batch k has been counted (the block boundary it stopped at), so the
+  // read is a guess: it starts a little before the end of batch k (kRewind); a last block longer than that is read again.
+  const size_t kRewind = (size_t)4 << 20;
+  int s = 0;
+  size_t fpos = (size_t)(abs_bit >> 3) & ~(size_t)4095;
+  size_t got = load(s, fpos);
+  if (got == SIZE_MAX) return bail(1);
+  CU_B(load_err);
   for (;;) {
-    const size_t fpos = (size_t)(abs_bit >> 3) & ~(size_t)4095;
-    const size_t want_now = fsize - fpos < ctx->comp_cap ? fsize - fpos : ctx->comp_cap;
-    bool io_bad = false;
-    const size_t got = parallel_pread(fd, ctx->h_comp, want_now, fpos, &io_bad);
-    if (io_bad) return bail(1);
-    mark("pread");
+    fqgpu_ctx::CompSlot& slot = ctx->comp[s];
+    uint8_t* const d_comp = slot.d;
+    CU_B(cudaStreamWaitEvent(ctx->stream, slot.h2d, 0));
+    mark("pread+h2d");
     const u64 start_bit = abs_bit - (u64)fpos * 8ull;
     if (start_bit + 10 > (u64)got * 8ull) return bail(1);  // the stream ends without a last block: truncated
     size_t chunk_bytes = (got / 12288 + 4095) & ~(size_t)4095;
@@ -706,20 +767,26 @@ static int count_gzip(fqgpu_ctx* ctx, const char* path) {
     if ((got + chunk_bytes - 1) / chunk_bytes > (size_t)fq::GZ_MAX_CHUNKS) chunk_bytes = ((got + fq::GZ_MAX_CHUNKS - 1) / fq::GZ_MAX_CHUNKS + 4095) & ~(size_t)4095;
     const int nchunks = (int)((got + chunk_bytes - 1) / chunk_bytes);
     const uint32_t wvalid = prior_out < fq::GZ_WINDOW ? (uint32_t)prior_out : fq::GZ_WINDOW;
-    CU_B(cudaMemcpyAsync(ctx->d_comp, ctx->h_comp, got, cudaMemcpyHostToDevice, ctx->stream));
-    CU_B(cudaMemsetAsync(ctx->d_comp + got, 0, 64, ctx->stream));
     CU_B(cudaMemsetAsync(d_err, 0, 16, ctx->stream));
-    mark("h2d");
-    CU_B(fq::launch_gz_sync(ctx->d_comp, got, (uint32_t)chunk_bytes, nchunks, start_bit, chunks, d_err + 1, ctx->stream));
+    CU_B(fq::launch_gz_sync(d_comp, got, (uint32_t)chunk_bytes, nchunks, start_bit, chunks, d_err + 1, ctx->stream));
     CU_B(cudaMemcpyAsync((uint8_t*)ctx->h_gzres + sizeof(fq::GzResult) + 4, d_err + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU_B(cudaStreamSynchronize(ctx->stream));
     // blocks longer than 64 chunks on average (stored or fixed-code streams, no dynamic headers to find): one warp
     // would decode nearly everything alone -- zlib on the host is faster than that
     if (nchunks >= 64 && (size_t)h_err[1] * 64 < (size_t)nchunks) return bail(1);
     mark("sync");
-    CU_B(fq::launch_gz_count(ctx->d_comp, got, (uint32_t)chunk_bytes, chunks, nchunks, wvalid, ctx->stream));
+    CU_B(fq::launch_gz_count(d_comp, got, (uint32_t)chunk_bytes, chunks, nchunks, wvalid, ctx->stream));
     CU_B(fq::launch_gz_chain(chunks, nchunks, prior_out, d_res, ctx->d_gzorder, ctx->d_gzcoff, ctx->stream));
     CU_B(cudaMemcpyAsync(ctx->h_gzres, ctx->d_gzres, sizeof(fq::GzResult), cudaMemcpyDeviceToHost, ctx->stream));
+    // while the device counts: the next batch's bytes
+    size_t next_fpos = 0, next_got = 0;
+    const bool ahead = fpos + got < fsize;
+    if (ahead) {
+      next_fpos = (fpos + got - (got / 2 < kRewind ? got / 2 : kRewind)) & ~(size_t)4095;
+      next_got = load(s ^ 1, next_fpos);
+      if (next_got == SIZE_MAX) return bail(1);
+      CU_B(load_err);
+    }
     CU_B(cudaStreamSynchronize(ctx->stream));
     ctx->launches += 3;
     mark("count");
@@ -757,7 +824,8 @@ static int count_gzip(fqgpu_ctx* ctx, const char* path) {
       uint8_t* trows = (uint8_t*)(grows + (ctx->gzwbuf_cap / 8 + 2) * fq::GZ_WINDOW);
       (void)ngroups;
       mark("alloc");
-      CU_B(fq::launch_gz_write(ctx->d_comp, got, (uint32_t)chunk_bytes, chunks, nchunks, ctx->d_gzsym, ctx->d_gzwindow, wvalid, d_err, ctx->stream));
+      CU_B(fq::launch_gz_write(d_comp, got, (uint32_t)chunk_bytes, chunks, nchunks, ctx->d_gzsym, ctx->d_gzwindow, wvalid, d_err, ctx->stream));
+      CU_B(cudaEventRecord(slot.done, ctx->stream));  // (the last kernel that reads the slot)
       mark("write");
       CU_B(fq::launch_gz_windows(ctx->d_gzcoff, res.nchain, K, ctx->d_gzsym, symrows, grows, trows, ctx->d_gzwindow, ctx->stream));
       CU_B(fq::launch_gz_resolve(ctx->d_gzsym, symrows, trows, K, ctx->d_gzcoff, res.nchain, total, ctx->d_inflated, ctx->grid / 2, ctx->stream));
@@ -786,23 +854,42 @@ static int count_gzip(fqgpu_ctx* ctx, const char* path) {
     ctx->gzip_passed += res.passed;
     prior_out += total;
     abs_bit = (u64)fpos * 8ull + res.end_bit;
-    if (!res.final_block) continue;
-    // the member's trailer: CRC-32 and ISIZE, both checked like gzread does
-    const size_t tpos = (size_t)((abs_bit + 7) >> 3);
-    uint8_t tr[8];
-    if (tpos + 8 > fsize || pread(fd, tr, 8, (off_t)tpos) != 8) return bail(1);
-    const uint32_t isize = (uint32_t)tr[4] | ((uint32_t)tr[5] << 8) | ((uint32_t)tr[6] << 16) | ((uint32_t)tr[7] << 24);
-    const uint32_t crc = (uint32_t)tr[0] | ((uint32_t)tr[1] << 8) | ((uint32_t)tr[2] << 16) | ((uint32_t)tr[3] << 24);
-    if (isize != (uint32_t)prior_out || crc != (crc_reg ^ 0xFFFFFFFFu)) return bail(1);
-    // another member behind it (`cat a.gz b.gz`) continues the stream; anything else is ignored, as gzread does
-    payload = gzip_payload_offset(fd, tpos + 8, fsize);
-    if (!payload) break;
-    // a long row of small members (each one costs a batch of its own): gzread is no slower on those
-    if (++members >= 64 && (tpos + 8) / members < ((size_t)256 << 10)) return bail(1);
-    abs_bit = (u64)payload * 8ull;
-    prior_out = 0;
-    crc_reg = 0xFFFFFFFFu;
+    // where the stream goes on -- the next block, or, behind a member's last block, the next member's first
+    bool more = true;
+    if (res.final_block) {
+      // the member's trailer: CRC-32 and ISIZE, both checked like gzread does
+      const size_t tpos = (size_t)((abs_bit + 7) >> 3);
+      uint8_t tr[8];
+      if (tpos + 8 > fsize || pread(fd, tr, 8, (off_t)tpos) != 8) return bail(1);
+      const uint32_t isize = (uint32_t)tr[4] | ((uint32_t)tr[5] << 8) | ((uint32_t)tr[6] << 16) | ((uint32_t)tr[7] << 24);
+      const uint32_t crc = (uint32_t)tr[0] | ((uint32_t)tr[1] << 8) | ((uint32_t)tr[2] << 16) | ((uint32_t)tr[3] << 24);
+      if (isize != (uint32_t)prior_out || crc != (crc_reg ^ 0xFFFFFFFFu)) return bail(1);
+      // another member behind it (`cat a.gz b.gz`) continues the stream; anything else is ignored, as gzread does
+      payload = gzip_payload_offset(fd, tpos + 8, fsize);
+      if (!payload) {
+        more = false;
+      } else {
+        // a long row of small members (each one costs a batch of its own): gzread is no slower on those
+        if (++members >= 64 && (tpos + 8) / members < ((size_t)256 << 10)) return bail(1);
+        abs_bit = (u64)payload * 8ull;
+        prior_out = 0;
+        crc_reg = 0xFFFFFFFFu;
+      }
+    }
+    if (!more) break;
+    // the bytes from there: already on their way if the guess covered the position
+    s ^= 1;
+    if (ahead && (size_t)(abs_bit >> 3) >= next_fpos && (abs_bit >> 3) + 16 < (u64)next_fpos + next_got) {
+      fpos = next_fpos; got = next_got;
+    } else {
+      fpos = (size_t)(abs_bit >> 3) & ~(size_t)4095;
+      if (fpos >= fsize) return bail(1);  // the stream ends without a last block: truncated
+      got = load(s, fpos);
+      if (got == SIZE_MAX) return bail(1);
+      CU_B(load_err);
+    }
   }
+  if (ctx->cstream) cudaStreamSynchronize(ctx->cstream);  // (a read-ahead that was not needed)
 #undef CU_B
   close(fd);
   return FQGPU_OK;

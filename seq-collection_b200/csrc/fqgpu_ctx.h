@@ -81,14 +81,21 @@ struct fqgpu_ctx {
   u64 x_step = 0;
   u64* h_xres = nullptr;       // pinned: combined block + first wrong rank + end carry
   // on-device BGZF inflate (fq_bgzf.cu): compressed batch (pinned host + device), inflated bytes, member table
-  uint8_t* h_comp = nullptr;
-  uint8_t* d_comp = nullptr;
+  // two slots, so that the file read and the H2D copy of the next batch run under the kernels of this one
+  struct CompSlot {
+    uint8_t* h = nullptr;          // pinned: compressed bytes as read from the file
+    uint8_t* d = nullptr;          // the same on the device
+    void* h_members = nullptr;     // pinned: BGZF member table of the batch
+    void* d_members = nullptr;
+    uint32_t* h_status = nullptr;  // pinned: per-member outcome
+    uint32_t* d_status = nullptr;
+    cudaEvent_t h2d = nullptr;     // the slot's bytes are on the device
+    cudaEvent_t done = nullptr;    // the kernels that read the slot have finished
+  } comp[2];
   size_t comp_cap = 0;
+  size_t members_cap = 0;
   uint8_t* d_inflated = nullptr;
   size_t inflated_cap = 0;
-  void* d_members = nullptr;
-  uint32_t* d_mstatus = nullptr;
-  size_t members_cap = 0;
   u64 bgzf_members = 0;        // members inflated on the device since the last reset (diagnostics)
   // on-device inflate of ordinary gzip (fq_gzip.cu): chunk table, chain, 16-bit symbols, windows
   void* d_gzchunks = nullptr;
