@@ -92,6 +92,13 @@ __device__ __forceinline__ uint32_t nl_mask16_ascii(const uint4& v) {
   uint32_t hi = __dp4a(nl_flags_ascii(v.z), 0x08040201u, __dp4a(nl_flags_ascii(v.w), 0x80402010u, 0u));
   return (lo >> 7) | (hi << 1);
 }
+// the same for '\r'
+__device__ __forceinline__ uint32_t cr_mask16(const uint4& v) {
+  auto flags = [](uint32_t w) { const uint32_t x = w ^ 0x0D0D0D0Du; return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u; };
+  uint32_t lo = __dp4a(flags(v.x), 0x08040201u, __dp4a(flags(v.y), 0x80402010u, 0u));
+  uint32_t hi = __dp4a(flags(v.z), 0x08040201u, __dp4a(flags(v.w), 0x80402010u, 0u));
+  return (lo >> 7) | (hi << 1);
+}
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {

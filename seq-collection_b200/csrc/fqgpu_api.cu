@@ -75,6 +75,8 @@ void fqgpu_destroy(fqgpu_ctx* ctx) {
     if (c.done) cudaEventDestroy(c.done);
   }
   cudaFree(ctx->d_inflated);
+  cudaFree(ctx->d_metaseg);
+  cudaFree(ctx->d_metastart);
   cudaFree(ctx->d_gzchunks);
   cudaFree(ctx->d_gzorder);
   cudaFree(ctx->d_gzcoff);
@@ -175,9 +177,19 @@ static int fqgpu_launch_scan(fqgpu_ctx* ctx, const uint8_t* p, size_t n, u64 met
   if (meta_records) {
     const uintptr_t addr = (uintptr_t)p;
     const uint32_t lo0 = (uint32_t)(addr & 15);
+    const size_t nseg = fq::meta_seg_count((u64)lo0 + n);
+    if (ctx->metaseg_cap < nseg) {
+      CU_TRY(ctx, cudaStreamSynchronize(ctx->mstream));
+      cudaFree(ctx->d_metaseg);
+      ctx->d_metaseg = nullptr; ctx->metaseg_cap = 0;
+      const size_t cap = nseg + (nseg >> 2) + 64;
+      CU_TRY(ctx, cudaMalloc(&ctx->d_metaseg, cap * fq::meta_seg_bytes()));
+      ctx->metaseg_cap = cap;
+    }
+    if (!ctx->d_metastart) CU_TRY(ctx, cudaMalloc(&ctx->d_metastart, sizeof(u64)));
     CU_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     CU_TRY(ctx, cudaStreamWaitEvent(ctx->mstream, ctx->ev_fork, 0));
-    CU_TRY(ctx, fq::launch_meta((const uint8_t*)(addr - lo0), lo0, (u64)lo0 + n, ctx->d_carry, meta_records, ctx->mstream));
+    CU_TRY(ctx, fq::launch_meta((const uint8_t*)(addr - lo0), lo0, (u64)lo0 + n, ctx->d_carry, meta_records, ctx->d_metaseg, ctx->d_metastart, ctx->mstream));
     CU_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->mstream));
   }
   CU_TRY(ctx, fq::launch_scan(p, n, ctx->d_carry, ctx->d_shard, ctx->d_acc, ctx->d_desc, ctx->d_ctl,

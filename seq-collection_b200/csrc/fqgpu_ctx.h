@@ -19,7 +19,9 @@ cudaError_t scan_configure();
 cudaError_t launch_reset(u64* acc, Carry* carry, u64* ctl, cudaStream_t st);
 cudaError_t launch_scan(const void* ptr, size_t nbytes, Carry* carry, ShardInfo* shard, u64* acc, SpanDesc* desc, u64* ctl,
                         bool unknown_start, int resident, bool core_only, cudaStream_t st);
-cudaError_t launch_meta(const uint8_t* base, uint32_t lo0, u64 end, Carry* carry, u64 meta_records, cudaStream_t st);
+size_t meta_seg_count(u64 end);
+size_t meta_seg_bytes();
+cudaError_t launch_meta(const uint8_t* base, uint32_t lo0, u64 end, Carry* carry, u64 meta_records, void* segs, u64* start, cudaStream_t st);
 cudaError_t launch_synth_illumina(void* dptr, u64 first_byte, u64 nbytes, u64 seed, cudaStream_t st);
 cudaError_t launch_synth_illumina_tally(u64 first_record, u64 n_records, u64 seed, u64* d_out, cudaStream_t st);
 void synth_illumina_meta_range(u64 first_record, u64 m, u64 seed, long long* qmin, long long* qmax);
@@ -81,6 +83,10 @@ struct fqgpu_ctx {
   u64 x_step = 0;
   u64* h_xres = nullptr;       // pinned: combined block + first wrong rank + end carry
   // on-device BGZF inflate (fq_bgzf.cu): compressed batch (pinned host + device), inflated bytes, member table
+  // fq-meta fold (fq_meta.cu): per-segment results of a launch, and where the sequential walk takes over
+  void* d_metaseg = nullptr;
+  size_t metaseg_cap = 0;      // segments
+  u64* d_metastart = nullptr;
   // two slots, so that the file read and the H2D copy of the next batch run under the kernels of this one
   struct CompSlot {
     uint8_t* h = nullptr;          // pinned: compressed bytes as read from the file
