@@ -158,10 +158,17 @@ static_assert(sizeof(MetaSeg) == 24, "MetaSeg layout");
 struct LineAcc {  // min / max of one line's content bytes so far, in two lanes of 16 bits (VIMNMX3.U16x2 takes two words per step)
   uint32_t mn2, mx2, has;
   __device__ __forceinline__ void clear() { mn2 = 0x00FF00FFu; mx2 = 0; has = 0; }
-  __device__ __forceinline__ void add(uint32_t c) { mn2 = __vminu2(mn2, c | (c << 16)); mx2 = __vmaxu2(mx2, c | (c << 16)); has = 1; }
-  __device__ __forceinline__ void add4(uint32_t w) {  // four content bytes
-    const uint32_t lo = w & 0x00FF00FFu, hi = (w >> 8) & 0x00FF00FFu;
-    mn2 = __vminu2(mn2, __vminu2(lo, hi)); mx2 = __vmaxu2(mx2, __vmaxu2(lo, hi)); has = 1;
+  // the bytes of the 16-byte group v whose bit is set in `mask`
+  __device__ __forceinline__ void add_masked(const uint4& v, uint32_t mask) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t bm = ((((mask >> (4 * j)) & 15u) * 0x00204081u) & 0x01010101u) * 0xFFu;  // four bits -> four bytes
+      const uint32_t lo = w[j] | ~bm, hi = w[j] & bm;                                          // left out: 0xFF for the min, 0 for the max
+      mn2 = __vminu2(mn2, __vminu2(lo & 0x00FF00FFu, (lo >> 8) & 0x00FF00FFu));
+      mx2 = __vmaxu2(mx2, __vmaxu2(hi & 0x00FF00FFu, (hi >> 8) & 0x00FF00FFu));
+    }
+    has |= mask != 0u;
   }
   __device__ __forceinline__ uint32_t min_byte() const { return min(mn2 & 0xFFFFu, mn2 >> 16); }
   __device__ __forceinline__ uint32_t max_byte() const { return max(mx2 & 0xFFFFu, mx2 >> 16); }
@@ -213,68 +220,58 @@ __global__ void __launch_bounds__(SEG_THREADS) fq_meta_seg_kernel(const uint8_t*
     cur.clear();
   };
   if (a < b) {
-    // the two bytes before the range (0x100: before the launch)
-    uint32_t p1 = a > lo0 ? base[a - 1] : 0x100u, p2 = a > (u64)lo0 + 1 ? base[a - 2] : 0x100u;
+    // Every group of 16 bytes goes through the same steps, whatever it holds (a warp's lanes meet their newlines in
+    // different rounds: a branch per case ran with 6 of 32 lanes active, measured): masks of the newlines and of the
+    // '\r' that are dropped, the content before each newline to the line that is open, the rest to the next one.
+    // What the two bytes before a newline were decides whether the line was empty; for the group's first bytes those
+    // are the last bytes of the group before, kept as bits: '\n'?, '\r'?, before the launch's first byte?
+    auto before = [&](uint32_t d, uint32_t& is_nl, uint32_t& is_cr, uint32_t& is_st) {  // the byte d before the thread's range
+      is_nl = is_cr = is_st = 0;
+      if (a < (u64)lo0 + d) { is_st = 1; return; }
+      const u64 pos = a - d;
+      const uint32_t c = pos >= seg0 ? seg_s[(uint32_t)((pos - seg0) >> 8) * ROW + (uint32_t)((pos - seg0) & 255u)] : base[pos];
+      is_nl = c == '\n'; is_cr = c == '\r';
+    };
+    uint32_t pnl1, pnl2, pcr1, pcr2, pst1, pst2;
+    before(1, pnl1, pcr1, pst1);
+    before(2, pnl2, pcr2, pst2);
     const bool carried_content = carry->cur_has != 0;  // (the line open at the launch's first byte)
     for (uint32_t q = 0; q < SEG_PER_THREAD / 16; q++) {
       const u64 g = g0 + q * 16;
       if (g >= b || g + 16 <= a) continue;
       const uint4 v = *reinterpret_cast<const uint4*>(row + q * 16);
-      const bool whole = g >= a && g + 16 <= b;
-      // no byte below 32 (no '\n', no '\r'): sixteen bytes of one line, the common case.  Bit 5 of b | b >> 1 | b >> 2
-      // is set for a byte >= 32.
-      const uint32_t t = (v.x | (v.x >> 1) | (v.x >> 2)) & (v.y | (v.y >> 1) | (v.y >> 2)) & (v.z | (v.z >> 1) | (v.z >> 2)) &
-                         (v.w | (v.w >> 1) | (v.w >> 2));
-      if (whole && (t & 0x20202020u) == 0x20202020u) {
-        cur.add4(v.x); cur.add4(v.y); cur.add4(v.z); cur.add4(v.w);
-        p2 = (v.w >> 16) & 0xFFu; p1 = v.w >> 24;
-        continue;
-      }
       // the byte after the group: the row's next, the next thread's first, or memory (the segment's last group)
       uint32_t after = 0x100u;
       if (g + 16 < end) after = q + 1 < SEG_PER_THREAD / 16 ? row[q * 16 + 16] : (tid + 1 < SEG_THREADS ? row[ROW] : (uint32_t)base[g + 16]);
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-      const int ka = g >= a ? 0 : (int)(a - g), kb = g + 16 <= b ? 16 : (int)(b - g);
-      const int kend = end - g > 16 ? 17 : (int)(end - g);  // bytes of the launch from g on (capped)
+      const uint32_t ka = g >= a ? 0u : (uint32_t)(a - g), kb = g + 16 <= b ? 16u : (uint32_t)(b - g);
+      const uint32_t kend = end - g > 16 ? 17u : (uint32_t)(end - g);  // bytes of the launch from g on (capped)
       const uint32_t inrange = ((1u << kb) - 1u) & ~((1u << ka) - 1u);
-      const uint32_t nl_all = nl_mask16(v) & (kend >= 16 ? 0xFFFFu : (1u << kend) - 1u);  // (bytes behind the launch's end are not data)
-      const uint32_t nlm = nl_all & inrange;
+      const uint32_t st_all = g < (u64)lo0 ? (1u << (uint32_t)((u64)lo0 - g)) - 1u : 0u;       // bytes before the launch's first
+      const uint32_t data = (kend >= 16 ? 0xFFFFu : (1u << kend) - 1u) & ~st_all;             // bytes of the launch
+      const uint32_t nl_all = nl_mask16(v) & data, cr_all = cr_mask16(v) & data;
       // a '\r' directly before a newline is dropped; a '\r' that is the launch's last byte is left to the next launch
-      uint32_t drop = cr_mask16(v) & ((nl_all >> 1) | (after == '\n' ? 0x8000u : 0u));
-      if (kend <= 16 && ((cr_mask16(v) >> (kend - 1)) & 1u) && kend - 1 >= ka && kend - 1 < kb) { ends_cr = 1; drop |= 1u << (kend - 1); }
-      const uint32_t content = inrange & ~nlm & ~drop;
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const uint32_t cb = (content >> (4 * j)) & 15u, nb = (nlm >> (4 * j)) & 15u;
-        if (nb == 0u && cb == 15u) { cur.add4(w[j]); continue; }  // four bytes of content
-        if ((nb | cb) == 0u) continue;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const int k = 4 * j + i;
-          const uint32_t c = (w[j] >> (8 * i)) & 0xFFu;
-          if ((nb >> i) & 1u) {
-            // an empty line: nothing but a dropped '\r' between this newline and the one before (or the launch's first
-            // byte, where the carried open line decides).  The two bytes before it: in the group, or the group before.
-            const uint32_t b1 = k >= 1 ? (w[(k - 1) >> 2] >> (8 * ((k - 1) & 3))) & 0xFFu : p1;
-            const uint32_t b2 = k >= 2 ? (w[(k - 2) >> 2] >> (8 * ((k - 2) & 3))) & 0xFFu : (k == 1 ? p1 : p2);
-            const uint32_t q1 = k - 1 >= ka ? b1 : p1, q2 = k - 2 >= ka ? b2 : (k - 1 >= ka ? p1 : p2);  // (bytes before `a`: as carried)
-            const bool bare = q1 == '\n' || (q1 == '\r' && q2 == '\n');
-            const bool at_start = q1 == 0x100u || (q1 == '\r' && q2 == 0x100u);
-            if (bare || (at_start && !carried_content)) empty |= 1u << (rel & 3u);
-            close_line(rel & 3u);
-            rel++;
-          } else if ((cb >> i) & 1u) {
-            cur.add(c);
-          }
-        }
+      uint32_t drop = cr_all & ((nl_all >> 1) | (after == '\n' ? 0x8000u : 0u));
+      const uint32_t last_cr = kend <= 16 ? cr_all & inrange & (1u << (kend - 1)) : 0u;
+      if (last_cr) ends_cr = 1;
+      drop |= last_cr;
+      uint32_t nls = nl_all & inrange, rem = inrange & ~nl_all & ~drop;
+      // bit k: the byte before byte k is a newline, or a '\r' with a newline before it (positions shifted by 2 to take
+      // the two carried bytes in); the same for "before the launch's first byte"
+      const uint32_t e_nl = (nl_all << 2) | (pnl1 << 1) | pnl2, e_cr = (cr_all << 2) | (pcr1 << 1) | pcr2, e_st = (st_all << 2) | (pst1 << 1) | pst2;
+      const uint32_t bare = ((e_nl << 1) | ((e_cr << 1) & (e_nl << 2))) >> 2, atst = ((e_st << 1) | ((e_cr << 1) & (e_st << 2))) >> 2;
+      const uint32_t empties = nls & (bare | (carried_content ? 0u : atst));
+      while (nls) {
+        const uint32_t pos = (uint32_t)__ffs((int)nls) - 1u, below = (1u << pos) - 1u;
+        cur.add_masked(v, rem & below);
+        if ((empties >> pos) & 1u) empty |= 1u << (rel & 3u);
+        close_line(rel & 3u);
+        rel++;
+        rem &= ~below;
+        nls &= nls - 1u;
       }
-      // the last two bytes of the thread's range so far
-      {
-        const u64 lo64 = ((u64)v.y << 32) | v.x, hi64 = ((u64)v.w << 32) | v.z;
-        auto byte_at = [&](int pos) { return (uint32_t)((pos < 8 ? lo64 : hi64) >> (8 * (pos & 7))) & 0xFFu; };
-        p2 = kb - 2 >= ka ? byte_at(kb - 2) : p1;  // (a single byte of the group in range: the one carried moves up)
-        p1 = byte_at(kb - 1);
-      }
+      cur.add_masked(v, rem);
+      pnl1 = (nl_all >> 15) & 1u; pnl2 = (nl_all >> 14) & 1u; pcr1 = (cr_all >> 15) & 1u; pcr2 = (cr_all >> 14) & 1u;
+      pst1 = (st_all >> 15) & 1u; pst2 = (st_all >> 14) & 1u;
     }
   }
   // the open part at the thread's end also counts for its residue; and it is what the segment's open line is made of
