@@ -273,13 +273,15 @@ def gz_leg(fq, ctx, n_records: int):
             finally:
                 os.environ.pop("FQGPU_NO_GZIP_DEVICE", None)
             assert bytes(st_host) == bytes(want), "gz end to end (host zlib): result differs from the generator's tallies"
-        # the quality range over ALL reads (-n <all reads>) on the same file: the fold is sequential in the line order
-        # (src/fq_meta.nim:100-102) and runs on one CTA beside the scan, so this variant is bound by it
+        # the quality range over ALL reads (-n <all reads>) on the same file: the fold (src/fq_meta.nim:100-102 is
+        # sequential in the line order) runs many CTAs wide where it is a plain min/max, csrc/fq_meta.cu
         with fq.FqGpu(meta_records=n_records) as g:
             want_all = g.synth_illumina_tally(0, n_records, SEED_ILLUMINA)
-            t0 = time.perf_counter()
-            st_all = g.count_file(path)
-            t_all = time.perf_counter() - t0
+            t_all = 1e9
+            for _ in range(2):
+                t0 = time.perf_counter()
+                st_all = g.count_file(path)
+                t_all = min(t_all, time.perf_counter() - t0)
             assert bytes(st_all) == bytes(want_all), "gz end to end, -n all: result differs from the generator's tallies"
         return {"value": n / best / 1e9, "unit": "GB/s of uncompressed bytes", "records": n_records, "raw_bytes": n, "gz_bytes": len(blob),
                 "seconds": best, "fq_count_row": fq.fq_count_row(st), "fq_meta": {"min_qual": st.meta_qual_min, "max_qual": st.meta_qual_max, "n_lines": st.meta_lines // 4},
@@ -288,7 +290,7 @@ def gz_leg(fq, ctx, n_records: int):
                               "note": "the same file with FQGPU_NO_GZIP_DEVICE=1: gzread on ONE host thread into the pinned ring, the reference's gzip_stream path"},
                 "fq_meta_all_reads": {"value": n / t_all / 1e9, "seconds": t_all, "min_qual": st_all.meta_qual_min, "max_qual": st_all.meta_qual_max,
                                       "n_lines": st_all.meta_lines // 4,
-                                      "note": "the same with -n <all reads>: bound by the sequential quality-range fold (one CTA), not by the inflate"},
+                                      "note": "the same with -n <all reads>: the quality-range fold over every record (segments folded in parallel, csrc/fq_meta.cu), best of 2"},
                 "note": "single-member gzip (level 6), inflated on the device: block starts guessed per chunk and proven by the chunk before "
                         "landing on them, back-references across chunks carried as markers and resolved through a chain of 32 KiB windows, "
                         "CRC-32 + ISIZE of the member verified; fq-meta sample -n 100 (the reference's default); wall clock from open() to "
@@ -367,7 +369,7 @@ def ingest_leg(fq, ctx, buf, nbytes):
                              "note": "uncompressed .fq in the page cache -> pinned ring (multi-threaded reads) -> H2D -> scan; wall clock, best of 3"}
         os.remove(path)
         # BGZF: 64 KiB members, zlib level 6 (compressed here by a thread pool; zlib releases the GIL)
-        n_gz = min(nbytes, 360 * 1_000_000)
+        n_gz = min(nbytes, 1440 * 1_000_000)
         n_gz -= n_gz % REC_BYTES
         want = ctx.count_device(buf.data_ptr(), n_gz)
         raw = buf[:n_gz].cpu().numpy().tobytes()
@@ -384,7 +386,7 @@ def ingest_leg(fq, ctx, buf, nbytes):
                 os.environ["FQGPU_NO_GZIP_DEVICE"] = env
             try:
                 best = 1e9
-                for _ in range(2):
+                for _ in range(1 if env else 3):
                     t0 = time.perf_counter()
                     st = fctx.count_file(path)
                     best = min(best, time.perf_counter() - t0)

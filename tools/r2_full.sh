@@ -13,7 +13,7 @@ try:
     keep['roofline'] = {k: d['roofline'][k] for k in ('achieved','frac','traffic')}
     for k in ('e2e','core_only','ont','gz','index','cpu_baseline'):
         v = d.get(k)
-        keep[k] = ({kk: vv for kk, vv in v.items() if kk in ('value','frac_of_hbm_peak','roofline','error','seconds','fq_count_row','fq_meta')} if isinstance(v, dict) else v)
+        keep[k] = ({kk: vv for kk, vv in v.items() if kk in ('value','frac_of_hbm_peak','roofline','error','seconds','fq_count_row','fq_meta','host_zlib','fq_meta_all_reads','chunks_inflated_on_device','false_block_starts_skipped')} if isinstance(v, dict) else v)
     keep['ingest'] = {k: (v.get('value') if isinstance(v, dict) else v) for k, v in (d.get('ingest') or {}).items()}
     print(json.dumps(keep, indent=1))
 except Exception as e:
