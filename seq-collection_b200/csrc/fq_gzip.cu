@@ -532,32 +532,44 @@ __global__ void __launch_bounds__(WIN_THREADS) gz_rows_kernel(const u64* __restr
 
 // ---- 6. resolve ------------------------------------------------------------------------------------------------------------
 constexpr int RES_THREADS = 256;
+constexpr uint32_t RES_SLICE = RES_THREADS * 8 * 8;  // output positions per CTA step
 __global__ void __launch_bounds__(RES_THREADS) gz_resolve_kernel(const uint16_t* __restrict__ markers, const uint16_t* __restrict__ symrows,
                                                                  const uint8_t* __restrict__ trows, uint32_t K, const u64* __restrict__ coff,
                                                                  uint32_t nchain, u64 total, uint8_t* __restrict__ out) {
-  const u64 ngroups8 = (total + 7) / 8;
-  for (u64 g = (u64)blockIdx.x * RES_THREADS + threadIdx.x; g < ngroups8; g += (u64)gridDim.x * RES_THREADS) {
-    const u64 p0 = g * 8;
-    uint32_t lo = 0, hi = nchain;  // the chain chunk holding p0: the last i with coff[i] <= p0
-    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (coff[mid] <= p0) lo = mid; else hi = mid; }
-    uint32_t i = lo;
-    u64 next = coff[i + 1];
-    const uint4 q = *reinterpret_cast<const uint4*>(markers + p0);  // (the buffer is padded to a multiple of 8 symbols)
-    const uint32_t s[8] = {q.x & 0xFFFFu, q.x >> 16, q.y & 0xFFFFu, q.y >> 16, q.z & 0xFFFFu, q.z >> 16, q.w & 0xFFFFu, q.w >> 16};
-    u64 packed = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      const u64 p = p0 + (u64)k;
-      while (p >= next && i + 1 < nchain) { i++; next = coff[i + 1]; }
-      uint32_t v = s[k];
-      if (v >= 256u && p < total) {
-        // through the chunk's window relative to its group's, then through the group's window
-        if (i % K) v = symrows[(size_t)i * GZ_WINDOW + (v & 0x7FFFu)];
-        if (v >= 256u) v = trows[(size_t)(i / K) * GZ_WINDOW + (v & 0x7FFFu)];
-      }
-      packed |= (u64)(v & 0xFFu) << (8 * k);
+  __shared__ uint32_t first_s;
+  const u64 nslices = (total + RES_SLICE - 1) / RES_SLICE;
+  for (u64 sl = blockIdx.x; sl < nslices; sl += gridDim.x) {
+    const u64 s0 = sl * RES_SLICE;
+    __syncthreads();
+    if (threadIdx.x == 0) {  // the chain chunk holding the slice's first position: the last i with coff[i] <= s0
+      uint32_t lo = 0, hi = nchain;
+      while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (coff[mid] <= s0) lo = mid; else hi = mid; }
+      first_s = lo;
     }
-    *reinterpret_cast<u64*>(out + p0) = packed;  // (padded likewise)
+    __syncthreads();
+    uint32_t i = first_s;
+    u64 next = coff[i + 1];
+#pragma unroll 2
+    for (uint32_t r = 0; r < 8; r++) {
+      const u64 p0 = s0 + ((u64)r * RES_THREADS + threadIdx.x) * 8;
+      if (p0 >= total) break;
+      const uint4 q = *reinterpret_cast<const uint4*>(markers + p0);  // (the buffer is padded to a multiple of 8 symbols)
+      const uint32_t s[8] = {q.x & 0xFFFFu, q.x >> 16, q.y & 0xFFFFu, q.y >> 16, q.z & 0xFFFFu, q.z >> 16, q.w & 0xFFFFu, q.w >> 16};
+      u64 packed = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const u64 p = p0 + (u64)k;
+        while (p >= next && i + 1 < nchain) { i++; next = coff[i + 1]; }
+        uint32_t v = s[k];
+        if (v >= 256u && p < total) {
+          // through the chunk's window relative to its group's, then through the group's window
+          if (i % K) v = symrows[(size_t)i * GZ_WINDOW + (v & 0x7FFFu)];
+          if (v >= 256u) v = trows[(size_t)(i / K) * GZ_WINDOW + (v & 0x7FFFu)];
+        }
+        packed |= (u64)(v & 0xFFu) << (8 * k);
+      }
+      *reinterpret_cast<u64*>(out + p0) = packed;  // (padded likewise)
+    }
   }
 }
 
@@ -644,6 +656,13 @@ __global__ void __launch_bounds__(CRCB_THREADS) gz_crc_fold_kernel(const uint32_
 }
 
 // ---- launchers ---------------------------------------------------------------------------------------------------------------
+// once per device (fqgpu_create): the kernels that take more than 48 KiB of dynamic shared memory
+cudaError_t gz_configure() {
+  cudaError_t e = cudaFuncSetAttribute(gz_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GZ_MAX_CHUNKS * (int)sizeof(int));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(gz_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem_bytes<uint16_t>());
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(gz_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem_bytes<uint8_t>());
+  return e;
+}
 cudaError_t launch_gz_sync(const uint8_t* d_comp, size_t nbytes, uint32_t chunk_bytes, int nchunks, unsigned long long start_bit,
                            GzChunk* chunks, uint32_t* nfound, cudaStream_t st) {
   gz_sync_kernel<<<(nchunks + GZ_WARPS - 1) / GZ_WARPS, 32 * GZ_WARPS, 0, st>>>(reinterpret_cast<const uint32_t*>(d_comp), (u64)nbytes, chunk_bytes,
@@ -658,12 +677,6 @@ cudaError_t launch_gz_count(const uint8_t* d_comp, size_t nbytes, uint32_t chunk
 }
 cudaError_t launch_gz_chain(GzChunk* chunks, int nchunks, unsigned long long prior_out, GzResult* res, uint32_t* order,
                             unsigned long long* coff, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gz_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GZ_MAX_CHUNKS * (int)sizeof(int));
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
   if (nchunks > GZ_MAX_CHUNKS) return cudaErrorInvalidValue;
   gz_chain_kernel<<<1, CHAIN_THREADS, (size_t)nchunks * sizeof(int), st>>>(chunks, nchunks, prior_out, res, order, coff);
   return cudaGetLastError();
@@ -680,13 +693,6 @@ uint32_t gz_group_chunks(uint32_t nchain, int sms) {
 }
 cudaError_t launch_gz_windows(const unsigned long long* coff, uint32_t nchain, uint32_t K, const uint16_t* markers, uint16_t* symrows,
                               uint16_t* grows, uint8_t* trows, uint8_t* window, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gz_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem_bytes<uint16_t>());
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gz_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_smem_bytes<uint8_t>());
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
   if (nchain == 0 || K == 0) return cudaErrorInvalidValue;
   const uint32_t ngroups = (nchain + K - 1) / K;
   cudaError_t e = cudaMemcpyAsync(trows, window, GZ_WINDOW, cudaMemcpyDeviceToDevice, st);  // row 0: the window before the batch
@@ -699,7 +705,7 @@ cudaError_t launch_gz_windows(const unsigned long long* coff, uint32_t nchain, u
 cudaError_t launch_gz_resolve(const uint16_t* markers, const uint16_t* symrows, const uint8_t* trows, uint32_t K, const unsigned long long* coff,
                               uint32_t nchain, unsigned long long total_out, uint8_t* out, int sms, cudaStream_t st) {
   if (total_out == 0) return cudaSuccess;
-  const u64 want = (total_out / 8 + RES_THREADS - 1) / RES_THREADS;
+  const u64 want = (total_out + RES_SLICE - 1) / RES_SLICE;
   const int grid = (int)(want < (u64)sms * 8 ? (want ? want : 1) : (u64)sms * 8);
   gz_resolve_kernel<<<grid, RES_THREADS, 0, st>>>(markers, symrows, trows, K, coff, nchain, total_out, out);
   return cudaGetLastError();

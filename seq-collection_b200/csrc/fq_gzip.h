@@ -40,6 +40,9 @@ struct GzResult {
   uint32_t passed;               // starts found by the search that were not block boundaries
 };
 
+// Once per device, before the first launch.
+cudaError_t gz_configure();
+
 // All kernels run on `st`; positions are bits relative to the first byte of d_comp (4-byte aligned, the bytes
 // behind nbytes up to the next word zeroed).  `window` = the 32 KiB before the batch's first block, right-aligned,
 // of which the last `wvalid` bytes exist; launch_gz_windows replaces it with the window behind the batch.

@@ -444,17 +444,15 @@ __global__ void __launch_bounds__(JOIN_THREADS) fq_meta_join_kernel(const uint8_
 
 // The prefix fold of a launch over bytes [lo0, end) of `base` (16-byte aligned).  `segs`: room for meta_seg_count(end)
 // segments; `start`: one word.
+// once per device (fqgpu_create)
+cudaError_t meta_configure() {
+  return cudaFuncSetAttribute(fq_meta_seg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_THREADS * (SEG_PER_THREAD + 16));
+}
 size_t meta_seg_count(u64 end) { return (size_t)((end + SEG_BYTES - 1) / SEG_BYTES); }
 size_t meta_seg_bytes() { return sizeof(MetaSeg); }
 cudaError_t launch_meta(const uint8_t* base, uint32_t lo0, u64 end, Carry* carry, u64 meta_records, void* segs, u64* start, cudaStream_t st) {
   const uint32_t nseg = (uint32_t)meta_seg_count(end);
   if (nseg == 0) return cudaSuccess;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(fq_meta_seg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_THREADS * (SEG_PER_THREAD + 16));
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
   if (meta_records * 4 <= 4096) {  // a small sample (the default is 100 reads): the sequential walk alone
     fq_meta_par_kernel<<<1, META_THREADS, 0, st>>>(base, lo0, nullptr, end, carry, meta_records);
     return cudaGetLastError();

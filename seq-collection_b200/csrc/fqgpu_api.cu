@@ -125,6 +125,8 @@ int fqgpu_create(fqgpu_ctx** out, const fqgpu_config* cfg) {
   CU_NEW(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
   CU_NEW(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   CU_NEW(fq::scan_configure());
+  CU_NEW(fq::meta_configure());
+  CU_NEW(fq::gz_configure());
   ctx->grid = prop.multiProcessorCount * fq::scan_ctas_per_sm();
   if (ctx->grid > fq::RESIDENT_CTAS) ctx->grid = fq::RESIDENT_CTAS;
   CU_NEW(cudaMalloc(&ctx->d_acc, fq::BLOCK_WORDS * sizeof(u64)));
@@ -703,9 +705,11 @@ static int count_gzip(fqgpu_ctx* ctx, const char* path) {
   // (on every way out the streams are drained: the slots may still be in use by copies in flight)
   auto bail = [&](int code) { if (ctx->cstream) cudaStreamSynchronize(ctx->cstream); cudaStreamSynchronize(ctx->stream); close(fd); return code; };
 #define CU_B(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return bail(FQGPU_ECUDA); } } while (0)
+  // buffers whose size follows the input: when they do not fit, the host path (which streams) takes the file
+#define CU_ALLOC(call) do { cudaError_t e_ = (call); if (e_ == cudaErrorMemoryAllocation) { cudaGetLastError(); return bail(1); } if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return bail(FQGPU_ECUDA); } } while (0)
   CU_B(cudaSetDevice(ctx->device));
   const size_t batch_cap = env_size("FQGPU_GZ_BATCH_MB", 512, 1, 1024) << 20;
-  CU_B(ensure_comp_slots(ctx, fsize + 4096 < batch_cap ? ((fsize + 8191) & ~(size_t)4095) : batch_cap));
+  CU_ALLOC(ensure_comp_slots(ctx, fsize + 4096 < batch_cap ? ((fsize + 8191) & ~(size_t)4095) : batch_cap));
   if (!ctx->d_gzchunks) {
     CU_B(cudaMalloc(&ctx->d_gzchunks, (size_t)fq::GZ_MAX_CHUNKS * sizeof(fq::GzChunk)));
     CU_B(cudaMalloc(&ctx->d_gzorder, (size_t)fq::GZ_MAX_CHUNKS * sizeof(uint32_t)));
@@ -811,14 +815,14 @@ static int count_gzip(fqgpu_ctx* ctx, const char* path) {
         cudaFree(ctx->d_gzsym);
         ctx->d_gzsym = nullptr; ctx->gzsym_cap = 0;
         const size_t cap = (size_t)total + ((size_t)total >> 3) + 4096;
-        CU_B(cudaMalloc(&ctx->d_gzsym, cap * sizeof(uint16_t)));
+        CU_ALLOC(cudaMalloc(&ctx->d_gzsym, cap * sizeof(uint16_t)));
         ctx->gzsym_cap = cap;
       }
       if (ctx->inflated_cap < total + 64) {
         cudaFree(ctx->d_inflated);
         ctx->d_inflated = nullptr; ctx->inflated_cap = 0;
         const size_t cap = ((size_t)total + ((size_t)total >> 3) + 8192) & ~(size_t)4095;
-        CU_B(cudaMalloc(&ctx->d_inflated, cap));
+        CU_ALLOC(cudaMalloc(&ctx->d_inflated, cap));
         ctx->inflated_cap = cap;
       }
       const uint32_t K = fq::gz_group_chunks(res.nchain, ctx->grid / 2);
@@ -828,7 +832,7 @@ static int count_gzip(fqgpu_ctx* ctx, const char* path) {
         ctx->d_gzwbuf = nullptr; ctx->gzwbuf_cap = 0;
         const size_t rows = (size_t)res.nchain + 1 + ((size_t)res.nchain >> 2);
         // per chunk a row of symbols; per group (at most one per 8 chunks) a row of symbols and a row of bytes
-        CU_B(cudaMalloc(&ctx->d_gzwbuf, rows * fq::GZ_WINDOW * 2 + (rows / 8 + 2) * fq::GZ_WINDOW * 3));
+        CU_ALLOC(cudaMalloc(&ctx->d_gzwbuf, rows * fq::GZ_WINDOW * 2 + (rows / 8 + 2) * fq::GZ_WINDOW * 3));
         ctx->gzwbuf_cap = rows;
       }
       uint16_t* symrows = (uint16_t*)ctx->d_gzwbuf;
@@ -847,7 +851,7 @@ static int count_gzip(fqgpu_ctx* ctx, const char* path) {
       if (ctx->gzraw_cap < nslices + 1) {
         cudaFree(ctx->d_gzraw);
         ctx->d_gzraw = nullptr; ctx->gzraw_cap = 0;
-        CU_B(cudaMalloc(&ctx->d_gzraw, (nslices + 1 + (nslices >> 3)) * sizeof(uint32_t)));
+        CU_ALLOC(cudaMalloc(&ctx->d_gzraw, (nslices + 1 + (nslices >> 3)) * sizeof(uint32_t)));
         ctx->gzraw_cap = nslices + 1 + (nslices >> 3);
       }
       CU_B(fq::launch_gz_crc(ctx->d_inflated, total, ctx->d_gzraw, crc_xpow8(fq::GZ_CRC_SLICE), crc_xpow8((u64)fq::GZ_CRC_SLICE * q), q, d_err + 2, ctx->stream));
@@ -903,6 +907,7 @@ static int count_gzip(fqgpu_ctx* ctx, const char* path) {
   }
   if (ctx->cstream) cudaStreamSynchronize(ctx->cstream);  // (a read-ahead that was not needed)
 #undef CU_B
+#undef CU_ALLOC
   close(fd);
   return FQGPU_OK;
 }

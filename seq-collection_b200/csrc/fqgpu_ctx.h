@@ -19,6 +19,7 @@ cudaError_t scan_configure();
 cudaError_t launch_reset(u64* acc, Carry* carry, u64* ctl, cudaStream_t st);
 cudaError_t launch_scan(const void* ptr, size_t nbytes, Carry* carry, ShardInfo* shard, u64* acc, SpanDesc* desc, u64* ctl,
                         bool unknown_start, int resident, bool core_only, cudaStream_t st);
+cudaError_t meta_configure();
 size_t meta_seg_count(u64 end);
 size_t meta_seg_bytes();
 cudaError_t launch_meta(const uint8_t* base, uint32_t lo0, u64 end, Carry* carry, u64 meta_records, void* segs, u64* start, cudaStream_t st);
