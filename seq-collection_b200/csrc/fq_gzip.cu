@@ -88,12 +88,14 @@ __device__ __forceinline__ int gz_dyn_lengths(GzBits& b, WarpTables& t, int lane
 // ---- 1. block-start search ---------------------------------------------------------------------------------------
 // Is bit t the first bit of a dynamic block the way a compressor writes one?  (Stricter than inflate(): both codes
 // complete -- zlib, libdeflate, igzip and pigz always emit complete codes -- or a distance code of at most one
-// symbol.  A real start that fails this is merely not used: the chunk before decodes through it.)
+// symbol; no trailing zero lengths.  A real start that fails this is merely not used: the chunk before decodes through it.)
 __device__ bool gz_header_plausible(const uint32_t* words, const uint32_t* wend, u64 t, WarpTables& tb, int lane) {
   GzBits b;
   b.init(words, wend, t + 3);
   int nlen, ndist;
   if (gz_dyn_lengths(b, tb, lane, nlen, ndist)) return false;
+  // a compressor sends no more lengths than it has to: the last one of either alphabet is not zero
+  if (tb.lens[nlen - 1] == 0 || (ndist > 1 && tb.lens[nlen + ndist - 1] == 0)) return false;
   uint32_t sl = 0, sd = 0, nd = 0;
   for (int s = lane; s < nlen; s += 32) { const int l = tb.lens[s]; if (l) sl += 32768u >> l; }
   for (int s = lane; s < ndist; s += 32) { const int l = tb.lens[nlen + s]; if (l) { sd += 32768u >> l; nd++; } }
@@ -138,10 +140,11 @@ __global__ void __launch_bounds__(32 * GZ_WARPS) gz_sync_kernel(const uint32_t* 
       if (ok) {  // the (HCLEN + 4) code lengths of 3 bits from bit 17, three at a time: the Kraft sum of a complete code is 128
         const int ncode = (int)((a >> 13) & 15u) + 4;
         u64 pre = (((((u64)bq << 32) | a) >> 17) | ((u64)cq << 47)) & ((1ull << (3 * ncode)) - 1ull);
+        ok = ncode == 4 || (pre >> (3 * (ncode - 1))) != 0;  // (the same for the code-length code: its last length sent is not zero)
         uint32_t kraft = 0;
 #pragma unroll
         for (int k = 0; k < 7; k++) { kraft += kraft3[(uint32_t)pre & 511u]; pre >>= 9; }
-        ok = kraft == 128u;
+        ok = ok && kraft == 128u;
       }
       uint32_t m = __ballot_sync(0xffffffffu, ok);
       while (m) {

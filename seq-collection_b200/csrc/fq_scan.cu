@@ -67,7 +67,10 @@ constexpr int KMAX = 63;                      // lines with more full groups are
 constexpr int LONG_CAP = TILE / (16 * (KMAX + 1)) + 2;
 constexpr int OPEN_CLIP = 1 << 30;            // line positions saturate here (>= POS_BINS is the overflow bin anyway)
 constexpr int MIN_SPAN_TILES = 32;            // spans are at least this long (1 MiB)
-constexpr int WAVE_SPAN_TILES = 512;          // ... and 16 MiB before a launch gets more spans than resident CTAs
+#ifndef FQ_WAVE_SPAN_TILES
+#define FQ_WAVE_SPAN_TILES 512
+#endif
+constexpr int WAVE_SPAN_TILES = FQ_WAVE_SPAN_TILES;  // ... and 16 MiB before a launch gets more spans than resident CTAs
 // Per-position quality sums, 16-bit pairs.  Q = position + 16.  Even Q: pair A = Q >> 1 of the EVEN table holds
 // (Q, Q+1); odd Q: pair A = (Q+1) >> 1 of the ODD table holds (Q, Q+1).  Pair A lives in cell (r, c) with
 // 8 c + r = A, r < 8, at word r * PT_STRIDE + c; a group adds its eight pairs at immediate offsets PT_STRIDE * i,

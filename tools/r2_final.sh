@@ -8,6 +8,8 @@ timeout 900 python bench.py > gpurun_out/r2_bench_n1.json 2> gpurun_out/bench_n1
 GZ_HOST=0 FQGPU_GZ_TRACE=1 timeout 600 python tools/gz_time.py 4000000 100 > gpurun_out/r2_gzip_trace.txt 2>&1
 GZ_HOST=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/r2_gzip_launches.csv python tools/gz_time.py 4000000 100 > gpurun_out/gz_ncu.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/r2_bgzf_launches.csv python tools/bgzf_time.py 4000000 > gpurun_out/bgzf_ncu.log 2>&1
+GZ_HOST=0 timeout 900 ncu --set full --import-source on --clock-control none -k regex:"gz_sync_kernel|gz_count_kernel|gz_write_kernel" -c 3 -f -o gpurun_out/r2_gzip_kernels python tools/gz_time.py 4000000 100 > gpurun_out/gz_ncu_full.log 2>&1
+timeout 900 ncu --set full --import-source on --clock-control none -k regex:fq_meta_seg_kernel -s 12 -c 1 -f -o gpurun_out/r2_meta_seg python bench.py --steps 1 --warmup 1 --records 20000000 --meta-records 20000000 --no-ont --no-gz --no-ingest --no-e2e --no-cpu-baseline > gpurun_out/meta_ncu2.log 2>&1
 python - <<'PY'
 import csv, collections
 for name in ('gzip', 'bgzf'):
