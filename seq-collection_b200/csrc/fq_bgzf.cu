@@ -2,7 +2,8 @@
 // the scan kernels.
 //
 // The reference inflates .gz input on the host, one byte stream through zlib (src/utils/gzip_stream.nim:16-17,
-// src/fq_count.nim:32); a single gzip member cannot be inflated in parallel.  A BGZF file is a concatenation of
+// src/fq_count.nim:32); a single gzip member has to be guessed at to be inflated in parallel (fq_gzip.cu does that).
+// A BGZF file needs no guessing: it is a concatenation of
 // gzip members of at most 64 KiB, each with its compressed size in the header's "BC" extra field and its
 // uncompressed size in the trailer, so every member is an independent DEFLATE stream with a known output
 // offset: the host only walks the member headers, the compressed bytes go to the GPU as they are, and ONE WARP
@@ -10,8 +11,11 @@
 // output buffer.  A DEFLATE stream is serial, and 32 members sharing a warp run one after the other (measured
 // 1.01 active threads per instruction), so each member gets its own warp; all 32 lanes decode the same bits in
 // lockstep (broadcast loads, no divergence: 32 identical lanes cost what one costs), which leaves the warp free for
-// the parallel parts -- filling the per-warp lookup tables in shared memory (10-bit literal/length, 8-bit distance;
-// longer codes walk the canonical code), copying matches 32 bytes per step, the CRC.  The output buffer, which fqgpu_scan_device then scans like any HBM-resident input.  Anything that is not well-formed BGZF makes the caller fall back to the zlib path.
+// the parallel parts -- filling the per-warp lookup tables in shared memory (fq_inflate.cuh: 9-bit literal/length,
+// 8-bit distance, one 32-bit entry per symbol with everything the loop needs; longer codes walk the canonical code),
+// copying matches 32 bytes per step, the CRC.  The output is the buffer fqgpu_scan_device then scans like any
+// HBM-resident input.  Anything that is not well-formed BGZF makes the caller take the next path (gzip on the device,
+// then zlib).
 #include <cuda_runtime.h>
 #include <stdint.h>
 

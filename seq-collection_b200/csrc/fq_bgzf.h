@@ -15,7 +15,7 @@ struct BgzfMember {
   unsigned int pad;
 };
 
-// One warp per member (lane 0 decodes); status[i] = 0 or the reason member i could not be inflated.
+// One warp per member (all lanes in lockstep); status[i] = 0 or the reason member i could not be inflated.
 cudaError_t launch_bgzf_inflate(const uint8_t* d_comp, const BgzfMember* d_members, int n, uint8_t* d_out, uint32_t* d_status,
                                 cudaStream_t st);
 
