@@ -518,24 +518,29 @@ static const size_t kBgzfBatchBytes = (size_t)64 << 20;  // compressed bytes per
 static const size_t kBgzfBatchMembers = 32768;           // members (= inflating warps) per batch
 
 // the two staging slots for compressed input (shared by the BGZF and the gzip path)
-static cudaError_t ensure_comp_slots(fqgpu_ctx* ctx, size_t want) {
+static cudaError_t ensure_comp_slots(fqgpu_ctx* ctx, size_t want, int nslots) {
   cudaError_t e = cudaSuccess;
   if (!ctx->cstream && (e = cudaStreamCreateWithFlags(&ctx->cstream, cudaStreamNonBlocking)) != cudaSuccess) return e;
   for (auto& c : ctx->comp) {
     if (!c.h2d && (e = cudaEventCreateWithFlags(&c.h2d, cudaEventDisableTiming)) != cudaSuccess) return e;
     if (!c.done && (e = cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming)) != cudaSuccess) return e;
   }
-  if (ctx->comp_cap >= want) return cudaSuccess;
-  if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return e;
-  ctx->comp_cap = 0;
-  for (auto& c : ctx->comp) {
-    if (c.h) cudaFreeHost(c.h);
-    cudaFree(c.d);
-    c.h = nullptr; c.d = nullptr;
-    if ((e = cudaMallocHost(&c.h, want)) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&c.d, want + 64)) != cudaSuccess) return e;
+  if (ctx->comp_cap < want) {  // (both slots have the same size)
+    if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return e;
+    for (auto& c : ctx->comp) {
+      if (c.h) cudaFreeHost(c.h);
+      cudaFree(c.d);
+      c.h = nullptr; c.d = nullptr;
+    }
+    ctx->comp_cap = want;
   }
-  ctx->comp_cap = want;
+  // the second slot only when a second batch is read ahead: pinned memory is the most expensive thing to allocate here
+  for (int k = 0; k < nslots && k < 2; k++) {
+    fqgpu_ctx::CompSlot& c = ctx->comp[k];
+    if (c.h && c.d) continue;
+    if (!c.h && (e = cudaMallocHost(&c.h, ctx->comp_cap)) != cudaSuccess) { ctx->comp_cap = 0; return e; }
+    if (!c.d && (e = cudaMalloc(&c.d, ctx->comp_cap + 64)) != cudaSuccess) { ctx->comp_cap = 0; return e; }
+  }
   return cudaSuccess;
 }
 
@@ -555,7 +560,7 @@ static int count_bgzf(fqgpu_ctx* ctx, const char* path) {
 #define CU_B(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return bail(FQGPU_ECUDA); } } while (0)
   CU_B(cudaSetDevice(ctx->device));
   const size_t batch_cap = env_size("FQGPU_BGZF_BATCH_MB", kBgzfBatchBytes >> 20, 1, 1024) << 20;
-  CU_B(ensure_comp_slots(ctx, fsize < batch_cap ? ((fsize + 4095) & ~(size_t)4095) : batch_cap));
+  CU_B(ensure_comp_slots(ctx, fsize < batch_cap ? ((fsize + 4095) & ~(size_t)4095) : batch_cap, fsize > batch_cap ? 2 : 1));
   if (ctx->members_cap < kBgzfBatchMembers) {
     for (auto& c : ctx->comp) {
       CU_B(cudaMallocHost(&c.h_members, kBgzfBatchMembers * sizeof(fq::BgzfMember)));
@@ -579,6 +584,7 @@ static int count_bgzf(fqgpu_ctx* ctx, const char* path) {
   size_t pos = 0;
   for (int k = 0; pos < fsize; k++) {
     const int s = k & 1;
+    if (s && !ctx->comp[1].h) CU_B(ensure_comp_slots(ctx, ctx->comp_cap, 2));  // (a second batch after all: many tiny members)
     fqgpu_ctx::CompSlot& c = ctx->comp[s];
     if (int r = settle(s)) return bail(r);  // (also: the slot's buffers are free again)
     const size_t want_now = fsize - pos < ctx->comp_cap ? fsize - pos : ctx->comp_cap;
@@ -709,7 +715,7 @@ static int count_gzip(fqgpu_ctx* ctx, const char* path) {
 #define CU_ALLOC(call) do { cudaError_t e_ = (call); if (e_ == cudaErrorMemoryAllocation) { cudaGetLastError(); return bail(1); } if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return bail(FQGPU_ECUDA); } } while (0)
   CU_B(cudaSetDevice(ctx->device));
   const size_t batch_cap = env_size("FQGPU_GZ_BATCH_MB", 512, 1, 1024) << 20;
-  CU_ALLOC(ensure_comp_slots(ctx, fsize + 4096 < batch_cap ? ((fsize + 8191) & ~(size_t)4095) : batch_cap));
+  CU_ALLOC(ensure_comp_slots(ctx, fsize + 4096 < batch_cap ? ((fsize + 8191) & ~(size_t)4095) : batch_cap, 1));
   if (!ctx->d_gzchunks) {
     CU_B(cudaMalloc(&ctx->d_gzchunks, (size_t)fq::GZ_MAX_CHUNKS * sizeof(fq::GzChunk)));
     CU_B(cudaMalloc(&ctx->d_gzorder, (size_t)fq::GZ_MAX_CHUNKS * sizeof(uint32_t)));
@@ -798,6 +804,7 @@ static int count_gzip(fqgpu_ctx* ctx, const char* path) {
     size_t next_fpos = 0, next_got = 0;
     const bool ahead = fpos + got < fsize;
     if (ahead) {
+      CU_ALLOC(ensure_comp_slots(ctx, ctx->comp_cap, 2));
       next_fpos = (fpos + got - (got / 2 < kRewind ? got / 2 : kRewind)) & ~(size_t)4095;
       next_got = load(s ^ 1, next_fpos);
       if (next_got == SIZE_MAX) return bail(1);
@@ -893,9 +900,10 @@ static int count_gzip(fqgpu_ctx* ctx, const char* path) {
       }
     }
     if (!more) break;
-    // the bytes from there: already on their way if the guess covered the position
-    s ^= 1;
+    // the bytes from there: already on their way into the other slot if the guess covered the position; if not, they
+    // are read into this one again (its kernels are through: the sync above)
     if (ahead && (size_t)(abs_bit >> 3) >= next_fpos && (abs_bit >> 3) + 16 < (u64)next_fpos + next_got) {
+      s ^= 1;
       fpos = next_fpos; got = next_got;
     } else {
       fpos = (size_t)(abs_bit >> 3) & ~(size_t)4095;
@@ -1147,7 +1155,15 @@ int fqgpu_count_files(const fqgpu_config* cfg, const char* const* paths, const i
     if (ndev <= 0) { g_create_error = "fqgpu_count_files: no CUDA device"; for (int i = 0; i < n; i++) rc[i] = FQGPU_ECUDA; return FQGPU_ECUDA; }
     dev0 = 0;
   }
-  int nthr = n_threads > 0 ? n_threads : (n < 8 ? n : 8);
+  // default: up to 8 files in flight; `.gz` files, which are inflated on the device, keep the GPU busy one at a time and
+  // pay for every context's buffers: two in flight (one is read while the other one's kernels run)
+  bool any_gz = false;
+  for (int i = 0; i < n && !any_gz; i++) {
+    const size_t L = paths[i] ? strlen(paths[i]) : 0;
+    any_gz = as_gz ? as_gz[i] != 0 : (L >= 3 && strcmp(paths[i] + L - 3, ".gz") == 0);
+  }
+  const int dflt = any_gz && !getenv("FQGPU_NO_GZIP_DEVICE") ? 2 * ndev : 8;
+  int nthr = n_threads > 0 ? n_threads : (n < dflt ? n : dflt);
   if (nthr > n) nthr = n;
   for (int i = 0; i < n; i++) { rc[i] = FQGPU_ECUDA; memset(&out[i], 0, sizeof(fqgpu_stats)); }
   std::atomic<int> next(0);

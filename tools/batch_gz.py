@@ -41,7 +41,7 @@ ctx.close()
 out = {"config": "%d files x gzip -6 of synthetic Illumina 2x150 bp, %d records each (%.2f GB raw in total)" % (a.files, a.records, a.files * n / 1e9),
        "host_cores": os.cpu_count(), "runs": {}}
 want = [O.fq_count_row(O.count_file(p, 0)) for p in paths]
-for threads in (1, a.files):
+for threads in sorted({1, 2, 4, a.files}):
     best = 1e9
     for _ in range(2):
         t0 = time.perf_counter()
