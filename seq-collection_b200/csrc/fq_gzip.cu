@@ -127,32 +127,48 @@ __global__ void __launch_bounds__(32 * GZ_WARPS) gz_sync_kernel(const uint32_t* 
     if (lo <= start_bit) lo = start_bit + 1;
     const u64 last = end_bits > 96 ? end_bits - 96 : 0;  // a block header and an end-of-block do not fit behind this
     if (hi > last) hi = last;
-    const uint32_t* p = words + (lo >> 5);
-    uint32_t w0 = p < wend ? __ldg(p) : 0u, w1 = p + 1 < wend ? __ldg(p + 1) : 0u, w2 = p + 2 < wend ? __ldg(p + 2) : 0u,
-             w3 = p + 3 < wend ? __ldg(p + 3) : 0u;
-    for (u64 t0 = lo & ~31ull; t0 < hi; t0 += 32, p++) {
-      const uint32_t w4 = p + 4 < wend ? __ldg(p + 4) : 0u;  // (for the next round)
-      const uint32_t a = __funnelshift_r(w0, w1, lane), bq = __funnelshift_r(w1, w2, lane), cq = __funnelshift_r(w2, w3, lane);
-      w0 = w1; w1 = w2; w2 = w3; w3 = w4;
-      const u64 t = t0 + (u64)lane;
-      // BFINAL = 0, BTYPE = 2 (bits 1-2, LSB first), HLIT <= 29, HDIST <= 29
-      bool ok = (a & 7u) == 4u && ((a >> 3) & 31u) <= 29u && ((a >> 8) & 31u) <= 29u && t >= lo && t < hi;
-      if (ok) {  // the (HCLEN + 4) code lengths of 3 bits from bit 17, three at a time: the Kraft sum of a complete code is 128
+    // A round covers 32 words = 1024 positions; every lane takes the 32 positions that start in ITS word.  The
+    // three header bits (BFINAL = 0, BTYPE = 2: bits 0, 0, 1 from the position on) leave about four of them; for each
+    // the lane checks the rest of the fixed bits and the Kraft sum of the code-length code (the (HCLEN + 4) lengths of
+    // 3 bits from bit 17, three per table lookup: a complete code sums to 128; the last one sent is not zero), and
+    // keeps a bit mask of the survivors.  (Before: one position per lane and round -- four instructions per position
+    // where this takes a tenth of that.)  The few survivors are parsed by the whole warp, in stream order.
+    for (u64 r0 = lo & ~1023ull; r0 < hi && found == GZ_NONE; r0 += 1024) {
+      const u64 t0 = r0 + 32ull * (u64)lane;  // the first position of this lane's word
+      const uint32_t* q = words + (t0 >> 5);
+      uint32_t x[5];
+#pragma unroll
+      for (int i = 0; i < 5; i++) x[i] = q + i < wend ? __ldg(q + i) : 0u;
+      // candidates: bit p of the word and the two bits above it are 0, 0, 1
+      uint32_t cand = ~x[0] & ~__funnelshift_r(x[0], x[1], 1) & __funnelshift_r(x[0], x[1], 2);
+      if (t0 < lo) cand &= t0 + 32 <= lo ? 0u : ~((1u << (uint32_t)(lo - t0)) - 1u);
+      if (t0 + 32 > hi) cand &= t0 >= hi ? 0u : (1u << (uint32_t)(hi - t0)) - 1u;
+      uint32_t surv = 0;
+      while (cand) {
+        const uint32_t j = (uint32_t)__ffs((int)cand) - 1u;
+        cand &= cand - 1u;
+        const uint32_t a = __funnelshift_r(x[0], x[1], j), bq = __funnelshift_r(x[1], x[2], j), cq = __funnelshift_r(x[2], x[3], j);
+        if (((a >> 3) & 31u) > 29u || ((a >> 8) & 31u) > 29u) continue;  // HLIT, HDIST
         const int ncode = (int)((a >> 13) & 15u) + 4;
         u64 pre = (((((u64)bq << 32) | a) >> 17) | ((u64)cq << 47)) & ((1ull << (3 * ncode)) - 1ull);
-        ok = ncode == 4 || (pre >> (3 * (ncode - 1))) != 0;  // (the same for the code-length code: its last length sent is not zero)
+        if (ncode != 4 && (pre >> (3 * (ncode - 1))) == 0) continue;
         uint32_t kraft = 0;
 #pragma unroll
         for (int k = 0; k < 7; k++) { kraft += kraft3[(uint32_t)pre & 511u]; pre >>= 9; }
-        ok = ok && kraft == 128u;
+        if (kraft == 128u) surv |= 1u << j;
       }
-      uint32_t m = __ballot_sync(0xffffffffu, ok);
-      while (m) {
-        const int j = __ffs((int)m) - 1;
-        m &= m - 1;
-        if (gz_header_plausible(words, wend, t0 + (u64)j, tables[warp], lane)) { found = t0 + (u64)j; break; }
+      uint32_t lanes = __ballot_sync(0xffffffffu, surv != 0u);
+      while (lanes && found == GZ_NONE) {
+        const int l = __ffs((int)lanes) - 1;
+        lanes &= lanes - 1;
+        uint32_t sv = __shfl_sync(0xffffffffu, surv, l);
+        while (sv) {
+          const uint32_t j = (uint32_t)__ffs((int)sv) - 1u;
+          sv &= sv - 1u;
+          const u64 t = r0 + 32ull * (u64)l + j;
+          if (gz_header_plausible(words, wend, t, tables[warp], lane)) { found = t; break; }
+        }
       }
-      if (found != GZ_NONE) break;
     }
   }
   if (lane == 0) {
