@@ -101,17 +101,15 @@ __device__ __noinline__ int bgzf_inflate_member(const uint8_t* __restrict__ comp
     }
     for (;;) {  // literals and matches of this DEFLATE block
       const uint32_t e = huff_peek<HUFF_LITLEN, LBITS>(b, t.lit, t.lcount, t.lsym);
-      const uint32_t kind = e & HK_MASK;
-      if (kind == HK_LITERAL) {
+      if (!(e & HK_MASK)) {  // a literal
         huff_take(b, e);
         if (produced >= cap) return BGZF_ESIZE;
         if (lane == 0) o[produced] = (uint8_t)(e >> 16);
         produced++;
-      } else if (kind == HK_END) {
-        huff_take(b, e);
+      } else if ((e & HK_MASK) != HK_MATCH) {
+        if ((e & HK_MASK) == HK_INVALID) return BGZF_ECODE;
+        huff_take(b, e);  // end of block
         break;
-      } else if (kind == HK_INVALID) {
-        return BGZF_ECODE;
       } else {
         const uint32_t len = huff_take(b, e);  // (>= 33 bits were there: 15 + 5 used)
         const uint32_t de = huff_peek<HUFF_DIST, DBITS>(b, t.dist, t.dcount, t.dsym);

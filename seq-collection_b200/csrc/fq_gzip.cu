@@ -283,16 +283,14 @@ __device__ __noinline__ void gz_chunk(const uint32_t* __restrict__ words, u64 nb
           if (b.w > wstop) continue;
         }
         const uint32_t e = huff_peek<HUFF_LITLEN, LBITS>(b, t.lit, t.lcount, t.lsym);
-        const uint32_t kind = e & HK_MASK;
-        if (kind == HK_LITERAL) {
+        if (!(e & HK_MASK)) {  // a literal
           huff_take(b, e);
           if (WRITE && lane == 0) m[produced] = (uint16_t)(e >> 16);
           produced++;
-        } else if (kind == HK_END) {
-          huff_take(b, e);
+        } else if ((e & HK_MASK) != HK_MATCH) {
+          if ((e & HK_MASK) == HK_INVALID) { flags |= GZC_ERROR; stop = true; }
+          else huff_take(b, e);  // end of block
           break;
-        } else if (kind == HK_INVALID) {
-          flags |= GZC_ERROR; stop = true; break;
         } else {
           const uint32_t len = huff_take(b, e);  // (>= 33 bits were there: 15 + 5 used)
           const uint32_t de = huff_peek<HUFF_DIST, DBITS>(b, t.dist, t.dcount, t.dsym);
