@@ -161,6 +161,8 @@ unsigned long long fqgpu_bgzf_members(const fqgpu_ctx* ctx);
  * search proposed that were not block boundaries. */
 unsigned long long fqgpu_gzip_chunks(const fqgpu_ctx* ctx);
 unsigned long long fqgpu_gzip_false_starts(const fqgpu_ctx* ctx);
+/* batches of the gzip path whose symbols did not fit the one-pass arena and were decoded a second time */
+unsigned long long fqgpu_gzip_second_passes(const fqgpu_ctx* ctx);
 
 /* Many files at once (replaces the sequential `for fastq in files` loop of sc.nim:115-116).
  * Files are independent streams, so up to n_threads host threads (0 = min(n, 8)) each own a private context --

@@ -119,6 +119,7 @@ def load_library(path: str | None = None):
         "fqgpu_bgzf_members": (C.c_ulonglong, [vp]),
         "fqgpu_gzip_chunks": (C.c_ulonglong, [vp]),
         "fqgpu_gzip_false_starts": (C.c_ulonglong, [vp]),
+        "fqgpu_gzip_second_passes": (C.c_ulonglong, [vp]),
         "fqgpu_meta_file_as": (i32, [vp, C.c_char_p, i32, C.POINTER(Stats)]),
         "fqgpu_count_file_sharded": (i32, [C.POINTER(Config), C.c_char_p, C.POINTER(i32), i32, C.POINTER(Stats)]),
         "fqgpu_count_files": (i32, [C.POINTER(Config), C.POINTER(C.c_char_p), C.POINTER(i32), i32, i32, C.POINTER(Stats), C.POINTER(i32)]),
@@ -168,7 +169,7 @@ def load_library(path: str | None = None):
 EXPORTED_SYMBOLS = [
     "fqgpu_abi_version", "fqgpu_stats_size", "fqgpu_build_info", "fqgpu_device_count", "fqgpu_create",
     "fqgpu_destroy", "fqgpu_last_error", "fqgpu_acquire", "fqgpu_submit", "fqgpu_finish", "fqgpu_reset",
-    "fqgpu_scan_host", "fqgpu_count_host", "fqgpu_count_file", "fqgpu_count_file_as", "fqgpu_count_files", "fqgpu_bgzf_members", "fqgpu_gzip_chunks", "fqgpu_gzip_false_starts", "fqgpu_meta_file_as", "fqgpu_count_file_sharded", "fqgpu_scan_device", "fqgpu_count_device",
+    "fqgpu_scan_host", "fqgpu_count_host", "fqgpu_count_file", "fqgpu_count_file_as", "fqgpu_count_files", "fqgpu_bgzf_members", "fqgpu_gzip_chunks", "fqgpu_gzip_false_starts", "fqgpu_gzip_second_passes", "fqgpu_meta_file_as", "fqgpu_count_file_sharded", "fqgpu_scan_device", "fqgpu_count_device",
     "fqgpu_shard_block_words", "fqgpu_shard_begin", "fqgpu_shard_export", "fqgpu_shard_combine",
     "fqgpu_shard_rescan", "fqgpu_shard_combine_host", "fqgpu_count_pair", "fqgpu_ipc_handle_bytes", "fqgpu_shard_xbuf_bytes", "fqgpu_shard_exchange_create",
     "fqgpu_shard_exchange_open", "fqgpu_shard_xbuf", "fqgpu_shard_exchange_set_peers", "fqgpu_shard_exchange_start", "fqgpu_shard_exchange_finish",
@@ -283,6 +284,10 @@ class FqGpu:
     def gzip_chunks(self) -> int:
         """Chunks of ordinary gzip input that the last count_file() inflated on the device (0: host zlib ran)."""
         return int(self.lib.fqgpu_gzip_chunks(self._ctx))
+
+    def gzip_second_passes(self) -> int:
+        """Batches of the last gzip input whose symbols did not fit the one-pass arena (they were decoded a second time)."""
+        return int(self.lib.fqgpu_gzip_second_passes(self._ctx))
 
     def gzip_false_starts(self) -> int:
         """Block starts the device search proposed that turned out not to be block boundaries (they are skipped)."""

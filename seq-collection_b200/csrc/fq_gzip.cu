@@ -180,13 +180,20 @@ __global__ void __launch_bounds__(32 * GZ_WARPS) gz_sync_kernel(const uint32_t* 
 }
 
 // ---- 2. / 4. the chunk decoder -----------------------------------------------------------------------------------------
-// COUNT (WRITE = false): decode from the chunk's start until a block ends on a later chunk's start (or the
-// stream / the batch ends); nothing is written.  WRITE: decode the same blocks again, up to the recorded end, as
-// 16-bit symbols into m[]: a byte, or 0x8000 | (position in the 32 KiB window before the chunk).  With `win` the
-// window is known (the batch's first chunk) and bytes are taken from it directly.
-template <bool WRITE>
+// GZ_COUNT: decode from the chunk's start until a block ends on a later chunk's start (or the stream / the batch
+// ends); nothing is written.  GZ_WRITE: decode the same blocks again, up to the recorded end, as 16-bit symbols into
+// m[]: a byte, or 0x8000 | (position in the 32 KiB window before the chunk).  With `win` the window is known (the
+// batch's first chunk) and bytes are taken from it directly.  GZ_BOTH: count AND write in one pass -- the symbols go
+// to the chunk's own slot of an over-sized arena (`cap` symbols: up to the slot of the next chunk that found a
+// start); a chunk whose output does not fit there (a stretch that compresses better than the arena allows for, a
+// false start run over) says so (GZC_REWRITE) and the batch takes the second pass after all.
+enum { GZ_COUNT = 0, GZ_WRITE = 1, GZ_BOTH = 2 };
+template <int MODE>
 __device__ __noinline__ void gz_chunk(const uint32_t* __restrict__ words, u64 nbytes, u64 chunk_bits, GzChunk* chunks, int nchunks, int c,
-                                      uint16_t* m, const uint8_t* __restrict__ win, uint32_t wvalid, WarpTables& t, int lane, uint32_t* err) {
+                                      uint16_t* m, u64 stride, const uint8_t* __restrict__ win, uint32_t wvalid, WarpTables& t, int lane,
+                                      uint32_t* err) {
+  constexpr bool WRITE = MODE == GZ_WRITE;   // the second pass: where to stop is known
+  constexpr bool STORE = MODE != GZ_COUNT;   // symbols are written
   const bool known = c == 0;  // the batch's first chunk: the window before it is known (wvalid bytes of it exist)
   const GzChunk ck = chunks[c];
   if (ck.start_bit == GZ_NONE) return;
@@ -208,6 +215,9 @@ __device__ __noinline__ void gz_chunk(const uint32_t* __restrict__ words, u64 nb
   // (w - w0) <= pos / 32 + 2 always, so b.w > wstop proves pos > limit
   const uint32_t* wstop = limit == GZ_NONE ? wend + 2 : words + (limit >> 5) + 2;
   uint32_t produced = 0, need = 0, flags = 0;
+  // (GZ_BOTH) room for the chunk's symbols: its own slot and those of the chunks behind it that found no start
+  const u64 cap = MODE == GZ_BOTH ? (u64)(nextc - c) * stride : ~0ull;
+  bool writing = STORE;
   u64 bpos = ck.start_bit;  // the last block boundary and the bytes produced up to it
   uint32_t bout = 0;
   int passed = 0, land = -1;
@@ -256,7 +266,8 @@ __device__ __noinline__ void gz_chunk(const uint32_t* __restrict__ words, u64 nb
         break;
       }
       if (produced > GZ_MAX_OUT - len) { flags |= GZC_GIVEUP; break; }
-      if (WRITE) for (uint32_t k = (uint32_t)lane; k < len; k += 32u) m[produced + k] = bytes[src + k];
+      if (STORE && writing && (u64)produced + len > cap) { writing = false; flags |= GZC_REWRITE; }
+      if (STORE && writing) for (uint32_t k = (uint32_t)lane; k < len; k += 32u) m[produced + k] = bytes[src + k];
       produced += len;
       b.init(words, wend, (src + len) * 8ull);
     } else {
@@ -285,7 +296,10 @@ __device__ __noinline__ void gz_chunk(const uint32_t* __restrict__ words, u64 nb
         const uint32_t e = huff_peek<HUFF_LITLEN, LBITS>(b, t.lit, t.lcount, t.lsym);
         if (!(e & HK_MASK)) {  // a literal
           huff_take(b, e);
-          if (WRITE && lane == 0) m[produced] = (uint16_t)(e >> 16);
+          if (STORE && writing) {
+            if ((u64)produced < cap) { if (lane == 0) m[produced] = (uint16_t)(e >> 16); }
+            else { writing = false; flags |= GZC_REWRITE; }
+          }
           produced++;
         } else if ((e & HK_MASK) != HK_MATCH) {
           if ((e & HK_MASK) == HK_INVALID) { flags |= GZC_ERROR; stop = true; }
@@ -302,7 +316,8 @@ __device__ __noinline__ void gz_chunk(const uint32_t* __restrict__ words, u64 nb
             need = back > need ? back : need;
           }
           if (produced > GZ_MAX_OUT) { flags |= GZC_GIVEUP; stop = true; break; }
-          if (WRITE) {
+          if (STORE && writing && (u64)produced + len > cap) { writing = false; flags |= GZC_REWRITE; }
+          if (STORE && writing) {
             __syncwarp();  // earlier symbols (lane 0's literals, other lanes' match symbols) are visible to every lane
             for (uint32_t k = (uint32_t)lane; k < len; k += 32u) {
               const uint32_t kk = dist >= len ? k : k % dist;  // a run shorter than its length repeats with period dist
@@ -343,7 +358,7 @@ __global__ void __launch_bounds__(32 * GZ_WARPS, GZ_MINB) gz_count_kernel(const 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x * GZ_WARPS + warp;
   if (c >= nchunks) return;
-  gz_chunk<false>(words, nbytes, chunk_bits, chunks, nchunks, c, nullptr, nullptr, wvalid, tables[warp], lane, nullptr);
+  gz_chunk<GZ_COUNT>(words, nbytes, chunk_bits, chunks, nchunks, c, nullptr, 0, nullptr, wvalid, tables[warp], lane, nullptr);
 }
 
 __global__ void __launch_bounds__(32 * GZ_WARPS, GZ_MINB) gz_write_kernel(const uint32_t* __restrict__ words, u64 nbytes, u64 chunk_bits, GzChunk* chunks,
@@ -353,20 +368,31 @@ __global__ void __launch_bounds__(32 * GZ_WARPS, GZ_MINB) gz_write_kernel(const 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x * GZ_WARPS + warp;
   if (c >= nchunks) return;
-  gz_chunk<true>(words, nbytes, chunk_bits, chunks, nchunks, c, markers + chunks[c].out_off, window, wvalid, tables[warp], lane, err);
+  gz_chunk<GZ_WRITE>(words, nbytes, chunk_bits, chunks, nchunks, c, markers + chunks[c].out_off, 0, window, wvalid, tables[warp], lane, err);
+}
+
+__global__ void __launch_bounds__(32 * GZ_WARPS, GZ_MINB) gz_both_kernel(const uint32_t* __restrict__ words, u64 nbytes, u64 chunk_bits, GzChunk* chunks,
+                                                                        int nchunks, uint16_t* arena, u64 stride, const uint8_t* __restrict__ window,
+                                                                        uint32_t wvalid) {
+  __shared__ WarpTables tables[GZ_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * GZ_WARPS + warp;
+  if (c >= nchunks) return;
+  gz_chunk<GZ_BOTH>(words, nbytes, chunk_bits, chunks, nchunks, c, arena + (u64)c * stride, stride, window, wvalid, tables[warp], lane, nullptr);
 }
 
 // ---- 3. the chain ------------------------------------------------------------------------------------------------------
 // One CTA.  Thread 0 follows the landings through shared memory; then all threads give the chain's chunks their
 // output offsets (an exclusive scan) and check them.
 constexpr int CHAIN_THREADS = 1024;
-__global__ void __launch_bounds__(CHAIN_THREADS) gz_chain_kernel(GzChunk* chunks, int nchunks, u64 prior_out, GzResult* res, uint32_t* order, u64* coff) {
+__global__ void __launch_bounds__(CHAIN_THREADS) gz_chain_kernel(GzChunk* chunks, int nchunks, u64 prior_out, GzResult* res, uint32_t* order, u64* coff,
+                                                                 u64 stride, u64* sbase) {
   extern __shared__ int land_s[];  // nchunks landings
-  __shared__ uint32_t nchain_s, bad_s;
+  __shared__ uint32_t nchain_s, bad_s, rewrite_s;
   __shared__ u64 wsum[CHAIN_THREADS / 32], carry_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int c = tid; c < nchunks; c += CHAIN_THREADS) land_s[c] = chunks[c].land;
-  if (tid == 0) { bad_s = 0; carry_s = 0; }
+  if (tid == 0) { bad_s = 0; carry_s = 0; rewrite_s = 0; }
   __syncthreads();
   if (tid == 0) {
     uint32_t n = 0;
@@ -403,6 +429,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS) gz_chain_kernel(GzChunk* chunks
       chunks[c].out_off = off;
       chunks[c].flags = flags | GZC_CHAIN;
       coff[i] = off;
+      if (stride) sbase[i] = (u64)c * stride - off;  // (wraps when off is the larger: added back modulo 2^64)
+      if (flags & GZC_REWRITE) atomicOr(&rewrite_s, 1u);
       if (i > 0 && (u64)need > off + prior_out) atomicOr(&bad_s, 1u);  // a match reaches behind the first byte of the stream
       if (i + 1 == nchain) {
         coff[nchain] = off + len;
@@ -419,7 +447,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS) gz_chain_kernel(GzChunk* chunks
   __syncthreads();
   if (lane == 0 && passed) atomicAdd(&passed_s, passed);
   __syncthreads();
-  if (tid == 0) { res->status = bad_s ? GZR_BROKEN : GZR_OK; res->nchain = nchain; res->passed = passed_s; }
+  if (tid == 0) { res->status = bad_s ? GZR_BROKEN : GZR_OK; res->nchain = nchain; res->passed = passed_s; res->rewrite = rewrite_s; res->pad = 0; }
 }
 
 // ---- 5. windows ----------------------------------------------------------------------------------------------------------
@@ -445,8 +473,8 @@ constexpr size_t win_smem_bytes() { return 2 * GZ_WINDOW * sizeof(T) + 2 * WIN_S
 // SYMBOLIC: CTA g walks chain chunks [g K, min((g + 1) K, nchain)); its symbols are the chunks' tails in `markers`.
 // otherwise: one CTA walks the groups; the symbols of step g are the row grows[g].
 template <bool SYMBOLIC>
-__global__ void __launch_bounds__(WIN_THREADS) gz_rows_kernel(const u64* __restrict__ coff, uint32_t nchain, uint32_t K, uint32_t ngroups,
-                                                              const uint16_t* __restrict__ markers, uint16_t* __restrict__ symrows,
+__global__ void __launch_bounds__(WIN_THREADS) gz_rows_kernel(const u64* __restrict__ coff, const u64* __restrict__ sbase, uint32_t nchain, uint32_t K,
+                                                              uint32_t ngroups, const uint16_t* __restrict__ markers, uint16_t* __restrict__ symrows,
                                                               uint16_t* __restrict__ grows, uint8_t* __restrict__ trows) {
   typedef typename std::conditional<SYMBOLIC, uint16_t, uint8_t>::type T;
   extern __shared__ __align__(128) uint8_t win_smem[];
@@ -480,8 +508,10 @@ __global__ void __launch_bounds__(WIN_THREADS) gz_rows_kernel(const u64* __restr
   };
   // the output range of step k: a chunk of the chain, or (group walk) a whole row that replaces the window
   auto range_of = [&](uint32_t k, u64& off, u64& end) {
-    if (SYMBOLIC) { off = coff[first + k]; end = coff[first + k + 1]; }
-    else { off = 0; end = GZ_WINDOW; }
+    if (SYMBOLIC) {  // (as indices into `markers`: output positions, or -- one-pass mode -- positions in the arena)
+      const u64 sh = sbase ? sbase[first + k] : 0ull;
+      off = coff[first + k] + sh; end = coff[first + k + 1] + sh;
+    } else { off = 0; end = GZ_WINDOW; }
   };
 
   if (SYMBOLIC) {
@@ -550,9 +580,10 @@ __global__ void __launch_bounds__(WIN_THREADS) gz_rows_kernel(const u64* __restr
 // ---- 6. resolve ------------------------------------------------------------------------------------------------------------
 constexpr int RES_THREADS = 256;
 constexpr uint32_t RES_SLICE = RES_THREADS * 8 * 8;  // output positions per CTA step
-__global__ void __launch_bounds__(RES_THREADS) gz_resolve_kernel(const uint16_t* __restrict__ markers, const uint16_t* __restrict__ symrows,
-                                                                 const uint8_t* __restrict__ trows, uint32_t K, const u64* __restrict__ coff,
-                                                                 uint32_t nchain, u64 total, uint8_t* __restrict__ out) {
+template <bool ARENA>
+__global__ void __launch_bounds__(RES_THREADS) gz_resolve_kernel(const uint16_t* __restrict__ markers, const u64* __restrict__ sbase,
+                                                                 const uint16_t* __restrict__ symrows, const uint8_t* __restrict__ trows, uint32_t K,
+                                                                 const u64* __restrict__ coff, uint32_t nchain, u64 total, uint8_t* __restrict__ out) {
   __shared__ uint32_t first_s;
   const u64 nslices = (total + RES_SLICE - 1) / RES_SLICE;
   for (u64 sl = blockIdx.x; sl < nslices; sl += gridDim.x) {
@@ -566,18 +597,23 @@ __global__ void __launch_bounds__(RES_THREADS) gz_resolve_kernel(const uint16_t*
     __syncthreads();
     uint32_t i = first_s;
     u64 next = coff[i + 1];
+    u64 sh = ARENA ? sbase[i] : 0ull;  // (one-pass mode: the chunk's symbols are in its slot of the arena)
 #pragma unroll 2
     for (uint32_t r = 0; r < 8; r++) {
       const u64 p0 = s0 + ((u64)r * RES_THREADS + threadIdx.x) * 8;
       if (p0 >= total) break;
-      const uint4 q = *reinterpret_cast<const uint4*>(markers + p0);  // (the buffer is padded to a multiple of 8 symbols)
-      const uint32_t s[8] = {q.x & 0xFFFFu, q.x >> 16, q.y & 0xFFFFu, q.y >> 16, q.z & 0xFFFFu, q.z >> 16, q.w & 0xFFFFu, q.w >> 16};
+      uint32_t s[8];
+      if (!ARENA) {
+        const uint4 q = *reinterpret_cast<const uint4*>(markers + p0);  // (the buffer is padded to a multiple of 8 symbols)
+        s[0] = q.x & 0xFFFFu; s[1] = q.x >> 16; s[2] = q.y & 0xFFFFu; s[3] = q.y >> 16;
+        s[4] = q.z & 0xFFFFu; s[5] = q.z >> 16; s[6] = q.w & 0xFFFFu; s[7] = q.w >> 16;
+      }
       u64 packed = 0;
 #pragma unroll
       for (int k = 0; k < 8; k++) {
         const u64 p = p0 + (u64)k;
-        while (p >= next && i + 1 < nchain) { i++; next = coff[i + 1]; }
-        uint32_t v = s[k];
+        while (p >= next && i + 1 < nchain) { i++; next = coff[i + 1]; if (ARENA) sh = sbase[i]; }
+        uint32_t v = ARENA ? (p < total ? (uint32_t)markers[sh + p] : 0u) : s[k];
         if (v >= 256u && p < total) {
           // through the chunk's window relative to its group's, then through the group's window
           if (i % K) v = symrows[(size_t)i * GZ_WINDOW + (v & 0x7FFFu)];
@@ -692,10 +728,16 @@ cudaError_t launch_gz_count(const uint8_t* d_comp, size_t nbytes, uint32_t chunk
                                                                                  (u64)chunk_bytes * 8ull, chunks, nchunks, wvalid);
   return cudaGetLastError();
 }
+cudaError_t launch_gz_both(const uint8_t* d_comp, size_t nbytes, uint32_t chunk_bytes, GzChunk* chunks, int nchunks, uint16_t* arena,
+                           unsigned long long stride, const uint8_t* window, uint32_t wvalid, cudaStream_t st) {
+  gz_both_kernel<<<(nchunks + GZ_WARPS - 1) / GZ_WARPS, 32 * GZ_WARPS, 0, st>>>(reinterpret_cast<const uint32_t*>(d_comp), (u64)nbytes,
+                                                                                (u64)chunk_bytes * 8ull, chunks, nchunks, arena, stride, window, wvalid);
+  return cudaGetLastError();
+}
 cudaError_t launch_gz_chain(GzChunk* chunks, int nchunks, unsigned long long prior_out, GzResult* res, uint32_t* order,
-                            unsigned long long* coff, cudaStream_t st) {
+                            unsigned long long* coff, unsigned long long stride, unsigned long long* sbase, cudaStream_t st) {
   if (nchunks > GZ_MAX_CHUNKS) return cudaErrorInvalidValue;
-  gz_chain_kernel<<<1, CHAIN_THREADS, (size_t)nchunks * sizeof(int), st>>>(chunks, nchunks, prior_out, res, order, coff);
+  gz_chain_kernel<<<1, CHAIN_THREADS, (size_t)nchunks * sizeof(int), st>>>(chunks, nchunks, prior_out, res, order, coff, stride, sbase);
   return cudaGetLastError();
 }
 cudaError_t launch_gz_write(const uint8_t* d_comp, size_t nbytes, uint32_t chunk_bytes, GzChunk* chunks, int nchunks, uint16_t* markers,
@@ -708,23 +750,24 @@ uint32_t gz_group_chunks(uint32_t nchain, int sms) {
   const uint32_t k = (nchain + (uint32_t)sms - 1) / (uint32_t)sms;
   return k < 8 ? 8 : k;
 }
-cudaError_t launch_gz_windows(const unsigned long long* coff, uint32_t nchain, uint32_t K, const uint16_t* markers, uint16_t* symrows,
-                              uint16_t* grows, uint8_t* trows, uint8_t* window, cudaStream_t st) {
+cudaError_t launch_gz_windows(const unsigned long long* coff, const unsigned long long* sbase, uint32_t nchain, uint32_t K, const uint16_t* markers,
+                              uint16_t* symrows, uint16_t* grows, uint8_t* trows, uint8_t* window, cudaStream_t st) {
   if (nchain == 0 || K == 0) return cudaErrorInvalidValue;
   const uint32_t ngroups = (nchain + K - 1) / K;
   cudaError_t e = cudaMemcpyAsync(trows, window, GZ_WINDOW, cudaMemcpyDeviceToDevice, st);  // row 0: the window before the batch
   if (e != cudaSuccess) return e;
-  gz_rows_kernel<true><<<ngroups, WIN_THREADS, win_smem_bytes<uint16_t>(), st>>>(coff, nchain, K, ngroups, markers, symrows, grows, trows);
-  gz_rows_kernel<false><<<1, WIN_THREADS, win_smem_bytes<uint8_t>(), st>>>(coff, nchain, K, ngroups, markers, symrows, grows, trows);
+  gz_rows_kernel<true><<<ngroups, WIN_THREADS, win_smem_bytes<uint16_t>(), st>>>(coff, sbase, nchain, K, ngroups, markers, symrows, grows, trows);
+  gz_rows_kernel<false><<<1, WIN_THREADS, win_smem_bytes<uint8_t>(), st>>>(coff, sbase, nchain, K, ngroups, markers, symrows, grows, trows);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   return cudaMemcpyAsync(window, trows + (size_t)ngroups * GZ_WINDOW, GZ_WINDOW, cudaMemcpyDeviceToDevice, st);  // the window behind the batch
 }
-cudaError_t launch_gz_resolve(const uint16_t* markers, const uint16_t* symrows, const uint8_t* trows, uint32_t K, const unsigned long long* coff,
-                              uint32_t nchain, unsigned long long total_out, uint8_t* out, int sms, cudaStream_t st) {
+cudaError_t launch_gz_resolve(const uint16_t* markers, const unsigned long long* sbase, const uint16_t* symrows, const uint8_t* trows, uint32_t K,
+                              const unsigned long long* coff, uint32_t nchain, unsigned long long total_out, uint8_t* out, int sms, cudaStream_t st) {
   if (total_out == 0) return cudaSuccess;
   const u64 want = (total_out + RES_SLICE - 1) / RES_SLICE;
   const int grid = (int)(want < (u64)sms * 8 ? (want ? want : 1) : (u64)sms * 8);
-  gz_resolve_kernel<<<grid, RES_THREADS, 0, st>>>(markers, symrows, trows, K, coff, nchain, total_out, out);
+  if (sbase) gz_resolve_kernel<true><<<grid, RES_THREADS, 0, st>>>(markers, sbase, symrows, trows, K, coff, nchain, total_out, out);
+  else gz_resolve_kernel<false><<<grid, RES_THREADS, 0, st>>>(markers, sbase, symrows, trows, K, coff, nchain, total_out, out);
   return cudaGetLastError();
 }
 cudaError_t launch_gz_crc(const uint8_t* d_out, unsigned long long total, uint32_t* d_raw, uint32_t xs, uint32_t xq, uint32_t q, uint32_t* d_crc2,

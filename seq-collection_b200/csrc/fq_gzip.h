@@ -16,6 +16,7 @@ enum : uint32_t {
   GZC_ERROR = 4u,       // the bits are not DEFLATE as zlib accepts it
   GZC_GIVEUP = 8u,      // too many block starts passed without landing on one / output too large for one chunk
   GZC_CHAIN = 16u,      // the chunk is part of the verified chain that starts at the batch's known first block
+  GZC_REWRITE = 32u,    // (one-pass mode) the chunk's symbols did not fit its slot of the arena: the batch needs the second pass
 };
 
 // One chunk of the compressed batch: the first DEFLATE block header found at or after the chunk's first bit, and
@@ -38,6 +39,8 @@ struct GzResult {
   unsigned long long end_bit;    // the bit after the last complete block
   uint32_t final_block;          // the stream's last block is inside the batch
   uint32_t passed;               // starts found by the search that were not block boundaries
+  uint32_t rewrite;              // (one-pass mode) some chunk of the chain could not keep its symbols: second pass needed
+  uint32_t pad;
 };
 
 // Once per device, before the first launch.
@@ -50,17 +53,22 @@ cudaError_t launch_gz_sync(const uint8_t* d_comp, size_t nbytes, uint32_t chunk_
                            GzChunk* chunks, uint32_t* nfound, cudaStream_t st);
 cudaError_t launch_gz_count(const uint8_t* d_comp, size_t nbytes, uint32_t chunk_bytes, GzChunk* chunks, int nchunks, uint32_t wvalid,
                             cudaStream_t st);
+// One-pass mode: count and write at once, chunk c's symbols to arena + c * stride (stride = symbols per chunk slot).
+cudaError_t launch_gz_both(const uint8_t* d_comp, size_t nbytes, uint32_t chunk_bytes, GzChunk* chunks, int nchunks, uint16_t* arena,
+                           unsigned long long stride, const uint8_t* window, uint32_t wvalid, cudaStream_t st);
+// stride != 0 (one-pass mode): sbase[i] = where chain chunk i's symbols are in the arena, minus its output offset
 cudaError_t launch_gz_chain(GzChunk* chunks, int nchunks, unsigned long long prior_out, GzResult* res, uint32_t* order,
-                            unsigned long long* coff, cudaStream_t st);
+                            unsigned long long* coff, unsigned long long stride, unsigned long long* sbase, cudaStream_t st);
 cudaError_t launch_gz_write(const uint8_t* d_comp, size_t nbytes, uint32_t chunk_bytes, GzChunk* chunks, int nchunks, uint16_t* markers,
                             const uint8_t* window, uint32_t wvalid, uint32_t* err, cudaStream_t st);
 // The windows: K = gz_group_chunks(nchain, SMs) chunks per group, ngroups = ceil(nchain / K).
 // symrows: (nchain + 1) rows of 32768 symbols; grows: ngroups rows of 32768 symbols; trows: (ngroups + 1) rows of 32 KiB.
 uint32_t gz_group_chunks(uint32_t nchain, int sms);
-cudaError_t launch_gz_windows(const unsigned long long* coff, uint32_t nchain, uint32_t K, const uint16_t* markers, uint16_t* symrows,
-                              uint16_t* grows, uint8_t* trows, uint8_t* window, cudaStream_t st);
-cudaError_t launch_gz_resolve(const uint16_t* markers, const uint16_t* symrows, const uint8_t* trows, uint32_t K, const unsigned long long* coff,
-                              uint32_t nchain, unsigned long long total_out, uint8_t* out, int sms, cudaStream_t st);
+// sbase: nullptr = the symbols of output position p are at markers[p] (second pass); else at markers[sbase[i] + p] (arena)
+cudaError_t launch_gz_windows(const unsigned long long* coff, const unsigned long long* sbase, uint32_t nchain, uint32_t K, const uint16_t* markers,
+                              uint16_t* symrows, uint16_t* grows, uint8_t* trows, uint8_t* window, cudaStream_t st);
+cudaError_t launch_gz_resolve(const uint16_t* markers, const unsigned long long* sbase, const uint16_t* symrows, const uint8_t* trows, uint32_t K,
+                              const unsigned long long* coff, uint32_t nchain, unsigned long long total_out, uint8_t* out, int sms, cudaStream_t st);
 
 // CRC-32 pieces of the batch's output: d_crc2[0] = the register (from zero) over the full 4 KiB slices, d_crc2[1] = over
 // the bytes behind them.  d_raw: total / 4096 + 1 words; xs = x^(8 * 4096), xq = x^(8 * 4096 * q) modulo the CRC

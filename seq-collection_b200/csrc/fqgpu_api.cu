@@ -80,6 +80,7 @@ void fqgpu_destroy(fqgpu_ctx* ctx) {
   cudaFree(ctx->d_gzchunks);
   cudaFree(ctx->d_gzorder);
   cudaFree(ctx->d_gzcoff);
+  cudaFree(ctx->d_gzsb);
   cudaFree(ctx->d_gzres);
   if (ctx->h_gzres) cudaFreeHost(ctx->h_gzres);
   cudaFree(ctx->d_gzsym);
@@ -155,6 +156,7 @@ int fqgpu_reset(fqgpu_ctx* ctx) {
   ctx->bgzf_members = 0;
   ctx->gzip_chunks = 0;
   ctx->gzip_passed = 0;
+  ctx->gzip_rewrites = 0;
   ctx->shard_rank = 0;
   ctx->shard_world = 1;
   ctx->shard_exact = false;
@@ -720,6 +722,7 @@ static int count_gzip(fqgpu_ctx* ctx, const char* path) {
     CU_B(cudaMalloc(&ctx->d_gzchunks, (size_t)fq::GZ_MAX_CHUNKS * sizeof(fq::GzChunk)));
     CU_B(cudaMalloc(&ctx->d_gzorder, (size_t)fq::GZ_MAX_CHUNKS * sizeof(uint32_t)));
     CU_B(cudaMalloc(&ctx->d_gzcoff, ((size_t)fq::GZ_MAX_CHUNKS + 1) * sizeof(u64)));
+    CU_B(cudaMalloc(&ctx->d_gzsb, ((size_t)fq::GZ_MAX_CHUNKS + 1) * sizeof(u64)));
     CU_B(cudaMalloc(&ctx->d_gzres, sizeof(fq::GzResult) + 16));
     CU_B(cudaMallocHost(&ctx->h_gzres, sizeof(fq::GzResult) + 16));
     CU_B(cudaMalloc(&ctx->d_gzwindow, fq::GZ_WINDOW));
@@ -730,6 +733,8 @@ static int count_gzip(fqgpu_ctx* ctx, const char* path) {
   const fq::GzResult* h_res = (const fq::GzResult*)ctx->h_gzres;
   const uint32_t* h_err = (const uint32_t*)((const uint8_t*)ctx->h_gzres + sizeof(fq::GzResult));
   const size_t chunk_min = env_size("FQGPU_GZ_CHUNK_KB", 16, 1, 1024) << 10;
+  const bool two_pass = getenv("FQGPU_GZ_TWO_PASS") != nullptr;
+  const size_t kArenaRatio = env_size("FQGPU_GZ_ARENA_RATIO", 8, 2, 64);
 
   const bool trace = getenv("FQGPU_GZ_TRACE") != nullptr;  // per-stage wall clock (adds stream syncs; diagnostics only)
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -797,8 +802,26 @@ static int count_gzip(fqgpu_ctx* ctx, const char* path) {
     // would decode nearly everything alone -- zlib on the host is faster than that
     if (nchunks >= 64 && (size_t)h_err[1] * 64 < (size_t)nchunks) return bail(1);
     mark("sync");
-    CU_B(fq::launch_gz_count(d_comp, got, (uint32_t)chunk_bytes, chunks, nchunks, wvalid, ctx->stream));
-    CU_B(fq::launch_gz_chain(chunks, nchunks, prior_out, d_res, ctx->d_gzorder, ctx->d_gzcoff, ctx->stream));
+    // One decode pass where the symbols can be kept where they fall: chunk c writes to its own slot of an arena with room
+    // for `kArenaRatio` output bytes per compressed byte (FASTQ is near 4.4; the arena is 2 * kArenaRatio times the
+    // batch).  A stretch that compresses better than that, a false start run over, or an arena that cannot be had
+    // sends the batch through the second pass (gz_write_kernel) as before; FQGPU_GZ_TWO_PASS=1 forces that.
+    const u64 stride = (u64)kArenaRatio * chunk_bytes;  // symbols per chunk slot
+    bool one_pass = !two_pass;
+    if (one_pass && ctx->gzsym_cap < (size_t)nchunks * stride + 16) {
+      cudaFree(ctx->d_gzsym);
+      ctx->d_gzsym = nullptr; ctx->gzsym_cap = 0;
+      const size_t cap = (size_t)nchunks * stride + 4096;
+      if (cudaMalloc(&ctx->d_gzsym, cap * sizeof(uint16_t)) == cudaSuccess) ctx->gzsym_cap = cap;
+      else { cudaGetLastError(); ctx->d_gzsym = nullptr; one_pass = false; }
+    }
+    if (one_pass) {
+      CU_B(fq::launch_gz_both(d_comp, got, (uint32_t)chunk_bytes, chunks, nchunks, ctx->d_gzsym, stride, ctx->d_gzwindow, wvalid, ctx->stream));
+      CU_B(cudaEventRecord(slot.done, ctx->stream));  // (the last kernel that reads the slot, unless the second pass is needed)
+    } else {
+      CU_B(fq::launch_gz_count(d_comp, got, (uint32_t)chunk_bytes, chunks, nchunks, wvalid, ctx->stream));
+    }
+    CU_B(fq::launch_gz_chain(chunks, nchunks, prior_out, d_res, ctx->d_gzorder, ctx->d_gzcoff, one_pass ? stride : 0ull, ctx->d_gzsb, ctx->stream));
     CU_B(cudaMemcpyAsync(ctx->h_gzres, ctx->d_gzres, sizeof(fq::GzResult), cudaMemcpyDeviceToHost, ctx->stream));
     // while the device counts: the next batch's bytes
     size_t next_fpos = 0, next_got = 0;
@@ -817,8 +840,10 @@ static int count_gzip(fqgpu_ctx* ctx, const char* path) {
     if (res.status != fq::GZR_OK) return bail(1);
     if (res.total_out == 0 && !res.final_block) return bail(1);  // no complete block in a whole batch, or a truncated file
     const u64 total = res.total_out;
+    const bool arena = one_pass && !res.rewrite;  // the symbols are where the one pass put them
+    if (one_pass && res.rewrite) ctx->gzip_rewrites++;
     if (total) {
-      if (ctx->gzsym_cap < total + 16) {
+      if (!arena && ctx->gzsym_cap < total + 16) {
         cudaFree(ctx->d_gzsym);
         ctx->d_gzsym = nullptr; ctx->gzsym_cap = 0;
         const size_t cap = (size_t)total + ((size_t)total >> 3) + 4096;
@@ -847,11 +872,14 @@ static int count_gzip(fqgpu_ctx* ctx, const char* path) {
       uint8_t* trows = (uint8_t*)(grows + (ctx->gzwbuf_cap / 8 + 2) * fq::GZ_WINDOW);
       (void)ngroups;
       mark("alloc");
-      CU_B(fq::launch_gz_write(d_comp, got, (uint32_t)chunk_bytes, chunks, nchunks, ctx->d_gzsym, ctx->d_gzwindow, wvalid, d_err, ctx->stream));
-      CU_B(cudaEventRecord(slot.done, ctx->stream));  // (the last kernel that reads the slot)
+      if (!arena) {
+        CU_B(fq::launch_gz_write(d_comp, got, (uint32_t)chunk_bytes, chunks, nchunks, ctx->d_gzsym, ctx->d_gzwindow, wvalid, d_err, ctx->stream));
+        CU_B(cudaEventRecord(slot.done, ctx->stream));  // (the last kernel that reads the slot)
+      }
       mark("write");
-      CU_B(fq::launch_gz_windows(ctx->d_gzcoff, res.nchain, K, ctx->d_gzsym, symrows, grows, trows, ctx->d_gzwindow, ctx->stream));
-      CU_B(fq::launch_gz_resolve(ctx->d_gzsym, symrows, trows, K, ctx->d_gzcoff, res.nchain, total, ctx->d_inflated, ctx->grid / 2, ctx->stream));
+      const u64* sbase = arena ? ctx->d_gzsb : nullptr;
+      CU_B(fq::launch_gz_windows(ctx->d_gzcoff, sbase, res.nchain, K, ctx->d_gzsym, symrows, grows, trows, ctx->d_gzwindow, ctx->stream));
+      CU_B(fq::launch_gz_resolve(ctx->d_gzsym, sbase, symrows, trows, K, ctx->d_gzcoff, res.nchain, total, ctx->d_inflated, ctx->grid / 2, ctx->stream));
       mark("windows");
       const u64 nslices = total / fq::GZ_CRC_SLICE;
       const uint32_t q = (uint32_t)((nslices + 1023) / 1024);
@@ -925,6 +953,7 @@ extern "C" {
 unsigned long long fqgpu_bgzf_members(const fqgpu_ctx* ctx) { return ctx ? ctx->bgzf_members : 0; }
 unsigned long long fqgpu_gzip_chunks(const fqgpu_ctx* ctx) { return ctx ? ctx->gzip_chunks : 0; }
 unsigned long long fqgpu_gzip_false_starts(const fqgpu_ctx* ctx) { return ctx ? ctx->gzip_passed : 0; }
+unsigned long long fqgpu_gzip_second_passes(const fqgpu_ctx* ctx) { return ctx ? ctx->gzip_rewrites : 0; }
 
 int fqgpu_count_file_as(fqgpu_ctx* ctx, const char* path, int as_gz, fqgpu_stats* out) {
   NvtxRange nvtx_("fqgpu_count_file_as");

@@ -108,6 +108,7 @@ struct fqgpu_ctx {
   void* d_gzchunks = nullptr;
   uint32_t* d_gzorder = nullptr;
   u64* d_gzcoff = nullptr;
+  u64* d_gzsb = nullptr;       // one-pass mode: where each chain chunk's symbols are in the arena
   void* d_gzres = nullptr;     // GzResult + the write pass's error word
   void* h_gzres = nullptr;     // pinned copy
   uint16_t* d_gzsym = nullptr;
@@ -118,6 +119,7 @@ struct fqgpu_ctx {
   size_t gzraw_cap = 0;
   uint8_t* d_gzwindow = nullptr;
   u64 gzip_chunks = 0;         // chunks of single-member gzip inflated on the device since the last reset (diagnostics)
+  u64 gzip_rewrites = 0;       // batches that needed the second decode pass after all
   u64 gzip_passed = 0;         // block starts the search found that turned out not to be block boundaries
 };
 

@@ -53,6 +53,7 @@ proc fqgpu_count_files*(cfg: ptr FqgpuConfig, paths: cstringArray, as_gz: ptr ci
 proc fqgpu_bgzf_members*(ctx: FqgpuCtx): culonglong
 proc fqgpu_gzip_chunks*(ctx: FqgpuCtx): culonglong        # > 0: an ordinary .gz was inflated on the device
 proc fqgpu_gzip_false_starts*(ctx: FqgpuCtx): culonglong
+proc fqgpu_gzip_second_passes*(ctx: FqgpuCtx): culonglong
 proc fqgpu_meta_file_as*(ctx: FqgpuCtx, path: cstring, as_gz: cint, stats: ptr FqgpuStats): cint
 proc fqgpu_count_file_sharded*(cfg: ptr FqgpuConfig, path: cstring, devices: ptr cint, world: cint, stats: ptr FqgpuStats): cint
 proc fqgpu_count_pair*(cfg: ptr FqgpuConfig, r1, r2: cstring, stats1, stats2: ptr FqgpuStats, paired: ptr cint): cint

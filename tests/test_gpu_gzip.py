@@ -176,6 +176,35 @@ def test_broken_gzip_behaves_like_the_zlib_path(ctx, tmp_path, monkeypatch):
             assert dev[1] == host[1], name
 
 
+def test_gzip_one_pass_arena_and_second_pass(ctx, tmp_path, monkeypatch):
+    """By default a batch is decoded once, every chunk's symbols into its own slot of an arena sized for 8 output bytes
+    per compressed byte; what does not fit there (data that compresses better, here also an arena made too small on
+    purpose) is decoded a second time into exact places, and FQGPU_GZ_TWO_PASS=1 always does that.  Same result."""
+    monkeypatch.setenv("FQGPU_GZ_CHUNK_KB", "4")
+    data = _bulk(6_000_000, first=4242)
+    want = O.count(data, 100)
+    path = _write(tmp_path, "plain.fq.gz", gz_bytes(data, 6))
+    st = ctx.count_file(path)
+    assert ctx.gzip_chunks() > 10 and ctx.gzip_second_passes() == 0
+    assert_equal_stats(st.to_dict(), want, "one pass")
+    monkeypatch.setenv("FQGPU_GZ_ARENA_RATIO", "2")  # FASTQ compresses about 4.4 : 1
+    st = ctx.count_file(path)
+    assert ctx.gzip_chunks() > 10 and ctx.gzip_second_passes() >= 1
+    assert_equal_stats(st.to_dict(), want, "arena too small: second pass")
+    monkeypatch.delenv("FQGPU_GZ_ARENA_RATIO")
+    monkeypatch.setenv("FQGPU_GZ_TWO_PASS", "1")
+    st = ctx.count_file(path)
+    assert ctx.gzip_chunks() > 10 and ctx.gzip_second_passes() == 0
+    assert_equal_stats(st.to_dict(), want, "two passes")
+    monkeypatch.delenv("FQGPU_GZ_TWO_PASS")
+    unit = corpus.rec(b"@r", b"ACGTNACGTTGCA" * 7, b"I!5#~" * 18 + b"J")
+    rep = unit * 60000  # compresses far better than 8 : 1
+    path = _write(tmp_path, "rep.fq.gz", gz_bytes(rep, 6))
+    st = ctx.count_file(path)
+    assert ctx.gzip_second_passes() >= 1
+    assert_equal_stats(st.to_dict(), O.count(rep, 100), "repetitive: second pass")
+
+
 def test_gzip_default_chunking_large_file(ctx, tmp_path):
     """Default chunk and batch sizes on a file large enough for thousands of chunks; no false starts expected to
     break the chain (they are counted, and skipped)."""
