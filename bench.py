@@ -292,7 +292,7 @@ def gz_leg(fq, ctx, n_records: int):
                                       "n_lines": st_all.meta_lines // 4,
                                       "note": "the same with -n <all reads>: the quality-range fold over every record (segments folded in parallel, csrc/fq_meta.cu), best of 2"},
                 "note": "single-member gzip (level 6), inflated on the device: block starts guessed per chunk and proven by the chunk before "
-                        "landing on them, back-references across chunks carried as markers and resolved through a chain of 32 KiB windows, "
+                        "landing on them, one decode pass, back-references across chunks carried as markers and resolved through a chain of 32 KiB windows, "
                         "CRC-32 + ISIZE of the member verified; fq-meta sample -n 100 (the reference's default); wall clock from open() to "
                         f"the finished statistics, best of 3 (the file was written in {t_comp:.1f} s)"}
     finally:

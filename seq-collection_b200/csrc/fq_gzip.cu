@@ -13,16 +13,18 @@
 //                       end-of-block symbol, a usable distance code).  32 lanes test 32 positions at once on the
 //                       17 fixed bits and the Kraft sum of the code-length code; the few survivors are parsed by
 //                       the whole warp.
-//   2. gz_count_kernel  every chunk that found a start decodes from it WITHOUT writing, until a block ends exactly
-//                       on the next chunk's start: that proves the next start (a start the decode runs over in
-//                       mid-block was a false positive and is skipped).  The chunk records where it came to rest,
-//                       how many bytes it produced and how far back its matches reached.
+//   2. gz_both_kernel   every chunk that found a start decodes from it until a block ends exactly on the next
+//                       chunk's start: that proves the next start (a start the decode runs over in mid-block was a
+//                       false positive and is skipped).  The chunk records where it came to rest, how many bytes it
+//                       produced and how far back its matches reached -- and writes its output, as 16-bit symbols, to
+//                       its own slot of an over-sized arena: a byte, or -- for a match that reaches behind the
+//                       chunk's first byte -- a MARKER holding the position in the 32 KiB window before the chunk.
+//                       Matches copy symbols, so markers propagate.
 //   3. gz_chain_kernel  follows the landings from the batch's first block (whose position IS known: the end of
 //                       the gzip header, or where the batch before stopped), gives the chunks on that chain
 //                       their output offsets, and checks every look-back against the bytes that exist.
-//   4. gz_write_kernel  the chain's chunks decode again, now writing 16-bit symbols: a byte, or -- for a match
-//                       that reaches behind the chunk's first byte -- a MARKER holding the position in the
-//                       32 KiB window before the chunk.  Matches copy symbols, so markers propagate.
+//   4. (gz_count_kernel + gz_write_kernel: the same in two passes -- count first, then write into exact places --
+//                       for a batch whose symbols did not fit the arena, or when no arena can be had.)
 //   5. gz_rows_kernel   "the 32 KiB before chunk i+1" from "the 32 KiB before chunk i" is a serial recurrence; windows of
 //                       symbols compose, so groups of chunks are walked in parallel relative to their own first
 //                       window and only the groups are walked in series (shared memory, fed by TMA).
